@@ -1,0 +1,122 @@
+"""Strategy file -> problem descriptor + warm start (the data ``setup_single_final_problem`` consumes).
+
+Reference data flow: ``Vehicle.__init__`` (confrez/control/vehicle.py:46-52) reads initial pose, obstacles
+and tube sets; ``main`` of each planner supplies ``init_offsets`` / ``final_headings``
+(multi_vehicle_planner.py:636-649).
+"""
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from conflict_rez_b200.control.compute_sets import (
+    compute_initial_states,
+    compute_obstacles,
+    compute_sets,
+    interp_along_sets,
+)
+from conflict_rez_b200.control import warmstart
+from conflict_rez_b200.problem import CollocationGuess, CollocationProblem
+from conflict_rez_b200.vehicle_types import VehicleBody, VehicleConfig
+from conflict_rez_b200.obstacle_types import GeofenceRegion
+
+DEFAULT_FINAL_HEADINGS = {"vehicle_0": 0.0, "vehicle_1": 3 * np.pi / 2, "vehicle_2": np.pi, "vehicle_3": np.pi / 2}
+
+
+def build_problem(
+    rl_file_name: str,
+    agents: Sequence[str],
+    init_offsets: Optional[np.ndarray] = None,
+    final_headings: Optional[Dict[str, float]] = None,
+    K: int = 5,
+    n_per_set: int = 5,
+    shrink_tube: float = 0.5,
+    dmin: float = 0.05,
+    vehicle_body: Optional[VehicleBody] = None,
+    vehicle_config: Optional[VehicleConfig] = None,
+    region: Optional[GeofenceRegion] = None,
+    obstacles: Optional[List] = None,
+    rl_tubes: Optional[Dict] = None,
+) -> CollocationProblem:
+    """``init_offsets``: ([B,] V, 3) offsets on (x, y, psi) added to the strategy's initial poses."""
+    vb = vehicle_body or VehicleBody()
+    vc = vehicle_config or VehicleConfig()
+    rg = region or GeofenceRegion()
+    obstacles = compute_obstacles(vb=vb) if obstacles is None else obstacles
+    tubes = compute_sets(rl_file_name) if rl_tubes is None else rl_tubes
+    init = compute_initial_states(rl_file_name, vb)
+    V = len(agents)
+    n_sets = np.array([len(tubes[a]) for a in agents])
+    Smax = int(n_sets.max())
+    tube_A = np.zeros((V, Smax, 2, 4, 2))
+    tube_b = np.zeros((V, Smax, 2, 4))
+    for ia, a in enumerate(agents):
+        for q, sets in enumerate(tubes[a]):
+            for ib, body in enumerate(("back", "front")):
+                tube_A[ia, q, ib] = sets[body].A
+                tube_b[ia, q, ib] = np.ravel(sets[body].b)
+    base = np.array([[init[a].x.x, init[a].x.y, init[a].e.psi] for a in agents])
+    init_pose = base if init_offsets is None else base + np.asarray(init_offsets, dtype=float)
+    fh = DEFAULT_FINAL_HEADINGS if final_headings is None else final_headings
+    heading = np.array([np.nan if fh.get(a) is None else float(fh[a]) for a in agents])
+    return CollocationProblem(
+        n_sets=n_sets,
+        obs_A=np.stack([o.A for o in obstacles]),
+        obs_b=np.stack([np.ravel(o.b) for o in obstacles]),
+        tube_A=tube_A,
+        tube_b=tube_b,
+        init_pose=init_pose,
+        final_heading=heading,
+        body_G=np.asarray(vb.A, dtype=float),
+        body_g=np.asarray(vb.b, dtype=float),
+        wb=vb.wb,
+        region=np.array([rg.x_min, rg.x_max, rg.y_min, rg.y_max]),
+        limits=np.array([vc.v_min, vc.v_max, vc.delta_min, vc.delta_max, vc.a_min, vc.a_max, vc.w_delta_min, vc.w_delta_max], dtype=float),
+        K=K,
+        n_per_set=n_per_set,
+        dmin=dmin,
+        shrink_tube=shrink_tube,
+    )
+
+
+def build_guess(prob: CollocationProblem, rl_file_name: str, agents: Sequence[str], N_ws: int = 30, dt_ws: float = 0.1) -> CollocationGuess:
+    """Spline pose guess -> kinematic state guess -> closed-form duals -> Radau resampling (batched over init poses).
+
+    The pose guess is shifted rigidly at t=0 towards each instance's perturbed initial pose and blended out over the
+    first set move, so that every instance starts from a guess consistent with its own initial condition.
+    """
+    vb = VehicleBody()
+    paths = interp_along_sets(rl_file_name, vb, N_ws)
+    batched = prob.batch is not None
+    init = prob.init_pose if batched else prob.init_pose[None]
+    B, V, O = init.shape[0], prob.V, prob.O
+    Mmax = int(prob.nodes.max())
+    z = np.zeros((B, V, Mmax, 7))
+    lam = np.zeros((B, V, Mmax, O, 4))
+    mu = np.zeros((B, V, Mmax, O, 4))
+    dts = np.zeros((B, V))
+    for ia, a in enumerate(agents):
+        path0 = paths[a]
+        N, M = int(prob.N[ia]), int(prob.nodes[ia])
+        blend = np.clip(1.0 - np.arange(len(path0)) / float(N_ws), 0.0, 1.0)[:, None]
+        for b in range(B):
+            path = path0 + blend * (init[b, ia] - path0[0])[None, :]
+            kin = warmstart.kinematic_guess(path, dt_ws, prob.wb, prob.limits)
+            sig = {k: kin[k] for k in ("x", "y", "psi", "v", "delta", "a", "w")}
+            t_i, res = warmstart.interp_ws_for_collocation(kin["t"], sig, N, prob.K)
+            zz = np.stack([res[k] for k in ("x", "y", "psi", "v", "delta", "a", "w")], axis=1)
+            z[b, ia, :M] = zz
+            l_, m_ = warmstart.dual_ws_rect(zz[:, 0], zz[:, 1], zz[:, 2], prob.obs_A, prob.obs_b, prob.body_G, prob.body_g)
+            lam[b, ia, :M], mu[b, ia, :M] = l_, m_
+            dts[b, ia] = kin["t"][-1] / N
+    P = len(prob.pairs)
+    pl = np.zeros((B, P, Mmax, 4))
+    pm = np.zeros((B, P, Mmax, 4))
+    ps = np.zeros((B, P, Mmax, 2))
+    for q, (a, b_) in enumerate(prob.pairs):
+        m = int(min(prob.nodes[a], prob.nodes[b_]))
+        za, zb = z[:, a, :m], z[:, b_, :m]
+        l_, m_, s_ = warmstart.joint_dual_ws_rect(za[..., 0], za[..., 1], za[..., 2], zb[..., 0], zb[..., 1], zb[..., 2], prob.body_G, prob.body_g)
+        pl[:, q, :m], pm[:, q, :m], ps[:, q, :m] = l_, m_, s_
+    dt0 = dts.mean(axis=1)  # multi_vehicle_planner.py:360
+    g = CollocationGuess(z, lam, mu, dt0, pl, pm, ps)
+    return g if batched else g.instance(0)
