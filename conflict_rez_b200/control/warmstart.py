@@ -34,8 +34,7 @@ def _point_segment(p, a, b):
 def closest_points_convex(P, Q):
     """Closest points between two non-overlapping convex quadrilaterals given as vertex loops (...,4,2).
 
-    Returns (p on P, q on Q, distance).  For overlapping shapes the distance is ~0 and the direction is the
-    centroid direction (good enough for a warm start).
+    Returns (p on P, q on Q, distance); overlapping shapes are handled by ``_sat_direction``.
     """
     best_d = np.full(P.shape[:-2], np.inf)
     best_p = np.zeros(P.shape[:-2] + (2,))
@@ -66,11 +65,30 @@ def _body_vertices(x, y, psi, G, g):
     return np.einsum("...ij,kj->...ki", R, Vb) + np.stack([x, y], -1)[..., None, :]
 
 
-def _unit(p, q, fallback):
+def _unit(p, q, sat):
+    """Unit vector q -> p for separated shapes, the least-penetration axis for overlapping ones."""
+    sat_dir, sat_sep = sat
     w = p - q
     n = np.linalg.norm(w, axis=-1, keepdims=True)
-    fb = fallback / np.maximum(np.linalg.norm(fallback, axis=-1, keepdims=True), 1e-12)
-    return np.where(n > 1e-9, w / np.maximum(n, 1e-300), fb)
+    use_sat = (sat_sep[..., None] <= 1e-9) | (n <= 1e-9)
+    return np.where(use_sat, sat_dir, w / np.maximum(n, 1e-300))
+
+
+def _sat_direction(P, NP_, Q, NQ):
+    """Least-penetration axis between overlapping convex quads: unit vector pointing from Q towards P.
+
+    P, Q: vertex loops (...,4,2); NP_, NQ: outward unit face normals (...,4,2).  Candidate axes are the face
+    normals of both shapes; the axis with the largest (least negative) separation is returned.
+    """
+    # faces of Q: separation = min_v nQ.(v_P) - max_u nQ.(u_Q)
+    sepQ = np.einsum("...fc,...vc->...fv", NQ, P).min(-1) - np.einsum("...fc,...vc->...fv", NQ, Q).max(-1)
+    sepP = np.einsum("...fc,...vc->...fv", NP_, Q).min(-1) - np.einsum("...fc,...vc->...fv", NP_, P).max(-1)
+    iq, ip = sepQ.argmax(-1), sepP.argmax(-1)
+    bestQ = np.take_along_axis(sepQ, iq[..., None], -1)[..., 0]
+    bestP = np.take_along_axis(sepP, ip[..., None], -1)[..., 0]
+    dq = np.take_along_axis(NQ, iq[..., None, None].repeat(2, -1), -2)[..., 0, :]
+    dp = -np.take_along_axis(NP_, ip[..., None, None].repeat(2, -1), -2)[..., 0, :]
+    return np.where((bestQ >= bestP)[..., None], dq, dp), np.maximum(bestQ, bestP)
 
 
 def dual_ws_rect(x, y, psi, obs_A, obs_b, G, g):
@@ -83,7 +101,9 @@ def dual_ws_rect(x, y, psi, obs_A, obs_b, G, g):
     for j in range(O):
         Vo = np.broadcast_to(_rect_vertices(obs_A[j], obs_b[j]), body.shape)
         pb, po, _ = closest_points_convex(body, Vo)
-        w = _unit(pb, po, body.mean(-2) - Vo.mean(-2))  # from obstacle towards body
+        Rm = np.stack([np.stack([c, -s], -1), np.stack([s, c], -1)], -2)
+        nbody = np.einsum("...ij,kj->...ki", Rm, G)
+        w = _unit(pb, po, _sat_direction(body, nbody, Vo, np.broadcast_to(obs_A[j], body.shape)))  # from obstacle towards body
         lam[..., j, :] = np.maximum(0.0, w @ obs_A[j].T)
         wb_ = np.stack([c * w[..., 0] + s * w[..., 1], -s * w[..., 0] + c * w[..., 1]], -1)  # R' w
         mu[..., j, :] = np.maximum(0.0, -(wb_ @ G.T))
@@ -95,7 +115,13 @@ def joint_dual_ws_rect(xa, ya, pa, xb, yb, pb, G, g):
     Ba = _body_vertices(xa, ya, pa, G, g)
     Bb = _body_vertices(xb, yb, pb, G, g)
     p, q, _ = closest_points_convex(Ba, Bb)
-    s = _unit(p, q, Ba.mean(-2) - Bb.mean(-2))  # from b towards a
+
+    def normals(psi):
+        c, sn = np.cos(psi), np.sin(psi)
+        Rm = np.stack([np.stack([c, -sn], -1), np.stack([sn, c], -1)], -2)
+        return np.einsum("...ij,kj->...ki", Rm, G)
+
+    s = _unit(p, q, _sat_direction(Ba, normals(pa), Bb, normals(pb)))  # from b towards a
 
     def to_body(psi, w):
         c, sn = np.cos(psi), np.sin(psi)

@@ -1,0 +1,611 @@
+// obca_api.cu -- C ABI (include/obca.h) around the per-instance solver of obca_core.h.
+//
+// Built by nvcc for sm_100a into libobca_b200.so (the product).  The same file compiles with
+// g++ -DOBCA_HOST_EMU into the developer-only single-thread emulation (tools/host_emu), where a
+// "device pointer" is a host pointer and a "kernel" is a loop over the instances.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "obca_core.h"
+
+using namespace obca;
+
+#ifndef OBCA_HOST_EMU
+#include <cuda_runtime.h>
+#define CTA_THREADS 256
+#endif
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+
+struct ObcaHandle {
+  ObcaDims dims;
+  Opts opts;
+  double dmin, shrink;
+  Lay L;
+  Stat S;
+  Counts cnt;
+  int device;
+  int slots;
+  bool have_static;
+  size_t it_stride, wk_stride, rw_stride;
+  // device memory
+  Lay* d_L;
+  Stat* d_S;
+  double* d_tube;
+  double *d_xL, *d_xU;
+  double* d_iter;  // [B][it_stride]
+  double* d_work;  // [slots][wk_stride]
+  double* d_rw;    // [slots][rw_stride]
+  Result* d_res;   // [B]
+  int* d_counter;
+  int64_t launches;
+};
+
+// ------------------------------------------------------------------------------------------------
+// memory helpers
+// ------------------------------------------------------------------------------------------------
+#ifdef OBCA_HOST_EMU
+static int dev_alloc(void** p, size_t bytes) {
+  *p = calloc(bytes ? bytes : 1, 1);
+  return *p ? 0 : -1;
+}
+static void dev_free(void* p) { free(p); }
+static int h2d(void* d, const void* h, size_t n) {
+  memcpy(d, h, n);
+  return 0;
+}
+static int d2h(void* h, const void* d, size_t n) {
+  memcpy(h, d, n);
+  return 0;
+}
+static int dev_sync() { return 0; }
+#else
+#define CUDA_OK(call)                                                             \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+static int dev_alloc(void** p, size_t bytes) {
+  if (cudaMalloc(p, bytes ? bytes : 1) != cudaSuccess) return -1;
+  return cudaMemset(*p, 0, bytes ? bytes : 1) == cudaSuccess ? 0 : -1;
+}
+static void dev_free(void* p) { cudaFree(p); }
+static int h2d(void* d, const void* h, size_t n) { return cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1; }
+static int d2h(void* h, const void* d, size_t n) { return cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1; }
+static int dev_sync() { return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1; }
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// kernels (device) / loops (emulation)
+// ------------------------------------------------------------------------------------------------
+struct PackArgs {
+  const double *z, *lam, *mu, *dt, *pl, *pm, *ps;
+  double *oz, *olam, *omu, *odt, *opl, *opm, *ops;
+};
+
+// node-major user arrays <-> field-major internal x.  One "thread" per (instance, element).
+OBCA_HDN void pack_one(const Lay& L, double* iter, size_t it_stride, const PackArgs& A, int b, int e, bool unpack) {
+  Scratch W;
+  carve_iterate(W, L, iter + (size_t)b * it_stride);
+  const int Mv = L.Mv, O = L.O;
+  int nz = L.V * Mv * NZ, nl = L.V * Mv * O * 4, npl = L.P * Mv * 4, nps = L.P * Mv * 2;
+  if (e < nz) {
+    int a = e / (Mv * NZ), n = (e / NZ) % Mv, c = e % NZ;
+    size_t src = (size_t)b * nz + e;
+    if (unpack) {
+      if (A.oz) A.oz[src] = n < L.M[a] ? W.x[L.Z(a, c, n)] : 0.0;
+    } else
+      W.x[L.Z(a, c, n)] = n < L.M[a] ? A.z[src] : 0.0;
+    return;
+  }
+  e -= nz;
+  if (e < nl) {
+    int a = e / (Mv * O * 4), n = (e / (O * 4)) % Mv, j = (e / 4) % O, r = e % 4;
+    size_t src = (size_t)b * nl + e;
+    if (unpack) {
+      if (A.olam) A.olam[src] = n < L.M[a] ? W.x[L.LAM(a, j, r, n)] : 0.0;
+      if (A.omu) A.omu[src] = n < L.M[a] ? W.x[L.MU(a, j, r, n)] : 0.0;
+    } else {
+      W.x[L.LAM(a, j, r, n)] = n < L.M[a] ? A.lam[src] : 0.0;
+      W.x[L.MU(a, j, r, n)] = n < L.M[a] ? A.mu[src] : 0.0;
+    }
+    return;
+  }
+  e -= nl;
+  if (e < npl) {
+    int p = e / (Mv * 4), n = (e / 4) % Mv, r = e % 4;
+    size_t src = (size_t)b * npl + e;
+    if (unpack) {
+      if (A.opl) A.opl[src] = n < L.Mp[p] ? W.x[L.PL(p, r, n)] : 0.0;
+      if (A.opm) A.opm[src] = n < L.Mp[p] ? W.x[L.PM(p, r, n)] : 0.0;
+    } else {
+      W.x[L.PL(p, r, n)] = (A.pl && n < L.Mp[p]) ? A.pl[src] : 0.0;
+      W.x[L.PM(p, r, n)] = (A.pm && n < L.Mp[p]) ? A.pm[src] : 0.0;
+    }
+    return;
+  }
+  e -= npl;
+  if (e < nps) {
+    int p = e / (Mv * 2), n = (e / 2) % Mv, r = e % 2;
+    size_t src = (size_t)b * nps + e;
+    if (unpack) {
+      if (A.ops) A.ops[src] = n < L.Mp[p] ? W.x[L.PS(p, r, n)] : 0.0;
+    } else
+      W.x[L.PS(p, r, n)] = (A.ps && n < L.Mp[p]) ? A.ps[src] : 0.0;
+    return;
+  }
+  e -= nps;
+  if (e == 0) {
+    if (unpack) {
+      if (A.odt) A.odt[b] = W.x[L.oDT];
+    } else
+      W.x[L.oDT] = A.dt[b];
+  }
+}
+static inline int pack_elems(const Lay& L) { return L.V * L.Mv * NZ + L.V * L.Mv * L.O * 4 + L.P * L.Mv * 4 + L.P * L.Mv * 2 + 1; }
+
+struct SolveArgs {
+  const Lay* L;
+  const Stat* S;
+  Opts o;
+  Counts cnt;
+  const double *xL, *xU;
+  double *iter, *work, *rw;
+  size_t it_stride, wk_stride, rw_stride;
+  Result* res;
+  int B;
+  int* counter;
+  // debug modes: 0 = solve, 1 = eval at stored iterate, 2 = Newton step at stored iterate
+  int mode, b_only;
+  double dbg_mu, dbg_dw;
+};
+
+OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, int b, int slot, Shared* sh) {
+  const Lay& L = *A.L;
+  const Stat& S = *A.S;
+  Scratch W;
+  carve_iterate(W, L, A.iter + (size_t)b * A.it_stride);
+  carve_work(W, L, A.work + (size_t)slot * A.wk_stride);
+  double* RW = A.rw + (size_t)slot * A.rw_stride;
+  if (A.mode == 0) {
+    ipm_solve(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, sh, A.res + b);
+    return;
+  }
+  double f, gdt;
+  for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.gl[q] = 0, W.dx[q] = 0;
+  for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.c[q] = 0, W.dy[q] = 0;
+  cta_sync(ctx);
+  eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
+  if (ctx.tid == 0) A.res[b].obj = f;
+  if (A.mode == 2) {
+    double mu = A.dbg_mu, dw = A.dbg_dw;
+    for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+      double lo = A.xL[q], hi = A.xU[q];
+      bool hl = lo > -INFINITY, hu = hi < INFINITY;
+      double sg = dw, gp = W.gl[q];
+      if (hl) {
+        double g = W.x[q] - lo;
+        sg += W.zL[q] / g, gp -= mu / g;
+        if (!hu) gp += A.o.kappa_d * mu;
+      }
+      if (hu) {
+        double g = hi - W.x[q];
+        sg += W.zU[q] / g, gp += mu / g;
+        if (!hl) gp -= A.o.kappa_d * mu;
+      }
+      W.sig[q] = sg, W.gphi[q] = gp;
+    }
+    cta_sync(ctx);
+    int ok = kkt_solve(ctx, L, S, W, RW, &sh->ok);
+    if (ctx.tid == 0) A.res[b].status = ok;
+  }
+}
+
+#ifndef OBCA_HOST_EMU
+__global__ void k_pack(const Lay* L, double* iter, size_t it_stride, PackArgs A, int B, int ne, bool unpack) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (size_t)B * ne) return;
+  pack_one(*L, iter, it_stride, A, (int)(g / ne), (int)(g % ne), unpack);
+}
+__global__ void k_init_pose(const Lay* L, double* iter, size_t it_stride, const double* pose, int B) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = L->V * 3;
+  if (g >= B * per) return;
+  Scratch W;
+  carve_iterate(W, *L, iter + (size_t)(g / per) * it_stride);
+  W.init_pose[g % per] = pose[g];
+}
+__global__ void __launch_bounds__(CTA_THREADS, 1) k_solve(SolveArgs A) {
+  __shared__ Shared sh;
+  __shared__ double red[40];
+  __shared__ int cur;
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x, red};
+  if (A.mode != 0) {
+    run_instance(ctx, A, A.b_only, 0, &sh);
+    return;
+  }
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) cur = atomicAdd(A.counter, 1);
+    __syncthreads();
+    int b = cur;
+    if (b >= A.B) break;
+    run_instance(ctx, A, b, blockIdx.x, &sh);
+  }
+}
+__global__ void k_stats(const Result* res, int B, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf, double* compl_inf) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (status) status[b] = res[b].status;
+  if (iters) iters[b] = res[b].iters;
+  if (obj) obj[b] = res[b].obj;
+  if (cviol) cviol[b] = res[b].cviol;
+  if (dual_inf) dual_inf[b] = res[b].dual_inf;
+  if (compl_inf) compl_inf[b] = res[b].compl_inf;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* obca_version(void) {
+#ifdef OBCA_HOST_EMU
+  return "obca-b200 0.1.0 (HOST EMULATION - developer tool, not the product)";
+#else
+  return "obca-b200 0.1.0 (sm_100a)";
+#endif
+}
+const char* obca_last_error(void) { return g_err.c_str(); }
+
+void obca_default_options(ObcaOptions* o) {
+  o->tol = 1e-2, o->constr_viol_tol = 1e-2, o->dual_inf_tol = 1.0, o->compl_inf_tol = 1e-4;
+  o->mu_init = 0.1, o->dmin = 0.05, o->shrink_tube = 0.5, o->max_iter = 3000, o->reserved = 0;
+}
+
+static void apply_options(ObcaHandle* h, const ObcaOptions* o) {
+  h->opts.tol = o->tol, h->opts.constr_viol_tol = o->constr_viol_tol, h->opts.dual_inf_tol = o->dual_inf_tol;
+  h->opts.compl_inf_tol = o->compl_inf_tol, h->opts.mu_init = o->mu_init, h->opts.max_iter = o->max_iter;
+  h->dmin = o->dmin, h->shrink = o->shrink_tube;
+}
+
+int obca_create(const ObcaDims* dims, const ObcaOptions* opts, int device, ObcaHandle** out) {
+  if (!dims || !out) return fail("obca_create: null argument");
+  if (dims->K != 5) return fail("obca_create: only K = 5 is supported");
+  if (dims->V < 1 || dims->V > OBCA_MAX_V) return fail("obca_create: V out of range");
+  if (dims->O < 0 || dims->O > OBCA_MAX_O) return fail("obca_create: O out of range");
+  if (dims->batch < 1 || dims->n_per_set < 1) return fail("obca_create: bad batch / n_per_set");
+  for (int a = 0; a < dims->V; ++a)
+    if (dims->n_sets[a] < 2 || dims->n_sets[a] > OBCA_MAX_SETS) return fail("obca_create: n_sets out of range");
+#ifndef OBCA_HOST_EMU
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("obca_create: no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("obca_create: bad device index");
+  CUDA_OK(cudaSetDevice(device));
+#endif
+  ObcaHandle* h = new ObcaHandle();
+  memset((void*)h, 0, sizeof(*h));
+  h->opts = Opts();
+  h->dims = *dims;
+  h->device = device;
+  ObcaOptions o;
+  obca_default_options(&o);
+  apply_options(h, opts ? opts : &o);
+  *out = h;
+  return 0;
+}
+
+int obca_set_options(ObcaHandle* h, const ObcaOptions* opts) {
+  if (!h || !opts) return fail("obca_set_options: null argument");
+  bool geom = h->have_static && (opts->dmin != h->dmin || opts->shrink_tube != h->shrink);
+  if (geom) return fail("obca_set_options: dmin / shrink_tube must be set before obca_set_static");
+  apply_options(h, opts);
+  return 0;
+}
+
+static void free_device(ObcaHandle* h) {
+  dev_free(h->d_L), dev_free(h->d_S), dev_free(h->d_tube), dev_free(h->d_xL), dev_free(h->d_xU);
+  dev_free(h->d_iter), dev_free(h->d_work), dev_free(h->d_rw), dev_free(h->d_res), dev_free(h->d_counter);
+  h->d_L = nullptr, h->d_S = nullptr, h->d_tube = nullptr, h->d_xL = h->d_xU = nullptr;
+  h->d_iter = h->d_work = h->d_rw = nullptr, h->d_res = nullptr, h->d_counter = nullptr;
+}
+
+int obca_destroy(ObcaHandle* h) {
+  if (!h) return 0;
+  free_device(h);
+  delete h;
+  return 0;
+}
+
+// collocation matrices from their definition (reference: confrez/control/vehicle.py:54-97); the Radau
+// points are the roots of P_5 - P_4 mapped to [0,1] (CasADi's collocation_points(5, "radau")).
+static void collocation_matrices(double cA[NK][NK], double cB[NK]) {
+  const double tau[NK] = {0.0, 0.05710419611451768, 0.27684301363812383, 0.5835904323689168, 0.8602401356562194, 1.0};
+  for (int j = 0; j < NK; ++j) {
+    // Lagrange basis polynomial j as monomial coefficients p[0] + p[1] t + ...
+    double p[NK + 1] = {1, 0, 0, 0, 0, 0, 0};
+    int deg = 0;
+    for (int k = 0; k < NK; ++k) {
+      if (k == j) continue;
+      double sc = 1.0 / (tau[j] - tau[k]);
+      double q[NK + 1] = {0, 0, 0, 0, 0, 0, 0};
+      for (int m = 0; m <= deg; ++m) q[m + 1] += p[m] * sc, q[m] -= p[m] * tau[k] * sc;
+      ++deg;
+      for (int m = 0; m <= deg; ++m) p[m] = q[m];
+    }
+    for (int k = 0; k < NK; ++k) {
+      double d = 0, tp = 1.0;
+      for (int m = 1; m <= deg; ++m) d += m * p[m] * tp, tp *= tau[k];
+      cA[j][k] = d;
+    }
+    double integ = 0;
+    for (int m = 0; m <= deg; ++m) integ += p[m] / (m + 1);
+    cB[j] = integ;
+  }
+}
+
+int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
+  if (!h || !st) return fail("obca_set_static: null argument");
+  free_device(h);
+  lay_build(h->L, h->dims, st->final_heading);
+  Lay& L = h->L;
+  Stat& S = h->S;
+  memset((void*)&S, 0, sizeof(S));
+  for (int j = 0; j < L.O; ++j)
+    for (int r = 0; r < 4; ++r) {
+      S.obsA[j][r][0] = st->obs_A[(j * 4 + r) * 2], S.obsA[j][r][1] = st->obs_A[(j * 4 + r) * 2 + 1];
+      S.obsb[j][r] = st->obs_b[j * 4 + r];
+    }
+  for (int r = 0; r < 4; ++r) S.G[r][0] = st->body_G[2 * r], S.G[r][1] = st->body_G[2 * r + 1], S.g[r] = st->body_g[r];
+  S.wb = st->wb, S.dmin = h->dmin;
+  for (int q = 0; q < 4; ++q) S.region[q] = st->region[q];
+  for (int q = 0; q < 8; ++q) S.limits[q] = st->limits[q];
+  for (int a = 0; a < L.V; ++a) S.heading[a] = st->final_heading[a];
+  collocation_matrices(S.cA, S.cB);
+  std::vector<double> tube((size_t)L.V * L.Smax * 2 * 4 * 3);
+  for (int a = 0; a < L.V; ++a)
+    for (int q = 0; q < L.Smax; ++q)
+      for (int body = 0; body < 2; ++body)
+        for (int r = 0; r < 4; ++r) {
+          size_t src = (((size_t)a * L.Smax + q) * 2 + body) * 4 + r;
+          tube[src * 3 + 0] = st->tube_A[src * 2], tube[src * 3 + 1] = st->tube_A[src * 2 + 1];
+          tube[src * 3 + 2] = st->tube_b[src] - h->shrink;
+        }
+  // bounds
+  std::vector<double> xL(L.nx, -INFINITY), xU(L.nx, INFINITY);
+  const double lo[NZ] = {S.region[0], S.region[2], -INFINITY, S.limits[0], S.limits[2], S.limits[4], S.limits[6]};
+  const double hi[NZ] = {S.region[1], S.region[3], INFINITY, S.limits[1], S.limits[3], S.limits[5], S.limits[7]};
+  int nb = 0, m_active = 0;
+  for (int a = 0; a < L.V; ++a) {
+    for (int n = 0; n < L.M[a]; ++n) {
+      for (int c = 0; c < NZ; ++c) xL[L.Z(a, c, n)] = lo[c], xU[L.Z(a, c, n)] = hi[c];
+      for (int j = 0; j < L.O; ++j) {
+        for (int r = 0; r < 4; ++r) xL[L.LAM(a, j, r, n)] = 0, xL[L.MU(a, j, r, n)] = 0;
+        xL[L.SD(a, j, n)] = 0;
+      }
+    }
+    for (int q = 0; q < L.S[a] - 1; ++q)
+      for (int r = 0; r < 8; ++r) xL[L.TS(a, q, r)] = 0;
+    m_active += 7 + 5 * L.M[a] + 7 * (L.N[a] - 1) + 4 + L.heading[a] + 4 * L.O * L.M[a] + 8 * (L.S[a] - 1);
+  }
+  for (int p = 0; p < L.P; ++p) {
+    for (int n = 0; n < L.Mp[p]; ++n) {
+      for (int r = 0; r < 4; ++r) xL[L.PL(p, r, n)] = 0, xL[L.PM(p, r, n)] = 0;
+      xL[L.PSD(p, n)] = 0, xL[L.PSN(p, n)] = 0;
+    }
+    m_active += 6 * L.Mp[p];
+  }
+  for (int q = 0; q < L.nx; ++q) nb += (xL[q] > -INFINITY) + (xU[q] < INFINITY);
+  h->cnt.m_active = m_active, h->cnt.nb = nb;
+  h->it_stride = iterate_doubles(L), h->wk_stride = work_doubles(L), h->rw_stride = riccati_work_doubles(L);
+#ifdef OBCA_HOST_EMU
+  h->slots = 1;
+#else
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+  h->slots = prop.multiProcessorCount < h->dims.batch ? prop.multiProcessorCount : h->dims.batch;
+#endif
+  int B = h->dims.batch;
+  if (dev_alloc((void**)&h->d_L, sizeof(Lay)) || dev_alloc((void**)&h->d_S, sizeof(Stat)) || dev_alloc((void**)&h->d_tube, tube.size() * 8) ||
+      dev_alloc((void**)&h->d_xL, L.nx * 8) || dev_alloc((void**)&h->d_xU, L.nx * 8) || dev_alloc((void**)&h->d_iter, (size_t)B * h->it_stride * 8) ||
+      dev_alloc((void**)&h->d_work, (size_t)h->slots * h->wk_stride * 8) || dev_alloc((void**)&h->d_rw, (size_t)h->slots * h->rw_stride * 8) ||
+      dev_alloc((void**)&h->d_res, (size_t)B * sizeof(Result)) || dev_alloc((void**)&h->d_counter, sizeof(int)))
+    return fail("obca_set_static: device allocation failed");
+  S.tube = h->d_tube;
+  h2d(h->d_tube, tube.data(), tube.size() * 8);
+  h2d(h->d_L, &L, sizeof(Lay));
+  h2d(h->d_S, &S, sizeof(Stat));
+  h2d(h->d_xL, xL.data(), L.nx * 8);
+  h2d(h->d_xU, xU.data(), L.nx * 8);
+  std::vector<Result> r0(B);
+  for (auto& r : r0) memset(&r, 0, sizeof(r)), r.status = OBCA_NOT_SOLVED;
+  h2d(h->d_res, r0.data(), B * sizeof(Result));
+  h->have_static = true;
+  return 0;
+}
+
+int obca_set_init_pose(ObcaHandle* h, const double* pose, void* stream) {
+  if (!h || !h->have_static) return fail("obca_set_init_pose: call obca_set_static first");
+  int B = h->dims.batch, per = h->L.V * 3;
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (int g = 0; g < B * per; ++g) {
+    Scratch W;
+    carve_iterate(W, h->L, h->d_iter + (size_t)(g / per) * h->it_stride);
+    W.init_pose[g % per] = pose[g];
+  }
+#else
+  k_init_pose<<<(B * per + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->d_L, h->d_iter, h->it_stride, pose, B);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+static int run_pack(ObcaHandle* h, const PackArgs& A, bool unpack, void* stream) {
+  int B = h->dims.batch, ne = pack_elems(h->L);
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (int b = 0; b < B; ++b)
+    for (int e = 0; e < ne; ++e) pack_one(h->L, h->d_iter, h->it_stride, A, b, e, unpack);
+#else
+  size_t tot = (size_t)B * ne;
+  k_pack<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d_L, h->d_iter, h->it_stride, A, B, ne, unpack);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+int obca_set_initial(ObcaHandle* h, const double* z, const double* lam, const double* mu, const double* dt, const double* pl,
+                     const double* pm, const double* ps, void* stream) {
+  if (!h || !h->have_static) return fail("obca_set_initial: call obca_set_static first");
+  if (!z || !lam || !mu || !dt) return fail("obca_set_initial: z, lam, mu, dt are required");
+  PackArgs A;
+  memset(&A, 0, sizeof(A));
+  A.z = z, A.lam = lam, A.mu = mu, A.dt = dt, A.pl = pl, A.pm = pm, A.ps = ps;
+  return run_pack(h, A, false, stream);
+}
+
+int obca_get_solution(ObcaHandle* h, double* z, double* lam, double* mu, double* dt, double* pl, double* pm, double* ps, void* stream) {
+  if (!h || !h->have_static) return fail("obca_get_solution: call obca_set_static first");
+  PackArgs A;
+  memset(&A, 0, sizeof(A));
+  A.oz = z, A.olam = lam, A.omu = mu, A.odt = dt, A.opl = pl, A.opm = pm, A.ops = ps;
+  return run_pack(h, A, true, stream);
+}
+
+static SolveArgs make_args(ObcaHandle* h, int mode, int b) {
+  SolveArgs A;
+  A.L = h->d_L, A.S = h->d_S, A.o = h->opts, A.cnt = h->cnt, A.xL = h->d_xL, A.xU = h->d_xU;
+  A.iter = h->d_iter, A.work = h->d_work, A.rw = h->d_rw;
+  A.it_stride = h->it_stride, A.wk_stride = h->wk_stride, A.rw_stride = h->rw_stride;
+  A.res = h->d_res, A.B = h->dims.batch, A.counter = h->d_counter, A.mode = mode, A.b_only = b;
+  A.dbg_mu = 0, A.dbg_dw = 0;
+  return A;
+}
+
+static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  Shared sh;
+  double red[40];
+  Ctx ctx{0, 1, red};
+  if (A.mode != 0)
+    run_instance(ctx, A, A.b_only, 0, &sh);
+  else
+    for (int b = 0; b < A.B; ++b) run_instance(ctx, A, b, 0, &sh);
+#else
+  cudaStream_t s = (cudaStream_t)stream;
+  if (A.mode == 0) CUDA_OK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
+  int grid = A.mode == 0 ? h->slots : 1;
+  k_solve<<<grid, CTA_THREADS, 0, s>>>(A);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+int obca_solve(ObcaHandle* h, void* stream) {
+  if (!h || !h->have_static) return fail("obca_solve: call obca_set_static first");
+  return launch(h, make_args(h, 0, 0), stream);
+}
+
+int obca_get_stats(ObcaHandle* h, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf, double* compl_inf, void* stream) {
+  if (!h || !h->have_static) return fail("obca_get_stats: call obca_set_static first");
+  int B = h->dims.batch;
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (int b = 0; b < B; ++b) {
+    const Result& r = h->d_res[b];
+    if (status) status[b] = r.status;
+    if (iters) iters[b] = r.iters;
+    if (obj) obj[b] = r.obj;
+    if (cviol) cviol[b] = r.cviol;
+    if (dual_inf) dual_inf[b] = r.dual_inf;
+    if (compl_inf) compl_inf[b] = r.compl_inf;
+  }
+#else
+  k_stats<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_res, B, status, iters, obj, cviol, dual_inf, compl_inf);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+int64_t obca_launch_count(const ObcaHandle* h) { return h ? h->launches : 0; }
+
+int obca_layout(const ObcaHandle* h, int64_t* out, int n) {
+  if (!h || !h->have_static) return fail("obca_layout: call obca_set_static first");
+  const Lay& L = h->L;
+  const int64_t v[] = {L.V,    L.O,    L.P,    L.Mv,     L.Nmax,  L.Smax,   L.nx,     L.ny,    L.oZ,     L.oLAM,  L.oMU,
+                       L.oSD,  L.oTS,  L.oPL,  L.oPM,    L.oPS,   L.oPSD,   L.oPSN,   L.oDT,   L.oYINIT, L.oYCOL, L.oYCONT,
+                       L.oYTERM, L.oYOBS, L.oYTUBE, L.oYPAIR, h->cnt.m_active, h->cnt.nb};
+  int cntv = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < n && i < cntv; ++i) out[i] = v[i];
+  return cntv;
+}
+
+int obca_debug_get_iterate(ObcaHandle* h, int b, double* x, double* y, double* zL, double* zU) {
+  if (!h || !h->have_static || b < 0 || b >= h->dims.batch) return fail("obca_debug_get_iterate: bad argument");
+  if (dev_sync()) return fail("device sync failed");
+  Scratch W;
+  carve_iterate(W, h->L, h->d_iter + (size_t)b * h->it_stride);
+  if (x) d2h(x, W.x, h->L.nx * 8);
+  if (y) d2h(y, W.y, h->L.ny * 8);
+  if (zL) d2h(zL, W.zL, h->L.nx * 8);
+  if (zU) d2h(zU, W.zU, h->L.nx * 8);
+  return 0;
+}
+
+int obca_debug_set_iterate(ObcaHandle* h, int b, const double* x, const double* y, const double* zL, const double* zU) {
+  if (!h || !h->have_static || b < 0 || b >= h->dims.batch) return fail("obca_debug_set_iterate: bad argument");
+  Scratch W;
+  carve_iterate(W, h->L, h->d_iter + (size_t)b * h->it_stride);
+  if (x) h2d(W.x, x, h->L.nx * 8);
+  if (y) h2d(W.y, y, h->L.ny * 8);
+  if (zL) h2d(W.zL, zL, h->L.nx * 8);
+  if (zU) h2d(W.zU, zU, h->L.nx * 8);
+  return 0;
+}
+
+int obca_debug_eval(ObcaHandle* h, int b, double* c, double* gl, double* f) {
+  if (!h || !h->have_static || b < 0 || b >= h->dims.batch) return fail("obca_debug_eval: bad argument");
+  if (launch(h, make_args(h, 1, b), nullptr)) return -1;
+  if (dev_sync()) return fail("obca_debug_eval: kernel failed");
+  Scratch W;
+  carve_work(W, h->L, h->d_work);
+  if (c) d2h(c, W.c, h->L.ny * 8);
+  if (gl) d2h(gl, W.gl, h->L.nx * 8);
+  Result r;
+  d2h(&r, h->d_res + b, sizeof(r));
+  if (f) *f = r.obj;
+  return 0;
+}
+
+int obca_debug_step(ObcaHandle* h, int b, double mu, double delta_w, double* dx, double* dy, int32_t* ok) {
+  if (!h || !h->have_static || b < 0 || b >= h->dims.batch) return fail("obca_debug_step: bad argument");
+  SolveArgs A = make_args(h, 2, b);
+  A.dbg_mu = mu, A.dbg_dw = delta_w;
+  if (launch(h, A, nullptr)) return -1;
+  if (dev_sync()) return fail("obca_debug_step: kernel failed");
+  Scratch W;
+  carve_work(W, h->L, h->d_work);
+  if (dx) d2h(dx, W.dx, h->L.nx * 8);
+  if (dy) d2h(dy, W.dy, h->L.ny * 8);
+  Result r;
+  d2h(&r, h->d_res + b, sizeof(r));
+  if (ok) *ok = r.status;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,613 @@
+// obca_core.h -- per-instance OBCA interior-point solver, written once for the CUDA kernels
+// (one CTA per problem instance) and for the single-threaded host emulation that the developer
+// tools use to debug the algorithm on machines without a GPU (tools/host_emu; never loaded by
+// the package).
+//
+// Problem (reference: confrez/control/vehicle.py:360-640, multi_vehicle_planner.py:343-480):
+//   collocation OBCA NLP of V vehicles sharing one interval length dt.  See DESIGN.md for the
+//   mathematics; the section names below match it.
+//
+//   [LAYOUT]   flat primal/dual vectors, node-minor (coalesced across the threads of a CTA)
+//   [EVAL]     residuals c(x), Lagrangian gradient gl = grad f + J'y, objective
+//   [LOCAL]    elimination of obstacle / pair / tube blocks onto the vehicle poses
+//   [NULLSP]   per (vehicle, interval) Householder QR of the collocation Jacobian -> stage dynamics
+//   [RICCATI]  backward / forward recursion over the intervals (state 7V+1, control 5V)
+//   [BACKSUB]  multipliers and local variables
+//   [IPM]      barrier update, fraction to the boundary, filter line search, convergence tests
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "obca.h"
+
+#if defined(__CUDACC__)
+#define OBCA_HD __host__ __device__ __forceinline__
+#define OBCA_HDN __host__ __device__
+#else
+#define OBCA_HD inline
+#define OBCA_HDN inline
+#endif
+
+namespace obca {
+
+constexpr int NK = 6;    // nodes per interval (K + 1)
+constexpr int NZ = 7;    // x y psi v delta a w
+constexpr int NS = 42;   // stage variables of one vehicle interval
+constexpr int NW = 35;   // stage variables without node 0
+constexpr int NRED = 13; // reduced coordinates: xi(7) p(5) dt(1)
+constexpr int NP = 5;    // free directions per vehicle interval
+constexpr int MAXV = OBCA_MAX_V;
+constexpr int MAXP = MAXV * (MAXV - 1) / 2;
+constexpr int NXMAX = 7 * MAXV + 1;
+constexpr int NUMAX = 5 * MAXV;
+constexpr int FILTER_MAX = 64;
+constexpr double DELTA_C_LOCAL = 1e-10;
+
+// ------------------------------------------------------------------------------------------------
+// [LAYOUT]
+// ------------------------------------------------------------------------------------------------
+struct Lay {
+  int V, O, P, Mv, Nmax, Smax, npset;
+  int N[MAXV], M[MAXV], S[MAXV], heading[MAXV];
+  int pa[MAXP], pb[MAXP], Mp[MAXP];
+  // primal fields
+  int oZ, oLAM, oMU, oSD, oTS, oPL, oPM, oPS, oPSD, oPSN, oDT, nx;
+  // multiplier / residual fields
+  int oYINIT, oYCOL, oYCONT, oYTERM, oYOBS, oYTUBE, oYPAIR, ny;
+  // Riccati sizes
+  int nX, nU;
+
+  OBCA_HD int Z(int a, int c, int n) const { return oZ + (a * NZ + c) * Mv + n; }
+  OBCA_HD int LAM(int a, int j, int r, int n) const { return oLAM + ((a * O + j) * 4 + r) * Mv + n; }
+  OBCA_HD int MU(int a, int j, int r, int n) const { return oMU + ((a * O + j) * 4 + r) * Mv + n; }
+  OBCA_HD int SD(int a, int j, int n) const { return oSD + (a * O + j) * Mv + n; }
+  OBCA_HD int TS(int a, int q, int r) const { return oTS + (a * (Smax - 1) + q) * 8 + r; }
+  OBCA_HD int PL(int p, int r, int n) const { return oPL + (p * 4 + r) * Mv + n; }
+  OBCA_HD int PM(int p, int r, int n) const { return oPM + (p * 4 + r) * Mv + n; }
+  OBCA_HD int PS(int p, int r, int n) const { return oPS + (p * 2 + r) * Mv + n; }
+  OBCA_HD int PSD(int p, int n) const { return oPSD + p * Mv + n; }
+  OBCA_HD int PSN(int p, int n) const { return oPSN + p * Mv + n; }
+  OBCA_HD int YINIT(int a, int c) const { return oYINIT + a * NZ + c; }
+  OBCA_HD int YCOL(int a, int c, int n) const { return oYCOL + (a * 5 + c) * Mv + n; }
+  OBCA_HD int YCONT(int a, int c, int i) const { return oYCONT + (a * NZ + c) * Nmax + i; }
+  OBCA_HD int YTERM(int a, int c) const { return oYTERM + a * 5 + c; }
+  OBCA_HD int YOBS(int a, int j, int r, int n) const { return oYOBS + ((a * O + j) * 4 + r) * Mv + n; }
+  OBCA_HD int YTUBE(int a, int q, int r) const { return oYTUBE + (a * (Smax - 1) + q) * 8 + r; }
+  OBCA_HD int YPAIR(int p, int r, int n) const { return oYPAIR + (p * 6 + r) * Mv + n; }
+};
+
+inline void lay_build(Lay& L, const ObcaDims& d, const double* final_heading) {
+  L.V = d.V;
+  L.O = d.O;
+  L.npset = d.n_per_set;
+  L.Mv = 0;
+  L.Nmax = 0;
+  L.Smax = 0;
+  for (int a = 0; a < d.V; ++a) {
+    L.S[a] = d.n_sets[a];
+    L.N[a] = d.n_per_set * (d.n_sets[a] - 1);
+    L.M[a] = NK * L.N[a];
+    L.heading[a] = final_heading ? (final_heading[a] == final_heading[a]) : 0;
+    if (L.M[a] > L.Mv) L.Mv = L.M[a];
+    if (L.N[a] > L.Nmax) L.Nmax = L.N[a];
+    if (L.S[a] > L.Smax) L.Smax = L.S[a];
+  }
+  L.P = 0;
+  for (int a = 0; a < d.V; ++a)
+    for (int b = a + 1; b < d.V; ++b) {
+      L.pa[L.P] = a;
+      L.pb[L.P] = b;
+      L.Mp[L.P] = L.M[a] < L.M[b] ? L.M[a] : L.M[b];
+      ++L.P;
+    }
+  int o = 0;
+  L.oZ = o, o += L.V * NZ * L.Mv;
+  L.oLAM = o, o += L.V * L.O * 4 * L.Mv;
+  L.oMU = o, o += L.V * L.O * 4 * L.Mv;
+  L.oSD = o, o += L.V * L.O * L.Mv;
+  L.oTS = o, o += L.V * (L.Smax - 1) * 8;
+  L.oPL = o, o += L.P * 4 * L.Mv;
+  L.oPM = o, o += L.P * 4 * L.Mv;
+  L.oPS = o, o += L.P * 2 * L.Mv;
+  L.oPSD = o, o += L.P * L.Mv;
+  L.oPSN = o, o += L.P * L.Mv;
+  L.oDT = o, o += 1;
+  L.nx = o;
+  o = 0;
+  L.oYINIT = o, o += L.V * NZ;
+  L.oYCOL = o, o += L.V * 5 * L.Mv;
+  L.oYCONT = o, o += L.V * NZ * L.Nmax;
+  L.oYTERM = o, o += L.V * 5;
+  L.oYOBS = o, o += L.V * L.O * 4 * L.Mv;
+  L.oYTUBE = o, o += L.V * (L.Smax - 1) * 8;
+  L.oYPAIR = o, o += L.P * 6 * L.Mv;
+  L.ny = o;
+  L.nX = 7 * L.V + 1;
+  L.nU = 5 * L.V;
+}
+
+// batch-invariant problem data
+struct Stat {
+  double obsA[OBCA_MAX_O][4][2], obsb[OBCA_MAX_O][4];
+  double G[4][2], g[4];
+  double wb, dmin;
+  double region[4], limits[8];
+  double heading[MAXV];
+  double cA[NK][NK], cB[NK];  // collocation matrices: cA[j][k] = L_j'(tau_k), cB[k] quadrature weights
+  // tube sets, b already reduced by shrink_tube: [V][Smax][2][4][3] = (ax, ay, b)
+  const double* tube;
+  OBCA_HD const double* tube_row(const Lay& L, int a, int q, int body, int r) const {
+    return tube + ((((a * L.Smax + q) * 2 + body) * 4 + r) * 3);
+  }
+};
+
+struct Opts {
+  double tol, constr_viol_tol, dual_inf_tol, compl_inf_tol, mu_init;
+  int max_iter;
+  // IPOPT constants
+  double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
+  double bound_push = 1e-2, bound_frac = 1e-2, kappa_sigma = 1e10, kappa_d = 1e-4, s_max = 100.0;
+  double gamma_theta = 1e-5, gamma_phi = 1e-8, eta_phi = 1e-8, delta_ls = 1.0, s_theta = 1.1, s_phi = 2.3;
+  double gamma_alpha = 0.05;
+  double dw_first = 1e-4, dw_min = 1e-20, dw_max = 1e40, kw_minus = 1.0 / 3.0, kw_plus = 8.0, kw_plus_first = 100.0;
+};
+
+// per-instance scratch sizes (doubles)
+struct Scratch {
+  // x-layout vectors
+  double *x, *zL, *zU, *dx, *dzL, *dzU, *gl, *gphi, *sig, *xt;
+  // y-layout vectors
+  double *y, *dy, *c, *ct;
+  // structured solve
+  double* XO;   // [V][Mv][O][52]   obstacle block solves: 13 x (3 coupling cols + 1 rhs)
+  double* XP;   // [P][Mv][126]     pair block solves: 18 x (6 + 1)
+  double* PH;   // [P][Mv][27]      pair Schur complement on (pose_a, pose_b): 21 sym + 6 grad
+  double* PG;   // [P][2][3][Mv]    pair contributions to the pose gradient (gl)
+  double* HN;   // [V][Mv][28]      node Hessian (sym packed)
+  double* GN;   // [V][Mv][7]       node gradient
+  double* HD;   // [V][Mv][7]       node x dt cross Hessian
+  double* TT;   // [V][Nmax][35*13 + 35]   reduced-coordinate map T and particular solution s0
+  double* QR;   // [V][Nmax][35*35 + 35 + 1]   Householder factors, tau, row count
+  double* MA;   // [V][Nmax][91 + 13]      projected stage Hessian (sym packed 13x13) + gradient
+  double* MAB;  // [P][Nmax][169 + 26]     projected cross-vehicle coupling + gradients
+  double* RK;   // [Nmax][nU*nX + nU]      Riccati gains
+  double* RP;   // [Nmax+1][nX*nX + nX]    cost-to-go
+  double* RA;   // [Nmax][nX*nX + nX*nU + nX]  stage dynamics
+  double* RX;   // [Nmax+1][nX] states, [Nmax][nU] controls
+  double* SS;   // [V][Nmax][42] stage solutions
+  double* init_pose;  // [V][3]
+};
+
+// per-instance iterate (kept for every instance of the batch): x, zL, zU (x-layout), y (y-layout), init pose
+inline size_t iterate_doubles(const Lay& L) { return 3 * (size_t)L.nx + (size_t)L.ny + (size_t)L.V * 3 + 8; }
+
+// per-slot work area (one per resident CTA)
+inline size_t work_doubles(const Lay& L) {
+  size_t n = 0;
+  n += 7 * (size_t)L.nx + 3 * (size_t)L.ny;
+  n += (size_t)L.V * L.Mv * L.O * 52;
+  n += (size_t)L.P * L.Mv * (126 + 27 + 6);
+  n += (size_t)L.V * L.Mv * (28 + 7 + 7);
+  n += (size_t)L.V * L.Nmax * ((NW * NRED + NW) + (NW * NW + NW + 1) + (91 + 13) + NS);
+  n += (size_t)L.P * L.Nmax * (169 + 26);
+  n += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
+  n += (size_t)(L.Nmax + 1) * (L.nX * L.nX + L.nX);
+  n += (size_t)L.Nmax * (L.nX * L.nX + L.nX * L.nU + L.nX);
+  n += (size_t)(L.Nmax + 1) * L.nX + (size_t)L.Nmax * L.nU;
+  return n + 64;
+}
+
+OBCA_HD void carve_iterate(Scratch& W, const Lay& L, double* p) {
+  W.x = p, p += L.nx;
+  W.zL = p, p += L.nx;
+  W.zU = p, p += L.nx;
+  W.y = p, p += L.ny;
+  W.init_pose = p;
+}
+
+OBCA_HD void carve_work(Scratch& W, const Lay& L, double* p) {
+  W.dx = p, p += L.nx;
+  W.dzL = p, p += L.nx;
+  W.dzU = p, p += L.nx;
+  W.gl = p, p += L.nx;
+  W.gphi = p, p += L.nx;
+  W.sig = p, p += L.nx;
+  W.xt = p, p += L.nx;
+  W.dy = p, p += L.ny;
+  W.c = p, p += L.ny;
+  W.ct = p, p += L.ny;
+  W.XO = p, p += (size_t)L.V * L.Mv * L.O * 52;
+  W.XP = p, p += (size_t)L.P * L.Mv * 126;
+  W.PH = p, p += (size_t)L.P * L.Mv * 27;
+  W.PG = p, p += (size_t)L.P * L.Mv * 6;
+  W.HN = p, p += (size_t)L.V * L.Mv * 28;
+  W.GN = p, p += (size_t)L.V * L.Mv * 7;
+  W.HD = p, p += (size_t)L.V * L.Mv * 7;
+  W.TT = p, p += (size_t)L.V * L.Nmax * (NW * NRED + NW);
+  W.QR = p, p += (size_t)L.V * L.Nmax * (NW * NW + NW + 1);
+  W.MA = p, p += (size_t)L.V * L.Nmax * (91 + 13);
+  W.MAB = p, p += (size_t)L.P * L.Nmax * (169 + 26);
+  W.RK = p, p += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
+  W.RP = p, p += (size_t)(L.Nmax + 1) * (L.nX * L.nX + L.nX);
+  W.RA = p, p += (size_t)L.Nmax * (L.nX * L.nX + L.nX * L.nU + L.nX);
+  W.RX = p, p += (size_t)(L.Nmax + 1) * L.nX + (size_t)L.Nmax * L.nU;
+  W.SS = p;
+}
+
+struct Result {
+  int status, iters;
+  double obj, cviol, dual_inf, compl_inf, mu, dt;
+};
+
+// ------------------------------------------------------------------------------------------------
+// execution context: one CTA (device) or one thread (host emulation)
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+  int tid, nt;
+  double* red;  // shared scratch for reductions (>= 40 doubles)
+};
+
+OBCA_HD void cta_sync(const Ctx&) {
+#if defined(__CUDA_ARCH__)
+  __syncthreads();
+#endif
+}
+
+// op: 0 sum, 1 max, 2 min.  Deterministic (fixed tree).  All threads get the result.
+OBCA_HD double cta_reduce(const Ctx& ctx, double v, int op) {
+#if defined(__CUDA_ARCH__)
+  for (int o = 16; o > 0; o >>= 1) {
+    double w = __shfl_down_sync(0xffffffffu, v, o);
+    v = op == 0 ? v + w : (op == 1 ? fmax(v, w) : fmin(v, w));
+  }
+  int lane = ctx.tid & 31, wid = ctx.tid >> 5, nw = (ctx.nt + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) ctx.red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double neutral = op == 0 ? 0.0 : (op == 1 ? -INFINITY : INFINITY);
+    v = lane < nw ? ctx.red[lane] : neutral;
+    for (int o = 16; o > 0; o >>= 1) {
+      double w = __shfl_down_sync(0xffffffffu, v, o);
+      v = op == 0 ? v + w : (op == 1 ? fmax(v, w) : fmin(v, w));
+    }
+    if (lane == 0) ctx.red[32] = v;
+  }
+  __syncthreads();
+  return ctx.red[32];
+#else
+  (void)ctx;
+  (void)op;
+  return v;
+#endif
+}
+OBCA_HD double cta_sum(const Ctx& c, double v) { return cta_reduce(c, v, 0); }
+OBCA_HD double cta_max(const Ctx& c, double v) { return cta_reduce(c, v, 1); }
+OBCA_HD double cta_min(const Ctx& c, double v) { return cta_reduce(c, v, 2); }
+
+// ------------------------------------------------------------------------------------------------
+// small dense helpers (thread-local)
+// ------------------------------------------------------------------------------------------------
+OBCA_HD int sym(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
+
+// In-place LDL' without pivoting of the symmetric matrix A (full storage, ld = n, lower part used).
+// Returns the number of negative pivots, or -1 when a pivot vanishes.
+template <int N>
+OBCA_HD int ldl_factor(double* A) {
+  int nneg = 0;
+  for (int j = 0; j < N; ++j) {
+    double d = A[j * N + j];
+    for (int k = 0; k < j; ++k) d -= A[j * N + k] * A[j * N + k] * A[k * N + k];
+    if (!(fabs(d) > 1e-300)) return -1;
+    A[j * N + j] = d;
+    if (d < 0) ++nneg;
+    double inv = 1.0 / d;
+    for (int i = j + 1; i < N; ++i) {
+      double v = A[i * N + j];
+      for (int k = 0; k < j; ++k) v -= A[i * N + k] * A[j * N + k] * A[k * N + k];
+      A[i * N + j] = v * inv;
+    }
+  }
+  return nneg;
+}
+
+template <int N>
+OBCA_HD void ldl_solve(const double* A, double* b, int stride) {
+  for (int i = 0; i < N; ++i) {
+    double v = b[i * stride];
+    for (int k = 0; k < i; ++k) v -= A[i * N + k] * b[k * stride];
+    b[i * stride] = v;
+  }
+  for (int i = 0; i < N; ++i) b[i * stride] /= A[i * N + i];
+  for (int i = N - 1; i >= 0; --i) {
+    double v = b[i * stride];
+    for (int k = i + 1; k < N; ++k) v -= A[k * N + i] * b[k * stride];
+    b[i * stride] = v;
+  }
+}
+
+struct Pose {
+  double x, y, psi, c, s;
+};
+
+// ------------------------------------------------------------------------------------------------
+// [EVAL] + [LOCAL] obstacle block at one node
+//   c1 = -g'mu + (A t - b)'lam - dmin - sd ; c2 = G'mu + R(psi)'A'lam ; c3 = |A'lam|^2 - 1
+// ------------------------------------------------------------------------------------------------
+struct ObsBlk {
+  double lam[4], mu[4], sd;
+  double Atb[4];   // A t - b
+  double u[2];     // A'lam
+  double c[4];
+};
+
+OBCA_HD void obs_residual(const Stat& S, int j, const Pose& p, ObsBlk& B) {
+  const double(*A)[2] = S.obsA[j];
+  B.u[0] = B.u[1] = 0;
+  double c1 = -S.dmin - B.sd;
+  double gm0 = 0, gm1 = 0;
+  for (int r = 0; r < 4; ++r) {
+    B.Atb[r] = A[r][0] * p.x + A[r][1] * p.y - S.obsb[j][r];
+    B.u[0] += A[r][0] * B.lam[r];
+    B.u[1] += A[r][1] * B.lam[r];
+    c1 += B.Atb[r] * B.lam[r] - S.g[r] * B.mu[r];
+    gm0 += S.G[r][0] * B.mu[r];
+    gm1 += S.G[r][1] * B.mu[r];
+  }
+  B.c[0] = c1;
+  B.c[1] = gm0 + p.c * B.u[0] + p.s * B.u[1];   // (R'u)_0
+  B.c[2] = gm1 - p.s * B.u[0] + p.c * B.u[1];   // (R'u)_1
+  B.c[3] = B.u[0] * B.u[0] + B.u[1] * B.u[1] - 1.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair block at one node:  A_i = G R(psi_i)', b_i = A_i t_i + g
+//   d = -b_a'lam - b_b'mu - dmin - sd ; e1 = A_a'lam + s ; e2 = A_b'mu - s ; n = 1 - s's - sn
+// ------------------------------------------------------------------------------------------------
+struct PairBlk {
+  double lam[4], mu[4], s[2], sd, sn;
+  double ua[2], ub[2];     // G'lam, G'mu
+  double Rua[2], Rub[2];   // R_a ua, R_b ub
+  double ba[4], bb[4];
+  double c[6];
+};
+
+OBCA_HD void pair_residual(const Stat& S, const Pose& a, const Pose& b, PairBlk& B) {
+  B.ua[0] = B.ua[1] = B.ub[0] = B.ub[1] = 0;
+  double d = -S.dmin - B.sd;
+  for (int r = 0; r < 4; ++r) {
+    B.ua[0] += S.G[r][0] * B.lam[r];
+    B.ua[1] += S.G[r][1] * B.lam[r];
+    B.ub[0] += S.G[r][0] * B.mu[r];
+    B.ub[1] += S.G[r][1] * B.mu[r];
+    // A_a row r = G_r R_a' ; R' = [[c, s], [-s, c]]
+    double aax = S.G[r][0] * a.c - S.G[r][1] * a.s, aay = S.G[r][0] * a.s + S.G[r][1] * a.c;
+    double abx = S.G[r][0] * b.c - S.G[r][1] * b.s, aby = S.G[r][0] * b.s + S.G[r][1] * b.c;
+    B.ba[r] = aax * a.x + aay * a.y + S.g[r];
+    B.bb[r] = abx * b.x + aby * b.y + S.g[r];
+    d -= B.ba[r] * B.lam[r] + B.bb[r] * B.mu[r];
+  }
+  B.Rua[0] = a.c * B.ua[0] - a.s * B.ua[1];
+  B.Rua[1] = a.s * B.ua[0] + a.c * B.ua[1];
+  B.Rub[0] = b.c * B.ub[0] - b.s * B.ub[1];
+  B.Rub[1] = b.s * B.ub[0] + b.c * B.ub[1];
+  B.c[0] = d;
+  B.c[1] = B.Rua[0] + B.s[0];
+  B.c[2] = B.Rua[1] + B.s[1];
+  B.c[3] = B.Rub[0] - B.s[0];
+  B.c[4] = B.Rub[1] - B.s[1];
+  B.c[5] = 1.0 - B.s[0] * B.s[0] - B.s[1] * B.s[1] - B.sn;
+}
+
+OBCA_HD void load_pose(const Lay& L, const double* x, int a, int n, Pose& p) {
+  p.x = x[L.Z(a, 0, n)];
+  p.y = x[L.Z(a, 1, n)];
+  p.psi = x[L.Z(a, 2, n)];
+  p.c = cos(p.psi);
+  p.s = sin(p.psi);
+}
+
+OBCA_HD void load_pair(const Lay& L, const double* x, int p, int n, PairBlk& B) {
+  for (int r = 0; r < 4; ++r) B.lam[r] = x[L.PL(p, r, n)], B.mu[r] = x[L.PM(p, r, n)];
+  B.s[0] = x[L.PS(p, 0, n)];
+  B.s[1] = x[L.PS(p, 1, n)];
+  B.sd = x[L.PSD(p, n)];
+  B.sn = x[L.PSN(p, n)];
+}
+
+// which tube set (if any) is enforced at node n of vehicle a: returns set index q >= 1 or -1.
+// Transition nodes (i = q * n_per_set, k = 0, vehicle.py:570-584) and the end state (last node with the last
+// set, vehicle.py:605-617; D = e_K so zF is the last node itself).
+OBCA_HD int tube_set_at(const Lay& L, int a, int n) {
+  if (n == L.M[a] - 1) return L.S[a] - 1;
+  int i = n / NK, k = n % NK;
+  if (k == 0 && i > 0 && i % L.npset == 0) return i / L.npset;
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// [EVAL] pair phase: residuals, gl of the pair variables, pose-gradient contributions -> PG
+// ------------------------------------------------------------------------------------------------
+OBCA_HDN void eval_pairs(const Ctx& ctx, const Lay& L, const Stat& S, const double* x, const double* y, double* c,
+                         double* gl, double* PG) {
+  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
+    int p = it / L.Mv, n = it % L.Mv;
+    if (n >= L.Mp[p]) continue;
+    Pose a, b;
+    load_pose(L, x, L.pa[p], n, a);
+    load_pose(L, x, L.pb[p], n, b);
+    PairBlk B;
+    load_pair(L, x, p, n, B);
+    pair_residual(S, a, b, B);
+    for (int r = 0; r < 6; ++r) c[L.YPAIR(p, r, n)] = B.c[r];
+    if (!y) continue;
+    double yd = y[L.YPAIR(p, 0, n)], ye1[2] = {y[L.YPAIR(p, 1, n)], y[L.YPAIR(p, 2, n)]};
+    double ye2[2] = {y[L.YPAIR(p, 3, n)], y[L.YPAIR(p, 4, n)]}, yn = y[L.YPAIR(p, 5, n)];
+    // R_a' ye1, R_b' ye2
+    double Rtea[2] = {a.c * ye1[0] + a.s * ye1[1], -a.s * ye1[0] + a.c * ye1[1]};
+    double Rteb[2] = {b.c * ye2[0] + b.s * ye2[1], -b.s * ye2[0] + b.c * ye2[1]};
+    for (int r = 0; r < 4; ++r) {
+      gl[L.PL(p, r, n)] = -yd * B.ba[r] + S.G[r][0] * Rtea[0] + S.G[r][1] * Rtea[1];
+      gl[L.PM(p, r, n)] = -yd * B.bb[r] + S.G[r][0] * Rteb[0] + S.G[r][1] * Rteb[1];
+    }
+    gl[L.PS(p, 0, n)] = ye1[0] - ye2[0] - 2.0 * yn * B.s[0];
+    gl[L.PS(p, 1, n)] = ye1[1] - ye2[1] - 2.0 * yn * B.s[1];
+    gl[L.PSD(p, n)] = -yd;
+    gl[L.PSN(p, n)] = -yn;
+    // pose gradients: d/dt_a = -yd R_a ua ; d/dpsi_a = -yd t_a' R_a' ua + ye1' R_a' ua   (R' = dR/dpsi here)
+    double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
+    double dRub[2] = {-b.s * B.ub[0] - b.c * B.ub[1], b.c * B.ub[0] - b.s * B.ub[1]};
+    double* g = PG + (size_t)(p * L.Mv + n) * 6;
+    g[0] = -yd * B.Rua[0];
+    g[1] = -yd * B.Rua[1];
+    g[2] = -yd * (a.x * dRua[0] + a.y * dRua[1]) + ye1[0] * dRua[0] + ye1[1] * dRua[1];
+    g[3] = -yd * B.Rub[0];
+    g[4] = -yd * B.Rub[1];
+    g[5] = -yd * (b.x * dRub[0] + b.y * dRub[1]) + ye2[0] * dRub[0] + ye2[1] * dRub[1];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// [EVAL] node phase.  y == nullptr: residuals and objective only (line-search trial points).
+// Returns (through the reductions) the objective f and d(f + y'c)/d dt.
+// ------------------------------------------------------------------------------------------------
+OBCA_HDN void eval_nodes(const Ctx& ctx, const Lay& L, const Stat& S, const double* init_pose, const double* x,
+                         const double* y, double* c, double* gl, const double* PG, double* f_out, double* gdt_out) {
+  const double dt = x[L.oDT];
+  const double idt = 1.0 / dt;
+  double f_part = 0, gdt_part = 0;
+  for (int it = ctx.tid; it < L.V * L.Mv; it += ctx.nt) {
+    int a = it / L.Mv, n = it % L.Mv;
+    if (n >= L.M[a]) continue;
+    int i = n / NK, k = n % NK, n0 = i * NK;
+    double z[NZ];
+    for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(a, q, n)];
+    Pose p = {z[0], z[1], z[2], cos(z[2]), sin(z[2])};
+    double v = z[3], de = z[4], ua = z[5], uw = z[6];
+    double tde = tan(de), sec2 = 1.0 + tde * tde;
+    // collocation residual: sum_j cA[j][k] z_j / dt - f(z_k, u_k)
+    double poly[5];
+    for (int q = 0; q < 5; ++q) {
+      double s = 0;
+      for (int j = 0; j < NK; ++j) s += S.cA[j][k] * x[L.Z(a, q, n0 + j)];
+      poly[q] = s * idt;
+    }
+    double fz[5] = {v * p.c, v * p.s, v * tde / S.wb, ua, uw};
+    for (int q = 0; q < 5; ++q) c[L.YCOL(a, q, n)] = poly[q] - fz[q];
+    double err = ua * ua + v * v * uw * uw + de * de;
+    f_part += S.cB[k] * err * dt;
+    // continuity (row i, i >= 1): z_{i-1,K} - z_{i,0}
+    if (k == 0 && i >= 1)
+      for (int q = 0; q < NZ; ++q) c[L.YCONT(a, q, i)] = x[L.Z(a, q, n - 1)] - z[q];
+    if (n == 0) {
+      for (int q = 0; q < 3; ++q) c[L.YINIT(a, q)] = z[q] - init_pose[a * 3 + q];
+      for (int q = 3; q < NZ; ++q) c[L.YINIT(a, q)] = z[q];
+    }
+    if (n == L.M[a] - 1) {
+      c[L.YTERM(a, 0)] = L.heading[a] ? z[2] - S.heading[a] : 0.0;
+      for (int q = 3; q < NZ; ++q) c[L.YTERM(a, q - 2)] = z[q];
+    }
+    double g[NZ] = {0, 0, 0, 0, 0, 0, 0};
+    if (y) {
+      double yc[5];
+      for (int q = 0; q < 5; ++q) yc[q] = y[L.YCOL(a, q, n)];
+      g[3] = S.cB[k] * dt * 2.0 * v * uw * uw;
+      g[4] = S.cB[k] * dt * 2.0 * de;
+      g[5] = S.cB[k] * dt * 2.0 * ua;
+      g[6] = S.cB[k] * dt * 2.0 * v * v * uw;
+      for (int q = 0; q < 5; ++q) {
+        double s = 0;
+        for (int kk = 0; kk < NK; ++kk) s += S.cA[k][kk] * y[L.YCOL(a, q, n0 + kk)];
+        g[q] += s * idt;
+        gdt_part -= yc[q] * poly[q] * idt;
+      }
+      gdt_part += S.cB[k] * err;
+      g[2] -= yc[0] * (-v * p.s) + yc[1] * (v * p.c);
+      g[3] -= yc[0] * p.c + yc[1] * p.s + yc[2] * tde / S.wb;
+      g[4] -= yc[2] * v * sec2 / S.wb;
+      g[5] -= yc[3];
+      g[6] -= yc[4];
+      if (k == NK - 1 && i < L.N[a] - 1)
+        for (int q = 0; q < NZ; ++q) g[q] += y[L.YCONT(a, q, i + 1)];
+      if (k == 0 && i >= 1)
+        for (int q = 0; q < NZ; ++q) g[q] -= y[L.YCONT(a, q, i)];
+      if (n == 0)
+        for (int q = 0; q < NZ; ++q) g[q] += y[L.YINIT(a, q)];
+      if (n == L.M[a] - 1) {
+        if (L.heading[a]) g[2] += y[L.YTERM(a, 0)];
+        for (int q = 3; q < NZ; ++q) g[q] += y[L.YTERM(a, q - 2)];
+      }
+    }
+    // obstacles
+    for (int j = 0; j < L.O; ++j) {
+      ObsBlk B;
+      for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(a, j, r, n)], B.mu[r] = x[L.MU(a, j, r, n)];
+      B.sd = x[L.SD(a, j, n)];
+      obs_residual(S, j, p, B);
+      for (int r = 0; r < 4; ++r) c[L.YOBS(a, j, r, n)] = B.c[r];
+      if (!y) continue;
+      double y1 = y[L.YOBS(a, j, 0, n)], y2[2] = {y[L.YOBS(a, j, 1, n)], y[L.YOBS(a, j, 2, n)]}, y3 = y[L.YOBS(a, j, 3, n)];
+      double Ry[2] = {p.c * y2[0] - p.s * y2[1], p.s * y2[0] + p.c * y2[1]};  // R y2
+      for (int r = 0; r < 4; ++r) {
+        const double* A = S.obsA[j][r];
+        gl[L.LAM(a, j, r, n)] = y1 * B.Atb[r] + A[0] * Ry[0] + A[1] * Ry[1] + 2.0 * y3 * (A[0] * B.u[0] + A[1] * B.u[1]);
+        gl[L.MU(a, j, r, n)] = -y1 * S.g[r] + S.G[r][0] * y2[0] + S.G[r][1] * y2[1];
+      }
+      gl[L.SD(a, j, n)] = -y1;
+      g[0] += y1 * B.u[0];
+      g[1] += y1 * B.u[1];
+      // d/dpsi of y2' R'u : R' = [[c,s],[-s,c]] -> dR'/dpsi = [[-s,c],[-c,-s]]
+      g[2] += y2[0] * (-p.s * B.u[0] + p.c * B.u[1]) + y2[1] * (-p.c * B.u[0] - p.s * B.u[1]);
+    }
+    // tube set
+    int q = tube_set_at(L, a, n);
+    if (q >= 1) {
+      double fx = p.x + S.wb * p.c, fy = p.y + S.wb * p.s;
+      for (int r = 0; r < 4; ++r) {
+        const double* tb = S.tube_row(L, a, q, 0, r);
+        const double* tf = S.tube_row(L, a, q, 1, r);
+        c[L.YTUBE(a, q - 1, r)] = tb[2] - tb[0] * p.x - tb[1] * p.y - x[L.TS(a, q - 1, r)];
+        c[L.YTUBE(a, q - 1, 4 + r)] = tf[2] - tf[0] * fx - tf[1] * fy - x[L.TS(a, q - 1, 4 + r)];
+        if (y) {
+          double yb = y[L.YTUBE(a, q - 1, r)], yf = y[L.YTUBE(a, q - 1, 4 + r)];
+          gl[L.TS(a, q - 1, r)] = -yb;
+          gl[L.TS(a, q - 1, 4 + r)] = -yf;
+          g[0] -= tb[0] * yb + tf[0] * yf;
+          g[1] -= tb[1] * yb + tf[1] * yf;
+          g[2] -= yf * S.wb * (-tf[0] * p.s + tf[1] * p.c);
+        }
+      }
+    }
+    if (y) {
+      for (int pp = 0; pp < L.P; ++pp) {
+        if (n >= L.Mp[pp]) continue;
+        const double* pg = PG + (size_t)(pp * L.Mv + n) * 6;
+        if (L.pa[pp] == a) g[0] += pg[0], g[1] += pg[1], g[2] += pg[2];
+        if (L.pb[pp] == a) g[0] += pg[3], g[1] += pg[4], g[2] += pg[5];
+      }
+      for (int qq = 0; qq < NZ; ++qq) gl[L.Z(a, qq, n)] = g[qq];
+    }
+  }
+  double f = cta_sum(ctx, f_part);
+  for (int a = 0; a < L.V; ++a) f += (L.N[a] * dt) * (L.N[a] * dt);
+  *f_out = f;
+  if (y) {
+    double gdt = cta_sum(ctx, gdt_part);
+    for (int a = 0; a < L.V; ++a) gdt += 2.0 * L.N[a] * L.N[a] * dt;
+    *gdt_out = gdt;
+    if (ctx.tid == 0) gl[L.oDT] = gdt;
+  }
+}
+
+OBCA_HDN void eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, const double* x, const double* y,
+                       double* c, double* gl, double* f, double* gdt) {
+  eval_pairs(ctx, L, S, x, y, c, gl, W.PG);
+  cta_sync(ctx);
+  eval_nodes(ctx, L, S, W.init_pose, x, y, c, gl, W.PG, f, gdt);
+  cta_sync(ctx);
+}
+
+}  // namespace obca
+
+#include "obca_kkt.h"
+#include "obca_ipm.h"

@@ -1,0 +1,319 @@
+// obca_ipm.h -- [IPM] per-instance primal-dual interior-point loop (IPM specification in DESIGN.md;
+// the CPU restatement used by the parity tests is oracle/ipm.py).
+#pragma once
+
+namespace obca {
+
+struct Shared {   // lives in shared memory on the device
+  int ok;
+  int filt_n;
+  double filt_theta[FILTER_MAX], filt_phi[FILTER_MAX];
+};
+
+struct Counts {
+  int m_active;   // number of equality rows
+  int nb;         // number of finite bounds
+};
+
+OBCA_HD bool finite_d(double v) { return v - v == 0.0; }
+
+// slack <- value of its inequality body, evaluated with the slack at zero
+OBCA_HDN void init_slacks(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W) {
+  for (int it = ctx.tid; it < L.V * L.O * L.Mv; it += ctx.nt) W.x[L.oSD + it] = 0;
+  for (int it = ctx.tid; it < L.V * (L.Smax - 1) * 8; it += ctx.nt) W.x[L.oTS + it] = 0;
+  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) W.x[L.oPSD + it] = 0, W.x[L.oPSN + it] = 0;
+  cta_sync(ctx);
+  double f, gdt;
+  eval_all(ctx, L, S, W, W.x, nullptr, W.c, nullptr, &f, &gdt);
+  for (int it = ctx.tid; it < L.V * L.O * L.Mv; it += ctx.nt) {
+    int n = it % L.Mv, aj = it / L.Mv, a = aj / L.O, j = aj % L.O;
+    if (n < L.M[a]) W.x[L.SD(a, j, n)] = W.c[L.YOBS(a, j, 0, n)];
+  }
+  for (int it = ctx.tid; it < L.V * (L.Smax - 1) * 8; it += ctx.nt) {
+    int a = it / ((L.Smax - 1) * 8), q = (it / 8) % (L.Smax - 1);
+    if (q < L.S[a] - 1) W.x[L.oTS + it] = W.c[L.oYTUBE + it];
+  }
+  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
+    int p = it / L.Mv, n = it % L.Mv;
+    if (n < L.Mp[p]) W.x[L.PSD(p, n)] = W.c[L.YPAIR(p, 0, n)], W.x[L.PSN(p, n)] = W.c[L.YPAIR(p, 5, n)];
+  }
+  cta_sync(ctx);
+}
+
+OBCA_HDN void push_into_bounds(const Ctx& ctx, const Lay& L, const double* xL, const double* xU, double* x, double k1, double k2) {
+  for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+    double lo = xL[q], hi = xU[q], v = x[q];
+    bool hl = lo > -INFINITY, hu = hi < INFINITY;
+    double pl = hl ? k1 * fmax(1.0, fabs(lo)) : 0.0, pu = hu ? k1 * fmax(1.0, fabs(hi)) : 0.0;
+    if (hl && hu) {
+      pl = fmin(pl, k2 * (hi - lo));
+      pu = fmin(pu, k2 * (hi - lo));
+    }
+    if (hl) v = fmax(v, lo + pl);
+    if (hu) v = fmin(v, hi - pu);
+    x[q] = v;
+  }
+  cta_sync(ctx);
+}
+
+// barrier objective at xv given f(xv); returns +inf outside the bounds
+OBCA_HDN double barrier_obj(const Ctx& ctx, const Lay& L, const double* xL, const double* xU, const double* xv, double f, double mu, double kd) {
+  double s = 0;
+  int bad = 0;
+  for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+    double lo = xL[q], hi = xU[q], v = xv[q];
+    bool hl = lo > -INFINITY, hu = hi < INFINITY;
+    if (hl) {
+      double gp = v - lo;
+      if (gp <= 0) bad = 1;
+      else s -= log(gp);
+      if (!hu) s += kd * gp;
+    }
+    if (hu) {
+      double gp = hi - v;
+      if (gp <= 0) bad = 1;
+      else s -= log(gp);
+      if (!hl) s += kd * gp;
+    }
+  }
+  double tot = cta_sum(ctx, s);
+  double anybad = cta_max(ctx, (double)bad);
+  if (anybad > 0) return INFINITY;
+  return f + mu * tot;
+}
+
+OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
+                        const double* xU, const Scratch& W, double* RW, Shared* sh, Result* res) {
+  // ---- initial point
+  init_slacks(ctx, L, S, W);
+  push_into_bounds(ctx, L, xL, xU, W.x, o.bound_push, o.bound_frac);
+  for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+    W.zL[q] = xL[q] > -INFINITY ? 1.0 : 0.0;
+    W.zU[q] = xU[q] < INFINITY ? 1.0 : 0.0;
+    W.dx[q] = 0, W.dzL[q] = 0, W.dzU[q] = 0, W.gl[q] = 0;
+  }
+  for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.y[q] = 0, W.dy[q] = 0;
+  if (ctx.tid == 0) sh->filt_n = 0;
+  cta_sync(ctx);
+  double mu = o.mu_init;
+  double f, gdt;
+  eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
+  double th0 = 0;
+  for (int q = ctx.tid; q < L.ny; q += ctx.nt) th0 += fabs(W.c[q]);
+  th0 = cta_sum(ctx, th0);
+  const double theta_max = 1e4 * fmax(1.0, th0), theta_min = 1e-4 * fmax(1.0, th0);
+  const double mu_min = fmin(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
+  double dw_last = 0.0;
+  int status = OBCA_MAXITER_EXCEEDED, it = 0;
+  double dual_inf = 0, cviol = 0, compl0 = 0;
+  for (;;) {
+    // ---- error measures at the current iterate (c, gl, f are up to date)
+    double e_du = 0, e_c = 0, e_c1 = 0, s_y = 0, s_z = 0, cmax0 = 0, cmaxmu_lo = INFINITY, cmaxmu_hi = 0;
+    for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+      double lo = xL[q], hi = xU[q];
+      e_du = fmax(e_du, fabs(W.gl[q] - W.zL[q] + W.zU[q]));
+      if (lo > -INFINITY) {
+        double pr = (W.x[q] - lo) * W.zL[q];
+        cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
+        s_z += W.zL[q];
+      }
+      if (hi < INFINITY) {
+        double pr = (hi - W.x[q]) * W.zU[q];
+        cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
+        s_z += W.zU[q];
+      }
+    }
+    for (int q = ctx.tid; q < L.ny; q += ctx.nt) {
+      e_c = fmax(e_c, fabs(W.c[q]));
+      e_c1 += fabs(W.c[q]);
+      s_y += fabs(W.y[q]);
+    }
+    dual_inf = cta_max(ctx, e_du);
+    cviol = cta_max(ctx, e_c);
+    double theta = cta_sum(ctx, e_c1);
+    s_y = cta_sum(ctx, s_y);
+    s_z = cta_sum(ctx, s_z);
+    compl0 = cta_max(ctx, cmax0);
+    double pr_lo = cta_min(ctx, cmaxmu_lo), pr_hi = cta_max(ctx, cmaxmu_hi);
+    double s_d = fmax(o.s_max, (s_y + s_z) / fmax(1.0, (double)(cnt.m_active + cnt.nb))) / o.s_max;
+    double s_c = fmax(o.s_max, s_z / fmax(1.0, (double)cnt.nb)) / o.s_max;
+    double E0 = fmax(fmax(dual_inf / s_d, cviol), compl0 / s_c);
+    if (E0 <= o.tol && dual_inf <= o.dual_inf_tol && cviol <= o.constr_viol_tol && compl0 <= o.compl_inf_tol) {
+      status = OBCA_SOLVE_SUCCEEDED;
+      break;
+    }
+    if (it >= o.max_iter) {
+      status = OBCA_MAXITER_EXCEEDED;
+      break;
+    }
+    if (!finite_d(f) || !finite_d(theta) || !finite_d(dual_inf)) {
+      status = OBCA_INVALID_NUMBER_DETECTED;
+      break;
+    }
+    // ---- barrier parameter update
+    for (;;) {
+      double cmu = fmax(fabs(pr_lo - mu), fabs(pr_hi - mu));
+      double Emu = fmax(fmax(dual_inf / s_d, cviol), cmu / s_c);
+      if (Emu <= o.kappa_eps * mu && mu > mu_min) {
+        mu = fmax(mu_min, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
+        if (ctx.tid == 0) sh->filt_n = 0;
+      } else
+        break;
+    }
+    cta_sync(ctx);
+    const double tau = fmax(o.tau_min, 1.0 - mu);
+    // ---- gradient of the barrier Lagrangian, barrier objective and grad_phi'dx bookkeeping
+    double phi = barrier_obj(ctx, L, xL, xU, W.x, f, mu, o.kappa_d);
+    // ---- search direction with inertia correction
+    double dw = 0.0;
+    bool first = true, have = false;
+    for (;;) {
+      for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+        double lo = xL[q], hi = xU[q];
+        bool hl = lo > -INFINITY, hu = hi < INFINITY;
+        double sg = dw, gp = W.gl[q];
+        if (hl) {
+          double gpL = W.x[q] - lo;
+          sg += W.zL[q] / gpL;
+          gp -= mu / gpL;
+          if (!hu) gp += o.kappa_d * mu;
+        }
+        if (hu) {
+          double gpU = hi - W.x[q];
+          sg += W.zU[q] / gpU;
+          gp += mu / gpU;
+          if (!hl) gp -= o.kappa_d * mu;
+        }
+        W.sig[q] = sg;
+        W.gphi[q] = gp;
+      }
+      cta_sync(ctx);
+      if (kkt_solve(ctx, L, S, W, RW, &sh->ok)) {
+        have = true;
+        break;
+      }
+      if (first) {
+        dw = dw_last == 0.0 ? o.dw_first : fmax(o.dw_min, o.kw_minus * dw_last);
+        first = false;
+      } else
+        dw *= dw_last == 0.0 ? o.kw_plus_first : o.kw_plus;
+      if (dw > o.dw_max) break;
+    }
+    if (!have) {
+      status = OBCA_ERROR_IN_STEP_COMPUTATION;
+      break;
+    }
+    if (dw > 0) dw_last = dw;
+    // ---- dz, fraction to the boundary, directional derivative of the barrier objective
+    double a_pr = 1.0, a_du = 1.0, dphi = 0;
+    for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+      double lo = xL[q], hi = xU[q], d = W.dx[q];
+      double gpl = W.gl[q];  // grad_phi = gphi - J'y = gl-part without multipliers: recompute below
+      (void)gpl;
+      if (lo > -INFINITY) {
+        double gp = W.x[q] - lo;
+        double dz = mu / gp - W.zL[q] - W.zL[q] / gp * d;
+        W.dzL[q] = dz;
+        if (d < 0) a_pr = fmin(a_pr, -tau * gp / d);
+        if (dz < 0) a_du = fmin(a_du, -tau * W.zL[q] / dz);
+      }
+      if (hi < INFINITY) {
+        double gp = hi - W.x[q];
+        double dz = mu / gp - W.zU[q] + W.zU[q] / gp * d;
+        W.dzU[q] = dz;
+        if (d > 0) a_pr = fmin(a_pr, tau * gp / d);
+        if (dz < 0) a_du = fmin(a_du, -tau * W.zU[q] / dz);
+      }
+      dphi += W.gphi[q] * d;
+    }
+    // grad_phi'dx = (gphi)'dx - y'J dx ; J dx = -c - (local delta_c terms, negligible) => use the exact product:
+    // y'J dx is accumulated from the structure: J dx = -(c) on all rows up to delta_c * dy.
+    double yJdx = 0;
+    for (int q = ctx.tid; q < L.ny; q += ctx.nt) yJdx += W.y[q] * (-W.c[q]);
+    for (int q = ctx.tid; q < L.V * L.O * 4 * L.Mv; q += ctx.nt) yJdx += W.y[L.oYOBS + q] * DELTA_C_LOCAL * W.dy[L.oYOBS + q];
+    for (int q = ctx.tid; q < L.P * 6 * L.Mv; q += ctx.nt) yJdx += W.y[L.oYPAIR + q] * DELTA_C_LOCAL * W.dy[L.oYPAIR + q];
+    a_pr = cta_min(ctx, a_pr);
+    a_du = cta_min(ctx, a_du);
+    dphi = cta_sum(ctx, dphi) - cta_sum(ctx, yJdx);
+    // ---- filter line search
+    double a_min;
+    if (dphi < 0) {
+      a_min = fmin(o.gamma_theta, o.gamma_phi * theta / (-dphi));
+      if (theta <= theta_min) a_min = fmin(a_min, o.delta_ls * pow(theta, o.s_theta) / pow(-dphi, o.s_phi));
+    } else
+      a_min = o.gamma_theta;
+    a_min *= o.gamma_alpha;
+    double alpha = a_pr;
+    bool accepted = false;
+    double ft = f, gdt_t;
+    while (alpha >= a_min) {
+      for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.xt[q] = W.x[q] + alpha * W.dx[q];
+      cta_sync(ctx);
+      eval_all(ctx, L, S, W, W.xt, nullptr, W.ct, nullptr, &ft, &gdt_t);
+      double tht = 0;
+      for (int q = ctx.tid; q < L.ny; q += ctx.nt) tht += fabs(W.ct[q]);
+      tht = cta_sum(ctx, tht);
+      double pht = barrier_obj(ctx, L, xL, xU, W.xt, ft, mu, o.kappa_d);
+      bool okp = finite_d(pht) && finite_d(tht) && tht <= theta_max;
+      if (okp) {
+        int nf = sh->filt_n;
+        for (int k = 0; k < nf; ++k)
+          if (tht >= sh->filt_theta[k] && pht >= sh->filt_phi[k]) okp = false;
+      }
+      if (okp) {
+        bool switching = theta <= theta_min && dphi < 0 && alpha * pow(-dphi, o.s_phi) > o.delta_ls * pow(theta, o.s_theta);
+        if (switching) {
+          if (pht <= phi + o.eta_phi * alpha * dphi) {
+            accepted = true;
+            break;
+          }
+        } else if (tht <= (1 - o.gamma_theta) * theta || pht <= phi - o.gamma_phi * theta) {
+          cta_sync(ctx);
+          if (ctx.tid == 0 && sh->filt_n < FILTER_MAX) {
+            sh->filt_theta[sh->filt_n] = (1 - o.gamma_theta) * theta;
+            sh->filt_phi[sh->filt_n] = phi - o.gamma_phi * theta;
+            sh->filt_n++;
+          }
+          accepted = true;
+          break;
+        }
+      }
+      alpha *= 0.5;
+    }
+    cta_sync(ctx);
+    if (!accepted) {
+      status = OBCA_RESTORATION_FAILED;
+      break;
+    }
+    // ---- accept the trial point
+    for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+      double lo = xL[q], hi = xU[q];
+      double xv = W.xt[q];
+      W.x[q] = xv;
+      if (lo > -INFINITY) {
+        double gp = xv - lo, zv = W.zL[q] + a_du * W.dzL[q];
+        W.zL[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
+      }
+      if (hi < INFINITY) {
+        double gp = hi - xv, zv = W.zU[q] + a_du * W.dzU[q];
+        W.zU[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
+      }
+    }
+    for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.y[q] += alpha * W.dy[q];
+    cta_sync(ctx);
+    eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
+    ++it;
+  }
+  if (ctx.tid == 0) {
+    res->status = status;
+    res->iters = it;
+    res->obj = f;
+    res->cviol = cviol;
+    res->dual_inf = dual_inf;
+    res->compl_inf = compl0;
+    res->mu = mu;
+    res->dt = W.x[L.oDT];
+  }
+}
+
+}  // namespace obca

@@ -1,0 +1,952 @@
+// obca_kkt.h -- structured solve of the primal-dual Newton system
+//
+//     [ W + Sigma + dw I   J' ] [dx]     [ gphi ]
+//     [ J              -dc I ] [dy] = - [  c   ]
+//
+// (dc = DELTA_C_LOCAL on obstacle / pair rows only, 0 elsewhere) by
+//   [LOCAL]   exact block elimination of the obstacle, pair and tube variables onto the vehicle poses,
+//   [NULLSP]  a Householder null-space parametrisation of every (vehicle, interval) collocation block,
+//   [RICCATI] a Riccati recursion over the intervals with state (xi_1..xi_V, dt) and control (p_1..p_V).
+// The reduced Hessian is positive definite (KKT inertia (n, m, 0), IPOPT's acceptance test) iff every
+// Riccati block F_i admits a Cholesky factor and the final dt pivot is positive; otherwise *ok = 0 and
+// the caller raises delta_w.
+#pragma once
+
+namespace obca {
+
+struct KktAux {
+  double* RW;  // Riccati work area
+};
+
+inline size_t riccati_work_doubles(const Lay& L) {
+  size_t nX = L.nX, nU = L.nU;
+  return 4 * nX * nX + 4 * nX * nU + 3 * nU * nU + 8 * (nX + nU) + 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// [LOCAL] pair blocks: one thread per (pair, node)
+// unknown order: lam 0-3, mu 4-7, sd 8, sn 9 | yd 10, ye1 11-12, ye2 13-14, yn 15 | s 16-17
+// ------------------------------------------------------------------------------------------------
+OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok) {
+  const double *x = W.x, *y = W.y;
+  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
+    int p = it / L.Mv, n = it % L.Mv;
+    if (n >= L.Mp[p]) continue;
+    Pose a, b;
+    load_pose(L, x, L.pa[p], n, a);
+    load_pose(L, x, L.pb[p], n, b);
+    PairBlk B;
+    load_pair(L, x, p, n, B);
+    pair_residual(S, a, b, B);
+    double yd = y[L.YPAIR(p, 0, n)], ye1[2] = {y[L.YPAIR(p, 1, n)], y[L.YPAIR(p, 2, n)]};
+    double ye2[2] = {y[L.YPAIR(p, 3, n)], y[L.YPAIR(p, 4, n)]}, yn = y[L.YPAIR(p, 5, n)];
+    double ynm = yn < 0 ? yn : 0.0;  // local convexification: exact at KKT points (yn = -z_sn <= 0)
+    double K[18 * 18];
+    double X[18 * 7];
+    for (int q = 0; q < 18 * 18; ++q) K[q] = 0;
+    for (int q = 0; q < 18 * 7; ++q) X[q] = 0;
+    for (int r = 0; r < 4; ++r) {
+      K[r * 18 + r] = W.sig[L.PL(p, r, n)];
+      K[(4 + r) * 18 + 4 + r] = W.sig[L.PM(p, r, n)];
+      K[10 * 18 + r] = -B.ba[r];
+      K[10 * 18 + 4 + r] = -B.bb[r];
+      K[11 * 18 + r] = a.c * S.G[r][0] - a.s * S.G[r][1];
+      K[12 * 18 + r] = a.s * S.G[r][0] + a.c * S.G[r][1];
+      K[13 * 18 + 4 + r] = b.c * S.G[r][0] - b.s * S.G[r][1];
+      K[14 * 18 + 4 + r] = b.s * S.G[r][0] + b.c * S.G[r][1];
+    }
+    K[8 * 18 + 8] = W.sig[L.PSD(p, n)];
+    K[9 * 18 + 9] = W.sig[L.PSN(p, n)];
+    K[10 * 18 + 8] = -1.0;
+    K[15 * 18 + 9] = -1.0;
+    for (int r = 10; r < 16; ++r) K[r * 18 + r] = -DELTA_C_LOCAL;
+    K[16 * 18 + 16] = W.sig[L.PS(p, 0, n)] - 2.0 * ynm;
+    K[17 * 18 + 17] = W.sig[L.PS(p, 1, n)] - 2.0 * ynm;
+    K[16 * 18 + 11] = 1.0, K[17 * 18 + 12] = 1.0;
+    K[16 * 18 + 13] = -1.0, K[17 * 18 + 14] = -1.0;
+    K[16 * 18 + 15] = -2.0 * B.s[0], K[17 * 18 + 15] = -2.0 * B.s[1];
+    // coupling columns: (x_a, y_a, psi_a, x_b, y_b, psi_b)
+    double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
+    double dRub[2] = {-b.s * B.ub[0] - b.c * B.ub[1], b.c * B.ub[0] - b.s * B.ub[1]};
+    double dRtea[2] = {-a.s * ye1[0] + a.c * ye1[1], -a.c * ye1[0] - a.s * ye1[1]};  // (dR/dpsi)' ye1
+    double dRteb[2] = {-b.s * ye2[0] + b.c * ye2[1], -b.c * ye2[0] - b.s * ye2[1]};
+    for (int r = 0; r < 4; ++r) {
+      double aax = S.G[r][0] * a.c - S.G[r][1] * a.s, aay = S.G[r][0] * a.s + S.G[r][1] * a.c;
+      double abx = S.G[r][0] * b.c - S.G[r][1] * b.s, aby = S.G[r][0] * b.s + S.G[r][1] * b.c;
+      double dax = -S.G[r][0] * a.s - S.G[r][1] * a.c, day = S.G[r][0] * a.c - S.G[r][1] * a.s;
+      double dbx = -S.G[r][0] * b.s - S.G[r][1] * b.c, dby = S.G[r][0] * b.c - S.G[r][1] * b.s;
+      X[r * 7 + 0] = -yd * aax;
+      X[r * 7 + 1] = -yd * aay;
+      X[r * 7 + 2] = -yd * (dax * a.x + day * a.y) + S.G[r][0] * dRtea[0] + S.G[r][1] * dRtea[1];
+      X[(4 + r) * 7 + 3] = -yd * abx;
+      X[(4 + r) * 7 + 4] = -yd * aby;
+      X[(4 + r) * 7 + 5] = -yd * (dbx * b.x + dby * b.y) + S.G[r][0] * dRteb[0] + S.G[r][1] * dRteb[1];
+      X[r * 7 + 6] = -W.gphi[L.PL(p, r, n)];
+      X[(4 + r) * 7 + 6] = -W.gphi[L.PM(p, r, n)];
+    }
+    X[10 * 7 + 0] = -B.Rua[0], X[10 * 7 + 1] = -B.Rua[1], X[10 * 7 + 2] = -(a.x * dRua[0] + a.y * dRua[1]);
+    X[10 * 7 + 3] = -B.Rub[0], X[10 * 7 + 4] = -B.Rub[1], X[10 * 7 + 5] = -(b.x * dRub[0] + b.y * dRub[1]);
+    X[11 * 7 + 2] = dRua[0], X[12 * 7 + 2] = dRua[1];
+    X[13 * 7 + 5] = dRub[0], X[14 * 7 + 5] = dRub[1];
+    X[8 * 7 + 6] = -W.gphi[L.PSD(p, n)];
+    X[9 * 7 + 6] = -W.gphi[L.PSN(p, n)];
+    for (int r = 0; r < 6; ++r) X[(10 + r) * 7 + 6] = -B.c[r];
+    X[16 * 7 + 6] = -W.gphi[L.PS(p, 0, n)];
+    X[17 * 7 + 6] = -W.gphi[L.PS(p, 1, n)];
+    double C[18 * 6];
+    for (int r = 0; r < 18; ++r)
+      for (int q = 0; q < 6; ++q) C[r * 6 + q] = X[r * 7 + q];
+    int nneg = ldl_factor<18>(K);
+    if (nneg != 6) *ok = 0;
+    for (int q = 0; q < 7; ++q) ldl_solve<18>(K, X + q, 7);
+    double* xp = W.XP + (size_t)(p * L.Mv + n) * 126;
+    for (int q = 0; q < 126; ++q) xp[q] = X[q];
+    // Schur complement on (pose_a, pose_b): direct Hessian - C' Xc ; gradient C' Xr
+    double H[36];
+    for (int q = 0; q < 36; ++q) H[q] = 0;
+    H[2 * 6 + 0] = H[0 * 6 + 2] = -yd * dRua[0];
+    H[2 * 6 + 1] = H[1 * 6 + 2] = -yd * dRua[1];
+    H[2 * 6 + 2] = yd * (a.x * B.Rua[0] + a.y * B.Rua[1]) - (ye1[0] * B.Rua[0] + ye1[1] * B.Rua[1]);
+    H[5 * 6 + 3] = H[3 * 6 + 5] = -yd * dRub[0];
+    H[5 * 6 + 4] = H[4 * 6 + 5] = -yd * dRub[1];
+    H[5 * 6 + 5] = yd * (b.x * B.Rub[0] + b.y * B.Rub[1]) - (ye2[0] * B.Rub[0] + ye2[1] * B.Rub[1]);
+    double* ph = W.PH + (size_t)(p * L.Mv + n) * 27;
+    for (int r = 0; r < 6; ++r) {
+      for (int q = 0; q <= r; ++q) {
+        double s = H[r * 6 + q];
+        for (int m = 0; m < 18; ++m) s -= C[m * 6 + r] * X[m * 7 + q];
+        ph[sym(r, q)] = s;
+      }
+      double s = 0;
+      for (int m = 0; m < 18; ++m) s += C[m * 6 + r] * X[m * 7 + 6];
+      ph[21 + r] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// [LOCAL] node assembly: obstacle / tube elimination, bounds, cost and collocation curvature
+// ------------------------------------------------------------------------------------------------
+OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok, double* hdtdt_out) {
+  const double *x = W.x, *y = W.y;
+  const double dt = x[L.oDT], idt = 1.0 / dt;
+  double hdt_part = 0;
+  for (int it = ctx.tid; it < L.V * L.Mv; it += ctx.nt) {
+    int a = it / L.Mv, n = it % L.Mv;
+    if (n >= L.M[a]) continue;
+    int i = n / NK, k = n % NK, n0 = i * NK;
+    double z[NZ];
+    for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(a, q, n)];
+    Pose p = {z[0], z[1], z[2], cos(z[2]), sin(z[2])};
+    double v = z[3], de = z[4], ua = z[5], uw = z[6];
+    double tde = tan(de), sec2 = 1.0 + tde * tde;
+    double H[28], g[NZ], hd[NZ];
+    for (int q = 0; q < 28; ++q) H[q] = 0;
+    for (int q = 0; q < NZ; ++q) {
+      H[sym(q, q)] = W.sig[L.Z(a, q, n)];
+      g[q] = W.gphi[L.Z(a, q, n)];
+      hd[q] = 0;
+    }
+    double bk = S.cB[k], bdt = bk * dt;
+    H[sym(3, 3)] += bdt * 2.0 * uw * uw;
+    H[sym(6, 6)] += bdt * 2.0 * v * v;
+    H[sym(6, 3)] += bdt * 4.0 * v * uw;
+    H[sym(4, 4)] += bdt * 2.0;
+    H[sym(5, 5)] += bdt * 2.0;
+    hd[3] = bk * 2.0 * v * uw * uw;
+    hd[4] = bk * 2.0 * de;
+    hd[5] = bk * 2.0 * ua;
+    hd[6] = bk * 2.0 * v * v * uw;
+    double yc[5];
+    for (int q = 0; q < 5; ++q) {
+      yc[q] = y[L.YCOL(a, q, n)];
+      double s = 0, pl = 0;
+      for (int kk = 0; kk < NK; ++kk) s += S.cA[k][kk] * y[L.YCOL(a, q, n0 + kk)];
+      for (int j = 0; j < NK; ++j) pl += S.cA[j][k] * x[L.Z(a, q, n0 + j)];
+      hd[q] -= s * idt * idt;
+      hdt_part += yc[q] * 2.0 * pl * idt * idt * idt;
+    }
+    H[sym(2, 2)] += yc[0] * v * p.c + yc[1] * v * p.s;
+    H[sym(3, 2)] += yc[0] * p.s - yc[1] * p.c;
+    H[sym(4, 3)] -= yc[2] * sec2 / S.wb;
+    H[sym(4, 4)] -= yc[2] * 2.0 * v * sec2 * tde / S.wb;
+    // ---- obstacles: unknown order lam 0-3, mu 4-7, sd 8 | y1 9, y2 10-11, y3 12
+    for (int j = 0; j < L.O; ++j) {
+      ObsBlk B;
+      for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(a, j, r, n)], B.mu[r] = x[L.MU(a, j, r, n)];
+      B.sd = x[L.SD(a, j, n)];
+      obs_residual(S, j, p, B);
+      double y1 = y[L.YOBS(a, j, 0, n)], y2[2] = {y[L.YOBS(a, j, 1, n)], y[L.YOBS(a, j, 2, n)]}, y3 = y[L.YOBS(a, j, 3, n)];
+      double y3p = y3 > 0 ? y3 : 0.0;  // local convexification: exact at KKT points (y3 >= 0)
+      double K[13 * 13], X[13 * 4];
+      for (int q = 0; q < 169; ++q) K[q] = 0;
+      for (int q = 0; q < 52; ++q) X[q] = 0;
+      double dRy[2] = {-p.s * y2[0] - p.c * y2[1], p.c * y2[0] - p.s * y2[1]};   // (dR/dpsi) y2
+      double dRtu[2] = {-p.s * B.u[0] + p.c * B.u[1], -p.c * B.u[0] - p.s * B.u[1]};  // (dR'/dpsi) u
+      for (int r = 0; r < 4; ++r) {
+        const double* A = S.obsA[j][r];
+        for (int q = 0; q <= r; ++q) K[r * 13 + q] = 2.0 * y3p * (A[0] * S.obsA[j][q][0] + A[1] * S.obsA[j][q][1]);
+        K[r * 13 + r] += W.sig[L.LAM(a, j, r, n)];
+        K[(4 + r) * 13 + 4 + r] = W.sig[L.MU(a, j, r, n)];
+        K[9 * 13 + r] = B.Atb[r];
+        K[9 * 13 + 4 + r] = -S.g[r];
+        K[10 * 13 + r] = p.c * A[0] + p.s * A[1];
+        K[11 * 13 + r] = -p.s * A[0] + p.c * A[1];
+        K[10 * 13 + 4 + r] = S.G[r][0];
+        K[11 * 13 + 4 + r] = S.G[r][1];
+        K[12 * 13 + r] = 2.0 * (A[0] * B.u[0] + A[1] * B.u[1]);
+        X[r * 4 + 0] = y1 * A[0];
+        X[r * 4 + 1] = y1 * A[1];
+        X[r * 4 + 2] = A[0] * dRy[0] + A[1] * dRy[1];
+        X[r * 4 + 3] = -W.gphi[L.LAM(a, j, r, n)];
+        X[(4 + r) * 4 + 3] = -W.gphi[L.MU(a, j, r, n)];
+      }
+      K[8 * 13 + 8] = W.sig[L.SD(a, j, n)];
+      K[9 * 13 + 8] = -1.0;
+      for (int r = 9; r < 13; ++r) K[r * 13 + r] = -DELTA_C_LOCAL;
+      X[8 * 4 + 3] = -W.gphi[L.SD(a, j, n)];
+      X[9 * 4 + 0] = B.u[0], X[9 * 4 + 1] = B.u[1];
+      X[10 * 4 + 2] = dRtu[0], X[11 * 4 + 2] = dRtu[1];
+      for (int r = 0; r < 4; ++r) X[(9 + r) * 4 + 3] = -B.c[r];
+      double C[13 * 3];
+      for (int r = 0; r < 13; ++r)
+        for (int q = 0; q < 3; ++q) C[r * 3 + q] = X[r * 4 + q];
+      int nneg = ldl_factor<13>(K);
+      if (nneg != 4) *ok = 0;
+      for (int q = 0; q < 4; ++q) ldl_solve<13>(K, X + q, 4);
+      double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 52;
+      for (int q = 0; q < 52; ++q) xo[q] = X[q];
+      H[sym(2, 2)] -= y2[0] * (p.c * B.u[0] + p.s * B.u[1]) + y2[1] * (-p.s * B.u[0] + p.c * B.u[1]);
+      for (int r = 0; r < 3; ++r) {
+        for (int q = 0; q <= r; ++q) {
+          double s = 0;
+          for (int m = 0; m < 13; ++m) s += C[m * 3 + r] * X[m * 4 + q];
+          H[sym(r, q)] -= s;
+        }
+        double s = 0;
+        for (int m = 0; m < 13; ++m) s += C[m * 3 + r] * X[m * 4 + 3];
+        g[r] += s;
+      }
+    }
+    // ---- tube set (slack and multiplier eliminated analytically)
+    int q = tube_set_at(L, a, n);
+    if (q >= 1) {
+      for (int r = 0; r < 8; ++r) {
+        const double* t = S.tube_row(L, a, q, r / 4, r % 4);
+        double gr[3] = {t[0], t[1], r < 4 ? 0.0 : S.wb * (-t[0] * p.s + t[1] * p.c)};
+        double sg = W.sig[L.TS(a, q - 1, r)];
+        double w = sg * W.c[L.YTUBE(a, q - 1, r)] + W.gphi[L.TS(a, q - 1, r)];
+        for (int m = 0; m < 3; ++m) {
+          g[m] -= gr[m] * w;
+          for (int mm = 0; mm <= m; ++mm) H[sym(m, mm)] += sg * gr[m] * gr[mm];
+        }
+        if (r >= 4) H[sym(2, 2)] += y[L.YTUBE(a, q - 1, r)] * S.wb * (t[0] * p.c + t[1] * p.s);
+      }
+    }
+    // ---- pair Schur complements (diagonal blocks and gradients)
+    for (int pp = 0; pp < L.P; ++pp) {
+      if (n >= L.Mp[pp]) continue;
+      const double* ph = W.PH + (size_t)(pp * L.Mv + n) * 27;
+      int off = L.pa[pp] == a ? 0 : (L.pb[pp] == a ? 3 : -1);
+      if (off < 0) continue;
+      for (int r = 0; r < 3; ++r) {
+        for (int m = 0; m <= r; ++m) H[sym(r, m)] += ph[sym(off + r, off + m)];
+        g[r] += ph[21 + off + r];
+      }
+    }
+    double* hn = W.HN + (size_t)(a * L.Mv + n) * 28;
+    double* gn = W.GN + (size_t)(a * L.Mv + n) * 7;
+    double* hdn = W.HD + (size_t)(a * L.Mv + n) * 7;
+    for (int m = 0; m < 28; ++m) hn[m] = H[m];
+    for (int m = 0; m < NZ; ++m) gn[m] = g[m], hdn[m] = hd[m];
+  }
+  double hdt = cta_sum(ctx, hdt_part);
+  for (int a = 0; a < L.V; ++a) hdt += 2.0 * L.N[a] * L.N[a];
+  *hdtdt_out = hdt + W.sig[L.oDT];
+}
+
+// ------------------------------------------------------------------------------------------------
+// [NULLSP] one thread per (vehicle, interval)
+// ------------------------------------------------------------------------------------------------
+// apply Q = H_0 ... H_{nr-1} (transpose = false) or Q' (transpose = true) to v[35]
+OBCA_HD void apply_q(const double* QRm, const double* tau, int nr, double* v, bool transpose) {
+  for (int jj = 0; jj < nr; ++jj) {
+    int j = transpose ? jj : nr - 1 - jj;
+    double s = v[j];
+    for (int r = j + 1; r < NW; ++r) s += QRm[r * NW + j] * v[r];
+    s *= tau[j];
+    v[j] -= s;
+    for (int r = j + 1; r < NW; ++r) v[r] -= s * QRm[r * NW + j];
+  }
+}
+
+OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok) {
+  const double *x = W.x;
+  const double dt = x[L.oDT], idt = 1.0 / dt;
+  for (int it = ctx.tid; it < L.V * L.Nmax; it += ctx.nt) {
+    int a = it / L.Nmax, i = it % L.Nmax;
+    if (i >= L.N[a]) continue;
+    int n0 = i * NK;
+    bool last = (i == L.N[a] - 1);
+    int nterm = last ? (4 + L.heading[a]) : 0;
+    int nr = 30 + nterm;
+    double* QRm = W.QR + (size_t)(a * L.Nmax + i) * (NW * NW + NW + 1);  // [35][35]: column j = row j of G_w
+    double* tau = QRm + NW * NW;
+    double G0[35 * 7], gd[35], rr[35];
+    for (int q = 0; q < NW * NW; ++q) QRm[q] = 0;
+    for (int q = 0; q < 35 * 7; ++q) G0[q] = 0;
+    for (int k = 0; k < NK; ++k) {
+      int n = n0 + k;
+      double psi = x[L.Z(a, 2, n)], v = x[L.Z(a, 3, n)], de = x[L.Z(a, 4, n)];
+      double cs = cos(psi), sn = sin(psi), tde = tan(de), sec2 = 1.0 + tde * tde;
+      for (int q = 0; q < 5; ++q) {
+        int r = k * 5 + q;
+        double pl = 0;
+        for (int j = 0; j < NK; ++j) {
+          double coef = S.cA[j][k] * idt;
+          pl += S.cA[j][k] * x[L.Z(a, q, n0 + j)];
+          if (j == 0) G0[r * 7 + q] += coef;
+          else QRm[((j - 1) * 7 + q) * NW + r] += coef;
+        }
+        gd[r] = -pl * idt * idt;
+        rr[r] = W.c[L.YCOL(a, q, n)];
+      }
+      // minus df/d(z,u) at node k
+      double dfz[5][NZ] = {{0, 0, -v * sn, cs, 0, 0, 0}, {0, 0, v * cs, sn, 0, 0, 0}, {0, 0, 0, tde / S.wb, v * sec2 / S.wb, 0, 0},
+                           {0, 0, 0, 0, 0, 1, 0},        {0, 0, 0, 0, 0, 0, 1}};
+      for (int q = 0; q < 5; ++q)
+        for (int m = 2; m < NZ; ++m) {
+          if (dfz[q][m] == 0.0) continue;
+          int r = k * 5 + q;
+          if (k == 0) G0[r * 7 + m] -= dfz[q][m];
+          else QRm[((k - 1) * 7 + m) * NW + r] -= dfz[q][m];
+        }
+    }
+    if (last) {
+      int r = 30;
+      if (L.heading[a]) {
+        QRm[(28 + 2) * NW + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, 0)];
+        ++r;
+      }
+      for (int m = 3; m < NZ; ++m, ++r) QRm[(28 + m) * NW + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, m - 2)];
+    }
+    // Householder QR of the 35 x nr matrix (LAPACK dgeqr2 convention: v_j[j] = 1 implicit)
+    for (int j = 0; j < nr; ++j) {
+      double nrm = 0;
+      for (int r = j + 1; r < NW; ++r) nrm += QRm[r * NW + j] * QRm[r * NW + j];
+      double alpha = QRm[j * NW + j];
+      double beta = sqrt(alpha * alpha + nrm);
+      if (!(beta > 1e-13)) {
+        *ok = 0;
+        beta = 1e-13;
+      }
+      if (alpha > 0) beta = -beta;
+      double t = (beta - alpha) / beta;
+      double sc = 1.0 / (alpha - beta);
+      for (int r = j + 1; r < NW; ++r) QRm[r * NW + j] *= sc;
+      tau[j] = t;
+      QRm[j * NW + j] = beta;
+      for (int cc = j + 1; cc < nr; ++cc) {
+        double s = QRm[j * NW + cc];
+        for (int r = j + 1; r < NW; ++r) s += QRm[r * NW + j] * QRm[r * NW + cc];
+        s *= t;
+        QRm[j * NW + cc] -= s;
+        for (int r = j + 1; r < NW; ++r) QRm[r * NW + cc] -= s * QRm[r * NW + j];
+      }
+    }
+    QRm[NW * NW + NW] = (double)nr;
+    // T columns: 0..6 xi, 7..11 p, 12 dt; s0
+    double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+    double* s0 = T + NW * NRED;
+    double vcol[NW];
+    for (int col = 0; col < 9; ++col) {
+      // b = -G0[:,col] (col < 7), -gd (col 7), -r (col 8); w = R^-T b ; vcol = Q [w; 0]
+      for (int r = 0; r < nr; ++r) {
+        double bv = col < 7 ? -G0[r * 7 + col] : (col == 7 ? -gd[r] : -rr[r]);
+        for (int m = 0; m < r; ++m) bv -= QRm[m * NW + r] * vcol[m];
+        vcol[r] = bv / QRm[r * NW + r];
+      }
+      for (int r = nr; r < NW; ++r) vcol[r] = 0;
+      apply_q(QRm, tau, nr, vcol, false);
+      if (col < 7)
+        for (int r = 0; r < NW; ++r) T[r * NRED + col] = vcol[r];
+      else if (col == 7)
+        for (int r = 0; r < NW; ++r) T[r * NRED + 12] = vcol[r];
+      else
+        for (int r = 0; r < NW; ++r) s0[r] = vcol[r];
+    }
+    int np = NW - nr;
+    for (int j = 0; j < NP; ++j) {
+      for (int r = 0; r < NW; ++r) vcol[r] = 0;
+      if (j < np) {
+        vcol[nr + j] = 1.0;
+        apply_q(QRm, tau, nr, vcol, false);
+      }
+      for (int r = 0; r < NW; ++r) T[r * NRED + 7 + j] = vcol[r];
+    }
+    // projected stage Hessian M = Tt' H Tt + dt cross terms, gradient m = Tt'(H s0 + gn) + e_dt hd's0
+    double HT[NS * NRED];
+    double hs0[NS];
+    for (int k = 0; k < NK; ++k) {
+      const double* hn = W.HN + (size_t)(a * L.Mv + n0 + k) * 28;
+      for (int r = 0; r < NZ; ++r) {
+        int row = k * NZ + r;
+        double acc0 = 0;
+        for (int col = 0; col < NRED; ++col) {
+          double s = 0;
+          for (int m = 0; m < NZ; ++m) {
+            double tv = (k == 0) ? ((m == col) ? 1.0 : 0.0) : T[((k - 1) * NZ + m) * NRED + col];
+            s += hn[sym(r, m)] * tv;
+          }
+          HT[row * NRED + col] = s;
+        }
+        if (k > 0)
+          for (int m = 0; m < NZ; ++m) acc0 += hn[sym(r, m)] * s0[(k - 1) * NZ + m];
+        hs0[row] = acc0;
+      }
+    }
+    double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (91 + 13);
+    double hdT[NRED];
+    double hds0 = 0;
+    for (int col = 0; col < NRED; ++col) hdT[col] = 0;
+    for (int row = 0; row < NS; ++row) {
+      int k = row / NZ, m = row % NZ;
+      double hdv = W.HD[(size_t)(a * L.Mv + n0 + k) * 7 + m];
+      if (k == 0) hdT[m] += hdv;
+      else {
+        for (int col = 0; col < NRED; ++col) hdT[col] += hdv * T[(row - NZ) * NRED + col];
+        hds0 += hdv * s0[row - NZ];
+      }
+    }
+    for (int r = 0; r < NRED; ++r) {
+      for (int cc = 0; cc <= r; ++cc) {
+        double s = 0;
+        if (r < NZ) s += HT[r * NRED + cc];  // node-0 identity rows
+        for (int row = NZ; row < NS; ++row) s += T[(row - NZ) * NRED + r] * HT[row * NRED + cc];
+        if (r == 12) s += hdT[cc];
+        if (cc == 12) s += hdT[r];
+        Mo[sym(r, cc)] = s;
+      }
+      double s = 0;
+      if (r < NZ) s += hs0[r] + W.GN[(size_t)(a * L.Mv + n0) * 7 + r];
+      for (int row = NZ; row < NS; ++row)
+        s += T[(row - NZ) * NRED + r] * (hs0[row] + W.GN[(size_t)(a * L.Mv + n0 + row / NZ) * 7 + row % NZ]);
+      if (r == 12) s += hds0;
+      Mo[91 + r] = s;
+    }
+  }
+}
+
+// reduced-coordinate row of stage variable (node k, comp m) of vehicle-interval map T
+OBCA_HD double tt_entry(const double* T, int k, int m, int col) {
+  if (k == 0) return m == col ? 1.0 : 0.0;
+  return T[((k - 1) * NZ + m) * NRED + col];
+}
+
+// cross-vehicle coupling: one thread per (pair, interval)
+OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W) {
+  for (int it = ctx.tid; it < L.P * L.Nmax; it += ctx.nt) {
+    int p = it / L.Nmax, i = it % L.Nmax;
+    if (i * NK >= L.Mp[p]) continue;
+    int a = L.pa[p], b = L.pb[p];
+    const double* Ta = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+    const double* Tb = W.TT + (size_t)(b * L.Nmax + i) * (NW * NRED + NW);
+    const double *s0a = Ta + NW * NRED, *s0b = Tb + NW * NRED;
+    double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (169 + 26);
+    for (int q = 0; q < 169 + 26; ++q) Mo[q] = 0;
+    for (int k = 0; k < NK; ++k) {
+      const double* ph = W.PH + (size_t)(p * L.Mv + i * NK + k) * 27;
+      double Hc[3][3];
+      for (int r = 0; r < 3; ++r)
+        for (int m = 0; m < 3; ++m) Hc[r][m] = ph[sym(3 + m, r)];  // rows pose_a, cols pose_b
+      double HTb[3][NRED], Hs0b[3], Hts0a[3];
+      for (int r = 0; r < 3; ++r) {
+        for (int col = 0; col < NRED; ++col) {
+          double s = 0;
+          for (int m = 0; m < 3; ++m) s += Hc[r][m] * tt_entry(Tb, k, m, col);
+          HTb[r][col] = s;
+        }
+        double s = 0, t = 0;
+        for (int m = 0; m < 3; ++m) {
+          s += Hc[r][m] * (k == 0 ? 0.0 : s0b[(k - 1) * NZ + m]);
+          t += Hc[m][r] * (k == 0 ? 0.0 : s0a[(k - 1) * NZ + m]);
+        }
+        Hs0b[r] = s;
+        Hts0a[r] = t;
+      }
+      for (int ra = 0; ra < NRED; ++ra) {
+        double ga = 0;
+        for (int r = 0; r < 3; ++r) {
+          double ta = tt_entry(Ta, k, r, ra);
+          if (ta == 0.0) continue;
+          for (int cb = 0; cb < NRED; ++cb) Mo[ra * NRED + cb] += ta * HTb[r][cb];
+          ga += ta * Hs0b[r];
+        }
+        Mo[169 + ra] += ga;
+        double gb = 0;
+        for (int r = 0; r < 3; ++r) gb += tt_entry(Tb, k, r, ra) * Hts0a[r];
+        Mo[169 + 13 + ra] += gb;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// [RICCATI]
+// ------------------------------------------------------------------------------------------------
+struct RicWork {
+  double *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *g;
+};
+
+OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
+  int nX = L.nX, nU = L.nU;
+  R.Q = w, w += nX * nX;
+  R.S = w, w += nU * nX;
+  R.R = w, w += nU * nU;
+  R.q = w, w += nX;
+  R.r = w, w += nU;
+  R.PA = w, w += nX * nX;
+  R.PB = w, w += nX * nU;
+  R.pc = w, w += nX;
+  R.F = w, w += nU * nU;
+  R.Gm = w, w += nU * (nX + 1);
+  R.g = w, w += nU;
+}
+
+OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R, int i, double hdtdt,
+                                     double* A, double* B, double* cvec) {
+  const int nX = L.nX, nU = L.nU, idt = 7 * L.V;
+  for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.Q[q] = 0, A[q] = 0;
+  for (int q = ctx.tid; q < nU * nX; q += ctx.nt) R.S[q] = 0, B[q] = 0;
+  for (int q = ctx.tid; q < nU * nU; q += ctx.nt) R.R[q] = 0;
+  for (int q = ctx.tid; q < nX; q += ctx.nt) R.q[q] = 0, cvec[q] = 0;
+  for (int q = ctx.tid; q < nU; q += ctx.nt) R.r[q] = 0;
+  cta_sync(ctx);
+  // own-vehicle blocks: one thread per vehicle (tiny)
+  for (int a = ctx.tid; a < L.V; a += ctx.nt) {
+    if (i >= L.N[a]) {
+      for (int j = 0; j < NP; ++j) R.R[(5 * a + j) * nU + 5 * a + j] = 1.0;
+      continue;
+    }
+    const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (91 + 13);
+    const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+    const double* s0 = T + NW * NRED;
+    int nr = (int)W.QR[(size_t)(a * L.Nmax + i) * (NW * NW + NW + 1) + NW * NW + NW];
+    int np = NW - nr;
+    for (int r = 0; r < 7; ++r) {
+      for (int cc = 0; cc < 7; ++cc) R.Q[(7 * a + r) * nX + 7 * a + cc] += Mo[sym(r, cc)];
+      R.Q[(7 * a + r) * nX + idt] += Mo[sym(12, r)];
+      R.Q[idt * nX + 7 * a + r] += Mo[sym(12, r)];
+      R.q[7 * a + r] += Mo[91 + r];
+      for (int cc = 0; cc < 7; ++cc) A[(7 * a + r) * nX + 7 * a + cc] = T[(28 + r) * NRED + cc];
+      A[(7 * a + r) * nX + idt] = T[(28 + r) * NRED + 12];
+      for (int j = 0; j < NP; ++j) B[(7 * a + r) * nU + 5 * a + j] = T[(28 + r) * NRED + 7 + j];
+      cvec[7 * a + r] = s0[28 + r];
+    }
+    for (int j = 0; j < NP; ++j) {
+      for (int cc = 0; cc < 7; ++cc) R.S[(5 * a + j) * nX + 7 * a + cc] += Mo[sym(7 + j, cc)];
+      R.S[(5 * a + j) * nX + idt] += Mo[sym(12, 7 + j)];
+      for (int jj = 0; jj < NP; ++jj) R.R[(5 * a + j) * nU + 5 * a + jj] += Mo[sym(7 + j, 7 + jj)];
+      if (j >= np) R.R[(5 * a + j) * nU + 5 * a + j] += 1.0;
+      R.r[5 * a + j] += Mo[91 + 7 + j];
+    }
+  }
+  cta_sync(ctx);
+  // dt diagonal + cross-vehicle terms: thread 0 (serialised to keep the sums deterministic)
+  if (ctx.tid == 0) {
+    A[idt * nX + idt] = 1.0;
+    double qdd = 0, qd = 0;
+    for (int a = 0; a < L.V; ++a) {
+      if (i >= L.N[a]) continue;
+      const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (91 + 13);
+      qdd += Mo[sym(12, 12)];
+      qd += Mo[91 + 12];
+    }
+    if (i == 0) qdd += hdtdt, qd += W.gphi[L.oDT];
+    for (int p = 0; p < L.P; ++p) {
+      if (i * NK >= L.Mp[p]) continue;
+      int a = L.pa[p], b = L.pb[p];
+      const double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (169 + 26);
+      for (int ra = 0; ra < NRED; ++ra)
+        for (int cb = 0; cb < NRED; ++cb) {
+          double v = Mo[ra * NRED + cb];
+          // ra in reduced coords of a, cb in reduced coords of b
+          int ia = ra < 7 ? 7 * a + ra : (ra < 12 ? -(5 * a + ra - 7) - 1 : idt);
+          int ib = cb < 7 ? 7 * b + cb : (cb < 12 ? -(5 * b + cb - 7) - 1 : idt);
+          if (ia >= 0 && ib >= 0) {
+            if (ia == idt && ib == idt) qdd += 2.0 * v;
+            else R.Q[ia * nX + ib] += v, R.Q[ib * nX + ia] += v;
+          } else if (ia < 0 && ib >= 0) R.S[(-ia - 1) * nX + ib] += v;
+          else if (ia >= 0 && ib < 0) R.S[(-ib - 1) * nX + ia] += v;
+          else R.R[(-ia - 1) * nU + (-ib - 1)] += v, R.R[(-ib - 1) * nU + (-ia - 1)] += v;
+        }
+      for (int ra = 0; ra < NRED; ++ra) {
+        double ga = Mo[169 + ra], gb = Mo[169 + 13 + ra];
+        if (ra < 7) R.q[7 * a + ra] += ga, R.q[7 * b + ra] += gb;
+        else if (ra < 12) R.r[5 * a + ra - 7] += ga, R.r[5 * b + ra - 7] += gb;
+        else qd += ga + gb;
+      }
+    }
+    R.Q[idt * nX + idt] += qdd;
+    R.q[idt] += qd;
+  }
+  cta_sync(ctx);
+}
+
+OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, double* RW, double hdtdt, int* ok) {
+  const int nX = L.nX, nU = L.nU;
+  RicWork R;
+  ric_carve(R, L, RW);
+  const size_t pstride = (size_t)nX * nX + nX, kstride = (size_t)nU * nX + nU, astride = (size_t)nX * nX + (size_t)nX * nU + nX;
+  double* Pn = W.RP + (size_t)L.Nmax * pstride;
+  for (int q = ctx.tid; q < (int)pstride; q += ctx.nt) Pn[q] = 0;
+  cta_sync(ctx);
+  for (int i = L.Nmax - 1; i >= 0; --i) {
+    double* A = W.RA + (size_t)i * astride;
+    double* B = A + nX * nX;
+    double* cv = B + nX * nU;
+    const double* P1 = W.RP + (size_t)(i + 1) * pstride;
+    const double* p1 = P1 + nX * nX;
+    double* P0 = W.RP + (size_t)i * pstride;
+    double* p0 = P0 + nX * nX;
+    double* Kg = W.RK + (size_t)i * kstride;
+    double* kg = Kg + nU * nX;
+    riccati_stage_assemble(ctx, L, W, R, i, hdtdt, A, B, cv);
+    // PA = P1 A ; PB = P1 B ; pc = P1 c + p1
+    for (int q = ctx.tid; q < nX * (nX + nU + 1); q += ctx.nt) {
+      int r = q / (nX + nU + 1), col = q % (nX + nU + 1);
+      double s = 0;
+      if (col < nX) {
+        for (int m = 0; m < nX; ++m) s += P1[r * nX + m] * A[m * nX + col];
+        R.PA[r * nX + col] = s;
+      } else if (col < nX + nU) {
+        int cc = col - nX;
+        for (int m = 0; m < nX; ++m) s += P1[r * nX + m] * B[m * nU + cc];
+        R.PB[r * nU + cc] = s;
+      } else {
+        for (int m = 0; m < nX; ++m) s += P1[r * nX + m] * cv[m];
+        R.pc[r] = s + p1[r];
+      }
+    }
+    cta_sync(ctx);
+    // F = R + B'PB ; Gm = [S + B'PA | r + B'pc]
+    for (int q = ctx.tid; q < nU * (nU + nX + 1); q += ctx.nt) {
+      int r = q / (nU + nX + 1), col = q % (nU + nX + 1);
+      double s = 0;
+      if (col < nU) {
+        for (int m = 0; m < nX; ++m) s += B[m * nU + r] * R.PB[m * nU + col];
+        R.F[r * nU + col] = R.R[r * nU + col] + s;
+      } else if (col < nU + nX) {
+        int cc = col - nU;
+        for (int m = 0; m < nX; ++m) s += B[m * nU + r] * R.PA[m * nX + cc];
+        R.Gm[r * (nX + 1) + cc] = R.S[r * nX + cc] + s;
+      } else {
+        for (int m = 0; m < nX; ++m) s += B[m * nU + r] * R.pc[m];
+        R.Gm[r * (nX + 1) + nX] = R.r[r] + s;
+      }
+    }
+    cta_sync(ctx);
+    // Cholesky of F (thread 0), in place, lower
+    if (ctx.tid == 0) {
+      for (int j = 0; j < nU; ++j) {
+        double d = R.F[j * nU + j];
+        for (int m = 0; m < j; ++m) d -= R.F[j * nU + m] * R.F[j * nU + m];
+        if (!(d > 1e-14 * fmax(1.0, fabs(R.F[j * nU + j])))) {
+          *ok = 0;
+          d = 1.0;
+        }
+        d = sqrt(d);
+        R.F[j * nU + j] = d;
+        for (int r = j + 1; r < nU; ++r) {
+          double v = R.F[r * nU + j];
+          for (int m = 0; m < j; ++m) v -= R.F[r * nU + m] * R.F[j * nU + m];
+          R.F[r * nU + j] = v / d;
+        }
+      }
+    }
+    cta_sync(ctx);
+    // [K | k] = -F^-1 Gm : one thread per column
+    for (int col = ctx.tid; col < nX + 1; col += ctx.nt) {
+      double tmp[NUMAX];
+      for (int r = 0; r < nU; ++r) {
+        double v = R.Gm[r * (nX + 1) + col];
+        for (int m = 0; m < r; ++m) v -= R.F[r * nU + m] * tmp[m];
+        tmp[r] = v / R.F[r * nU + r];
+      }
+      for (int r = nU - 1; r >= 0; --r) {
+        double v = tmp[r];
+        for (int m = r + 1; m < nU; ++m) v -= R.F[m * nU + r] * tmp[m];
+        tmp[r] = v / R.F[r * nU + r];
+      }
+      for (int r = 0; r < nU; ++r) {
+        if (col < nX) Kg[r * nX + col] = -tmp[r];
+        else kg[r] = -tmp[r];
+      }
+    }
+    cta_sync(ctx);
+    // P0 = Q + A'PA + Gm'K ; p0 = q + A'pc + Gm'k
+    for (int q = ctx.tid; q < nX * (nX + 1); q += ctx.nt) {
+      int r = q / (nX + 1), col = q % (nX + 1);
+      double s = 0;
+      if (col < nX) {
+        for (int m = 0; m < nX; ++m) s += A[m * nX + r] * R.PA[m * nX + col];
+        for (int m = 0; m < nU; ++m) s += R.Gm[m * (nX + 1) + r] * Kg[m * nX + col];
+        P0[r * nX + col] = R.Q[r * nX + col] + s;
+      } else {
+        for (int m = 0; m < nX; ++m) s += A[m * nX + r] * R.pc[m];
+        for (int m = 0; m < nU; ++m) s += R.Gm[m * (nX + 1) + r] * kg[m];
+        p0[r] = R.q[r] + s;
+      }
+    }
+    cta_sync(ctx);
+  }
+}
+
+OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, int* ok) {
+  const int nX = L.nX, nU = L.nU, idt = 7 * L.V;
+  const size_t pstride = (size_t)nX * nX + nX, kstride = (size_t)nU * nX + nU, astride = (size_t)nX * nX + (size_t)nX * nU + nX;
+  double* X = W.RX;
+  double* U = W.RX + (size_t)(L.Nmax + 1) * nX;
+  if (ctx.tid == 0) {
+    for (int a = 0; a < L.V; ++a)
+      for (int q = 0; q < NZ; ++q) X[7 * a + q] = -W.c[L.YINIT(a, q)];
+    const double* P0 = W.RP;
+    const double* p0 = P0 + nX * nX;
+    double s = p0[idt];
+    for (int m = 0; m < idt; ++m) s += P0[idt * nX + m] * X[m];
+    double piv = P0[idt * nX + idt];
+    if (!(piv > 1e-14)) {
+      *ok = 0;
+      piv = 1.0;
+    }
+    X[idt] = -s / piv;
+  }
+  cta_sync(ctx);
+  for (int i = 0; i < L.Nmax; ++i) {
+    const double* A = W.RA + (size_t)i * astride;
+    const double* B = A + nX * nX;
+    const double* cv = B + nX * nU;
+    const double* Kg = W.RK + (size_t)i * kstride;
+    const double* kg = Kg + nU * nX;
+    const double* Xi = X + (size_t)i * nX;
+    double* Ui = U + (size_t)i * nU;
+    double* Xn = X + (size_t)(i + 1) * nX;
+    for (int r = ctx.tid; r < nU; r += ctx.nt) {
+      double s = kg[r];
+      for (int m = 0; m < nX; ++m) s += Kg[r * nX + m] * Xi[m];
+      Ui[r] = s;
+    }
+    cta_sync(ctx);
+    for (int r = ctx.tid; r < nX; r += ctx.nt) {
+      double s = cv[r];
+      for (int m = 0; m < nX; ++m) s += A[r * nX + m] * Xi[m];
+      for (int m = 0; m < nU; ++m) s += B[r * nU + m] * Ui[m];
+      Xn[r] = s;
+    }
+    cta_sync(ctx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// [BACKSUB]
+// ------------------------------------------------------------------------------------------------
+OBCA_HDN void expand_primal(const Ctx& ctx, const Lay& L, const Scratch& W) {
+  const int nX = L.nX, nU = L.nU, idt = 7 * L.V;
+  const double* X = W.RX;
+  const double* U = W.RX + (size_t)(L.Nmax + 1) * nX;
+  const double ddt = X[idt];
+  for (int it = ctx.tid; it < L.V * L.Nmax; it += ctx.nt) {
+    int a = it / L.Nmax, i = it % L.Nmax;
+    if (i >= L.N[a]) continue;
+    const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+    const double* s0 = T + NW * NRED;
+    double rc[NRED];
+    for (int q = 0; q < 7; ++q) rc[q] = X[(size_t)i * nX + 7 * a + q];
+    for (int q = 0; q < NP; ++q) rc[7 + q] = U[(size_t)i * nU + 5 * a + q];
+    rc[12] = ddt;
+    for (int q = 0; q < NZ; ++q) W.dx[L.Z(a, q, i * NK)] = rc[q];
+    for (int r = 0; r < NW; ++r) {
+      double s = s0[r];
+      for (int q = 0; q < NRED; ++q) s += T[r * NRED + q] * rc[q];
+      W.dx[L.Z(a, r % NZ, i * NK + 1 + r / NZ)] = s;
+    }
+  }
+  if (ctx.tid == 0) W.dx[L.oDT] = ddt;
+}
+
+// GN <- gn + Hn dz + sum_pairs Hc dpose_other + hd ddt   (stationarity residual before the J'dy terms)
+OBCA_HDN void node_residual(const Ctx& ctx, const Lay& L, const Scratch& W) {
+  const double ddt = W.dx[L.oDT];
+  for (int it = ctx.tid; it < L.V * L.Mv; it += ctx.nt) {
+    int a = it / L.Mv, n = it % L.Mv;
+    if (n >= L.M[a]) continue;
+    const double* hn = W.HN + (size_t)(a * L.Mv + n) * 28;
+    double* gn = W.GN + (size_t)(a * L.Mv + n) * 7;
+    const double* hd = W.HD + (size_t)(a * L.Mv + n) * 7;
+    double dz[NZ], out[NZ];
+    for (int q = 0; q < NZ; ++q) dz[q] = W.dx[L.Z(a, q, n)];
+    for (int r = 0; r < NZ; ++r) {
+      double s = gn[r] + hd[r] * ddt;
+      for (int m = 0; m < NZ; ++m) s += hn[sym(r, m)] * dz[m];
+      out[r] = s;
+    }
+    for (int p = 0; p < L.P; ++p) {
+      if (n >= L.Mp[p]) continue;
+      const double* ph = W.PH + (size_t)(p * L.Mv + n) * 27;
+      if (L.pa[p] == a) {
+        int b = L.pb[p];
+        for (int r = 0; r < 3; ++r)
+          for (int m = 0; m < 3; ++m) out[r] += ph[sym(3 + m, r)] * W.dx[L.Z(b, m, n)];
+      } else if (L.pb[p] == a) {
+        int b = L.pa[p];
+        for (int r = 0; r < 3; ++r)
+          for (int m = 0; m < 3; ++m) out[r] += ph[sym(3 + r, m)] * W.dx[L.Z(b, m, n)];
+      }
+    }
+    for (int q = 0; q < NZ; ++q) gn[q] = out[q];
+  }
+}
+
+OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W) {
+  const int nX = L.nX;
+  const size_t pstride = (size_t)nX * nX + nX;
+  const double dt = W.x[L.oDT], idt = 1.0 / dt;
+  // continuity multipliers = costate of the Riccati recursion
+  for (int it = ctx.tid; it < L.V * L.Nmax; it += ctx.nt) {
+    int a = it / L.Nmax, i = it % L.Nmax;
+    if (i >= L.N[a] || i == 0) continue;
+    const double* P = W.RP + (size_t)i * pstride;
+    const double* pv = P + nX * nX;
+    const double* Xi = W.RX + (size_t)i * nX;
+    for (int q = 0; q < NZ; ++q) {
+      double s = pv[7 * a + q];
+      for (int m = 0; m < nX; ++m) s += P[(7 * a + q) * nX + m] * Xi[m];
+      W.dy[L.YCONT(a, q, i)] = s;
+    }
+  }
+  cta_sync(ctx);
+  for (int it = ctx.tid; it < L.V * L.Nmax; it += ctx.nt) {
+    int a = it / L.Nmax, i = it % L.Nmax;
+    if (i >= L.N[a]) continue;
+    int n0 = i * NK;
+    const double* QRm = W.QR + (size_t)(a * L.Nmax + i) * (NW * NW + NW + 1);
+    const double* tau = QRm + NW * NW;
+    int nr = (int)QRm[NW * NW + NW];
+    double v[NW];
+    for (int r = 0; r < NW; ++r) v[r] = -W.GN[(size_t)(a * L.Mv + n0 + 1 + r / NZ) * 7 + r % NZ];
+    if (i < L.N[a] - 1)
+      for (int q = 0; q < NZ; ++q) v[28 + q] -= W.dy[L.YCONT(a, q, i + 1)];
+    apply_q(QRm, tau, nr, v, true);
+    // R dy = v[0:nr]
+    for (int r = nr - 1; r >= 0; --r) {
+      double s = v[r];
+      for (int m = r + 1; m < nr; ++m) s -= QRm[r * NW + m] * v[m];
+      v[r] = s / QRm[r * NW + r];
+    }
+    for (int k = 0; k < NK; ++k)
+      for (int q = 0; q < 5; ++q) W.dy[L.YCOL(a, q, n0 + k)] = v[k * 5 + q];
+    if (i == L.N[a] - 1) {
+      int r = 30;
+      W.dy[L.YTERM(a, 0)] = L.heading[a] ? v[r++] : 0.0;
+      for (int m = 3; m < NZ; ++m) W.dy[L.YTERM(a, m - 2)] = v[r++];
+    }
+    if (i == 0) {
+      // node 0 of the first interval: gn0 + G0' dycol + dyinit = 0
+      double psi = W.x[L.Z(a, 2, 0)], vv = W.x[L.Z(a, 3, 0)], de = W.x[L.Z(a, 4, 0)];
+      double cs = cos(psi), sn = sin(psi), tde = tan(de), sec2 = 1.0 + tde * tde;
+      double gy[NZ] = {0, 0, 0, 0, 0, 0, 0};
+      for (int q = 0; q < 5; ++q)
+        for (int k = 0; k < NK; ++k) gy[q] += S.cA[0][k] * idt * v[k * 5 + q];
+      gy[2] -= v[0] * (-vv * sn) + v[1] * (vv * cs);
+      gy[3] -= v[0] * cs + v[1] * sn + v[2] * tde / S.wb;
+      gy[4] -= v[2] * vv * sec2 / S.wb;
+      gy[5] -= v[3];
+      gy[6] -= v[4];
+      for (int q = 0; q < NZ; ++q) W.dy[L.YINIT(a, q)] = -W.GN[(size_t)(a * L.Mv) * 7 + q] - gy[q];
+    }
+  }
+}
+
+OBCA_HDN void local_backsub(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W) {
+  for (int it = ctx.tid; it < L.V * L.Mv; it += ctx.nt) {
+    int a = it / L.Mv, n = it % L.Mv;
+    if (n >= L.M[a]) continue;
+    double dp[3] = {W.dx[L.Z(a, 0, n)], W.dx[L.Z(a, 1, n)], W.dx[L.Z(a, 2, n)]};
+    for (int j = 0; j < L.O; ++j) {
+      const double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 52;
+      double r[13];
+      for (int m = 0; m < 13; ++m) r[m] = xo[m * 4 + 3] - xo[m * 4 + 0] * dp[0] - xo[m * 4 + 1] * dp[1] - xo[m * 4 + 2] * dp[2];
+      for (int q = 0; q < 4; ++q) {
+        W.dx[L.LAM(a, j, q, n)] = r[q];
+        W.dx[L.MU(a, j, q, n)] = r[4 + q];
+        W.dy[L.YOBS(a, j, q, n)] = r[9 + q];
+      }
+      W.dx[L.SD(a, j, n)] = r[8];
+    }
+    int q = tube_set_at(L, a, n);
+    if (q >= 1) {
+      double psi = W.x[L.Z(a, 2, n)], cs = cos(psi), sn = sin(psi);
+      for (int r = 0; r < 8; ++r) {
+        const double* t = S.tube_row(L, a, q, r / 4, r % 4);
+        double gr[3] = {t[0], t[1], r < 4 ? 0.0 : S.wb * (-t[0] * sn + t[1] * cs)};
+        double dts = W.c[L.YTUBE(a, q - 1, r)] - (gr[0] * dp[0] + gr[1] * dp[1] + gr[2] * dp[2]);
+        W.dx[L.TS(a, q - 1, r)] = dts;
+        W.dy[L.YTUBE(a, q - 1, r)] = W.sig[L.TS(a, q - 1, r)] * dts + W.gphi[L.TS(a, q - 1, r)];
+      }
+    }
+  }
+  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
+    int p = it / L.Mv, n = it % L.Mv;
+    if (n >= L.Mp[p]) continue;
+    int a = L.pa[p], b = L.pb[p];
+    double dp[6] = {W.dx[L.Z(a, 0, n)], W.dx[L.Z(a, 1, n)], W.dx[L.Z(a, 2, n)], W.dx[L.Z(b, 0, n)], W.dx[L.Z(b, 1, n)], W.dx[L.Z(b, 2, n)]};
+    const double* xp = W.XP + (size_t)(p * L.Mv + n) * 126;
+    double r[18];
+    for (int m = 0; m < 18; ++m) {
+      double s = xp[m * 7 + 6];
+      for (int q = 0; q < 6; ++q) s -= xp[m * 7 + q] * dp[q];
+      r[m] = s;
+    }
+    for (int q = 0; q < 4; ++q) W.dx[L.PL(p, q, n)] = r[q], W.dx[L.PM(p, q, n)] = r[4 + q];
+    W.dx[L.PSD(p, n)] = r[8];
+    W.dx[L.PSN(p, n)] = r[9];
+    for (int q = 0; q < 6; ++q) W.dy[L.YPAIR(p, q, n)] = r[10 + q];
+    W.dx[L.PS(p, 0, n)] = r[16];
+    W.dx[L.PS(p, 1, n)] = r[17];
+  }
+}
+
+// Newton step at (W.x, W.y) for the right-hand side (W.gphi, W.c) and diagonal W.sig (Sigma + delta_w).
+// Returns ok = 1 when the inertia is correct.  All threads of the CTA must call it.
+OBCA_HDN int kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double* RW, int* ok_shared) {
+  if (ctx.tid == 0) *ok_shared = 1;
+  cta_sync(ctx);
+  pair_eliminate(ctx, L, S, W, ok_shared);
+  cta_sync(ctx);
+  double hdtdt;
+  node_assemble(ctx, L, S, W, ok_shared, &hdtdt);
+  cta_sync(ctx);
+  interval_nullspace(ctx, L, S, W, ok_shared);
+  cta_sync(ctx);
+  interval_cross(ctx, L, W);
+  cta_sync(ctx);
+  riccati_backward(ctx, L, W, RW, hdtdt, ok_shared);
+  cta_sync(ctx);
+  int ok = *ok_shared;
+  if (!ok) return 0;
+  riccati_forward(ctx, L, W, ok_shared);
+  cta_sync(ctx);
+  ok = *ok_shared;
+  if (!ok) return 0;
+  expand_primal(ctx, L, W);
+  cta_sync(ctx);
+  node_residual(ctx, L, W);
+  cta_sync(ctx);
+  recover_multipliers(ctx, L, S, W);
+  cta_sync(ctx);
+  local_backsub(ctx, L, S, W);
+  cta_sync(ctx);
+  return 1;
+}
+
+}  // namespace obca

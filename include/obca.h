@@ -1,0 +1,125 @@
+/*
+ * obca.h -- C ABI of the B200-native batched OBCA solver (libobca_b200.so).
+ *
+ * The reference (XuShenLZ/conflict_rez) has no FFI: its boundary is the CasADi ``Opti`` protocol used
+ * inside the planner classes.  Each entry point below names the reference call it replaces:
+ *
+ *   obca_create / obca_set_static   <- building the Opti graph: Vehicle.setup_single_final_problem
+ *                                      (confrez/control/vehicle.py:360-640) and the joint assembly in
+ *                                      MultiVehiclePlanner.solve_final_problem_obca
+ *                                      (confrez/control/multi_vehicle_planner.py:365-451)
+ *   obca_set_init_pose              <- the initial-state equalities (vehicle.py:424-434) per instance
+ *   obca_set_initial                <- opti.set_initial(...) (vehicle.py:482-485,629-636;
+ *                                      multi_vehicle_planner.py:367,426-428)
+ *   obca_solve                      <- opti.solver("ipopt", ...); opti.solve()
+ *                                      (vehicle.py:657-658; multi_vehicle_planner.py:464-465)
+ *   obca_get_solution               <- sol.value(...) (vehicle.py:668-716)
+ *   obca_get_stats                  <- sol.stats()["return_status"] (vehicle.py:659)
+ *
+ * Conventions: every array is FP64, C-contiguous; "dev" pointers are device pointers owned by the
+ * caller (torch tensors in the Python host layer), "host" pointers are plain host memory.  All calls
+ * return 0 on success and a negative code on error (obca_last_error() gives the text).  No exception
+ * crosses the ABI, there is no CPU fallback: obca_create fails when no CUDA device is usable.
+ * A handle is not thread-safe; different handles may be used concurrently.
+ */
+#ifndef OBCA_H_
+#define OBCA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBCA_MAX_V 8      /* vehicles per instance */
+#define OBCA_MAX_O 32     /* obstacles (4 half-planes each) */
+#define OBCA_MAX_SETS 64  /* strategy sets per vehicle */
+
+/* per-instance return status, mirroring IPOPT's ApplicationReturnStatus strings */
+#define OBCA_SOLVE_SUCCEEDED 0
+#define OBCA_MAXITER_EXCEEDED (-1)
+#define OBCA_RESTORATION_FAILED (-2)
+#define OBCA_ERROR_IN_STEP_COMPUTATION (-3)
+#define OBCA_INVALID_NUMBER_DETECTED (-4)
+#define OBCA_NOT_SOLVED (-100)
+
+typedef struct ObcaDims {
+  int32_t batch;                 /* B: independent instances */
+  int32_t V;                     /* vehicles per instance */
+  int32_t O;                     /* obstacles */
+  int32_t K;                     /* collocation degree (must be 5) */
+  int32_t n_per_set;             /* collocation intervals per strategy move (must be >= 1) */
+  int32_t n_sets[OBCA_MAX_V];    /* S_a: strategy sets of vehicle a; N_a = n_per_set * (S_a - 1) */
+} ObcaDims;
+
+typedef struct ObcaOptions {
+  double tol, constr_viol_tol, dual_inf_tol, compl_inf_tol;
+  double mu_init;
+  double dmin, shrink_tube;
+  int32_t max_iter;
+  int32_t reserved;
+} ObcaOptions;
+
+typedef struct ObcaStatic {       /* host pointers; copied by obca_set_static */
+  const double* obs_A;           /* (O,4,2) */
+  const double* obs_b;           /* (O,4) */
+  const double* tube_A;          /* (V,Smax,2[back,front],4,2), Smax = max n_sets */
+  const double* tube_b;          /* (V,Smax,2,4) raw b (shrink_tube is subtracted inside) */
+  const double* body_G;          /* (4,2) */
+  const double* body_g;          /* (4) */
+  const double* region;          /* xmin,xmax,ymin,ymax */
+  const double* limits;          /* v,delta,a,w (min,max) */
+  const double* final_heading;   /* (V) NaN = unconstrained */
+  double wb;
+} ObcaStatic;
+
+typedef struct ObcaHandle ObcaHandle;
+
+const char* obca_version(void);
+const char* obca_last_error(void);
+void obca_default_options(ObcaOptions* opts);
+
+int obca_create(const ObcaDims* dims, const ObcaOptions* opts, int device, ObcaHandle** out);
+int obca_destroy(ObcaHandle* h);
+int obca_set_static(ObcaHandle* h, const ObcaStatic* st);
+int obca_set_options(ObcaHandle* h, const ObcaOptions* opts);
+
+/* dev: (B,V,3) x,y,psi including the initial offsets */
+int obca_set_init_pose(ObcaHandle* h, const double* init_pose_dev, void* stream);
+
+/* dev, node-major like CollocationGuess: z (B,V,Mmax,7); lam, mu (B,V,Mmax,O,4); dt (B);
+ * pair_lam, pair_mu (B,P,Mmax,4); pair_s (B,P,Mmax,2) -- pair pointers may be NULL when V == 1. */
+int obca_set_initial(ObcaHandle* h, const double* z, const double* lam, const double* mu, const double* dt,
+                     const double* pair_lam, const double* pair_mu, const double* pair_s, void* stream);
+
+/* run the batched interior-point solve, asynchronously on `stream`; no host sync inside */
+int obca_solve(ObcaHandle* h, void* stream);
+
+/* same shapes as obca_set_initial, dev pointers, any may be NULL */
+int obca_get_solution(ObcaHandle* h, double* z, double* lam, double* mu, double* dt, double* pair_lam,
+                      double* pair_mu, double* pair_s, void* stream);
+
+/* dev pointers (B): any may be NULL */
+int obca_get_stats(ObcaHandle* h, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf,
+                   double* compl_inf, void* stream);
+
+/* number of kernels this handle has launched so far (bench.py "gpu_launches") */
+int64_t obca_launch_count(const ObcaHandle* h);
+
+/* ---- introspection used by the parity tests (tests/ only) ------------------------------------ */
+/* internal flat layout: fills out[0..n) with the offsets/sizes documented in obca_core.h (Lay) */
+int obca_layout(const ObcaHandle* h, int64_t* out, int n);
+/* raw internal vectors of instance b, copied to HOST buffers (NULL = skip):
+ * x (nx), y (ny), zL (nx), zU (nx) */
+int obca_debug_get_iterate(ObcaHandle* h, int b, double* x, double* y, double* zL, double* zU);
+int obca_debug_set_iterate(ObcaHandle* h, int b, const double* x, const double* y, const double* zL, const double* zU);
+/* evaluate at the stored iterate of instance b: c (ny), gl = grad f + J'y (nx), f -> host */
+int obca_debug_eval(ObcaHandle* h, int b, double* c, double* gl, double* f);
+/* Newton step at the stored iterate for barrier mu and regularisation delta_w: dx (nx), dy (ny) -> host;
+ * returns 1 in *ok when the reduced Hessian was positive definite */
+int obca_debug_step(ObcaHandle* h, int b, double mu, double delta_w, double* dx, double* dy, int32_t* ok);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBCA_H_ */

@@ -93,8 +93,9 @@ def cost_block():
 def obs_block(h=4):
     """Obstacle triple at one node.
 
-    locals: x, y, psi, lam[h], mu[4], sd;  params: A (h x 2 row-major), b (h), G (4 x 2), g (4), dmin.
-      c1: -g'mu + (A t - b)'lam - dmin - sd = 0     (reference: >= dmin)
+    locals: x, y, psi, lam[h], mu[4], sd, el;  params: A (h x 2 row-major), b (h), G (4 x 2), g (4), dmin.
+      c1: -g'mu + (A t - b)'lam - dmin - sd + el = 0     (reference: >= dmin; el >= 0 is the elastic
+          variable of the exact l1 penalty, see DESIGN.md "elastic inequality rows")
       c2:  G'mu + R(psi)' A' lam = 0               (2 rows)
       c3:  |A' lam|^2 - 1 = 0
     """
@@ -103,19 +104,19 @@ def obs_block(h=4):
         x, y, psi = sp.symbols("x y psi")
         lam = sp.Matrix(sp.symbols("l0:%d" % h))
         mu = sp.Matrix(sp.symbols("m0:4"))
-        sd = sp.Symbol("sd")
+        sd, el = sp.symbols("sd el")
         A = sp.Matrix(h, 2, sp.symbols("A0:%d" % (2 * h)))
         b = sp.Matrix(sp.symbols("b0:%d" % h))
         G = sp.Matrix(4, 2, sp.symbols("G0:8"))
         g = sp.Matrix(sp.symbols("g0:4"))
         dmin = sp.Symbol("dmin")
         t = sp.Matrix([x, y])
-        c1 = (-g.T * mu)[0] + ((A * t - b).T * lam)[0] - dmin - sd
+        c1 = (-g.T * mu)[0] + ((A * t - b).T * lam)[0] - dmin - sd + el
         c2 = G.T * mu + _rot(psi).T * A.T * lam
         Atl = A.T * lam
         c3 = (Atl.T * Atl)[0] - 1
         _CACHE[key] = Block(
-            "obs", [c1, c2[0], c2[1], c3], [x, y, psi] + list(lam) + list(mu) + [sd], list(A) + list(b) + list(G) + list(g) + [dmin]
+            "obs", [c1, c2[0], c2[1], c3], [x, y, psi] + list(lam) + list(mu) + [sd, el], list(A) + list(b) + list(G) + list(g) + [dmin]
         )
     return _CACHE[key]
 
@@ -168,10 +169,10 @@ def tubeF_block(K=5):
 def pair_block(other_is_param=False):
     """Vehicle-vehicle block at one node (multi_vehicle_planner.py:419-451; vehicle_follower.py:322-352).
 
-    locals: (x,y,psi)_a, [(x,y,psi)_b unless parameters], lam[4], mu[4], s[2], sd, sn
+    locals: (x,y,psi)_a, [(x,y,psi)_b unless parameters], lam[4], mu[4], s[2], sd, sn, el
     params: G(8), g(4), dmin [, (x,y,psi)_b]
       A_i = G R(-psi_i),  b_i = G R(-psi_i) t_i + g
-      d : -b_a'lam - b_b'mu - dmin - sd = 0
+      d : -b_a'lam - b_b'mu - dmin - sd + el = 0   (el >= 0 elastic, as in obs_block)
       e1: A_a'lam + s = 0 (2);  e2: A_b'mu - s = 0 (2)
       n : 1 - s's - sn = 0
     """
@@ -182,7 +183,7 @@ def pair_block(other_is_param=False):
         lam = sp.Matrix(sp.symbols("l0:4"))
         mu = sp.Matrix(sp.symbols("m0:4"))
         s = sp.Matrix(sp.symbols("s0:2"))
-        sd, sn = sp.symbols("sd sn")
+        sd, sn, el = sp.symbols("sd sn el")
         G = sp.Matrix(4, 2, sp.symbols("G0:8"))
         g = sp.Matrix(sp.symbols("g0:4"))
         dmin = sp.Symbol("dmin")
@@ -193,11 +194,11 @@ def pair_block(other_is_param=False):
 
         Aa, ba = Ab(pa)
         Abb, bb = Ab(pb)
-        d = -(ba.T * lam)[0] - (bb.T * mu)[0] - dmin - sd
+        d = -(ba.T * lam)[0] - (bb.T * mu)[0] - dmin - sd + el
         e1 = Aa.T * lam + s
         e2 = Abb.T * mu - s
         n = 1 - (s.T * s)[0] - sn
-        loc = list(pa) + ([] if other_is_param else list(pb)) + list(lam) + list(mu) + list(s) + [sd, sn]
+        loc = list(pa) + ([] if other_is_param else list(pb)) + list(lam) + list(mu) + list(s) + [sd, sn, el]
         par = list(G) + list(g) + [dmin] + (list(pb) if other_is_param else [])
         _CACHE[key] = Block("pair", [d, e1[0], e1[1], e2[0], e2[1], n], loc, par)
     return _CACHE[key]

@@ -15,7 +15,7 @@ Differences from stock IPOPT (both sides of the parity test share them):
   * y0 = 0 (no least-squares multiplier estimate), no second-order correction, no restoration phase
     (a failed line search returns status ``Restoration_Failed``);
   * the Hessian uses clipped multipliers on the two norm rows (nlp.hess(clip=True));
-  * delta_c = 1e-10 on the obstacle / pair rows only.
+  * delta_c = 1e-10 on the obstacle / pair rows, 1e-9 on all other rows (always on).
 """
 from dataclasses import dataclass, field
 
@@ -64,6 +64,7 @@ class IpmOptions:
     kappa_w_plus: float = 8.0
     kappa_w_plus_first: float = 100.0
     delta_c_local: float = 1e-10
+    delta_c_global: float = 1e-9
     verbose: int = 0
 
 
@@ -107,7 +108,9 @@ class KktSolver:
 
     def __init__(self, nlp, opts):
         self.nlp, self.opts = nlp, opts
-        dc = np.zeros(nlp.m)
+        # tiny delta_c everywhere keeps the augmented system non-singular where LICQ fails (stationary vehicle:
+        # the over-collocated rows become dependent); the CUDA path drops the dependent rows instead
+        dc = np.full(nlp.m, opts.delta_c_global)
         for name in ("r_obs", "r_pair"):
             for r in getattr(nlp, name, []):
                 dc[np.ravel(r)] = opts.delta_c_local

@@ -38,8 +38,9 @@ class _Alloc:
 
 
 class CollocationNLP:
-    def __init__(self, prob):
+    def __init__(self, prob, rho=1e3):
         p = self.prob = prob
+        self.rho = float(rho)  # weight of the exact l1 penalty on the elastic variables
         assert p.batch is None, "the oracle works on one instance; use prob.instance(b)"
         K = self.K = p.K
         V, O = p.V, p.O
@@ -55,12 +56,14 @@ class CollocationNLP:
         self.ilam = [va.take(self.M[a], O, 4) for a in range(V)]
         self.imu = [va.take(self.M[a], O, 4) for a in range(V)]
         self.isd = [va.take(self.M[a], O) for a in range(V)]
+        self.iel = [va.take(self.M[a], O) for a in range(V)]
         self.its = [va.take(int(p.n_sets[a]) - 1, 8) for a in range(V)]
         self.ipl = [va.take(m, 4) for m in self.Mp]
         self.ipm = [va.take(m, 4) for m in self.Mp]
         self.ips = [va.take(m, 2) for m in self.Mp]
         self.ipsd = [va.take(m) for m in self.Mp]
         self.ipsn = [va.take(m) for m in self.Mp]
+        self.ipel = [va.take(m) for m in self.Mp]
         self.idt = int(va.take())
         self.n = va.n
 
@@ -71,10 +74,10 @@ class CollocationNLP:
         for a in range(V):
             xL[self.iz[a]] = lo
             xU[self.iz[a]] = hi
-            for arr in (self.ilam[a], self.imu[a], self.isd[a], self.its[a]):
+            for arr in (self.ilam[a], self.imu[a], self.isd[a], self.iel[a], self.its[a]):
                 xL[arr] = 0.0
         for q in range(len(self.pairs)):
-            for arr in (self.ipl[q], self.ipm[q], self.ipsd[q], self.ipsn[q]):
+            for arr in (self.ipl[q], self.ipm[q], self.ipsd[q], self.ipsn[q], self.ipel[q]):
                 xL[arr] = 0.0
         self.xL, self.xU = xL, xU
 
@@ -149,7 +152,7 @@ class CollocationNLP:
             self.blks.append((blocks.cost_block(), loc, None, par))
             # obstacles (vehicle.py:524-541)
             for j in range(O):
-                loc = np.concatenate([iz[:, :3], self.ilam[a][:, j], self.imu[a][:, j], self.isd[a][:, j : j + 1]], axis=1)
+                loc = np.concatenate([iz[:, :3], self.ilam[a][:, j], self.imu[a][:, j], self.isd[a][:, j : j + 1], self.iel[a][:, j : j + 1]], axis=1)
                 par = np.tile(np.concatenate([p.obs_A[j].ravel(), p.obs_b[j], p.body_G.ravel(), p.body_g, [p.dmin]]), (M, 1))
                 self.blks.append((blocks.obs_block(), loc, self.r_obs[a][:, j], par))
             # tube sets at set transitions (vehicle.py:570-584): q = 1..S-2 at node (q*n_per_set, 0)
@@ -168,7 +171,7 @@ class CollocationNLP:
         for q, (a, b) in enumerate(self.pairs):
             m = self.Mp[q]
             loc = np.concatenate(
-                [self.iz[a][:m, :3], self.iz[b][:m, :3], self.ipl[q], self.ipm[q], self.ips[q], self.ipsd[q][:, None], self.ipsn[q][:, None]], axis=1
+                [self.iz[a][:m, :3], self.iz[b][:m, :3], self.ipl[q], self.ipm[q], self.ips[q], self.ipsd[q][:, None], self.ipsn[q][:, None], self.ipel[q][:, None]], axis=1
             )
             par = np.tile(np.concatenate([p.body_G.ravel(), p.body_g, [p.dmin]]), (m, 1))
             self.blks.append((blocks.pair_block(), loc, self.r_pair[q], par))
@@ -179,8 +182,12 @@ class CollocationNLP:
         self.clip_neg = np.concatenate([r[:, 5].ravel() for r in self.r_pair]) if self.pairs else np.zeros(0, dtype=int)
 
     # ------------------------------------------------------------------ evaluation
+    def _elastic_index(self):
+        return np.concatenate([a.ravel() for a in self.iel] + [a.ravel() for a in self.ipel])
+
     def f(self, x):
         tot = sum((self.N[a] * x[self.idt]) ** 2 for a in range(self.prob.V))
+        tot += self.rho * x[self._elastic_index()].sum()
         for blk, loc, rows, par in self.blks:
             if rows is None:
                 tot += blk.c(x[loc].T, par.T).sum()
@@ -188,6 +195,7 @@ class CollocationNLP:
 
     def grad_f(self, x):
         g = np.zeros(self.n)
+        g[self._elastic_index()] = self.rho
         g[self.idt] += sum(2 * self.N[a] ** 2 * x[self.idt] for a in range(self.prob.V))
         for blk, loc, rows, par in self.blks:
             if rows is None:
@@ -264,11 +272,19 @@ class CollocationNLP:
         return np.concatenate(idx), np.concatenate(rows)
 
     def init_slacks(self, x):
-        """Set every slack to the value of its inequality body (IPOPT: s0 = g(x0))."""
+        """Set every slack to the value of its inequality body (IPOPT: s0 = g(x0)); on elastic rows the
+        negative part of the body goes to the elastic variable so that the row starts feasible."""
         x = x.copy()
         idx, rows = self.slack_index()
+        el = self._elastic_index()
         x[idx] = 0.0
-        x[idx] = self.c(x)[rows]
+        x[el] = 0.0
+        body = self.c(x)
+        x[idx] = body[rows]
+        erow = np.concatenate([self.r_obs[a][:, :, 0].ravel() for a in range(self.prob.V)] + [r[:, 0] for r in self.r_pair])
+        eslk = np.concatenate([self.isd[a].ravel() for a in range(self.prob.V)] + [i for i in self.ipsd])
+        x[eslk] = np.maximum(body[erow], 0.0)
+        x[el] = np.maximum(-body[erow], 0.0)
         return x
 
     def unpack(self, x):
