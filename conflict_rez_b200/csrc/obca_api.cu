@@ -28,7 +28,7 @@ static int fail(const std::string& msg) {
 struct ObcaHandle {
   ObcaDims dims;
   Opts opts;
-  double dmin, shrink;
+  double dmin, shrink, rho;
   Lay L;
   Stat S;
   Counts cnt;
@@ -269,13 +269,13 @@ const char* obca_last_error(void) { return g_err.c_str(); }
 
 void obca_default_options(ObcaOptions* o) {
   o->tol = 1e-2, o->constr_viol_tol = 1e-2, o->dual_inf_tol = 1.0, o->compl_inf_tol = 1e-4;
-  o->mu_init = 0.1, o->dmin = 0.05, o->shrink_tube = 0.5, o->max_iter = 3000, o->reserved = 0;
+  o->mu_init = 0.1, o->dmin = 0.05, o->shrink_tube = 0.5, o->elastic_weight = 1e3, o->max_iter = 3000, o->reserved = 0;
 }
 
 static void apply_options(ObcaHandle* h, const ObcaOptions* o) {
   h->opts.tol = o->tol, h->opts.constr_viol_tol = o->constr_viol_tol, h->opts.dual_inf_tol = o->dual_inf_tol;
   h->opts.compl_inf_tol = o->compl_inf_tol, h->opts.mu_init = o->mu_init, h->opts.max_iter = o->max_iter;
-  h->dmin = o->dmin, h->shrink = o->shrink_tube;
+  h->dmin = o->dmin, h->shrink = o->shrink_tube, h->rho = o->elastic_weight;
 }
 
 int obca_create(const ObcaDims* dims, const ObcaOptions* opts, int device, ObcaHandle** out) {
@@ -306,8 +306,8 @@ int obca_create(const ObcaDims* dims, const ObcaOptions* opts, int device, ObcaH
 
 int obca_set_options(ObcaHandle* h, const ObcaOptions* opts) {
   if (!h || !opts) return fail("obca_set_options: null argument");
-  bool geom = h->have_static && (opts->dmin != h->dmin || opts->shrink_tube != h->shrink);
-  if (geom) return fail("obca_set_options: dmin / shrink_tube must be set before obca_set_static");
+  bool geom = h->have_static && (opts->dmin != h->dmin || opts->shrink_tube != h->shrink || opts->elastic_weight != h->rho);
+  if (geom) return fail("obca_set_options: dmin / shrink_tube / elastic_weight must be set before obca_set_static");
   apply_options(h, opts);
   return 0;
 }
@@ -366,7 +366,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
       S.obsb[j][r] = st->obs_b[j * 4 + r];
     }
   for (int r = 0; r < 4; ++r) S.G[r][0] = st->body_G[2 * r], S.G[r][1] = st->body_G[2 * r + 1], S.g[r] = st->body_g[r];
-  S.wb = st->wb, S.dmin = h->dmin;
+  S.wb = st->wb, S.dmin = h->dmin, S.rho = h->rho;
   for (int q = 0; q < 4; ++q) S.region[q] = st->region[q];
   for (int q = 0; q < 8; ++q) S.limits[q] = st->limits[q];
   for (int a = 0; a < L.V; ++a) S.heading[a] = st->final_heading[a];
@@ -390,7 +390,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
       for (int c = 0; c < NZ; ++c) xL[L.Z(a, c, n)] = lo[c], xU[L.Z(a, c, n)] = hi[c];
       for (int j = 0; j < L.O; ++j) {
         for (int r = 0; r < 4; ++r) xL[L.LAM(a, j, r, n)] = 0, xL[L.MU(a, j, r, n)] = 0;
-        xL[L.SD(a, j, n)] = 0;
+        xL[L.SD(a, j, n)] = 0, xL[L.EL(a, j, n)] = 0;
       }
     }
     for (int q = 0; q < L.S[a] - 1; ++q)
@@ -400,7 +400,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   for (int p = 0; p < L.P; ++p) {
     for (int n = 0; n < L.Mp[p]; ++n) {
       for (int r = 0; r < 4; ++r) xL[L.PL(p, r, n)] = 0, xL[L.PM(p, r, n)] = 0;
-      xL[L.PSD(p, n)] = 0, xL[L.PSN(p, n)] = 0;
+      xL[L.PSD(p, n)] = 0, xL[L.PSN(p, n)] = 0, xL[L.PEL(p, n)] = 0;
     }
     m_active += 6 * L.Mp[p];
   }
@@ -548,7 +548,7 @@ int obca_layout(const ObcaHandle* h, int64_t* out, int n) {
   if (!h || !h->have_static) return fail("obca_layout: call obca_set_static first");
   const Lay& L = h->L;
   const int64_t v[] = {L.V,    L.O,    L.P,    L.Mv,     L.Nmax,  L.Smax,   L.nx,     L.ny,    L.oZ,     L.oLAM,  L.oMU,
-                       L.oSD,  L.oTS,  L.oPL,  L.oPM,    L.oPS,   L.oPSD,   L.oPSN,   L.oDT,   L.oYINIT, L.oYCOL, L.oYCONT,
+                       L.oSD,  L.oEL,  L.oTS,  L.oPL,  L.oPM,    L.oPS,   L.oPSD,   L.oPSN,   L.oPEL,  L.oDT,   L.oYINIT, L.oYCOL, L.oYCONT,
                        L.oYTERM, L.oYOBS, L.oYTUBE, L.oYPAIR, h->cnt.m_active, h->cnt.nb};
   int cntv = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < cntv; ++i) out[i] = v[i];

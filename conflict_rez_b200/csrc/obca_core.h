@@ -34,12 +34,23 @@ constexpr int NK = 6;    // nodes per interval (K + 1)
 constexpr int NZ = 7;    // x y psi v delta a w
 constexpr int NS = 42;   // stage variables of one vehicle interval
 constexpr int NW = 35;   // stage variables without node 0
-constexpr int NRED = 13; // reduced coordinates: xi(7) p(5) dt(1)
-constexpr int NP = 5;    // free directions per vehicle interval
+constexpr int NP = 8;    // max free directions per vehicle interval (5 when the collocation Jacobian has full rank)
+constexpr int NRED = 7 + NP + 1;  // reduced coordinates: xi(7) p(NP) dt(1)
+constexpr int IDT = 7 + NP;       // index of dt in the reduced coordinates
+constexpr int NSYM = NRED * (NRED + 1) / 2;
+constexpr int NEX = 5;                 // max implied state-constraint rows handed to the previous interval
+constexpr int NC = 30 + 5 + NEX;       // max constraint rows of one (vehicle, interval) block
+constexpr int NDR = 8;                 // max dropped (dependent) rows recorded per block
+constexpr int EXSZ = 1 + NEX * 9;      // emitted rows: count, then (h_xi[7], h_dt, h0) each
+// QR record: [35*NC] reflectors / R staircase, [35] tau, [35] pivot column of each staircase row,
+// [4] (rank, rows, ndrop, unused), then NDR x (column j, emission slot or -1, staircase length, alpha[35], implied row h[9]), then nu[NEX]
+constexpr int QR_TAU = 35 * NC, QR_PIV = QR_TAU + 35, QR_META = QR_PIV + 35, QR_DROP = QR_META + 4, DRSZ = 3 + 35 + 9;
+constexpr int QR_NU = QR_DROP + NDR * DRSZ;  // multipliers of the received implied rows
+constexpr int QRSZ = QR_NU + NEX;
 constexpr int MAXV = OBCA_MAX_V;
 constexpr int MAXP = MAXV * (MAXV - 1) / 2;
 constexpr int NXMAX = 7 * MAXV + 1;
-constexpr int NUMAX = 5 * MAXV;
+constexpr int NUMAX = NP * MAXV;
 constexpr int FILTER_MAX = 64;
 constexpr double DELTA_C_LOCAL = 1e-10;
 
@@ -51,7 +62,7 @@ struct Lay {
   int N[MAXV], M[MAXV], S[MAXV], heading[MAXV];
   int pa[MAXP], pb[MAXP], Mp[MAXP];
   // primal fields
-  int oZ, oLAM, oMU, oSD, oTS, oPL, oPM, oPS, oPSD, oPSN, oDT, nx;
+  int oZ, oLAM, oMU, oSD, oEL, oTS, oPL, oPM, oPS, oPSD, oPSN, oPEL, oDT, nx;
   // multiplier / residual fields
   int oYINIT, oYCOL, oYCONT, oYTERM, oYOBS, oYTUBE, oYPAIR, ny;
   // Riccati sizes
@@ -61,12 +72,14 @@ struct Lay {
   OBCA_HD int LAM(int a, int j, int r, int n) const { return oLAM + ((a * O + j) * 4 + r) * Mv + n; }
   OBCA_HD int MU(int a, int j, int r, int n) const { return oMU + ((a * O + j) * 4 + r) * Mv + n; }
   OBCA_HD int SD(int a, int j, int n) const { return oSD + (a * O + j) * Mv + n; }
+  OBCA_HD int EL(int a, int j, int n) const { return oEL + (a * O + j) * Mv + n; }
   OBCA_HD int TS(int a, int q, int r) const { return oTS + (a * (Smax - 1) + q) * 8 + r; }
   OBCA_HD int PL(int p, int r, int n) const { return oPL + (p * 4 + r) * Mv + n; }
   OBCA_HD int PM(int p, int r, int n) const { return oPM + (p * 4 + r) * Mv + n; }
   OBCA_HD int PS(int p, int r, int n) const { return oPS + (p * 2 + r) * Mv + n; }
   OBCA_HD int PSD(int p, int n) const { return oPSD + p * Mv + n; }
   OBCA_HD int PSN(int p, int n) const { return oPSN + p * Mv + n; }
+  OBCA_HD int PEL(int p, int n) const { return oPEL + p * Mv + n; }
   OBCA_HD int YINIT(int a, int c) const { return oYINIT + a * NZ + c; }
   OBCA_HD int YCOL(int a, int c, int n) const { return oYCOL + (a * 5 + c) * Mv + n; }
   OBCA_HD int YCONT(int a, int c, int i) const { return oYCONT + (a * NZ + c) * Nmax + i; }
@@ -105,12 +118,14 @@ inline void lay_build(Lay& L, const ObcaDims& d, const double* final_heading) {
   L.oLAM = o, o += L.V * L.O * 4 * L.Mv;
   L.oMU = o, o += L.V * L.O * 4 * L.Mv;
   L.oSD = o, o += L.V * L.O * L.Mv;
+  L.oEL = o, o += L.V * L.O * L.Mv;
   L.oTS = o, o += L.V * (L.Smax - 1) * 8;
   L.oPL = o, o += L.P * 4 * L.Mv;
   L.oPM = o, o += L.P * 4 * L.Mv;
   L.oPS = o, o += L.P * 2 * L.Mv;
   L.oPSD = o, o += L.P * L.Mv;
   L.oPSN = o, o += L.P * L.Mv;
+  L.oPEL = o, o += L.P * L.Mv;
   L.oDT = o, o += 1;
   L.nx = o;
   o = 0;
@@ -123,14 +138,14 @@ inline void lay_build(Lay& L, const ObcaDims& d, const double* final_heading) {
   L.oYPAIR = o, o += L.P * 6 * L.Mv;
   L.ny = o;
   L.nX = 7 * L.V + 1;
-  L.nU = 5 * L.V;
+  L.nU = NP * L.V;
 }
 
 // batch-invariant problem data
 struct Stat {
   double obsA[OBCA_MAX_O][4][2], obsb[OBCA_MAX_O][4];
   double G[4][2], g[4];
-  double wb, dmin;
+  double wb, dmin, rho;
   double region[4], limits[8];
   double heading[MAXV];
   double cA[NK][NK], cB[NK];  // collocation matrices: cA[j][k] = L_j'(tau_k), cB[k] quadrature weights
@@ -159,15 +174,17 @@ struct Scratch {
   // y-layout vectors
   double *y, *dy, *c, *ct;
   // structured solve
-  double* XO;   // [V][Mv][O][52]   obstacle block solves: 13 x (3 coupling cols + 1 rhs)
-  double* XP;   // [P][Mv][126]     pair block solves: 18 x (6 + 1)
+  double* XO;   // [V][Mv][O][48]   obstacle block solves: 12 x (3 coupling cols + 1 rhs)
+  double* XP;   // [P][Mv][112]     pair block solves: 16 x (6 + 1)
   double* PH;   // [P][Mv][27]      pair Schur complement on (pose_a, pose_b): 21 sym + 6 grad
   double* PG;   // [P][2][3][Mv]    pair contributions to the pose gradient (gl)
   double* HN;   // [V][Mv][28]      node Hessian (sym packed)
   double* GN;   // [V][Mv][7]       node gradient
   double* HD;   // [V][Mv][7]       node x dt cross Hessian
   double* TT;   // [V][Nmax][35*13 + 35]   reduced-coordinate map T and particular solution s0
-  double* QR;   // [V][Nmax][35*35 + 35 + 1]   Householder factors, tau, row count
+  double* QR;   // [V][Nmax][QRSZ]   Householder factors, tau, pivots, dropped-row records
+  double* EM;   // [2][V][Nmax][EXSZ] implied rows emitted to the previous interval (double-buffered by pass)
+  double* DF;   // [2][V][Nmax] dirty flags (double-buffered by pass)
   double* MA;   // [V][Nmax][91 + 13]      projected stage Hessian (sym packed 13x13) + gradient
   double* MAB;  // [P][Nmax][169 + 26]     projected cross-vehicle coupling + gradients
   double* RK;   // [Nmax][nU*nX + nU]      Riccati gains
@@ -185,11 +202,11 @@ inline size_t iterate_doubles(const Lay& L) { return 3 * (size_t)L.nx + (size_t)
 inline size_t work_doubles(const Lay& L) {
   size_t n = 0;
   n += 7 * (size_t)L.nx + 3 * (size_t)L.ny;
-  n += (size_t)L.V * L.Mv * L.O * 52;
-  n += (size_t)L.P * L.Mv * (126 + 27 + 6);
+  n += (size_t)L.V * L.Mv * L.O * 48;
+  n += (size_t)L.P * L.Mv * (112 + 27 + 6);
   n += (size_t)L.V * L.Mv * (28 + 7 + 7);
-  n += (size_t)L.V * L.Nmax * ((NW * NRED + NW) + (NW * NW + NW + 1) + (91 + 13) + NS);
-  n += (size_t)L.P * L.Nmax * (169 + 26);
+  n += (size_t)L.V * L.Nmax * ((NW * NRED + NW) + QRSZ + (NSYM + NRED) + NS + 2 * EXSZ + 2);
+  n += (size_t)L.P * L.Nmax * (NRED * NRED + 2 * NRED);
   n += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
   n += (size_t)(L.Nmax + 1) * (L.nX * L.nX + L.nX);
   n += (size_t)L.Nmax * (L.nX * L.nX + L.nX * L.nU + L.nX);
@@ -216,17 +233,19 @@ OBCA_HD void carve_work(Scratch& W, const Lay& L, double* p) {
   W.dy = p, p += L.ny;
   W.c = p, p += L.ny;
   W.ct = p, p += L.ny;
-  W.XO = p, p += (size_t)L.V * L.Mv * L.O * 52;
-  W.XP = p, p += (size_t)L.P * L.Mv * 126;
+  W.XO = p, p += (size_t)L.V * L.Mv * L.O * 48;
+  W.XP = p, p += (size_t)L.P * L.Mv * 112;
   W.PH = p, p += (size_t)L.P * L.Mv * 27;
   W.PG = p, p += (size_t)L.P * L.Mv * 6;
   W.HN = p, p += (size_t)L.V * L.Mv * 28;
   W.GN = p, p += (size_t)L.V * L.Mv * 7;
   W.HD = p, p += (size_t)L.V * L.Mv * 7;
   W.TT = p, p += (size_t)L.V * L.Nmax * (NW * NRED + NW);
-  W.QR = p, p += (size_t)L.V * L.Nmax * (NW * NW + NW + 1);
-  W.MA = p, p += (size_t)L.V * L.Nmax * (91 + 13);
-  W.MAB = p, p += (size_t)L.P * L.Nmax * (169 + 26);
+  W.QR = p, p += (size_t)L.V * L.Nmax * QRSZ;
+  W.EM = p, p += (size_t)2 * L.V * L.Nmax * EXSZ;
+  W.DF = p, p += (size_t)2 * L.V * L.Nmax;
+  W.MA = p, p += (size_t)L.V * L.Nmax * (NSYM + NRED);
+  W.MAB = p, p += (size_t)L.P * L.Nmax * (NRED * NRED + 2 * NRED);
   W.RK = p, p += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
   W.RP = p, p += (size_t)(L.Nmax + 1) * (L.nX * L.nX + L.nX);
   W.RA = p, p += (size_t)L.Nmax * (L.nX * L.nX + L.nX * L.nU + L.nX);
@@ -335,7 +354,7 @@ struct Pose {
 //   c1 = -g'mu + (A t - b)'lam - dmin - sd ; c2 = G'mu + R(psi)'A'lam ; c3 = |A'lam|^2 - 1
 // ------------------------------------------------------------------------------------------------
 struct ObsBlk {
-  double lam[4], mu[4], sd;
+  double lam[4], mu[4], sd, el;
   double Atb[4];   // A t - b
   double u[2];     // A'lam
   double c[4];
@@ -344,7 +363,7 @@ struct ObsBlk {
 OBCA_HD void obs_residual(const Stat& S, int j, const Pose& p, ObsBlk& B) {
   const double(*A)[2] = S.obsA[j];
   B.u[0] = B.u[1] = 0;
-  double c1 = -S.dmin - B.sd;
+  double c1 = -S.dmin - B.sd + B.el;
   double gm0 = 0, gm1 = 0;
   for (int r = 0; r < 4; ++r) {
     B.Atb[r] = A[r][0] * p.x + A[r][1] * p.y - S.obsb[j][r];
@@ -365,7 +384,7 @@ OBCA_HD void obs_residual(const Stat& S, int j, const Pose& p, ObsBlk& B) {
 //   d = -b_a'lam - b_b'mu - dmin - sd ; e1 = A_a'lam + s ; e2 = A_b'mu - s ; n = 1 - s's - sn
 // ------------------------------------------------------------------------------------------------
 struct PairBlk {
-  double lam[4], mu[4], s[2], sd, sn;
+  double lam[4], mu[4], s[2], sd, sn, el;
   double ua[2], ub[2];     // G'lam, G'mu
   double Rua[2], Rub[2];   // R_a ua, R_b ub
   double ba[4], bb[4];
@@ -374,7 +393,7 @@ struct PairBlk {
 
 OBCA_HD void pair_residual(const Stat& S, const Pose& a, const Pose& b, PairBlk& B) {
   B.ua[0] = B.ua[1] = B.ub[0] = B.ub[1] = 0;
-  double d = -S.dmin - B.sd;
+  double d = -S.dmin - B.sd + B.el;
   for (int r = 0; r < 4; ++r) {
     B.ua[0] += S.G[r][0] * B.lam[r];
     B.ua[1] += S.G[r][1] * B.lam[r];
@@ -413,6 +432,7 @@ OBCA_HD void load_pair(const Lay& L, const double* x, int p, int n, PairBlk& B) 
   B.s[1] = x[L.PS(p, 1, n)];
   B.sd = x[L.PSD(p, n)];
   B.sn = x[L.PSN(p, n)];
+  B.el = x[L.PEL(p, n)];
 }
 
 // which tube set (if any) is enforced at node n of vehicle a: returns set index q >= 1 or -1.
@@ -454,6 +474,7 @@ OBCA_HDN void eval_pairs(const Ctx& ctx, const Lay& L, const Stat& S, const doub
     gl[L.PS(p, 1, n)] = ye1[1] - ye2[1] - 2.0 * yn * B.s[1];
     gl[L.PSD(p, n)] = -yd;
     gl[L.PSN(p, n)] = -yn;
+    gl[L.PEL(p, n)] = S.rho + yd;
     // pose gradients: d/dt_a = -yd R_a ua ; d/dpsi_a = -yd t_a' R_a' ua + ye1' R_a' ua   (R' = dR/dpsi here)
     double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
     double dRub[2] = {-b.s * B.ub[0] - b.c * B.ub[1], b.c * B.ub[0] - b.s * B.ub[1]};
@@ -543,6 +564,8 @@ OBCA_HDN void eval_nodes(const Ctx& ctx, const Lay& L, const Stat& S, const doub
       ObsBlk B;
       for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(a, j, r, n)], B.mu[r] = x[L.MU(a, j, r, n)];
       B.sd = x[L.SD(a, j, n)];
+      B.el = x[L.EL(a, j, n)];
+      f_part += S.rho * B.el;
       obs_residual(S, j, p, B);
       for (int r = 0; r < 4; ++r) c[L.YOBS(a, j, r, n)] = B.c[r];
       if (!y) continue;
@@ -554,6 +577,7 @@ OBCA_HDN void eval_nodes(const Ctx& ctx, const Lay& L, const Stat& S, const doub
         gl[L.MU(a, j, r, n)] = -y1 * S.g[r] + S.G[r][0] * y2[0] + S.G[r][1] * y2[1];
       }
       gl[L.SD(a, j, n)] = -y1;
+      gl[L.EL(a, j, n)] = S.rho + y1;
       g[0] += y1 * B.u[0];
       g[1] += y1 * B.u[1];
       // d/dpsi of y2' R'u : R' = [[c,s],[-s,c]] -> dR'/dpsi = [[-s,c],[-c,-s]]
@@ -587,6 +611,10 @@ OBCA_HDN void eval_nodes(const Ctx& ctx, const Lay& L, const Stat& S, const doub
       }
       for (int qq = 0; qq < NZ; ++qq) gl[L.Z(a, qq, n)] = g[qq];
     }
+  }
+  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
+    int pp = it / L.Mv, n = it % L.Mv;
+    if (n < L.Mp[pp]) f_part += S.rho * x[L.PEL(pp, n)];
   }
   double f = cta_sum(ctx, f_part);
   for (int a = 0; a < L.V; ++a) f += (L.N[a] * dt) * (L.N[a] * dt);

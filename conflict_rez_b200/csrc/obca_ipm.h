@@ -5,7 +5,8 @@
 namespace obca {
 
 struct Shared {   // lives in shared memory on the device
-  int ok;
+  int ok;      // kkt_solve: inertia / factorisation flag (must be followed by `again`)
+  int again;   // interval_nullspace: another pass needed
   int filt_n;
   double filt_theta[FILTER_MAX], filt_phi[FILTER_MAX];
 };
@@ -17,17 +18,22 @@ struct Counts {
 
 OBCA_HD bool finite_d(double v) { return v - v == 0.0; }
 
-// slack <- value of its inequality body, evaluated with the slack at zero
+// slack <- value of its inequality body, evaluated with slack and elastic variable at zero; on the elastic rows the
+// negative part of the body goes to the elastic variable, so that the row starts feasible (oracle/nlp.py:init_slacks)
 OBCA_HDN void init_slacks(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W) {
-  for (int it = ctx.tid; it < L.V * L.O * L.Mv; it += ctx.nt) W.x[L.oSD + it] = 0;
+  for (int it = ctx.tid; it < L.V * L.O * L.Mv; it += ctx.nt) W.x[L.oSD + it] = 0, W.x[L.oEL + it] = 0;
   for (int it = ctx.tid; it < L.V * (L.Smax - 1) * 8; it += ctx.nt) W.x[L.oTS + it] = 0;
-  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) W.x[L.oPSD + it] = 0, W.x[L.oPSN + it] = 0;
+  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) W.x[L.oPSD + it] = 0, W.x[L.oPSN + it] = 0, W.x[L.oPEL + it] = 0;
   cta_sync(ctx);
   double f, gdt;
   eval_all(ctx, L, S, W, W.x, nullptr, W.c, nullptr, &f, &gdt);
   for (int it = ctx.tid; it < L.V * L.O * L.Mv; it += ctx.nt) {
     int n = it % L.Mv, aj = it / L.Mv, a = aj / L.O, j = aj % L.O;
-    if (n < L.M[a]) W.x[L.SD(a, j, n)] = W.c[L.YOBS(a, j, 0, n)];
+    if (n < L.M[a]) {
+      double body = W.c[L.YOBS(a, j, 0, n)];
+      W.x[L.SD(a, j, n)] = body > 0 ? body : 0.0;
+      W.x[L.EL(a, j, n)] = body < 0 ? -body : 0.0;
+    }
   }
   for (int it = ctx.tid; it < L.V * (L.Smax - 1) * 8; it += ctx.nt) {
     int a = it / ((L.Smax - 1) * 8), q = (it / 8) % (L.Smax - 1);
@@ -35,7 +41,12 @@ OBCA_HDN void init_slacks(const Ctx& ctx, const Lay& L, const Stat& S, const Scr
   }
   for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
     int p = it / L.Mv, n = it % L.Mv;
-    if (n < L.Mp[p]) W.x[L.PSD(p, n)] = W.c[L.YPAIR(p, 0, n)], W.x[L.PSN(p, n)] = W.c[L.YPAIR(p, 5, n)];
+    if (n < L.Mp[p]) {
+      double body = W.c[L.YPAIR(p, 0, n)];
+      W.x[L.PSD(p, n)] = body > 0 ? body : 0.0;
+      W.x[L.PEL(p, n)] = body < 0 ? -body : 0.0;
+      W.x[L.PSN(p, n)] = W.c[L.YPAIR(p, 5, n)];
+    }
   }
   cta_sync(ctx);
 }

@@ -25,7 +25,9 @@ inline size_t riccati_work_doubles(const Lay& L) {
 
 // ------------------------------------------------------------------------------------------------
 // [LOCAL] pair blocks: one thread per (pair, node)
-// unknown order: lam 0-3, mu 4-7, sd 8, sn 9 | yd 10, ye1 11-12, ye2 13-14, yn 15 | s 16-17
+// unknown order: lam 0-3, mu 4-7 | yd 8, ye1 9-10, ye2 11-12, yn 13 | s 14-15
+// The slacks sd, sn and the elastic variable el enter one row each with coefficient -1 / +1 and a
+// diagonal Hessian, so they are eliminated analytically into the (yd, yd) and (yn, yn) pivots.
 // ------------------------------------------------------------------------------------------------
 OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok) {
   const double *x = W.x, *y = W.y;
@@ -41,30 +43,29 @@ OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const 
     double yd = y[L.YPAIR(p, 0, n)], ye1[2] = {y[L.YPAIR(p, 1, n)], y[L.YPAIR(p, 2, n)]};
     double ye2[2] = {y[L.YPAIR(p, 3, n)], y[L.YPAIR(p, 4, n)]}, yn = y[L.YPAIR(p, 5, n)];
     double ynm = yn < 0 ? yn : 0.0;  // local convexification: exact at KKT points (yn = -z_sn <= 0)
-    double K[18 * 18];
-    double X[18 * 7];
-    for (int q = 0; q < 18 * 18; ++q) K[q] = 0;
-    for (int q = 0; q < 18 * 7; ++q) X[q] = 0;
+    double K[16 * 16];
+    double X[16 * 7];
+    for (int q = 0; q < 16 * 16; ++q) K[q] = 0;
+    for (int q = 0; q < 16 * 7; ++q) X[q] = 0;
     for (int r = 0; r < 4; ++r) {
-      K[r * 18 + r] = W.sig[L.PL(p, r, n)];
-      K[(4 + r) * 18 + 4 + r] = W.sig[L.PM(p, r, n)];
-      K[10 * 18 + r] = -B.ba[r];
-      K[10 * 18 + 4 + r] = -B.bb[r];
-      K[11 * 18 + r] = a.c * S.G[r][0] - a.s * S.G[r][1];
-      K[12 * 18 + r] = a.s * S.G[r][0] + a.c * S.G[r][1];
-      K[13 * 18 + 4 + r] = b.c * S.G[r][0] - b.s * S.G[r][1];
-      K[14 * 18 + 4 + r] = b.s * S.G[r][0] + b.c * S.G[r][1];
+      K[r * 16 + r] = W.sig[L.PL(p, r, n)];
+      K[(4 + r) * 16 + 4 + r] = W.sig[L.PM(p, r, n)];
+      K[8 * 16 + r] = -B.ba[r];
+      K[8 * 16 + 4 + r] = -B.bb[r];
+      K[9 * 16 + r] = a.c * S.G[r][0] - a.s * S.G[r][1];
+      K[10 * 16 + r] = a.s * S.G[r][0] + a.c * S.G[r][1];
+      K[11 * 16 + 4 + r] = b.c * S.G[r][0] - b.s * S.G[r][1];
+      K[12 * 16 + 4 + r] = b.s * S.G[r][0] + b.c * S.G[r][1];
     }
-    K[8 * 18 + 8] = W.sig[L.PSD(p, n)];
-    K[9 * 18 + 9] = W.sig[L.PSN(p, n)];
-    K[10 * 18 + 8] = -1.0;
-    K[15 * 18 + 9] = -1.0;
-    for (int r = 10; r < 16; ++r) K[r * 18 + r] = -DELTA_C_LOCAL;
-    K[16 * 18 + 16] = W.sig[L.PS(p, 0, n)] - 2.0 * ynm;
-    K[17 * 18 + 17] = W.sig[L.PS(p, 1, n)] - 2.0 * ynm;
-    K[16 * 18 + 11] = 1.0, K[17 * 18 + 12] = 1.0;
-    K[16 * 18 + 13] = -1.0, K[17 * 18 + 14] = -1.0;
-    K[16 * 18 + 15] = -2.0 * B.s[0], K[17 * 18 + 15] = -2.0 * B.s[1];
+    const double isd = 1.0 / W.sig[L.PSD(p, n)], iel = 1.0 / W.sig[L.PEL(p, n)], isn = 1.0 / W.sig[L.PSN(p, n)];
+    K[8 * 16 + 8] = -(DELTA_C_LOCAL + isd + iel);
+    for (int r = 9; r < 13; ++r) K[r * 16 + r] = -DELTA_C_LOCAL;
+    K[13 * 16 + 13] = -(DELTA_C_LOCAL + isn);
+    K[14 * 16 + 14] = W.sig[L.PS(p, 0, n)] - 2.0 * ynm;
+    K[15 * 16 + 15] = W.sig[L.PS(p, 1, n)] - 2.0 * ynm;
+    K[14 * 16 + 9] = 1.0, K[15 * 16 + 10] = 1.0;
+    K[14 * 16 + 11] = -1.0, K[15 * 16 + 12] = -1.0;
+    K[14 * 16 + 13] = -2.0 * B.s[0], K[15 * 16 + 13] = -2.0 * B.s[1];
     // coupling columns: (x_a, y_a, psi_a, x_b, y_b, psi_b)
     double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
     double dRub[2] = {-b.s * B.ub[0] - b.c * B.ub[1], b.c * B.ub[0] - b.s * B.ub[1]};
@@ -84,23 +85,23 @@ OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const 
       X[r * 7 + 6] = -W.gphi[L.PL(p, r, n)];
       X[(4 + r) * 7 + 6] = -W.gphi[L.PM(p, r, n)];
     }
-    X[10 * 7 + 0] = -B.Rua[0], X[10 * 7 + 1] = -B.Rua[1], X[10 * 7 + 2] = -(a.x * dRua[0] + a.y * dRua[1]);
-    X[10 * 7 + 3] = -B.Rub[0], X[10 * 7 + 4] = -B.Rub[1], X[10 * 7 + 5] = -(b.x * dRub[0] + b.y * dRub[1]);
-    X[11 * 7 + 2] = dRua[0], X[12 * 7 + 2] = dRua[1];
-    X[13 * 7 + 5] = dRub[0], X[14 * 7 + 5] = dRub[1];
-    X[8 * 7 + 6] = -W.gphi[L.PSD(p, n)];
-    X[9 * 7 + 6] = -W.gphi[L.PSN(p, n)];
-    for (int r = 0; r < 6; ++r) X[(10 + r) * 7 + 6] = -B.c[r];
-    X[16 * 7 + 6] = -W.gphi[L.PS(p, 0, n)];
-    X[17 * 7 + 6] = -W.gphi[L.PS(p, 1, n)];
-    double C[18 * 6];
-    for (int r = 0; r < 18; ++r)
+    X[8 * 7 + 0] = -B.Rua[0], X[8 * 7 + 1] = -B.Rua[1], X[8 * 7 + 2] = -(a.x * dRua[0] + a.y * dRua[1]);
+    X[8 * 7 + 3] = -B.Rub[0], X[8 * 7 + 4] = -B.Rub[1], X[8 * 7 + 5] = -(b.x * dRub[0] + b.y * dRub[1]);
+    X[9 * 7 + 2] = dRua[0], X[10 * 7 + 2] = dRua[1];
+    X[11 * 7 + 5] = dRub[0], X[12 * 7 + 5] = dRub[1];
+    X[8 * 7 + 6] = -B.c[0] - W.gphi[L.PSD(p, n)] * isd + W.gphi[L.PEL(p, n)] * iel;
+    for (int r = 1; r < 5; ++r) X[(8 + r) * 7 + 6] = -B.c[r];
+    X[13 * 7 + 6] = -B.c[5] - W.gphi[L.PSN(p, n)] * isn;
+    X[14 * 7 + 6] = -W.gphi[L.PS(p, 0, n)];
+    X[15 * 7 + 6] = -W.gphi[L.PS(p, 1, n)];
+    double C[16 * 6];
+    for (int r = 0; r < 16; ++r)
       for (int q = 0; q < 6; ++q) C[r * 6 + q] = X[r * 7 + q];
-    int nneg = ldl_factor<18>(K);
+    int nneg = ldl_factor<16>(K);
     if (nneg != 6) *ok = 0;
-    for (int q = 0; q < 7; ++q) ldl_solve<18>(K, X + q, 7);
-    double* xp = W.XP + (size_t)(p * L.Mv + n) * 126;
-    for (int q = 0; q < 126; ++q) xp[q] = X[q];
+    for (int q = 0; q < 7; ++q) ldl_solve<16>(K, X + q, 7);
+    double* xp = W.XP + (size_t)(p * L.Mv + n) * 112;
+    for (int q = 0; q < 112; ++q) xp[q] = X[q];
     // Schur complement on (pose_a, pose_b): direct Hessian - C' Xc ; gradient C' Xr
     double H[36];
     for (int q = 0; q < 36; ++q) H[q] = 0;
@@ -114,11 +115,11 @@ OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const 
     for (int r = 0; r < 6; ++r) {
       for (int q = 0; q <= r; ++q) {
         double s = H[r * 6 + q];
-        for (int m = 0; m < 18; ++m) s -= C[m * 6 + r] * X[m * 7 + q];
+        for (int m = 0; m < 16; ++m) s -= C[m * 6 + r] * X[m * 7 + q];
         ph[sym(r, q)] = s;
       }
       double s = 0;
-      for (int m = 0; m < 18; ++m) s += C[m * 6 + r] * X[m * 7 + 6];
+      for (int m = 0; m < 16; ++m) s += C[m * 6 + r] * X[m * 7 + 6];
       ph[21 + r] = s;
     }
   }
@@ -170,61 +171,62 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
     H[sym(3, 2)] += yc[0] * p.s - yc[1] * p.c;
     H[sym(4, 3)] -= yc[2] * sec2 / S.wb;
     H[sym(4, 4)] -= yc[2] * 2.0 * v * sec2 * tde / S.wb;
-    // ---- obstacles: unknown order lam 0-3, mu 4-7, sd 8 | y1 9, y2 10-11, y3 12
+    // ---- obstacles: unknown order lam 0-3, mu 4-7 | y1 8, y2 9-10, y3 11  (sd, el folded into the y1 pivot)
     for (int j = 0; j < L.O; ++j) {
       ObsBlk B;
       for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(a, j, r, n)], B.mu[r] = x[L.MU(a, j, r, n)];
       B.sd = x[L.SD(a, j, n)];
+      B.el = x[L.EL(a, j, n)];
       obs_residual(S, j, p, B);
       double y1 = y[L.YOBS(a, j, 0, n)], y2[2] = {y[L.YOBS(a, j, 1, n)], y[L.YOBS(a, j, 2, n)]}, y3 = y[L.YOBS(a, j, 3, n)];
       double y3p = y3 > 0 ? y3 : 0.0;  // local convexification: exact at KKT points (y3 >= 0)
-      double K[13 * 13], X[13 * 4];
-      for (int q = 0; q < 169; ++q) K[q] = 0;
-      for (int q = 0; q < 52; ++q) X[q] = 0;
+      double K[12 * 12], X[12 * 4];
+      for (int q = 0; q < 144; ++q) K[q] = 0;
+      for (int q = 0; q < 48; ++q) X[q] = 0;
       double dRy[2] = {-p.s * y2[0] - p.c * y2[1], p.c * y2[0] - p.s * y2[1]};   // (dR/dpsi) y2
       double dRtu[2] = {-p.s * B.u[0] + p.c * B.u[1], -p.c * B.u[0] - p.s * B.u[1]};  // (dR'/dpsi) u
       for (int r = 0; r < 4; ++r) {
         const double* A = S.obsA[j][r];
-        for (int q = 0; q <= r; ++q) K[r * 13 + q] = 2.0 * y3p * (A[0] * S.obsA[j][q][0] + A[1] * S.obsA[j][q][1]);
-        K[r * 13 + r] += W.sig[L.LAM(a, j, r, n)];
-        K[(4 + r) * 13 + 4 + r] = W.sig[L.MU(a, j, r, n)];
-        K[9 * 13 + r] = B.Atb[r];
-        K[9 * 13 + 4 + r] = -S.g[r];
-        K[10 * 13 + r] = p.c * A[0] + p.s * A[1];
-        K[11 * 13 + r] = -p.s * A[0] + p.c * A[1];
-        K[10 * 13 + 4 + r] = S.G[r][0];
-        K[11 * 13 + 4 + r] = S.G[r][1];
-        K[12 * 13 + r] = 2.0 * (A[0] * B.u[0] + A[1] * B.u[1]);
+        for (int q = 0; q <= r; ++q) K[r * 12 + q] = 2.0 * y3p * (A[0] * S.obsA[j][q][0] + A[1] * S.obsA[j][q][1]);
+        K[r * 12 + r] += W.sig[L.LAM(a, j, r, n)];
+        K[(4 + r) * 12 + 4 + r] = W.sig[L.MU(a, j, r, n)];
+        K[8 * 12 + r] = B.Atb[r];
+        K[8 * 12 + 4 + r] = -S.g[r];
+        K[9 * 12 + r] = p.c * A[0] + p.s * A[1];
+        K[10 * 12 + r] = -p.s * A[0] + p.c * A[1];
+        K[9 * 12 + 4 + r] = S.G[r][0];
+        K[10 * 12 + 4 + r] = S.G[r][1];
+        K[11 * 12 + r] = 2.0 * (A[0] * B.u[0] + A[1] * B.u[1]);
         X[r * 4 + 0] = y1 * A[0];
         X[r * 4 + 1] = y1 * A[1];
         X[r * 4 + 2] = A[0] * dRy[0] + A[1] * dRy[1];
         X[r * 4 + 3] = -W.gphi[L.LAM(a, j, r, n)];
         X[(4 + r) * 4 + 3] = -W.gphi[L.MU(a, j, r, n)];
       }
-      K[8 * 13 + 8] = W.sig[L.SD(a, j, n)];
-      K[9 * 13 + 8] = -1.0;
-      for (int r = 9; r < 13; ++r) K[r * 13 + r] = -DELTA_C_LOCAL;
-      X[8 * 4 + 3] = -W.gphi[L.SD(a, j, n)];
-      X[9 * 4 + 0] = B.u[0], X[9 * 4 + 1] = B.u[1];
-      X[10 * 4 + 2] = dRtu[0], X[11 * 4 + 2] = dRtu[1];
-      for (int r = 0; r < 4; ++r) X[(9 + r) * 4 + 3] = -B.c[r];
-      double C[13 * 3];
-      for (int r = 0; r < 13; ++r)
+      const double isd = 1.0 / W.sig[L.SD(a, j, n)], iel = 1.0 / W.sig[L.EL(a, j, n)];
+      K[8 * 12 + 8] = -(DELTA_C_LOCAL + isd + iel);
+      for (int r = 9; r < 12; ++r) K[r * 12 + r] = -DELTA_C_LOCAL;
+      X[8 * 4 + 0] = B.u[0], X[8 * 4 + 1] = B.u[1];
+      X[9 * 4 + 2] = dRtu[0], X[10 * 4 + 2] = dRtu[1];
+      X[8 * 4 + 3] = -B.c[0] - W.gphi[L.SD(a, j, n)] * isd + W.gphi[L.EL(a, j, n)] * iel;
+      for (int r = 1; r < 4; ++r) X[(8 + r) * 4 + 3] = -B.c[r];
+      double C[12 * 3];
+      for (int r = 0; r < 12; ++r)
         for (int q = 0; q < 3; ++q) C[r * 3 + q] = X[r * 4 + q];
-      int nneg = ldl_factor<13>(K);
+      int nneg = ldl_factor<12>(K);
       if (nneg != 4) *ok = 0;
-      for (int q = 0; q < 4; ++q) ldl_solve<13>(K, X + q, 4);
-      double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 52;
-      for (int q = 0; q < 52; ++q) xo[q] = X[q];
+      for (int q = 0; q < 4; ++q) ldl_solve<12>(K, X + q, 4);
+      double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 48;
+      for (int q = 0; q < 48; ++q) xo[q] = X[q];
       H[sym(2, 2)] -= y2[0] * (p.c * B.u[0] + p.s * B.u[1]) + y2[1] * (-p.s * B.u[0] + p.c * B.u[1]);
       for (int r = 0; r < 3; ++r) {
         for (int q = 0; q <= r; ++q) {
           double s = 0;
-          for (int m = 0; m < 13; ++m) s += C[m * 3 + r] * X[m * 4 + q];
+          for (int m = 0; m < 12; ++m) s += C[m * 3 + r] * X[m * 4 + q];
           H[sym(r, q)] -= s;
         }
         double s = 0;
-        for (int m = 0; m < 13; ++m) s += C[m * 3 + r] * X[m * 4 + 3];
+        for (int m = 0; m < 12; ++m) s += C[m * 3 + r] * X[m * 4 + 3];
         g[r] += s;
       }
     }
@@ -267,173 +269,278 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
 
 // ------------------------------------------------------------------------------------------------
 // [NULLSP] one thread per (vehicle, interval)
+//
+// G_w (nr x 35) = Jacobian of the interval's collocation (+ terminal) rows w.r.t. the stage variables of nodes
+// 1..K.  Householder QR of G_w' with a rank test: where LICQ fails (a vehicle standing still over a whole
+// interval makes the over-collocated rows dependent) the dependent rows are dropped and the null space grows,
+// the analogue of IPOPT's delta_c perturbation for a singular Jacobian.
+// QR record: [35*35] reflectors below / R on and above the staircase, [35] tau, [35] pivot column of every
+// staircase row, [2] (rank, nr).
 // ------------------------------------------------------------------------------------------------
-// apply Q = H_0 ... H_{nr-1} (transpose = false) or Q' (transpose = true) to v[35]
-OBCA_HD void apply_q(const double* QRm, const double* tau, int nr, double* v, bool transpose) {
-  for (int jj = 0; jj < nr; ++jj) {
-    int j = transpose ? jj : nr - 1 - jj;
-    double s = v[j];
-    for (int r = j + 1; r < NW; ++r) s += QRm[r * NW + j] * v[r];
-    s *= tau[j];
-    v[j] -= s;
-    for (int r = j + 1; r < NW; ++r) v[r] -= s * QRm[r * NW + j];
+// apply Q = H_0 ... H_{rk-1} (transpose = false) or Q' (transpose = true) to v[35]
+OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
+  const double* tau = QRm + QR_TAU;
+  const double* piv = QRm + QR_PIV;
+  for (int jj = 0; jj < rk; ++jj) {
+    int i = transpose ? jj : rk - 1 - jj;          // reflector i acts on rows i..34, stored in column piv[i]
+    int col = (int)piv[i];
+    double s = v[i];
+    for (int r = i + 1; r < NW; ++r) s += QRm[r * NC + col] * v[r];
+    s *= tau[i];
+    v[i] -= s;
+    for (int r = i + 1; r < NW; ++r) v[r] -= s * QRm[r * NC + col];
   }
 }
 
-OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok) {
-  const double *x = W.x;
+// One (vehicle, interval) block: rows = 30 collocation rows (+ terminal rows in the last interval) + the implied
+// rows `ex` received from interval i+1 (they act on the node-K variables).  Writes T, s0, the QR record, the
+// projected Hessian, and the implied rows `em` for interval i-1.
+OBCA_HDN void nullspace_block(const Lay& L, const Stat& S, const Scratch& W, int a, int i, const double* ex, double* em, int* ok) {
+  const double* x = W.x;
   const double dt = x[L.oDT], idt = 1.0 / dt;
-  for (int it = ctx.tid; it < L.V * L.Nmax; it += ctx.nt) {
-    int a = it / L.Nmax, i = it % L.Nmax;
-    if (i >= L.N[a]) continue;
-    int n0 = i * NK;
-    bool last = (i == L.N[a] - 1);
-    int nterm = last ? (4 + L.heading[a]) : 0;
-    int nr = 30 + nterm;
-    double* QRm = W.QR + (size_t)(a * L.Nmax + i) * (NW * NW + NW + 1);  // [35][35]: column j = row j of G_w
-    double* tau = QRm + NW * NW;
-    double G0[35 * 7], gd[35], rr[35];
-    for (int q = 0; q < NW * NW; ++q) QRm[q] = 0;
-    for (int q = 0; q < 35 * 7; ++q) G0[q] = 0;
-    for (int k = 0; k < NK; ++k) {
-      int n = n0 + k;
-      double psi = x[L.Z(a, 2, n)], v = x[L.Z(a, 3, n)], de = x[L.Z(a, 4, n)];
-      double cs = cos(psi), sn = sin(psi), tde = tan(de), sec2 = 1.0 + tde * tde;
-      for (int q = 0; q < 5; ++q) {
+  const int n0 = i * NK;
+  const bool last = (i == L.N[a] - 1);
+  const int nterm = last ? (4 + L.heading[a]) : 0;
+  const int nex = (int)ex[0];
+  const int nr = 30 + nterm + nex;
+  double* QRm = W.QR + (size_t)(a * L.Nmax + i) * QRSZ;  // [35][NC]: column j = row j of G_w
+  double* tau = QRm + QR_TAU;
+  double* piv = QRm + QR_PIV;
+  double G0[NC * 7], gd[NC], rr[NC];
+  for (int q = 0; q < NW * NC; ++q) QRm[q] = 0;
+  for (int q = 0; q < NC * 7; ++q) G0[q] = 0;
+  for (int k = 0; k < NK; ++k) {
+    int n = n0 + k;
+    double psi = x[L.Z(a, 2, n)], v = x[L.Z(a, 3, n)], de = x[L.Z(a, 4, n)];
+    double cs = cos(psi), sn = sin(psi), tde = tan(de), sec2 = 1.0 + tde * tde;
+    for (int q = 0; q < 5; ++q) {
+      int r = k * 5 + q;
+      double pl = 0;
+      for (int j = 0; j < NK; ++j) {
+        double coef = S.cA[j][k] * idt;
+        pl += S.cA[j][k] * x[L.Z(a, q, n0 + j)];
+        if (j == 0) G0[r * 7 + q] += coef;
+        else QRm[((j - 1) * 7 + q) * NC + r] += coef;
+      }
+      gd[r] = -pl * idt * idt;
+      rr[r] = W.c[L.YCOL(a, q, n)];
+    }
+    // minus df/d(z,u) at node k
+    double dfz[5][NZ] = {{0, 0, -v * sn, cs, 0, 0, 0}, {0, 0, v * cs, sn, 0, 0, 0}, {0, 0, 0, tde / S.wb, v * sec2 / S.wb, 0, 0},
+                         {0, 0, 0, 0, 0, 1, 0},        {0, 0, 0, 0, 0, 0, 1}};
+    for (int q = 0; q < 5; ++q)
+      for (int m = 2; m < NZ; ++m) {
+        if (dfz[q][m] == 0.0) continue;
         int r = k * 5 + q;
-        double pl = 0;
-        for (int j = 0; j < NK; ++j) {
-          double coef = S.cA[j][k] * idt;
-          pl += S.cA[j][k] * x[L.Z(a, q, n0 + j)];
-          if (j == 0) G0[r * 7 + q] += coef;
-          else QRm[((j - 1) * 7 + q) * NW + r] += coef;
-        }
-        gd[r] = -pl * idt * idt;
-        rr[r] = W.c[L.YCOL(a, q, n)];
+        if (k == 0) G0[r * 7 + m] -= dfz[q][m];
+        else QRm[((k - 1) * 7 + m) * NC + r] -= dfz[q][m];
       }
-      // minus df/d(z,u) at node k
-      double dfz[5][NZ] = {{0, 0, -v * sn, cs, 0, 0, 0}, {0, 0, v * cs, sn, 0, 0, 0}, {0, 0, 0, tde / S.wb, v * sec2 / S.wb, 0, 0},
-                           {0, 0, 0, 0, 0, 1, 0},        {0, 0, 0, 0, 0, 0, 1}};
-      for (int q = 0; q < 5; ++q)
-        for (int m = 2; m < NZ; ++m) {
-          if (dfz[q][m] == 0.0) continue;
-          int r = k * 5 + q;
-          if (k == 0) G0[r * 7 + m] -= dfz[q][m];
-          else QRm[((k - 1) * 7 + m) * NW + r] -= dfz[q][m];
-        }
+  }
+  int r = 30;
+  if (last) {
+    if (L.heading[a]) {
+      QRm[(28 + 2) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, 0)];
+      ++r;
     }
-    if (last) {
-      int r = 30;
-      if (L.heading[a]) {
-        QRm[(28 + 2) * NW + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, 0)];
-        ++r;
-      }
-      for (int m = 3; m < NZ; ++m, ++r) QRm[(28 + m) * NW + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, m - 2)];
-    }
-    // Householder QR of the 35 x nr matrix (LAPACK dgeqr2 convention: v_j[j] = 1 implicit)
-    for (int j = 0; j < nr; ++j) {
-      double nrm = 0;
-      for (int r = j + 1; r < NW; ++r) nrm += QRm[r * NW + j] * QRm[r * NW + j];
-      double alpha = QRm[j * NW + j];
-      double beta = sqrt(alpha * alpha + nrm);
-      if (!(beta > 1e-13)) {
+    for (int m = 3; m < NZ; ++m, ++r) QRm[(28 + m) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, m - 2)];
+  }
+  for (int e = 0; e < nex; ++e, ++r) {
+    const double* h = ex + 1 + e * 9;
+    for (int m = 0; m < NZ; ++m) QRm[(28 + m) * NC + r] = h[m];
+    gd[r] = h[7], rr[r] = h[8];
+  }
+  // Householder QR with rank test (LAPACK dgeqr2 reflector convention: v[rk] = 1 implicit)
+  int rk = 0, ndrop = 0, nem = 0;
+  for (int j = 0; j < nr; ++j) {
+    double nrm = 0, full = 0;
+    for (int q = 0; q < rk; ++q) full += QRm[q * NC + j] * QRm[q * NC + j];
+    for (int q = rk + 1; q < NW; ++q) nrm += QRm[q * NC + j] * QRm[q * NC + j];
+    double alpha = rk < NW ? QRm[rk * NC + j] : 0.0;
+    double beta = sqrt(alpha * alpha + nrm);
+    full = sqrt(full + alpha * alpha + nrm);
+    if (rk >= NW || !(beta > 1e-8 * full) || !(full > 0)) {
+      // dependent row j = sum_i al[i] * (staircase row i): its remainder is an implied constraint on (xi, dt)
+      if (ndrop >= NDR) {
         *ok = 0;
-        beta = 1e-13;
+        continue;
       }
-      if (alpha > 0) beta = -beta;
-      double t = (beta - alpha) / beta;
-      double sc = 1.0 / (alpha - beta);
-      for (int r = j + 1; r < NW; ++r) QRm[r * NW + j] *= sc;
-      tau[j] = t;
-      QRm[j * NW + j] = beta;
-      for (int cc = j + 1; cc < nr; ++cc) {
-        double s = QRm[j * NW + cc];
-        for (int r = j + 1; r < NW; ++r) s += QRm[r * NW + j] * QRm[r * NW + cc];
-        s *= t;
-        QRm[j * NW + cc] -= s;
-        for (int r = j + 1; r < NW; ++r) QRm[r * NW + cc] -= s * QRm[r * NW + j];
+      double* dr = QRm + QR_DROP + ndrop * DRSZ;
+      double* al = dr + 3;
+      for (int q = rk - 1; q >= 0; --q) {
+        double sacc = QRm[q * NC + j];
+        for (int m = q + 1; m < rk; ++m) sacc -= al[m] * QRm[q * NC + (int)piv[m]];
+        al[q] = sacc / QRm[q * NC + (int)piv[q]];
       }
+      double h[9];
+      for (int m = 0; m < 7; ++m) h[m] = G0[j * 7 + m];
+      h[7] = gd[j], h[8] = rr[j];
+      double scale = fabs(gd[j]);
+      for (int m = 0; m < 7; ++m) scale = fmax(scale, fabs(G0[j * 7 + m]));
+      for (int q = 0; q < rk; ++q) {
+        int jp = (int)piv[q];
+        for (int m = 0; m < 7; ++m) h[m] -= al[q] * G0[jp * 7 + m];
+        h[7] -= al[q] * gd[jp];
+        h[8] -= al[q] * rr[jp];
+      }
+      double hmax = fabs(h[7]);
+      for (int m = 0; m < 7; ++m) hmax = fmax(hmax, fabs(h[m]));
+      int slot = -1;
+      if (i > 0 && hmax > 1e-7 * fmax(1.0, scale)) {
+        if (nem < NEX) {
+          slot = nem++;
+          for (int m = 0; m < 9; ++m) em[1 + slot * 9 + m] = h[m];
+        } else
+          *ok = 0;
+      }
+      dr[0] = (double)j, dr[1] = (double)slot, dr[2] = (double)rk;
+      for (int m = 0; m < 9; ++m) dr[3 + 35 + m] = h[m];
+      ++ndrop;
+      continue;
     }
-    QRm[NW * NW + NW] = (double)nr;
-    // T columns: 0..6 xi, 7..11 p, 12 dt; s0
-    double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
-    double* s0 = T + NW * NRED;
-    double vcol[NW];
-    for (int col = 0; col < 9; ++col) {
-      // b = -G0[:,col] (col < 7), -gd (col 7), -r (col 8); w = R^-T b ; vcol = Q [w; 0]
-      for (int r = 0; r < nr; ++r) {
-        double bv = col < 7 ? -G0[r * 7 + col] : (col == 7 ? -gd[r] : -rr[r]);
-        for (int m = 0; m < r; ++m) bv -= QRm[m * NW + r] * vcol[m];
-        vcol[r] = bv / QRm[r * NW + r];
-      }
-      for (int r = nr; r < NW; ++r) vcol[r] = 0;
-      apply_q(QRm, tau, nr, vcol, false);
-      if (col < 7)
-        for (int r = 0; r < NW; ++r) T[r * NRED + col] = vcol[r];
-      else if (col == 7)
-        for (int r = 0; r < NW; ++r) T[r * NRED + 12] = vcol[r];
-      else
-        for (int r = 0; r < NW; ++r) s0[r] = vcol[r];
+    if (alpha > 0) beta = -beta;
+    double t = (beta - alpha) / beta;
+    double sc = 1.0 / (alpha - beta);
+    for (int q = rk + 1; q < NW; ++q) QRm[q * NC + j] *= sc;
+    tau[rk] = t;
+    piv[rk] = (double)j;
+    QRm[rk * NC + j] = beta;
+    for (int cc = j + 1; cc < nr; ++cc) {
+      double sacc = QRm[rk * NC + cc];
+      for (int q = rk + 1; q < NW; ++q) sacc += QRm[q * NC + j] * QRm[q * NC + cc];
+      sacc *= t;
+      QRm[rk * NC + cc] -= sacc;
+      for (int q = rk + 1; q < NW; ++q) QRm[q * NC + cc] -= sacc * QRm[q * NC + j];
     }
-    int np = NW - nr;
-    for (int j = 0; j < NP; ++j) {
-      for (int r = 0; r < NW; ++r) vcol[r] = 0;
-      if (j < np) {
-        vcol[nr + j] = 1.0;
-        apply_q(QRm, tau, nr, vcol, false);
-      }
-      for (int r = 0; r < NW; ++r) T[r * NRED + 7 + j] = vcol[r];
+    ++rk;
+  }
+  em[0] = (double)nem;
+  QRm[QR_META + 0] = (double)rk;
+  QRm[QR_META + 1] = (double)nr;
+  QRm[QR_META + 2] = (double)ndrop;
+  int np = NW - rk;
+  if (np > NP) {
+    *ok = 0;
+    np = NP;
+  }
+  // T columns: 0..6 xi, 7..7+NP-1 p, IDT dt; s0
+  double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+  double* s0 = T + NW * NRED;
+  double vcol[NW];
+  for (int col = 0; col < 9; ++col) {
+    // b = -G0[:,col] (col < 7), -gd (col 7), -r (col 8); solve R' w = b on the staircase; vcol = Q [w; 0]
+    for (int ii = 0; ii < rk; ++ii) {
+      int j = (int)piv[ii];
+      double bv = col < 7 ? -G0[j * 7 + col] : (col == 7 ? -gd[j] : -rr[j]);
+      for (int m = 0; m < ii; ++m) bv -= QRm[m * NC + j] * vcol[m];
+      vcol[ii] = bv / QRm[ii * NC + j];
     }
-    // projected stage Hessian M = Tt' H Tt + dt cross terms, gradient m = Tt'(H s0 + gn) + e_dt hd's0
-    double HT[NS * NRED];
-    double hs0[NS];
-    for (int k = 0; k < NK; ++k) {
-      const double* hn = W.HN + (size_t)(a * L.Mv + n0 + k) * 28;
-      for (int r = 0; r < NZ; ++r) {
-        int row = k * NZ + r;
-        double acc0 = 0;
-        for (int col = 0; col < NRED; ++col) {
-          double s = 0;
-          for (int m = 0; m < NZ; ++m) {
-            double tv = (k == 0) ? ((m == col) ? 1.0 : 0.0) : T[((k - 1) * NZ + m) * NRED + col];
-            s += hn[sym(r, m)] * tv;
-          }
-          HT[row * NRED + col] = s;
+    for (int q = rk; q < NW; ++q) vcol[q] = 0;
+    apply_q(QRm, rk, vcol, false);
+    if (col < 7)
+      for (int q = 0; q < NW; ++q) T[q * NRED + col] = vcol[q];
+    else if (col == 7)
+      for (int q = 0; q < NW; ++q) T[q * NRED + IDT] = vcol[q];
+    else
+      for (int q = 0; q < NW; ++q) s0[q] = vcol[q];
+  }
+  for (int j = 0; j < NP; ++j) {
+    for (int q = 0; q < NW; ++q) vcol[q] = 0;
+    if (j < np) {
+      vcol[rk + j] = 1.0;
+      apply_q(QRm, rk, vcol, false);
+    }
+    for (int q = 0; q < NW; ++q) T[q * NRED + 7 + j] = vcol[q];
+  }
+  // projected stage Hessian M = Tt' H Tt + dt cross terms, gradient m = Tt'(H s0 + gn) + e_dt hd's0
+  double HT[NS * NRED];
+  double hs0[NS];
+  for (int k = 0; k < NK; ++k) {
+    const double* hn = W.HN + (size_t)(a * L.Mv + n0 + k) * 28;
+    for (int q = 0; q < NZ; ++q) {
+      int row = k * NZ + q;
+      double acc0 = 0;
+      for (int col = 0; col < NRED; ++col) {
+        double sacc = 0;
+        for (int m = 0; m < NZ; ++m) {
+          double tv = (k == 0) ? ((m == col) ? 1.0 : 0.0) : T[((k - 1) * NZ + m) * NRED + col];
+          sacc += hn[sym(q, m)] * tv;
         }
-        if (k > 0)
-          for (int m = 0; m < NZ; ++m) acc0 += hn[sym(r, m)] * s0[(k - 1) * NZ + m];
-        hs0[row] = acc0;
+        HT[row * NRED + col] = sacc;
+      }
+      if (k > 0)
+        for (int m = 0; m < NZ; ++m) acc0 += hn[sym(q, m)] * s0[(k - 1) * NZ + m];
+      hs0[row] = acc0;
+    }
+  }
+  double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
+  double hdT[NRED];
+  double hds0 = 0;
+  for (int col = 0; col < NRED; ++col) hdT[col] = 0;
+  for (int row = 0; row < NS; ++row) {
+    int k = row / NZ, m = row % NZ;
+    double hdv = W.HD[(size_t)(a * L.Mv + n0 + k) * 7 + m];
+    if (k == 0) hdT[m] += hdv;
+    else {
+      for (int col = 0; col < NRED; ++col) hdT[col] += hdv * T[(row - NZ) * NRED + col];
+      hds0 += hdv * s0[row - NZ];
+    }
+  }
+  for (int q = 0; q < NRED; ++q) {
+    for (int cc = 0; cc <= q; ++cc) {
+      double sacc = 0;
+      if (q < NZ) sacc += HT[q * NRED + cc];  // node-0 identity rows
+      for (int row = NZ; row < NS; ++row) sacc += T[(row - NZ) * NRED + q] * HT[row * NRED + cc];
+      if (q == IDT) sacc += hdT[cc];
+      if (cc == IDT) sacc += hdT[q];
+      Mo[sym(q, cc)] = sacc;
+    }
+    double sacc = 0;
+    if (q < NZ) sacc += hs0[q] + W.GN[(size_t)(a * L.Mv + n0) * 7 + q];
+    for (int row = NZ; row < NS; ++row)
+      sacc += T[(row - NZ) * NRED + q] * (hs0[row] + W.GN[(size_t)(a * L.Mv + n0 + row / NZ) * 7 + row % NZ]);
+    if (q == IDT) sacc += hds0;
+    Mo[NSYM + q] = sacc;
+  }
+}
+
+// All blocks in parallel; blocks whose Jacobian is rank deficient hand implied rows to the previous interval, which is
+// then re-processed in the next pass (buffers are double-buffered by pass parity so that the passes are race-free
+// and deterministic).  Usually two passes: the last interval of a vehicle with an axis-aligned final approach.
+OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok, int* again) {
+  const int nblk = L.V * L.Nmax;
+  for (int it = ctx.tid; it < nblk; it += ctx.nt) {
+    W.DF[it] = 1.0, W.DF[nblk + it] = 0.0;
+    W.EM[(size_t)it * EXSZ] = 0.0, W.EM[(size_t)(nblk + it) * EXSZ] = 0.0;
+  }
+  cta_sync(ctx);
+  for (int pass = 0; pass <= L.Nmax; ++pass) {
+    const int cur = pass & 1, nxt = cur ^ 1;
+    if (ctx.tid == 0) *again = 0;
+    for (int it = ctx.tid; it < nblk; it += ctx.nt) W.DF[nxt * nblk + it] = 0.0;
+    cta_sync(ctx);
+    for (int it = ctx.tid; it < nblk; it += ctx.nt) {
+      int a = it / L.Nmax, i = it % L.Nmax;
+      if (i >= L.N[a]) continue;
+      const double* em_old = W.EM + (size_t)(cur * nblk + it) * EXSZ;
+      double* em_new = W.EM + (size_t)(nxt * nblk + it) * EXSZ;
+      if (W.DF[cur * nblk + it] == 0.0) {
+        for (int q = 0; q < EXSZ; ++q) em_new[q] = em_old[q];
+        continue;
+      }
+      double none = 0.0;
+      const double* ex = (i + 1 < L.N[a]) ? W.EM + (size_t)(cur * nblk + it + 1) * EXSZ : &none;
+      nullspace_block(L, S, W, a, i, ex, em_new, ok);
+      bool changed = em_new[0] != em_old[0];
+      for (int q = 1; q < 1 + 9 * (int)em_new[0] && !changed; ++q)
+        changed = fabs(em_new[q] - em_old[q]) > 1e-12 * fmax(1.0, fabs(em_new[q]));
+      if (changed && i > 0) {
+        W.DF[nxt * nblk + it - 1] = 1.0;
+        *again = 1;
       }
     }
-    double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (91 + 13);
-    double hdT[NRED];
-    double hds0 = 0;
-    for (int col = 0; col < NRED; ++col) hdT[col] = 0;
-    for (int row = 0; row < NS; ++row) {
-      int k = row / NZ, m = row % NZ;
-      double hdv = W.HD[(size_t)(a * L.Mv + n0 + k) * 7 + m];
-      if (k == 0) hdT[m] += hdv;
-      else {
-        for (int col = 0; col < NRED; ++col) hdT[col] += hdv * T[(row - NZ) * NRED + col];
-        hds0 += hdv * s0[row - NZ];
-      }
-    }
-    for (int r = 0; r < NRED; ++r) {
-      for (int cc = 0; cc <= r; ++cc) {
-        double s = 0;
-        if (r < NZ) s += HT[r * NRED + cc];  // node-0 identity rows
-        for (int row = NZ; row < NS; ++row) s += T[(row - NZ) * NRED + r] * HT[row * NRED + cc];
-        if (r == 12) s += hdT[cc];
-        if (cc == 12) s += hdT[r];
-        Mo[sym(r, cc)] = s;
-      }
-      double s = 0;
-      if (r < NZ) s += hs0[r] + W.GN[(size_t)(a * L.Mv + n0) * 7 + r];
-      for (int row = NZ; row < NS; ++row)
-        s += T[(row - NZ) * NRED + r] * (hs0[row] + W.GN[(size_t)(a * L.Mv + n0 + row / NZ) * 7 + row % NZ]);
-      if (r == 12) s += hds0;
-      Mo[91 + r] = s;
-    }
+    cta_sync(ctx);
+    if (!*again) break;
+    cta_sync(ctx);
   }
 }
 
@@ -452,8 +559,8 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W) {
     const double* Ta = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
     const double* Tb = W.TT + (size_t)(b * L.Nmax + i) * (NW * NRED + NW);
     const double *s0a = Ta + NW * NRED, *s0b = Tb + NW * NRED;
-    double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (169 + 26);
-    for (int q = 0; q < 169 + 26; ++q) Mo[q] = 0;
+    double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
+    for (int q = 0; q < NRED * NRED + 2 * NRED; ++q) Mo[q] = 0;
     for (int k = 0; k < NK; ++k) {
       const double* ph = W.PH + (size_t)(p * L.Mv + i * NK + k) * 27;
       double Hc[3][3];
@@ -482,10 +589,10 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W) {
           for (int cb = 0; cb < NRED; ++cb) Mo[ra * NRED + cb] += ta * HTb[r][cb];
           ga += ta * Hs0b[r];
         }
-        Mo[169 + ra] += ga;
+        Mo[NRED * NRED + ra] += ga;
         double gb = 0;
         for (int r = 0; r < 3; ++r) gb += tt_entry(Tb, k, r, ra) * Hts0a[r];
-        Mo[169 + 13 + ra] += gb;
+        Mo[NRED * NRED + NRED + ra] += gb;
       }
     }
   }
@@ -525,30 +632,30 @@ OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch
   // own-vehicle blocks: one thread per vehicle (tiny)
   for (int a = ctx.tid; a < L.V; a += ctx.nt) {
     if (i >= L.N[a]) {
-      for (int j = 0; j < NP; ++j) R.R[(5 * a + j) * nU + 5 * a + j] = 1.0;
+      for (int j = 0; j < NP; ++j) R.R[(NP * a + j) * nU + NP * a + j] = 1.0;
       continue;
     }
-    const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (91 + 13);
+    const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
     const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
     const double* s0 = T + NW * NRED;
-    int nr = (int)W.QR[(size_t)(a * L.Nmax + i) * (NW * NW + NW + 1) + NW * NW + NW];
-    int np = NW - nr;
+    int rk = (int)W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_META];
+    int np = NW - rk;
     for (int r = 0; r < 7; ++r) {
       for (int cc = 0; cc < 7; ++cc) R.Q[(7 * a + r) * nX + 7 * a + cc] += Mo[sym(r, cc)];
-      R.Q[(7 * a + r) * nX + idt] += Mo[sym(12, r)];
-      R.Q[idt * nX + 7 * a + r] += Mo[sym(12, r)];
-      R.q[7 * a + r] += Mo[91 + r];
+      R.Q[(7 * a + r) * nX + idt] += Mo[sym(IDT, r)];
+      R.Q[idt * nX + 7 * a + r] += Mo[sym(IDT, r)];
+      R.q[7 * a + r] += Mo[NSYM + r];
       for (int cc = 0; cc < 7; ++cc) A[(7 * a + r) * nX + 7 * a + cc] = T[(28 + r) * NRED + cc];
-      A[(7 * a + r) * nX + idt] = T[(28 + r) * NRED + 12];
-      for (int j = 0; j < NP; ++j) B[(7 * a + r) * nU + 5 * a + j] = T[(28 + r) * NRED + 7 + j];
+      A[(7 * a + r) * nX + idt] = T[(28 + r) * NRED + IDT];
+      for (int j = 0; j < NP; ++j) B[(7 * a + r) * nU + NP * a + j] = T[(28 + r) * NRED + 7 + j];
       cvec[7 * a + r] = s0[28 + r];
     }
     for (int j = 0; j < NP; ++j) {
-      for (int cc = 0; cc < 7; ++cc) R.S[(5 * a + j) * nX + 7 * a + cc] += Mo[sym(7 + j, cc)];
-      R.S[(5 * a + j) * nX + idt] += Mo[sym(12, 7 + j)];
-      for (int jj = 0; jj < NP; ++jj) R.R[(5 * a + j) * nU + 5 * a + jj] += Mo[sym(7 + j, 7 + jj)];
-      if (j >= np) R.R[(5 * a + j) * nU + 5 * a + j] += 1.0;
-      R.r[5 * a + j] += Mo[91 + 7 + j];
+      for (int cc = 0; cc < 7; ++cc) R.S[(NP * a + j) * nX + 7 * a + cc] += Mo[sym(7 + j, cc)];
+      R.S[(NP * a + j) * nX + idt] += Mo[sym(IDT, 7 + j)];
+      for (int jj = 0; jj < NP; ++jj) R.R[(NP * a + j) * nU + NP * a + jj] += Mo[sym(7 + j, 7 + jj)];
+      if (j >= np) R.R[(NP * a + j) * nU + NP * a + j] += 1.0;
+      R.r[NP * a + j] += Mo[NSYM + 7 + j];
     }
   }
   cta_sync(ctx);
@@ -558,21 +665,22 @@ OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch
     double qdd = 0, qd = 0;
     for (int a = 0; a < L.V; ++a) {
       if (i >= L.N[a]) continue;
-      const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (91 + 13);
-      qdd += Mo[sym(12, 12)];
-      qd += Mo[91 + 12];
+      const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
+      qdd += Mo[sym(IDT, IDT)];
+      qd += Mo[NSYM + IDT];
     }
     if (i == 0) qdd += hdtdt, qd += W.gphi[L.oDT];
     for (int p = 0; p < L.P; ++p) {
       if (i * NK >= L.Mp[p]) continue;
       int a = L.pa[p], b = L.pb[p];
-      const double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (169 + 26);
+      const double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
       for (int ra = 0; ra < NRED; ++ra)
         for (int cb = 0; cb < NRED; ++cb) {
           double v = Mo[ra * NRED + cb];
-          // ra in reduced coords of a, cb in reduced coords of b
-          int ia = ra < 7 ? 7 * a + ra : (ra < 12 ? -(5 * a + ra - 7) - 1 : idt);
-          int ib = cb < 7 ? 7 * b + cb : (cb < 12 ? -(5 * b + cb - 7) - 1 : idt);
+          if (v == 0.0) continue;
+          // ra in reduced coords of a, cb in reduced coords of b; negative = control index
+          int ia = ra < 7 ? 7 * a + ra : (ra < IDT ? -(NP * a + ra - 7) - 1 : idt);
+          int ib = cb < 7 ? 7 * b + cb : (cb < IDT ? -(NP * b + cb - 7) - 1 : idt);
           if (ia >= 0 && ib >= 0) {
             if (ia == idt && ib == idt) qdd += 2.0 * v;
             else R.Q[ia * nX + ib] += v, R.Q[ib * nX + ia] += v;
@@ -581,9 +689,9 @@ OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch
           else R.R[(-ia - 1) * nU + (-ib - 1)] += v, R.R[(-ib - 1) * nU + (-ia - 1)] += v;
         }
       for (int ra = 0; ra < NRED; ++ra) {
-        double ga = Mo[169 + ra], gb = Mo[169 + 13 + ra];
+        double ga = Mo[NRED * NRED + ra], gb = Mo[NRED * NRED + NRED + ra];
         if (ra < 7) R.q[7 * a + ra] += ga, R.q[7 * b + ra] += gb;
-        else if (ra < 12) R.r[5 * a + ra - 7] += ga, R.r[5 * b + ra - 7] += gb;
+        else if (ra < IDT) R.r[NP * a + ra - 7] += ga, R.r[NP * b + ra - 7] += gb;
         else qd += ga + gb;
       }
     }
@@ -762,8 +870,8 @@ OBCA_HDN void expand_primal(const Ctx& ctx, const Lay& L, const Scratch& W) {
     const double* s0 = T + NW * NRED;
     double rc[NRED];
     for (int q = 0; q < 7; ++q) rc[q] = X[(size_t)i * nX + 7 * a + q];
-    for (int q = 0; q < NP; ++q) rc[7 + q] = U[(size_t)i * nU + 5 * a + q];
-    rc[12] = ddt;
+    for (int q = 0; q < NP; ++q) rc[7 + q] = U[(size_t)i * nU + NP * a + q];
+    rc[IDT] = ddt;
     for (int q = 0; q < NZ; ++q) W.dx[L.Z(a, q, i * NK)] = rc[q];
     for (int r = 0; r < NW; ++r) {
       double s = s0[r];
@@ -807,6 +915,17 @@ OBCA_HDN void node_residual(const Ctx& ctx, const Lay& L, const Scratch& W) {
   }
 }
 
+// multiplier of constraint row r of block (a, i): collocation rows, terminal rows, then received implied rows
+OBCA_HD double* block_row_multiplier(const Lay& L, const Scratch& W, int a, int i, int r) {
+  if (r < 30) return &W.dy[L.YCOL(a, r % 5, i * NK + r / 5)];
+  int nterm = (i == L.N[a] - 1) ? (4 + L.heading[a]) : 0;
+  if (r < 30 + nterm) {
+    int t = r - 30;
+    return &W.dy[L.YTERM(a, L.heading[a] ? t : t + 1)];
+  }
+  return &W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_NU + (r - 30 - nterm)];
+}
+
 OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W) {
   const int nX = L.nX;
   const size_t pstride = (size_t)nX * nX + nX;
@@ -829,40 +948,59 @@ OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, c
     int a = it / L.Nmax, i = it % L.Nmax;
     if (i >= L.N[a]) continue;
     int n0 = i * NK;
-    const double* QRm = W.QR + (size_t)(a * L.Nmax + i) * (NW * NW + NW + 1);
-    const double* tau = QRm + NW * NW;
-    int nr = (int)QRm[NW * NW + NW];
-    double v[NW];
+    const double* QRm = W.QR + (size_t)(a * L.Nmax + i) * QRSZ;
+    const double* piv = QRm + QR_PIV;
+    int rk = (int)QRm[QR_META], nr = (int)QRm[QR_META + 1];
+    double v[NW], dyr[NC];
     for (int r = 0; r < NW; ++r) v[r] = -W.GN[(size_t)(a * L.Mv + n0 + 1 + r / NZ) * 7 + r % NZ];
     if (i < L.N[a] - 1)
       for (int q = 0; q < NZ; ++q) v[28 + q] -= W.dy[L.YCONT(a, q, i + 1)];
-    apply_q(QRm, tau, nr, v, true);
-    // R dy = v[0:nr]
-    for (int r = nr - 1; r >= 0; --r) {
-      double s = v[r];
-      for (int m = r + 1; m < nr; ++m) s -= QRm[r * NW + m] * v[m];
-      v[r] = s / QRm[r * NW + r];
+    apply_q(QRm, rk, v, true);
+    // R dy = v[0:rk] on the staircase; dropped (dependent) rows keep dy = 0 here
+    for (int r = 0; r < nr; ++r) dyr[r] = 0;
+    for (int ii = rk - 1; ii >= 0; --ii) {
+      int j = (int)piv[ii];
+      double s = v[ii];
+      for (int m = ii + 1; m < rk; ++m) {
+        int jm = (int)piv[m];
+        s -= QRm[ii * NC + jm] * dyr[jm];
+      }
+      dyr[j] = s / QRm[ii * NC + j];
     }
-    for (int k = 0; k < NK; ++k)
-      for (int q = 0; q < 5; ++q) W.dy[L.YCOL(a, q, n0 + k)] = v[k * 5 + q];
-    if (i == L.N[a] - 1) {
-      int r = 30;
-      W.dy[L.YTERM(a, 0)] = L.heading[a] ? v[r++] : 0.0;
-      for (int m = 3; m < NZ; ++m) W.dy[L.YTERM(a, m - 2)] = v[r++];
-    }
+    for (int r = 0; r < nr; ++r) *block_row_multiplier(L, W, a, i, r) = dyr[r];
+    if (i == L.N[a] - 1 && !L.heading[a]) W.dy[L.YTERM(a, 0)] = 0.0;
     if (i == 0) {
       // node 0 of the first interval: gn0 + G0' dycol + dyinit = 0
       double psi = W.x[L.Z(a, 2, 0)], vv = W.x[L.Z(a, 3, 0)], de = W.x[L.Z(a, 4, 0)];
       double cs = cos(psi), sn = sin(psi), tde = tan(de), sec2 = 1.0 + tde * tde;
       double gy[NZ] = {0, 0, 0, 0, 0, 0, 0};
       for (int q = 0; q < 5; ++q)
-        for (int k = 0; k < NK; ++k) gy[q] += S.cA[0][k] * idt * v[k * 5 + q];
-      gy[2] -= v[0] * (-vv * sn) + v[1] * (vv * cs);
-      gy[3] -= v[0] * cs + v[1] * sn + v[2] * tde / S.wb;
-      gy[4] -= v[2] * vv * sec2 / S.wb;
-      gy[5] -= v[3];
-      gy[6] -= v[4];
+        for (int k = 0; k < NK; ++k) gy[q] += S.cA[0][k] * idt * dyr[k * 5 + q];
+      gy[2] -= dyr[0] * (-vv * sn) + dyr[1] * (vv * cs);
+      gy[3] -= dyr[0] * cs + dyr[1] * sn + dyr[2] * tde / S.wb;
+      gy[4] -= dyr[2] * vv * sec2 / S.wb;
+      gy[5] -= dyr[3];
+      gy[6] -= dyr[4];
       for (int q = 0; q < NZ; ++q) W.dy[L.YINIT(a, q)] = -W.GN[(size_t)(a * L.Mv) * 7 + q] - gy[q];
+    }
+  }
+  cta_sync(ctx);
+  // implied rows: their multipliers nu (known at block i once block i is final) flow to the dependent rows of
+  // block i+1 and to the continuity multiplier between the two blocks.  One thread per vehicle, upwards.
+  for (int a = ctx.tid; a < L.V; a += ctx.nt) {
+    for (int i = 0; i + 1 < L.N[a]; ++i) {
+      const double* nu = W.QR + (size_t)(a * L.Nmax + i) * QRSZ + QR_NU;
+      const double* Qn = W.QR + (size_t)(a * L.Nmax + i + 1) * QRSZ;
+      int ndrop = (int)Qn[QR_META + 2];
+      for (int d = 0; d < ndrop; ++d) {
+        const double* dr = Qn + QR_DROP + d * DRSZ;
+        int j = (int)dr[0], slot = (int)dr[1], rkd = (int)dr[2];
+        if (slot < 0) continue;
+        double nv = nu[slot];
+        *block_row_multiplier(L, W, a, i + 1, j) += nv;
+        for (int q = 0; q < rkd; ++q) *block_row_multiplier(L, W, a, i + 1, (int)Qn[QR_PIV + q]) -= dr[3 + q] * nv;
+        for (int q = 0; q < NZ; ++q) W.dy[L.YCONT(a, q, i + 1)] += nv * dr[3 + 35 + q];
+      }
     }
   }
 }
@@ -873,15 +1011,17 @@ OBCA_HDN void local_backsub(const Ctx& ctx, const Lay& L, const Stat& S, const S
     if (n >= L.M[a]) continue;
     double dp[3] = {W.dx[L.Z(a, 0, n)], W.dx[L.Z(a, 1, n)], W.dx[L.Z(a, 2, n)]};
     for (int j = 0; j < L.O; ++j) {
-      const double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 52;
-      double r[13];
-      for (int m = 0; m < 13; ++m) r[m] = xo[m * 4 + 3] - xo[m * 4 + 0] * dp[0] - xo[m * 4 + 1] * dp[1] - xo[m * 4 + 2] * dp[2];
+      const double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 48;
+      double r[12];
+      for (int m = 0; m < 12; ++m) r[m] = xo[m * 4 + 3] - xo[m * 4 + 0] * dp[0] - xo[m * 4 + 1] * dp[1] - xo[m * 4 + 2] * dp[2];
       for (int q = 0; q < 4; ++q) {
         W.dx[L.LAM(a, j, q, n)] = r[q];
         W.dx[L.MU(a, j, q, n)] = r[4 + q];
-        W.dy[L.YOBS(a, j, q, n)] = r[9 + q];
+        W.dy[L.YOBS(a, j, q, n)] = r[8 + q];
       }
-      W.dx[L.SD(a, j, n)] = r[8];
+      // sd: sig dsd - dy1 = -gphi ; el: sig del + dy1 = -gphi
+      W.dx[L.SD(a, j, n)] = (r[8] - W.gphi[L.SD(a, j, n)]) / W.sig[L.SD(a, j, n)];
+      W.dx[L.EL(a, j, n)] = -(r[8] + W.gphi[L.EL(a, j, n)]) / W.sig[L.EL(a, j, n)];
     }
     int q = tube_set_at(L, a, n);
     if (q >= 1) {
@@ -900,19 +1040,20 @@ OBCA_HDN void local_backsub(const Ctx& ctx, const Lay& L, const Stat& S, const S
     if (n >= L.Mp[p]) continue;
     int a = L.pa[p], b = L.pb[p];
     double dp[6] = {W.dx[L.Z(a, 0, n)], W.dx[L.Z(a, 1, n)], W.dx[L.Z(a, 2, n)], W.dx[L.Z(b, 0, n)], W.dx[L.Z(b, 1, n)], W.dx[L.Z(b, 2, n)]};
-    const double* xp = W.XP + (size_t)(p * L.Mv + n) * 126;
-    double r[18];
-    for (int m = 0; m < 18; ++m) {
+    const double* xp = W.XP + (size_t)(p * L.Mv + n) * 112;
+    double r[16];
+    for (int m = 0; m < 16; ++m) {
       double s = xp[m * 7 + 6];
       for (int q = 0; q < 6; ++q) s -= xp[m * 7 + q] * dp[q];
       r[m] = s;
     }
     for (int q = 0; q < 4; ++q) W.dx[L.PL(p, q, n)] = r[q], W.dx[L.PM(p, q, n)] = r[4 + q];
-    W.dx[L.PSD(p, n)] = r[8];
-    W.dx[L.PSN(p, n)] = r[9];
-    for (int q = 0; q < 6; ++q) W.dy[L.YPAIR(p, q, n)] = r[10 + q];
-    W.dx[L.PS(p, 0, n)] = r[16];
-    W.dx[L.PS(p, 1, n)] = r[17];
+    for (int q = 0; q < 6; ++q) W.dy[L.YPAIR(p, q, n)] = r[8 + q];
+    W.dx[L.PS(p, 0, n)] = r[14];
+    W.dx[L.PS(p, 1, n)] = r[15];
+    W.dx[L.PSD(p, n)] = (r[8] - W.gphi[L.PSD(p, n)]) / W.sig[L.PSD(p, n)];
+    W.dx[L.PEL(p, n)] = -(r[8] + W.gphi[L.PEL(p, n)]) / W.sig[L.PEL(p, n)];
+    W.dx[L.PSN(p, n)] = (r[13] - W.gphi[L.PSN(p, n)]) / W.sig[L.PSN(p, n)];
   }
 }
 
@@ -926,7 +1067,7 @@ OBCA_HDN int kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratc
   double hdtdt;
   node_assemble(ctx, L, S, W, ok_shared, &hdtdt);
   cta_sync(ctx);
-  interval_nullspace(ctx, L, S, W, ok_shared);
+  interval_nullspace(ctx, L, S, W, ok_shared, ok_shared + 1);
   cta_sync(ctx);
   interval_cross(ctx, L, W);
   cta_sync(ctx);

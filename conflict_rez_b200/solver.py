@@ -1,0 +1,343 @@
+"""ctypes binding of ``libobca_b200.so`` (C ABI in ``include/obca.h``) and the batched front door.
+
+This is the drop-in for the ``opti.solver("ipopt", ...); opti.solve()`` call of the reference
+(confrez/control/vehicle.py:657-658, multi_vehicle_planner.py:464-465): the planners fill a
+:class:`~conflict_rez_b200.problem.CollocationProblem` / ``CollocationGuess`` and call
+:meth:`ObcaSolver.solve`.  PyTorch is used for device memory and streams only; every numerical step runs in
+the hand-written sm_100a kernels.  There is **no CPU fallback**: a missing library or a missing GPU raises.
+"""
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from conflict_rez_b200.problem import CollocationGuess, CollocationProblem
+
+OBCA_MAX_V = 8
+_LIB_NAME = "libobca_b200.so"
+
+RETURN_STATUS = {
+    0: "Solve_Succeeded",
+    -1: "Maximum_Iterations_Exceeded",
+    -2: "Restoration_Failed",
+    -3: "Error_In_Step_Computation",
+    -4: "Invalid_Number_Detected",
+    -100: "Not_Solved",
+}
+
+
+class ObcaDims(ctypes.Structure):
+    _fields_ = [
+        ("batch", ctypes.c_int32),
+        ("V", ctypes.c_int32),
+        ("O", ctypes.c_int32),
+        ("K", ctypes.c_int32),
+        ("n_per_set", ctypes.c_int32),
+        ("n_sets", ctypes.c_int32 * OBCA_MAX_V),
+    ]
+
+
+class ObcaOptions(ctypes.Structure):
+    _fields_ = [
+        ("tol", ctypes.c_double),
+        ("constr_viol_tol", ctypes.c_double),
+        ("dual_inf_tol", ctypes.c_double),
+        ("compl_inf_tol", ctypes.c_double),
+        ("mu_init", ctypes.c_double),
+        ("dmin", ctypes.c_double),
+        ("shrink_tube", ctypes.c_double),
+        ("elastic_weight", ctypes.c_double),
+        ("max_iter", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+class ObcaStatic(ctypes.Structure):
+    _fields_ = [(n, _dp) for n in ("obs_A", "obs_b", "tube_A", "tube_b", "body_G", "body_g", "region", "limits", "final_heading")] + [
+        ("wb", ctypes.c_double)
+    ]
+
+
+EXPORTS = [
+    "obca_version",
+    "obca_last_error",
+    "obca_default_options",
+    "obca_create",
+    "obca_destroy",
+    "obca_set_static",
+    "obca_set_options",
+    "obca_set_init_pose",
+    "obca_set_initial",
+    "obca_solve",
+    "obca_get_solution",
+    "obca_get_stats",
+    "obca_launch_count",
+    "obca_layout",
+    "obca_debug_get_iterate",
+    "obca_debug_set_iterate",
+    "obca_debug_eval",
+    "obca_debug_step",
+]
+
+
+def default_library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    path = path or default_library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  conflict_rez_b200 has no CPU fallback." % path
+        )
+    lib = ctypes.CDLL(path)
+    vp, i32p = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)
+    lib.obca_version.restype = ctypes.c_char_p
+    lib.obca_last_error.restype = ctypes.c_char_p
+    lib.obca_default_options.argtypes = [ctypes.POINTER(ObcaOptions)]
+    lib.obca_create.argtypes = [ctypes.POINTER(ObcaDims), ctypes.POINTER(ObcaOptions), ctypes.c_int, ctypes.POINTER(vp)]
+    lib.obca_destroy.argtypes = [vp]
+    lib.obca_set_static.argtypes = [vp, ctypes.POINTER(ObcaStatic)]
+    lib.obca_set_options.argtypes = [vp, ctypes.POINTER(ObcaOptions)]
+    lib.obca_set_init_pose.argtypes = [vp, vp, vp]
+    lib.obca_set_initial.argtypes = [vp] + [vp] * 7 + [vp]
+    lib.obca_solve.argtypes = [vp, vp]
+    lib.obca_get_solution.argtypes = [vp] + [vp] * 7 + [vp]
+    lib.obca_get_stats.argtypes = [vp] + [vp] * 6 + [vp]
+    lib.obca_launch_count.argtypes = [vp]
+    lib.obca_launch_count.restype = ctypes.c_int64
+    lib.obca_layout.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+    lib.obca_debug_get_iterate.argtypes = [vp, ctypes.c_int] + [_dp] * 4
+    lib.obca_debug_set_iterate.argtypes = [vp, ctypes.c_int] + [_dp] * 4
+    lib.obca_debug_eval.argtypes = [vp, ctypes.c_int, _dp, _dp, _dp]
+    lib.obca_debug_step.argtypes = [vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, _dp, _dp, i32p]
+    return lib
+
+
+@dataclass
+class SolveOptions:
+    """IPOPT options the reference passes (vehicle.py:648-656) plus the formulation constants."""
+
+    tol: float = 1e-2
+    constr_viol_tol: float = 1e-2
+    dual_inf_tol: float = 1.0
+    compl_inf_tol: float = 1e-4
+    mu_init: float = 0.1
+    max_iter: int = 3000
+    elastic_weight: float = 1e3
+
+
+@dataclass
+class BatchResult:
+    status: np.ndarray  # (B,) int32, see RETURN_STATUS
+    iters: np.ndarray
+    obj: np.ndarray
+    cviol: np.ndarray
+    dual_inf: np.ndarray
+    compl_inf: np.ndarray
+    z: np.ndarray  # (B,V,Mmax,7)
+    lam: np.ndarray
+    mu: np.ndarray
+    dt: np.ndarray
+    pair_lam: Optional[np.ndarray]
+    pair_mu: Optional[np.ndarray]
+    pair_s: Optional[np.ndarray]
+
+    def return_status(self, b: int = 0) -> str:
+        return RETURN_STATUS.get(int(self.status[b]), "Unknown")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(_dp)
+
+
+class ObcaSolver:
+    """One handle = one problem shape (V, sets, obstacles) x one batch size on one GPU."""
+
+    def __init__(self, prob: CollocationProblem, options: Optional[SolveOptions] = None, device="cuda:0", lib: Optional[ctypes.CDLL] = None):
+        self.lib = lib if lib is not None else load_library()
+        self.device = torch.device(device)
+        self.is_emulation = b"EMULATION" in self.lib.obca_version()
+        if self.device.type != "cuda" and not self.is_emulation:
+            raise RuntimeError("ObcaSolver needs a CUDA device (no CPU fallback)")
+        if self.device.type == "cuda" and not torch.cuda.is_available():
+            raise RuntimeError("ObcaSolver: CUDA is not available on this machine (no CPU fallback)")
+        self.prob = prob
+        self.opts = options or SolveOptions()
+        self.B = prob.batch or 1
+        self.V, self.O, self.P = prob.V, prob.O, len(prob.pairs)
+        self.Mmax = int(prob.nodes.max())
+        dims = ObcaDims(batch=self.B, V=self.V, O=self.O, K=prob.K, n_per_set=prob.n_per_set)
+        for a in range(self.V):
+            dims.n_sets[a] = int(prob.n_sets[a])
+        copts = ObcaOptions()
+        self.lib.obca_default_options(ctypes.byref(copts))
+        for name in ("tol", "constr_viol_tol", "dual_inf_tol", "compl_inf_tol", "mu_init", "max_iter", "elastic_weight"):
+            setattr(copts, name, getattr(self.opts, name))
+        copts.dmin, copts.shrink_tube = prob.dmin, prob.shrink_tube
+        self.handle = ctypes.c_void_p()
+        dev_index = self.device.index or 0 if self.device.type == "cuda" else 0
+        self._check(self.lib.obca_create(ctypes.byref(dims), ctypes.byref(copts), dev_index, ctypes.byref(self.handle)))
+        keep = {n: np.ascontiguousarray(getattr(prob, n), dtype=np.float64) for n in ("obs_A", "obs_b", "tube_A", "tube_b", "body_G", "body_g", "region", "limits", "final_heading")}
+        st = ObcaStatic(wb=float(prob.wb), **{n: _np_ptr(a) for n, a in keep.items()})
+        self._check(self.lib.obca_set_static(self.handle, ctypes.byref(st)))
+        self._stream = None
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError("obca: " + self.lib.obca_last_error().decode())
+        return rc
+
+    def _stream_ptr(self):
+        if self.device.type != "cuda":
+            return None
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _to_dev(self, a, shape):
+        t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64).reshape(shape))
+        if self.device.type == "cuda":
+            t = t.pin_memory().to(self.device, non_blocking=True)
+        return t.contiguous()
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.obca_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.obca_launch_count(self.handle))
+
+    # -- device-resident API (inputs already on the GPU) -------------------------------------------------
+    def upload(self, guess: CollocationGuess, init_pose: Optional[np.ndarray] = None):
+        """Host -> device copies of the per-instance data; returns the device tensors (kept alive by the caller)."""
+        B, V, M, O, P = self.B, self.V, self.Mmax, self.O, self.P
+        pose = self.prob.init_pose if init_pose is None else init_pose
+        d = {
+            "pose": self._to_dev(pose, (B, V, 3)),
+            "z": self._to_dev(guess.z, (B, V, M, 7)),
+            "lam": self._to_dev(guess.lam, (B, V, M, O, 4)),
+            "mu": self._to_dev(guess.mu, (B, V, M, O, 4)),
+            "dt": self._to_dev(np.broadcast_to(guess.dt, (B,)), (B,)),
+        }
+        if P:
+            d["pl"] = self._to_dev(guess.pair_lam, (B, P, M, 4))
+            d["pm"] = self._to_dev(guess.pair_mu, (B, P, M, 4))
+            d["ps"] = self._to_dev(guess.pair_s, (B, P, M, 2))
+        return d
+
+    def set_inputs(self, d):
+        s = self._stream_ptr()
+        self._check(self.lib.obca_set_init_pose(self.handle, _ptr(d["pose"]), s))
+        self._check(
+            self.lib.obca_set_initial(self.handle, _ptr(d["z"]), _ptr(d["lam"]), _ptr(d["mu"]), _ptr(d["dt"]), _ptr(d.get("pl")), _ptr(d.get("pm")), _ptr(d.get("ps")), s)
+        )
+
+    def run(self):
+        """Launch the batched interior-point solve on the current stream (asynchronous)."""
+        self._check(self.lib.obca_solve(self.handle, self._stream_ptr()))
+
+    def fetch_stats(self):
+        B = self.B
+        dev = self.device
+        st = torch.empty(B, dtype=torch.int32, device=dev)
+        it = torch.empty(B, dtype=torch.int32, device=dev)
+        dbl = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(4)]
+        self._check(self.lib.obca_get_stats(self.handle, _ptr(st), _ptr(it), *[_ptr(t) for t in dbl], self._stream_ptr()))
+        return st, it, dbl
+
+    def fetch_solution(self):
+        B, V, M, O, P = self.B, self.V, self.Mmax, self.O, self.P
+        dev = self.device
+        out = {
+            "z": torch.empty((B, V, M, 7), dtype=torch.float64, device=dev),
+            "lam": torch.empty((B, V, M, O, 4), dtype=torch.float64, device=dev),
+            "mu": torch.empty((B, V, M, O, 4), dtype=torch.float64, device=dev),
+            "dt": torch.empty((B,), dtype=torch.float64, device=dev),
+        }
+        if P:
+            out["pl"] = torch.empty((B, P, M, 4), dtype=torch.float64, device=dev)
+            out["pm"] = torch.empty((B, P, M, 4), dtype=torch.float64, device=dev)
+            out["ps"] = torch.empty((B, P, M, 2), dtype=torch.float64, device=dev)
+        self._check(
+            self.lib.obca_get_solution(self.handle, _ptr(out["z"]), _ptr(out["lam"]), _ptr(out["mu"]), _ptr(out["dt"]), _ptr(out.get("pl")), _ptr(out.get("pm")), _ptr(out.get("ps")), self._stream_ptr())
+        )
+        return out
+
+    # -- host-buffer API (the call a planner makes) ------------------------------------------------------
+    def solve(self, guess: CollocationGuess, init_pose: Optional[np.ndarray] = None, want_duals: bool = True) -> BatchResult:
+        """Host arrays in, host arrays out: H2D copies, batched solve, D2H copies."""
+        d = self.upload(guess, init_pose)
+        self.set_inputs(d)
+        self.run()
+        st, it, dbl = self.fetch_stats()
+        sol = self.fetch_solution()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        cpu = lambda t: None if t is None else t.cpu().numpy()
+        return BatchResult(
+            status=cpu(st),
+            iters=cpu(it),
+            obj=cpu(dbl[0]),
+            cviol=cpu(dbl[1]),
+            dual_inf=cpu(dbl[2]),
+            compl_inf=cpu(dbl[3]),
+            z=cpu(sol["z"]),
+            lam=cpu(sol["lam"]) if want_duals else None,
+            mu=cpu(sol["mu"]) if want_duals else None,
+            dt=cpu(sol["dt"]),
+            pair_lam=cpu(sol.get("pl")),
+            pair_mu=cpu(sol.get("pm")),
+            pair_s=cpu(sol.get("ps")),
+        )
+
+    # -- introspection for the parity tests --------------------------------------------------------------
+    def layout(self):
+        buf = (ctypes.c_int64 * 40)()
+        n = self._check(self.lib.obca_layout(self.handle, buf, 40))
+        names = ["V", "O", "P", "Mv", "Nmax", "Smax", "nx", "ny", "oZ", "oLAM", "oMU", "oSD", "oEL", "oTS", "oPL", "oPM", "oPS", "oPSD", "oPSN", "oPEL", "oDT",
+                 "oYINIT", "oYCOL", "oYCONT", "oYTERM", "oYOBS", "oYTUBE", "oYPAIR", "m_active", "nb"]
+        assert n == len(names)
+        return {k: int(buf[i]) for i, k in enumerate(names)}
+
+    def debug_get_iterate(self, b=0):
+        L = self.layout()
+        x, zL, zU = (np.zeros(L["nx"]) for _ in range(3))
+        y = np.zeros(L["ny"])
+        self._check(self.lib.obca_debug_get_iterate(self.handle, b, _np_ptr(x), _np_ptr(y), _np_ptr(zL), _np_ptr(zU)))
+        return x, y, zL, zU
+
+    def debug_set_iterate(self, b, x=None, y=None, zL=None, zU=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, zL, zU)]
+        self._check(self.lib.obca_debug_set_iterate(self.handle, b, *[None if a is None else _np_ptr(a) for a in arrs]))
+
+    def debug_eval(self, b=0):
+        L = self.layout()
+        c, gl, f = np.zeros(L["ny"]), np.zeros(L["nx"]), ctypes.c_double()
+        self._check(self.lib.obca_debug_eval(self.handle, b, _np_ptr(c), _np_ptr(gl), ctypes.cast(ctypes.byref(f), _dp)))
+        return c, gl, f.value
+
+    def debug_step(self, b, mu, delta_w):
+        L = self.layout()
+        dx, dy, ok = np.zeros(L["nx"]), np.zeros(L["ny"]), ctypes.c_int32()
+        self._check(self.lib.obca_debug_step(self.handle, b, mu, delta_w, _np_ptr(dx), _np_ptr(dy), ctypes.byref(ok)))
+        return dx, dy, int(ok.value)

@@ -56,6 +56,7 @@ typedef struct ObcaOptions {
   double tol, constr_viol_tol, dual_inf_tol, compl_inf_tol;
   double mu_init;
   double dmin, shrink_tube;
+  double elastic_weight;         /* rho of the exact l1 penalty on the elastic variables of the distance rows */
   int32_t max_iter;
   int32_t reserved;
 } ObcaOptions;
