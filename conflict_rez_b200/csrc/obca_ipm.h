@@ -115,6 +115,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
   const double theta_max = 1e4 * fmax(1.0, th0), theta_min = 1e-4 * fmax(1.0, th0);
   const double mu_min = fmin(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
   double dw_last = 0.0;
+  bool tiny_last = false, force_mu = false;
   int status = OBCA_MAXITER_EXCEEDED, it = 0;
   double dual_inf = 0, cviol = 0, compl0 = 0;
   for (;;) {
@@ -149,6 +150,9 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     double s_d = fmax(o.s_max, (s_y + s_z) / fmax(1.0, (double)(cnt.m_active + cnt.nb))) / o.s_max;
     double s_c = fmax(o.s_max, s_z / fmax(1.0, (double)cnt.nb)) / o.s_max;
     double E0 = fmax(fmax(dual_inf / s_d, cviol), compl0 / s_c);
+#ifdef OBCA_HOST_EMU
+    if (getenv("OBCA_TRACE")) printf("%4d f=%.8e th=%.2e du=%.2e co=%.2e mu=%.1e dw=%.1e\n", it, f, theta, dual_inf, compl0, mu, dw_last);
+#endif
     if (E0 <= o.tol && dual_inf <= o.dual_inf_tol && cviol <= o.constr_viol_tol && compl0 <= o.compl_inf_tol) {
       status = OBCA_SOLVE_SUCCEEDED;
       break;
@@ -165,12 +169,14 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     for (;;) {
       double cmu = fmax(fabs(pr_lo - mu), fabs(pr_hi - mu));
       double Emu = fmax(fmax(dual_inf / s_d, cviol), cmu / s_c);
-      if (Emu <= o.kappa_eps * mu && mu > mu_min) {
+      if ((Emu <= o.kappa_eps * mu || force_mu) && mu > mu_min) {
         mu = fmax(mu_min, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
         if (ctx.tid == 0) sh->filt_n = 0;
+        force_mu = false;
       } else
         break;
     }
+    force_mu = false;
     cta_sync(ctx);
     const double tau = fmax(o.tau_min, 1.0 - mu);
     // ---- gradient of the barrier Lagrangian, barrier objective and grad_phi'dx bookkeeping
@@ -216,11 +222,10 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     }
     if (dw > 0) dw_last = dw;
     // ---- dz, fraction to the boundary, directional derivative of the barrier objective
-    double a_pr = 1.0, a_du = 1.0, dphi = 0;
+    double a_pr = 1.0, a_du = 1.0, dphi = 0, rel = 0;
     for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
       double lo = xL[q], hi = xU[q], d = W.dx[q];
-      double gpl = W.gl[q];  // grad_phi = gphi - J'y = gl-part without multipliers: recompute below
-      (void)gpl;
+      rel = fmax(rel, fabs(d) / (1.0 + fabs(W.x[q])));
       if (lo > -INFINITY) {
         double gp = W.x[q] - lo;
         double dz = mu / gp - W.zL[q] - W.zL[q] / gp * d;
@@ -245,6 +250,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     for (int q = ctx.tid; q < L.P * 6 * L.Mv; q += ctx.nt) yJdx += W.y[L.oYPAIR + q] * DELTA_C_LOCAL * W.dy[L.oYPAIR + q];
     a_pr = cta_min(ctx, a_pr);
     a_du = cta_min(ctx, a_du);
+    rel = cta_max(ctx, rel);
     dphi = cta_sum(ctx, dphi) - cta_sum(ctx, yJdx);
     // ---- filter line search
     double a_min;
@@ -257,7 +263,21 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     double alpha = a_pr;
     bool accepted = false;
     double ft = f, gdt_t;
-    while (alpha >= a_min) {
+    // IPOPT compares with a machine-precision slack (Compare_le: lhs - rhs <= 10 eps |base|)
+    const double EPS = 2.220446049250313e-16;
+    const double slack_phi = 10 * EPS * fabs(phi), slack_th = 10 * EPS * fabs(theta);
+    // tiny-step rule: a step below 10 eps relative size is accepted without line search and forces a mu update
+    if (rel < 10 * EPS) {
+      if (tiny_last && mu <= mu_min) {
+        status = OBCA_SOLVED_TO_ACCEPTABLE_LEVEL;
+        break;
+      }
+      tiny_last = true, force_mu = true;
+      for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.xt[q] = W.x[q] + alpha * W.dx[q];
+      accepted = true;
+    } else
+      tiny_last = false;
+    while (alpha >= a_min && !accepted) {
       for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.xt[q] = W.x[q] + alpha * W.dx[q];
       cta_sync(ctx);
       eval_all(ctx, L, S, W, W.xt, nullptr, W.ct, nullptr, &ft, &gdt_t);
@@ -274,11 +294,11 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       if (okp) {
         bool switching = theta <= theta_min && dphi < 0 && alpha * pow(-dphi, o.s_phi) > o.delta_ls * pow(theta, o.s_theta);
         if (switching) {
-          if (pht <= phi + o.eta_phi * alpha * dphi) {
+          if (pht - (phi + o.eta_phi * alpha * dphi) <= slack_phi) {
             accepted = true;
             break;
           }
-        } else if (tht <= (1 - o.gamma_theta) * theta || pht <= phi - o.gamma_phi * theta) {
+        } else if (tht - (1 - o.gamma_theta) * theta <= slack_th || pht - (phi - o.gamma_phi * theta) <= slack_phi) {
           cta_sync(ctx);
           if (ctx.tid == 0 && sh->filt_n < FILTER_MAX) {
             sh->filt_theta[sh->filt_n] = (1 - o.gamma_theta) * theta;
@@ -292,8 +312,12 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       alpha *= 0.5;
     }
     cta_sync(ctx);
+#ifdef OBCA_HOST_EMU
+    if (getenv("OBCA_TRACE")) printf("       a_pr=%.3e a_du=%.3e alpha=%.3e a_min=%.3e dphi=%.3e dw=%.1e acc=%d\n", a_pr, a_du, alpha, a_min, dphi, dw, (int)accepted);
+#endif
     if (!accepted) {
-      status = OBCA_RESTORATION_FAILED;
+      // IPOPT: a line-search failure at an "acceptable" point (acceptable_tol = 1e-6) ends with Solved_To_Acceptable_Level
+      status = (E0 <= 1e-6 && cviol <= 1e-2 && compl0 <= 1e-2) ? OBCA_SOLVED_TO_ACCEPTABLE_LEVEL : OBCA_RESTORATION_FAILED;
       break;
     }
     // ---- accept the trial point

@@ -21,6 +21,7 @@ _LIB_NAME = "libobca_b200.so"
 
 RETURN_STATUS = {
     0: "Solve_Succeeded",
+    1: "Solved_To_Acceptable_Level",
     -1: "Maximum_Iterations_Exceeded",
     -2: "Restoration_Failed",
     -3: "Error_In_Step_Computation",

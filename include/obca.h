@@ -37,6 +37,7 @@ extern "C" {
 
 /* per-instance return status, mirroring IPOPT's ApplicationReturnStatus strings */
 #define OBCA_SOLVE_SUCCEEDED 0
+#define OBCA_SOLVED_TO_ACCEPTABLE_LEVEL 1   /* search direction below machine precision at the smallest mu */
 #define OBCA_MAXITER_EXCEEDED (-1)
 #define OBCA_RESTORATION_FAILED (-2)
 #define OBCA_ERROR_IN_STEP_COMPUTATION (-3)

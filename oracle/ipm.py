@@ -173,6 +173,8 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
     theta_max, theta_min = 1e4 * max(1.0, th0), 1e-4 * max(1.0, th0)
     filt = []
     delta_w_last = 0.0
+    tiny_last = False
+    force_mu = False
     hist = []
     status = -1
     it = 0
@@ -202,9 +204,11 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
             status = -4
             break
         mu_min = min(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0)  # IPOPT monotone update floor
-        while E(mu) <= o.kappa_eps * mu and mu > mu_min:
+        while (E(mu) <= o.kappa_eps * mu or force_mu) and mu > mu_min:
             mu = max(mu_min, min(o.kappa_mu * mu, mu ** o.theta_mu))
             filt = []
+            force_mu = False
+        force_mu = False
         tau = max(o.tau_min, 1.0 - mu)
 
         # ---- search direction
@@ -256,7 +260,21 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
         a_min *= o.gamma_alpha
         alpha = a_pr
         accepted = False
-        while alpha >= a_min:
+        # IPOPT compares with a machine-precision slack (Compare_le: lhs - rhs <= 10 eps |base|)
+        slack_phi, slack_th = 10 * np.finfo(float).eps * abs(ph), 10 * np.finfo(float).eps * abs(th)
+        # tiny-step rule: a step below 10 eps relative size is accepted without line search and forces a mu update
+        tiny = np.max(np.abs(dx) / (1.0 + np.abs(x))) < 10 * np.finfo(float).eps
+        if tiny:
+            if tiny_last and mu <= mu_min:
+                status = 1
+                break
+            tiny_last = True
+            force_mu = True
+            xt = x + alpha * dx
+            accepted = True
+        else:
+            tiny_last = False
+        while alpha >= a_min and not accepted:
             xt = x + alpha * dx
             ct = nlp.c(xt)
             tht, pht = theta(ct), phi(xt, mu)
@@ -264,16 +282,17 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
             if ok:
                 switching = th <= theta_min and dphi < 0 and alpha * (-dphi) ** o.s_phi > o.delta_ls * th ** o.s_theta
                 if switching:
-                    if pht <= ph + o.eta_phi * alpha * dphi:
+                    if pht - (ph + o.eta_phi * alpha * dphi) <= slack_phi:
                         accepted = True
                         break
-                elif tht <= (1 - o.gamma_theta) * th or pht <= ph - o.gamma_phi * th:
+                elif tht - (1 - o.gamma_theta) * th <= slack_th or pht - (ph - o.gamma_phi * th) <= slack_phi:
                     filt.append(((1 - o.gamma_theta) * th, ph - o.gamma_phi * th))
                     accepted = True
                     break
             alpha *= 0.5
         if not accepted:
-            status = -2
+            # IPOPT: a line-search failure at an "acceptable" point (acceptable_tol = 1e-6) is Solved_To_Acceptable_Level
+            status = 1 if (E(0.0) <= 1e-6 and cviol <= 1e-2 and compl(0.0) <= 1e-2) else -2
             break
         x = x + alpha * dx
         y = y + alpha * dy
