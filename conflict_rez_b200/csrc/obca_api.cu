@@ -46,6 +46,7 @@ struct ObcaHandle {
   double* d_rw;    // [slots][rw_stride]
   Result* d_res;   // [B]
   int* d_counter;
+  long long* d_prof;  // [slots][NPROF + 1]
   int64_t launches;
 };
 
@@ -163,6 +164,7 @@ struct SolveArgs {
   Result* res;
   int B;
   int* counter;
+  long long* prof;
   // debug modes: 0 = solve, 1 = eval at stored iterate, 2 = Newton step at stored iterate
   int mode, b_only;
   double dbg_mu, dbg_dw;
@@ -227,7 +229,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) k_solve(SolveArgs A) {
   __shared__ Shared sh;
   __shared__ double red[40];
   __shared__ int cur;
-  Ctx ctx{(int)threadIdx.x, (int)blockDim.x, red};
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x, red, A.prof ? A.prof + (size_t)blockIdx.x * (NPROF + 1) : nullptr};
+  if (ctx.prof && threadIdx.x == 0) ctx.prof[NPROF] = clock64();
   if (A.mode != 0) {
     run_instance(ctx, A, A.b_only, 0, &sh);
     return;
@@ -314,7 +317,8 @@ int obca_set_options(ObcaHandle* h, const ObcaOptions* opts) {
 
 static void free_device(ObcaHandle* h) {
   dev_free(h->d_L), dev_free(h->d_S), dev_free(h->d_tube), dev_free(h->d_xL), dev_free(h->d_xU);
-  dev_free(h->d_iter), dev_free(h->d_work), dev_free(h->d_rw), dev_free(h->d_res), dev_free(h->d_counter);
+  dev_free(h->d_iter), dev_free(h->d_work), dev_free(h->d_rw), dev_free(h->d_res), dev_free(h->d_counter), dev_free(h->d_prof);
+  h->d_prof = nullptr;
   h->d_L = nullptr, h->d_S = nullptr, h->d_tube = nullptr, h->d_xL = h->d_xU = nullptr;
   h->d_iter = h->d_work = h->d_rw = nullptr, h->d_res = nullptr, h->d_counter = nullptr;
 }
@@ -418,7 +422,8 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   if (dev_alloc((void**)&h->d_L, sizeof(Lay)) || dev_alloc((void**)&h->d_S, sizeof(Stat)) || dev_alloc((void**)&h->d_tube, tube.size() * 8) ||
       dev_alloc((void**)&h->d_xL, L.nx * 8) || dev_alloc((void**)&h->d_xU, L.nx * 8) || dev_alloc((void**)&h->d_iter, (size_t)B * h->it_stride * 8) ||
       dev_alloc((void**)&h->d_work, (size_t)h->slots * h->wk_stride * 8) || dev_alloc((void**)&h->d_rw, (size_t)h->slots * h->rw_stride * 8) ||
-      dev_alloc((void**)&h->d_res, (size_t)B * sizeof(Result)) || dev_alloc((void**)&h->d_counter, sizeof(int)))
+      dev_alloc((void**)&h->d_res, (size_t)B * sizeof(Result)) || dev_alloc((void**)&h->d_counter, sizeof(int)) ||
+      dev_alloc((void**)&h->d_prof, (size_t)h->slots * (NPROF + 1) * sizeof(long long)))
     return fail("obca_set_static: device allocation failed");
   S.tube = h->d_tube;
   h2d(h->d_tube, tube.data(), tube.size() * 8);
@@ -490,6 +495,7 @@ static SolveArgs make_args(ObcaHandle* h, int mode, int b) {
   A.iter = h->d_iter, A.work = h->d_work, A.rw = h->d_rw;
   A.it_stride = h->it_stride, A.wk_stride = h->wk_stride, A.rw_stride = h->rw_stride;
   A.res = h->d_res, A.B = h->dims.batch, A.counter = h->d_counter, A.mode = mode, A.b_only = b;
+  A.prof = getenv("OBCA_PROFILE") ? h->d_prof : nullptr;
   A.dbg_mu = 0, A.dbg_dw = 0;
   return A;
 }
@@ -499,7 +505,7 @@ static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
   (void)stream;
   Shared sh;
   double red[40];
-  Ctx ctx{0, 1, red};
+  Ctx ctx{0, 1, red, nullptr};
   if (A.mode != 0)
     run_instance(ctx, A, A.b_only, 0, &sh);
   else
@@ -543,6 +549,18 @@ int obca_get_stats(ObcaHandle* h, int32_t* status, int32_t* iters, double* obj, 
 }
 
 int64_t obca_launch_count(const ObcaHandle* h) { return h ? h->launches : 0; }
+
+int obca_debug_profile(ObcaHandle* h, int64_t* out, int n) {
+  if (!h || !h->have_static) return fail("obca_debug_profile: call obca_set_static first");
+  if (dev_sync()) return fail("device sync failed");
+  std::vector<long long> buf((size_t)h->slots * (NPROF + 1));
+  d2h(buf.data(), h->d_prof, buf.size() * sizeof(long long));
+  for (int i = 0; i < n && i < NPROF; ++i) {
+    out[i] = 0;
+    for (int s = 0; s < h->slots; ++s) out[i] += buf[(size_t)s * (NPROF + 1) + i];
+  }
+  return NPROF;
+}
 
 int obca_layout(const ObcaHandle* h, int64_t* out, int n) {
   if (!h || !h->have_static) return fail("obca_layout: call obca_set_static first");

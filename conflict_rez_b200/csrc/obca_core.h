@@ -264,7 +264,24 @@ struct Result {
 struct Ctx {
   int tid, nt;
   double* red;  // shared scratch for reductions (>= 40 doubles)
+  long long* prof;  // optional per-slot phase cycle counters [NPROF + 1] (last = time stamp), or nullptr
 };
+
+constexpr int NPROF = 16;
+// phase ids: 0 eval_pairs 1 eval_nodes 2 pair_eliminate 3 node_assemble 4 nullspace 5 cross 6 riccati_bwd 7 riccati_fwd
+//            8 expand+node_residual 9 multipliers 10 local_backsub 11 ipm vector ops / line-search bookkeeping
+OBCA_HD void prof_mark(const Ctx& ctx, int phase) {
+#if defined(__CUDA_ARCH__)
+  if (ctx.prof && ctx.tid == 0) {
+    long long t = clock64();
+    ctx.prof[phase] += t - ctx.prof[NPROF];
+    ctx.prof[NPROF] = t;
+  }
+#else
+  (void)ctx;
+  (void)phase;
+#endif
+}
 
 OBCA_HD void cta_sync(const Ctx&) {
 #if defined(__CUDA_ARCH__)
@@ -629,10 +646,13 @@ OBCA_HDN void eval_nodes(const Ctx& ctx, const Lay& L, const Stat& S, const doub
 
 OBCA_HDN void eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, const double* x, const double* y,
                        double* c, double* gl, double* f, double* gdt) {
+  prof_mark(ctx, 11);
   eval_pairs(ctx, L, S, x, y, c, gl, W.PG);
   cta_sync(ctx);
+  prof_mark(ctx, 0);
   eval_nodes(ctx, L, S, W.init_pose, x, y, c, gl, W.PG, f, gdt);
   cta_sync(ctx);
+  prof_mark(ctx, 1);
 }
 
 }  // namespace obca

@@ -1062,31 +1062,41 @@ OBCA_HDN void local_backsub(const Ctx& ctx, const Lay& L, const Stat& S, const S
 OBCA_HDN int kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double* RW, int* ok_shared) {
   if (ctx.tid == 0) *ok_shared = 1;
   cta_sync(ctx);
+  prof_mark(ctx, 11);
   pair_eliminate(ctx, L, S, W, ok_shared);
   cta_sync(ctx);
+  prof_mark(ctx, 2);
   double hdtdt;
   node_assemble(ctx, L, S, W, ok_shared, &hdtdt);
   cta_sync(ctx);
+  prof_mark(ctx, 3);
   interval_nullspace(ctx, L, S, W, ok_shared, ok_shared + 1);
   cta_sync(ctx);
+  prof_mark(ctx, 4);
   interval_cross(ctx, L, W);
   cta_sync(ctx);
+  prof_mark(ctx, 5);
   riccati_backward(ctx, L, W, RW, hdtdt, ok_shared);
   cta_sync(ctx);
+  prof_mark(ctx, 6);
   int ok = *ok_shared;
   if (!ok) return 0;
   riccati_forward(ctx, L, W, ok_shared);
   cta_sync(ctx);
+  prof_mark(ctx, 7);
   ok = *ok_shared;
   if (!ok) return 0;
   expand_primal(ctx, L, W);
   cta_sync(ctx);
   node_residual(ctx, L, W);
   cta_sync(ctx);
+  prof_mark(ctx, 8);
   recover_multipliers(ctx, L, S, W);
   cta_sync(ctx);
+  prof_mark(ctx, 9);
   local_backsub(ctx, L, S, W);
   cta_sync(ctx);
+  prof_mark(ctx, 10);
   return 1;
 }
 

@@ -84,6 +84,7 @@ EXPORTS = [
     "obca_debug_set_iterate",
     "obca_debug_eval",
     "obca_debug_step",
+    "obca_debug_profile",
 ]
 
 
@@ -120,6 +121,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.obca_debug_set_iterate.argtypes = [vp, ctypes.c_int] + [_dp] * 4
     lib.obca_debug_eval.argtypes = [vp, ctypes.c_int, _dp, _dp, _dp]
     lib.obca_debug_step.argtypes = [vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, _dp, _dp, i32p]
+    lib.obca_debug_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
     return lib
 
 
@@ -208,7 +210,7 @@ class ObcaSolver:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _to_dev(self, a, shape):
-        t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64).reshape(shape))
+        t = torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True).reshape(shape))
         if self.device.type == "cuda":
             t = t.pin_memory().to(self.device, non_blocking=True)
         return t.contiguous()
@@ -319,6 +321,14 @@ class ObcaSolver:
                  "oYINIT", "oYCOL", "oYCONT", "oYTERM", "oYOBS", "oYTUBE", "oYPAIR", "m_active", "nb"]
         assert n == len(names)
         return {k: int(buf[i]) for i, k in enumerate(names)}
+
+    PHASES = ["eval_pairs", "eval_nodes", "pair_eliminate", "node_assemble", "nullspace", "cross", "riccati_bwd", "riccati_fwd",
+              "expand+residual", "multipliers", "local_backsub", "ipm_vector_ops"]
+
+    def debug_profile(self):
+        buf = (ctypes.c_int64 * 16)()
+        self._check(self.lib.obca_debug_profile(self.handle, buf, 16))
+        return {k: int(buf[i]) for i, k in enumerate(self.PHASES)}
 
     def debug_get_iterate(self, b=0):
         L = self.layout()

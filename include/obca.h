@@ -121,6 +121,10 @@ int obca_debug_eval(ObcaHandle* h, int b, double* c, double* gl, double* f);
  * returns 1 in *ok when the reduced Hessian was positive definite */
 int obca_debug_step(ObcaHandle* h, int b, double mu, double delta_w, double* dx, double* dy, int32_t* ok);
 
+/* per-phase SM cycle counters summed over the resident CTAs (filled when the environment variable OBCA_PROFILE is set
+ * at solve time; phase ids in obca_core.h) */
+int obca_debug_profile(ObcaHandle* h, int64_t* out, int n);
+
 #ifdef __cplusplus
 }
 #endif

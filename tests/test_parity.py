@@ -1,0 +1,184 @@
+"""Parity of the solver against the CPU oracle, through the C ABI (ctypes).
+
+Every test runs against two builds of the *same* kernel source:
+  * ``cuda`` -- libobca_b200.so on the B200 (``-m gpu``): the product;
+  * ``emu``  -- the developer host emulation (one CPU thread plays one CTA): lets the CPU-only CI exercise the host
+    logic, the ABI and the algorithm.  It is not reachable from the package.
+
+Tolerances (north_star): objective 1e-6 relative, constraint violation <= 1e-6, trajectories 1e-4 where both sides
+reach the same local optimum.  Raw residuals / Newton steps are compared much tighter (1e-8 relative).
+"""
+import numpy as np
+import pytest
+
+from cases import check_solution_properties, load_golden, oracle_newton_step
+from conftest import make_case
+from layout_map import build_maps
+
+from conflict_rez_b200.solver import ObcaSolver, SolveOptions
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=BACKENDS)
+def backend(request):
+    if request.param == "emu":
+        return request.getfixturevalue("emu_lib"), "cpu"
+    return request.getfixturevalue("cuda_lib"), "cuda:0"
+
+
+def _solver(backend, prob, **opts):
+    lib, dev = backend
+    return ObcaSolver(prob, SolveOptions(**opts), device=dev, lib=lib)
+
+
+@pytest.fixture(scope="module")
+def nlp_cache():
+    return {}
+
+
+def _nlp(cache, key, prob):
+    from oracle.nlp import CollocationNLP
+
+    if key not in cache:
+        cache[key] = CollocationNLP(prob)
+    return cache[key]
+
+
+@pytest.mark.parametrize("agents", [("vehicle_1",), ("vehicle_1", "vehicle_2"), ("vehicle_3",)], ids=["single", "joint_ragged", "stop_move"])
+def test_residuals_gradient_and_newton_step(backend, strategy_file, nlp_cache, agents):
+    """c(x), grad f + J'y, f and the Newton step (dx, dy) at the solver's own initial point vs the oracle."""
+    from oracle import ipm
+
+    prob, guess = make_case(strategy_file, agents)
+    nlp = _nlp(nlp_cache, agents, prob)
+    sv = _solver(backend, prob, max_iter=0)
+    sv.solve(guess)  # max_iter = 0: slack initialisation + push into the bounds only
+    L = sv.layout()
+    assert L["m_active"] == nlp.m and L["nb"] == int(np.isfinite(nlp.xL).sum() + np.isfinite(nlp.xU).sum())
+    ix, iy = build_maps(L, nlp)
+    xd, _, zLd, zUd = sv.debug_get_iterate(0)
+    x0 = ipm.push_into_bounds(nlp.init_slacks(nlp.pack(guess)), nlp.xL, nlp.xU, 1e-2, 1e-2)
+    assert np.allclose(xd[ix], x0, rtol=0, atol=1e-10)
+    rng = np.random.default_rng(5)
+    y = 0.3 * rng.standard_normal(nlp.m)
+    yd = np.zeros(L["ny"])
+    yd[iy] = y
+    sv.debug_set_iterate(0, y=yd)
+    c_d, gl_d, f_d = sv.debug_eval(0)
+    mu, dw = 0.1, 1e-3
+    dx_o, dy_o, c_o, gl_o = oracle_newton_step(nlp, x0, y, zLd[ix], zUd[ix], mu, dw)
+    assert abs(f_d - nlp.f(x0)) <= 1e-10 * abs(f_d)
+    assert np.abs(c_d[iy] - c_o).max() <= 1e-9 * max(1.0, np.abs(c_o).max())
+    assert np.abs(gl_d[ix] - gl_o).max() <= 1e-9 * max(1.0, np.abs(gl_o).max())
+    dx_d, dy_d, ok = sv.debug_step(0, mu, dw)
+    assert ok == 1
+    if agents != ("vehicle_3",):  # the stop move makes the KKT matrix singular (LICQ fails): steps are not unique there
+        assert np.abs(dx_d[ix] - dx_o).max() <= 1e-7 * np.abs(dx_o).max()
+        assert np.abs(dy_d[iy] - dy_o).max() <= 1e-7 * np.abs(dy_o).max()
+    else:
+        # any solution of the singular system is acceptable: check the KKT residual of the device step instead
+        hasL, hasU = np.isfinite(nlp.xL), np.isfinite(nlp.xU)
+        J = nlp.jac(x0)
+        r2 = J @ dx_d[ix] + c_o
+        cols = np.concatenate([r.ravel() for r in nlp.r_col])
+        mask = np.ones(nlp.m, bool)
+        mask[cols] = False
+        assert np.abs(r2[mask]).max() <= 1e-6 * max(1.0, np.abs(c_o).max())
+    sv.close()
+
+
+@pytest.mark.parametrize("name", ["single_vehicle_1", "single_vehicle_2", "single_vehicle_2_free_heading", "joint_vehicle_1_2"])
+def test_solution_matches_golden(backend, name):
+    """Full interior-point solve from the golden warm start vs the oracle's golden solution."""
+    prob, guess, gold = load_golden(name)
+    # tol = 1e-7: the structured solve has no iterative refinement yet, so the last digits IPOPT/the oracle squeeze out
+    # at 1e-8 are not always reachable (DESIGN.md "known limits"); 1e-7 is well inside the parity tolerances below
+    sv = _solver(backend, prob, tol=1e-7, constr_viol_tol=1e-7, max_iter=500)
+    res = sv.solve(guess)
+    assert res.status[0] == 0, res.return_status(0)
+    assert abs(res.obj[0] - gold["obj"]) <= 1e-6 * abs(gold["obj"])
+    assert res.cviol[0] <= 1e-6
+    assert np.abs(res.z[0] - gold["z"]).max() <= 1e-4
+    assert abs(res.dt[0] - gold["dt"]) <= 1e-6
+    worst = check_solution_properties(prob, res.z, res.dt, tol=1e-6)
+    assert worst["collocation"] <= 1e-6 and worst["continuity"] <= 1e-6 and worst["init"] <= 1e-6 and worst["terminal"] <= 1e-6
+    assert worst["tube"] <= 1e-6 and worst["bounds"] <= 1e-9
+    assert worst["obstacle_clearance"] >= prob.dmin - 1e-5
+    if prob.V > 1:
+        assert worst["vehicle_clearance"] >= prob.dmin - 1e-5
+    print(name, "iterations: solver %d, oracle %d" % (res.iters[0], gold["iters"]))
+    sv.close()
+
+
+def test_reference_tolerance_iteration_counts(backend, strategy_file):
+    """At the reference's own tolerances (tol = constr_viol_tol = 1e-2) the solve converges and lands within 1e-3 of the
+    tight solution; iteration counts are reported side by side with the oracle's."""
+    prob, guess, gold = load_golden("single_vehicle_1")
+    sv = _solver(backend, prob)
+    res = sv.solve(guess)
+    assert res.status[0] == 0
+    assert abs(res.obj[0] - gold["obj"]) <= 1e-3 * abs(gold["obj"])
+    assert res.iters[0] <= 80
+    sv.close()
+
+
+def test_batch_equals_individual_solves_and_is_deterministic(backend, strategy_file):
+    """Instances of a batch are independent: a batch of 3 perturbed initial poses == 3 separate solves, bit for bit,
+    and repeated runs reproduce the same bits."""
+    from conflict_rez_b200.control.batch_planner import random_init_offsets
+
+    offs = random_init_offsets(3, 1, seed=3)
+    prob, guess = make_case(strategy_file, ("vehicle_2",), init_offsets=offs)
+    sv = _solver(backend, prob)
+    r1, r2 = sv.solve(guess), sv.solve(guess)
+    assert np.array_equal(r1.z, r2.z) and np.array_equal(r1.iters, r2.iters)
+    assert (r1.status == 0).all()
+    assert np.abs(r1.z[:, 0, 0, :3] - prob.init_pose[:, 0]).max() <= 1e-6
+    for b in range(3):
+        pb, gb = prob.instance(b), guess.instance(b)
+        pb.init_pose = pb.init_pose  # single-instance view
+        s1 = _solver(backend, pb)
+        rb = s1.solve(gb)
+        assert np.array_equal(rb.z[0], r1.z[b]) and rb.iters[0] == r1.iters[b]
+        s1.close()
+    sv.close()
+
+
+def test_error_paths(backend):
+    """Bad dimensions and call order are reported through return codes + obca_last_error (no crash, no fallback)."""
+    import ctypes
+
+    from conflict_rez_b200 import solver as S
+
+    lib, _ = backend
+    dims = S.ObcaDims(batch=1, V=1, O=6, K=4, n_per_set=5)
+    dims.n_sets[0] = 5
+    h = ctypes.c_void_p()
+    assert lib.obca_create(ctypes.byref(dims), None, 0, ctypes.byref(h)) < 0
+    assert b"K = 5" in lib.obca_last_error()
+    dims.K, dims.V = 5, 9
+    assert lib.obca_create(ctypes.byref(dims), None, 0, ctypes.byref(h)) < 0
+    dims.V = 1
+    assert lib.obca_create(ctypes.byref(dims), None, 0, ctypes.byref(h)) == 0
+    assert lib.obca_solve(h, None) < 0  # obca_set_static has not been called
+    assert b"obca_set_static" in lib.obca_last_error()
+    lib.obca_destroy(h)
+
+
+@pytest.mark.gpu
+def test_four_vehicle_batch_properties(cuda_lib, strategy_file):
+    """Full-size 4-vehicle joint problem (n = 75 601 per instance), batch of 8 randomized initial conditions through the
+    reference pipeline (single solves -> pair duals -> joint solve): every converged plan satisfies the problem
+    statement (dynamics, tubes, terminal conditions) and is collision free by plain geometry."""
+    from conflict_rez_b200.control.batch_planner import random_init_offsets, solve_joint_batch
+
+    agents = ["vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"]
+    plan = solve_joint_batch(strategy_file, agents, random_init_offsets(8, 4, seed=0), SolveOptions(max_iter=600), lib=cuda_lib)
+    res = plan.result
+    ok = res.status >= 0
+    assert ok.sum() >= 6, res.status
+    worst = check_solution_properties(plan.problem, res.z[ok], res.dt[ok])
+    assert worst["collocation"] <= 1e-2 and worst["tube"] <= 1e-2 and worst["terminal"] <= 1e-2 and worst["init"] <= 1e-2
+    assert worst["obstacle_clearance"] >= plan.problem.dmin - 1e-2
+    assert worst["vehicle_clearance"] >= plan.problem.dmin - 1e-2
