@@ -167,16 +167,16 @@ struct SolveArgs {
   long long* prof;
   // debug modes: 0 = solve, 1 = eval at stored iterate, 2 = Newton step at stored iterate
   int mode, b_only;
+  int rw_in_smem;  // Riccati work arena in dynamic shared memory (else per-slot global memory)
   double dbg_mu, dbg_dw;
 };
 
-OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, int b, int slot, Shared* sh) {
+OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, int b, int slot, Shared* sh, double* RW) {
   const Lay& L = *A.L;
   const Stat& S = *A.S;
   Scratch W;
   carve_iterate(W, L, A.iter + (size_t)b * A.it_stride);
   carve_work(W, L, A.work + (size_t)slot * A.wk_stride);
-  double* RW = A.rw + (size_t)slot * A.rw_stride;
   if (A.mode == 0) {
     ipm_solve(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, sh, A.res + b);
     return;
@@ -229,10 +229,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) k_solve(SolveArgs A) {
   __shared__ Shared sh;
   __shared__ double red[40];
   __shared__ int cur;
+  extern __shared__ double arena[];
+  double* RW = A.rw_in_smem ? arena : A.rw + (size_t)blockIdx.x * A.rw_stride;
   Ctx ctx{(int)threadIdx.x, (int)blockDim.x, red, A.prof ? A.prof + (size_t)blockIdx.x * (NPROF + 1) : nullptr};
   if (ctx.prof && threadIdx.x == 0) ctx.prof[NPROF] = clock64();
   if (A.mode != 0) {
-    run_instance(ctx, A, A.b_only, 0, &sh);
+    run_instance(ctx, A, A.b_only, 0, &sh, RW);
     return;
   }
   for (;;) {
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) k_solve(SolveArgs A) {
     __syncthreads();
     int b = cur;
     if (b >= A.B) break;
-    run_instance(ctx, A, b, blockIdx.x, &sh);
+    run_instance(ctx, A, b, blockIdx.x, &sh, RW);
   }
 }
 __global__ void k_stats(const Result* res, int B, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf, double* compl_inf) {
@@ -497,6 +499,7 @@ static SolveArgs make_args(ObcaHandle* h, int mode, int b) {
   A.res = h->d_res, A.B = h->dims.batch, A.counter = h->d_counter, A.mode = mode, A.b_only = b;
   A.prof = getenv("OBCA_PROFILE") ? h->d_prof : nullptr;
   A.dbg_mu = 0, A.dbg_dw = 0;
+  A.rw_in_smem = h->rw_stride * sizeof(double) <= 200 * 1024;
   return A;
 }
 
@@ -507,14 +510,16 @@ static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
   double red[40];
   Ctx ctx{0, 1, red, nullptr};
   if (A.mode != 0)
-    run_instance(ctx, A, A.b_only, 0, &sh);
+    run_instance(ctx, A, A.b_only, 0, &sh, A.rw);
   else
-    for (int b = 0; b < A.B; ++b) run_instance(ctx, A, b, 0, &sh);
+    for (int b = 0; b < A.B; ++b) run_instance(ctx, A, b, 0, &sh, A.rw);
 #else
   cudaStream_t s = (cudaStream_t)stream;
   if (A.mode == 0) CUDA_OK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   int grid = A.mode == 0 ? h->slots : 1;
-  k_solve<<<grid, CTA_THREADS, 0, s>>>(A);
+  size_t smem = A.rw_in_smem ? h->rw_stride * sizeof(double) : 0;
+  if (smem) CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_solve<<<grid, CTA_THREADS, smem, s>>>(A);
   h->launches++;
   CUDA_OK(cudaGetLastError());
 #endif

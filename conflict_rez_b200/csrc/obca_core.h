@@ -52,7 +52,7 @@ constexpr int MAXP = MAXV * (MAXV - 1) / 2;
 constexpr int NXMAX = 7 * MAXV + 1;
 constexpr int NUMAX = NP * MAXV;
 constexpr int FILTER_MAX = 64;
-constexpr double DELTA_C_LOCAL = 1e-10;
+constexpr double DELTA_C_LOCAL = 1e-8;
 
 // ------------------------------------------------------------------------------------------------
 // [LAYOUT]
@@ -189,7 +189,6 @@ struct Scratch {
   double* MAB;  // [P][Nmax][169 + 26]     projected cross-vehicle coupling + gradients
   double* RK;   // [Nmax][nU*nX + nU]      Riccati gains
   double* RP;   // [Nmax+1][nX*nX + nX]    cost-to-go
-  double* RA;   // [Nmax][nX*nX + nX*nU + nX]  stage dynamics
   double* RX;   // [Nmax+1][nX] states, [Nmax][nU] controls
   double* SS;   // [V][Nmax][42] stage solutions
   double* init_pose;  // [V][3]
@@ -209,7 +208,6 @@ inline size_t work_doubles(const Lay& L) {
   n += (size_t)L.P * L.Nmax * (NRED * NRED + 2 * NRED);
   n += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
   n += (size_t)(L.Nmax + 1) * (L.nX * L.nX + L.nX);
-  n += (size_t)L.Nmax * (L.nX * L.nX + L.nX * L.nU + L.nX);
   n += (size_t)(L.Nmax + 1) * L.nX + (size_t)L.Nmax * L.nU;
   return n + 64;
 }
@@ -248,7 +246,6 @@ OBCA_HD void carve_work(Scratch& W, const Lay& L, double* p) {
   W.MAB = p, p += (size_t)L.P * L.Nmax * (NRED * NRED + 2 * NRED);
   W.RK = p, p += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
   W.RP = p, p += (size_t)(L.Nmax + 1) * (L.nX * L.nX + L.nX);
-  W.RA = p, p += (size_t)L.Nmax * (L.nX * L.nX + L.nX * L.nU + L.nX);
   W.RX = p, p += (size_t)(L.Nmax + 1) * L.nX + (size_t)L.Nmax * L.nU;
   W.SS = p;
 }

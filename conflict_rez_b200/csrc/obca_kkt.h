@@ -18,10 +18,6 @@ struct KktAux {
   double* RW;  // Riccati work area
 };
 
-inline size_t riccati_work_doubles(const Lay& L) {
-  size_t nX = L.nX, nU = L.nU;
-  return 4 * nX * nX + 4 * nX * nU + 3 * nU * nU + 8 * (nX + nU) + 16;
-}
 
 // ------------------------------------------------------------------------------------------------
 // [LOCAL] pair blocks: one thread per (pair, node)
@@ -599,14 +595,25 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// [RICCATI]
+// [RICCATI]  stage i: state X = (xi_1 .. xi_V, dt), control U = free directions of the active vehicles (compacted,
+// nu_i = sum_a np_a(i) <= NP V).  The dynamics are block diagonal per vehicle plus a dt column:
+//   xi_a' = Aa xi_a + da dt + Ba u_a + ca   (rows 28..34 of the block's T map),   dt' = dt.
+// All stage matrices live in the work arena RW (shared memory on the device).
 // ------------------------------------------------------------------------------------------------
 struct RicWork {
-  double *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *g;
+  double *P, *p, *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *K, *Ab, *Bb, *db, *cb;
+  int *uoff, *npv;  // [MAXV + 1]
 };
+
+inline size_t riccati_work_doubles(const Lay& L) {
+  size_t nX = L.nX, nU = L.nU;
+  return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32;
+}
 
 OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
   int nX = L.nX, nU = L.nU;
+  R.P = w, w += nX * nX;
+  R.p = w, w += nX;
   R.Q = w, w += nX * nX;
   R.S = w, w += nU * nX;
   R.R = w, w += nU * nU;
@@ -617,193 +624,273 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
   R.pc = w, w += nX;
   R.F = w, w += nU * nU;
   R.Gm = w, w += nU * (nX + 1);
-  R.g = w, w += nU;
+  R.K = w, w += nU * (nX + 1);
+  R.Ab = w, w += L.V * 49;
+  R.Bb = w, w += L.V * 7 * NP;
+  R.db = w, w += L.V * 7;
+  R.cb = w, w += L.V * 7;
+  R.uoff = (int*)w;
+  R.npv = R.uoff + (MAXV + 1);
 }
 
-OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R, int i, double hdtdt,
-                                     double* A, double* B, double* cvec) {
-  const int nX = L.nX, nU = L.nU, idt = 7 * L.V;
-  for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.Q[q] = 0, A[q] = 0;
-  for (int q = ctx.tid; q < nU * nX; q += ctx.nt) R.S[q] = 0, B[q] = 0;
-  for (int q = ctx.tid; q < nU * nU; q += ctx.nt) R.R[q] = 0;
-  for (int q = ctx.tid; q < nX; q += ctx.nt) R.q[q] = 0, cvec[q] = 0;
-  for (int q = ctx.tid; q < nU; q += ctx.nt) R.r[q] = 0;
-  cta_sync(ctx);
-  // own-vehicle blocks: one thread per vehicle (tiny)
-  for (int a = ctx.tid; a < L.V; a += ctx.nt) {
-    if (i >= L.N[a]) {
-      for (int j = 0; j < NP; ++j) R.R[(NP * a + j) * nU + NP * a + j] = 1.0;
-      continue;
-    }
-    const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
+// free directions of block (a, i): 35 - rank, 0 for a vehicle whose horizon has ended
+OBCA_HD int block_np(const Lay& L, const Scratch& W, int a, int i) {
+  if (i >= L.N[a]) return 0;
+  int np = NW - (int)W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_META];
+  return np > NP ? NP : np;
+}
+
+// reduced coordinate of vehicle a -> (kind, index): kind 0 = state index, 1 = control index, -1 = unused control slot
+OBCA_HD int red_target(int a, int rc, int V, const int* uoff, const int* npv, int* kind) {
+  if (rc < 7) {
+    *kind = 0;
+    return 7 * a + rc;
+  }
+  if (rc == IDT) {
+    *kind = 0;
+    return 7 * V;
+  }
+  if (rc - 7 < npv[a]) {
+    *kind = 1;
+    return uoff[a] + rc - 7;
+  }
+  *kind = -1;
+  return 0;
+}
+
+OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R, int i, double hdtdt, int nu) {
+  const int nX = L.nX, idt = 7 * L.V, V = L.V;
+  for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.Q[q] = 0;
+  for (int q = ctx.tid; q < nu * nX; q += ctx.nt) R.S[q] = 0;
+  for (int q = ctx.tid; q < nu * nu; q += ctx.nt) R.R[q] = 0;
+  // block dynamics from the T maps
+  for (int it = ctx.tid; it < V * 7 * (NRED + 1); it += ctx.nt) {
+    int a = it / (7 * (NRED + 1)), r = (it / (NRED + 1)) % 7, cc = it % (NRED + 1);
+    bool active = i < L.N[a];
     const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
-    const double* s0 = T + NW * NRED;
-    int rk = (int)W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_META];
-    int np = NW - rk;
-    for (int r = 0; r < 7; ++r) {
-      for (int cc = 0; cc < 7; ++cc) R.Q[(7 * a + r) * nX + 7 * a + cc] += Mo[sym(r, cc)];
-      R.Q[(7 * a + r) * nX + idt] += Mo[sym(IDT, r)];
-      R.Q[idt * nX + 7 * a + r] += Mo[sym(IDT, r)];
-      R.q[7 * a + r] += Mo[NSYM + r];
-      for (int cc = 0; cc < 7; ++cc) A[(7 * a + r) * nX + 7 * a + cc] = T[(28 + r) * NRED + cc];
-      A[(7 * a + r) * nX + idt] = T[(28 + r) * NRED + IDT];
-      for (int j = 0; j < NP; ++j) B[(7 * a + r) * nU + NP * a + j] = T[(28 + r) * NRED + 7 + j];
-      cvec[7 * a + r] = s0[28 + r];
-    }
-    for (int j = 0; j < NP; ++j) {
-      for (int cc = 0; cc < 7; ++cc) R.S[(NP * a + j) * nX + 7 * a + cc] += Mo[sym(7 + j, cc)];
-      R.S[(NP * a + j) * nX + idt] += Mo[sym(IDT, 7 + j)];
-      for (int jj = 0; jj < NP; ++jj) R.R[(NP * a + j) * nU + NP * a + jj] += Mo[sym(7 + j, 7 + jj)];
-      if (j >= np) R.R[(NP * a + j) * nU + NP * a + j] += 1.0;
-      R.r[NP * a + j] += Mo[NSYM + 7 + j];
-    }
+    double v = 0.0;
+    if (active) v = cc < NRED ? T[(28 + r) * NRED + cc] : T[NW * NRED + 28 + r];
+    if (cc < 7) R.Ab[a * 49 + r * 7 + cc] = v;
+    else if (cc < IDT) R.Bb[(a * 7 + r) * NP + cc - 7] = v;
+    else if (cc == IDT) R.db[a * 7 + r] = v;
+    else R.cb[a * 7 + r] = v;
   }
   cta_sync(ctx);
-  // dt diagonal + cross-vehicle terms: thread 0 (serialised to keep the sums deterministic)
-  if (ctx.tid == 0) {
-    A[idt * nX + idt] = 1.0;
-    double qdd = 0, qd = 0;
-    for (int a = 0; a < L.V; ++a) {
-      if (i >= L.N[a]) continue;
-      const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
-      qdd += Mo[sym(IDT, IDT)];
-      qd += Mo[NSYM + IDT];
+  // pass A: own-vehicle entries that do not involve dt
+  for (int it = ctx.tid; it < V * NRED * NRED; it += ctx.nt) {
+    int a = it / (NRED * NRED), r = (it / NRED) % NRED, cc = it % NRED;
+    if (i >= L.N[a] || r == IDT || cc == IDT) continue;
+    int kr, kc;
+    int tr = red_target(a, r, V, R.uoff, R.npv, &kr), tc = red_target(a, cc, V, R.uoff, R.npv, &kc);
+    if (kr < 0 || kc < 0) continue;
+    double v = W.MA[(size_t)(a * L.Nmax + i) * (NSYM + NRED) + sym(r, cc)];
+    if (kr == 0 && kc == 0) R.Q[tr * nX + tc] = v;
+    else if (kr == 1 && kc == 0) R.S[tr * nX + tc] = v;
+    else if (kr == 1 && kc == 1) R.R[tr * nu + tc] = v;
+  }
+  // pass B: cross-vehicle entries that do not involve dt (each (pair, ra, cb) owns its targets)
+  for (int it = ctx.tid; it < L.P * NRED * NRED; it += ctx.nt) {
+    int p = it / (NRED * NRED), ra = (it / NRED) % NRED, cb = it % NRED;
+    if (i * NK >= L.Mp[p] || ra == IDT || cb == IDT) continue;
+    int a = L.pa[p], b = L.pb[p], ka, kb;
+    int ta = red_target(a, ra, V, R.uoff, R.npv, &ka), tb = red_target(b, cb, V, R.uoff, R.npv, &kb);
+    if (ka < 0 || kb < 0) continue;
+    double v = W.MAB[(size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED) + ra * NRED + cb];
+    if (ka == 0 && kb == 0) R.Q[ta * nX + tb] = v, R.Q[tb * nX + ta] = v;
+    else if (ka == 1 && kb == 0) R.S[ta * nX + tb] = v;
+    else if (ka == 0 && kb == 1) R.S[tb * nX + ta] = v;
+    else R.R[ta * nu + tb] = v, R.R[tb * nu + ta] = v;
+  }
+  // pass C: everything that touches dt, and the gradients: one thread per target, fixed summation order
+  for (int t = ctx.tid; t < idt + nu + 1; t += ctx.nt) {
+    int a = -1, rc = IDT;
+    if (t < idt) a = t / 7, rc = t % 7;
+    else if (t < idt + nu) {
+      for (int aa = 0; aa < V; ++aa)
+        if (t - idt >= R.uoff[aa] && t - idt < R.uoff[aa] + R.npv[aa]) a = aa, rc = 7 + t - idt - R.uoff[aa];
     }
-    if (i == 0) qdd += hdtdt, qd += W.gphi[L.oDT];
-    for (int p = 0; p < L.P; ++p) {
-      if (i * NK >= L.Mp[p]) continue;
-      int a = L.pa[p], b = L.pb[p];
-      const double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
-      for (int ra = 0; ra < NRED; ++ra)
-        for (int cb = 0; cb < NRED; ++cb) {
-          double v = Mo[ra * NRED + cb];
-          if (v == 0.0) continue;
-          // ra in reduced coords of a, cb in reduced coords of b; negative = control index
-          int ia = ra < 7 ? 7 * a + ra : (ra < IDT ? -(NP * a + ra - 7) - 1 : idt);
-          int ib = cb < 7 ? 7 * b + cb : (cb < IDT ? -(NP * b + cb - 7) - 1 : idt);
-          if (ia >= 0 && ib >= 0) {
-            if (ia == idt && ib == idt) qdd += 2.0 * v;
-            else R.Q[ia * nX + ib] += v, R.Q[ib * nX + ia] += v;
-          } else if (ia < 0 && ib >= 0) R.S[(-ia - 1) * nX + ib] += v;
-          else if (ia >= 0 && ib < 0) R.S[(-ib - 1) * nX + ia] += v;
-          else R.R[(-ia - 1) * nU + (-ib - 1)] += v, R.R[(-ib - 1) * nU + (-ia - 1)] += v;
-        }
-      for (int ra = 0; ra < NRED; ++ra) {
-        double ga = Mo[NRED * NRED + ra], gb = Mo[NRED * NRED + NRED + ra];
-        if (ra < 7) R.q[7 * a + ra] += ga, R.q[7 * b + ra] += gb;
-        else if (ra < IDT) R.r[NP * a + ra - 7] += ga, R.r[NP * b + ra - 7] += gb;
-        else qd += ga + gb;
+    double hd = 0, g = 0;
+    if (a >= 0) {
+      if (i < L.N[a]) {
+        const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
+        hd = Mo[sym(IDT, rc)], g = Mo[NSYM + rc];
       }
+      for (int p = 0; p < L.P; ++p) {
+        if (i * NK >= L.Mp[p]) continue;
+        const double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
+        if (L.pa[p] == a) hd += Mo[rc * NRED + IDT], g += Mo[NRED * NRED + rc];
+        else if (L.pb[p] == a) hd += Mo[IDT * NRED + rc], g += Mo[NRED * NRED + NRED + rc];
+      }
+      if (t < idt) R.Q[t * nX + idt] = hd, R.Q[idt * nX + t] = hd, R.q[t] = g;
+      else R.S[(t - idt) * nX + idt] = hd, R.r[t - idt] = g;
+    } else {
+      for (int aa = 0; aa < V; ++aa) {
+        if (i >= L.N[aa]) continue;
+        const double* Mo = W.MA + (size_t)(aa * L.Nmax + i) * (NSYM + NRED);
+        hd += Mo[sym(IDT, IDT)], g += Mo[NSYM + IDT];
+      }
+      for (int p = 0; p < L.P; ++p) {
+        if (i * NK >= L.Mp[p]) continue;
+        const double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
+        hd += 2.0 * Mo[IDT * NRED + IDT], g += Mo[NRED * NRED + IDT] + Mo[NRED * NRED + NRED + IDT];
+      }
+      if (i == 0) hd += hdtdt, g += W.gphi[L.oDT];
+      R.Q[idt * nX + idt] = hd, R.q[idt] = g;
     }
-    R.Q[idt * nX + idt] += qdd;
-    R.q[idt] += qd;
   }
   cta_sync(ctx);
 }
 
 OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, double* RW, double hdtdt, int* ok) {
-  const int nX = L.nX, nU = L.nU;
+  const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V;
   RicWork R;
   ric_carve(R, L, RW);
-  const size_t pstride = (size_t)nX * nX + nX, kstride = (size_t)nU * nX + nU, astride = (size_t)nX * nX + (size_t)nX * nU + nX;
-  double* Pn = W.RP + (size_t)L.Nmax * pstride;
-  for (int q = ctx.tid; q < (int)pstride; q += ctx.nt) Pn[q] = 0;
+  const size_t pstride = (size_t)nX * nX + nX, kstride = (size_t)nUmax * nX + nUmax;
+  for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.P[q] = 0;
+  for (int q = ctx.tid; q < nX; q += ctx.nt) R.p[q] = 0;
+  {
+    double* Pn = W.RP + (size_t)L.Nmax * pstride;
+    for (int q = ctx.tid; q < (int)pstride; q += ctx.nt) Pn[q] = 0;
+  }
   cta_sync(ctx);
   for (int i = L.Nmax - 1; i >= 0; --i) {
-    double* A = W.RA + (size_t)i * astride;
-    double* B = A + nX * nX;
-    double* cv = B + nX * nU;
-    const double* P1 = W.RP + (size_t)(i + 1) * pstride;
-    const double* p1 = P1 + nX * nX;
-    double* P0 = W.RP + (size_t)i * pstride;
-    double* p0 = P0 + nX * nX;
-    double* Kg = W.RK + (size_t)i * kstride;
-    double* kg = Kg + nU * nX;
-    riccati_stage_assemble(ctx, L, W, R, i, hdtdt, A, B, cv);
-    // PA = P1 A ; PB = P1 B ; pc = P1 c + p1
-    for (int q = ctx.tid; q < nX * (nX + nU + 1); q += ctx.nt) {
-      int r = q / (nX + nU + 1), col = q % (nX + nU + 1);
+    if (ctx.tid == 0) {
+      int off = 0;
+      for (int a = 0; a < V; ++a) {
+        R.uoff[a] = off;
+        R.npv[a] = block_np(L, W, a, i);
+        off += R.npv[a];
+      }
+      R.uoff[V] = off;
+    }
+    cta_sync(ctx);
+    const int nu = R.uoff[V];
+    riccati_stage_assemble(ctx, L, W, R, i, hdtdt, nu);
+    // PA = P A ; PB = P B ; pc = P c + p   (block structure of A, B)
+    for (int it = ctx.tid; it < nX * (nX + nu + 1); it += ctx.nt) {
+      int r = it / (nX + nu + 1), col = it % (nX + nu + 1);
+      const double* Pr = R.P + r * nX;
       double s = 0;
-      if (col < nX) {
-        for (int m = 0; m < nX; ++m) s += P1[r * nX + m] * A[m * nX + col];
+      if (col < idt) {
+        int a = col / 7, c = col % 7;
+        for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Ab[a * 49 + m * 7 + c];
         R.PA[r * nX + col] = s;
-      } else if (col < nX + nU) {
-        int cc = col - nX;
-        for (int m = 0; m < nX; ++m) s += P1[r * nX + m] * B[m * nU + cc];
-        R.PB[r * nU + cc] = s;
+      } else if (col == idt) {
+        s = Pr[idt];
+        for (int m = 0; m < idt; ++m) s += Pr[m] * R.db[m];
+        R.PA[r * nX + idt] = s;
+      } else if (col < nX + nu) {
+        int u = col - nX, a = 0;
+        while (u >= R.uoff[a + 1]) ++a;
+        int j = u - R.uoff[a];
+        for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Bb[(a * 7 + m) * NP + j];
+        R.PB[r * nu + u] = s;
       } else {
-        for (int m = 0; m < nX; ++m) s += P1[r * nX + m] * cv[m];
-        R.pc[r] = s + p1[r];
+        s = R.p[r];
+        for (int m = 0; m < idt; ++m) s += Pr[m] * R.cb[m];
+        R.pc[r] = s;
       }
     }
     cta_sync(ctx);
     // F = R + B'PB ; Gm = [S + B'PA | r + B'pc]
-    for (int q = ctx.tid; q < nU * (nU + nX + 1); q += ctx.nt) {
-      int r = q / (nU + nX + 1), col = q % (nU + nX + 1);
+    for (int it = ctx.tid; it < nu * (nu + nX + 1); it += ctx.nt) {
+      int u = it / (nu + nX + 1), col = it % (nu + nX + 1), a = 0;
+      while (u >= R.uoff[a + 1]) ++a;
+      int j = u - R.uoff[a];
+      const double* Bj = R.Bb + (a * 7) * NP + j;
       double s = 0;
-      if (col < nU) {
-        for (int m = 0; m < nX; ++m) s += B[m * nU + r] * R.PB[m * nU + col];
-        R.F[r * nU + col] = R.R[r * nU + col] + s;
-      } else if (col < nU + nX) {
-        int cc = col - nU;
-        for (int m = 0; m < nX; ++m) s += B[m * nU + r] * R.PA[m * nX + cc];
-        R.Gm[r * (nX + 1) + cc] = R.S[r * nX + cc] + s;
+      if (col < nu) {
+        for (int m = 0; m < 7; ++m) s += Bj[m * NP] * R.PB[(7 * a + m) * nu + col];
+        R.F[u * nu + col] = R.R[u * nu + col] + s;
+      } else if (col < nu + nX) {
+        int c = col - nu;
+        for (int m = 0; m < 7; ++m) s += Bj[m * NP] * R.PA[(7 * a + m) * nX + c];
+        R.Gm[u * (nX + 1) + c] = R.S[u * nX + c] + s;
       } else {
-        for (int m = 0; m < nX; ++m) s += B[m * nU + r] * R.pc[m];
-        R.Gm[r * (nX + 1) + nX] = R.r[r] + s;
+        for (int m = 0; m < 7; ++m) s += Bj[m * NP] * R.pc[7 * a + m];
+        R.Gm[u * (nX + 1) + nX] = R.r[u] + s;
       }
     }
     cta_sync(ctx);
-    // Cholesky of F (thread 0), in place, lower
-    if (ctx.tid == 0) {
-      for (int j = 0; j < nU; ++j) {
-        double d = R.F[j * nU + j];
-        for (int m = 0; m < j; ++m) d -= R.F[j * nU + m] * R.F[j * nU + m];
-        if (!(d > 1e-14 * fmax(1.0, fabs(R.F[j * nU + j])))) {
-          *ok = 0;
-          d = 1.0;
-        }
-        d = sqrt(d);
-        R.F[j * nU + j] = d;
-        for (int r = j + 1; r < nU; ++r) {
-          double v = R.F[r * nU + j];
-          for (int m = 0; m < j; ++m) v -= R.F[r * nU + m] * R.F[j * nU + m];
-          R.F[r * nU + j] = v / d;
-        }
+    // Cholesky F = L L' (right-looking, whole CTA); a non-positive pivot means the reduced Hessian is not PD
+    for (int j = 0; j < nu; ++j) {
+      cta_sync(ctx);
+      double d = R.F[j * nu + j];
+      bool bad = !(d > 1e-14 * fmax(1.0, fabs(R.R[j * nu + j])));
+      if (bad) d = 1.0;
+      double sd = sqrt(d);
+      cta_sync(ctx);
+      if (bad && ctx.tid == 0) *ok = 0;
+      for (int r = j + ctx.tid; r < nu; r += ctx.nt) R.F[r * nu + j] = (r == j) ? sd : R.F[r * nu + j] / sd;
+      cta_sync(ctx);
+      int rem = nu - j - 1;
+      for (int it = ctx.tid; it < rem * rem; it += ctx.nt) {
+        int r = j + 1 + it / rem, c = j + 1 + it % rem;
+        if (c <= r) R.F[r * nu + c] -= R.F[r * nu + j] * R.F[c * nu + j];
       }
     }
     cta_sync(ctx);
     // [K | k] = -F^-1 Gm : one thread per column
     for (int col = ctx.tid; col < nX + 1; col += ctx.nt) {
       double tmp[NUMAX];
-      for (int r = 0; r < nU; ++r) {
+      for (int r = 0; r < nu; ++r) {
         double v = R.Gm[r * (nX + 1) + col];
-        for (int m = 0; m < r; ++m) v -= R.F[r * nU + m] * tmp[m];
-        tmp[r] = v / R.F[r * nU + r];
+        for (int m = 0; m < r; ++m) v -= R.F[r * nu + m] * tmp[m];
+        tmp[r] = v / R.F[r * nu + r];
       }
-      for (int r = nU - 1; r >= 0; --r) {
+      for (int r = nu - 1; r >= 0; --r) {
         double v = tmp[r];
-        for (int m = r + 1; m < nU; ++m) v -= R.F[m * nU + r] * tmp[m];
-        tmp[r] = v / R.F[r * nU + r];
+        for (int m = r + 1; m < nu; ++m) v -= R.F[m * nu + r] * tmp[m];
+        tmp[r] = v / R.F[r * nu + r];
       }
-      for (int r = 0; r < nU; ++r) {
-        if (col < nX) Kg[r * nX + col] = -tmp[r];
-        else kg[r] = -tmp[r];
+      for (int r = 0; r < nu; ++r) R.K[r * (nX + 1) + col] = -tmp[r];
+    }
+    cta_sync(ctx);
+    // gains to global memory (forward pass) in the padded layout [nUmax][nX] + [nUmax]
+    {
+      double* Kg = W.RK + (size_t)i * kstride;
+      for (int it = ctx.tid; it < nu * (nX + 1); it += ctx.nt) {
+        int u = it / (nX + 1), col = it % (nX + 1);
+        if (col < nX) Kg[u * nX + col] = R.K[it];
+        else Kg[nUmax * nX + u] = R.K[it];
+      }
+    }
+    // P <- Q + A'PA + Gm'K ; p <- q + A'pc + Gm'k   (written into Q/q first, then copied: P is still needed)
+    for (int it = ctx.tid; it < nX * (nX + 1); it += ctx.nt) {
+      int r = it / (nX + 1), col = it % (nX + 1);
+      double s = 0;
+      if (col < nX) {
+        if (r < idt) {
+          int a = r / 7, rr = r % 7;
+          for (int m = 0; m < 7; ++m) s += R.Ab[a * 49 + m * 7 + rr] * R.PA[(7 * a + m) * nX + col];
+        } else {
+          s = R.PA[idt * nX + col];
+          for (int m = 0; m < idt; ++m) s += R.db[m] * R.PA[m * nX + col];
+        }
+        for (int m = 0; m < nu; ++m) s += R.Gm[m * (nX + 1) + r] * R.K[m * (nX + 1) + col];
+        R.Q[r * nX + col] += s;
+      } else {
+        if (r < idt) {
+          int a = r / 7, rr = r % 7;
+          for (int m = 0; m < 7; ++m) s += R.Ab[a * 49 + m * 7 + rr] * R.pc[7 * a + m];
+        } else {
+          s = R.pc[idt];
+          for (int m = 0; m < idt; ++m) s += R.db[m] * R.pc[m];
+        }
+        for (int m = 0; m < nu; ++m) s += R.Gm[m * (nX + 1) + r] * R.K[m * (nX + 1) + nX];
+        R.q[r] += s;
       }
     }
     cta_sync(ctx);
-    // P0 = Q + A'PA + Gm'K ; p0 = q + A'pc + Gm'k
-    for (int q = ctx.tid; q < nX * (nX + 1); q += ctx.nt) {
-      int r = q / (nX + 1), col = q % (nX + 1);
-      double s = 0;
-      if (col < nX) {
-        for (int m = 0; m < nX; ++m) s += A[m * nX + r] * R.PA[m * nX + col];
-        for (int m = 0; m < nU; ++m) s += R.Gm[m * (nX + 1) + r] * Kg[m * nX + col];
-        P0[r * nX + col] = R.Q[r * nX + col] + s;
-      } else {
-        for (int m = 0; m < nX; ++m) s += A[m * nX + r] * R.pc[m];
-        for (int m = 0; m < nU; ++m) s += R.Gm[m * (nX + 1) + r] * kg[m];
-        p0[r] = R.q[r] + s;
+    {
+      double* P0 = W.RP + (size_t)i * pstride;
+      for (int q = ctx.tid; q < nX * nX; q += ctx.nt) {
+        double v = R.Q[q];
+        R.P[q] = v, P0[q] = v;
+      }
+      for (int q = ctx.tid; q < nX; q += ctx.nt) {
+        double v = R.q[q];
+        R.p[q] = v, P0[nX * nX + q] = v;
       }
     }
     cta_sync(ctx);
@@ -811,12 +898,12 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
 }
 
 OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, int* ok) {
-  const int nX = L.nX, nU = L.nU, idt = 7 * L.V;
-  const size_t pstride = (size_t)nX * nX + nX, kstride = (size_t)nU * nX + nU, astride = (size_t)nX * nX + (size_t)nX * nU + nX;
+  const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V;
+  const size_t pstride = (size_t)nX * nX + nX, kstride = (size_t)nUmax * nX + nUmax;
   double* X = W.RX;
   double* U = W.RX + (size_t)(L.Nmax + 1) * nX;
   if (ctx.tid == 0) {
-    for (int a = 0; a < L.V; ++a)
+    for (int a = 0; a < V; ++a)
       for (int q = 0; q < NZ; ++q) X[7 * a + q] = -W.c[L.YINIT(a, q)];
     const double* P0 = W.RP;
     const double* p0 = P0 + nX * nX;
@@ -831,24 +918,39 @@ OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, in
   }
   cta_sync(ctx);
   for (int i = 0; i < L.Nmax; ++i) {
-    const double* A = W.RA + (size_t)i * astride;
-    const double* B = A + nX * nX;
-    const double* cv = B + nX * nU;
     const double* Kg = W.RK + (size_t)i * kstride;
-    const double* kg = Kg + nU * nX;
+    const double* kg = Kg + nUmax * nX;
     const double* Xi = X + (size_t)i * nX;
-    double* Ui = U + (size_t)i * nU;
+    double* Ui = U + (size_t)i * nUmax;  // padded per-vehicle layout: NP slots per vehicle
     double* Xn = X + (size_t)(i + 1) * nX;
-    for (int r = ctx.tid; r < nU; r += ctx.nt) {
-      double s = kg[r];
-      for (int m = 0; m < nX; ++m) s += Kg[r * nX + m] * Xi[m];
-      Ui[r] = s;
+    // controls: compacted index u -> (vehicle, slot)
+    for (int t = ctx.tid; t < V * NP; t += ctx.nt) {
+      int a = t / NP, j = t % NP;
+      int off = 0;
+      for (int aa = 0; aa < a; ++aa) off += block_np(L, W, aa, i);
+      double s = 0;
+      if (j < block_np(L, W, a, i)) {
+        int u = off + j;
+        s = kg[u];
+        for (int m = 0; m < nX; ++m) s += Kg[u * nX + m] * Xi[m];
+      }
+      Ui[t] = s;
     }
     cta_sync(ctx);
     for (int r = ctx.tid; r < nX; r += ctx.nt) {
-      double s = cv[r];
-      for (int m = 0; m < nX; ++m) s += A[r * nX + m] * Xi[m];
-      for (int m = 0; m < nU; ++m) s += B[r * nU + m] * Ui[m];
+      double s;
+      if (r == idt) s = Xi[idt];
+      else {
+        int a = r / 7, rr = r % 7;
+        s = 0;
+        if (i < L.N[a]) {
+          const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+          const double* Tr = T + (28 + rr) * NRED;
+          s = T[NW * NRED + 28 + rr] + Tr[IDT] * Xi[idt];
+          for (int m = 0; m < 7; ++m) s += Tr[m] * Xi[7 * a + m];
+          for (int j = 0; j < NP; ++j) s += Tr[7 + j] * Ui[a * NP + j];
+        }
+      }
       Xn[r] = s;
     }
     cta_sync(ctx);

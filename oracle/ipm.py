@@ -15,7 +15,7 @@ Differences from stock IPOPT (both sides of the parity test share them):
   * y0 = 0 (no least-squares multiplier estimate), no second-order correction, no restoration phase
     (a failed line search returns status ``Restoration_Failed``);
   * the Hessian uses clipped multipliers on the two norm rows (nlp.hess(clip=True));
-  * delta_c = 1e-10 on the obstacle / pair rows, 1e-9 on all other rows (always on).
+  * delta_c = 1e-8 on the obstacle / pair rows, 1e-9 on all other rows (always on).
 """
 from dataclasses import dataclass, field
 
@@ -63,7 +63,7 @@ class IpmOptions:
     kappa_w_minus: float = 1.0 / 3.0
     kappa_w_plus: float = 8.0
     kappa_w_plus_first: float = 100.0
-    delta_c_local: float = 1e-10
+    delta_c_local: float = 1e-8
     delta_c_global: float = 1e-9
     verbose: int = 0
 

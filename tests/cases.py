@@ -23,7 +23,7 @@ def load_golden(name):
     return prob, guess, sol
 
 
-def oracle_newton_step(nlp, x, y, zL, zU, mu, delta_w, kappa_d=1e-4, dc_local=1e-10):
+def oracle_newton_step(nlp, x, y, zL, zU, mu, delta_w, kappa_d=1e-4, dc_local=1e-8):
     """Reference Newton step: sparse LU of the full primal-dual system with iterative refinement."""
     hasL, hasU = np.isfinite(nlp.xL), np.isfinite(nlp.xU)
     gL, gU = np.where(hasL, x - nlp.xL, 1.0), np.where(hasU, nlp.xU - x, 1.0)

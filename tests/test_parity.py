@@ -80,7 +80,10 @@ def test_residuals_gradient_and_newton_step(backend, strategy_file, nlp_cache, a
         # any solution of the singular system is acceptable: check the KKT residual of the device step instead
         hasL, hasU = np.isfinite(nlp.xL), np.isfinite(nlp.xU)
         J = nlp.jac(x0)
-        r2 = J @ dx_d[ix] + c_o
+        dc = np.zeros(nlp.m)
+        for rr in nlp.r_obs + nlp.r_pair:
+            dc[np.ravel(rr)] = 1e-8
+        r2 = J @ dx_d[ix] - dc * dy_d[iy] + c_o
         cols = np.concatenate([r.ravel() for r in nlp.r_col])
         mask = np.ones(nlp.m, bool)
         mask[cols] = False
