@@ -17,6 +17,9 @@ using namespace obca;
 #ifndef OBCA_HOST_EMU
 #include <cuda_runtime.h>
 #define CTA_THREADS 256
+#define NWARPS (CTA_THREADS / 32)
+#else
+#define NWARPS 1
 #endif
 
 static thread_local std::string g_err;
@@ -412,7 +415,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   }
   for (int q = 0; q < L.nx; ++q) nb += (xL[q] > -INFINITY) + (xU[q] < INFINITY);
   h->cnt.m_active = m_active, h->cnt.nb = nb;
-  h->it_stride = iterate_doubles(L), h->wk_stride = work_doubles(L), h->rw_stride = riccati_work_doubles(L);
+  h->it_stride = iterate_doubles(L), h->wk_stride = work_doubles(L), h->rw_stride = riccati_work_doubles(L, NWARPS);
 #ifdef OBCA_HOST_EMU
   h->slots = 1;
 #else

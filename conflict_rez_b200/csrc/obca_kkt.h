@@ -288,10 +288,36 @@ OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
   }
 }
 
-// One (vehicle, interval) block: rows = 30 collocation rows (+ terminal rows in the last interval) + the implied
-// rows `ex` received from interval i+1 (they act on the node-K variables).  Writes T, s0, the QR record, the
-// projected Hessian, and the implied rows `em` for interval i-1.
-OBCA_HDN void nullspace_block(const Lay& L, const Stat& S, const Scratch& W, int a, int i, const double* ex, double* em, int* ok) {
+// ---- warp-cooperative execution helpers: on the device the body runs once per lane; the host emulation loops over lanes
+#if defined(__CUDA_ARCH__)
+#define OBCA_LANES(lane) for (int lane = (ctx.tid & 31), once_ = 1; once_; once_ = 0)
+#define OBCA_WARP_SYNC() __syncwarp()
+#else
+#define OBCA_LANES(lane) for (int lane = 0; lane < 32; ++lane)
+#define OBCA_WARP_SYNC()
+#endif
+
+constexpr int NSW = 2720;  // shared-memory doubles per warp of the null-space phase
+
+// apply Q or Q' to the strided vector v[q * stride], q < 35 (reflectors in the shared-memory QR matrix)
+OBCA_HD void apply_q_strided(const double* Mq, const double* tau, const double* piv, int rk, double* v, int stride, bool transpose) {
+  for (int jj = 0; jj < rk; ++jj) {
+    int i = transpose ? jj : rk - 1 - jj;
+    int col = (int)piv[i];
+    double s = v[i * stride];
+    for (int r = i + 1; r < NW; ++r) s += Mq[r * NC + col] * v[r * stride];
+    s *= tau[i];
+    v[i * stride] -= s;
+    for (int r = i + 1; r < NW; ++r) v[r * stride] -= s * Mq[r * NC + col];
+  }
+}
+
+// One (vehicle, interval) block, processed by one warp with its working set in shared memory `sw` (NSW doubles):
+// rows = 30 collocation rows (+ terminal rows in the last interval) + the implied rows `ex` received from interval
+// i+1 (they act on the node-K variables).  Writes T, s0, the QR record, the projected Hessian, and the implied rows
+// `em` for interval i-1.
+OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int a, int i, const double* ex, double* em,
+                              int* ok, double* sw) {
   const double* x = W.x;
   const double dt = x[L.oDT], idt = 1.0 / dt;
   const int n0 = i * NK;
@@ -299,59 +325,88 @@ OBCA_HDN void nullspace_block(const Lay& L, const Stat& S, const Scratch& W, int
   const int nterm = last ? (4 + L.heading[a]) : 0;
   const int nex = (int)ex[0];
   const int nr = 30 + nterm + nex;
-  double* QRm = W.QR + (size_t)(a * L.Nmax + i) * QRSZ;  // [35][NC]: column j = row j of G_w
-  double* tau = QRm + QR_TAU;
-  double* piv = QRm + QR_PIV;
-  double G0[NC * 7], gd[NC], rr[NC];
-  for (int q = 0; q < NW * NC; ++q) QRm[q] = 0;
-  for (int q = 0; q < NC * 7; ++q) G0[q] = 0;
-  for (int k = 0; k < NK; ++k) {
-    int n = n0 + k;
-    double psi = x[L.Z(a, 2, n)], v = x[L.Z(a, 3, n)], de = x[L.Z(a, 4, n)];
-    double cs = cos(psi), sn = sin(psi), tde = tan(de), sec2 = 1.0 + tde * tde;
-    for (int q = 0; q < 5; ++q) {
-      int r = k * 5 + q;
+  double* Mq = sw;                 // [35][NC]
+  double* G0 = Mq + NW * NC;       // [NC][7]
+  double* gd = G0 + NC * 7;        // [NC]
+  double* rr = gd + NC;            // [NC]
+  double* tau = rr + NC;           // [35]
+  double* piv = tau + NW;          // [35]
+  double* T = piv + NW;            // [35][NRED]
+  double* s0 = T + NW * NRED;      // [35]
+  double* zb = s0 + NW;            // [42] states of the interval
+  double* hdv = zb + NS;           // [42] node x dt cross Hessian
+  double* gnv = hdv + NS;          // [42] node gradients
+  double* wred = gnv + NS;         // [64] reduction scratch
+  double* misc = wred + 64;        // [64]: al[35], h[9], flags
+  double* QRg = W.QR + (size_t)(a * L.Nmax + i) * QRSZ;
+  OBCA_LANES(lane) {
+    for (int q = lane; q < NW * NC + NC * 7; q += 32) Mq[q] = 0;  // Mq and G0 are contiguous
+    for (int q = lane; q < NS; q += 32) {
+      zb[q] = x[L.Z(a, q % NZ, n0 + q / NZ)];
+      hdv[q] = W.HD[(size_t)(a * L.Mv + n0 + q / NZ) * 7 + q % NZ];
+      gnv[q] = W.GN[(size_t)(a * L.Mv + n0 + q / NZ) * 7 + q % NZ];
+    }
+  }
+  OBCA_WARP_SYNC();
+  OBCA_LANES(lane) {
+    if (lane < 30) {
+      int k = lane / 5, q = lane % 5, r = lane;
+      double psi = zb[k * NZ + 2], v = zb[k * NZ + 3], de = zb[k * NZ + 4];
+      double cs = cos(psi), sn = sin(psi), tde = tan(de), sec2 = 1.0 + tde * tde;
       double pl = 0;
       for (int j = 0; j < NK; ++j) {
         double coef = S.cA[j][k] * idt;
-        pl += S.cA[j][k] * x[L.Z(a, q, n0 + j)];
+        pl += S.cA[j][k] * zb[j * NZ + q];
         if (j == 0) G0[r * 7 + q] += coef;
-        else QRm[((j - 1) * 7 + q) * NC + r] += coef;
+        else Mq[((j - 1) * 7 + q) * NC + r] += coef;
       }
       gd[r] = -pl * idt * idt;
-      rr[r] = W.c[L.YCOL(a, q, n)];
-    }
-    // minus df/d(z,u) at node k
-    double dfz[5][NZ] = {{0, 0, -v * sn, cs, 0, 0, 0}, {0, 0, v * cs, sn, 0, 0, 0}, {0, 0, 0, tde / S.wb, v * sec2 / S.wb, 0, 0},
-                         {0, 0, 0, 0, 0, 1, 0},        {0, 0, 0, 0, 0, 0, 1}};
-    for (int q = 0; q < 5; ++q)
+      rr[r] = W.c[L.YCOL(a, q, n0 + k)];
+      double dfz[NZ] = {0, 0, 0, 0, 0, 0, 0};  // df_q/d(z,u) at node k
+      if (q == 0) dfz[2] = -v * sn, dfz[3] = cs;
+      else if (q == 1) dfz[2] = v * cs, dfz[3] = sn;
+      else if (q == 2) dfz[3] = tde / S.wb, dfz[4] = v * sec2 / S.wb;
+      else if (q == 3) dfz[5] = 1.0;
+      else dfz[6] = 1.0;
       for (int m = 2; m < NZ; ++m) {
-        if (dfz[q][m] == 0.0) continue;
-        int r = k * 5 + q;
-        if (k == 0) G0[r * 7 + m] -= dfz[q][m];
-        else QRm[((k - 1) * 7 + m) * NC + r] -= dfz[q][m];
+        if (dfz[m] == 0.0) continue;
+        if (k == 0) G0[r * 7 + m] -= dfz[m];
+        else Mq[((k - 1) * 7 + m) * NC + r] -= dfz[m];
       }
-  }
-  int r = 30;
-  if (last) {
-    if (L.heading[a]) {
-      QRm[(28 + 2) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, 0)];
-      ++r;
+    } else if (lane == 30) {
+      int r = 30;
+      if (last) {
+        if (L.heading[a]) {
+          Mq[(28 + 2) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, 0)];
+          ++r;
+        }
+        for (int m = 3; m < NZ; ++m, ++r) Mq[(28 + m) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, m - 2)];
+      }
+      for (int e = 0; e < nex; ++e, ++r) {
+        const double* h = ex + 1 + e * 9;
+        for (int m = 0; m < NZ; ++m) Mq[(28 + m) * NC + r] = h[m];
+        gd[r] = h[7], rr[r] = h[8];
+      }
     }
-    for (int m = 3; m < NZ; ++m, ++r) QRm[(28 + m) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, m - 2)];
   }
-  for (int e = 0; e < nex; ++e, ++r) {
-    const double* h = ex + 1 + e * 9;
-    for (int m = 0; m < NZ; ++m) QRm[(28 + m) * NC + r] = h[m];
-    gd[r] = h[7], rr[r] = h[8];
-  }
+  OBCA_WARP_SYNC();
   // Householder QR with rank test (LAPACK dgeqr2 reflector convention: v[rk] = 1 implicit)
   int rk = 0, ndrop = 0, nem = 0;
   for (int j = 0; j < nr; ++j) {
-    double nrm = 0, full = 0;
-    for (int q = 0; q < rk; ++q) full += QRm[q * NC + j] * QRm[q * NC + j];
-    for (int q = rk + 1; q < NW; ++q) nrm += QRm[q * NC + j] * QRm[q * NC + j];
-    double alpha = rk < NW ? QRm[rk * NC + j] : 0.0;
+    OBCA_LANES(lane) {
+      double head = 0, tail = 0;
+      for (int q = lane; q < NW; q += 32) {
+        double v = Mq[q * NC + j];
+        if (q < rk) head += v * v;
+        else if (q > rk) tail += v * v;
+      }
+      wred[lane] = head, wred[32 + lane] = tail;
+    }
+    OBCA_WARP_SYNC();
+    double full = 0, nrm = 0;
+    for (int q = 0; q < 32; ++q) full += wred[q], nrm += wred[32 + q];
+    OBCA_WARP_SYNC();
+    double alpha = rk < NW ? Mq[rk * NC + j] : 0.0;
     double beta = sqrt(alpha * alpha + nrm);
     full = sqrt(full + alpha * alpha + nrm);
     if (rk >= NW || !(beta > 1e-8 * full) || !(full > 0)) {
@@ -360,150 +415,184 @@ OBCA_HDN void nullspace_block(const Lay& L, const Stat& S, const Scratch& W, int
         *ok = 0;
         continue;
       }
-      double* dr = QRm + QR_DROP + ndrop * DRSZ;
-      double* al = dr + 3;
-      for (int q = rk - 1; q >= 0; --q) {
-        double sacc = QRm[q * NC + j];
-        for (int m = q + 1; m < rk; ++m) sacc -= al[m] * QRm[q * NC + (int)piv[m]];
-        al[q] = sacc / QRm[q * NC + (int)piv[q]];
+      OBCA_LANES(lane) {
+        if (lane == 0) {
+          double* dr = QRg + QR_DROP + ndrop * DRSZ;
+          double* al = misc;
+          for (int q = rk - 1; q >= 0; --q) {
+            double sacc = Mq[q * NC + j];
+            for (int m = q + 1; m < rk; ++m) sacc -= al[m] * Mq[q * NC + (int)piv[m]];
+            al[q] = sacc / Mq[q * NC + (int)piv[q]];
+          }
+          double h[9];
+          for (int m = 0; m < 7; ++m) h[m] = G0[j * 7 + m];
+          h[7] = gd[j], h[8] = rr[j];
+          double scale = fabs(gd[j]);
+          for (int m = 0; m < 7; ++m) scale = fmax(scale, fabs(G0[j * 7 + m]));
+          for (int q = 0; q < rk; ++q) {
+            int jp = (int)piv[q];
+            for (int m = 0; m < 7; ++m) h[m] -= al[q] * G0[jp * 7 + m];
+            h[7] -= al[q] * gd[jp];
+            h[8] -= al[q] * rr[jp];
+            dr[3 + q] = al[q];
+          }
+          double hmax = fabs(h[7]);
+          for (int m = 0; m < 7; ++m) hmax = fmax(hmax, fabs(h[m]));
+          int slot = -1;
+          misc[40] = 0.0;
+          if (i > 0 && hmax > 1e-7 * fmax(1.0, scale)) {
+            if (nem < NEX) {
+              slot = nem;
+              misc[40] = 1.0;
+              for (int m = 0; m < 9; ++m) em[1 + slot * 9 + m] = h[m];
+            } else
+              *ok = 0;
+          }
+          dr[0] = (double)j, dr[1] = (double)slot, dr[2] = (double)rk;
+          for (int m = 0; m < 9; ++m) dr[3 + 35 + m] = h[m];
+        }
       }
-      double h[9];
-      for (int m = 0; m < 7; ++m) h[m] = G0[j * 7 + m];
-      h[7] = gd[j], h[8] = rr[j];
-      double scale = fabs(gd[j]);
-      for (int m = 0; m < 7; ++m) scale = fmax(scale, fabs(G0[j * 7 + m]));
-      for (int q = 0; q < rk; ++q) {
-        int jp = (int)piv[q];
-        for (int m = 0; m < 7; ++m) h[m] -= al[q] * G0[jp * 7 + m];
-        h[7] -= al[q] * gd[jp];
-        h[8] -= al[q] * rr[jp];
-      }
-      double hmax = fabs(h[7]);
-      for (int m = 0; m < 7; ++m) hmax = fmax(hmax, fabs(h[m]));
-      int slot = -1;
-      if (i > 0 && hmax > 1e-7 * fmax(1.0, scale)) {
-        if (nem < NEX) {
-          slot = nem++;
-          for (int m = 0; m < 9; ++m) em[1 + slot * 9 + m] = h[m];
-        } else
-          *ok = 0;
-      }
-      dr[0] = (double)j, dr[1] = (double)slot, dr[2] = (double)rk;
-      for (int m = 0; m < 9; ++m) dr[3 + 35 + m] = h[m];
+      OBCA_WARP_SYNC();
+      if (misc[40] != 0.0) ++nem;
+      OBCA_WARP_SYNC();
       ++ndrop;
       continue;
     }
     if (alpha > 0) beta = -beta;
-    double t = (beta - alpha) / beta;
-    double sc = 1.0 / (alpha - beta);
-    for (int q = rk + 1; q < NW; ++q) QRm[q * NC + j] *= sc;
-    tau[rk] = t;
-    piv[rk] = (double)j;
-    QRm[rk * NC + j] = beta;
-    for (int cc = j + 1; cc < nr; ++cc) {
-      double sacc = QRm[rk * NC + cc];
-      for (int q = rk + 1; q < NW; ++q) sacc += QRm[q * NC + j] * QRm[q * NC + cc];
-      sacc *= t;
-      QRm[rk * NC + cc] -= sacc;
-      for (int q = rk + 1; q < NW; ++q) QRm[q * NC + cc] -= sacc * QRm[q * NC + j];
+    const double t = (beta - alpha) / beta;
+    const double sc = 1.0 / (alpha - beta);
+    OBCA_LANES(lane) {
+      for (int q = rk + 1 + lane; q < NW; q += 32) Mq[q * NC + j] *= sc;
+      if (lane == 0) tau[rk] = t, piv[rk] = (double)j, Mq[rk * NC + j] = beta;
     }
+    OBCA_WARP_SYNC();
+    OBCA_LANES(lane) {
+      for (int cc = j + 1 + lane; cc < nr; cc += 32) {
+        double sacc = Mq[rk * NC + cc];
+        for (int q = rk + 1; q < NW; ++q) sacc += Mq[q * NC + j] * Mq[q * NC + cc];
+        sacc *= t;
+        Mq[rk * NC + cc] -= sacc;
+        for (int q = rk + 1; q < NW; ++q) Mq[q * NC + cc] -= sacc * Mq[q * NC + j];
+      }
+    }
+    OBCA_WARP_SYNC();
     ++rk;
   }
-  em[0] = (double)nem;
-  QRm[QR_META + 0] = (double)rk;
-  QRm[QR_META + 1] = (double)nr;
-  QRm[QR_META + 2] = (double)ndrop;
   int np = NW - rk;
   if (np > NP) {
     *ok = 0;
     np = NP;
   }
-  // T columns: 0..6 xi, 7..7+NP-1 p, IDT dt; s0
-  double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
-  double* s0 = T + NW * NRED;
-  double vcol[NW];
-  for (int col = 0; col < 9; ++col) {
-    // b = -G0[:,col] (col < 7), -gd (col 7), -r (col 8); solve R' w = b on the staircase; vcol = Q [w; 0]
-    for (int ii = 0; ii < rk; ++ii) {
-      int j = (int)piv[ii];
-      double bv = col < 7 ? -G0[j * 7 + col] : (col == 7 ? -gd[j] : -rr[j]);
-      for (int m = 0; m < ii; ++m) bv -= QRm[m * NC + j] * vcol[m];
-      vcol[ii] = bv / QRm[ii * NC + j];
-    }
-    for (int q = rk; q < NW; ++q) vcol[q] = 0;
-    apply_q(QRm, rk, vcol, false);
-    if (col < 7)
-      for (int q = 0; q < NW; ++q) T[q * NRED + col] = vcol[q];
-    else if (col == 7)
-      for (int q = 0; q < NW; ++q) T[q * NRED + IDT] = vcol[q];
-    else
-      for (int q = 0; q < NW; ++q) s0[q] = vcol[q];
-  }
-  for (int j = 0; j < NP; ++j) {
-    for (int q = 0; q < NW; ++q) vcol[q] = 0;
-    if (j < np) {
-      vcol[rk + j] = 1.0;
-      apply_q(QRm, rk, vcol, false);
-    }
-    for (int q = 0; q < NW; ++q) T[q * NRED + 7 + j] = vcol[q];
-  }
-  // projected stage Hessian M = Tt' H Tt + dt cross terms, gradient m = Tt'(H s0 + gn) + e_dt hd's0
-  double HT[NS * NRED];
-  double hs0[NS];
-  for (int k = 0; k < NK; ++k) {
-    const double* hn = W.HN + (size_t)(a * L.Mv + n0 + k) * 28;
-    for (int q = 0; q < NZ; ++q) {
-      int row = k * NZ + q;
-      double acc0 = 0;
-      for (int col = 0; col < NRED; ++col) {
-        double sacc = 0;
-        for (int m = 0; m < NZ; ++m) {
-          double tv = (k == 0) ? ((m == col) ? 1.0 : 0.0) : T[((k - 1) * NZ + m) * NRED + col];
-          sacc += hn[sym(q, m)] * tv;
+  // T columns (one lane per column): 0..6 xi, 7..7+NP-1 p, IDT dt; s0
+  OBCA_LANES(lane) {
+    if (lane == 0) em[0] = (double)nem, QRg[QR_META + 0] = (double)rk, QRg[QR_META + 1] = (double)nr, QRg[QR_META + 2] = (double)ndrop;
+    if (lane < 9 + NP) {
+      int col = lane;
+      double* v = col < 7 ? T + col : (col == 7 ? T + IDT : (col == 8 ? s0 : T + 7 + (col - 9)));
+      int stride = col == 8 ? 1 : NRED;
+      if (col < 9) {
+        // b = -G0[:,col] (col < 7), -gd (col 7), -r (col 8); solve R' w = b on the staircase; v = Q [w; 0]
+        for (int ii = 0; ii < rk; ++ii) {
+          int j = (int)piv[ii];
+          double bv = col < 7 ? -G0[j * 7 + col] : (col == 7 ? -gd[j] : -rr[j]);
+          for (int m = 0; m < ii; ++m) bv -= Mq[m * NC + j] * v[m * stride];
+          v[ii * stride] = bv / Mq[ii * NC + j];
         }
-        HT[row * NRED + col] = sacc;
+        for (int q = rk; q < NW; ++q) v[q * stride] = 0;
+        apply_q_strided(Mq, tau, piv, rk, v, stride, false);
+      } else {
+        int jn = col - 9;
+        for (int q = 0; q < NW; ++q) v[q * stride] = 0;
+        if (jn < np) {
+          v[(rk + jn) * stride] = 1.0;
+          apply_q_strided(Mq, tau, piv, rk, v, stride, false);
+        }
       }
+    }
+  }
+  OBCA_WARP_SYNC();
+  // QR record and T map to global memory (multiplier recovery, Riccati dynamics, primal expansion)
+  double* Tg = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+  OBCA_LANES(lane) {
+    for (int q = lane; q < NW * NC; q += 32) QRg[q] = Mq[q];
+    for (int q = lane; q < NW; q += 32) QRg[QR_TAU + q] = tau[q], QRg[QR_PIV + q] = piv[q];
+    for (int q = lane; q < NW * NRED + NW; q += 32) Tg[q] = T[q];  // T and s0 are contiguous
+  }
+  OBCA_WARP_SYNC();
+  // projected stage Hessian M = Tt' H Tt + dt cross terms, gradient m = Tt'(H s0 + gn) + e_dt hd's0
+  double* HT = Mq;                    // [42][NRED]   (the QR matrix is no longer needed in shared memory)
+  double* hs0 = HT + NS * NRED;       // [42]
+  double* hn = hs0 + NS;              // [6][28]
+  double* hdT = hn + NK * 28;         // [NRED] + hds0
+  OBCA_LANES(lane) {
+    for (int q = lane; q < NK * 28; q += 32) hn[q] = W.HN[(size_t)(a * L.Mv + n0) * 28 + q];
+  }
+  OBCA_WARP_SYNC();
+  OBCA_LANES(lane) {
+    for (int e = lane; e < NS * NRED; e += 32) {
+      int row = e / NRED, col = e % NRED, k = row / NZ, q = row % NZ;
+      double sacc = 0;
+      for (int m = 0; m < NZ; ++m) {
+        double tv = (k == 0) ? ((m == col) ? 1.0 : 0.0) : T[((k - 1) * NZ + m) * NRED + col];
+        sacc += hn[k * 28 + sym(q, m)] * tv;
+      }
+      HT[e] = sacc;
+    }
+    for (int row = lane; row < NS; row += 32) {
+      int k = row / NZ, q = row % NZ;
+      double acc0 = 0;
       if (k > 0)
-        for (int m = 0; m < NZ; ++m) acc0 += hn[sym(q, m)] * s0[(k - 1) * NZ + m];
+        for (int m = 0; m < NZ; ++m) acc0 += hn[k * 28 + sym(q, m)] * s0[(k - 1) * NZ + m];
       hs0[row] = acc0;
     }
-  }
-  double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
-  double hdT[NRED];
-  double hds0 = 0;
-  for (int col = 0; col < NRED; ++col) hdT[col] = 0;
-  for (int row = 0; row < NS; ++row) {
-    int k = row / NZ, m = row % NZ;
-    double hdv = W.HD[(size_t)(a * L.Mv + n0 + k) * 7 + m];
-    if (k == 0) hdT[m] += hdv;
-    else {
-      for (int col = 0; col < NRED; ++col) hdT[col] += hdv * T[(row - NZ) * NRED + col];
-      hds0 += hdv * s0[row - NZ];
-    }
-  }
-  for (int q = 0; q < NRED; ++q) {
-    for (int cc = 0; cc <= q; ++cc) {
+    if (lane < NRED) {
+      double sacc = lane < NZ ? hdv[lane] : 0.0;
+      for (int row = NZ; row < NS; ++row) sacc += hdv[row] * T[(row - NZ) * NRED + lane];
+      hdT[lane] = sacc;
+    } else if (lane == NRED) {
       double sacc = 0;
-      if (q < NZ) sacc += HT[q * NRED + cc];  // node-0 identity rows
-      for (int row = NZ; row < NS; ++row) sacc += T[(row - NZ) * NRED + q] * HT[row * NRED + cc];
-      if (q == IDT) sacc += hdT[cc];
-      if (cc == IDT) sacc += hdT[q];
-      Mo[sym(q, cc)] = sacc;
+      for (int row = NZ; row < NS; ++row) sacc += hdv[row] * s0[row - NZ];
+      hdT[NRED] = sacc;
     }
-    double sacc = 0;
-    if (q < NZ) sacc += hs0[q] + W.GN[(size_t)(a * L.Mv + n0) * 7 + q];
-    for (int row = NZ; row < NS; ++row)
-      sacc += T[(row - NZ) * NRED + q] * (hs0[row] + W.GN[(size_t)(a * L.Mv + n0 + row / NZ) * 7 + row % NZ]);
-    if (q == IDT) sacc += hds0;
-    Mo[NSYM + q] = sacc;
   }
+  OBCA_WARP_SYNC();
+  double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
+  OBCA_LANES(lane) {
+    for (int e = lane; e < NSYM + NRED; e += 32) {
+      if (e < NSYM) {
+        int q = 0;
+        while ((q + 1) * (q + 2) / 2 <= e) ++q;
+        int cc = e - q * (q + 1) / 2;
+        double sacc = 0;
+        if (q < NZ) sacc += HT[q * NRED + cc];  // node-0 identity rows
+        for (int row = NZ; row < NS; ++row) sacc += T[(row - NZ) * NRED + q] * HT[row * NRED + cc];
+        if (q == IDT) sacc += hdT[cc];
+        if (cc == IDT) sacc += hdT[q];
+        Mo[e] = sacc;
+      } else {
+        int q = e - NSYM;
+        double sacc = 0;
+        if (q < NZ) sacc += hs0[q] + gnv[q];
+        for (int row = NZ; row < NS; ++row) sacc += T[(row - NZ) * NRED + q] * (hs0[row] + gnv[row]);
+        if (q == IDT) sacc += hdT[NRED];
+        Mo[e] = sacc;
+      }
+    }
+  }
+  OBCA_WARP_SYNC();
 }
 
-// All blocks in parallel; blocks whose Jacobian is rank deficient hand implied rows to the previous interval, which is
-// then re-processed in the next pass (buffers are double-buffered by pass parity so that the passes are race-free
-// and deterministic).  Usually two passes: the last interval of a vehicle with an axis-aligned final approach.
-OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok, int* again) {
+// All blocks in parallel (one warp each); blocks whose Jacobian is rank deficient hand implied rows to the previous
+// interval, which is then re-processed in the next pass (buffers are double-buffered by pass parity so that the passes
+// are race-free and deterministic).  Usually two passes: the last interval of a vehicle with an axis-aligned final approach.
+OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok, int* again, double* arena) {
   const int nblk = L.V * L.Nmax;
+#if defined(__CUDA_ARCH__)
+  const int wid = ctx.tid >> 5, nw = ctx.nt >> 5;
+#else
+  const int wid = 0, nw = 1;
+#endif
+  double* sw = arena + (size_t)wid * NSW;
   for (int it = ctx.tid; it < nblk; it += ctx.nt) {
     W.DF[it] = 1.0, W.DF[nblk + it] = 0.0;
     W.EM[(size_t)it * EXSZ] = 0.0, W.EM[(size_t)(nblk + it) * EXSZ] = 0.0;
@@ -514,24 +603,30 @@ OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, co
     if (ctx.tid == 0) *again = 0;
     for (int it = ctx.tid; it < nblk; it += ctx.nt) W.DF[nxt * nblk + it] = 0.0;
     cta_sync(ctx);
-    for (int it = ctx.tid; it < nblk; it += ctx.nt) {
+    for (int it = wid; it < nblk; it += nw) {
       int a = it / L.Nmax, i = it % L.Nmax;
       if (i >= L.N[a]) continue;
       const double* em_old = W.EM + (size_t)(cur * nblk + it) * EXSZ;
       double* em_new = W.EM + (size_t)(nxt * nblk + it) * EXSZ;
       if (W.DF[cur * nblk + it] == 0.0) {
-        for (int q = 0; q < EXSZ; ++q) em_new[q] = em_old[q];
+        OBCA_LANES(lane) {
+          for (int q = lane; q < EXSZ; q += 32) em_new[q] = em_old[q];
+        }
         continue;
       }
       double none = 0.0;
       const double* ex = (i + 1 < L.N[a]) ? W.EM + (size_t)(cur * nblk + it + 1) * EXSZ : &none;
-      nullspace_block(L, S, W, a, i, ex, em_new, ok);
-      bool changed = em_new[0] != em_old[0];
-      for (int q = 1; q < 1 + 9 * (int)em_new[0] && !changed; ++q)
-        changed = fabs(em_new[q] - em_old[q]) > 1e-12 * fmax(1.0, fabs(em_new[q]));
-      if (changed && i > 0) {
-        W.DF[nxt * nblk + it - 1] = 1.0;
-        *again = 1;
+      nullspace_block(ctx, L, S, W, a, i, ex, em_new, ok, sw);
+      OBCA_LANES(lane) {
+        if (lane == 0) {
+          bool changed = em_new[0] != em_old[0];
+          for (int q = 1; q < 1 + 9 * (int)em_new[0] && !changed; ++q)
+            changed = fabs(em_new[q] - em_old[q]) > 1e-12 * fmax(1.0, fabs(em_new[q]));
+          if (changed && i > 0) {
+            W.DF[nxt * nblk + it - 1] = 1.0;
+            *again = 1;
+          }
+        }
       }
     }
     cta_sync(ctx);
@@ -605,9 +700,15 @@ struct RicWork {
   int *uoff, *npv;  // [MAXV + 1]
 };
 
-inline size_t riccati_work_doubles(const Lay& L) {
+inline size_t riccati_only_doubles(const Lay& L) {
   size_t nX = L.nX, nU = L.nU;
   return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32;
+}
+
+// work arena shared by the null-space phase (NSW doubles per warp) and the Riccati phase
+inline size_t riccati_work_doubles(const Lay& L, int nwarps) {
+  size_t a = riccati_only_doubles(L), b = (size_t)nwarps * NSW;
+  return a > b ? a : b;
 }
 
 OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
@@ -1172,7 +1273,7 @@ OBCA_HDN int kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratc
   node_assemble(ctx, L, S, W, ok_shared, &hdtdt);
   cta_sync(ctx);
   prof_mark(ctx, 3);
-  interval_nullspace(ctx, L, S, W, ok_shared, ok_shared + 1);
+  interval_nullspace(ctx, L, S, W, ok_shared, ok_shared + 1, RW);
   cta_sync(ctx);
   prof_mark(ctx, 4);
   interval_cross(ctx, L, W);
