@@ -173,6 +173,8 @@ struct Scratch {
   double *x, *zL, *zU, *dx, *dzL, *dzU, *gl, *gphi, *sig, *xt;
   // y-layout vectors
   double *y, *dy, *c, *ct;
+  // best "acceptable" iterate so far (IPOPT StoreAcceptablePoint): x, zL, zU, y
+  double *bx, *bzL, *bzU, *by;
   // structured solve
   double* XO;   // [V][Mv][O][48]   obstacle block solves: 12 x (3 coupling cols + 1 rhs)
   double* XP;   // [P][Mv][112]     pair block solves: 16 x (6 + 1)
@@ -200,7 +202,7 @@ inline size_t iterate_doubles(const Lay& L) { return 3 * (size_t)L.nx + (size_t)
 // per-slot work area (one per resident CTA)
 inline size_t work_doubles(const Lay& L) {
   size_t n = 0;
-  n += 7 * (size_t)L.nx + 3 * (size_t)L.ny;
+  n += 10 * (size_t)L.nx + 4 * (size_t)L.ny;
   n += (size_t)L.V * L.Mv * L.O * 48;
   n += (size_t)L.P * L.Mv * (112 + 27 + 6);
   n += (size_t)L.V * L.Mv * (28 + 7 + 7);
@@ -231,6 +233,10 @@ OBCA_HD void carve_work(Scratch& W, const Lay& L, double* p) {
   W.dy = p, p += L.ny;
   W.c = p, p += L.ny;
   W.ct = p, p += L.ny;
+  W.bx = p, p += L.nx;
+  W.bzL = p, p += L.nx;
+  W.bzU = p, p += L.nx;
+  W.by = p, p += L.ny;
   W.XO = p, p += (size_t)L.V * L.Mv * L.O * 48;
   W.XP = p, p += (size_t)L.P * L.Mv * 112;
   W.PH = p, p += (size_t)L.P * L.Mv * 27;
@@ -356,6 +362,48 @@ OBCA_HD void ldl_solve(const double* A, double* b, int stride) {
     double v = b[i * stride];
     for (int k = i + 1; k < N; ++k) v -= A[k * N + i] * b[k * stride];
     b[i * stride] = v;
+  }
+}
+
+// Cholesky of a small SPD matrix in packed lower storage (sym(r, c)); returns false on a non-positive pivot.
+template <int N>
+OBCA_HD bool chol_packed(double* A) {
+  bool good = true;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double d = A[sym(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= A[sym(j, k)] * A[sym(j, k)];
+    if (!(d > 0)) good = false, d = 1.0;
+    d = sqrt(d);
+    A[sym(j, j)] = d;
+    double inv = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      double v = A[sym(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= A[sym(i, k)] * A[sym(j, k)];
+      A[sym(i, j)] = v * inv;
+    }
+  }
+  return good;
+}
+
+template <int N>
+OBCA_HD void chol_solve_packed(const double* A, double* b) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v -= A[sym(i, k)] * b[k];
+    b[i] = v / A[sym(i, i)];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) v -= A[sym(k, i)] * b[k];
+    b[i] = v / A[sym(i, i)];
   }
 }
 

@@ -71,6 +71,7 @@ OBCA_HDN void push_into_bounds(const Ctx& ctx, const Lay& L, const double* xL, c
 OBCA_HDN double barrier_obj(const Ctx& ctx, const Lay& L, const double* xL, const double* xU, const double* xv, double f, double mu, double kd) {
   double s = 0;
   int bad = 0;
+#pragma unroll 4
   for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
     double lo = xL[q], hi = xU[q], v = xv[q];
     bool hl = lo > -INFINITY, hu = hi < INFINITY;
@@ -116,11 +117,15 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
   const double mu_min = fmin(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
   double dw_last = 0.0;
   bool tiny_last = false, force_mu = false;
+  // IPOPT acceptable-point bookkeeping: acceptable_tol 1e-6, acceptable_iter 15
+  double best_E = INFINITY, best_f = 0, best_cv = 0, best_du = 0, best_co = 0;
+  int n_acceptable = 0;
   int status = OBCA_MAXITER_EXCEEDED, it = 0;
   double dual_inf = 0, cviol = 0, compl0 = 0;
   for (;;) {
     // ---- error measures at the current iterate (c, gl, f are up to date)
     double e_du = 0, e_c = 0, e_c1 = 0, s_y = 0, s_z = 0, cmax0 = 0, cmaxmu_lo = INFINITY, cmaxmu_hi = 0;
+#pragma unroll 4
     for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
       double lo = xL[q], hi = xU[q];
       e_du = fmax(e_du, fabs(W.gl[q] - W.zL[q] + W.zU[q]));
@@ -135,6 +140,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
         s_z += W.zU[q];
       }
     }
+#pragma unroll 4
     for (int q = ctx.tid; q < L.ny; q += ctx.nt) {
       e_c = fmax(e_c, fabs(W.c[q]));
       e_c1 += fabs(W.c[q]);
@@ -157,6 +163,19 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       status = OBCA_SOLVE_SUCCEEDED;
       break;
     }
+    if (E0 <= 1e-6 && cviol <= 1e-2 && compl0 <= 1e-2) {
+      ++n_acceptable;
+      if (E0 < best_E) {
+        best_E = E0, best_f = f, best_cv = cviol, best_du = dual_inf, best_co = compl0;
+        for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.bx[q] = W.x[q], W.bzL[q] = W.zL[q], W.bzU[q] = W.zU[q];
+        for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.by[q] = W.y[q];
+      }
+      if (n_acceptable >= 15) {
+        status = OBCA_SOLVED_TO_ACCEPTABLE_LEVEL;
+        break;
+      }
+    } else
+      n_acceptable = 0;
     if (it >= o.max_iter) {
       status = OBCA_MAXITER_EXCEEDED;
       break;
@@ -185,24 +204,33 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     double dw = 0.0;
     bool first = true, have = false;
     for (;;) {
-      for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
-        double lo = xL[q], hi = xU[q];
-        bool hl = lo > -INFINITY, hu = hi < INFINITY;
-        double sg = dw, gp = W.gl[q];
-        if (hl) {
-          double gpL = W.x[q] - lo;
-          sg += W.zL[q] / gpL;
-          gp -= mu / gpL;
-          if (!hu) gp += o.kappa_d * mu;
+      {
+        const double* __restrict__ rx = W.x;
+        const double* __restrict__ rgl = W.gl;
+        const double* __restrict__ rzL = W.zL;
+        const double* __restrict__ rzU = W.zU;
+        double* __restrict__ wsig = W.sig;
+        double* __restrict__ wgphi = W.gphi;
+#pragma unroll 4
+        for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+          double lo = xL[q], hi = xU[q], xv = rx[q], zl = rzL[q], zu = rzU[q];
+          bool hl = lo > -INFINITY, hu = hi < INFINITY;
+          double sg = dw, gp = rgl[q];
+          if (hl) {
+            double gpL = xv - lo;
+            sg += zl / gpL;
+            gp -= mu / gpL;
+            if (!hu) gp += o.kappa_d * mu;
+          }
+          if (hu) {
+            double gpU = hi - xv;
+            sg += zu / gpU;
+            gp += mu / gpU;
+            if (!hl) gp -= o.kappa_d * mu;
+          }
+          wsig[q] = sg;
+          wgphi[q] = gp;
         }
-        if (hu) {
-          double gpU = hi - W.x[q];
-          sg += W.zU[q] / gpU;
-          gp += mu / gpU;
-          if (!hl) gp -= o.kappa_d * mu;
-        }
-        W.sig[q] = sg;
-        W.gphi[q] = gp;
       }
       cta_sync(ctx);
       if (kkt_solve(ctx, L, S, W, RW, &sh->ok)) {
@@ -223,24 +251,34 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     if (dw > 0) dw_last = dw;
     // ---- dz, fraction to the boundary, directional derivative of the barrier objective
     double a_pr = 1.0, a_du = 1.0, dphi = 0, rel = 0;
-    for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
-      double lo = xL[q], hi = xU[q], d = W.dx[q];
-      rel = fmax(rel, fabs(d) / (1.0 + fabs(W.x[q])));
-      if (lo > -INFINITY) {
-        double gp = W.x[q] - lo;
-        double dz = mu / gp - W.zL[q] - W.zL[q] / gp * d;
-        W.dzL[q] = dz;
-        if (d < 0) a_pr = fmin(a_pr, -tau * gp / d);
-        if (dz < 0) a_du = fmin(a_du, -tau * W.zL[q] / dz);
+    {
+      const double* __restrict__ rx = W.x;
+      const double* __restrict__ rdx = W.dx;
+      const double* __restrict__ rzL = W.zL;
+      const double* __restrict__ rzU = W.zU;
+      const double* __restrict__ rgphi = W.gphi;
+      double* __restrict__ wdzL = W.dzL;
+      double* __restrict__ wdzU = W.dzU;
+#pragma unroll 4
+      for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
+        double lo = xL[q], hi = xU[q], d = rdx[q], xv = rx[q], zl = rzL[q], zu = rzU[q], gq = rgphi[q];
+        rel = fmax(rel, fabs(d) / (1.0 + fabs(xv)));
+        if (lo > -INFINITY) {
+          double gp = xv - lo;
+          double dz = mu / gp - zl - zl / gp * d;
+          wdzL[q] = dz;
+          if (d < 0) a_pr = fmin(a_pr, -tau * gp / d);
+          if (dz < 0) a_du = fmin(a_du, -tau * zl / dz);
+        }
+        if (hi < INFINITY) {
+          double gp = hi - xv;
+          double dz = mu / gp - zu + zu / gp * d;
+          wdzU[q] = dz;
+          if (d > 0) a_pr = fmin(a_pr, tau * gp / d);
+          if (dz < 0) a_du = fmin(a_du, -tau * zu / dz);
+        }
+        dphi += gq * d;
       }
-      if (hi < INFINITY) {
-        double gp = hi - W.x[q];
-        double dz = mu / gp - W.zU[q] + W.zU[q] / gp * d;
-        W.dzU[q] = dz;
-        if (d > 0) a_pr = fmin(a_pr, tau * gp / d);
-        if (dz < 0) a_du = fmin(a_du, -tau * W.zU[q] / dz);
-      }
-      dphi += W.gphi[q] * d;
     }
     // grad_phi'dx = (gphi)'dx - y'J dx ; J dx = -c - (local delta_c terms, negligible) => use the exact product:
     // y'J dx is accumulated from the structure: J dx = -(c) on all rows up to delta_c * dy.
@@ -278,7 +316,13 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     } else
       tiny_last = false;
     while (alpha >= a_min && !accepted) {
-      for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.xt[q] = W.x[q] + alpha * W.dx[q];
+      {
+        const double* __restrict__ rx = W.x;
+        const double* __restrict__ rdx = W.dx;
+        double* __restrict__ wxt = W.xt;
+#pragma unroll 4
+        for (int q = ctx.tid; q < L.nx; q += ctx.nt) wxt[q] = rx[q] + alpha * rdx[q];
+      }
       cta_sync(ctx);
       eval_all(ctx, L, S, W, W.xt, nullptr, W.ct, nullptr, &ft, &gdt_t);
       double tht = 0;
@@ -316,8 +360,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     if (getenv("OBCA_TRACE")) printf("       a_pr=%.3e a_du=%.3e alpha=%.3e a_min=%.3e dphi=%.3e dw=%.1e acc=%d\n", a_pr, a_du, alpha, a_min, dphi, dw, (int)accepted);
 #endif
     if (!accepted) {
-      // IPOPT: a line-search failure at an "acceptable" point (acceptable_tol = 1e-6) ends with Solved_To_Acceptable_Level
-      status = (E0 <= 1e-6 && cviol <= 1e-2 && compl0 <= 1e-2) ? OBCA_SOLVED_TO_ACCEPTABLE_LEVEL : OBCA_RESTORATION_FAILED;
+      status = OBCA_RESTORATION_FAILED;  // becomes Solved_To_Acceptable_Level below when an acceptable point was stored
       break;
     }
     // ---- accept the trial point
@@ -338,6 +381,15 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     cta_sync(ctx);
     eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
     ++it;
+  }
+  cta_sync(ctx);
+  if (status != OBCA_SOLVE_SUCCEEDED && best_E < INFINITY) {
+    // restore the best acceptable point (IPOPT RestoreAcceptablePoint)
+    for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.x[q] = W.bx[q], W.zL[q] = W.bzL[q], W.zU[q] = W.bzU[q];
+    for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.y[q] = W.by[q];
+    status = OBCA_SOLVED_TO_ACCEPTABLE_LEVEL;
+    f = best_f, cviol = best_cv, dual_inf = best_du, compl0 = best_co;
+    cta_sync(ctx);
   }
   if (ctx.tid == 0) {
     res->status = status;

@@ -39,63 +39,115 @@ OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const 
     double yd = y[L.YPAIR(p, 0, n)], ye1[2] = {y[L.YPAIR(p, 1, n)], y[L.YPAIR(p, 2, n)]};
     double ye2[2] = {y[L.YPAIR(p, 3, n)], y[L.YPAIR(p, 4, n)]}, yn = y[L.YPAIR(p, 5, n)];
     double ynm = yn < 0 ? yn : 0.0;  // local convexification: exact at KKT points (yn = -z_sn <= 0)
-    double K[16 * 16];
+    // Block elimination in registers: lam, mu (diagonal Hessians) -> 5 x 5 Schur complement on (yd, ye1, ye2)
+    // (the yn row only has its own pivot), then the 2 x 2 system of s.  7 right-hand sides (6 pose couplings + residual).
     double X[16 * 7];
-    for (int q = 0; q < 16 * 16; ++q) K[q] = 0;
-    for (int q = 0; q < 16 * 7; ++q) X[q] = 0;
-    for (int r = 0; r < 4; ++r) {
-      K[r * 16 + r] = W.sig[L.PL(p, r, n)];
-      K[(4 + r) * 16 + 4 + r] = W.sig[L.PM(p, r, n)];
-      K[8 * 16 + r] = -B.ba[r];
-      K[8 * 16 + 4 + r] = -B.bb[r];
-      K[9 * 16 + r] = a.c * S.G[r][0] - a.s * S.G[r][1];
-      K[10 * 16 + r] = a.s * S.G[r][0] + a.c * S.G[r][1];
-      K[11 * 16 + 4 + r] = b.c * S.G[r][0] - b.s * S.G[r][1];
-      K[12 * 16 + 4 + r] = b.s * S.G[r][0] + b.c * S.G[r][1];
-    }
     const double isd = 1.0 / W.sig[L.PSD(p, n)], iel = 1.0 / W.sig[L.PEL(p, n)], isn = 1.0 / W.sig[L.PSN(p, n)];
-    K[8 * 16 + 8] = -(DELTA_C_LOCAL + isd + iel);
-    for (int r = 9; r < 13; ++r) K[r * 16 + r] = -DELTA_C_LOCAL;
-    K[13 * 16 + 13] = -(DELTA_C_LOCAL + isn);
-    K[14 * 16 + 14] = W.sig[L.PS(p, 0, n)] - 2.0 * ynm;
-    K[15 * 16 + 15] = W.sig[L.PS(p, 1, n)] - 2.0 * ynm;
-    K[14 * 16 + 9] = 1.0, K[15 * 16 + 10] = 1.0;
-    K[14 * 16 + 11] = -1.0, K[15 * 16 + 12] = -1.0;
-    K[14 * 16 + 13] = -2.0 * B.s[0], K[15 * 16 + 13] = -2.0 * B.s[1];
+    const double dn = DELTA_C_LOCAL + isn;
+    const double hs0 = W.sig[L.PS(p, 0, n)] - 2.0 * ynm, hs1 = W.sig[L.PS(p, 1, n)] - 2.0 * ynm;
+    double sl[4], smu[4], ea[4], fa[4], eb[4], fb[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      sl[r] = 1.0 / W.sig[L.PL(p, r, n)];
+      smu[r] = 1.0 / W.sig[L.PM(p, r, n)];
+      ea[r] = a.c * S.G[r][0] - a.s * S.G[r][1];
+      fa[r] = a.s * S.G[r][0] + a.c * S.G[r][1];
+      eb[r] = b.c * S.G[r][0] - b.s * S.G[r][1];
+      fb[r] = b.s * S.G[r][0] + b.c * S.G[r][1];
+    }
+    double S5[15];
+    {
+      double s00 = DELTA_C_LOCAL + isd + iel, s01 = 0, s02 = 0, s03 = 0, s04 = 0;
+      double s11 = DELTA_C_LOCAL, s12 = 0, s22 = DELTA_C_LOCAL, s33 = DELTA_C_LOCAL, s34 = 0, s44 = DELTA_C_LOCAL;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        s00 += B.ba[r] * B.ba[r] * sl[r] + B.bb[r] * B.bb[r] * smu[r];
+        s01 -= B.ba[r] * ea[r] * sl[r], s02 -= B.ba[r] * fa[r] * sl[r];
+        s03 -= B.bb[r] * eb[r] * smu[r], s04 -= B.bb[r] * fb[r] * smu[r];
+        s11 += ea[r] * ea[r] * sl[r], s12 += ea[r] * fa[r] * sl[r], s22 += fa[r] * fa[r] * sl[r];
+        s33 += eb[r] * eb[r] * smu[r], s34 += eb[r] * fb[r] * smu[r], s44 += fb[r] * fb[r] * smu[r];
+      }
+      S5[sym(0, 0)] = s00, S5[sym(1, 0)] = s01, S5[sym(2, 0)] = s02, S5[sym(3, 0)] = s03, S5[sym(4, 0)] = s04;
+      S5[sym(1, 1)] = s11, S5[sym(2, 1)] = s12, S5[sym(2, 2)] = s22, S5[sym(3, 1)] = 0, S5[sym(3, 2)] = 0, S5[sym(4, 1)] = 0, S5[sym(4, 2)] = 0;
+      S5[sym(3, 3)] = s33, S5[sym(4, 3)] = s34, S5[sym(4, 4)] = s44;
+    }
+    if (!chol_packed<5>(S5)) *ok = 0;
+    // Z = S6^-1 E' with E = [[0, 1, 0, -1, 0, -2 s0], [0, 0, 1, 0, -1, -2 s1]]
+    double Z0[6] = {0, 1, 0, -1, 0, -2.0 * B.s[0] / dn}, Z1[6] = {0, 0, 1, 0, -1, -2.0 * B.s[1] / dn};
+    chol_solve_packed<5>(S5, Z0);
+    chol_solve_packed<5>(S5, Z1);
+    // Ms = diag(hs) + E Z  (2 x 2, symmetric positive definite)
+    double m00 = hs0 + Z0[1] - Z0[3] - 2.0 * B.s[0] * Z0[5];
+    double m01 = Z1[1] - Z1[3] - 2.0 * B.s[0] * Z1[5];
+    double m11 = hs1 + Z1[2] - Z1[4] - 2.0 * B.s[1] * Z1[5];
+    double det = m00 * m11 - m01 * m01;
+    if (!(m00 > 0) || !(det > 0)) *ok = 0;
     // coupling columns: (x_a, y_a, psi_a, x_b, y_b, psi_b)
     double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
     double dRub[2] = {-b.s * B.ub[0] - b.c * B.ub[1], b.c * B.ub[0] - b.s * B.ub[1]};
     double dRtea[2] = {-a.s * ye1[0] + a.c * ye1[1], -a.c * ye1[0] - a.s * ye1[1]};  // (dR/dpsi)' ye1
     double dRteb[2] = {-b.s * ye2[0] + b.c * ye2[1], -b.c * ye2[0] - b.s * ye2[1]};
+    double C[16 * 6];
+#pragma unroll
+    for (int q = 0; q < 16 * 6; ++q) C[q] = 0;
+#pragma unroll
     for (int r = 0; r < 4; ++r) {
-      double aax = S.G[r][0] * a.c - S.G[r][1] * a.s, aay = S.G[r][0] * a.s + S.G[r][1] * a.c;
-      double abx = S.G[r][0] * b.c - S.G[r][1] * b.s, aby = S.G[r][0] * b.s + S.G[r][1] * b.c;
       double dax = -S.G[r][0] * a.s - S.G[r][1] * a.c, day = S.G[r][0] * a.c - S.G[r][1] * a.s;
       double dbx = -S.G[r][0] * b.s - S.G[r][1] * b.c, dby = S.G[r][0] * b.c - S.G[r][1] * b.s;
-      X[r * 7 + 0] = -yd * aax;
-      X[r * 7 + 1] = -yd * aay;
-      X[r * 7 + 2] = -yd * (dax * a.x + day * a.y) + S.G[r][0] * dRtea[0] + S.G[r][1] * dRtea[1];
-      X[(4 + r) * 7 + 3] = -yd * abx;
-      X[(4 + r) * 7 + 4] = -yd * aby;
-      X[(4 + r) * 7 + 5] = -yd * (dbx * b.x + dby * b.y) + S.G[r][0] * dRteb[0] + S.G[r][1] * dRteb[1];
-      X[r * 7 + 6] = -W.gphi[L.PL(p, r, n)];
-      X[(4 + r) * 7 + 6] = -W.gphi[L.PM(p, r, n)];
+      C[r * 6 + 0] = -yd * ea[r];
+      C[r * 6 + 1] = -yd * fa[r];
+      C[r * 6 + 2] = -yd * (dax * a.x + day * a.y) + S.G[r][0] * dRtea[0] + S.G[r][1] * dRtea[1];
+      C[(4 + r) * 6 + 3] = -yd * eb[r];
+      C[(4 + r) * 6 + 4] = -yd * fb[r];
+      C[(4 + r) * 6 + 5] = -yd * (dbx * b.x + dby * b.y) + S.G[r][0] * dRteb[0] + S.G[r][1] * dRteb[1];
     }
-    X[8 * 7 + 0] = -B.Rua[0], X[8 * 7 + 1] = -B.Rua[1], X[8 * 7 + 2] = -(a.x * dRua[0] + a.y * dRua[1]);
-    X[8 * 7 + 3] = -B.Rub[0], X[8 * 7 + 4] = -B.Rub[1], X[8 * 7 + 5] = -(b.x * dRub[0] + b.y * dRub[1]);
-    X[9 * 7 + 2] = dRua[0], X[10 * 7 + 2] = dRua[1];
-    X[11 * 7 + 5] = dRub[0], X[12 * 7 + 5] = dRub[1];
-    X[8 * 7 + 6] = -B.c[0] - W.gphi[L.PSD(p, n)] * isd + W.gphi[L.PEL(p, n)] * iel;
-    for (int r = 1; r < 5; ++r) X[(8 + r) * 7 + 6] = -B.c[r];
-    X[13 * 7 + 6] = -B.c[5] - W.gphi[L.PSN(p, n)] * isn;
-    X[14 * 7 + 6] = -W.gphi[L.PS(p, 0, n)];
-    X[15 * 7 + 6] = -W.gphi[L.PS(p, 1, n)];
-    double C[16 * 6];
-    for (int r = 0; r < 16; ++r)
-      for (int q = 0; q < 6; ++q) C[r * 6 + q] = X[r * 7 + q];
-    int nneg = ldl_factor<16>(K);
-    if (nneg != 6) *ok = 0;
-    for (int q = 0; q < 7; ++q) ldl_solve<16>(K, X + q, 7);
+    C[8 * 6 + 0] = -B.Rua[0], C[8 * 6 + 1] = -B.Rua[1], C[8 * 6 + 2] = -(a.x * dRua[0] + a.y * dRua[1]);
+    C[8 * 6 + 3] = -B.Rub[0], C[8 * 6 + 4] = -B.Rub[1], C[8 * 6 + 5] = -(b.x * dRub[0] + b.y * dRub[1]);
+    C[9 * 6 + 2] = dRua[0], C[10 * 6 + 2] = dRua[1];
+    C[11 * 6 + 5] = dRub[0], C[12 * 6 + 5] = dRub[1];
+    for (int k = 0; k < 7; ++k) {
+      double bl[4], bm[4], by[6], bs[2];
+      if (k < 6) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) bl[r] = C[r * 6 + k], bm[r] = C[(4 + r) * 6 + k];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) by[r] = C[(8 + r) * 6 + k];
+        bs[0] = bs[1] = 0;
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) bl[r] = -W.gphi[L.PL(p, r, n)], bm[r] = -W.gphi[L.PM(p, r, n)];
+        by[0] = -B.c[0] - W.gphi[L.PSD(p, n)] * isd + W.gphi[L.PEL(p, n)] * iel;
+#pragma unroll
+        for (int r = 1; r < 5; ++r) by[r] = -B.c[r];
+        by[5] = -B.c[5] - W.gphi[L.PSN(p, n)] * isn;
+        bs[0] = -W.gphi[L.PS(p, 0, n)], bs[1] = -W.gphi[L.PS(p, 1, n)];
+      }
+      // ry = J D^-1 b - by   (J rows: yd [-ba, -bb]; e1 [ea; fa | 0]; e2 [0 | eb; fb]; yn 0)
+      double ry[6] = {-by[0], -by[1], -by[2], -by[3], -by[4], -by[5]};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        double tl = bl[r] * sl[r], tm = bm[r] * smu[r];
+        ry[0] -= B.ba[r] * tl + B.bb[r] * tm;
+        ry[1] += ea[r] * tl, ry[2] += fa[r] * tl, ry[3] += eb[r] * tm, ry[4] += fb[r] * tm;
+      }
+      // u = S6^-1 ry ; ds = Ms^-1 (bs - E u) ; dy = u + Z ds
+      ry[5] /= dn;
+      chol_solve_packed<5>(S5, ry);
+      double q0 = bs[0] - (ry[1] - ry[3] - 2.0 * B.s[0] * ry[5]);
+      double q1 = bs[1] - (ry[2] - ry[4] - 2.0 * B.s[1] * ry[5]);
+      double ds0 = (m11 * q0 - m01 * q1) / det, ds1 = (m00 * q1 - m01 * q0) / det;
+      double dy[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) dy[r] = ry[r] + Z0[r] * ds0 + Z1[r] * ds1;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        X[r * 7 + k] = (bl[r] - (-B.ba[r] * dy[0] + ea[r] * dy[1] + fa[r] * dy[2])) * sl[r];
+        X[(4 + r) * 7 + k] = (bm[r] - (-B.bb[r] * dy[0] + eb[r] * dy[3] + fb[r] * dy[4])) * smu[r];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) X[(8 + r) * 7 + k] = dy[r];
+      X[14 * 7 + k] = ds0, X[15 * 7 + k] = ds1;
+    }
     double* xp = W.XP + (size_t)(p * L.Mv + n) * 112;
     for (int q = 0; q < 112; ++q) xp[q] = X[q];
     // Schur complement on (pose_a, pose_b): direct Hessian - C' Xc ; gradient C' Xr
@@ -176,42 +228,94 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
       obs_residual(S, j, p, B);
       double y1 = y[L.YOBS(a, j, 0, n)], y2[2] = {y[L.YOBS(a, j, 1, n)], y[L.YOBS(a, j, 2, n)]}, y3 = y[L.YOBS(a, j, 3, n)];
       double y3p = y3 > 0 ? y3 : 0.0;  // local convexification: exact at KKT points (y3 >= 0)
-      double K[12 * 12], X[12 * 4];
-      for (int q = 0; q < 144; ++q) K[q] = 0;
-      for (int q = 0; q < 48; ++q) X[q] = 0;
+      // Block elimination in registers: lam (H = diag + 2 y3+ A A'), mu (diagonal), then the 4 x 4 Schur complement
+      //   S = D + Jl Hl^-1 Jl' + Jm Dm^-1 Jm'  on (y1, y2, y3); 4 right-hand sides (3 pose couplings + residual).
+      double X[12 * 4];
       double dRy[2] = {-p.s * y2[0] - p.c * y2[1], p.c * y2[0] - p.s * y2[1]};   // (dR/dpsi) y2
       double dRtu[2] = {-p.s * B.u[0] + p.c * B.u[1], -p.c * B.u[0] - p.s * B.u[1]};  // (dR'/dpsi) u
+      double Hl[10], Jl[4][4], sm[4], Cl[4][3], bl[4], bm[4];
+#pragma unroll
       for (int r = 0; r < 4; ++r) {
         const double* A = S.obsA[j][r];
-        for (int q = 0; q <= r; ++q) K[r * 12 + q] = 2.0 * y3p * (A[0] * S.obsA[j][q][0] + A[1] * S.obsA[j][q][1]);
-        K[r * 12 + r] += W.sig[L.LAM(a, j, r, n)];
-        K[(4 + r) * 12 + 4 + r] = W.sig[L.MU(a, j, r, n)];
-        K[8 * 12 + r] = B.Atb[r];
-        K[8 * 12 + 4 + r] = -S.g[r];
-        K[9 * 12 + r] = p.c * A[0] + p.s * A[1];
-        K[10 * 12 + r] = -p.s * A[0] + p.c * A[1];
-        K[9 * 12 + 4 + r] = S.G[r][0];
-        K[10 * 12 + 4 + r] = S.G[r][1];
-        K[11 * 12 + r] = 2.0 * (A[0] * B.u[0] + A[1] * B.u[1]);
-        X[r * 4 + 0] = y1 * A[0];
-        X[r * 4 + 1] = y1 * A[1];
-        X[r * 4 + 2] = A[0] * dRy[0] + A[1] * dRy[1];
-        X[r * 4 + 3] = -W.gphi[L.LAM(a, j, r, n)];
-        X[(4 + r) * 4 + 3] = -W.gphi[L.MU(a, j, r, n)];
+#pragma unroll
+        for (int q = 0; q <= r; ++q) Hl[sym(r, q)] = 2.0 * y3p * (A[0] * S.obsA[j][q][0] + A[1] * S.obsA[j][q][1]);
+        Hl[sym(r, r)] += W.sig[L.LAM(a, j, r, n)];
+        sm[r] = W.sig[L.MU(a, j, r, n)];
+        Jl[0][r] = B.Atb[r];
+        Jl[1][r] = p.c * A[0] + p.s * A[1];
+        Jl[2][r] = -p.s * A[0] + p.c * A[1];
+        Jl[3][r] = 2.0 * (A[0] * B.u[0] + A[1] * B.u[1]);
+        Cl[r][0] = y1 * A[0];
+        Cl[r][1] = y1 * A[1];
+        Cl[r][2] = A[0] * dRy[0] + A[1] * dRy[1];
+        bl[r] = -W.gphi[L.LAM(a, j, r, n)];
+        bm[r] = -W.gphi[L.MU(a, j, r, n)];
       }
       const double isd = 1.0 / W.sig[L.SD(a, j, n)], iel = 1.0 / W.sig[L.EL(a, j, n)];
-      K[8 * 12 + 8] = -(DELTA_C_LOCAL + isd + iel);
-      for (int r = 9; r < 12; ++r) K[r * 12 + r] = -DELTA_C_LOCAL;
-      X[8 * 4 + 0] = B.u[0], X[8 * 4 + 1] = B.u[1];
-      X[9 * 4 + 2] = dRtu[0], X[10 * 4 + 2] = dRtu[1];
-      X[8 * 4 + 3] = -B.c[0] - W.gphi[L.SD(a, j, n)] * isd + W.gphi[L.EL(a, j, n)] * iel;
-      for (int r = 1; r < 4; ++r) X[(8 + r) * 4 + 3] = -B.c[r];
+      if (!chol_packed<4>(Hl)) *ok = 0;
+      double Wl[4][4];  // Wl[i] = Hl^-1 Jl[i]'
+#pragma unroll
+      for (int i2 = 0; i2 < 4; ++i2) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Wl[i2][r] = Jl[i2][r];
+        chol_solve_packed<4>(Hl, Wl[i2]);
+      }
+      // Jm rows: -g, G[:,0], G[:,1], 0
+      double Ss[10];
+#pragma unroll
+      for (int i2 = 0; i2 < 4; ++i2)
+#pragma unroll
+        for (int j2 = 0; j2 <= i2; ++j2) {
+          double acc = 0;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            acc += Jl[i2][r] * Wl[j2][r];
+            double ji = i2 == 0 ? -S.g[r] : (i2 == 1 ? S.G[r][0] : (i2 == 2 ? S.G[r][1] : 0.0));
+            double jj = j2 == 0 ? -S.g[r] : (j2 == 1 ? S.G[r][0] : (j2 == 2 ? S.G[r][1] : 0.0));
+            acc += ji * jj / sm[r];
+          }
+          Ss[sym(i2, j2)] = acc;
+        }
+      Ss[sym(0, 0)] += DELTA_C_LOCAL + isd + iel;
+      Ss[sym(1, 1)] += DELTA_C_LOCAL, Ss[sym(2, 2)] += DELTA_C_LOCAL, Ss[sym(3, 3)] += DELTA_C_LOCAL;
+      if (!chol_packed<4>(Ss)) *ok = 0;
+      const double Cy[4][3] = {{B.u[0], B.u[1], 0.0}, {0.0, 0.0, dRtu[0]}, {0.0, 0.0, dRtu[1]}, {0.0, 0.0, 0.0}};
+      const double byr[4] = {-B.c[0] - W.gphi[L.SD(a, j, n)] * isd + W.gphi[L.EL(a, j, n)] * iel, -B.c[1], -B.c[2], -B.c[3]};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        double t[4], ry[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) t[r] = k < 3 ? Cl[r][k] : bl[r];
+        chol_solve_packed<4>(Hl, t);
+#pragma unroll
+        for (int i2 = 0; i2 < 4; ++i2) {
+          double acc = k < 3 ? -Cy[i2][k] : -byr[i2];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            acc += Jl[i2][r] * t[r];
+            if (k == 3) {
+              double ji = i2 == 0 ? -S.g[r] : (i2 == 1 ? S.G[r][0] : (i2 == 2 ? S.G[r][1] : 0.0));
+              acc += ji * bm[r] / sm[r];
+            }
+          }
+          ry[i2] = acc;
+        }
+        chol_solve_packed<4>(Ss, ry);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          double dl = t[r], jm = -S.g[r] * ry[0] + S.G[r][0] * ry[1] + S.G[r][1] * ry[2];
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) dl -= Wl[i2][r] * ry[i2];
+          X[r * 4 + k] = dl;
+          X[(4 + r) * 4 + k] = ((k == 3 ? bm[r] : 0.0) - jm) / sm[r];
+          X[(8 + r) * 4 + k] = ry[r];
+        }
+      }
       double C[12 * 3];
-      for (int r = 0; r < 12; ++r)
-        for (int q = 0; q < 3; ++q) C[r * 3 + q] = X[r * 4 + q];
-      int nneg = ldl_factor<12>(K);
-      if (nneg != 4) *ok = 0;
-      for (int q = 0; q < 4; ++q) ldl_solve<12>(K, X + q, 4);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) C[r * 3 + q] = Cl[r][q], C[(4 + r) * 3 + q] = 0.0, C[(8 + r) * 3 + q] = Cy[r][q];
       double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 48;
       for (int q = 0; q < 48; ++q) xo[q] = X[q];
       H[sym(2, 2)] -= y2[0] * (p.c * B.u[0] + p.s * B.u[1]) + y2[1] * (-p.s * B.u[0] + p.c * B.u[1]);
@@ -641,51 +745,78 @@ OBCA_HD double tt_entry(const double* T, int k, int m, int col) {
   return T[((k - 1) * NZ + m) * NRED + col];
 }
 
-// cross-vehicle coupling: one thread per (pair, interval)
-OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W) {
-  for (int it = ctx.tid; it < L.P * L.Nmax; it += ctx.nt) {
+// cross-vehicle coupling: one warp per (pair, interval); lanes own the output entries
+//   Mab[ra][cb] = sum_k Ta_k[:,ra]' Hc_k Tb_k[:,cb]  (pose rows of the T maps), plus the two gradient pieces
+OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, double* arena) {
+#if defined(__CUDA_ARCH__)
+  const int wid = ctx.tid >> 5, nw = ctx.nt >> 5;
+#else
+  const int wid = 0, nw = 1;
+#endif
+  double* sw = arena + (size_t)wid * NSW;
+  double* ta = sw;                  // [6][3][NRED] pose rows of Ta
+  double* tb = ta + NK * 3 * NRED;  // [6][3][NRED]
+  double* sa = tb + NK * 3 * NRED;  // [6][3] pose entries of s0a
+  double* sb = sa + NK * 3;         // [6][3]
+  double* hc = sb + NK * 3;         // [6][9] rows pose_a, cols pose_b
+  for (int it = wid; it < L.P * L.Nmax; it += nw) {
     int p = it / L.Nmax, i = it % L.Nmax;
     if (i * NK >= L.Mp[p]) continue;
     int a = L.pa[p], b = L.pb[p];
     const double* Ta = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
     const double* Tb = W.TT + (size_t)(b * L.Nmax + i) * (NW * NRED + NW);
-    const double *s0a = Ta + NW * NRED, *s0b = Tb + NW * NRED;
-    double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
-    for (int q = 0; q < NRED * NRED + 2 * NRED; ++q) Mo[q] = 0;
-    for (int k = 0; k < NK; ++k) {
-      const double* ph = W.PH + (size_t)(p * L.Mv + i * NK + k) * 27;
-      double Hc[3][3];
-      for (int r = 0; r < 3; ++r)
-        for (int m = 0; m < 3; ++m) Hc[r][m] = ph[sym(3 + m, r)];  // rows pose_a, cols pose_b
-      double HTb[3][NRED], Hs0b[3], Hts0a[3];
-      for (int r = 0; r < 3; ++r) {
-        for (int col = 0; col < NRED; ++col) {
-          double s = 0;
-          for (int m = 0; m < 3; ++m) s += Hc[r][m] * tt_entry(Tb, k, m, col);
-          HTb[r][col] = s;
-        }
-        double s = 0, t = 0;
-        for (int m = 0; m < 3; ++m) {
-          s += Hc[r][m] * (k == 0 ? 0.0 : s0b[(k - 1) * NZ + m]);
-          t += Hc[m][r] * (k == 0 ? 0.0 : s0a[(k - 1) * NZ + m]);
-        }
-        Hs0b[r] = s;
-        Hts0a[r] = t;
+    OBCA_LANES(lane) {
+      for (int e = lane; e < NK * 3 * NRED; e += 32) {
+        int k = e / (3 * NRED), r = (e / NRED) % 3, col = e % NRED;
+        ta[e] = tt_entry(Ta, k, r, col);
+        tb[e] = tt_entry(Tb, k, r, col);
       }
-      for (int ra = 0; ra < NRED; ++ra) {
-        double ga = 0;
-        for (int r = 0; r < 3; ++r) {
-          double ta = tt_entry(Ta, k, r, ra);
-          if (ta == 0.0) continue;
-          for (int cb = 0; cb < NRED; ++cb) Mo[ra * NRED + cb] += ta * HTb[r][cb];
-          ga += ta * Hs0b[r];
-        }
-        Mo[NRED * NRED + ra] += ga;
-        double gb = 0;
-        for (int r = 0; r < 3; ++r) gb += tt_entry(Tb, k, r, ra) * Hts0a[r];
-        Mo[NRED * NRED + NRED + ra] += gb;
+      for (int e = lane; e < NK * 3; e += 32) {
+        int k = e / 3, r = e % 3;
+        sa[e] = k == 0 ? 0.0 : Ta[NW * NRED + (k - 1) * NZ + r];
+        sb[e] = k == 0 ? 0.0 : Tb[NW * NRED + (k - 1) * NZ + r];
+      }
+      for (int e = lane; e < NK * 9; e += 32) {
+        int k = e / 9, r = (e / 3) % 3, m = e % 3;
+        hc[e] = W.PH[(size_t)(p * L.Mv + i * NK + k) * 27 + sym(3 + m, r)];
       }
     }
+    OBCA_WARP_SYNC();
+    double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
+    OBCA_LANES(lane) {
+      for (int e = lane; e < NRED * NRED + 2 * NRED; e += 32) {
+        double acc = 0;
+        if (e < NRED * NRED) {
+          int ra = e / NRED, cb = e % NRED;
+          for (int k = 0; k < NK; ++k)
+            for (int r = 0; r < 3; ++r) {
+              double t = ta[(k * 3 + r) * NRED + ra];
+              if (t == 0.0) continue;
+              double h = 0;
+              for (int m = 0; m < 3; ++m) h += hc[k * 9 + r * 3 + m] * tb[(k * 3 + m) * NRED + cb];
+              acc += t * h;
+            }
+        } else if (e < NRED * NRED + NRED) {
+          int ra = e - NRED * NRED;  // Ta' Hc s0b
+          for (int k = 0; k < NK; ++k)
+            for (int r = 0; r < 3; ++r) {
+              double h = 0;
+              for (int m = 0; m < 3; ++m) h += hc[k * 9 + r * 3 + m] * sb[k * 3 + m];
+              acc += ta[(k * 3 + r) * NRED + ra] * h;
+            }
+        } else {
+          int rb = e - NRED * NRED - NRED;  // Tb' Hc' s0a
+          for (int k = 0; k < NK; ++k)
+            for (int m = 0; m < 3; ++m) {
+              double h = 0;
+              for (int r = 0; r < 3; ++r) h += hc[k * 9 + r * 3 + m] * sa[k * 3 + r];
+              acc += tb[(k * 3 + m) * NRED + rb] * h;
+            }
+        }
+        Mo[e] = acc;
+      }
+    }
+    OBCA_WARP_SYNC();
   }
 }
 
@@ -1276,7 +1407,7 @@ OBCA_HDN int kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratc
   interval_nullspace(ctx, L, S, W, ok_shared, ok_shared + 1, RW);
   cta_sync(ctx);
   prof_mark(ctx, 4);
-  interval_cross(ctx, L, W);
+  interval_cross(ctx, L, W, RW);
   cta_sync(ctx);
   prof_mark(ctx, 5);
   riccati_backward(ctx, L, W, RW, hdtdt, ok_shared);

@@ -175,6 +175,8 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
     delta_w_last = 0.0
     tiny_last = False
     force_mu = False
+    best = None  # IPOPT StoreAcceptablePoint: best iterate with E0 <= acceptable_tol = 1e-6
+    n_acceptable = 0
     hist = []
     status = -1
     it = 0
@@ -197,6 +199,15 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
         if E(0.0) <= o.tol and dual_inf <= o.dual_inf_tol and cviol <= o.constr_viol_tol and compl(0.0) <= o.compl_inf_tol:
             status = 0
             break
+        if E(0.0) <= 1e-6 and cviol <= 1e-2 and compl(0.0) <= 1e-2:
+            n_acceptable += 1
+            if best is None or E(0.0) < best[0]:
+                best = (E(0.0), x.copy(), y.copy(), zL.copy(), zU.copy())
+            if n_acceptable >= 15:
+                status = 1
+                break
+        else:
+            n_acceptable = 0
         if it >= o.max_iter:
             status = -1
             break
@@ -291,8 +302,7 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
                     break
             alpha *= 0.5
         if not accepted:
-            # IPOPT: a line-search failure at an "acceptable" point (acceptable_tol = 1e-6) is Solved_To_Acceptable_Level
-            status = 1 if (E(0.0) <= 1e-6 and cviol <= 1e-2 and compl(0.0) <= 1e-2) else -2
+            status = -2  # becomes Solved_To_Acceptable_Level below when an acceptable point was stored
             break
         x = x + alpha * dx
         y = y + alpha * dy
@@ -303,4 +313,7 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
         zU = np.where(hasU, np.clip(zU, mu / (o.kappa_sigma * gU), o.kappa_sigma * mu / gU), 0.0)
         hist[-1].update(alpha=alpha, alpha_du=a_du, dw_used=dw)
         it += 1
+    if status != 0 and best is not None:
+        _, x, y, zL, zU = best  # IPOPT RestoreAcceptablePoint
+        status = 1
     return IpmResult(x, y, zL, zU, status, it, float(nlp.f(x)), float(np.abs(nlp.c(x)).max()), float(dual_inf), float(compl(0.0)), mu, hist)
