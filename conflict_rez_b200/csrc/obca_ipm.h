@@ -125,19 +125,34 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
   for (;;) {
     // ---- error measures at the current iterate (c, gl, f are up to date)
     double e_du = 0, e_c = 0, e_c1 = 0, s_y = 0, s_z = 0, cmax0 = 0, cmaxmu_lo = INFINITY, cmaxmu_hi = 0;
-#pragma unroll 4
-    for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
-      double lo = xL[q], hi = xU[q];
-      e_du = fmax(e_du, fabs(W.gl[q] - W.zL[q] + W.zU[q]));
-      if (lo > -INFINITY) {
-        double pr = (W.x[q] - lo) * W.zL[q];
-        cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
-        s_z += W.zL[q];
+    double s_log = 0, s_gap = 0;  // barrier pieces: phi = f + mu (-sum log gap + kappa_d sum one-sided gap)
+    for (int q0 = ctx.tid; q0 < L.nx; q0 += 4 * ctx.nt) {
+      double lo[4], hi[4], xv[4], zl[4], zu[4], gq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int q = q0 + u * ctx.nt;
+        bool in = q < L.nx;
+        lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
+        xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0, gq[u] = in ? W.gl[q] : 0.0;
       }
-      if (hi < INFINITY) {
-        double pr = (hi - W.x[q]) * W.zU[q];
-        cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
-        s_z += W.zU[q];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        e_du = fmax(e_du, fabs(gq[u] - zl[u] + zu[u]));
+        bool hl = lo[u] > -INFINITY, hu = hi[u] < INFINITY;
+        if (hl) {
+          double gp = xv[u] - lo[u], pr = gp * zl[u];
+          cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
+          s_z += zl[u];
+          s_log -= log(gp);
+          if (!hu) s_gap += gp;
+        }
+        if (hu) {
+          double gp = hi[u] - xv[u], pr = gp * zu[u];
+          cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
+          s_z += zu[u];
+          s_log -= log(gp);
+          if (!hl) s_gap += gp;
+        }
       }
     }
 #pragma unroll 4
@@ -151,6 +166,8 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     double theta = cta_sum(ctx, e_c1);
     s_y = cta_sum(ctx, s_y);
     s_z = cta_sum(ctx, s_z);
+    s_log = cta_sum(ctx, s_log);
+    s_gap = cta_sum(ctx, s_gap);
     compl0 = cta_max(ctx, cmax0);
     double pr_lo = cta_min(ctx, cmaxmu_lo), pr_hi = cta_max(ctx, cmaxmu_hi);
     double s_d = fmax(o.s_max, (s_y + s_z) / fmax(1.0, (double)(cnt.m_active + cnt.nb))) / o.s_max;
@@ -199,37 +216,38 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     cta_sync(ctx);
     const double tau = fmax(o.tau_min, 1.0 - mu);
     // ---- gradient of the barrier Lagrangian, barrier objective and grad_phi'dx bookkeeping
-    double phi = barrier_obj(ctx, L, xL, xU, W.x, f, mu, o.kappa_d);
+    const double phi = f + mu * (s_log + o.kappa_d * s_gap);  // the iterate is strictly inside its bounds
     // ---- search direction with inertia correction
     double dw = 0.0;
     bool first = true, have = false;
     for (;;) {
-      {
-        const double* __restrict__ rx = W.x;
-        const double* __restrict__ rgl = W.gl;
-        const double* __restrict__ rzL = W.zL;
-        const double* __restrict__ rzU = W.zU;
-        double* __restrict__ wsig = W.sig;
-        double* __restrict__ wgphi = W.gphi;
-#pragma unroll 4
-        for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
-          double lo = xL[q], hi = xU[q], xv = rx[q], zl = rzL[q], zu = rzU[q];
-          bool hl = lo > -INFINITY, hu = hi < INFINITY;
-          double sg = dw, gp = rgl[q];
+      for (int q0 = ctx.tid; q0 < L.nx; q0 += 4 * ctx.nt) {
+        double lo[4], hi[4], xv[4], zl[4], zu[4], gq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          int q = q0 + u * ctx.nt;
+          bool in = q < L.nx;
+          lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
+          xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0, gq[u] = in ? W.gl[q] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          int q = q0 + u * ctx.nt;
+          bool hl = lo[u] > -INFINITY, hu = hi[u] < INFINITY;
+          double sg = dw, gp = gq[u];
           if (hl) {
-            double gpL = xv - lo;
-            sg += zl / gpL;
+            double gpL = xv[u] - lo[u];
+            sg += zl[u] / gpL;
             gp -= mu / gpL;
             if (!hu) gp += o.kappa_d * mu;
           }
           if (hu) {
-            double gpU = hi - xv;
-            sg += zu / gpU;
+            double gpU = hi[u] - xv[u];
+            sg += zu[u] / gpU;
             gp += mu / gpU;
             if (!hl) gp -= o.kappa_d * mu;
           }
-          wsig[q] = sg;
-          wgphi[q] = gp;
+          if (q < L.nx) W.sig[q] = sg, W.gphi[q] = gp;
         }
       }
       cta_sync(ctx);
@@ -251,33 +269,33 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     if (dw > 0) dw_last = dw;
     // ---- dz, fraction to the boundary, directional derivative of the barrier objective
     double a_pr = 1.0, a_du = 1.0, dphi = 0, rel = 0;
-    {
-      const double* __restrict__ rx = W.x;
-      const double* __restrict__ rdx = W.dx;
-      const double* __restrict__ rzL = W.zL;
-      const double* __restrict__ rzU = W.zU;
-      const double* __restrict__ rgphi = W.gphi;
-      double* __restrict__ wdzL = W.dzL;
-      double* __restrict__ wdzU = W.dzU;
-#pragma unroll 4
-      for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
-        double lo = xL[q], hi = xU[q], d = rdx[q], xv = rx[q], zl = rzL[q], zu = rzU[q], gq = rgphi[q];
-        rel = fmax(rel, fabs(d) / (1.0 + fabs(xv)));
-        if (lo > -INFINITY) {
-          double gp = xv - lo;
-          double dz = mu / gp - zl - zl / gp * d;
-          wdzL[q] = dz;
+    for (int q0 = ctx.tid; q0 < L.nx; q0 += 4 * ctx.nt) {
+      double lo[4], hi[4], xv[4], zl[4], zu[4], gq[4], dd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int q = q0 + u * ctx.nt;
+        bool in = q < L.nx;
+        lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
+        xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0;
+        gq[u] = in ? W.gphi[q] : 0.0, dd[u] = in ? W.dx[q] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        double d = dd[u];
+        rel = fmax(rel, fabs(d) / (1.0 + fabs(xv[u])));
+        if (lo[u] > -INFINITY) {
+          double gp = xv[u] - lo[u];
+          double dz = mu / gp - zl[u] - zl[u] / gp * d;
           if (d < 0) a_pr = fmin(a_pr, -tau * gp / d);
-          if (dz < 0) a_du = fmin(a_du, -tau * zl / dz);
+          if (dz < 0) a_du = fmin(a_du, -tau * zl[u] / dz);
         }
-        if (hi < INFINITY) {
-          double gp = hi - xv;
-          double dz = mu / gp - zu + zu / gp * d;
-          wdzU[q] = dz;
+        if (hi[u] < INFINITY) {
+          double gp = hi[u] - xv[u];
+          double dz = mu / gp - zu[u] + zu[u] / gp * d;
           if (d > 0) a_pr = fmin(a_pr, tau * gp / d);
-          if (dz < 0) a_du = fmin(a_du, -tau * zu / dz);
+          if (dz < 0) a_du = fmin(a_du, -tau * zu[u] / dz);
         }
-        dphi += gq * d;
+        dphi += gq[u] * d;
       }
     }
     // grad_phi'dx = (gphi)'dx - y'J dx ; J dx = -c - (local delta_c terms, negligible) => use the exact product:
@@ -363,18 +381,32 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       status = OBCA_RESTORATION_FAILED;  // becomes Solved_To_Acceptable_Level below when an acceptable point was stored
       break;
     }
-    // ---- accept the trial point
-    for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
-      double lo = xL[q], hi = xU[q];
-      double xv = W.xt[q];
-      W.x[q] = xv;
-      if (lo > -INFINITY) {
-        double gp = xv - lo, zv = W.zL[q] + a_du * W.dzL[q];
-        W.zL[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
+    // ---- accept the trial point (dz is recomputed from dx; x + alpha dx reproduces the trial point bit for bit)
+    for (int q0 = ctx.tid; q0 < L.nx; q0 += 4 * ctx.nt) {
+      double lo[4], hi[4], xv[4], zl[4], zu[4], dd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int q = q0 + u * ctx.nt;
+        bool in = q < L.nx;
+        lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
+        xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0, dd[u] = in ? W.dx[q] : 0.0;
       }
-      if (hi < INFINITY) {
-        double gp = hi - xv, zv = W.zU[q] + a_du * W.dzU[q];
-        W.zU[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int q = q0 + u * ctx.nt;
+        if (q >= L.nx) continue;
+        double d = dd[u], xn = xv[u] + alpha * d;
+        W.x[q] = xn;
+        if (lo[u] > -INFINITY) {
+          double gp0 = xv[u] - lo[u], gp = xn - lo[u];
+          double zv = zl[u] + a_du * (mu / gp0 - zl[u] - zl[u] / gp0 * d);
+          W.zL[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
+        }
+        if (hi[u] < INFINITY) {
+          double gp0 = hi[u] - xv[u], gp = hi[u] - xn;
+          double zv = zu[u] + a_du * (mu / gp0 - zu[u] + zu[u] / gp0 * d);
+          W.zU[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
+        }
       }
     }
     for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.y[q] += alpha * W.dy[q];

@@ -497,19 +497,30 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   // Householder QR with rank test (LAPACK dgeqr2 reflector convention: v[rk] = 1 implicit)
   int rk = 0, ndrop = 0, nem = 0;
   for (int j = 0; j < nr; ++j) {
-    OBCA_LANES(lane) {
+    double full = 0, nrm = 0;
+#if defined(__CUDA_ARCH__)
+    {
+      const int lane = ctx.tid & 31;
       double head = 0, tail = 0;
       for (int q = lane; q < NW; q += 32) {
         double v = Mq[q * NC + j];
         if (q < rk) head += v * v;
         else if (q > rk) tail += v * v;
       }
-      wred[lane] = head, wred[32 + lane] = tail;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        head += __shfl_xor_sync(0xffffffffu, head, o);
+        tail += __shfl_xor_sync(0xffffffffu, tail, o);
+      }
+      full = head, nrm = tail;
     }
-    OBCA_WARP_SYNC();
-    double full = 0, nrm = 0;
-    for (int q = 0; q < 32; ++q) full += wred[q], nrm += wred[32 + q];
-    OBCA_WARP_SYNC();
+#else
+    for (int q = 0; q < NW; ++q) {
+      double v = Mq[q * NC + j];
+      if (q < rk) full += v * v;
+      else if (q > rk) nrm += v * v;
+    }
+#endif
     double alpha = rk < NW ? Mq[rk * NC + j] : 0.0;
     double beta = sqrt(alpha * alpha + nrm);
     full = sqrt(full + alpha * alpha + nrm);
@@ -997,7 +1008,9 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     }
     cta_sync(ctx);
     const int nu = R.uoff[V];
+    prof_mark(ctx, 6);
     riccati_stage_assemble(ctx, L, W, R, i, hdtdt, nu);
+    prof_mark(ctx, 12);
     // PA = P A ; PB = P B ; pc = P c + p   (block structure of A, B)
     for (int it = ctx.tid; it < nX * (nX + nu + 1); it += ctx.nt) {
       int r = it / (nX + nu + 1), col = it % (nX + nu + 1);
@@ -1044,6 +1057,7 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
       }
     }
     cta_sync(ctx);
+    prof_mark(ctx, 13);
     // Cholesky F = L L' (right-looking, whole CTA); a non-positive pivot means the reduced Hessian is not PD
     for (int j = 0; j < nu; ++j) {
       cta_sync(ctx);
@@ -1062,6 +1076,7 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
       }
     }
     cta_sync(ctx);
+    prof_mark(ctx, 14);
     // [K | k] = -F^-1 Gm : one thread per column
     for (int col = ctx.tid; col < nX + 1; col += ctx.nt) {
       double tmp[NUMAX];
@@ -1078,6 +1093,7 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
       for (int r = 0; r < nu; ++r) R.K[r * (nX + 1) + col] = -tmp[r];
     }
     cta_sync(ctx);
+    prof_mark(ctx, 15);
     // gains to global memory (forward pass) in the padded layout [nUmax][nX] + [nUmax]
     {
       double* Kg = W.RK + (size_t)i * kstride;

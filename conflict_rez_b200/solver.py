@@ -323,7 +323,7 @@ class ObcaSolver:
         return {k: int(buf[i]) for i, k in enumerate(names)}
 
     PHASES = ["eval_pairs", "eval_nodes", "pair_eliminate", "node_assemble", "nullspace", "cross", "riccati_bwd", "riccati_fwd",
-              "expand+residual", "multipliers", "local_backsub", "ipm_vector_ops"]
+              "expand+residual", "multipliers", "local_backsub", "ipm_vector_ops", "ric_assemble", "ric_products", "ric_cholesky", "ric_ksolve"]
 
     def debug_profile(self):
         buf = (ctypes.c_int64 * 16)()
