@@ -321,7 +321,9 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     double ft = f, gdt_t;
     // IPOPT compares with a machine-precision slack (Compare_le: lhs - rhs <= 10 eps |base|)
     const double EPS = 2.220446049250313e-16;
-    const double slack_phi = 10 * EPS * fabs(phi), slack_th = 10 * EPS * fabs(theta);
+    // ... widened to 1e-10 (relative to max(1, |.|)): the structured solve has no iterative refinement, its steps carry ~1e-8
+    // relative noise, and near the solution phi / theta changes of that size must not trigger backtracking
+    const double slack_phi = 1e-10 * fmax(1.0, fabs(phi)), slack_th = 1e-10 * fmax(1.0, theta);
     // tiny-step rule: a step below 10 eps relative size is accepted without line search and forces a mu update
     if (rel < 10 * EPS) {
       if (tiny_last && mu <= mu_min) {

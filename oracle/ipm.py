@@ -272,7 +272,8 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
         alpha = a_pr
         accepted = False
         # IPOPT compares with a machine-precision slack (Compare_le: lhs - rhs <= 10 eps |base|)
-        slack_phi, slack_th = 10 * np.finfo(float).eps * abs(ph), 10 * np.finfo(float).eps * abs(th)
+        # widened to 1e-10 relative (shared with the CUDA solver, whose structured steps carry ~1e-8 relative noise)
+        slack_phi, slack_th = 1e-10 * max(1.0, abs(ph)), 1e-10 * max(1.0, th)
         # tiny-step rule: a step below 10 eps relative size is accepted without line search and forces a mu update
         tiny = np.max(np.abs(dx) / (1.0 + np.abs(x))) < 10 * np.finfo(float).eps
         if tiny:
