@@ -838,13 +838,14 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, dou
 // All stage matrices live in the work arena RW (shared memory on the device).
 // ------------------------------------------------------------------------------------------------
 struct RicWork {
-  double *P, *p, *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *K, *Ab, *Bb, *db, *cb;
+  double *P, *p, *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *K, *Ab, *Bb, *db, *cb, *invd, *MAs, *MABs;
   int *uoff, *npv;  // [MAXV + 1]
 };
 
 inline size_t riccati_only_doubles(const Lay& L) {
   size_t nX = L.nX, nU = L.nU;
-  return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32;
+  return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU +
+         (size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED);
 }
 
 // work arena shared by the null-space phase (NSW doubles per warp) and the Riccati phase
@@ -872,6 +873,9 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
   R.Bb = w, w += L.V * 7 * NP;
   R.db = w, w += L.V * 7;
   R.cb = w, w += L.V * 7;
+  R.invd = w, w += nU;
+  R.MAs = w, w += L.V * (NSYM + NRED);
+  R.MABs = w, w += L.P * (NRED * NRED + 2 * NRED);
   R.uoff = (int*)w;
   R.npv = R.uoff + (MAXV + 1);
 }
@@ -906,6 +910,15 @@ OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch
   for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.Q[q] = 0;
   for (int q = ctx.tid; q < nu * nX; q += ctx.nt) R.S[q] = 0;
   for (int q = ctx.tid; q < nu * nu; q += ctx.nt) R.R[q] = 0;
+  // stage data -> shared memory (coalesced, independent loads)
+  for (int it = ctx.tid; it < V * (NSYM + NRED); it += ctx.nt) {
+    int a = it / (NSYM + NRED);
+    R.MAs[it] = i < L.N[a] ? W.MA[(size_t)(a * L.Nmax + i) * (NSYM + NRED) + it % (NSYM + NRED)] : 0.0;
+  }
+  for (int it = ctx.tid; it < L.P * (NRED * NRED + 2 * NRED); it += ctx.nt) {
+    int p = it / (NRED * NRED + 2 * NRED);
+    R.MABs[it] = i * NK < L.Mp[p] ? W.MAB[(size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED) + it % (NRED * NRED + 2 * NRED)] : 0.0;
+  }
   // block dynamics from the T maps
   for (int it = ctx.tid; it < V * 7 * (NRED + 1); it += ctx.nt) {
     int a = it / (7 * (NRED + 1)), r = (it / (NRED + 1)) % 7, cc = it % (NRED + 1);
@@ -926,7 +939,7 @@ OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch
     int kr, kc;
     int tr = red_target(a, r, V, R.uoff, R.npv, &kr), tc = red_target(a, cc, V, R.uoff, R.npv, &kc);
     if (kr < 0 || kc < 0) continue;
-    double v = W.MA[(size_t)(a * L.Nmax + i) * (NSYM + NRED) + sym(r, cc)];
+    double v = R.MAs[a * (NSYM + NRED) + sym(r, cc)];
     if (kr == 0 && kc == 0) R.Q[tr * nX + tc] = v;
     else if (kr == 1 && kc == 0) R.S[tr * nX + tc] = v;
     else if (kr == 1 && kc == 1) R.R[tr * nu + tc] = v;
@@ -938,7 +951,7 @@ OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch
     int a = L.pa[p], b = L.pb[p], ka, kb;
     int ta = red_target(a, ra, V, R.uoff, R.npv, &ka), tb = red_target(b, cb, V, R.uoff, R.npv, &kb);
     if (ka < 0 || kb < 0) continue;
-    double v = W.MAB[(size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED) + ra * NRED + cb];
+    double v = R.MABs[p * (NRED * NRED + 2 * NRED) + ra * NRED + cb];
     if (ka == 0 && kb == 0) R.Q[ta * nX + tb] = v, R.Q[tb * nX + ta] = v;
     else if (ka == 1 && kb == 0) R.S[ta * nX + tb] = v;
     else if (ka == 0 && kb == 1) R.S[tb * nX + ta] = v;
@@ -955,12 +968,12 @@ OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch
     double hd = 0, g = 0;
     if (a >= 0) {
       if (i < L.N[a]) {
-        const double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
+        const double* Mo = R.MAs + a * (NSYM + NRED);
         hd = Mo[sym(IDT, rc)], g = Mo[NSYM + rc];
       }
       for (int p = 0; p < L.P; ++p) {
         if (i * NK >= L.Mp[p]) continue;
-        const double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
+        const double* Mo = R.MABs + p * (NRED * NRED + 2 * NRED);
         if (L.pa[p] == a) hd += Mo[rc * NRED + IDT], g += Mo[NRED * NRED + rc];
         else if (L.pb[p] == a) hd += Mo[IDT * NRED + rc], g += Mo[NRED * NRED + NRED + rc];
       }
@@ -969,12 +982,12 @@ OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch
     } else {
       for (int aa = 0; aa < V; ++aa) {
         if (i >= L.N[aa]) continue;
-        const double* Mo = W.MA + (size_t)(aa * L.Nmax + i) * (NSYM + NRED);
+        const double* Mo = R.MAs + aa * (NSYM + NRED);
         hd += Mo[sym(IDT, IDT)], g += Mo[NSYM + IDT];
       }
       for (int p = 0; p < L.P; ++p) {
         if (i * NK >= L.Mp[p]) continue;
-        const double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
+        const double* Mo = R.MABs + p * (NRED * NRED + 2 * NRED);
         hd += 2.0 * Mo[IDT * NRED + IDT], g += Mo[NRED * NRED + IDT] + Mo[NRED * NRED + NRED + IDT];
       }
       if (i == 0) hd += hdtdt, g += W.gphi[L.oDT];
@@ -1058,39 +1071,50 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     }
     cta_sync(ctx);
     prof_mark(ctx, 13);
-    // Cholesky F = L L' (right-looking, whole CTA); a non-positive pivot means the reduced Hessian is not PD
-    for (int j = 0; j < nu; ++j) {
-      cta_sync(ctx);
-      double d = R.F[j * nu + j];
-      bool bad = !(d > 1e-14 * fmax(1.0, fabs(R.R[j * nu + j])));
-      if (bad) d = 1.0;
-      double sd = sqrt(d);
-      cta_sync(ctx);
-      if (bad && ctx.tid == 0) *ok = 0;
-      for (int r = j + ctx.tid; r < nu; r += ctx.nt) R.F[r * nu + j] = (r == j) ? sd : R.F[r * nu + j] / sd;
-      cta_sync(ctx);
-      int rem = nu - j - 1;
-      for (int it = ctx.tid; it < rem * rem; it += ctx.nt) {
-        int r = j + 1 + it / rem, c = j + 1 + it % rem;
-        if (c <= r) R.F[r * nu + c] -= R.F[r * nu + j] * R.F[c * nu + j];
+    // Cholesky F = L L' by warp 0 (right-looking, lanes over rows / columns); a non-positive pivot means the reduced
+    // Hessian is not positive definite
+#if defined(__CUDA_ARCH__)
+    if (ctx.tid < 32)
+#endif
+    {
+      for (int j = 0; j < nu; ++j) {
+        double d = R.F[j * nu + j];
+        bool bad = !(d > 1e-14 * fmax(1.0, fabs(R.R[j * nu + j])));
+        if (bad) d = 1.0;
+        const double sd = sqrt(d), inv = 1.0 / sd;
+        OBCA_WARP_SYNC();
+        OBCA_LANES(lane) {
+          if (lane == 0) {
+            R.invd[j] = inv;
+            if (bad) *ok = 0;
+          }
+          for (int r = j + lane; r < nu; r += 32) R.F[r * nu + j] = (r == j) ? sd : R.F[r * nu + j] * inv;
+        }
+        OBCA_WARP_SYNC();
+        OBCA_LANES(lane) {
+          for (int c = j + 1 + lane; c < nu; c += 32) {
+            const double lcj = R.F[c * nu + j];
+            for (int r = c; r < nu; ++r) R.F[r * nu + c] -= R.F[r * nu + j] * lcj;
+          }
+        }
+        OBCA_WARP_SYNC();
       }
     }
     cta_sync(ctx);
     prof_mark(ctx, 14);
-    // [K | k] = -F^-1 Gm : one thread per column
+    // [K | k] = -F^-1 Gm : one thread per column, in place in shared memory
     for (int col = ctx.tid; col < nX + 1; col += ctx.nt) {
-      double tmp[NUMAX];
       for (int r = 0; r < nu; ++r) {
         double v = R.Gm[r * (nX + 1) + col];
-        for (int m = 0; m < r; ++m) v -= R.F[r * nu + m] * tmp[m];
-        tmp[r] = v / R.F[r * nu + r];
+        for (int m = 0; m < r; ++m) v -= R.F[r * nu + m] * R.K[m * (nX + 1) + col];
+        R.K[r * (nX + 1) + col] = v * R.invd[r];
       }
       for (int r = nu - 1; r >= 0; --r) {
-        double v = tmp[r];
-        for (int m = r + 1; m < nu; ++m) v -= R.F[m * nu + r] * tmp[m];
-        tmp[r] = v / R.F[r * nu + r];
+        double v = R.K[r * (nX + 1) + col];
+        for (int m = r + 1; m < nu; ++m) v -= R.F[m * nu + r] * R.K[m * (nX + 1) + col];
+        R.K[r * (nX + 1) + col] = v * R.invd[r];
       }
-      for (int r = 0; r < nu; ++r) R.K[r * (nX + 1) + col] = -tmp[r];
+      for (int r = 0; r < nu; ++r) R.K[r * (nX + 1) + col] = -R.K[r * (nX + 1) + col];
     }
     cta_sync(ctx);
     prof_mark(ctx, 15);
