@@ -403,16 +403,29 @@ OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
 
 constexpr int NSW = 2720;  // shared-memory doubles per warp of the null-space phase
 
-// apply Q or Q' to the strided vector v[q * stride], q < 35 (reflectors in the shared-memory QR matrix)
+// apply Q or Q' to the strided vector v[q * stride], q < 35 (reflectors in the shared-memory QR matrix).
+// Fixed trip counts + four accumulators: the loads of one reflector are independent and the FP64 chain is short, so a
+// single warp keeps its pipes busy (this phase is latency bound otherwise: 8 warps per SM).
 OBCA_HD void apply_q_strided(const double* Mq, const double* tau, const double* piv, int rk, double* v, int stride, bool transpose) {
   for (int jj = 0; jj < rk; ++jj) {
-    int i = transpose ? jj : rk - 1 - jj;
-    int col = (int)piv[i];
-    double s = v[i * stride];
-    for (int r = i + 1; r < NW; ++r) s += Mq[r * NC + col] * v[r * stride];
-    s *= tau[i];
+    const int i = transpose ? jj : rk - 1 - jj;
+    const double* u = Mq + (int)piv[i];
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+    for (int r = 0; r < 32; r += 4) {
+      s0 += (r > i ? u[r * NC] : 0.0) * v[r * stride];
+      s1 += (r + 1 > i ? u[(r + 1) * NC] : 0.0) * v[(r + 1) * stride];
+      s2 += (r + 2 > i ? u[(r + 2) * NC] : 0.0) * v[(r + 2) * stride];
+      s3 += (r + 3 > i ? u[(r + 3) * NC] : 0.0) * v[(r + 3) * stride];
+    }
+    s0 += (32 > i ? u[32 * NC] : 0.0) * v[32 * stride];
+    s1 += (33 > i ? u[33 * NC] : 0.0) * v[33 * stride];
+    s2 += (34 > i ? u[34 * NC] : 0.0) * v[34 * stride];
+    const double s = ((s0 + s1) + (s2 + s3) + v[i * stride]) * tau[i];
     v[i * stride] -= s;
-    for (int r = i + 1; r < NW; ++r) v[r * stride] -= s * Mq[r * NC + col];
+#pragma unroll
+    for (int r = 0; r < NW; ++r)
+      if (r > i) v[r * stride] -= s * u[r * NC];
   }
 }
 
@@ -583,11 +596,22 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     OBCA_WARP_SYNC();
     OBCA_LANES(lane) {
       for (int cc = j + 1 + lane; cc < nr; cc += 32) {
-        double sacc = Mq[rk * NC + cc];
-        for (int q = rk + 1; q < NW; ++q) sacc += Mq[q * NC + j] * Mq[q * NC + cc];
-        sacc *= t;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          a0 += (q > rk ? Mq[q * NC + j] : 0.0) * Mq[q * NC + cc];
+          a1 += (q + 1 > rk ? Mq[(q + 1) * NC + j] : 0.0) * Mq[(q + 1) * NC + cc];
+          a2 += (q + 2 > rk ? Mq[(q + 2) * NC + j] : 0.0) * Mq[(q + 2) * NC + cc];
+          a3 += (q + 3 > rk ? Mq[(q + 3) * NC + j] : 0.0) * Mq[(q + 3) * NC + cc];
+        }
+        a0 += (32 > rk ? Mq[32 * NC + j] : 0.0) * Mq[32 * NC + cc];
+        a1 += (33 > rk ? Mq[33 * NC + j] : 0.0) * Mq[33 * NC + cc];
+        a2 += (34 > rk ? Mq[34 * NC + j] : 0.0) * Mq[34 * NC + cc];
+        const double sacc = ((a0 + a1) + (a2 + a3) + Mq[rk * NC + cc]) * t;
         Mq[rk * NC + cc] -= sacc;
-        for (int q = rk + 1; q < NW; ++q) Mq[q * NC + cc] -= sacc * Mq[q * NC + j];
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+          if (q > rk) Mq[q * NC + cc] -= sacc * Mq[q * NC + j];
       }
     }
     OBCA_WARP_SYNC();
