@@ -73,43 +73,63 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def cpu_sample(args_tuple):
-    """Bounded CPU sample: `iters` interior-point iterations of the oracle port on one joint instance."""
-    prob, guess, iters = args_tuple
+_WORKER = {}
+
+
+def _cpu_worker_init(prob, guess_list):
+    """Per-process setup of the oracle port (sympy block generation + sparse NLP assembly, untimed)."""
     os.environ["OMP_NUM_THREADS"] = "1"
     from oracle import ipm
     from oracle.nlp import CollocationNLP
 
-    nlp = CollocationNLP(prob)
-    x0 = nlp.init_slacks(nlp.pack(guess))
+    _WORKER["ipm"] = ipm
+    _WORKER["cases"] = []
+    for b, guess in enumerate(guess_list):
+        nlp = CollocationNLP(prob.instance(b))
+        _WORKER["cases"].append((nlp, nlp.init_slacks(nlp.pack(guess))))
+
+
+def cpu_sample(args_tuple):
+    """Bounded CPU sample: `iters` interior-point iterations of the oracle port on one joint instance."""
+    b, iters = args_tuple
+    ipm = _WORKER["ipm"]
+    nlp, x0 = _WORKER["cases"][b % len(_WORKER["cases"])]
     t0 = time.perf_counter()
     res = ipm.solve(nlp, x0, ipm.IpmOptions(max_iter=iters))
     return (time.perf_counter() - t0) / max(1, res.iters), res.iters
 
 
-def cpu_baseline(plan, median_iters, n_proc, sample_iters=4):
-    """Oracle port on host cores: seconds per IPM iteration on `n_proc` instances in parallel -> solves/sec at the
-    iteration count the GPU needed (the CPU would need a full ~150 s solve per instance otherwise)."""
-    import multiprocessing as mp
+class CpuBaseline:
+    """Oracle port on host cores: seconds per IPM iteration with `n_proc` single-threaded processes running in parallel
+    -> solves/sec at a given iteration count per solve (a full CPU solve of the 4-vehicle problem takes minutes)."""
 
-    jobs = [(plan.problem.instance(b % (plan.problem.batch or 1)), plan.guess.instance(b % (plan.problem.batch or 1)), sample_iters) for b in range(n_proc)]
-    t0 = time.perf_counter()
-    if n_proc == 1:
-        out = [cpu_sample(jobs[0])]
-    else:
-        with mp.get_context("spawn").Pool(n_proc) as pool:
-            out = pool.map(cpu_sample, jobs)
-    wall = time.perf_counter() - t0
-    sec_per_iter = float(np.mean([o[0] for o in out]))
-    value = n_proc / (sec_per_iter * max(1.0, median_iters))
-    return {
-        "value": value,
-        "unit": "solves/s",
-        "cores": n_proc,
-        "kind": "port",
-        "sample": "%d IPM iterations of the oracle port (oracle/ipm.py, SuperLU) on %d joint instance(s), %.3f s/iteration, "
-        "extrapolated to the %d iterations of the median GPU solve; sample wall %.1f s" % (sample_iters, n_proc, sec_per_iter, int(median_iters), wall),
-    }
+    def __init__(self, plan, n_proc, n_cases=1):
+        import multiprocessing as mp
+
+        self.n_proc = n_proc
+        B = plan.problem.batch or 1
+        guesses = [plan.guess.instance(b % B) for b in range(n_cases)]
+        self.pool = mp.get_context("spawn").Pool(n_proc, initializer=_cpu_worker_init, initargs=(plan.problem, guesses))
+        self.pool.map(cpu_sample, [(0, 0)] * n_proc)  # make sure every worker finished its setup
+
+    def sample(self, iters_per_solve, sample_iters=4):
+        t0 = time.perf_counter()
+        out = self.pool.map(cpu_sample, [(b, sample_iters) for b in range(self.n_proc)], chunksize=1)
+        wall = time.perf_counter() - t0
+        sec_per_iter = float(np.mean([o[0] for o in out]))
+        value = self.n_proc / (sec_per_iter * max(1.0, iters_per_solve))
+        return {
+            "value": value,
+            "unit": "solves/s",
+            "cores": self.n_proc,
+            "kind": "port",
+            "sample": "%d IPM iterations of the oracle port (oracle/ipm.py, SuperLU) on %d joint instance(s) in parallel, %.3f s/iteration, "
+            "extrapolated to %d iterations per solve; sample wall %.1f s" % (sample_iters, self.n_proc, sec_per_iter, int(iters_per_solve), wall),
+        }
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def main():
@@ -155,20 +175,18 @@ def main():
         from conflict_rez_b200.control.scenario import build_guess, build_problem
 
         n_proc = max(1, min(os.cpu_count() or 1, 16))
-        offs = random_init_offsets(max(n_proc, 1), 4)
+        offs = random_init_offsets(1, 4)
         prob = build_problem(fn, AGENTS, init_offsets=offs)
         guess = build_guess(prob, fn, AGENTS)
-
-        class _P:
-            problem, guess_ = prob, guess
-
         plan = type("Plan", (), {"problem": prob, "guess": guess})
+        base = CpuBaseline(plan, n_proc)
         vals = []
         t_all = time.perf_counter()
         for s in range(args.warmup + args.steps):
-            cb = cpu_baseline(plan, 60.0, n_proc, sample_iters=3)
+            cb = base.sample(60.0, sample_iters=3)
             if s >= args.warmup:
                 vals.append(cb["value"])
+        base.close()
         value = float(np.mean(vals))
         cb["value"] = value
         line = {
@@ -315,7 +333,9 @@ def main():
         },
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(plan, float(np.median(it_h)), 1, sample_iters=4)
+        base = CpuBaseline(plan, 1)
+        line["cpu_baseline"] = base.sample(float(np.median(it_h)), sample_iters=4)
+        base.close()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -174,9 +174,7 @@ struct SolveArgs {
   double dbg_mu, dbg_dw;
 };
 
-OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, int b, int slot, Shared* sh, double* RW) {
-  const Lay& L = *A.L;
-  const Stat& S = *A.S;
+OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, const Lay& L, const Stat& S, int b, int slot, Shared* sh, double* RW) {
   Scratch W;
   carve_iterate(W, L, A.iter + (size_t)b * A.it_stride);
   carve_work(W, L, A.work + (size_t)slot * A.wk_stride);
@@ -233,11 +231,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) k_solve(SolveArgs A) {
   __shared__ double red[40];
   __shared__ int cur;
   extern __shared__ double arena[];
-  double* RW = A.rw_in_smem ? arena : A.rw + (size_t)blockIdx.x * A.rw_stride;
+  __shared__ Lay sL;
+  __shared__ Stat sS;
+  {
+    const int* srcL = (const int*)A.L;
+    int* dstL = (int*)&sL;
+    for (int q = threadIdx.x; q < (int)(sizeof(Lay) / sizeof(int)); q += blockDim.x) dstL[q] = srcL[q];
+    const double* srcS = (const double*)A.S;
+    double* dstS = (double*)&sS;
+    for (int q = threadIdx.x; q < (int)(sizeof(Stat) / sizeof(double)); q += blockDim.x) dstS[q] = srcS[q];
+  }
+  __syncthreads();
+  double* RW = arena;
   Ctx ctx{(int)threadIdx.x, (int)blockDim.x, red, A.prof ? A.prof + (size_t)blockIdx.x * (NPROF + 1) : nullptr};
   if (ctx.prof && threadIdx.x == 0) ctx.prof[NPROF] = clock64();
   if (A.mode != 0) {
-    run_instance(ctx, A, A.b_only, 0, &sh, RW);
+    run_instance(ctx, A, sL, sS, A.b_only, 0, &sh, RW);
     return;
   }
   for (;;) {
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) k_solve(SolveArgs A) {
     __syncthreads();
     int b = cur;
     if (b >= A.B) break;
-    run_instance(ctx, A, b, blockIdx.x, &sh, RW);
+    run_instance(ctx, A, sL, sS, b, blockIdx.x, &sh, RW);
   }
 }
 __global__ void k_stats(const Result* res, int B, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf, double* compl_inf) {
@@ -416,6 +425,10 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   for (int q = 0; q < L.nx; ++q) nb += (xL[q] > -INFINITY) + (xU[q] < INFINITY);
   h->cnt.m_active = m_active, h->cnt.nb = nb;
   h->it_stride = iterate_doubles(L), h->wk_stride = work_doubles(L), h->rw_stride = riccati_work_doubles(L, NWARPS);
+#ifndef OBCA_HOST_EMU
+  if (h->rw_stride * sizeof(double) > 200 * 1024)
+    return fail("obca_set_static: the shared-memory work arena of this problem shape exceeds 200 KB (too many vehicles for this build)");
+#endif
 #ifdef OBCA_HOST_EMU
   h->slots = 1;
 #else
@@ -502,7 +515,7 @@ static SolveArgs make_args(ObcaHandle* h, int mode, int b) {
   A.res = h->d_res, A.B = h->dims.batch, A.counter = h->d_counter, A.mode = mode, A.b_only = b;
   A.prof = getenv("OBCA_PROFILE") ? h->d_prof : nullptr;
   A.dbg_mu = 0, A.dbg_dw = 0;
-  A.rw_in_smem = h->rw_stride * sizeof(double) <= 200 * 1024;
+  A.rw_in_smem = 1;
   return A;
 }
 
@@ -513,9 +526,9 @@ static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
   double red[40];
   Ctx ctx{0, 1, red, nullptr};
   if (A.mode != 0)
-    run_instance(ctx, A, A.b_only, 0, &sh, A.rw);
+    run_instance(ctx, A, *A.L, *A.S, A.b_only, 0, &sh, A.rw);
   else
-    for (int b = 0; b < A.B; ++b) run_instance(ctx, A, b, 0, &sh, A.rw);
+    for (int b = 0; b < A.B; ++b) run_instance(ctx, A, *A.L, *A.S, b, 0, &sh, A.rw);
 #else
   cudaStream_t s = (cudaStream_t)stream;
   if (A.mode == 0) CUDA_OK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));

@@ -28,6 +28,15 @@
 #define OBCA_HDN inline
 #endif
 
+// address-space hints: the work arena is always dynamic shared memory on the device
+#if defined(__CUDA_ARCH__)
+#define OBCA_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#define OBCA_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#else
+#define OBCA_ASSUME_SHARED(p) ((void)0)
+#define OBCA_ASSUME_GLOBAL(p) ((void)0)
+#endif
+
 namespace obca {
 
 constexpr int NK = 6;    // nodes per interval (K + 1)
@@ -255,6 +264,23 @@ OBCA_HD void carve_work(Scratch& W, const Lay& L, double* p) {
   W.RX = p, p += (size_t)(L.Nmax + 1) * L.nX + (size_t)L.Nmax * L.nU;
   W.SS = p;
 }
+
+// tells the compiler that every scratch pointer is a global-memory pointer (LDG/STG instead of generic LD/ST)
+OBCA_HD void assume_scratch(const Scratch& W) {
+  OBCA_ASSUME_GLOBAL(W.x), OBCA_ASSUME_GLOBAL(W.zL), OBCA_ASSUME_GLOBAL(W.zU), OBCA_ASSUME_GLOBAL(W.dx), OBCA_ASSUME_GLOBAL(W.gl);
+  OBCA_ASSUME_GLOBAL(W.gphi), OBCA_ASSUME_GLOBAL(W.sig), OBCA_ASSUME_GLOBAL(W.xt), OBCA_ASSUME_GLOBAL(W.y), OBCA_ASSUME_GLOBAL(W.dy);
+  OBCA_ASSUME_GLOBAL(W.c), OBCA_ASSUME_GLOBAL(W.ct), OBCA_ASSUME_GLOBAL(W.XO), OBCA_ASSUME_GLOBAL(W.XP), OBCA_ASSUME_GLOBAL(W.PH);
+  OBCA_ASSUME_GLOBAL(W.PG), OBCA_ASSUME_GLOBAL(W.HN), OBCA_ASSUME_GLOBAL(W.GN), OBCA_ASSUME_GLOBAL(W.HD), OBCA_ASSUME_GLOBAL(W.TT);
+  OBCA_ASSUME_GLOBAL(W.QR), OBCA_ASSUME_GLOBAL(W.EM), OBCA_ASSUME_GLOBAL(W.DF), OBCA_ASSUME_GLOBAL(W.MA), OBCA_ASSUME_GLOBAL(W.MAB);
+  OBCA_ASSUME_GLOBAL(W.RK), OBCA_ASSUME_GLOBAL(W.RP), OBCA_ASSUME_GLOBAL(W.RX), OBCA_ASSUME_GLOBAL(W.init_pose);
+}
+
+// Lay / Stat live in shared memory inside k_solve (copied once per CTA)
+#if defined(__CUDA_ARCH__)
+#define OBCA_ASSUME_STATIC(L, S) (__builtin_assume(__isShared(&(L))), __builtin_assume(__isShared(&(S))))
+#else
+#define OBCA_ASSUME_STATIC(L, S) ((void)0)
+#endif
 
 struct Result {
   int status, iters;
@@ -512,6 +538,9 @@ OBCA_HD int tube_set_at(const Lay& L, int a, int n) {
 // ------------------------------------------------------------------------------------------------
 OBCA_HDN void eval_pairs(const Ctx& ctx, const Lay& L, const Stat& S, const double* x, const double* y, double* c,
                          double* gl, double* PG) {
+  OBCA_ASSUME_STATIC(L, S);
+  OBCA_ASSUME_GLOBAL(x), OBCA_ASSUME_GLOBAL(c), OBCA_ASSUME_GLOBAL(PG);
+  if (y) OBCA_ASSUME_GLOBAL(y), OBCA_ASSUME_GLOBAL(gl);
   for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
     int p = it / L.Mv, n = it % L.Mv;
     if (n >= L.Mp[p]) continue;
@@ -556,6 +585,9 @@ OBCA_HDN void eval_pairs(const Ctx& ctx, const Lay& L, const Stat& S, const doub
 // ------------------------------------------------------------------------------------------------
 OBCA_HDN void eval_nodes(const Ctx& ctx, const Lay& L, const Stat& S, const double* init_pose, const double* x,
                          const double* y, double* c, double* gl, const double* PG, double* f_out, double* gdt_out) {
+  OBCA_ASSUME_STATIC(L, S);
+  OBCA_ASSUME_GLOBAL(x), OBCA_ASSUME_GLOBAL(c), OBCA_ASSUME_GLOBAL(PG), OBCA_ASSUME_GLOBAL(init_pose);
+  if (y) OBCA_ASSUME_GLOBAL(y), OBCA_ASSUME_GLOBAL(gl);
   const double dt = x[L.oDT];
   const double idt = 1.0 / dt;
   double f_part = 0, gdt_part = 0;

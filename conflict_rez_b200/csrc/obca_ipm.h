@@ -96,6 +96,9 @@ OBCA_HDN double barrier_obj(const Ctx& ctx, const Lay& L, const double* xL, cons
 
 OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
                         const double* xU, const Scratch& W, double* RW, Shared* sh, Result* res) {
+  assume_scratch(W);
+  OBCA_ASSUME_STATIC(L, S);
+  OBCA_ASSUME_GLOBAL(xL), OBCA_ASSUME_GLOBAL(xU);
   // ---- initial point
   init_slacks(ctx, L, S, W);
   push_into_bounds(ctx, L, xL, xU, W.x, o.bound_push, o.bound_frac);

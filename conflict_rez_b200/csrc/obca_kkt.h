@@ -26,6 +26,8 @@ struct KktAux {
 // diagonal Hessian, so they are eliminated analytically into the (yd, yd) and (yn, yn) pivots.
 // ------------------------------------------------------------------------------------------------
 OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok) {
+  assume_scratch(W);
+  OBCA_ASSUME_STATIC(L, S);
   const double *x = W.x, *y = W.y;
   for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
     int p = it / L.Mv, n = it % L.Mv;
@@ -177,6 +179,8 @@ OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const 
 // [LOCAL] node assembly: obstacle / tube elimination, bounds, cost and collocation curvature
 // ------------------------------------------------------------------------------------------------
 OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok, double* hdtdt_out) {
+  assume_scratch(W);
+  OBCA_ASSUME_STATIC(L, S);
   const double *x = W.x, *y = W.y;
   const double dt = x[L.oDT], idt = 1.0 / dt;
   double hdt_part = 0;
@@ -407,6 +411,10 @@ constexpr int NSW = 2720;  // shared-memory doubles per warp of the null-space p
 // Fixed trip counts + four accumulators: the loads of one reflector are independent and the FP64 chain is short, so a
 // single warp keeps its pipes busy (this phase is latency bound otherwise: 8 warps per SM).
 OBCA_HD void apply_q_strided(const double* Mq, const double* tau, const double* piv, int rk, double* v, int stride, bool transpose) {
+  OBCA_ASSUME_SHARED(Mq);
+  OBCA_ASSUME_SHARED(tau);
+  OBCA_ASSUME_SHARED(piv);
+  OBCA_ASSUME_SHARED(v);
   for (int jj = 0; jj < rk; ++jj) {
     const int i = transpose ? jj : rk - 1 - jj;
     const double* u = Mq + (int)piv[i];
@@ -435,6 +443,10 @@ OBCA_HD void apply_q_strided(const double* Mq, const double* tau, const double* 
 // `em` for interval i-1.
 OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int a, int i, const double* ex, double* em,
                               int* ok, double* sw) {
+  OBCA_ASSUME_SHARED(sw);
+  OBCA_ASSUME_STATIC(L, S);
+  assume_scratch(W);
+  OBCA_ASSUME_GLOBAL(ex), OBCA_ASSUME_GLOBAL(em);
   const double* x = W.x;
   const double dt = x[L.oDT], idt = 1.0 / dt;
   const int n0 = i * NK;
@@ -725,6 +737,8 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
 // interval, which is then re-processed in the next pass (buffers are double-buffered by pass parity so that the passes
 // are race-free and deterministic).  Usually two passes: the last interval of a vehicle with an axis-aligned final approach.
 OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok, int* again, double* arena) {
+  assume_scratch(W);
+  OBCA_ASSUME_STATIC(L, S);
   const int nblk = L.V * L.Nmax;
 #if defined(__CUDA_ARCH__)
   const int wid = ctx.tid >> 5, nw = ctx.nt >> 5;
@@ -783,11 +797,13 @@ OBCA_HD double tt_entry(const double* T, int k, int m, int col) {
 // cross-vehicle coupling: one warp per (pair, interval); lanes own the output entries
 //   Mab[ra][cb] = sum_k Ta_k[:,ra]' Hc_k Tb_k[:,cb]  (pose rows of the T maps), plus the two gradient pieces
 OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, double* arena) {
+  assume_scratch(W);
 #if defined(__CUDA_ARCH__)
   const int wid = ctx.tid >> 5, nw = ctx.nt >> 5;
 #else
   const int wid = 0, nw = 1;
 #endif
+  OBCA_ASSUME_SHARED(arena);
   double* sw = arena + (size_t)wid * NSW;
   double* ta = sw;                  // [6][3][NRED] pose rows of Ta
   double* tb = ta + NK * 3 * NRED;  // [6][3][NRED]
@@ -879,6 +895,7 @@ inline size_t riccati_work_doubles(const Lay& L, int nwarps) {
 }
 
 OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
+  OBCA_ASSUME_SHARED(w);
   int nX = L.nX, nU = L.nU;
   R.P = w, w += nX * nX;
   R.p = w, w += nX;
@@ -929,7 +946,8 @@ OBCA_HD int red_target(int a, int rc, int V, const int* uoff, const int* npv, in
   return 0;
 }
 
-OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R, int i, double hdtdt, int nu) {
+OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R, int i, double hdtdt, int nu) {
+  assume_scratch(W);
   const int nX = L.nX, idt = 7 * L.V, V = L.V;
   for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.Q[q] = 0;
   for (int q = ctx.tid; q < nu * nX; q += ctx.nt) R.S[q] = 0;
@@ -1022,6 +1040,7 @@ OBCA_HDN void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch
 }
 
 OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, double* RW, double hdtdt, int* ok) {
+  assume_scratch(W);
   const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V;
   RicWork R;
   ric_carve(R, L, RW);
@@ -1194,6 +1213,7 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
 }
 
 OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, int* ok) {
+  assume_scratch(W);
   const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V;
   const size_t pstride = (size_t)nX * nX + nX, kstride = (size_t)nUmax * nX + nUmax;
   double* X = W.RX;
@@ -1257,6 +1277,7 @@ OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, in
 // [BACKSUB]
 // ------------------------------------------------------------------------------------------------
 OBCA_HDN void expand_primal(const Ctx& ctx, const Lay& L, const Scratch& W) {
+  assume_scratch(W);
   const int nX = L.nX, nU = L.nU, idt = 7 * L.V;
   const double* X = W.RX;
   const double* U = W.RX + (size_t)(L.Nmax + 1) * nX;
@@ -1282,6 +1303,7 @@ OBCA_HDN void expand_primal(const Ctx& ctx, const Lay& L, const Scratch& W) {
 
 // GN <- gn + Hn dz + sum_pairs Hc dpose_other + hd ddt   (stationarity residual before the J'dy terms)
 OBCA_HDN void node_residual(const Ctx& ctx, const Lay& L, const Scratch& W) {
+  assume_scratch(W);
   const double ddt = W.dx[L.oDT];
   for (int it = ctx.tid; it < L.V * L.Mv; it += ctx.nt) {
     int a = it / L.Mv, n = it % L.Mv;
@@ -1325,6 +1347,8 @@ OBCA_HD double* block_row_multiplier(const Lay& L, const Scratch& W, int a, int 
 }
 
 OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W) {
+  assume_scratch(W);
+  OBCA_ASSUME_STATIC(L, S);
   const int nX = L.nX;
   const size_t pstride = (size_t)nX * nX + nX;
   const double dt = W.x[L.oDT], idt = 1.0 / dt;
@@ -1404,6 +1428,8 @@ OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, c
 }
 
 OBCA_HDN void local_backsub(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W) {
+  assume_scratch(W);
+  OBCA_ASSUME_STATIC(L, S);
   for (int it = ctx.tid; it < L.V * L.Mv; it += ctx.nt) {
     int a = it / L.Mv, n = it % L.Mv;
     if (n >= L.M[a]) continue;
