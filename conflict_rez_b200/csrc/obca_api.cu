@@ -16,8 +16,10 @@ using namespace obca;
 
 #ifndef OBCA_HOST_EMU
 #include <cuda_runtime.h>
+#ifndef CTA_THREADS
 #define CTA_THREADS 256
-#define NWARPS (CTA_THREADS / 32)
+#endif
+#define NWARPS ((CTA_THREADS / 32) < 8 ? (CTA_THREADS / 32) : 8)  // warps that own a null-space work area
 #else
 #define NWARPS 1
 #endif

@@ -244,7 +244,7 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
 #pragma unroll
         for (int q = 0; q <= r; ++q) Hl[sym(r, q)] = 2.0 * y3p * (A[0] * S.obsA[j][q][0] + A[1] * S.obsA[j][q][1]);
         Hl[sym(r, r)] += W.sig[L.LAM(a, j, r, n)];
-        sm[r] = W.sig[L.MU(a, j, r, n)];
+        sm[r] = 1.0 / W.sig[L.MU(a, j, r, n)];  // inverse
         Jl[0][r] = B.Atb[r];
         Jl[1][r] = p.c * A[0] + p.s * A[1];
         Jl[2][r] = -p.s * A[0] + p.c * A[1];
@@ -276,7 +276,7 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
             acc += Jl[i2][r] * Wl[j2][r];
             double ji = i2 == 0 ? -S.g[r] : (i2 == 1 ? S.G[r][0] : (i2 == 2 ? S.G[r][1] : 0.0));
             double jj = j2 == 0 ? -S.g[r] : (j2 == 1 ? S.G[r][0] : (j2 == 2 ? S.G[r][1] : 0.0));
-            acc += ji * jj / sm[r];
+            acc += ji * jj * sm[r];
           }
           Ss[sym(i2, j2)] = acc;
         }
@@ -299,7 +299,7 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
             acc += Jl[i2][r] * t[r];
             if (k == 3) {
               double ji = i2 == 0 ? -S.g[r] : (i2 == 1 ? S.G[r][0] : (i2 == 2 ? S.G[r][1] : 0.0));
-              acc += ji * bm[r] / sm[r];
+              acc += ji * bm[r] * sm[r];
             }
           }
           ry[i2] = acc;
@@ -311,7 +311,7 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
 #pragma unroll
           for (int i2 = 0; i2 < 4; ++i2) dl -= Wl[i2][r] * ry[i2];
           X[r * 4 + k] = dl;
-          X[(4 + r) * 4 + k] = ((k == 3 ? bm[r] : 0.0) - jm) / sm[r];
+          X[(4 + r) * 4 + k] = ((k == 3 ? bm[r] : 0.0) - jm) * sm[r];
           X[(8 + r) * 4 + k] = ry[r];
         }
       }
@@ -407,9 +407,7 @@ OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
 
 constexpr int NSW = 2720;  // shared-memory doubles per warp of the null-space phase
 
-// apply Q or Q' to the strided vector v[q * stride], q < 35 (reflectors in the shared-memory QR matrix).
-// Fixed trip counts + four accumulators: the loads of one reflector are independent and the FP64 chain is short, so a
-// single warp keeps its pipes busy (this phase is latency bound otherwise: 8 warps per SM).
+// apply Q or Q' to the strided vector v[q * stride], q < 35 (reflectors in the shared-memory QR matrix)
 OBCA_HD void apply_q_strided(const double* Mq, const double* tau, const double* piv, int rk, double* v, int stride, bool transpose) {
   OBCA_ASSUME_SHARED(Mq);
   OBCA_ASSUME_SHARED(tau);
@@ -418,22 +416,16 @@ OBCA_HD void apply_q_strided(const double* Mq, const double* tau, const double* 
   for (int jj = 0; jj < rk; ++jj) {
     const int i = transpose ? jj : rk - 1 - jj;
     const double* u = Mq + (int)piv[i];
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-    for (int r = 0; r < 32; r += 4) {
-      s0 += (r > i ? u[r * NC] : 0.0) * v[r * stride];
-      s1 += (r + 1 > i ? u[(r + 1) * NC] : 0.0) * v[(r + 1) * stride];
-      s2 += (r + 2 > i ? u[(r + 2) * NC] : 0.0) * v[(r + 2) * stride];
-      s3 += (r + 3 > i ? u[(r + 3) * NC] : 0.0) * v[(r + 3) * stride];
+    double s0 = v[i * stride], s1 = 0.0;
+    int r = i + 1;
+    for (; r + 1 < NW; r += 2) {  // two accumulators: halves the dependent FP64 chain
+      s0 += u[r * NC] * v[r * stride];
+      s1 += u[(r + 1) * NC] * v[(r + 1) * stride];
     }
-    s0 += (32 > i ? u[32 * NC] : 0.0) * v[32 * stride];
-    s1 += (33 > i ? u[33 * NC] : 0.0) * v[33 * stride];
-    s2 += (34 > i ? u[34 * NC] : 0.0) * v[34 * stride];
-    const double s = ((s0 + s1) + (s2 + s3) + v[i * stride]) * tau[i];
+    if (r < NW) s0 += u[r * NC] * v[r * stride];
+    const double s = (s0 + s1) * tau[i];
     v[i * stride] -= s;
-#pragma unroll
-    for (int r = 0; r < NW; ++r)
-      if (r > i) v[r * stride] -= s * u[r * NC];
+    for (r = i + 1; r < NW; ++r) v[r * stride] -= s * u[r * NC];
   }
 }
 
@@ -608,22 +600,16 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     OBCA_WARP_SYNC();
     OBCA_LANES(lane) {
       for (int cc = j + 1 + lane; cc < nr; cc += 32) {
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          a0 += (q > rk ? Mq[q * NC + j] : 0.0) * Mq[q * NC + cc];
-          a1 += (q + 1 > rk ? Mq[(q + 1) * NC + j] : 0.0) * Mq[(q + 1) * NC + cc];
-          a2 += (q + 2 > rk ? Mq[(q + 2) * NC + j] : 0.0) * Mq[(q + 2) * NC + cc];
-          a3 += (q + 3 > rk ? Mq[(q + 3) * NC + j] : 0.0) * Mq[(q + 3) * NC + cc];
+        double a0 = Mq[rk * NC + cc], a1 = 0.0;
+        int q = rk + 1;
+        for (; q + 1 < NW; q += 2) {
+          a0 += Mq[q * NC + j] * Mq[q * NC + cc];
+          a1 += Mq[(q + 1) * NC + j] * Mq[(q + 1) * NC + cc];
         }
-        a0 += (32 > rk ? Mq[32 * NC + j] : 0.0) * Mq[32 * NC + cc];
-        a1 += (33 > rk ? Mq[33 * NC + j] : 0.0) * Mq[33 * NC + cc];
-        a2 += (34 > rk ? Mq[34 * NC + j] : 0.0) * Mq[34 * NC + cc];
-        const double sacc = ((a0 + a1) + (a2 + a3) + Mq[rk * NC + cc]) * t;
+        if (q < NW) a0 += Mq[q * NC + j] * Mq[q * NC + cc];
+        const double sacc = (a0 + a1) * t;
         Mq[rk * NC + cc] -= sacc;
-#pragma unroll
-        for (int q = 0; q < NW; ++q)
-          if (q > rk) Mq[q * NC + cc] -= sacc * Mq[q * NC + j];
+        for (q = rk + 1; q < NW; ++q) Mq[q * NC + cc] -= sacc * Mq[q * NC + j];
       }
     }
     OBCA_WARP_SYNC();
@@ -741,22 +727,23 @@ OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, co
   OBCA_ASSUME_STATIC(L, S);
   const int nblk = L.V * L.Nmax;
 #if defined(__CUDA_ARCH__)
-  const int wid = ctx.tid >> 5, nw = ctx.nt >> 5;
+  const int wid = ctx.tid >> 5, nw = (ctx.nt >> 5) < 8 ? (ctx.nt >> 5) : 8;
 #else
   const int wid = 0, nw = 1;
 #endif
-  double* sw = arena + (size_t)wid * NSW;
+  double* sw = arena + (size_t)(wid < nw ? wid : 0) * NSW;
   for (int it = ctx.tid; it < nblk; it += ctx.nt) {
     W.DF[it] = 1.0, W.DF[nblk + it] = 0.0;
     W.EM[(size_t)it * EXSZ] = 0.0, W.EM[(size_t)(nblk + it) * EXSZ] = 0.0;
   }
+  if (ctx.tid == 0) W.EM[(size_t)2 * nblk * EXSZ] = 0.0;
   cta_sync(ctx);
   for (int pass = 0; pass <= L.Nmax; ++pass) {
     const int cur = pass & 1, nxt = cur ^ 1;
     if (ctx.tid == 0) *again = 0;
     for (int it = ctx.tid; it < nblk; it += ctx.nt) W.DF[nxt * nblk + it] = 0.0;
     cta_sync(ctx);
-    for (int it = wid; it < nblk; it += nw) {
+    for (int it = wid; it < nblk && wid < nw; it += nw) {
       int a = it / L.Nmax, i = it % L.Nmax;
       if (i >= L.N[a]) continue;
       const double* em_old = W.EM + (size_t)(cur * nblk + it) * EXSZ;
@@ -767,8 +754,8 @@ OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, co
         }
         continue;
       }
-      double none = 0.0;
-      const double* ex = (i + 1 < L.N[a]) ? W.EM + (size_t)(cur * nblk + it + 1) * EXSZ : &none;
+      // the last block of a vehicle receives no implied rows: point at the always-empty record behind the two buffers
+      const double* ex = (i + 1 < L.N[a]) ? W.EM + (size_t)(cur * nblk + it + 1) * EXSZ : W.EM + (size_t)2 * nblk * EXSZ;
       nullspace_block(ctx, L, S, W, a, i, ex, em_new, ok, sw);
       OBCA_LANES(lane) {
         if (lane == 0) {
@@ -799,18 +786,18 @@ OBCA_HD double tt_entry(const double* T, int k, int m, int col) {
 OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, double* arena) {
   assume_scratch(W);
 #if defined(__CUDA_ARCH__)
-  const int wid = ctx.tid >> 5, nw = ctx.nt >> 5;
+  const int wid = ctx.tid >> 5, nw = (ctx.nt >> 5) < 8 ? (ctx.nt >> 5) : 8;
 #else
   const int wid = 0, nw = 1;
 #endif
   OBCA_ASSUME_SHARED(arena);
-  double* sw = arena + (size_t)wid * NSW;
+  double* sw = arena + (size_t)(wid < nw ? wid : 0) * NSW;
   double* ta = sw;                  // [6][3][NRED] pose rows of Ta
   double* tb = ta + NK * 3 * NRED;  // [6][3][NRED]
   double* sa = tb + NK * 3 * NRED;  // [6][3] pose entries of s0a
   double* sb = sa + NK * 3;         // [6][3]
   double* hc = sb + NK * 3;         // [6][9] rows pose_a, cols pose_b
-  for (int it = wid; it < L.P * L.Nmax; it += nw) {
+  for (int it = wid; it < L.P * L.Nmax && wid < nw; it += nw) {
     int p = it / L.Nmax, i = it % L.Nmax;
     if (i * NK >= L.Mp[p]) continue;
     int a = L.pa[p], b = L.pb[p];
