@@ -181,14 +181,16 @@ OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, const Lay& L, con
   carve_iterate(W, L, A.iter + (size_t)b * A.it_stride);
   carve_work(W, L, A.work + (size_t)slot * A.wk_stride);
   if (A.mode == 0) {
-    ipm_solve(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, sh, A.res + b);
+    if (L.mode == 0) ipm_solve<0>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, sh, A.res + b);
+    else ipm_solve<1>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, sh, A.res + b);
     return;
   }
   double f, gdt;
   for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.gl[q] = 0, W.dx[q] = 0;
   for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.c[q] = 0, W.dy[q] = 0;
   cta_sync(ctx);
-  eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
+  if (L.mode == 0) eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
+  else mpc_eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
   if (ctx.tid == 0) A.res[b].obj = f;
   if (A.mode == 2) {
     double mu = A.dbg_mu, dw = A.dbg_dw;
@@ -209,7 +211,7 @@ OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, const Lay& L, con
       W.sig[q] = sg, W.gphi[q] = gp;
     }
     cta_sync(ctx);
-    int ok = kkt_solve(ctx, L, S, W, RW, &sh->ok);
+    int ok = L.mode == 0 ? kkt_solve(ctx, L, S, W, RW, &sh->ok) : mpc_kkt_solve(ctx, L, S, W, RW, &sh->ok);
     if (ctx.tid == 0) A.res[b].status = ok;
   }
 }
@@ -300,11 +302,18 @@ static void apply_options(ObcaHandle* h, const ObcaOptions* o) {
 int obca_create(const ObcaDims* dims, const ObcaOptions* opts, int device, ObcaHandle** out) {
   if (!dims || !out) return fail("obca_create: null argument");
   if (dims->K != 5) return fail("obca_create: only K = 5 is supported");
-  if (dims->V < 1 || dims->V > OBCA_MAX_V) return fail("obca_create: V out of range");
   if (dims->O < 0 || dims->O > OBCA_MAX_O) return fail("obca_create: O out of range");
-  if (dims->batch < 1 || dims->n_per_set < 1) return fail("obca_create: bad batch / n_per_set");
-  for (int a = 0; a < dims->V; ++a)
-    if (dims->n_sets[a] < 2 || dims->n_sets[a] > OBCA_MAX_SETS) return fail("obca_create: n_sets out of range");
+  if (dims->batch < 1) return fail("obca_create: bad batch");
+  if (dims->mode == OBCA_MODE_MPC) {
+    if (dims->horizon < 2 || dims->horizon > 4096) return fail("obca_create: MPC horizon out of range");
+    if (dims->n_others < 0 || dims->n_others > MAXP) return fail("obca_create: n_others out of range");
+  } else if (dims->mode == OBCA_MODE_COLLOCATION) {
+    if (dims->V < 1 || dims->V > OBCA_MAX_V) return fail("obca_create: V out of range");
+    if (dims->n_per_set < 1) return fail("obca_create: bad n_per_set");
+    for (int a = 0; a < dims->V; ++a)
+      if (dims->n_sets[a] < 2 || dims->n_sets[a] > OBCA_MAX_SETS) return fail("obca_create: n_sets out of range");
+  } else
+    return fail("obca_create: unknown mode");
 #ifndef OBCA_HOST_EMU
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("obca_create: no CUDA device (this library has no CPU fallback)");
@@ -376,7 +385,9 @@ static void collocation_matrices(double cA[NK][NK], double cB[NK]) {
 int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   if (!h || !st) return fail("obca_set_static: null argument");
   free_device(h);
-  lay_build(h->L, h->dims, st->final_heading);
+  const bool mpc = h->dims.mode == OBCA_MODE_MPC;
+  if (mpc) lay_build_mpc(h->L, h->dims.horizon, h->dims.O, h->dims.n_others);
+  else lay_build(h->L, h->dims, st->final_heading);
   Lay& L = h->L;
   Stat& S = h->S;
   memset((void*)&S, 0, sizeof(S));
@@ -386,13 +397,13 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
       S.obsb[j][r] = st->obs_b[j * 4 + r];
     }
   for (int r = 0; r < 4; ++r) S.G[r][0] = st->body_G[2 * r], S.G[r][1] = st->body_G[2 * r + 1], S.g[r] = st->body_g[r];
-  S.wb = st->wb, S.dmin = h->dmin, S.rho = h->rho;
+  S.wb = st->wb, S.dmin = h->dmin, S.rho = h->rho, S.dt_mpc = st->mpc_dt;
   for (int q = 0; q < 4; ++q) S.region[q] = st->region[q];
   for (int q = 0; q < 8; ++q) S.limits[q] = st->limits[q];
-  for (int a = 0; a < L.V; ++a) S.heading[a] = st->final_heading[a];
+  for (int a = 0; a < L.V; ++a) S.heading[a] = mpc ? 0.0 : st->final_heading[a];
   collocation_matrices(S.cA, S.cB);
   std::vector<double> tube((size_t)L.V * L.Smax * 2 * 4 * 3);
-  for (int a = 0; a < L.V; ++a)
+  for (int a = 0; a < L.V && !mpc; ++a)
     for (int q = 0; q < L.Smax; ++q)
       for (int body = 0; body < 2; ++body)
         for (int r = 0; r < 4; ++r) {
@@ -415,7 +426,8 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
     }
     for (int q = 0; q < L.S[a] - 1; ++q)
       for (int r = 0; r < 8; ++r) xL[L.TS(a, q, r)] = 0;
-    m_active += 7 + 5 * L.M[a] + 7 * (L.N[a] - 1) + 4 + L.heading[a] + 4 * L.O * L.M[a] + 8 * (L.S[a] - 1);
+    if (mpc) m_active += 5 + 5 * (L.M[a] - 1) + 4 * L.O * L.M[a];
+    else m_active += 7 + 5 * L.M[a] + 7 * (L.N[a] - 1) + 4 + L.heading[a] + 4 * L.O * L.M[a] + 8 * (L.S[a] - 1);
   }
   for (int p = 0; p < L.P; ++p) {
     for (int n = 0; n < L.Mp[p]; ++n) {
@@ -426,7 +438,8 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   }
   for (int q = 0; q < L.nx; ++q) nb += (xL[q] > -INFINITY) + (xU[q] < INFINITY);
   h->cnt.m_active = m_active, h->cnt.nb = nb;
-  h->it_stride = iterate_doubles(L), h->wk_stride = work_doubles(L), h->rw_stride = riccati_work_doubles(L, NWARPS);
+  h->it_stride = iterate_doubles(L), h->wk_stride = work_doubles(L);
+  h->rw_stride = mpc ? mpc_work_doubles(L) : riccati_work_doubles(L, NWARPS);
 #ifndef OBCA_HOST_EMU
   if (h->rw_stride * sizeof(double) > 200 * 1024)
     return fail("obca_set_static: the shared-memory work arena of this problem shape exceeds 200 KB (too many vehicles for this build)");
@@ -460,6 +473,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
 
 int obca_set_init_pose(ObcaHandle* h, const double* pose, void* stream) {
   if (!h || !h->have_static) return fail("obca_set_init_pose: call obca_set_static first");
+  if (h->L.mode != 0) return fail("obca_set_init_pose: collocation mode only (use obca_set_mpc_params)");
   int B = h->dims.batch, per = h->L.V * 3;
 #ifdef OBCA_HOST_EMU
   (void)stream;
@@ -470,6 +484,45 @@ int obca_set_init_pose(ObcaHandle* h, const double* pose, void* stream) {
   }
 #else
   k_init_pose<<<(B * per + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->d_L, h->d_iter, h->it_stride, pose, B);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+#ifndef OBCA_HOST_EMU
+__global__ void k_mpc_params(const Lay* L, double* iter, size_t it_stride, const double* cur, const double* ref, const double* others, int B) {
+  const int N = L->Mv, P = L->P, per = 5 + 3 * N * (1 + P);
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (size_t)B * per) return;
+  int b = (int)(g / per), e = (int)(g % per);
+  Scratch W;
+  carve_iterate(W, *L, iter + (size_t)b * it_stride);
+  double v;
+  if (e < 5) v = cur[(size_t)b * 5 + e];
+  else if (e < 5 + 3 * N) v = ref[(size_t)b * 3 * N + (e - 5)];
+  else v = others[(size_t)b * 3 * N * P + (e - 5 - 3 * N)];
+  W.init_pose[e] = v;
+}
+#endif
+
+int obca_set_mpc_params(ObcaHandle* h, const double* cur, const double* ref, const double* others, void* stream) {
+  if (!h || !h->have_static) return fail("obca_set_mpc_params: call obca_set_static first");
+  if (h->L.mode != 1) return fail("obca_set_mpc_params: the handle was not created in MPC mode");
+  if (!cur || !ref || (h->L.P > 0 && !others)) return fail("obca_set_mpc_params: null argument");
+  const int B = h->dims.batch, N = h->L.Mv, P = h->L.P, per = 5 + 3 * N * (1 + P);
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (int b = 0; b < B; ++b) {
+    Scratch W;
+    carve_iterate(W, h->L, h->d_iter + (size_t)b * h->it_stride);
+    for (int e = 0; e < per; ++e)
+      W.init_pose[e] = e < 5 ? cur[(size_t)b * 5 + e] : (e < 5 + 3 * N ? ref[(size_t)b * 3 * N + (e - 5)] : others[(size_t)b * 3 * N * P + (e - 5 - 3 * N)]);
+  }
+#else
+  (void)per;
+  size_t tot = (size_t)B * per;
+  k_mpc_params<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d_L, h->d_iter, h->it_stride, cur, ref, others, B);
   h->launches++;
   CUDA_OK(cudaGetLastError());
 #endif

@@ -67,6 +67,7 @@ constexpr double DELTA_C_LOCAL = 1e-8;
 // [LAYOUT]
 // ------------------------------------------------------------------------------------------------
 struct Lay {
+  int mode;  // 0 = collocation OBCA (single / joint), 1 = MPC (obca_mpc.h)
   int V, O, P, Mv, Nmax, Smax, npset;
   int N[MAXV], M[MAXV], S[MAXV], heading[MAXV];
   int pa[MAXP], pb[MAXP], Mp[MAXP];
@@ -98,7 +99,10 @@ struct Lay {
   OBCA_HD int YPAIR(int p, int r, int n) const { return oYPAIR + (p * 6 + r) * Mv + n; }
 };
 
+inline void lay_offsets(Lay& L);
+
 inline void lay_build(Lay& L, const ObcaDims& d, const double* final_heading) {
+  L.mode = 0;
   L.V = d.V;
   L.O = d.O;
   L.npset = d.n_per_set;
@@ -122,6 +126,12 @@ inline void lay_build(Lay& L, const ObcaDims& d, const double* final_heading) {
       L.Mp[L.P] = L.M[a] < L.M[b] ? L.M[a] : L.M[b];
       ++L.P;
     }
+  lay_offsets(L);
+  L.nX = 7 * L.V + 1;
+  L.nU = NP * L.V;
+}
+
+inline void lay_offsets(Lay& L) {
   int o = 0;
   L.oZ = o, o += L.V * NZ * L.Mv;
   L.oLAM = o, o += L.V * L.O * 4 * L.Mv;
@@ -146,15 +156,27 @@ inline void lay_build(Lay& L, const ObcaDims& d, const double* final_heading) {
   L.oYTUBE = o, o += L.V * (L.Smax - 1) * 8;
   L.oYPAIR = o, o += L.P * 6 * L.Mv;
   L.ny = o;
-  L.nX = 7 * L.V + 1;
-  L.nU = NP * L.V;
 }
+
+// MPC problem: one vehicle, N nodes, P other vehicles (parameters); YCOL rows are the dynamics rows
+inline void lay_build_mpc(Lay& L, int horizon, int n_obstacles, int n_others) {
+  L.mode = 1;
+  L.V = 1, L.O = n_obstacles, L.npset = 1;
+  L.Mv = horizon, L.Nmax = 1, L.Smax = 1;
+  L.S[0] = 1, L.N[0] = 1, L.M[0] = horizon, L.heading[0] = 0;
+  L.P = n_others;
+  for (int p = 0; p < n_others; ++p) L.pa[p] = 0, L.pb[p] = 0, L.Mp[p] = horizon;
+  lay_offsets(L);
+  L.nX = 5, L.nU = 2;
+}
+
 
 // batch-invariant problem data
 struct Stat {
   double obsA[OBCA_MAX_O][4][2], obsb[OBCA_MAX_O][4];
   double G[4][2], g[4];
   double wb, dmin, rho;
+  double dt_mpc;  // fixed sample time of the MPC problem (vehicle_follower.py:146)
   double region[4], limits[8];
   double heading[MAXV];
   double cA[NK][NK], cB[NK];  // collocation matrices: cA[j][k] = L_j'(tau_k), cB[k] quadrature weights
@@ -206,7 +228,10 @@ struct Scratch {
 };
 
 // per-instance iterate (kept for every instance of the batch): x, zL, zU (x-layout), y (y-layout), init pose
-inline size_t iterate_doubles(const Lay& L) { return 3 * (size_t)L.nx + (size_t)L.ny + (size_t)L.V * 3 + 8; }
+inline size_t iterate_doubles(const Lay& L) {
+  size_t par = L.mode == 1 ? 5 + (size_t)3 * L.Mv * (1 + L.P) : (size_t)L.V * 3;  // init poses, or MPC parameters
+  return 3 * (size_t)L.nx + (size_t)L.ny + par + 8;
+}
 
 // per-slot work area (one per resident CTA)
 inline size_t work_doubles(const Lay& L) {
@@ -735,4 +760,5 @@ OBCA_HDN void eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Scratc
 }  // namespace obca
 
 #include "obca_kkt.h"
+#include "obca_mpc.h"
 #include "obca_ipm.h"

@@ -18,15 +18,29 @@ struct Counts {
 
 OBCA_HD bool finite_d(double v) { return v - v == 0.0; }
 
+// model dispatch: MODE 0 = collocation OBCA (obca_core.h / obca_kkt.h), MODE 1 = MPC (obca_mpc.h)
+template <int MODE>
+OBCA_HD void model_eval(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, const double* x, const double* y, double* c, double* gl,
+                        double* f, double* gdt) {
+  if (MODE == 0) eval_all(ctx, L, S, W, x, y, c, gl, f, gdt);
+  else mpc_eval_all(ctx, L, S, W, x, y, c, gl, f, gdt);
+}
+template <int MODE>
+OBCA_HD int model_kkt(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double* RW, int* ok) {
+  if (MODE == 0) return kkt_solve(ctx, L, S, W, RW, ok);
+  return mpc_kkt_solve(ctx, L, S, W, RW, ok);
+}
+
 // slack <- value of its inequality body, evaluated with slack and elastic variable at zero; on the elastic rows the
 // negative part of the body goes to the elastic variable, so that the row starts feasible (oracle/nlp.py:init_slacks)
+template <int MODE>
 OBCA_HDN void init_slacks(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W) {
   for (int it = ctx.tid; it < L.V * L.O * L.Mv; it += ctx.nt) W.x[L.oSD + it] = 0, W.x[L.oEL + it] = 0;
   for (int it = ctx.tid; it < L.V * (L.Smax - 1) * 8; it += ctx.nt) W.x[L.oTS + it] = 0;
   for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) W.x[L.oPSD + it] = 0, W.x[L.oPSN + it] = 0, W.x[L.oPEL + it] = 0;
   cta_sync(ctx);
   double f, gdt;
-  eval_all(ctx, L, S, W, W.x, nullptr, W.c, nullptr, &f, &gdt);
+  model_eval<MODE>(ctx, L, S, W, W.x, nullptr, W.c, nullptr, &f, &gdt);
   for (int it = ctx.tid; it < L.V * L.O * L.Mv; it += ctx.nt) {
     int n = it % L.Mv, aj = it / L.Mv, a = aj / L.O, j = aj % L.O;
     if (n < L.M[a]) {
@@ -94,13 +108,14 @@ OBCA_HDN double barrier_obj(const Ctx& ctx, const Lay& L, const double* xL, cons
   return f + mu * tot;
 }
 
+template <int MODE>
 OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
                         const double* xU, const Scratch& W, double* RW, Shared* sh, Result* res) {
   assume_scratch(W);
   OBCA_ASSUME_STATIC(L, S);
   OBCA_ASSUME_GLOBAL(xL), OBCA_ASSUME_GLOBAL(xU);
   // ---- initial point
-  init_slacks(ctx, L, S, W);
+  init_slacks<MODE>(ctx, L, S, W);
   push_into_bounds(ctx, L, xL, xU, W.x, o.bound_push, o.bound_frac);
   for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
     W.zL[q] = xL[q] > -INFINITY ? 1.0 : 0.0;
@@ -112,7 +127,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
   cta_sync(ctx);
   double mu = o.mu_init;
   double f, gdt;
-  eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
+  model_eval<MODE>(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
   double th0 = 0;
   for (int q = ctx.tid; q < L.ny; q += ctx.nt) th0 += fabs(W.c[q]);
   th0 = cta_sum(ctx, th0);
@@ -254,7 +269,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
         }
       }
       cta_sync(ctx);
-      if (kkt_solve(ctx, L, S, W, RW, &sh->ok)) {
+      if (model_kkt<MODE>(ctx, L, S, W, RW, &sh->ok)) {
         have = true;
         break;
       }
@@ -347,7 +362,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
         for (int q = ctx.tid; q < L.nx; q += ctx.nt) wxt[q] = rx[q] + alpha * rdx[q];
       }
       cta_sync(ctx);
-      eval_all(ctx, L, S, W, W.xt, nullptr, W.ct, nullptr, &ft, &gdt_t);
+      model_eval<MODE>(ctx, L, S, W, W.xt, nullptr, W.ct, nullptr, &ft, &gdt_t);
       double tht = 0;
       for (int q = ctx.tid; q < L.ny; q += ctx.nt) tht += fabs(W.ct[q]);
       tht = cta_sum(ctx, tht);
@@ -416,7 +431,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     }
     for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.y[q] += alpha * W.dy[q];
     cta_sync(ctx);
-    eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
+    model_eval<MODE>(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
     ++it;
   }
   cta_sync(ctx);

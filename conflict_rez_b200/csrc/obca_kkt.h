@@ -25,16 +25,9 @@ struct KktAux {
 // The slacks sd, sn and the elastic variable el enter one row each with coefficient -1 / +1 and a
 // diagonal Hessian, so they are eliminated analytically into the (yd, yd) and (yn, yn) pivots.
 // ------------------------------------------------------------------------------------------------
-OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok) {
-  assume_scratch(W);
-  OBCA_ASSUME_STATIC(L, S);
+OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, int p, int n, const Pose& a, const Pose& b, int* ok) {
   const double *x = W.x, *y = W.y;
-  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
-    int p = it / L.Mv, n = it % L.Mv;
-    if (n >= L.Mp[p]) continue;
-    Pose a, b;
-    load_pose(L, x, L.pa[p], n, a);
-    load_pose(L, x, L.pb[p], n, b);
+  {
     PairBlk B;
     load_pair(L, x, p, n, B);
     pair_residual(S, a, b, B);
@@ -175,56 +168,24 @@ OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// [LOCAL] node assembly: obstacle / tube elimination, bounds, cost and collocation curvature
-// ------------------------------------------------------------------------------------------------
-OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok, double* hdtdt_out) {
+OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok) {
   assume_scratch(W);
   OBCA_ASSUME_STATIC(L, S);
+  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
+    int p = it / L.Mv, n = it % L.Mv;
+    if (n >= L.Mp[p]) continue;
+    Pose a, b;
+    load_pose(L, W.x, L.pa[p], n, a);
+    load_pose(L, W.x, L.pb[p], n, b);
+    pair_block_eliminate(L, S, W, p, n, a, b, ok);
+  }
+}
+
+// one (node, obstacle) block: unknown order lam 0-3, mu 4-7 | y1 8, y2 9-10, y3 11 (sd, el folded into the y1 pivot);
+// stores the block solves for the back-substitution and adds the Schur complement to the node Hessian H / gradient g
+OBCA_HD void obs_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, int a, int n, int j, const Pose& p, double* H, double* g, int* ok) {
   const double *x = W.x, *y = W.y;
-  const double dt = x[L.oDT], idt = 1.0 / dt;
-  double hdt_part = 0;
-  for (int it = ctx.tid; it < L.V * L.Mv; it += ctx.nt) {
-    int a = it / L.Mv, n = it % L.Mv;
-    if (n >= L.M[a]) continue;
-    int i = n / NK, k = n % NK, n0 = i * NK;
-    double z[NZ];
-    for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(a, q, n)];
-    Pose p = {z[0], z[1], z[2], cos(z[2]), sin(z[2])};
-    double v = z[3], de = z[4], ua = z[5], uw = z[6];
-    double tde = tan(de), sec2 = 1.0 + tde * tde;
-    double H[28], g[NZ], hd[NZ];
-    for (int q = 0; q < 28; ++q) H[q] = 0;
-    for (int q = 0; q < NZ; ++q) {
-      H[sym(q, q)] = W.sig[L.Z(a, q, n)];
-      g[q] = W.gphi[L.Z(a, q, n)];
-      hd[q] = 0;
-    }
-    double bk = S.cB[k], bdt = bk * dt;
-    H[sym(3, 3)] += bdt * 2.0 * uw * uw;
-    H[sym(6, 6)] += bdt * 2.0 * v * v;
-    H[sym(6, 3)] += bdt * 4.0 * v * uw;
-    H[sym(4, 4)] += bdt * 2.0;
-    H[sym(5, 5)] += bdt * 2.0;
-    hd[3] = bk * 2.0 * v * uw * uw;
-    hd[4] = bk * 2.0 * de;
-    hd[5] = bk * 2.0 * ua;
-    hd[6] = bk * 2.0 * v * v * uw;
-    double yc[5];
-    for (int q = 0; q < 5; ++q) {
-      yc[q] = y[L.YCOL(a, q, n)];
-      double s = 0, pl = 0;
-      for (int kk = 0; kk < NK; ++kk) s += S.cA[k][kk] * y[L.YCOL(a, q, n0 + kk)];
-      for (int j = 0; j < NK; ++j) pl += S.cA[j][k] * x[L.Z(a, q, n0 + j)];
-      hd[q] -= s * idt * idt;
-      hdt_part += yc[q] * 2.0 * pl * idt * idt * idt;
-    }
-    H[sym(2, 2)] += yc[0] * v * p.c + yc[1] * v * p.s;
-    H[sym(3, 2)] += yc[0] * p.s - yc[1] * p.c;
-    H[sym(4, 3)] -= yc[2] * sec2 / S.wb;
-    H[sym(4, 4)] -= yc[2] * 2.0 * v * sec2 * tde / S.wb;
-    // ---- obstacles: unknown order lam 0-3, mu 4-7 | y1 8, y2 9-10, y3 11  (sd, el folded into the y1 pivot)
-    for (int j = 0; j < L.O; ++j) {
+  {
       ObsBlk B;
       for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(a, j, r, n)], B.mu[r] = x[L.MU(a, j, r, n)];
       B.sd = x[L.SD(a, j, n)];
@@ -333,7 +294,89 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
         for (int m = 0; m < 12; ++m) s += C[m * 3 + r] * X[m * 4 + 3];
         g[r] += s;
       }
+  }
+}
+
+OBCA_HD void obs_block_backsub(const Lay& L, const Scratch& W, int a, int n, int j, const double* dp) {
+  const double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 48;
+  double r[12];
+  for (int m = 0; m < 12; ++m) r[m] = xo[m * 4 + 3] - xo[m * 4 + 0] * dp[0] - xo[m * 4 + 1] * dp[1] - xo[m * 4 + 2] * dp[2];
+  for (int q = 0; q < 4; ++q) {
+    W.dx[L.LAM(a, j, q, n)] = r[q];
+    W.dx[L.MU(a, j, q, n)] = r[4 + q];
+    W.dy[L.YOBS(a, j, q, n)] = r[8 + q];
+  }
+  // sd: sig dsd - dy1 = -gphi ; el: sig del + dy1 = -gphi
+  W.dx[L.SD(a, j, n)] = (r[8] - W.gphi[L.SD(a, j, n)]) / W.sig[L.SD(a, j, n)];
+  W.dx[L.EL(a, j, n)] = -(r[8] + W.gphi[L.EL(a, j, n)]) / W.sig[L.EL(a, j, n)];
+}
+
+OBCA_HD void pair_block_backsub(const Lay& L, const Scratch& W, int p, int n, const double* dp) {
+  const double* xp = W.XP + (size_t)(p * L.Mv + n) * 112;
+  double r[16];
+  for (int m = 0; m < 16; ++m) {
+    double s = xp[m * 7 + 6];
+    for (int q = 0; q < 6; ++q) s -= xp[m * 7 + q] * dp[q];
+    r[m] = s;
+  }
+  for (int q = 0; q < 4; ++q) W.dx[L.PL(p, q, n)] = r[q], W.dx[L.PM(p, q, n)] = r[4 + q];
+  for (int q = 0; q < 6; ++q) W.dy[L.YPAIR(p, q, n)] = r[8 + q];
+  W.dx[L.PS(p, 0, n)] = r[14];
+  W.dx[L.PS(p, 1, n)] = r[15];
+  W.dx[L.PSD(p, n)] = (r[8] - W.gphi[L.PSD(p, n)]) / W.sig[L.PSD(p, n)];
+  W.dx[L.PEL(p, n)] = -(r[8] + W.gphi[L.PEL(p, n)]) / W.sig[L.PEL(p, n)];
+  W.dx[L.PSN(p, n)] = (r[13] - W.gphi[L.PSN(p, n)]) / W.sig[L.PSN(p, n)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// [LOCAL] node assembly: obstacle / tube elimination, bounds, cost and collocation curvature
+// ------------------------------------------------------------------------------------------------
+OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok, double* hdtdt_out) {
+  assume_scratch(W);
+  OBCA_ASSUME_STATIC(L, S);
+  const double *x = W.x, *y = W.y;
+  const double dt = x[L.oDT], idt = 1.0 / dt;
+  double hdt_part = 0;
+  for (int it = ctx.tid; it < L.V * L.Mv; it += ctx.nt) {
+    int a = it / L.Mv, n = it % L.Mv;
+    if (n >= L.M[a]) continue;
+    int i = n / NK, k = n % NK, n0 = i * NK;
+    double z[NZ];
+    for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(a, q, n)];
+    Pose p = {z[0], z[1], z[2], cos(z[2]), sin(z[2])};
+    double v = z[3], de = z[4], ua = z[5], uw = z[6];
+    double tde = tan(de), sec2 = 1.0 + tde * tde;
+    double H[28], g[NZ], hd[NZ];
+    for (int q = 0; q < 28; ++q) H[q] = 0;
+    for (int q = 0; q < NZ; ++q) {
+      H[sym(q, q)] = W.sig[L.Z(a, q, n)];
+      g[q] = W.gphi[L.Z(a, q, n)];
+      hd[q] = 0;
     }
+    double bk = S.cB[k], bdt = bk * dt;
+    H[sym(3, 3)] += bdt * 2.0 * uw * uw;
+    H[sym(6, 6)] += bdt * 2.0 * v * v;
+    H[sym(6, 3)] += bdt * 4.0 * v * uw;
+    H[sym(4, 4)] += bdt * 2.0;
+    H[sym(5, 5)] += bdt * 2.0;
+    hd[3] = bk * 2.0 * v * uw * uw;
+    hd[4] = bk * 2.0 * de;
+    hd[5] = bk * 2.0 * ua;
+    hd[6] = bk * 2.0 * v * v * uw;
+    double yc[5];
+    for (int q = 0; q < 5; ++q) {
+      yc[q] = y[L.YCOL(a, q, n)];
+      double s = 0, pl = 0;
+      for (int kk = 0; kk < NK; ++kk) s += S.cA[k][kk] * y[L.YCOL(a, q, n0 + kk)];
+      for (int j = 0; j < NK; ++j) pl += S.cA[j][k] * x[L.Z(a, q, n0 + j)];
+      hd[q] -= s * idt * idt;
+      hdt_part += yc[q] * 2.0 * pl * idt * idt * idt;
+    }
+    H[sym(2, 2)] += yc[0] * v * p.c + yc[1] * v * p.s;
+    H[sym(3, 2)] += yc[0] * p.s - yc[1] * p.c;
+    H[sym(4, 3)] -= yc[2] * sec2 / S.wb;
+    H[sym(4, 4)] -= yc[2] * 2.0 * v * sec2 * tde / S.wb;
+    for (int j = 0; j < L.O; ++j) obs_block_eliminate(L, S, W, a, n, j, p, H, g, ok);
     // ---- tube set (slack and multiplier eliminated analytically)
     int q = tube_set_at(L, a, n);
     if (q >= 1) {
@@ -1421,19 +1464,7 @@ OBCA_HDN void local_backsub(const Ctx& ctx, const Lay& L, const Stat& S, const S
     int a = it / L.Mv, n = it % L.Mv;
     if (n >= L.M[a]) continue;
     double dp[3] = {W.dx[L.Z(a, 0, n)], W.dx[L.Z(a, 1, n)], W.dx[L.Z(a, 2, n)]};
-    for (int j = 0; j < L.O; ++j) {
-      const double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 48;
-      double r[12];
-      for (int m = 0; m < 12; ++m) r[m] = xo[m * 4 + 3] - xo[m * 4 + 0] * dp[0] - xo[m * 4 + 1] * dp[1] - xo[m * 4 + 2] * dp[2];
-      for (int q = 0; q < 4; ++q) {
-        W.dx[L.LAM(a, j, q, n)] = r[q];
-        W.dx[L.MU(a, j, q, n)] = r[4 + q];
-        W.dy[L.YOBS(a, j, q, n)] = r[8 + q];
-      }
-      // sd: sig dsd - dy1 = -gphi ; el: sig del + dy1 = -gphi
-      W.dx[L.SD(a, j, n)] = (r[8] - W.gphi[L.SD(a, j, n)]) / W.sig[L.SD(a, j, n)];
-      W.dx[L.EL(a, j, n)] = -(r[8] + W.gphi[L.EL(a, j, n)]) / W.sig[L.EL(a, j, n)];
-    }
+    for (int j = 0; j < L.O; ++j) obs_block_backsub(L, W, a, n, j, dp);
     int q = tube_set_at(L, a, n);
     if (q >= 1) {
       double psi = W.x[L.Z(a, 2, n)], cs = cos(psi), sn = sin(psi);
@@ -1451,20 +1482,7 @@ OBCA_HDN void local_backsub(const Ctx& ctx, const Lay& L, const Stat& S, const S
     if (n >= L.Mp[p]) continue;
     int a = L.pa[p], b = L.pb[p];
     double dp[6] = {W.dx[L.Z(a, 0, n)], W.dx[L.Z(a, 1, n)], W.dx[L.Z(a, 2, n)], W.dx[L.Z(b, 0, n)], W.dx[L.Z(b, 1, n)], W.dx[L.Z(b, 2, n)]};
-    const double* xp = W.XP + (size_t)(p * L.Mv + n) * 112;
-    double r[16];
-    for (int m = 0; m < 16; ++m) {
-      double s = xp[m * 7 + 6];
-      for (int q = 0; q < 6; ++q) s -= xp[m * 7 + q] * dp[q];
-      r[m] = s;
-    }
-    for (int q = 0; q < 4; ++q) W.dx[L.PL(p, q, n)] = r[q], W.dx[L.PM(p, q, n)] = r[4 + q];
-    for (int q = 0; q < 6; ++q) W.dy[L.YPAIR(p, q, n)] = r[8 + q];
-    W.dx[L.PS(p, 0, n)] = r[14];
-    W.dx[L.PS(p, 1, n)] = r[15];
-    W.dx[L.PSD(p, n)] = (r[8] - W.gphi[L.PSD(p, n)]) / W.sig[L.PSD(p, n)];
-    W.dx[L.PEL(p, n)] = -(r[8] + W.gphi[L.PEL(p, n)]) / W.sig[L.PEL(p, n)];
-    W.dx[L.PSN(p, n)] = (r[13] - W.gphi[L.PSN(p, n)]) / W.sig[L.PSN(p, n)];
+    pair_block_backsub(L, W, p, n, dp);
   }
 }
 

@@ -1,0 +1,448 @@
+// obca_mpc.h -- distributed-MPC NLP of VehicleFollower.setup_controller (confrez/control/vehicle_follower.py:146-368):
+// horizon of N nodes, RK4 x 4 dynamics (confrez/control/dynamic_model.py:30-58), obstacle OBCA triples per node,
+// one pair block per other vehicle whose predicted pose is a parameter, tracking cost.
+//
+// The flat layout is the collocation layout `Lay` with V = 1 vehicle, Mv = N nodes, P = number of others; the YCOL field
+// holds the multipliers of the dynamics rows  z_{n+1} - F(z_n, u_n) = 0  (n < N-1), YINIT the five initial-state rows.
+// Per instance parameters (stored behind the iterate): cur[5], ref[N][3], others[P][N][3].
+//
+//   [EVAL]     residuals, Lagrangian gradient (dynamics Jacobian by first-order forward mode)
+//   [LOCAL]    obstacle / pair blocks: the same eliminations as the collocation problem (obca_kkt.h)
+//   [RICCATI]  classical stage-wise recursion, state 5, control 2; the Lagrangian Hessian of the RK4 map comes from
+//              second-order forward-mode jets
+#pragma once
+
+namespace obca {
+
+// ------------------------------------------------------------------------------------------------
+// forward-mode jets in the 7 inputs (z, u): value, gradient, (optionally) packed Hessian
+// ------------------------------------------------------------------------------------------------
+template <bool HESS>
+struct Jet {
+  double v, g[7], h[HESS ? 28 : 1];
+};
+
+template <bool H>
+OBCA_HD Jet<H> jet_const(double c) {
+  Jet<H> r;
+  r.v = c;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r.g[i] = 0;
+  if (H)
+#pragma unroll
+    for (int i = 0; i < 28; ++i) r.h[i] = 0;
+  return r;
+}
+
+template <bool H>
+OBCA_HD Jet<H> jet_var(double c, int k) {
+  Jet<H> r = jet_const<H>(c);
+  r.g[k] = 1.0;
+  return r;
+}
+
+// r = a + s * b
+template <bool H>
+OBCA_HD Jet<H> jet_axpy(const Jet<H>& a, double s, const Jet<H>& b) {
+  Jet<H> r;
+  r.v = a.v + s * b.v;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r.g[i] = a.g[i] + s * b.g[i];
+  if (H)
+#pragma unroll
+    for (int i = 0; i < 28; ++i) r.h[i] = a.h[i] + s * b.h[i];
+  return r;
+}
+
+template <bool H>
+OBCA_HD Jet<H> jet_mul(const Jet<H>& a, const Jet<H>& b) {
+  Jet<H> r;
+  r.v = a.v * b.v;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r.g[i] = a.v * b.g[i] + b.v * a.g[i];
+  if (H)
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) r.h[sym(i, j)] = a.v * b.h[sym(i, j)] + b.v * a.h[sym(i, j)] + a.g[i] * b.g[j] + a.g[j] * b.g[i];
+  return r;
+}
+
+// r = f(a) given f, f', f'' at a.v
+template <bool H>
+OBCA_HD Jet<H> jet_unary(const Jet<H>& a, double f0, double f1, double f2) {
+  Jet<H> r;
+  r.v = f0;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r.g[i] = f1 * a.g[i];
+  if (H)
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) r.h[sym(i, j)] = f1 * a.h[sym(i, j)] + f2 * a.g[i] * a.g[j];
+  return r;
+}
+
+// kinematic bicycle f(z, u) on jets (dynamic_model.py:5-27); z = (x, y, psi, v, delta), u = (a, w)
+template <bool H>
+OBCA_HD void jet_f(const Jet<H>* z, const Jet<H>* u, double wb, Jet<H>* out) {
+  const double c = cos(z[2].v), s = sin(z[2].v), t = tan(z[4].v), sec2 = 1.0 + t * t;
+  Jet<H> jc = jet_unary<H>(z[2], c, -s, -c), js = jet_unary<H>(z[2], s, c, -s);
+  Jet<H> jt = jet_unary<H>(z[4], t / wb, sec2 / wb, 2.0 * t * sec2 / wb);
+  out[0] = jet_mul<H>(z[3], jc);
+  out[1] = jet_mul<H>(z[3], js);
+  out[2] = jet_mul<H>(z[3], jt);
+  out[3] = u[0];
+  out[4] = u[1];
+}
+
+// RK4 with 4 sub-steps of h = dt / 4 (dynamic_model.py:30-58) on jets
+template <bool H>
+OBCA_HD void jet_rk4(const double* zu, double dt, double wb, Jet<H>* z) {
+  Jet<H> u[2] = {jet_var<H>(zu[5], 5), jet_var<H>(zu[6], 6)};
+#pragma unroll
+  for (int q = 0; q < 5; ++q) z[q] = jet_var<H>(zu[q], q);
+  const double h = dt / 4.0;
+  for (int sub = 0; sub < 4; ++sub) {
+    Jet<H> a1[5], a2[5], a3[5], a4[5], tmp[5];
+    jet_f<H>(z, u, wb, a1);
+    for (int q = 0; q < 5; ++q) tmp[q] = jet_axpy<H>(z[q], h / 2, a1[q]);
+    jet_f<H>(tmp, u, wb, a2);
+    for (int q = 0; q < 5; ++q) tmp[q] = jet_axpy<H>(z[q], h / 2, a2[q]);
+    jet_f<H>(tmp, u, wb, a3);
+    for (int q = 0; q < 5; ++q) tmp[q] = jet_axpy<H>(z[q], h, a3[q]);
+    jet_f<H>(tmp, u, wb, a4);
+    for (int q = 0; q < 5; ++q) {
+      Jet<H> acc = jet_axpy<H>(z[q], h / 6, a1[q]);
+      acc = jet_axpy<H>(acc, h / 3, a2[q]);
+      acc = jet_axpy<H>(acc, h / 3, a3[q]);
+      z[q] = jet_axpy<H>(acc, h / 6, a4[q]);
+    }
+  }
+}
+
+// plain RK4 (values only) for the line-search trial points
+OBCA_HD void rk4_value(const double* zu, double dt, double wb, double* out) {
+  double z[5] = {zu[0], zu[1], zu[2], zu[3], zu[4]};
+  const double ua = zu[5], uw = zu[6], h = dt / 4.0;
+  for (int sub = 0; sub < 4; ++sub) {
+    double k[4][5], zz[5];
+    for (int st = 0; st < 4; ++st) {
+      const double f = st == 0 ? 0.0 : (st == 3 ? h : h / 2);
+      for (int q = 0; q < 5; ++q) zz[q] = st == 0 ? z[q] : z[q] + f * k[st - 1][q];
+      k[st][0] = zz[3] * cos(zz[2]);
+      k[st][1] = zz[3] * sin(zz[2]);
+      k[st][2] = zz[3] * tan(zz[4]) / wb;
+      k[st][3] = ua;
+      k[st][4] = uw;
+    }
+    for (int q = 0; q < 5; ++q) z[q] += h / 6 * (k[0][q] + 2 * k[1][q] + 2 * k[2][q] + k[3][q]);
+  }
+  for (int q = 0; q < 5; ++q) out[q] = z[q];
+}
+
+// per-instance MPC parameters behind the iterate: cur[5], ref[N][3], others[P][N][3]
+struct MpcPar {
+  const double *cur, *ref, *others;
+};
+OBCA_HD MpcPar mpc_par(const Lay& L, const Scratch& W) {
+  MpcPar p;
+  p.cur = W.init_pose;
+  p.ref = p.cur + 5;
+  p.others = p.ref + 3 * L.Mv;
+  return p;
+}
+inline size_t mpc_param_doubles(const Lay& L) { return 5 + (size_t)3 * L.Mv * (1 + L.P); }
+
+OBCA_HD void load_other_pose(const Lay& L, const MpcPar& par, int o, int n, Pose& p) {
+  const double* q = par.others + ((size_t)o * L.Mv + n) * 3;
+  p.x = q[0], p.y = q[1], p.psi = q[2];
+  p.c = cos(p.psi), p.s = sin(p.psi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// [EVAL]
+// ------------------------------------------------------------------------------------------------
+OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, const double* x, const double* y, double* c,
+                           double* gl, double* f_out, double* gdt_out) {
+  OBCA_ASSUME_STATIC(L, S);
+  assume_scratch(W);
+  const MpcPar par = mpc_par(L, W);
+  const int N = L.Mv;
+  double* PG = W.PG;
+  prof_mark(ctx, 11);
+  // pair blocks (other vehicle's pose is a parameter): residuals, gl of the pair variables, own-pose gradient -> PG
+  for (int it = ctx.tid; it < L.P * N; it += ctx.nt) {
+    int o = it / N, n = it % N;
+    Pose a, b;
+    load_pose(L, x, 0, n, a);
+    load_other_pose(L, par, o, n, b);
+    PairBlk B;
+    load_pair(L, x, o, n, B);
+    pair_residual(S, a, b, B);
+    for (int r = 0; r < 6; ++r) c[L.YPAIR(o, r, n)] = B.c[r];
+    if (!y) continue;
+    double yd = y[L.YPAIR(o, 0, n)], ye1[2] = {y[L.YPAIR(o, 1, n)], y[L.YPAIR(o, 2, n)]};
+    double ye2[2] = {y[L.YPAIR(o, 3, n)], y[L.YPAIR(o, 4, n)]}, yn = y[L.YPAIR(o, 5, n)];
+    double Rtea[2] = {a.c * ye1[0] + a.s * ye1[1], -a.s * ye1[0] + a.c * ye1[1]};
+    double Rteb[2] = {b.c * ye2[0] + b.s * ye2[1], -b.s * ye2[0] + b.c * ye2[1]};
+    for (int r = 0; r < 4; ++r) {
+      gl[L.PL(o, r, n)] = -yd * B.ba[r] + S.G[r][0] * Rtea[0] + S.G[r][1] * Rtea[1];
+      gl[L.PM(o, r, n)] = -yd * B.bb[r] + S.G[r][0] * Rteb[0] + S.G[r][1] * Rteb[1];
+    }
+    gl[L.PS(o, 0, n)] = ye1[0] - ye2[0] - 2.0 * yn * B.s[0];
+    gl[L.PS(o, 1, n)] = ye1[1] - ye2[1] - 2.0 * yn * B.s[1];
+    gl[L.PSD(o, n)] = -yd;
+    gl[L.PSN(o, n)] = -yn;
+    gl[L.PEL(o, n)] = S.rho + yd;
+    double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
+    double* g = PG + (size_t)(o * L.Mv + n) * 6;
+    g[0] = -yd * B.Rua[0];
+    g[1] = -yd * B.Rua[1];
+    g[2] = -yd * (a.x * dRua[0] + a.y * dRua[1]) + ye1[0] * dRua[0] + ye1[1] * dRua[1];
+  }
+  cta_sync(ctx);
+  prof_mark(ctx, 0);
+  double f_part = 0;
+  for (int n = ctx.tid; n < N; n += ctx.nt) {
+    double z[NZ];
+    for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
+    Pose p = {z[0], z[1], z[2], cos(z[2]), sin(z[2])};
+    const double* rf = par.ref + 3 * n;
+    double ex = z[0] - rf[0], ey = z[1] - rf[1], ep = z[2] - rf[2];
+    f_part += 100.0 * (ex * ex + ey * ey + ep * ep) + z[5] * z[5] + z[3] * z[3] * z[6] * z[6] + z[4] * z[4];
+    double g[NZ] = {200.0 * ex, 200.0 * ey, 200.0 * ep, 2.0 * z[3] * z[6] * z[6], 2.0 * z[4], 2.0 * z[5], 2.0 * z[3] * z[3] * z[6]};
+    if (n == 0)
+      for (int q = 0; q < 5; ++q) c[L.YINIT(0, q)] = z[q] - par.cur[q];
+    if (n < N - 1) {
+      if (y) {
+        Jet<false> F[5];
+        jet_rk4<false>(z, S.dt_mpc, S.wb, F);
+        for (int r = 0; r < 5; ++r) {
+          c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r].v;
+          double yr = y[L.YCOL(0, r, n)];
+          for (int q = 0; q < NZ; ++q) g[q] -= yr * F[r].g[q];
+        }
+      } else {
+        double F[5];
+        rk4_value(z, S.dt_mpc, S.wb, F);
+        for (int r = 0; r < 5; ++r) c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r];
+      }
+    }
+    if (y) {
+      if (n >= 1)
+        for (int r = 0; r < 5; ++r) g[r] += y[L.YCOL(0, r, n - 1)];
+      if (n == 0)
+        for (int q = 0; q < 5; ++q) g[q] += y[L.YINIT(0, q)];
+    }
+    for (int j = 0; j < L.O; ++j) {
+      ObsBlk B;
+      for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(0, j, r, n)], B.mu[r] = x[L.MU(0, j, r, n)];
+      B.sd = x[L.SD(0, j, n)];
+      B.el = x[L.EL(0, j, n)];
+      f_part += S.rho * B.el;
+      obs_residual(S, j, p, B);
+      for (int r = 0; r < 4; ++r) c[L.YOBS(0, j, r, n)] = B.c[r];
+      if (!y) continue;
+      double y1 = y[L.YOBS(0, j, 0, n)], y2[2] = {y[L.YOBS(0, j, 1, n)], y[L.YOBS(0, j, 2, n)]}, y3 = y[L.YOBS(0, j, 3, n)];
+      double Ry[2] = {p.c * y2[0] - p.s * y2[1], p.s * y2[0] + p.c * y2[1]};
+      for (int r = 0; r < 4; ++r) {
+        const double* A = S.obsA[j][r];
+        gl[L.LAM(0, j, r, n)] = y1 * B.Atb[r] + A[0] * Ry[0] + A[1] * Ry[1] + 2.0 * y3 * (A[0] * B.u[0] + A[1] * B.u[1]);
+        gl[L.MU(0, j, r, n)] = -y1 * S.g[r] + S.G[r][0] * y2[0] + S.G[r][1] * y2[1];
+      }
+      gl[L.SD(0, j, n)] = -y1;
+      gl[L.EL(0, j, n)] = S.rho + y1;
+      g[0] += y1 * B.u[0];
+      g[1] += y1 * B.u[1];
+      g[2] += y2[0] * (-p.s * B.u[0] + p.c * B.u[1]) + y2[1] * (-p.c * B.u[0] - p.s * B.u[1]);
+    }
+    for (int o = 0; o < L.P; ++o) f_part += S.rho * x[L.PEL(o, n)];
+    if (y) {
+      for (int o = 0; o < L.P; ++o) {
+        const double* pg = PG + (size_t)(o * L.Mv + n) * 6;
+        g[0] += pg[0], g[1] += pg[1], g[2] += pg[2];
+      }
+      for (int q = 0; q < NZ; ++q) gl[L.Z(0, q, n)] = g[q];
+    }
+  }
+  *f_out = cta_sum(ctx, f_part);
+  *gdt_out = 0.0;
+  cta_sync(ctx);
+  prof_mark(ctx, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// [LOCAL] + [RICCATI] + [BACKSUB]
+// ------------------------------------------------------------------------------------------------
+OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double* RW, int* ok_shared) {
+  OBCA_ASSUME_STATIC(L, S);
+  assume_scratch(W);
+  OBCA_ASSUME_SHARED(RW);
+  const MpcPar par = mpc_par(L, W);
+  const int N = L.Mv;
+  const double *x = W.x, *y = W.y;
+  if (ctx.tid == 0) *ok_shared = 1;
+  cta_sync(ctx);
+  prof_mark(ctx, 11);
+  // pair blocks: same elimination as the joint problem, the other pose being constant (its Schur block is unused)
+  for (int it = ctx.tid; it < L.P * N; it += ctx.nt) {
+    int o = it / N, n = it % N;
+    Pose a, b;
+    load_pose(L, x, 0, n, a);
+    load_other_pose(L, par, o, n, b);
+    pair_block_eliminate(L, S, W, o, n, a, b, ok_shared);
+  }
+  cta_sync(ctx);
+  prof_mark(ctx, 2);
+  // node Hessian / gradient (7 x 7) and dynamics linearisation; stage data in the arena: per node
+  //   Hn[28], gn[7], A[5][7] (dF/d(z,u)), r[5] (dynamics residual)
+  double* HN = RW;                    // [N][28]
+  double* GN = HN + (size_t)N * 28;   // [N][7]
+  double* AJ = GN + (size_t)N * 7;    // [N][35]
+  for (int n = ctx.tid; n < N; n += ctx.nt) {
+    double z[NZ];
+    for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
+    Pose p = {z[0], z[1], z[2], cos(z[2]), sin(z[2])};
+    double H[28], g[NZ];
+    for (int q = 0; q < 28; ++q) H[q] = 0;
+    for (int q = 0; q < NZ; ++q) H[sym(q, q)] = W.sig[L.Z(0, q, n)], g[q] = W.gphi[L.Z(0, q, n)];
+    H[sym(0, 0)] += 200.0, H[sym(1, 1)] += 200.0, H[sym(2, 2)] += 200.0;
+    H[sym(3, 3)] += 2.0 * z[6] * z[6], H[sym(6, 6)] += 2.0 * z[3] * z[3], H[sym(6, 3)] += 4.0 * z[3] * z[6];
+    H[sym(4, 4)] += 2.0, H[sym(5, 5)] += 2.0;
+    if (n < N - 1) {
+      Jet<true> F[5];
+      jet_rk4<true>(z, S.dt_mpc, S.wb, F);
+      for (int r = 0; r < 5; ++r) {
+        double yr = y[L.YCOL(0, r, n)];
+        for (int q = 0; q < 28; ++q) H[q] -= yr * F[r].h[q];
+        for (int q = 0; q < NZ; ++q) AJ[(size_t)n * 35 + r * 7 + q] = F[r].g[q];
+      }
+    }
+    for (int j = 0; j < L.O; ++j) obs_block_eliminate(L, S, W, 0, n, j, p, H, g, ok_shared);
+    for (int o = 0; o < L.P; ++o) {
+      const double* ph = W.PH + (size_t)(o * L.Mv + n) * 27;
+      for (int r = 0; r < 3; ++r) {
+        for (int m = 0; m <= r; ++m) H[sym(r, m)] += ph[sym(r, m)];
+        g[r] += ph[21 + r];
+      }
+    }
+    for (int q = 0; q < 28; ++q) HN[(size_t)n * 28 + q] = H[q];
+    for (int q = 0; q < NZ; ++q) GN[(size_t)n * 7 + q] = g[q];
+  }
+  cta_sync(ctx);
+  prof_mark(ctx, 3);
+  // Riccati recursion (state 5, control 2), serial over the stages: thread 0
+  double* PP = AJ + (size_t)N * 35;   // [N][25 + 5] cost-to-go
+  double* KK = PP + (size_t)N * 30;   // [N][2*5 + 2] gains
+  double* DZ = KK + (size_t)N * 12;   // [N][7] step
+  if (ctx.tid == 0) {
+    double P[25], pv[5];
+    for (int q = 0; q < 25; ++q) P[q] = 0;
+    for (int q = 0; q < 5; ++q) pv[q] = 0;
+    for (int n = N - 1; n >= 0; --n) {
+      const double* H = HN + (size_t)n * 28;
+      const double* g = GN + (size_t)n * 7;
+      double Q[7][7], qv[7];
+      for (int r = 0; r < 7; ++r) {
+        qv[r] = g[r];
+        for (int m = 0; m < 7; ++m) Q[r][m] = H[sym(r, m)];
+      }
+      if (n < N - 1) {
+        // next state dz' = A w - r ; cost-to-go 1/2 dz' P dz' + pv dz'
+        const double* A = AJ + (size_t)n * 35;
+        double PA[5][7], Pr[5];
+        for (int r = 0; r < 5; ++r) {
+          double cr = 0;
+          for (int m = 0; m < 5; ++m) cr += P[r * 5 + m] * W.c[L.YCOL(0, m, n)];
+          Pr[r] = pv[r] - cr;  // P (-r) + pv
+          for (int q = 0; q < 7; ++q) {
+            double s = 0;
+            for (int m = 0; m < 5; ++m) s += P[r * 5 + m] * A[m * 7 + q];
+            PA[r][q] = s;
+          }
+        }
+        for (int r = 0; r < 7; ++r) {
+          for (int q = 0; q < 7; ++q) {
+            double s = 0;
+            for (int m = 0; m < 5; ++m) s += A[m * 7 + r] * PA[m][q];
+            Q[r][q] += s;
+          }
+          double s = 0;
+          for (int m = 0; m < 5; ++m) s += A[m * 7 + r] * Pr[m];
+          qv[r] += s;
+        }
+      }
+      // eliminate the control (rows/cols 5,6): F = Q_uu must be positive definite
+      double f00 = Q[5][5], f01 = Q[5][6], f11 = Q[6][6], det = f00 * f11 - f01 * f01;
+      if (!(f00 > 0) || !(det > 1e-14 * f00 * f11)) {
+        *ok_shared = 0;
+        f00 = f11 = 1.0, f01 = 0.0, det = 1.0;
+      }
+      double i00 = f11 / det, i01 = -f01 / det, i11 = f00 / det;
+      double* K = KK + (size_t)n * 12;
+      for (int q = 0; q < 5; ++q) {
+        K[q] = -(i00 * Q[5][q] + i01 * Q[6][q]);
+        K[5 + q] = -(i01 * Q[5][q] + i11 * Q[6][q]);
+      }
+      K[10] = -(i00 * qv[5] + i01 * qv[6]);
+      K[11] = -(i01 * qv[5] + i11 * qv[6]);
+      for (int r = 0; r < 5; ++r) {
+        for (int q = 0; q < 5; ++q) P[r * 5 + q] = Q[r][q] + Q[r][5] * K[q] + Q[r][6] * K[5 + q];
+        pv[r] = qv[r] + Q[r][5] * K[10] + Q[r][6] * K[11];
+      }
+      for (int q = 0; q < 25; ++q) PP[(size_t)n * 30 + q] = P[q];
+      for (int q = 0; q < 5; ++q) PP[(size_t)n * 30 + 25 + q] = pv[q];
+    }
+    // forward pass
+    double dz[5];
+    for (int q = 0; q < 5; ++q) dz[q] = -W.c[L.YINIT(0, q)];
+    for (int n = 0; n < N; ++n) {
+      const double* K = KK + (size_t)n * 12;
+      double du0 = K[10], du1 = K[11];
+      for (int q = 0; q < 5; ++q) du0 += K[q] * dz[q], du1 += K[5 + q] * dz[q];
+      double* w = DZ + (size_t)n * 7;
+      for (int q = 0; q < 5; ++q) w[q] = dz[q];
+      w[5] = du0, w[6] = du1;
+      if (n < N - 1) {
+        const double* A = AJ + (size_t)n * 35;
+        double nz[5];
+        for (int r = 0; r < 5; ++r) {
+          double s = -W.c[L.YCOL(0, r, n)];
+          for (int q = 0; q < 7; ++q) s += A[r * 7 + q] * w[q];
+          nz[r] = s;
+        }
+        for (int q = 0; q < 5; ++q) dz[q] = nz[q];
+      }
+    }
+  }
+  cta_sync(ctx);
+  prof_mark(ctx, 6);
+  if (!*ok_shared) return 0;
+  // primal step, multipliers (costates), local blocks
+  for (int n = ctx.tid; n < N; n += ctx.nt) {
+    const double* w = DZ + (size_t)n * 7;
+    for (int q = 0; q < NZ; ++q) W.dx[L.Z(0, q, n)] = w[q];
+    // multiplier of the row that defines z_n: dy = -(P_n dz_n + p_n)
+    const double* P = PP + (size_t)n * 30;
+    for (int r = 0; r < 5; ++r) {
+      double s = P[25 + r];
+      for (int m = 0; m < 5; ++m) s += P[r * 5 + m] * w[m];
+      if (n == 0) W.dy[L.YINIT(0, r)] = -s;
+      else W.dy[L.YCOL(0, r, n - 1)] = -s;
+    }
+    double dp[3] = {w[0], w[1], w[2]};
+    for (int j = 0; j < L.O; ++j) obs_block_backsub(L, W, 0, n, j, dp);
+    for (int o = 0; o < L.P; ++o) {
+      double dp6[6] = {w[0], w[1], w[2], 0.0, 0.0, 0.0};
+      pair_block_backsub(L, W, o, n, dp6);
+    }
+  }
+  cta_sync(ctx);
+  prof_mark(ctx, 10);
+  return 1;
+}
+
+inline size_t mpc_work_doubles(const Lay& L) { return (size_t)L.Mv * (28 + 7 + 35 + 30 + 12 + 7) + 16; }
+
+}  // namespace obca

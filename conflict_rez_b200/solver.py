@@ -38,6 +38,9 @@ class ObcaDims(ctypes.Structure):
         ("K", ctypes.c_int32),
         ("n_per_set", ctypes.c_int32),
         ("n_sets", ctypes.c_int32 * OBCA_MAX_V),
+        ("mode", ctypes.c_int32),
+        ("horizon", ctypes.c_int32),
+        ("n_others", ctypes.c_int32),
     ]
 
 
@@ -61,7 +64,8 @@ _dp = ctypes.POINTER(ctypes.c_double)
 
 class ObcaStatic(ctypes.Structure):
     _fields_ = [(n, _dp) for n in ("obs_A", "obs_b", "tube_A", "tube_b", "body_G", "body_g", "region", "limits", "final_heading")] + [
-        ("wb", ctypes.c_double)
+        ("wb", ctypes.c_double),
+        ("mpc_dt", ctypes.c_double),
     ]
 
 
@@ -75,6 +79,7 @@ EXPORTS = [
     "obca_set_options",
     "obca_set_init_pose",
     "obca_set_initial",
+    "obca_set_mpc_params",
     "obca_solve",
     "obca_get_solution",
     "obca_get_stats",
@@ -111,6 +116,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.obca_set_options.argtypes = [vp, ctypes.POINTER(ObcaOptions)]
     lib.obca_set_init_pose.argtypes = [vp, vp, vp]
     lib.obca_set_initial.argtypes = [vp] + [vp] * 7 + [vp]
+    lib.obca_set_mpc_params.argtypes = [vp, vp, vp, vp, vp]
     lib.obca_solve.argtypes = [vp, vp]
     lib.obca_get_solution.argtypes = [vp] + [vp] * 7 + [vp]
     lib.obca_get_stats.argtypes = [vp] + [vp] * 6 + [vp]
@@ -352,3 +358,98 @@ class ObcaSolver:
         dx, dy, ok = np.zeros(L["nx"]), np.zeros(L["ny"]), ctypes.c_int32()
         self._check(self.lib.obca_debug_step(self.handle, b, mu, delta_w, _np_ptr(dx), _np_ptr(dy), ctypes.byref(ok)))
         return dx, dy, int(ok.value)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MPC mode: the NLP of VehicleFollower.setup_controller / step (confrez/control/vehicle_follower.py:146-563)
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class MpcProblem:
+    """Static data of the distributed-MPC controller: horizon, sample time, obstacles, body, limits (vehicle_follower.py:146-368)."""
+
+    obs_A: np.ndarray  # (O,4,2)
+    obs_b: np.ndarray  # (O,4)
+    n_others: int
+    N: int = 30
+    dt: float = 0.1
+    body_G: np.ndarray = None
+    body_g: np.ndarray = None
+    wb: float = 2.5
+    region: np.ndarray = None
+    limits: np.ndarray = None
+    dmin: float = 0.05
+    batch: int = 1
+
+    def __post_init__(self):
+        if self.body_G is None:
+            self.body_G = np.array([[1.0, 0], [0, 1], [-1, 0], [0, -1]])
+        if self.body_g is None:
+            self.body_g = np.array([3.3, 0.9, 0.6, 0.9])
+        if self.region is None:
+            self.region = np.array([2.5, 32.5, 7.5, 27.5])
+        if self.limits is None:
+            self.limits = np.array([-2.5, 2.5, -0.85, 0.85, -1.5, 1.5, -1.0, 1.0])
+
+
+class ObcaMpcSolver(ObcaSolver):
+    """One handle per controller shape; ``batch`` instances (e.g. the vehicles of one scene) are solved in one launch."""
+
+    def __init__(self, prob: MpcProblem, options: Optional[SolveOptions] = None, device="cuda:0", lib: Optional[ctypes.CDLL] = None):
+        self.lib = lib if lib is not None else load_library()
+        self.device = torch.device(device)
+        self.is_emulation = b"EMULATION" in self.lib.obca_version()
+        if self.device.type != "cuda" and not self.is_emulation:
+            raise RuntimeError("ObcaMpcSolver needs a CUDA device (no CPU fallback)")
+        if self.device.type == "cuda" and not torch.cuda.is_available():
+            raise RuntimeError("ObcaMpcSolver: CUDA is not available on this machine (no CPU fallback)")
+        self.prob = prob
+        self.opts = options or SolveOptions(max_iter=600)  # vehicle_follower.py:362-364
+        self.B, self.V, self.O, self.P, self.Mmax = prob.batch, 1, prob.obs_A.shape[0], prob.n_others, prob.N
+        dims = ObcaDims(batch=self.B, V=1, O=self.O, K=5, n_per_set=1, mode=1, horizon=prob.N, n_others=prob.n_others)
+        copts = ObcaOptions()
+        self.lib.obca_default_options(ctypes.byref(copts))
+        for name in ("tol", "constr_viol_tol", "dual_inf_tol", "compl_inf_tol", "mu_init", "max_iter", "elastic_weight"):
+            setattr(copts, name, getattr(self.opts, name))
+        copts.dmin = prob.dmin
+        self.handle = ctypes.c_void_p()
+        dev_index = self.device.index or 0 if self.device.type == "cuda" else 0
+        self._check(self.lib.obca_create(ctypes.byref(dims), ctypes.byref(copts), dev_index, ctypes.byref(self.handle)))
+        keep = {n: np.ascontiguousarray(getattr(prob, n), dtype=np.float64) for n in ("obs_A", "obs_b", "body_G", "body_g", "region", "limits")}
+        st = ObcaStatic(wb=float(prob.wb), mpc_dt=float(prob.dt), **{n: _np_ptr(a) for n, a in keep.items()})
+        self._check(self.lib.obca_set_static(self.handle, ctypes.byref(st)))
+
+    def upload_params(self, cur, ref, others):
+        B, N, P = self.B, self.Mmax, self.P
+        d = {"cur": self._to_dev(cur, (B, 5)), "ref": self._to_dev(ref, (B, N, 3))}
+        d["others"] = self._to_dev(others, (B, P, N, 3)) if P else None
+        return d
+
+    def set_params(self, d):
+        self._check(self.lib.obca_set_mpc_params(self.handle, _ptr(d["cur"]), _ptr(d["ref"]), _ptr(d.get("others")), self._stream_ptr()))
+
+    def upload(self, guess: CollocationGuess, init_pose=None):
+        B, M, O, P = self.B, self.Mmax, self.O, self.P
+        d = {
+            "z": self._to_dev(guess.z, (B, 1, M, 7)),
+            "lam": self._to_dev(guess.lam, (B, 1, M, O, 4)),
+            "mu": self._to_dev(guess.mu, (B, 1, M, O, 4)),
+            "dt": self._to_dev(np.zeros(B), (B,)),
+        }
+        if P:
+            d["pl"] = self._to_dev(guess.pair_lam, (B, P, M, 4))
+            d["pm"] = self._to_dev(guess.pair_mu, (B, P, M, 4))
+            d["ps"] = self._to_dev(guess.pair_s, (B, P, M, 2))
+        return d
+
+    def set_inputs(self, d):
+        self._check(
+            self.lib.obca_set_initial(self.handle, _ptr(d["z"]), _ptr(d["lam"]), _ptr(d["mu"]), _ptr(d["dt"]), _ptr(d.get("pl")), _ptr(d.get("pm")), _ptr(d.get("ps")), self._stream_ptr())
+        )
+
+    def solve_step(self, cur, ref, others, guess: CollocationGuess) -> BatchResult:
+        """One MPC solve for every instance: parameters + warm start in (host), solution out (host)."""
+        self.set_params(self.upload_params(cur, ref, others))
+        return ObcaSolver.solve(self, guess)
+
+    def solve(self, guess, init_pose=None, want_duals=True):  # parameters must have been set with set_params
+        return ObcaSolver.solve(self, guess, want_duals=want_duals)

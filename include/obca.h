@@ -34,6 +34,8 @@ extern "C" {
 #define OBCA_MAX_V 8      /* vehicles per instance */
 #define OBCA_MAX_O 32     /* obstacles (4 half-planes each) */
 #define OBCA_MAX_SETS 64  /* strategy sets per vehicle */
+#define OBCA_MODE_COLLOCATION 0
+#define OBCA_MODE_MPC 1   /* VehicleFollower.setup_controller NLP (confrez/control/vehicle_follower.py:146-368) */
 
 /* per-instance return status, mirroring IPOPT's ApplicationReturnStatus strings */
 #define OBCA_SOLVE_SUCCEEDED 0
@@ -51,6 +53,9 @@ typedef struct ObcaDims {
   int32_t K;                     /* collocation degree (must be 5) */
   int32_t n_per_set;             /* collocation intervals per strategy move (must be >= 1) */
   int32_t n_sets[OBCA_MAX_V];    /* S_a: strategy sets of vehicle a; N_a = n_per_set * (S_a - 1) */
+  int32_t mode;                  /* OBCA_MODE_COLLOCATION (default 0) or OBCA_MODE_MPC */
+  int32_t horizon;               /* MPC: nodes N (vehicle_follower.py:146, N = 30) */
+  int32_t n_others;              /* MPC: other vehicles whose predictions are parameters */
 } ObcaDims;
 
 typedef struct ObcaOptions {
@@ -73,6 +78,7 @@ typedef struct ObcaStatic {       /* host pointers; copied by obca_set_static */
   const double* limits;          /* v,delta,a,w (min,max) */
   const double* final_heading;   /* (V) NaN = unconstrained */
   double wb;
+  double mpc_dt;                 /* MPC sample time (vehicle_follower.py:146, dt = 0.1); unused in collocation mode */
 } ObcaStatic;
 
 typedef struct ObcaHandle ObcaHandle;
@@ -93,6 +99,11 @@ int obca_set_init_pose(ObcaHandle* h, const double* init_pose_dev, void* stream)
  * pair_lam, pair_mu (B,P,Mmax,4); pair_s (B,P,Mmax,2) -- pair pointers may be NULL when V == 1. */
 int obca_set_initial(ObcaHandle* h, const double* z, const double* lam, const double* mu, const double* dt,
                      const double* pair_lam, const double* pair_mu, const double* pair_s, void* stream);
+
+/* MPC mode, replaces opti.set_value(...) of VehicleFollower.step (vehicle_follower.py:432-456): dev pointers
+ * cur (B,5) current state, ref (B,N,3) reference x,y,psi, others (B,n_others,N,3) neighbours' shifted predictions.
+ * obca_set_initial takes z (B,1,N,7), lam/mu (B,1,N,O,4), dt (B, ignored), pair_* (B,n_others,N,.) in this mode. */
+int obca_set_mpc_params(ObcaHandle* h, const double* cur, const double* ref, const double* others, void* stream);
 
 /* run the batched interior-point solve, asynchronously on `stream`; no host sync inside */
 int obca_solve(ObcaHandle* h, void* stream);
