@@ -132,6 +132,23 @@ class CpuBaseline:
         self.pool.join()
 
 
+def mpc_latency(rl_file, device, steps):
+    """Second half of BASELINE.json's metric: p50 / p99 latency of one distributed-MPC control step (4 vehicles, horizon 30,
+    vehicle_follower.py:main), host parameters in -> first input + predictions on the host, all vehicles in one launch."""
+    from conflict_rez_b200.control.vehicle_follower import MultiDistributedFollower
+    from conflict_rez_b200.pytypes import VehicleState
+
+    heads = {"vehicle_0": 0.0, "vehicle_1": 3 * np.pi / 2, "vehicle_2": np.pi, "vehicle_3": np.pi / 2}
+    mdf = MultiDistributedFollower(rl_file, {a: True for a in AGENTS}, {a: {} for a in AGENTS}, {a: VehicleState() for a in AGENTS}, heads, device=device)
+    mdf.setup_multi_vehicles()
+    mdf.solve(num_iter=steps)
+    t = 1e3 * np.array(mdf.step_time[5:])  # first steps warm the allocator / pinned buffers
+    fails = int(sum(v.N - 1 - v.back_up_steps > 0 for v in mdf.vehicles))
+    return {"p50_step_ms": float(np.percentile(t, 50)), "p99_step_ms": float(np.percentile(t, 99)), "mean_step_ms": float(t.mean()), "steps": int(len(t)),
+            "vehicles": len(AGENTS), "horizon": 30, "vehicles_in_backup_at_end": fails,
+            "note": "closed loop, Jacobi exchange of predictions on the host, one batched k_solve launch per control step (4 NLPs)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -141,6 +158,8 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="instances per GPU")
     ap.add_argument("--tol", type=float, default=1e-2, help="IPOPT tol / constr_viol_tol of the reference (vehicle.py:651-652)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mpc", action="store_true", help="skip the distributed-MPC latency leg (second half of the metric)")
+    ap.add_argument("--mpc-steps", type=int, default=150)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -332,6 +351,8 @@ def main():
             },
         },
     }
+    if world == 1 and not args.no_mpc:
+        line["mpc"] = mpc_latency(fn, device, args.mpc_steps)
     if world == 1 and not args.no_cpu_baseline:
         base = CpuBaseline(plan, 1)
         line["cpu_baseline"] = base.sample(float(np.median(it_h)), sample_iters=4)
