@@ -162,4 +162,5 @@ def test_distributed_mpc_closed_loop(backend, strategy_file):
     ca = body_corners(np.array(a.final_traj.x), np.array(a.final_traj.y), np.array(a.final_traj.psi), None, np.array([3.3, 0.9, 0.6, 0.9]))
     cb = body_corners(np.array(b.final_traj.x), np.array(b.final_traj.y), np.array(b.final_traj.psi), None, np.array([3.3, 0.9, 0.6, 0.9]))
     assert quad_distance(ca, cb).min() >= 0.05 - 1e-2
-    assert mdf.solver.launch_count > 0
+    if dev != "cpu":
+        assert mdf.solver.launch_count > 0  # the CUDA kernels ran (the emulation does not count launches)
