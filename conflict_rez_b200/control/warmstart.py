@@ -141,12 +141,14 @@ def kinematic_guess(path, dt, wb, limits):
     v = dx * np.cos(psi) + dy * np.sin(psi)
     v = np.clip(v, 0.9 * limits[0], 0.9 * limits[1])
     v[0] = v[-1] = 0.0
-    safe_v = np.where(np.abs(v) > 1e-3, v, np.inf)
-    delta = np.clip(np.arctan(wb * dpsi / safe_v), 0.9 * limits[2], 0.9 * limits[3])
-    delta[0] = delta[-1] = 0.0
+    # Steering is left at zero: differentiating the Bezier heading gives a steering guess that saturates around every
+    # cusp and stop move (|v| ~ 0), which starts the interior-point iteration on the steering bounds and made ~5 % of
+    # the randomized instances jam there.  delta = w = 0 starts strictly inside the box (the reference's state_ws NLP
+    # also starts from zero steering, vehicle.py:197-205).
+    delta = np.zeros(T)
+    w = np.zeros(T)
     a = np.clip(np.gradient(v, dt), 0.9 * limits[4], 0.9 * limits[5])
-    w = np.clip(np.gradient(delta, dt), 0.9 * limits[6], 0.9 * limits[7])
-    a[0] = w[0] = a[-1] = w[-1] = 0.0
+    a[0] = a[-1] = 0.0
     return {"t": dt * np.arange(T), "x": x, "y": y, "psi": psi, "v": v, "delta": delta, "a": a, "w": w}
 
 

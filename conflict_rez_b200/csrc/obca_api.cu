@@ -19,7 +19,10 @@ using namespace obca;
 #ifndef CTA_THREADS
 #define CTA_THREADS 256
 #endif
-#define NWARPS ((CTA_THREADS / 32) < 8 ? (CTA_THREADS / 32) : 8)  // warps that own a null-space work area
+#ifndef CTAS_PER_SM
+#define CTAS_PER_SM 1   // 2 was measured slower (128-register cap, 4 null-space warps, L1 squeezed): 68.9 vs 99.6 solves/s
+#endif
+#define NWARPS OBCA_NS_WARPS  // warps that own a null-space work area
 #else
 #define NWARPS 1
 #endif
@@ -230,7 +233,7 @@ __global__ void k_init_pose(const Lay* L, double* iter, size_t it_stride, const 
   carve_iterate(W, *L, iter + (size_t)(g / per) * it_stride);
   W.init_pose[g % per] = pose[g];
 }
-__global__ void __launch_bounds__(CTA_THREADS, 1) k_solve(SolveArgs A) {
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_solve(SolveArgs A) {
   __shared__ Shared sh;
   __shared__ double red[40];
   __shared__ int cur;
@@ -441,7 +444,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   h->it_stride = iterate_doubles(L), h->wk_stride = work_doubles(L);
   h->rw_stride = mpc ? mpc_work_doubles(L) : riccati_work_doubles(L, NWARPS);
 #ifndef OBCA_HOST_EMU
-  if (h->rw_stride * sizeof(double) > 200 * 1024)
+  if (h->rw_stride * sizeof(double) > (size_t)(CTAS_PER_SM == 1 ? 200 : 100) * 1024)
     return fail("obca_set_static: the shared-memory work arena of this problem shape exceeds 200 KB (too many vehicles for this build)");
 #endif
 #ifdef OBCA_HOST_EMU
@@ -449,7 +452,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
 #else
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
-  h->slots = prop.multiProcessorCount < h->dims.batch ? prop.multiProcessorCount : h->dims.batch;
+  h->slots = CTAS_PER_SM * prop.multiProcessorCount < h->dims.batch ? CTAS_PER_SM * prop.multiProcessorCount : h->dims.batch;
 #endif
   int B = h->dims.batch;
   if (dev_alloc((void**)&h->d_L, sizeof(Lay)) || dev_alloc((void**)&h->d_S, sizeof(Stat)) || dev_alloc((void**)&h->d_tube, tube.size() * 8) ||

@@ -37,6 +37,19 @@
 #define OBCA_ASSUME_GLOBAL(p) ((void)0)
 #endif
 
+// warps per CTA that own a shared-memory work area in the null-space / coupling phases, and whether the Riccati phase
+// stages its inputs in shared memory (needs 19 KB more; off when two CTAs share an SM)
+#ifndef OBCA_NS_WARPS
+#if defined(OBCA_HOST_EMU)
+#define OBCA_NS_WARPS 1
+#else
+#define OBCA_NS_WARPS 8
+#endif
+#endif
+#ifndef OBCA_RIC_PREFETCH
+#define OBCA_RIC_PREFETCH 1
+#endif
+
 namespace obca {
 
 constexpr int NK = 6;    // nodes per interval (K + 1)

@@ -326,6 +326,22 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     a_du = cta_min(ctx, a_du);
     rel = cta_max(ctx, rel);
     dphi = cta_sum(ctx, dphi) - cta_sum(ctx, yJdx);
+#ifdef OBCA_HOST_EMU
+    if (getenv("OBCA_TRACE")) {  // which variable limits the primal step
+      int arg = -1, up = 0;
+      double best = 2.0;
+      for (int q = 0; q < L.nx; ++q) {
+        double d = W.dx[q];
+        if (xL[q] > -INFINITY && d < 0 && -tau * (W.x[q] - xL[q]) / d < best) best = -tau * (W.x[q] - xL[q]) / d, arg = q, up = 0;
+        if (xU[q] < INFINITY && d > 0 && tau * (xU[q] - W.x[q]) / d < best) best = tau * (xU[q] - W.x[q]) / d, arg = q, up = 1;
+      }
+      const int offs[] = {L.oZ, L.oLAM, L.oMU, L.oSD, L.oEL, L.oTS, L.oPL, L.oPM, L.oPS, L.oPSD, L.oPSN, L.oPEL, L.oDT, L.nx};
+      const char* nm[] = {"Z", "LAM", "MU", "SD", "EL", "TS", "PL", "PM", "PS", "PSD", "PSN", "PEL", "DT"};
+      for (int k = 0; k < 13 && arg >= 0; ++k)
+        if (arg >= offs[k] && arg < offs[k + 1])
+          printf("       block %s[%d] (n=%d) %s x=%.3e dx=%.3e\n", nm[k], (arg - offs[k]) / L.Mv, (arg - offs[k]) % L.Mv, up ? "upper" : "lower", W.x[arg], W.dx[arg]);
+    }
+#endif
     // ---- filter line search
     double a_min;
     if (dphi < 0) {

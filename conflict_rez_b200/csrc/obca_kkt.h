@@ -770,7 +770,7 @@ OBCA_HDN void interval_nullspace(const Ctx& ctx, const Lay& L, const Stat& S, co
   OBCA_ASSUME_STATIC(L, S);
   const int nblk = L.V * L.Nmax;
 #if defined(__CUDA_ARCH__)
-  const int wid = ctx.tid >> 5, nw = (ctx.nt >> 5) < 8 ? (ctx.nt >> 5) : 8;
+  const int wid = ctx.tid >> 5, nw = (ctx.nt >> 5) < OBCA_NS_WARPS ? (ctx.nt >> 5) : OBCA_NS_WARPS;
 #else
   const int wid = 0, nw = 1;
 #endif
@@ -829,7 +829,7 @@ OBCA_HD double tt_entry(const double* T, int k, int m, int col) {
 OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, double* arena) {
   assume_scratch(W);
 #if defined(__CUDA_ARCH__)
-  const int wid = ctx.tid >> 5, nw = (ctx.nt >> 5) < 8 ? (ctx.nt >> 5) : 8;
+  const int wid = ctx.tid >> 5, nw = (ctx.nt >> 5) < OBCA_NS_WARPS ? (ctx.nt >> 5) : OBCA_NS_WARPS;
 #else
   const int wid = 0, nw = 1;
 #endif
@@ -915,7 +915,7 @@ struct RicWork {
 inline size_t riccati_only_doubles(const Lay& L) {
   size_t nX = L.nX, nU = L.nU;
   return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU +
-         (size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED);
+         (OBCA_RIC_PREFETCH ? (size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) : 0);
 }
 
 // work arena shared by the null-space phase (NSW doubles per warp) and the Riccati phase
@@ -945,8 +945,9 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
   R.db = w, w += L.V * 7;
   R.cb = w, w += L.V * 7;
   R.invd = w, w += nU;
-  R.MAs = w, w += L.V * (NSYM + NRED);
-  R.MABs = w, w += L.P * (NRED * NRED + 2 * NRED);
+  R.MAs = w;
+  R.MABs = w + L.V * (NSYM + NRED);
+  if (OBCA_RIC_PREFETCH) w += L.V * (NSYM + NRED) + L.P * (NRED * NRED + 2 * NRED);
   R.uoff = (int*)w;
   R.npv = R.uoff + (MAXV + 1);
 }
@@ -982,7 +983,8 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
   for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.Q[q] = 0;
   for (int q = ctx.tid; q < nu * nX; q += ctx.nt) R.S[q] = 0;
   for (int q = ctx.tid; q < nu * nu; q += ctx.nt) R.R[q] = 0;
-  // stage data -> shared memory (coalesced, independent loads)
+  // stage data -> shared memory (coalesced, independent loads) when the arena has room for it
+#if OBCA_RIC_PREFETCH
   for (int it = ctx.tid; it < V * (NSYM + NRED); it += ctx.nt) {
     int a = it / (NSYM + NRED);
     R.MAs[it] = i < L.N[a] ? W.MA[(size_t)(a * L.Nmax + i) * (NSYM + NRED) + it % (NSYM + NRED)] : 0.0;
@@ -991,6 +993,12 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
     int p = it / (NRED * NRED + 2 * NRED);
     R.MABs[it] = i * NK < L.Mp[p] ? W.MAB[(size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED) + it % (NRED * NRED + 2 * NRED)] : 0.0;
   }
+#define OBCA_MA(a) (R.MAs + (a) * (NSYM + NRED))
+#define OBCA_MAB(p) (R.MABs + (p) * (NRED * NRED + 2 * NRED))
+#else
+#define OBCA_MA(a) (W.MA + (size_t)((a) * L.Nmax + i) * (NSYM + NRED))
+#define OBCA_MAB(p) (W.MAB + (size_t)((p) * L.Nmax + i) * (NRED * NRED + 2 * NRED))
+#endif
   // block dynamics from the T maps
   for (int it = ctx.tid; it < V * 7 * (NRED + 1); it += ctx.nt) {
     int a = it / (7 * (NRED + 1)), r = (it / (NRED + 1)) % 7, cc = it % (NRED + 1);
@@ -1011,7 +1019,7 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
     int kr, kc;
     int tr = red_target(a, r, V, R.uoff, R.npv, &kr), tc = red_target(a, cc, V, R.uoff, R.npv, &kc);
     if (kr < 0 || kc < 0) continue;
-    double v = R.MAs[a * (NSYM + NRED) + sym(r, cc)];
+    double v = OBCA_MA(a)[sym(r, cc)];
     if (kr == 0 && kc == 0) R.Q[tr * nX + tc] = v;
     else if (kr == 1 && kc == 0) R.S[tr * nX + tc] = v;
     else if (kr == 1 && kc == 1) R.R[tr * nu + tc] = v;
@@ -1023,7 +1031,7 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
     int a = L.pa[p], b = L.pb[p], ka, kb;
     int ta = red_target(a, ra, V, R.uoff, R.npv, &ka), tb = red_target(b, cb, V, R.uoff, R.npv, &kb);
     if (ka < 0 || kb < 0) continue;
-    double v = R.MABs[p * (NRED * NRED + 2 * NRED) + ra * NRED + cb];
+    double v = OBCA_MAB(p)[ra * NRED + cb];
     if (ka == 0 && kb == 0) R.Q[ta * nX + tb] = v, R.Q[tb * nX + ta] = v;
     else if (ka == 1 && kb == 0) R.S[ta * nX + tb] = v;
     else if (ka == 0 && kb == 1) R.S[tb * nX + ta] = v;
@@ -1040,12 +1048,12 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
     double hd = 0, g = 0;
     if (a >= 0) {
       if (i < L.N[a]) {
-        const double* Mo = R.MAs + a * (NSYM + NRED);
+        const double* Mo = OBCA_MA(a);
         hd = Mo[sym(IDT, rc)], g = Mo[NSYM + rc];
       }
       for (int p = 0; p < L.P; ++p) {
         if (i * NK >= L.Mp[p]) continue;
-        const double* Mo = R.MABs + p * (NRED * NRED + 2 * NRED);
+        const double* Mo = OBCA_MAB(p);
         if (L.pa[p] == a) hd += Mo[rc * NRED + IDT], g += Mo[NRED * NRED + rc];
         else if (L.pb[p] == a) hd += Mo[IDT * NRED + rc], g += Mo[NRED * NRED + NRED + rc];
       }
@@ -1054,12 +1062,12 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
     } else {
       for (int aa = 0; aa < V; ++aa) {
         if (i >= L.N[aa]) continue;
-        const double* Mo = R.MAs + aa * (NSYM + NRED);
+        const double* Mo = OBCA_MA(aa);
         hd += Mo[sym(IDT, IDT)], g += Mo[NSYM + IDT];
       }
       for (int p = 0; p < L.P; ++p) {
         if (i * NK >= L.Mp[p]) continue;
-        const double* Mo = R.MABs + p * (NRED * NRED + 2 * NRED);
+        const double* Mo = OBCA_MAB(p);
         hd += 2.0 * Mo[IDT * NRED + IDT], g += Mo[NRED * NRED + IDT] + Mo[NRED * NRED + NRED + IDT];
       }
       if (i == 0) hd += hdtdt, g += W.gphi[L.oDT];
