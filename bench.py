@@ -202,7 +202,7 @@ def main():
         vals = []
         t_all = time.perf_counter()
         for s in range(args.warmup + args.steps):
-            cb = base.sample(60.0, sample_iters=3)
+            cb = base.sample(52.0, sample_iters=3)
             if s >= args.warmup:
                 vals.append(cb["value"])
         base.close()
@@ -213,7 +213,7 @@ def main():
             "ms_per_step": 1e3 * (time.perf_counter() - t_all) / (args.warmup + args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "impl": "reference", "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
-            "note": "reference arm = CPU restatement (oracle port: numpy/scipy SuperLU interior point from the kinematic warm start, 60 iterations "
+            "note": "reference arm = CPU restatement (oracle port: numpy/scipy SuperLU interior point from the kinematic warm start, 52 iterations "
             "assumed per solve); CasADi/IPOPT are not installable in this image",
         }
         print(json.dumps(line))
