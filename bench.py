@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 AGENTS = ["vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"]
 METRIC = "converged multi-vehicle OBCA solves/sec (batched)"
 # SURVEY.md section 8(d) convention for the 4-vehicle joint problem, per IPM iteration and instance
+DRAM_BYTES_PER_ITER_NCU = 22.1e6  # measured, see roofline.traffic_note
 BYTES_PER_ITER = 3.456e6
 FLOPS_PER_ITER_CONVENTION = 767e6
 FP64_PEAK_TFLOPS = 37.0  # B200 data sheet (non-tensor FP64); not measured on this pool
@@ -236,11 +237,13 @@ def main():
     opts = SolveOptions(tol=args.tol, constr_viol_tol=args.tol, max_iter=600)
     offs_all = random_init_offsets(args.batch * world, 4, seed=0)
     offs = offs_all[rank * args.batch : (rank + 1) * args.batch]
-    plan = prepare_joint_batch(fn, AGENTS, offs, opts, device=device)  # warm start: single-vehicle solves + pair duals
-    sv = ObcaSolver(plan.problem, opts, device=device)
+    t_ws = time.perf_counter()
+    plan = prepare_joint_batch(fn, AGENTS, offs, opts, device=device)  # warm start: single-vehicle solves + pair duals, on the device
+    t_ws = time.perf_counter() - t_ws
+    sv = plan.solver
 
-    # ---------------- device-resident timing (value): inputs already in HBM
-    dev_in = sv.upload(plan.guess)
+    # ---------------- device-resident timing (value): inputs already in HBM (the warm start never left the device)
+    dev_in = plan.dev_guess
     barrier()
 
     def step_device():
@@ -339,7 +342,10 @@ def main():
             "peak": peak,
             "unit": "GB/s",
             "frac": achieved_gbs / peak,
-            "traffic": None,
+            "traffic": DRAM_BYTES_PER_ITER_NCU * sum_iters / world,
+            "traffic_note": "22.1 MB of DRAM traffic per IPM iteration and instance (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+            "capture of k_solve, profiles/r01_ncu_full_k_solve_summary.txt) x the iterations of one launch; 6.4x the algorithmic bytes: "
+            "per-CTA work areas (block solves, QR records, T maps) and local-memory arrays stream through L2/HBM every iteration",
             "peak_source": peak_src,
             "note": "algorithmic bytes = 3.456 MB per IPM iteration and instance (one read + one write of the primal-dual iterate, SURVEY.md 8d) "
             "x iterations of all instances / k_solve time; the kernel is FP64-latency bound, not bandwidth bound (DESIGN.md)",
@@ -350,6 +356,11 @@ def main():
                 "so this is an equivalent-work figure, not executed flops",
             },
         },
+    }
+    line["warm_start"] = {
+        "wall_s_rank0": t_ws, **plan.timing, "single_vehicle_fail_rank0": int(sum((r.status < 0).sum() for r in plan.singles)),
+        "note": "untimed setup of the step (SURVEY.md 8f rank 1): vectorised pose guess on the host, obstacle and pair duals by obca_dual_ws / "
+        "obca_joint_dual_ws on the device, 4 batched single-vehicle solves; the joint warm start stays in HBM",
     }
     if world == 1 and not args.no_mpc:
         line["mpc"] = mpc_latency(fn, device, args.mpc_steps)

@@ -3,16 +3,18 @@
 Reference flow (confrez/control/multi_vehicle_planner.py:659-667): ``solve_single_problems`` (one collocation OBCA
 solve per agent, :68-109) -> ``joint_dual_ws`` (:208-341) -> ``solve_final_problem_obca`` (:343-480).  Here every stage
 runs over a batch of B independent instances (different ``init_offsets``): the per-agent solves and the joint solve go
-through :class:`conflict_rez_b200.solver.ObcaSolver` (CUDA), the pair-dual warm start is the closed form of
-``control.warmstart``.
+through :class:`conflict_rez_b200.solver.ObcaSolver` (CUDA), the dual warm starts are the closed forms of
+``control.warmstart`` evaluated on the device (``obca_dual_ws`` / ``obca_joint_dual_ws``).
 """
+import time
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
+import torch
 
 from conflict_rez_b200.control import warmstart
-from conflict_rez_b200.control.scenario import build_guess, build_problem
+from conflict_rez_b200.control.scenario import build_guess, build_problem, pose_guess
 from conflict_rez_b200.problem import CollocationGuess, CollocationProblem
 from conflict_rez_b200.solver import BatchResult, ObcaSolver, SolveOptions
 
@@ -58,6 +60,14 @@ class JointPlan:
     guess: CollocationGuess
     singles: List[BatchResult]
     result: Optional[BatchResult] = None
+    dev_guess: Optional[dict] = None  # the joint warm start as device tensors (ObcaSolver.set_inputs format)
+    timing: Optional[dict] = None
+    solver: Optional[ObcaSolver] = None  # the joint handle (kept open for the caller; close() when done)
+
+
+def _sync(device):
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
 
 
 def prepare_joint_batch(
@@ -70,22 +80,60 @@ def prepare_joint_batch(
     final_headings: Optional[Dict[str, float]] = None,
     **problem_kwargs,
 ) -> JointPlan:
-    """Everything up to (not including) the joint solve: batched single-vehicle solves + joint warm start."""
+    """Everything up to (not including) the joint solve, device resident: vectorised pose guess on the
+    host, obstacle duals on the device (``obca_dual_ws``), batched single-vehicle solves, joint warm start assembled on
+    the device with the pair duals from ``obca_joint_dual_ws``.  An agent whose single-vehicle solve failed contributes
+    its initial guess instead of the failed iterate."""
     init_offsets = np.asarray(init_offsets, dtype=float)
+    tm = {}
+    t0 = time.perf_counter()
+    prob = build_problem(rl_file_name, list(agents), init_offsets=init_offsets, final_headings=final_headings, **problem_kwargs)
+    z0, dts = pose_guess(prob, rl_file_name, list(agents))
+    tm["host_pose_guess_s"] = time.perf_counter() - t0
+    B, V, O = z0.shape[0], prob.V, prob.O
+    Mmax = int(prob.nodes.max())
+    joint = ObcaSolver(prob, options, device=device, lib=lib)
+    dev = joint.device
+    t0 = time.perf_counter()
+    zj = torch.zeros((B, V, Mmax, 7), dtype=torch.float64, device=dev)
+    lamj = torch.zeros((B, V, Mmax, O, 4), dtype=torch.float64, device=dev)
+    muj = torch.zeros_like(lamj)
+    dt_sum = torch.zeros(B, dtype=torch.float64, device=dev)
     singles = []
     for ia, agent in enumerate(agents):
         p1 = build_problem(rl_file_name, [agent], init_offsets=init_offsets[:, ia : ia + 1], final_headings=final_headings, **problem_kwargs)
-        g1 = build_guess(p1, rl_file_name, [agent])
+        M = int(p1.nodes[0])
         sv = ObcaSolver(p1, options, device=device, lib=lib)
-        singles.append(sv.solve(g1))
+        d = {"pose": sv._to_dev(p1.init_pose, (B, 1, 3)), "z": sv._to_dev(z0[:, ia : ia + 1, :M], (B, 1, M, 7)), "dt": sv._to_dev(dts[:, ia], (B,))}
+        d["lam"], d["mu"] = sv.dual_ws(d["z"])
+        sv.set_inputs(d)
+        sv.run()
+        st, it, dbl = sv.fetch_stats()
+        sol = sv.fetch_solution()
+        ok = st >= 0
+        pick = lambda a, b: torch.where(ok.view((B,) + (1,) * (a.dim() - 1)), a, b)
+        zj[:, ia, :M] = pick(sol["z"], d["z"])[:, 0]
+        lamj[:, ia, :M] = pick(sol["lam"], d["lam"])[:, 0]
+        muj[:, ia, :M] = pick(sol["mu"], d["mu"])[:, 0]
+        dt_sum += pick(sol["dt"], d["dt"])
+        cpu = lambda t: t.cpu().numpy()
+        singles.append(BatchResult(cpu(st), cpu(it), cpu(dbl[0]), cpu(dbl[1]), cpu(dbl[2]), cpu(dbl[3]), cpu(sol["z"]), None, None, cpu(sol["dt"]), None, None, None))
         sv.close()
-    prob = build_problem(rl_file_name, list(agents), init_offsets=init_offsets, final_headings=final_headings, **problem_kwargs)
-    return JointPlan(prob, joint_guess_from_singles(prob, singles), singles)
+    dg = {"pose": joint._to_dev(prob.init_pose, (B, V, 3)), "z": zj, "lam": lamj, "mu": muj, "dt": dt_sum / V}  # dt0: multi_vehicle_planner.py:360
+    if joint.P:
+        dg["pl"], dg["pm"], dg["ps"] = joint.joint_dual_ws(zj)
+    _sync(dev)
+    tm["device_warm_start_s"] = time.perf_counter() - t0
+    host = lambda k: dg[k].cpu().numpy() if k in dg else None
+    guess = CollocationGuess(host("z"), host("lam"), host("mu"), host("dt"), host("pl"), host("pm"), host("ps"))
+    return JointPlan(prob, guess, singles, dev_guess=dg, timing=tm, solver=joint)
 
 
 def solve_joint_batch(rl_file_name, agents, init_offsets, options=None, device="cuda:0", lib=None, **kw) -> JointPlan:
     plan = prepare_joint_batch(rl_file_name, agents, init_offsets, options, device, lib, **kw)
-    sv = ObcaSolver(plan.problem, options, device=device, lib=lib)
-    plan.result = sv.solve(plan.guess)
-    sv.close()
+    t0 = time.perf_counter()
+    plan.result = plan.solver.solve(plan.guess)
+    plan.timing["joint_solve_s"] = time.perf_counter() - t0
+    plan.solver.close()
+    plan.solver = None
     return plan

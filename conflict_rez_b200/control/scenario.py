@@ -78,36 +78,44 @@ def build_problem(
     )
 
 
-def build_guess(prob: CollocationProblem, rl_file_name: str, agents: Sequence[str], N_ws: int = 30, dt_ws: float = 0.1) -> CollocationGuess:
-    """Spline pose guess -> kinematic state guess -> closed-form duals -> Radau resampling (batched over init poses).
+def pose_guess(prob: CollocationProblem, rl_file_name: str, agents: Sequence[str], N_ws: int = 30, dt_ws: float = 0.1):
+    """Spline pose guess -> kinematic state guess -> Radau resampling, vectorised over the batch: z (B,V,Mmax,7), dts (B,V).
 
     The pose guess is shifted rigidly at t=0 towards each instance's perturbed initial pose and blended out over the
     first set move, so that every instance starts from a guess consistent with its own initial condition.
     """
     vb = VehicleBody()
     paths = interp_along_sets(rl_file_name, vb, N_ws)
-    batched = prob.batch is not None
-    init = prob.init_pose if batched else prob.init_pose[None]
-    B, V, O = init.shape[0], prob.V, prob.O
+    init = prob.init_pose if prob.batch is not None else prob.init_pose[None]
+    B, V = init.shape[0], prob.V
     Mmax = int(prob.nodes.max())
     z = np.zeros((B, V, Mmax, 7))
-    lam = np.zeros((B, V, Mmax, O, 4))
-    mu = np.zeros((B, V, Mmax, O, 4))
     dts = np.zeros((B, V))
     for ia, a in enumerate(agents):
         path0 = paths[a]
         N, M = int(prob.N[ia]), int(prob.nodes[ia])
         blend = np.clip(1.0 - np.arange(len(path0)) / float(N_ws), 0.0, 1.0)[:, None]
-        for b in range(B):
-            path = path0 + blend * (init[b, ia] - path0[0])[None, :]
-            kin = warmstart.kinematic_guess(path, dt_ws, prob.wb, prob.limits)
-            sig = {k: kin[k] for k in ("x", "y", "psi", "v", "delta", "a", "w")}
-            t_i, res = warmstart.interp_ws_for_collocation(kin["t"], sig, N, prob.K)
-            zz = np.stack([res[k] for k in ("x", "y", "psi", "v", "delta", "a", "w")], axis=1)
-            z[b, ia, :M] = zz
-            l_, m_ = warmstart.dual_ws_rect(zz[:, 0], zz[:, 1], zz[:, 2], prob.obs_A, prob.obs_b, prob.body_G, prob.body_g)
-            lam[b, ia, :M], mu[b, ia, :M] = l_, m_
-            dts[b, ia] = kin["t"][-1] / N
+        path = path0[None] + blend[None] * (init[:, ia] - path0[0])[:, None, :]  # (B,T,3)
+        kin = warmstart.kinematic_guess(path, dt_ws, prob.wb, prob.limits)
+        for c, k in enumerate(("x", "y", "psi", "v", "delta", "a", "w")):
+            z[:, ia, :M, c] = warmstart.resample_for_collocation(kin["t"], kin[k], N, prob.K)
+        dts[:, ia] = kin["t"][-1] / N
+    return z, dts
+
+
+def build_guess(prob: CollocationProblem, rl_file_name: str, agents: Sequence[str], N_ws: int = 30, dt_ws: float = 0.1) -> CollocationGuess:
+    """``pose_guess`` + closed-form duals on the host (the batched planners compute the duals on the device instead,
+    ``ObcaSolver.dual_ws`` / ``joint_dual_ws``; both implement control/warmstart.py's formulas)."""
+    batched = prob.batch is not None
+    z, dts = pose_guess(prob, rl_file_name, agents, N_ws, dt_ws)
+    B, V, O = z.shape[0], prob.V, prob.O
+    Mmax = int(prob.nodes.max())
+    lam = np.zeros((B, V, Mmax, O, 4))
+    mu = np.zeros((B, V, Mmax, O, 4))
+    for ia in range(V):
+        M = int(prob.nodes[ia])
+        zz = z[:, ia, :M]
+        lam[:, ia, :M], mu[:, ia, :M] = warmstart.dual_ws_rect(zz[..., 0], zz[..., 1], zz[..., 2], prob.obs_A, prob.obs_b, prob.body_G, prob.body_g)
     P = len(prob.pairs)
     pl = np.zeros((B, P, Mmax, 4))
     pm = np.zeros((B, P, Mmax, 4))

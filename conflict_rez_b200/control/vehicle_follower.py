@@ -194,6 +194,7 @@ class MultiDistributedFollower(object):
             self.vehicles.append(v)
         self.iter_time = {agent: [] for agent in self.agents}
         self.step_time: List[float] = []
+        self.step_iters: List[int] = []
         self.single_results: Dict[str, VehiclePrediction] = {}
         self.final_results: Dict[str, VehiclePrediction] = {}
         self.solver = None
@@ -224,6 +225,7 @@ class MultiDistributedFollower(object):
             res = self.solver.solve_step(cur, ref, others, guess)  # all vehicles of this control step in one launch
             dt_solve = time.perf_counter() - t0
             self.step_time.append(dt_solve)
+            self.step_iters.append(int(np.max(res.iters)))
             for b, v in enumerate(self.vehicles):
                 v.apply_result(bool(res.status[b] >= 0), res, b, dt_solve)
         for v in self.vehicles:

@@ -133,22 +133,22 @@ def joint_dual_ws_rect(xa, ya, pa, xb, yb, pb, G, g):
 
 
 def kinematic_guess(path, dt, wb, limits):
-    """(T,3) pose samples spaced ``dt`` apart -> dict of arrays x,y,psi,v,delta,a,w,t (len T)."""
+    """(..., T, 3) pose samples spaced ``dt`` apart -> dict of arrays x,y,psi,v,delta,a,w (..., T) and t (T,)."""
     path = np.asarray(path, dtype=float)
-    x, y, psi = path[:, 0], path[:, 1], np.unwrap(path[:, 2])
-    T = len(x)
-    dx, dy, dpsi = np.gradient(x, dt), np.gradient(y, dt), np.gradient(psi, dt)
+    x, y, psi = path[..., 0], path[..., 1], np.unwrap(path[..., 2], axis=-1)
+    T = x.shape[-1]
+    dx, dy = np.gradient(x, dt, axis=-1), np.gradient(y, dt, axis=-1)
     v = dx * np.cos(psi) + dy * np.sin(psi)
     v = np.clip(v, 0.9 * limits[0], 0.9 * limits[1])
-    v[0] = v[-1] = 0.0
+    v[..., 0] = v[..., -1] = 0.0
     # Steering is left at zero: differentiating the Bezier heading gives a steering guess that saturates around every
     # cusp and stop move (|v| ~ 0), which starts the interior-point iteration on the steering bounds and made ~5 % of
     # the randomized instances jam there.  delta = w = 0 starts strictly inside the box (the reference's state_ws NLP
     # also starts from zero steering, vehicle.py:197-205).
-    delta = np.zeros(T)
-    w = np.zeros(T)
-    a = np.clip(np.gradient(v, dt), 0.9 * limits[4], 0.9 * limits[5])
-    a[0] = a[-1] = 0.0
+    delta = np.zeros_like(v)
+    w = np.zeros_like(v)
+    a = np.clip(np.gradient(v, dt, axis=-1), 0.9 * limits[4], 0.9 * limits[5])
+    a[..., 0] = a[..., -1] = 0.0
     return {"t": dt * np.arange(T), "x": x, "y": y, "psi": psi, "v": v, "delta": delta, "a": a, "w": w}
 
 
@@ -171,3 +171,14 @@ def interp_ws_for_collocation(t, signals, N, K=5):
         res = np.stack([np.interp(t_interp, t, flat[:, c]) for c in range(flat.shape[1])], axis=1)
         out[name] = res.reshape((len(t_interp),) + sig.shape[1:])
     return t_interp, out
+
+
+def resample_for_collocation(t, sig, N, K=5):
+    """Batched form of ``interp_ws_for_collocation`` for signals (..., T) that share the time grid ``t`` (T,):
+    linear interpolation onto t_interp = (i + tau_k)/N * t[-1]; returns (..., N*(K+1))."""
+    tau = radau_nodes(K)
+    t_interp = (np.arange(N)[:, None] + tau[None, :]).ravel() / N * t[-1]
+    idx = np.clip(np.searchsorted(t, t_interp, side="right") - 1, 0, len(t) - 2)
+    wgt = (t_interp - t[idx]) / (t[idx + 1] - t[idx])
+    sig = np.asarray(sig, dtype=float)
+    return sig[..., idx] + (sig[..., idx + 1] - sig[..., idx]) * wgt

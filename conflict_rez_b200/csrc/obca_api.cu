@@ -532,6 +532,54 @@ int obca_set_mpc_params(ObcaHandle* h, const double* cur, const double* ref, con
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// closed-form dual warm starts (obca_ws.h)
+// ------------------------------------------------------------------------------------------------
+#ifndef OBCA_HOST_EMU
+__global__ void k_dual_ws(const Lay* L, const Stat* S, const double* z, double* lam, double* mu, size_t tot) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < tot) ws_obstacle_item(*L, *S, z, lam, mu, g);
+}
+__global__ void k_joint_dual_ws(const Lay* L, const Stat* S, const double* z, double* pl, double* pm, double* ps, size_t tot) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < tot) ws_pair_item(*L, *S, z, pl, pm, ps, g);
+}
+#endif
+
+int obca_dual_ws(ObcaHandle* h, const double* z, double* lam, double* mu, void* stream) {
+  if (!h || !h->have_static) return fail("obca_dual_ws: call obca_set_static first");
+  if (!z || !lam || !mu) return fail("obca_dual_ws: null argument");
+  const size_t tot = (size_t)h->dims.batch * h->L.V * h->L.Mv * h->L.O;
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (size_t g = 0; g < tot; ++g) ws_obstacle_item(h->L, h->S, z, lam, mu, g);
+#else
+  if (tot) {
+    k_dual_ws<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->d_L, h->d_S, z, lam, mu, tot);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+#endif
+  return 0;
+}
+
+int obca_joint_dual_ws(ObcaHandle* h, const double* z, double* pl, double* pm, double* ps, void* stream) {
+  if (!h || !h->have_static) return fail("obca_joint_dual_ws: call obca_set_static first");
+  if (h->L.mode != 0) return fail("obca_joint_dual_ws: collocation mode only");
+  if (h->L.P == 0) return 0;
+  if (!z || !pl || !pm || !ps) return fail("obca_joint_dual_ws: null argument");
+  const size_t tot = (size_t)h->dims.batch * h->L.P * h->L.Mv;
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (size_t g = 0; g < tot; ++g) ws_pair_item(h->L, h->S, z, pl, pm, ps, g);
+#else
+  k_joint_dual_ws<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->d_L, h->d_S, z, pl, pm, ps, tot);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
 static int run_pack(ObcaHandle* h, const PackArgs& A, bool unpack, void* stream) {
   int B = h->dims.batch, ne = pack_elems(h->L);
 #ifdef OBCA_HOST_EMU

@@ -774,4 +774,5 @@ OBCA_HDN void eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Scratc
 
 #include "obca_kkt.h"
 #include "obca_mpc.h"
+#include "obca_ws.h"
 #include "obca_ipm.h"

@@ -80,6 +80,8 @@ EXPORTS = [
     "obca_set_init_pose",
     "obca_set_initial",
     "obca_set_mpc_params",
+    "obca_dual_ws",
+    "obca_joint_dual_ws",
     "obca_solve",
     "obca_get_solution",
     "obca_get_stats",
@@ -117,6 +119,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.obca_set_init_pose.argtypes = [vp, vp, vp]
     lib.obca_set_initial.argtypes = [vp] + [vp] * 7 + [vp]
     lib.obca_set_mpc_params.argtypes = [vp, vp, vp, vp, vp]
+    lib.obca_dual_ws.argtypes = [vp, vp, vp, vp, vp]
+    lib.obca_joint_dual_ws.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.obca_solve.argtypes = [vp, vp]
     lib.obca_get_solution.argtypes = [vp] + [vp] * 7 + [vp]
     lib.obca_get_stats.argtypes = [vp] + [vp] * 6 + [vp]
@@ -253,6 +257,27 @@ class ObcaSolver:
             d["pm"] = self._to_dev(guess.pair_mu, (B, P, M, 4))
             d["ps"] = self._to_dev(guess.pair_s, (B, P, M, 2))
         return d
+
+    def dual_ws(self, z):
+        """Device warm start of the obstacle duals (replaces ``Vehicle.dual_ws``): z (B,V,Mmax,7) device -> lam, mu."""
+        B, V, M, O = self.B, self.V, self.Mmax, self.O
+        z = z.contiguous()
+        assert tuple(z.shape) == (B, V, M, 7) and z.dtype == torch.float64
+        lam = torch.empty((B, V, M, O, 4), dtype=torch.float64, device=z.device)
+        mu = torch.empty_like(lam)
+        self._check(self.lib.obca_dual_ws(self.handle, _ptr(z), _ptr(lam), _ptr(mu), self._stream_ptr()))
+        return lam, mu
+
+    def joint_dual_ws(self, z):
+        """Device warm start of the pair duals (replaces ``MultiVehiclePlanner.joint_dual_ws``): z -> pair_lam, pair_mu, pair_s."""
+        B, V, M, P = self.B, self.V, self.Mmax, self.P
+        z = z.contiguous()
+        assert tuple(z.shape) == (B, V, M, 7) and z.dtype == torch.float64
+        pl = torch.empty((B, P, M, 4), dtype=torch.float64, device=z.device)
+        pm = torch.empty_like(pl)
+        ps = torch.empty((B, P, M, 2), dtype=torch.float64, device=z.device)
+        self._check(self.lib.obca_joint_dual_ws(self.handle, _ptr(z), _ptr(pl), _ptr(pm), _ptr(ps), self._stream_ptr()))
+        return pl, pm, ps
 
     def set_inputs(self, d):
         s = self._stream_ptr()

@@ -105,6 +105,13 @@ int obca_set_initial(ObcaHandle* h, const double* z, const double* lam, const do
  * obca_set_initial takes z (B,1,N,7), lam/mu (B,1,N,O,4), dt (B, ignored), pair_* (B,n_others,N,.) in this mode. */
 int obca_set_mpc_params(ObcaHandle* h, const double* cur, const double* ref, const double* others, void* stream);
 
+/* Dual warm starts in closed form for 4-face polytopes, on the device (all pointers dev, node-major like obca_set_initial):
+ * obca_dual_ws replaces Vehicle.dual_ws (confrez/control/vehicle.py:233-296): poses z (B,V,Mmax,7) -> lam, mu (B,V,Mmax,O,4);
+ * obca_joint_dual_ws replaces MultiVehiclePlanner.joint_dual_ws (confrez/control/multi_vehicle_planner.py:208-341):
+ * z -> pair_lam, pair_mu (B,P,Mmax,4), pair_s (B,P,Mmax,2).  Entries of padding nodes are set to zero. */
+int obca_dual_ws(ObcaHandle* h, const double* z, double* lam, double* mu, void* stream);
+int obca_joint_dual_ws(ObcaHandle* h, const double* z, double* pair_lam, double* pair_mu, double* pair_s, void* stream);
+
 /* run the batched interior-point solve, asynchronously on `stream`; no host sync inside */
 int obca_solve(ObcaHandle* h, void* stream);
 

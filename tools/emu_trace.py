@@ -15,7 +15,7 @@ agents = ["vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"]
 opts = SolveOptions(tol=1e-2, constr_viol_tol=1e-2, max_iter=600)
 offs = random_init_offsets(512, 4, seed=0)[ids]
 plan = prepare_joint_batch(fn, agents, offs, opts, device="cpu", lib=lib)
-sv = ObcaSolver(plan.problem, opts, device="cpu", lib=lib)
+sv = plan.solver
 os.environ["OBCA_TRACE"] = "1"
 res = sv.solve(plan.guess)
 print("status", res.status, "iters", res.iters)

@@ -13,7 +13,7 @@ fn = os.path.join(tempfile.mkdtemp(), "4v"); write_strategy(fn)
 agents = ["vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"]
 opts = SolveOptions(max_iter=600)
 plan = prepare_joint_batch(fn, agents, random_init_offsets(B, 4), opts)
-sv = ObcaSolver(plan.problem, opts)
+sv = plan.solver
 d = sv.upload(plan.guess); sv.set_inputs(d); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); sv.run(); e1.record(); torch.cuda.synchronize()

@@ -12,7 +12,7 @@ fn = os.path.join(tempfile.mkdtemp(), "4v"); write_strategy(fn)
 agents = ["vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"]
 opts = SolveOptions(tol=1e-2, constr_viol_tol=1e-2, max_iter=600)
 plan = prepare_joint_batch(fn, agents, random_init_offsets(B, 4, seed=0), opts)
-sv = ObcaSolver(plan.problem, opts)
+sv = plan.solver
 d = sv.upload(plan.guess)
 
 

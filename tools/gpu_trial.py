@@ -18,7 +18,7 @@ plan = prepare_joint_batch(fn, agents, random_init_offsets(B, 4), opts)
 print("prepare %.2fs" % (time.time() - t0))
 for a, r in zip(agents, plan.singles):
     print(a, "status", np.unique(r.status, return_counts=True), "iters med %d max %d" % (np.median(r.iters), r.iters.max()))
-sv = ObcaSolver(plan.problem, opts)
+sv = plan.solver
 d = sv.upload(plan.guess)
 for rep in range(2):
     sv.set_inputs(d)
