@@ -598,7 +598,7 @@ static int run_pack(ObcaHandle* h, const PackArgs& A, bool unpack, void* stream)
 int obca_set_initial(ObcaHandle* h, const double* z, const double* lam, const double* mu, const double* dt, const double* pl,
                      const double* pm, const double* ps, void* stream) {
   if (!h || !h->have_static) return fail("obca_set_initial: call obca_set_static first");
-  if (!z || !lam || !mu || !dt) return fail("obca_set_initial: z, lam, mu, dt are required");
+  if (!z || !dt || (h->L.O > 0 && (!lam || !mu))) return fail("obca_set_initial: z, lam, mu, dt are required");
   PackArgs A;
   memset(&A, 0, sizeof(A));
   A.z = z, A.lam = lam, A.mu = mu, A.dt = dt, A.pl = pl, A.pm = pm, A.ps = ps;

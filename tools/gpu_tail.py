@@ -23,6 +23,10 @@ def timed():
     return e0.elapsed_time(e1)
 
 
+for a, r in zip(agents, plan.singles):
+    bad = np.nonzero(r.status < 0)[0]
+    print(a, "single failures", bad.tolist(), r.status[bad].tolist(), "iters p50 %d max %d" % (np.median(r.iters), r.iters.max()))
+print("warm start timing", plan.timing)
 timed()
 ms = timed()
 st, it, dbl = sv.fetch_stats(); it = it.cpu().numpy(); st = st.cpu().numpy()
@@ -34,5 +38,7 @@ for n in it:  # the device queue hands out instances in index order to whichever
 mk = max(h)
 print("B=%d %.1f ms; iters sum %d mean %.1f med %d p90 %d p99 %d max %d; status ok %d" % (
     B, ms, it.sum(), it.mean(), np.median(it), np.percentile(it, 90), np.percentile(it, 99), it.max(), (st >= 0).sum()))
+bad = np.unique(np.concatenate([np.nonzero(r.status < 0)[0] for r in plan.singles]))
+print("joint iterations of the instances with a failed single:", it[bad].tolist(), " slowest 12:", np.argsort(-it)[:12].tolist(), np.sort(it)[::-1][:12].tolist())
 print("queue makespan %d iterations vs ideal %.1f (efficiency %.2f); ms per iteration on the critical CTA %.2f" % (
     mk, it.sum() / len(h), it.sum() / len(h) / mk, ms / mk))
