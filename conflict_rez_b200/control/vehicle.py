@@ -81,12 +81,33 @@ class Vehicle(object):
     # ------------------------------------------------------------------ warm start
     def state_ws(self, N: int = 30, dt: float = 0.1, init_offset: VehicleState = VehicleState(), final_heading: float = None,
                  bounded_input: bool = False, shrink_tube: float = 0.8, spline_ws: bool = False, verbose: int = 0) -> VehiclePrediction:
+        """Tube-following state warm start (vehicle.py:99-231).  The reference solves an Euler-discretised NLP without
+        obstacles; here the *collocation* problem without obstacles is solved on the device from the kinematic
+        reconstruction of the Bezier pose guess, and its solution is sampled on the reference's uniform grid."""
         path = interp_along_sets(self.rl_file_name, self.vehicle_body, N)[self.agent].copy()
         off = np.array([init_offset.x.x, init_offset.x.y, init_offset.e.psi])
         path += np.clip(1.0 - np.arange(len(path)) / float(N), 0.0, 1.0)[:, None] * off[None, :]
         vc = self.vehicle_config
         limits = np.array([vc.v_min, vc.v_max, vc.delta_min, vc.delta_max, vc.a_min, vc.a_max, vc.w_delta_min, vc.w_delta_max], dtype=float)
         kin = warmstart.kinematic_guess(path, dt, self.vehicle_body.wb, limits)
+        names = ("x", "y", "psi", "v", "delta", "a", "w")
+        K, nps = 5, 5
+        Ncol = nps * (self.num_sets - 1)
+        zc = np.stack([warmstart.resample_for_collocation(kin["t"], kin[k], Ncol, K) for k in names], axis=1)
+        tube = JointProblem([], self.vehicle_body, self.vehicle_config, self.region)
+        tube.add_vehicle(dict(agent=self.agent, tube=self.rl_tube, pose0=path[0] * 1.0, heading=final_heading, z=zc,
+                              lam=np.zeros((len(zc), 0, 4)), mu=np.zeros((len(zc), 0, 4)), dt0=kin["t"][-1] / Ncol),
+                         dict(K=K, n_per_set=nps, dmin=0.05, shrink_tube=shrink_tube), None)
+        try:
+            sol = tube.solve(self.solve_options, self.device, getattr(self, "_lib", None))
+            r = sol.result
+            tn = ((np.arange(Ncol)[:, None] + warmstart.radau_nodes(K)[None, :]).ravel()) * float(r.dt[0])
+            tu = np.linspace(0.0, tn[-1], len(kin["t"]))
+            kin = {k: np.interp(tu, tn, r.z[0, 0, : len(tn), c]) for c, k in enumerate(names)}
+            kin["t"] = tu
+        except RuntimeError as e:  # keep the kinematic guess when the tube-following solve does not converge
+            if not hasattr(e, "sol"):
+                raise
         result = VehiclePrediction()
         result.t = kin["t"]
         result.x, result.y, result.psi, result.v = kin["x"], kin["y"], kin["psi"], kin["v"]
@@ -227,7 +248,8 @@ class JointProblem:
         vc, rg = self.vc, self.region
         prob = CollocationProblem(
             n_sets=n_sets,
-            obs_A=np.stack([o.A for o in self.obstacles]), obs_b=np.stack([np.ravel(o.b) for o in self.obstacles]),
+            obs_A=np.stack([o.A for o in self.obstacles]) if O else np.zeros((0, 4, 2)),
+            obs_b=np.stack([np.ravel(o.b) for o in self.obstacles]) if O else np.zeros((0, 4)),
             tube_A=tube_A, tube_b=tube_b, init_pose=np.stack([b["pose0"] for b in self.blocks]),
             final_heading=np.array([np.nan if b["heading"] is None else float(b["heading"]) for b in self.blocks]),
             body_G=np.asarray(self.vb.A, float), body_g=np.asarray(self.vb.b, float), wb=self.vb.wb,
