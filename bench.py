@@ -366,7 +366,7 @@ def main():
         line["mpc"] = mpc_latency(fn, device, args.mpc_steps)
     if world == 1 and not args.no_cpu_baseline:
         base = CpuBaseline(plan, 1)
-        line["cpu_baseline"] = base.sample(float(np.median(it_h)), sample_iters=4)
+        line["cpu_baseline"] = base.sample(float(np.median(it_h)), sample_iters=16)
         base.close()
     print(json.dumps(line))
     if world > 1:
