@@ -121,6 +121,67 @@ OBCA_HD void jet_rk4(const double* zu, double dt, double wb, Jet<H>* z) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// univariate Taylor jets v + a t + b t^2 along one direction d of the 7 inputs: the work of the dynamics derivatives is
+// split into (node, direction) tasks that run on different threads.  d'(grad^2 F_r) d = 2 b_r, (dF_r/d(z,u)) d = a_r.
+// ------------------------------------------------------------------------------------------------
+template <bool SECOND>
+struct Tay {
+  double v, a, b;
+};
+template <bool S2>
+OBCA_HD Tay<S2> tay_axpy(const Tay<S2>& x, double s, const Tay<S2>& y) {
+  Tay<S2> r;
+  r.v = x.v + s * y.v, r.a = x.a + s * y.a, r.b = S2 ? x.b + s * y.b : 0.0;
+  return r;
+}
+template <bool S2>
+OBCA_HD Tay<S2> tay_mul(const Tay<S2>& x, const Tay<S2>& y) {
+  Tay<S2> r;
+  r.v = x.v * y.v, r.a = x.v * y.a + x.a * y.v, r.b = S2 ? x.v * y.b + x.a * y.a + x.b * y.v : 0.0;
+  return r;
+}
+template <bool S2>
+OBCA_HD Tay<S2> tay_unary(const Tay<S2>& x, double f0, double f1, double f2) {
+  Tay<S2> r;
+  r.v = f0, r.a = f1 * x.a, r.b = S2 ? f1 * x.b + 0.5 * f2 * x.a * x.a : 0.0;
+  return r;
+}
+template <bool S2>
+OBCA_HD void tay_f(const Tay<S2>* z, const Tay<S2>* u, double wb, Tay<S2>* out) {
+  const double c = cos(z[2].v), s = sin(z[2].v), t = tan(z[4].v), sec2 = 1.0 + t * t;
+  Tay<S2> jc = tay_unary<S2>(z[2], c, -s, -c), js = tay_unary<S2>(z[2], s, c, -s);
+  Tay<S2> jt = tay_unary<S2>(z[4], t / wb, sec2 / wb, 2.0 * t * sec2 / wb);
+  out[0] = tay_mul<S2>(z[3], jc);
+  out[1] = tay_mul<S2>(z[3], js);
+  out[2] = tay_mul<S2>(z[3], jt);
+  out[3] = u[0];
+  out[4] = u[1];
+}
+// RK4 x 4 (dynamic_model.py:30-58) along z(t) = zu + t d
+template <bool S2>
+OBCA_HD void tay_rk4(const double* zu, const double* d, double dt, double wb, Tay<S2>* z) {
+  Tay<S2> u[2] = {{zu[5], d[5], 0.0}, {zu[6], d[6], 0.0}};
+  for (int q = 0; q < 5; ++q) z[q].v = zu[q], z[q].a = d[q], z[q].b = 0.0;
+  const double h = dt / 4.0;
+  for (int sub = 0; sub < 4; ++sub) {
+    Tay<S2> a1[5], a2[5], a3[5], a4[5], tmp[5];
+    tay_f<S2>(z, u, wb, a1);
+    for (int q = 0; q < 5; ++q) tmp[q] = tay_axpy<S2>(z[q], h / 2, a1[q]);
+    tay_f<S2>(tmp, u, wb, a2);
+    for (int q = 0; q < 5; ++q) tmp[q] = tay_axpy<S2>(z[q], h / 2, a2[q]);
+    tay_f<S2>(tmp, u, wb, a3);
+    for (int q = 0; q < 5; ++q) tmp[q] = tay_axpy<S2>(z[q], h, a3[q]);
+    tay_f<S2>(tmp, u, wb, a4);
+    for (int q = 0; q < 5; ++q) {
+      Tay<S2> acc = tay_axpy<S2>(z[q], h / 6, a1[q]);
+      acc = tay_axpy<S2>(acc, h / 3, a2[q]);
+      acc = tay_axpy<S2>(acc, h / 3, a3[q]);
+      z[q] = tay_axpy<S2>(acc, h / 6, a4[q]);
+    }
+  }
+}
+
 // plain RK4 (values only) for the line-search trial points
 OBCA_HD void rk4_value(const double* zu, double dt, double wb, double* out) {
   double z[5] = {zu[0], zu[1], zu[2], zu[3], zu[4]};
@@ -204,67 +265,88 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   cta_sync(ctx);
   prof_mark(ctx, 0);
   double f_part = 0;
+  // scratch (the collocation-mode node buffers are free in MPC mode): dynamics y'J columns [N][5], obstacle pose gradients [N][O][3]
+  double* JG = W.HN;
+  double* OG = W.HN + (size_t)N * 5;
+  // tasks (node, nonlinear input i = psi, v, delta, a, w): column i of the dynamics Jacobian, contracted with y; residual rows
+  if (y) {
+    for (int it = ctx.tid; it < (N - 1) * 5; it += ctx.nt) {
+      const int n = it / 5, i = it % 5;
+      double z[NZ], d[NZ] = {0, 0, 0, 0, 0, 0, 0};
+      for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
+      d[2 + i] = 1.0;
+      Tay<false> F[5];
+      tay_rk4<false>(z, d, S.dt_mpc, S.wb, F);
+      double acc = 0;
+      for (int r = 0; r < 5; ++r) acc += y[L.YCOL(0, r, n)] * F[r].a;
+      JG[n * 5 + i] = acc;
+      if (i == 0)
+        for (int r = 0; r < 5; ++r) c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r].v;
+    }
+  } else {
+    for (int n = ctx.tid; n < N - 1; n += ctx.nt) {
+      double z[NZ], F[5];
+      for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
+      rk4_value(z, S.dt_mpc, S.wb, F);
+      for (int r = 0; r < 5; ++r) c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r];
+    }
+  }
+  // tasks (node, obstacle): residual rows, gradient of the block variables, pose gradient
+  for (int it = ctx.tid; it < N * L.O; it += ctx.nt) {
+    const int n = it / L.O, j = it % L.O;
+    Pose p;
+    load_pose(L, x, 0, n, p);
+    ObsBlk B;
+    for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(0, j, r, n)], B.mu[r] = x[L.MU(0, j, r, n)];
+    B.sd = x[L.SD(0, j, n)];
+    B.el = x[L.EL(0, j, n)];
+    f_part += S.rho * B.el;
+    obs_residual(S, j, p, B);
+    for (int r = 0; r < 4; ++r) c[L.YOBS(0, j, r, n)] = B.c[r];
+    if (!y) continue;
+    double y1 = y[L.YOBS(0, j, 0, n)], y2[2] = {y[L.YOBS(0, j, 1, n)], y[L.YOBS(0, j, 2, n)]}, y3 = y[L.YOBS(0, j, 3, n)];
+    double Ry[2] = {p.c * y2[0] - p.s * y2[1], p.s * y2[0] + p.c * y2[1]};
+    for (int r = 0; r < 4; ++r) {
+      const double* A = S.obsA[j][r];
+      gl[L.LAM(0, j, r, n)] = y1 * B.Atb[r] + A[0] * Ry[0] + A[1] * Ry[1] + 2.0 * y3 * (A[0] * B.u[0] + A[1] * B.u[1]);
+      gl[L.MU(0, j, r, n)] = -y1 * S.g[r] + S.G[r][0] * y2[0] + S.G[r][1] * y2[1];
+    }
+    gl[L.SD(0, j, n)] = -y1;
+    gl[L.EL(0, j, n)] = S.rho + y1;
+    double* og = OG + (size_t)it * 3;
+    og[0] = y1 * B.u[0];
+    og[1] = y1 * B.u[1];
+    og[2] = y2[0] * (-p.s * B.u[0] + p.c * B.u[1]) + y2[1] * (-p.c * B.u[0] - p.s * B.u[1]);
+  }
+  cta_sync(ctx);
   for (int n = ctx.tid; n < N; n += ctx.nt) {
     double z[NZ];
     for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
-    Pose p = {z[0], z[1], z[2], cos(z[2]), sin(z[2])};
     const double* rf = par.ref + 3 * n;
     double ex = z[0] - rf[0], ey = z[1] - rf[1], ep = z[2] - rf[2];
     f_part += 100.0 * (ex * ex + ey * ey + ep * ep) + z[5] * z[5] + z[3] * z[3] * z[6] * z[6] + z[4] * z[4];
-    double g[NZ] = {200.0 * ex, 200.0 * ey, 200.0 * ep, 2.0 * z[3] * z[6] * z[6], 2.0 * z[4], 2.0 * z[5], 2.0 * z[3] * z[3] * z[6]};
+    for (int o = 0; o < L.P; ++o) f_part += S.rho * x[L.PEL(o, n)];
     if (n == 0)
       for (int q = 0; q < 5; ++q) c[L.YINIT(0, q)] = z[q] - par.cur[q];
+    if (!y) continue;
+    double g[NZ] = {200.0 * ex, 200.0 * ey, 200.0 * ep, 2.0 * z[3] * z[6] * z[6], 2.0 * z[4], 2.0 * z[5], 2.0 * z[3] * z[3] * z[6]};
     if (n < N - 1) {
-      if (y) {
-        Jet<false> F[5];
-        jet_rk4<false>(z, S.dt_mpc, S.wb, F);
-        for (int r = 0; r < 5; ++r) {
-          c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r].v;
-          double yr = y[L.YCOL(0, r, n)];
-          for (int q = 0; q < NZ; ++q) g[q] -= yr * F[r].g[q];
-        }
-      } else {
-        double F[5];
-        rk4_value(z, S.dt_mpc, S.wb, F);
-        for (int r = 0; r < 5; ++r) c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r];
-      }
+      g[0] -= y[L.YCOL(0, 0, n)], g[1] -= y[L.YCOL(0, 1, n)];  // F_x = x + ..., F_y = y + ...: identity columns
+      for (int i = 0; i < 5; ++i) g[2 + i] -= JG[n * 5 + i];
     }
-    if (y) {
-      if (n >= 1)
-        for (int r = 0; r < 5; ++r) g[r] += y[L.YCOL(0, r, n - 1)];
-      if (n == 0)
-        for (int q = 0; q < 5; ++q) g[q] += y[L.YINIT(0, q)];
-    }
+    if (n >= 1)
+      for (int r = 0; r < 5; ++r) g[r] += y[L.YCOL(0, r, n - 1)];
+    if (n == 0)
+      for (int q = 0; q < 5; ++q) g[q] += y[L.YINIT(0, q)];
     for (int j = 0; j < L.O; ++j) {
-      ObsBlk B;
-      for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(0, j, r, n)], B.mu[r] = x[L.MU(0, j, r, n)];
-      B.sd = x[L.SD(0, j, n)];
-      B.el = x[L.EL(0, j, n)];
-      f_part += S.rho * B.el;
-      obs_residual(S, j, p, B);
-      for (int r = 0; r < 4; ++r) c[L.YOBS(0, j, r, n)] = B.c[r];
-      if (!y) continue;
-      double y1 = y[L.YOBS(0, j, 0, n)], y2[2] = {y[L.YOBS(0, j, 1, n)], y[L.YOBS(0, j, 2, n)]}, y3 = y[L.YOBS(0, j, 3, n)];
-      double Ry[2] = {p.c * y2[0] - p.s * y2[1], p.s * y2[0] + p.c * y2[1]};
-      for (int r = 0; r < 4; ++r) {
-        const double* A = S.obsA[j][r];
-        gl[L.LAM(0, j, r, n)] = y1 * B.Atb[r] + A[0] * Ry[0] + A[1] * Ry[1] + 2.0 * y3 * (A[0] * B.u[0] + A[1] * B.u[1]);
-        gl[L.MU(0, j, r, n)] = -y1 * S.g[r] + S.G[r][0] * y2[0] + S.G[r][1] * y2[1];
-      }
-      gl[L.SD(0, j, n)] = -y1;
-      gl[L.EL(0, j, n)] = S.rho + y1;
-      g[0] += y1 * B.u[0];
-      g[1] += y1 * B.u[1];
-      g[2] += y2[0] * (-p.s * B.u[0] + p.c * B.u[1]) + y2[1] * (-p.c * B.u[0] - p.s * B.u[1]);
+      const double* og = OG + (size_t)(n * L.O + j) * 3;
+      g[0] += og[0], g[1] += og[1], g[2] += og[2];
     }
-    for (int o = 0; o < L.P; ++o) f_part += S.rho * x[L.PEL(o, n)];
-    if (y) {
-      for (int o = 0; o < L.P; ++o) {
-        const double* pg = PG + (size_t)(o * L.Mv + n) * 6;
-        g[0] += pg[0], g[1] += pg[1], g[2] += pg[2];
-      }
-      for (int q = 0; q < NZ; ++q) gl[L.Z(0, q, n)] = g[q];
+    for (int o = 0; o < L.P; ++o) {
+      const double* pg = PG + (size_t)(o * L.Mv + n) * 6;
+      g[0] += pg[0], g[1] += pg[1], g[2] += pg[2];
     }
+    for (int q = 0; q < NZ; ++q) gl[L.Z(0, q, n)] = g[q];
   }
   *f_out = cta_sum(ctx, f_part);
   *gdt_out = 0.0;
@@ -300,10 +382,42 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   double* HN = RW;                    // [N][28]
   double* GN = HN + (size_t)N * 28;   // [N][7]
   double* AJ = GN + (size_t)N * 7;    // [N][35]
+  double* PP = AJ + (size_t)N * 35;   // [N][25 + 5] cost-to-go
+  double* KK = PP + (size_t)N * 30;   // [N][2*5 + 2] gains
+  double* DZ = KK + (size_t)N * 12;   // [N][7] step
+  double* QD = DZ + (size_t)N * 7;    // [N][15] y-contracted second directional derivatives of the RK4 map
+  double* OB = QD + (size_t)N * 15;   // [N][O][9] obstacle Schur complements on the pose (6 sym + 3 grad)
+  // tasks (node, direction): e_i and e_i + e_j over the nonlinear inputs (psi, v, delta, a, w); x and y enter F linearly
+  for (int it = ctx.tid; it < (N - 1) * 15; it += ctx.nt) {
+    const int n = it / 15, k = it % 15;
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= k) ++i;
+    const int j = k - i * (i + 1) / 2;
+    double z[NZ], d[NZ] = {0, 0, 0, 0, 0, 0, 0};
+    for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
+    d[2 + i] = 1.0, d[2 + j] = 1.0;
+    Tay<true> F[5];
+    tay_rk4<true>(z, d, S.dt_mpc, S.wb, F);
+    double acc = 0;
+    for (int r = 0; r < 5; ++r) acc += y[L.YCOL(0, r, n)] * 2.0 * F[r].b;
+    QD[n * 15 + k] = acc;
+    if (i == j)
+      for (int r = 0; r < 5; ++r) AJ[(size_t)n * 35 + r * 7 + 2 + i] = F[r].a;
+  }
+  for (int it = ctx.tid; it < N * L.O; it += ctx.nt) {
+    const int n = it / L.O, j = it % L.O;
+    Pose p;
+    load_pose(L, x, 0, n, p);
+    double H6[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0};
+    obs_block_eliminate(L, S, W, 0, n, j, p, H6, g3, ok_shared);
+    double* ob = OB + (size_t)it * 9;
+    for (int q = 0; q < 6; ++q) ob[q] = H6[q];
+    for (int q = 0; q < 3; ++q) ob[6 + q] = g3[q];
+  }
+  cta_sync(ctx);
   for (int n = ctx.tid; n < N; n += ctx.nt) {
     double z[NZ];
     for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
-    Pose p = {z[0], z[1], z[2], cos(z[2]), sin(z[2])};
     double H[28], g[NZ];
     for (int q = 0; q < 28; ++q) H[q] = 0;
     for (int q = 0; q < NZ; ++q) H[sym(q, q)] = W.sig[L.Z(0, q, n)], g[q] = W.gphi[L.Z(0, q, n)];
@@ -311,15 +425,19 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
     H[sym(3, 3)] += 2.0 * z[6] * z[6], H[sym(6, 6)] += 2.0 * z[3] * z[3], H[sym(6, 3)] += 4.0 * z[3] * z[6];
     H[sym(4, 4)] += 2.0, H[sym(5, 5)] += 2.0;
     if (n < N - 1) {
-      Jet<true> F[5];
-      jet_rk4<true>(z, S.dt_mpc, S.wb, F);
-      for (int r = 0; r < 5; ++r) {
-        double yr = y[L.YCOL(0, r, n)];
-        for (int q = 0; q < 28; ++q) H[q] -= yr * F[r].h[q];
-        for (int q = 0; q < NZ; ++q) AJ[(size_t)n * 35 + r * 7 + q] = F[r].g[q];
-      }
+      const double* qd = QD + n * 15;
+      for (int i = 0; i < 5; ++i)
+        for (int j = 0; j <= i; ++j) {
+          const double hij = i == j ? qd[sym(i, i)] : 0.5 * (qd[sym(i, j)] - qd[sym(i, i)] - qd[sym(j, j)]);
+          H[sym(2 + i, 2 + j)] -= hij;
+        }
+      for (int r = 0; r < 5; ++r) AJ[(size_t)n * 35 + r * 7 + 0] = r == 0 ? 1.0 : 0.0, AJ[(size_t)n * 35 + r * 7 + 1] = r == 1 ? 1.0 : 0.0;
     }
-    for (int j = 0; j < L.O; ++j) obs_block_eliminate(L, S, W, 0, n, j, p, H, g, ok_shared);
+    for (int j = 0; j < L.O; ++j) {
+      const double* ob = OB + (size_t)(n * L.O + j) * 9;
+      for (int q = 0; q < 6; ++q) H[q] += ob[q];
+      for (int q = 0; q < 3; ++q) g[q] += ob[6 + q];
+    }
     for (int o = 0; o < L.P; ++o) {
       const double* ph = W.PH + (size_t)(o * L.Mv + n) * 27;
       for (int r = 0; r < 3; ++r) {
@@ -333,86 +451,108 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   cta_sync(ctx);
   prof_mark(ctx, 3);
   // Riccati recursion (state 5, control 2), serial over the stages: thread 0
-  double* PP = AJ + (size_t)N * 35;   // [N][25 + 5] cost-to-go
-  double* KK = PP + (size_t)N * 30;   // [N][2*5 + 2] gains
-  double* DZ = KK + (size_t)N * 12;   // [N][7] step
-  if (ctx.tid == 0) {
-    double P[25], pv[5];
-    for (int q = 0; q < 25; ++q) P[q] = 0;
-    for (int q = 0; q < 5; ++q) pv[q] = 0;
+  // warp 0, lanes over the matrix entries; per stage: PA = P A, Q += A'PA, gains, cost-to-go
+  double* SC = OB + (size_t)N * L.O * 9;  // [112] stage scratch: PA[35], Pr[5], Q[49], qv[7], K[12]
+  if (ctx.tid < 32) {
+    double *PA = SC, *Pr = SC + 35, *Q = SC + 40, *qv = SC + 89;
     for (int n = N - 1; n >= 0; --n) {
       const double* H = HN + (size_t)n * 28;
       const double* g = GN + (size_t)n * 7;
-      double Q[7][7], qv[7];
-      for (int r = 0; r < 7; ++r) {
-        qv[r] = g[r];
-        for (int m = 0; m < 7; ++m) Q[r][m] = H[sym(r, m)];
-      }
+      const double* A = AJ + (size_t)n * 35;
+      const double* Pn = PP + (size_t)(n + 1) * 30;  // cost-to-go of the next stage (not read for n = N-1)
+      double* K = KK + (size_t)n * 12;
       if (n < N - 1) {
-        // next state dz' = A w - r ; cost-to-go 1/2 dz' P dz' + pv dz'
-        const double* A = AJ + (size_t)n * 35;
-        double PA[5][7], Pr[5];
-        for (int r = 0; r < 5; ++r) {
-          double cr = 0;
-          for (int m = 0; m < 5; ++m) cr += P[r * 5 + m] * W.c[L.YCOL(0, m, n)];
-          Pr[r] = pv[r] - cr;  // P (-r) + pv
-          for (int q = 0; q < 7; ++q) {
-            double s = 0;
-            for (int m = 0; m < 5; ++m) s += P[r * 5 + m] * A[m * 7 + q];
-            PA[r][q] = s;
+        OBCA_LANES(lane) {
+          for (int e = lane; e < 40; e += 32) {
+            if (e < 35) {
+              const int r = e / 7, q = e % 7;
+              double sacc = 0;
+              for (int m = 0; m < 5; ++m) sacc += Pn[r * 5 + m] * A[m * 7 + q];
+              PA[e] = sacc;
+            } else {
+              const int r = e - 35;
+              double cr = 0;
+              for (int m = 0; m < 5; ++m) cr += Pn[r * 5 + m] * W.c[L.YCOL(0, m, n)];
+              Pr[r] = Pn[25 + r] - cr;  // P (-r) + pv
+            }
           }
         }
-        for (int r = 0; r < 7; ++r) {
-          for (int q = 0; q < 7; ++q) {
-            double s = 0;
-            for (int m = 0; m < 5; ++m) s += A[m * 7 + r] * PA[m][q];
-            Q[r][q] += s;
+        OBCA_WARP_SYNC();
+      }
+      OBCA_LANES(lane) {
+        for (int e = lane; e < 56; e += 32) {
+          if (e < 49) {
+            const int r = e / 7, q = e % 7;
+            double sacc = H[sym(r, q)];
+            if (n < N - 1)
+              for (int m = 0; m < 5; ++m) sacc += A[m * 7 + r] * PA[m * 7 + q];
+            Q[e] = sacc;
+          } else {
+            const int r = e - 49;
+            double sacc = g[r];
+            if (n < N - 1)
+              for (int m = 0; m < 5; ++m) sacc += A[m * 7 + r] * Pr[m];
+            qv[r] = sacc;
           }
-          double s = 0;
-          for (int m = 0; m < 5; ++m) s += A[m * 7 + r] * Pr[m];
-          qv[r] += s;
         }
       }
+      OBCA_WARP_SYNC();
       // eliminate the control (rows/cols 5,6): F = Q_uu must be positive definite
-      double f00 = Q[5][5], f01 = Q[5][6], f11 = Q[6][6], det = f00 * f11 - f01 * f01;
+      double f00 = Q[5 * 7 + 5], f01 = Q[5 * 7 + 6], f11 = Q[6 * 7 + 6], det = f00 * f11 - f01 * f01;
       if (!(f00 > 0) || !(det > 1e-14 * f00 * f11)) {
         *ok_shared = 0;
         f00 = f11 = 1.0, f01 = 0.0, det = 1.0;
       }
-      double i00 = f11 / det, i01 = -f01 / det, i11 = f00 / det;
-      double* K = KK + (size_t)n * 12;
-      for (int q = 0; q < 5; ++q) {
-        K[q] = -(i00 * Q[5][q] + i01 * Q[6][q]);
-        K[5 + q] = -(i01 * Q[5][q] + i11 * Q[6][q]);
+      const double i00 = f11 / det, i01 = -f01 / det, i11 = f00 / det;
+      OBCA_LANES(lane) {
+        if (lane < 12) {
+          const int q = lane % 6, row = lane / 6;  // q = 5: the constant term
+          const double b5 = q < 5 ? Q[5 * 7 + q] : qv[5], b6 = q < 5 ? Q[6 * 7 + q] : qv[6];
+          const double kv = row == 0 ? -(i00 * b5 + i01 * b6) : -(i01 * b5 + i11 * b6);
+          K[q < 5 ? row * 5 + q : 10 + row] = kv;
+        }
       }
-      K[10] = -(i00 * qv[5] + i01 * qv[6]);
-      K[11] = -(i01 * qv[5] + i11 * qv[6]);
-      for (int r = 0; r < 5; ++r) {
-        for (int q = 0; q < 5; ++q) P[r * 5 + q] = Q[r][q] + Q[r][5] * K[q] + Q[r][6] * K[5 + q];
-        pv[r] = qv[r] + Q[r][5] * K[10] + Q[r][6] * K[11];
+      OBCA_WARP_SYNC();
+      OBCA_LANES(lane) {
+        if (lane < 30) {
+          double* Po = PP + (size_t)n * 30;
+          if (lane < 25) {
+            const int r = lane / 5, q = lane % 5;
+            Po[lane] = Q[r * 7 + q] + Q[r * 7 + 5] * K[q] + Q[r * 7 + 6] * K[5 + q];
+          } else {
+            const int r = lane - 25;
+            Po[lane] = qv[r] + Q[r * 7 + 5] * K[10] + Q[r * 7 + 6] * K[11];
+          }
+        }
       }
-      for (int q = 0; q < 25; ++q) PP[(size_t)n * 30 + q] = P[q];
-      for (int q = 0; q < 5; ++q) PP[(size_t)n * 30 + 25 + q] = pv[q];
+      OBCA_WARP_SYNC();
     }
     // forward pass
-    double dz[5];
-    for (int q = 0; q < 5; ++q) dz[q] = -W.c[L.YINIT(0, q)];
+    OBCA_LANES(lane) {
+      if (lane < 5) DZ[lane] = -W.c[L.YINIT(0, lane)];
+    }
+    OBCA_WARP_SYNC();
     for (int n = 0; n < N; ++n) {
       const double* K = KK + (size_t)n * 12;
-      double du0 = K[10], du1 = K[11];
-      for (int q = 0; q < 5; ++q) du0 += K[q] * dz[q], du1 += K[5 + q] * dz[q];
       double* w = DZ + (size_t)n * 7;
-      for (int q = 0; q < 5; ++q) w[q] = dz[q];
-      w[5] = du0, w[6] = du1;
+      OBCA_LANES(lane) {
+        if (lane < 2) {
+          double du = K[10 + lane];
+          for (int q = 0; q < 5; ++q) du += K[lane * 5 + q] * w[q];
+          w[5 + lane] = du;
+        }
+      }
+      OBCA_WARP_SYNC();
       if (n < N - 1) {
         const double* A = AJ + (size_t)n * 35;
-        double nz[5];
-        for (int r = 0; r < 5; ++r) {
-          double s = -W.c[L.YCOL(0, r, n)];
-          for (int q = 0; q < 7; ++q) s += A[r * 7 + q] * w[q];
-          nz[r] = s;
+        OBCA_LANES(lane) {
+          if (lane < 5) {
+            double sacc = -W.c[L.YCOL(0, lane, n)];
+            for (int q = 0; q < 7; ++q) sacc += A[lane * 7 + q] * w[q];
+            w[7 + lane] = sacc;  // dz of stage n+1
+          }
         }
-        for (int q = 0; q < 5; ++q) dz[q] = nz[q];
+        OBCA_WARP_SYNC();
       }
     }
   }
@@ -443,6 +583,6 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   return 1;
 }
 
-inline size_t mpc_work_doubles(const Lay& L) { return (size_t)L.Mv * (28 + 7 + 35 + 30 + 12 + 7) + 16; }
+inline size_t mpc_work_doubles(const Lay& L) { return (size_t)(L.Mv + 1) * (28 + 7 + 35 + 30 + 12 + 7 + 15 + 9 * L.O) + 128; }
 
 }  // namespace obca
