@@ -451,24 +451,32 @@ OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
 constexpr int NSW = 2720;  // shared-memory doubles per warp of the null-space phase
 
 // apply Q or Q' to the strided vector v[q * stride], q < 35 (reflectors in the shared-memory QR matrix)
-OBCA_HD void apply_q_strided(const double* Mq, const double* tau, const double* piv, int rk, double* v, int stride, bool transpose) {
+OBCA_HD void apply_q_strided(const double* __restrict__ Mq, const double* __restrict__ tau, const double* __restrict__ piv, int rk,
+                             double* __restrict__ v, int stride, bool transpose) {
   OBCA_ASSUME_SHARED(Mq);
   OBCA_ASSUME_SHARED(tau);
   OBCA_ASSUME_SHARED(piv);
   OBCA_ASSUME_SHARED(v);
   for (int jj = 0; jj < rk; ++jj) {
     const int i = transpose ? jj : rk - 1 - jj;
-    const double* u = Mq + (int)piv[i];
-    double s0 = v[i * stride], s1 = 0.0;
+    const double* __restrict__ u = Mq + (int)piv[i];
+    double s0 = v[i * stride], s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int r = i + 1;
-    for (; r + 1 < NW; r += 2) {  // two accumulators: halves the dependent FP64 chain
-      s0 += u[r * NC] * v[r * stride];
-      s1 += u[(r + 1) * NC] * v[(r + 1) * stride];
+    for (; r + 3 < NW; r += 4) {  // four accumulators: loads issue back to back, the dependent FP64 chain is a quarter as long
+      const double u0 = u[r * NC], u1 = u[(r + 1) * NC], u2 = u[(r + 2) * NC], u3 = u[(r + 3) * NC];
+      const double v0 = v[r * stride], v1 = v[(r + 1) * stride], v2 = v[(r + 2) * stride], v3 = v[(r + 3) * stride];
+      s0 += u0 * v0, s1 += u1 * v1, s2 += u2 * v2, s3 += u3 * v3;
     }
-    if (r < NW) s0 += u[r * NC] * v[r * stride];
-    const double s = (s0 + s1) * tau[i];
+    for (; r < NW; ++r) s0 += u[r * NC] * v[r * stride];
+    const double s = ((s0 + s1) + (s2 + s3)) * tau[i];
     v[i * stride] -= s;
-    for (r = i + 1; r < NW; ++r) v[r * stride] -= s * u[r * NC];
+    r = i + 1;
+    for (; r + 3 < NW; r += 4) {  // loads first, then the stores: no store -> load serialisation
+      const double u0 = u[r * NC], u1 = u[(r + 1) * NC], u2 = u[(r + 2) * NC], u3 = u[(r + 3) * NC];
+      const double v0 = v[r * stride], v1 = v[(r + 1) * stride], v2 = v[(r + 2) * stride], v3 = v[(r + 3) * stride];
+      v[r * stride] = v0 - s * u0, v[(r + 1) * stride] = v1 - s * u1, v[(r + 2) * stride] = v2 - s * u2, v[(r + 3) * stride] = v3 - s * u3;
+    }
+    for (; r < NW; ++r) v[r * stride] -= s * u[r * NC];
   }
 }
 
@@ -554,6 +562,7 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     }
   }
   OBCA_WARP_SYNC();
+  prof_mark(ctx, 16);
   // Householder QR with rank test (LAPACK dgeqr2 reflector convention: v[rk] = 1 implicit)
   int rk = 0, ndrop = 0, nem = 0;
   for (int j = 0; j < nr; ++j) {
@@ -634,25 +643,35 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
       continue;
     }
     if (alpha > 0) beta = -beta;
-    const double t = (beta - alpha) / beta;
+    const double ibeta = 1.0 / beta;
+    const double t = (beta - alpha) * ibeta;
     const double sc = 1.0 / (alpha - beta);
     OBCA_LANES(lane) {
       for (int q = rk + 1 + lane; q < NW; q += 32) Mq[q * NC + j] *= sc;
-      if (lane == 0) tau[rk] = t, piv[rk] = (double)j, Mq[rk * NC + j] = beta;
+      if (lane == 0) tau[rk] = t, piv[rk] = (double)j, Mq[rk * NC + j] = beta, wred[rk] = ibeta;
     }
     OBCA_WARP_SYNC();
     OBCA_LANES(lane) {
       for (int cc = j + 1 + lane; cc < nr; cc += 32) {
-        double a0 = Mq[rk * NC + cc], a1 = 0.0;
+        const double* uj = Mq + j;
+        double* vc = Mq + cc;
+        double a0 = vc[rk * NC], a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int q = rk + 1;
-        for (; q + 1 < NW; q += 2) {
-          a0 += Mq[q * NC + j] * Mq[q * NC + cc];
-          a1 += Mq[(q + 1) * NC + j] * Mq[(q + 1) * NC + cc];
+        for (; q + 3 < NW; q += 4) {
+          const double u0 = uj[q * NC], u1 = uj[(q + 1) * NC], u2 = uj[(q + 2) * NC], u3 = uj[(q + 3) * NC];
+          const double v0 = vc[q * NC], v1 = vc[(q + 1) * NC], v2 = vc[(q + 2) * NC], v3 = vc[(q + 3) * NC];
+          a0 += u0 * v0, a1 += u1 * v1, a2 += u2 * v2, a3 += u3 * v3;
         }
-        if (q < NW) a0 += Mq[q * NC + j] * Mq[q * NC + cc];
-        const double sacc = (a0 + a1) * t;
-        Mq[rk * NC + cc] -= sacc;
-        for (q = rk + 1; q < NW; ++q) Mq[q * NC + cc] -= sacc * Mq[q * NC + j];
+        for (; q < NW; ++q) a0 += uj[q * NC] * vc[q * NC];
+        const double sacc = ((a0 + a1) + (a2 + a3)) * t;
+        vc[rk * NC] -= sacc;
+        q = rk + 1;
+        for (; q + 3 < NW; q += 4) {  // column cc != column j: load everything first, then store
+          const double u0 = uj[q * NC], u1 = uj[(q + 1) * NC], u2 = uj[(q + 2) * NC], u3 = uj[(q + 3) * NC];
+          const double v0 = vc[q * NC], v1 = vc[(q + 1) * NC], v2 = vc[(q + 2) * NC], v3 = vc[(q + 3) * NC];
+          vc[q * NC] = v0 - sacc * u0, vc[(q + 1) * NC] = v1 - sacc * u1, vc[(q + 2) * NC] = v2 - sacc * u2, vc[(q + 3) * NC] = v3 - sacc * u3;
+        }
+        for (; q < NW; ++q) vc[q * NC] -= sacc * uj[q * NC];
       }
     }
     OBCA_WARP_SYNC();
@@ -663,34 +682,66 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     *ok = 0;
     np = NP;
   }
+  prof_mark(ctx, 17);
   // T columns (one lane per column): 0..6 xi, 7..7+NP-1 p, IDT dt; s0
   OBCA_LANES(lane) {
     if (lane == 0) em[0] = (double)nem, QRg[QR_META + 0] = (double)rk, QRg[QR_META + 1] = (double)nr, QRg[QR_META + 2] = (double)ndrop;
     if (lane < 9 + NP) {
-      int col = lane;
-      double* v = col < 7 ? T + col : (col == 7 ? T + IDT : (col == 8 ? s0 : T + 7 + (col - 9)));
-      int stride = col == 8 ? 1 : NRED;
+      // The column lives in registers (all indices below are compile-time constants after unrolling): the shared-memory
+      // pipe, shared by the 8 warps of the CTA, then only serves the broadcast loads of R and of the reflectors.
+      const int col = lane;
+      double v[NW];
+#pragma unroll
+      for (int q = 0; q < NW; ++q) v[q] = 0.0;
       if (col < 9) {
-        // b = -G0[:,col] (col < 7), -gd (col 7), -r (col 8); solve R' w = b on the staircase; v = Q [w; 0]
-        for (int ii = 0; ii < rk; ++ii) {
-          int j = (int)piv[ii];
-          double bv = col < 7 ? -G0[j * 7 + col] : (col == 7 ? -gd[j] : -rr[j]);
-          for (int m = 0; m < ii; ++m) bv -= Mq[m * NC + j] * v[m * stride];
-          v[ii * stride] = bv / Mq[ii * NC + j];
+        // b = -G0[:,col] (col < 7), -gd (col 7), -r (col 8); forward substitution R' w = b on the staircase
+#pragma unroll
+        for (int ii = 0; ii < NW; ++ii) {
+          if (ii < rk) {
+            const int j = (int)piv[ii];
+            const double* Rj = Mq + j;
+            double b0 = col < 7 ? -G0[j * 7 + col] : (col == 7 ? -gd[j] : -rr[j]), b1 = 0.0;
+#pragma unroll
+            for (int m = 0; m + 1 < ii; m += 2) b0 -= Rj[m * NC] * v[m], b1 -= Rj[(m + 1) * NC] * v[m + 1];
+            if (ii & 1) b0 -= Rj[(ii - 1) * NC] * v[ii - 1];
+            v[ii] = (b0 + b1) * wred[ii];
+          }
         }
-        for (int q = rk; q < NW; ++q) v[q * stride] = 0;
-        apply_q_strided(Mq, tau, piv, rk, v, stride, false);
       } else {
-        int jn = col - 9;
-        for (int q = 0; q < NW; ++q) v[q * stride] = 0;
-        if (jn < np) {
-          v[(rk + jn) * stride] = 1.0;
-          apply_q_strided(Mq, tau, piv, rk, v, stride, false);
+        const int jn = col - 9;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) v[q] = (jn < np && q == rk + jn) ? 1.0 : 0.0;
+      }
+      if (col < 9 || col - 9 < np) {
+        // v <- H_0 ... H_{rk-1} v ; reflector i = (1, u_{i+1..34}) stored below the staircase of its pivot column
+#pragma unroll
+        for (int i = NW - 1; i >= 0; --i) {
+          if (i < rk) {
+            const double* u = Mq + (int)piv[i];
+            double a0 = v[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int r = i + 1; r < NW; ++r) {
+              const double ur = u[r * NC];
+              if (((r - i - 1) & 3) == 0) a0 += ur * v[r];
+              else if (((r - i - 1) & 3) == 1) a1 += ur * v[r];
+              else if (((r - i - 1) & 3) == 2) a2 += ur * v[r];
+              else a3 += ur * v[r];
+            }
+            const double sacc = ((a0 + a1) + (a2 + a3)) * tau[i];
+            v[i] -= sacc;
+#pragma unroll
+            for (int r = i + 1; r < NW; ++r) v[r] -= sacc * u[r * NC];
+          }
         }
       }
+      double* vo = col < 7 ? T + col : (col == 7 ? T + IDT : (col == 8 ? s0 : T + 7 + (col - 9)));
+      const int stride = col == 8 ? 1 : NRED;
+#pragma unroll
+      for (int q = 0; q < NW; ++q) vo[q * stride] = v[q];
     }
   }
   OBCA_WARP_SYNC();
+  prof_mark(ctx, 18);
   // QR record and T map to global memory (multiplier recovery, Riccati dynamics, primal expansion)
   double* Tg = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
   OBCA_LANES(lane) {
@@ -699,6 +750,7 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     for (int q = lane; q < NW * NRED + NW; q += 32) Tg[q] = T[q];  // T and s0 are contiguous
   }
   OBCA_WARP_SYNC();
+  prof_mark(ctx, 19);
   // projected stage Hessian M = Tt' H Tt + dt cross terms, gradient m = Tt'(H s0 + gn) + e_dt hd's0
   double* HT = Mq;                    // [42][NRED]   (the QR matrix is no longer needed in shared memory)
   double* hs0 = HT + NS * NRED;       // [42]
@@ -760,6 +812,7 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     }
   }
   OBCA_WARP_SYNC();
+  prof_mark(ctx, 20);
 }
 
 // All blocks in parallel (one warp each); blocks whose Jacobian is rank deficient hand implied rows to the previous

@@ -354,11 +354,12 @@ class ObcaSolver:
         return {k: int(buf[i]) for i, k in enumerate(names)}
 
     PHASES = ["eval_pairs", "eval_nodes", "pair_eliminate", "node_assemble", "nullspace", "cross", "riccati_bwd", "riccati_fwd",
-              "expand+residual", "multipliers", "local_backsub", "ipm_vector_ops", "ric_assemble", "ric_products", "ric_cholesky", "ric_ksolve"]
+              "expand+residual", "multipliers", "local_backsub", "ipm_vector_ops", "ric_assemble", "ric_products", "ric_cholesky", "ric_ksolve",
+              "ns_setup", "ns_qr", "ns_tcols", "ns_store", "ns_project", "ns_spare"]
 
     def debug_profile(self):
-        buf = (ctypes.c_int64 * 16)()
-        self._check(self.lib.obca_debug_profile(self.handle, buf, 16))
+        buf = (ctypes.c_int64 * 22)()
+        self._check(self.lib.obca_debug_profile(self.handle, buf, 22))
         return {k: int(buf[i]) for i, k in enumerate(self.PHASES)}
 
     def debug_get_iterate(self, b=0):
