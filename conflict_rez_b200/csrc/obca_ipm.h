@@ -4,6 +4,9 @@
 
 namespace obca {
 
+constexpr int VW = 8;  // elements per thread and batch in the flat passes: enough independent loads in flight to cover DRAM latency
+
+
 struct Shared {   // lives in shared memory on the device
   int ok;      // kkt_solve: inertia / factorisation flag (must be followed by `again`)
   int again;   // interval_nullspace: another pass needed
@@ -81,33 +84,6 @@ OBCA_HDN void push_into_bounds(const Ctx& ctx, const Lay& L, const double* xL, c
   cta_sync(ctx);
 }
 
-// barrier objective at xv given f(xv); returns +inf outside the bounds
-OBCA_HDN double barrier_obj(const Ctx& ctx, const Lay& L, const double* xL, const double* xU, const double* xv, double f, double mu, double kd) {
-  double s = 0;
-  int bad = 0;
-#pragma unroll 4
-  for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
-    double lo = xL[q], hi = xU[q], v = xv[q];
-    bool hl = lo > -INFINITY, hu = hi < INFINITY;
-    if (hl) {
-      double gp = v - lo;
-      if (gp <= 0) bad = 1;
-      else s -= log(gp);
-      if (!hu) s += kd * gp;
-    }
-    if (hu) {
-      double gp = hi - v;
-      if (gp <= 0) bad = 1;
-      else s -= log(gp);
-      if (!hl) s += kd * gp;
-    }
-  }
-  double tot = cta_sum(ctx, s);
-  double anybad = cta_max(ctx, (double)bad);
-  if (anybad > 0) return INFINITY;
-  return f + mu * tot;
-}
-
 template <int MODE>
 OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
                         const double* xU, const Scratch& W, double* RW, Shared* sh, Result* res) {
@@ -144,17 +120,17 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     // ---- error measures at the current iterate (c, gl, f are up to date)
     double e_du = 0, e_c = 0, e_c1 = 0, s_y = 0, s_z = 0, cmax0 = 0, cmaxmu_lo = INFINITY, cmaxmu_hi = 0;
     double s_log = 0, s_gap = 0;  // barrier pieces: phi = f + mu (-sum log gap + kappa_d sum one-sided gap)
-    for (int q0 = ctx.tid; q0 < L.nx; q0 += 4 * ctx.nt) {
-      double lo[4], hi[4], xv[4], zl[4], zu[4], gq[4];
+    for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
+      double lo[VW], hi[VW], xv[VW], zl[VW], zu[VW], gq[VW];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < VW; ++u) {
         int q = q0 + u * ctx.nt;
         bool in = q < L.nx;
         lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
         xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0, gq[u] = in ? W.gl[q] : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < VW; ++u) {
         e_du = fmax(e_du, fabs(gq[u] - zl[u] + zu[u]));
         bool hl = lo[u] > -INFINITY, hu = hi[u] < INFINITY;
         if (hl) {
@@ -239,17 +215,17 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     double dw = 0.0;
     bool first = true, have = false;
     for (;;) {
-      for (int q0 = ctx.tid; q0 < L.nx; q0 += 4 * ctx.nt) {
-        double lo[4], hi[4], xv[4], zl[4], zu[4], gq[4];
+      for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
+        double lo[VW], hi[VW], xv[VW], zl[VW], zu[VW], gq[VW];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < VW; ++u) {
           int q = q0 + u * ctx.nt;
           bool in = q < L.nx;
           lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
           xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0, gq[u] = in ? W.gl[q] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < VW; ++u) {
           int q = q0 + u * ctx.nt;
           bool hl = lo[u] > -INFINITY, hu = hi[u] < INFINITY;
           double sg = dw, gp = gq[u];
@@ -287,10 +263,10 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     if (dw > 0) dw_last = dw;
     // ---- dz, fraction to the boundary, directional derivative of the barrier objective
     double a_pr = 1.0, a_du = 1.0, dphi = 0, rel = 0;
-    for (int q0 = ctx.tid; q0 < L.nx; q0 += 4 * ctx.nt) {
-      double lo[4], hi[4], xv[4], zl[4], zu[4], gq[4], dd[4];
+    for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
+      double lo[VW], hi[VW], xv[VW], zl[VW], zu[VW], gq[VW], dd[VW];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < VW; ++u) {
         int q = q0 + u * ctx.nt;
         bool in = q < L.nx;
         lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
@@ -298,7 +274,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
         gq[u] = in ? W.gphi[q] : 0.0, dd[u] = in ? W.dx[q] : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < VW; ++u) {
         double d = dd[u];
         rel = fmax(rel, fabs(d) / (1.0 + fabs(xv[u])));
         if (lo[u] > -INFINITY) {
@@ -370,19 +346,45 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     } else
       tiny_last = false;
     while (alpha >= a_min && !accepted) {
-      {
-        const double* __restrict__ rx = W.x;
-        const double* __restrict__ rdx = W.dx;
-        double* __restrict__ wxt = W.xt;
-#pragma unroll 4
-        for (int q = ctx.tid; q < L.nx; q += ctx.nt) wxt[q] = rx[q] + alpha * rdx[q];
+      // trial point and its barrier terms in one pass
+      double sbar = 0;
+      int bad = 0;
+      for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
+        double lo[VW], hi[VW], xv[VW], dd[VW];
+#pragma unroll
+        for (int u = 0; u < VW; ++u) {
+          int q = q0 + u * ctx.nt;
+          bool in = q < L.nx;
+          lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY, xv[u] = in ? W.x[q] : 0.0, dd[u] = in ? W.dx[q] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < VW; ++u) {
+          int q = q0 + u * ctx.nt;
+          const double v = xv[u] + alpha * dd[u];
+          if (q < L.nx) W.xt[q] = v;
+          const bool hl = lo[u] > -INFINITY, hu = hi[u] < INFINITY;
+          if (hl) {
+            const double gp = v - lo[u];
+            if (gp <= 0) bad = 1;
+            else sbar -= log(gp);
+            if (!hu) sbar += o.kappa_d * gp;
+          }
+          if (hu) {
+            const double gp = hi[u] - v;
+            if (gp <= 0) bad = 1;
+            else sbar -= log(gp);
+            if (!hl) sbar += o.kappa_d * gp;
+          }
+        }
       }
       cta_sync(ctx);
       model_eval<MODE>(ctx, L, S, W, W.xt, nullptr, W.ct, nullptr, &ft, &gdt_t);
       double tht = 0;
+#pragma unroll 4
       for (int q = ctx.tid; q < L.ny; q += ctx.nt) tht += fabs(W.ct[q]);
       tht = cta_sum(ctx, tht);
-      double pht = barrier_obj(ctx, L, xL, xU, W.xt, ft, mu, o.kappa_d);
+      sbar = cta_sum(ctx, sbar);
+      const double pht = cta_max(ctx, (double)bad) > 0 ? INFINITY : ft + mu * sbar;
       bool okp = finite_d(pht) && finite_d(tht) && tht <= theta_max;
       if (okp) {
         int nf = sh->filt_n;
@@ -418,17 +420,17 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       break;
     }
     // ---- accept the trial point (dz is recomputed from dx; x + alpha dx reproduces the trial point bit for bit)
-    for (int q0 = ctx.tid; q0 < L.nx; q0 += 4 * ctx.nt) {
-      double lo[4], hi[4], xv[4], zl[4], zu[4], dd[4];
+    for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
+      double lo[VW], hi[VW], xv[VW], zl[VW], zu[VW], dd[VW];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < VW; ++u) {
         int q = q0 + u * ctx.nt;
         bool in = q < L.nx;
         lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
         xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0, dd[u] = in ? W.dx[q] : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < VW; ++u) {
         int q = q0 + u * ctx.nt;
         if (q >= L.nx) continue;
         double d = dd[u], xn = xv[u] + alpha * d;
