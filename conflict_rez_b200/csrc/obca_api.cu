@@ -184,8 +184,8 @@ OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, const Lay& L, con
   carve_iterate(W, L, A.iter + (size_t)b * A.it_stride);
   carve_work(W, L, A.work + (size_t)slot * A.wk_stride);
   if (A.mode == 0) {
-    if (L.mode == 0) ipm_solve<0>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, sh, A.res + b);
-    else ipm_solve<1>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, sh, A.res + b);
+    if (L.mode == 0) ipm_solve<0>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, A.rw_stride, sh, A.res + b);
+    else ipm_solve<1>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, A.rw_stride, sh, A.res + b);
     return;
   }
   double f, gdt;
@@ -456,7 +456,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
 #endif
   int B = h->dims.batch;
   if (dev_alloc((void**)&h->d_L, sizeof(Lay)) || dev_alloc((void**)&h->d_S, sizeof(Stat)) || dev_alloc((void**)&h->d_tube, tube.size() * 8) ||
-      dev_alloc((void**)&h->d_xL, L.nx * 8) || dev_alloc((void**)&h->d_xU, L.nx * 8) || dev_alloc((void**)&h->d_iter, (size_t)B * h->it_stride * 8) ||
+      dev_alloc((void**)&h->d_xL, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_xU, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_iter, (size_t)B * h->it_stride * 8) ||
       dev_alloc((void**)&h->d_work, (size_t)h->slots * h->wk_stride * 8) || dev_alloc((void**)&h->d_rw, (size_t)h->slots * h->rw_stride * 8) ||
       dev_alloc((void**)&h->d_res, (size_t)B * sizeof(Result)) || dev_alloc((void**)&h->d_counter, sizeof(int)) ||
       dev_alloc((void**)&h->d_prof, (size_t)h->slots * (NPROF + 1) * sizeof(long long)))

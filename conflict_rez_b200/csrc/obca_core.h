@@ -240,16 +240,20 @@ struct Scratch {
   double* init_pose;  // [V][3]
 };
 
+// vector lengths are padded to an even number of doubles: every flat vector starts 16-byte aligned, which the bulk
+// copies (TMA) of the staged passes need, and may be read one element past its end
+OBCA_HD size_t ev(size_t n) { return (n + 1) & ~(size_t)1; }
+
 // per-instance iterate (kept for every instance of the batch): x, zL, zU (x-layout), y (y-layout), init pose
 inline size_t iterate_doubles(const Lay& L) {
   size_t par = L.mode == 1 ? 5 + (size_t)3 * L.Mv * (1 + L.P) : (size_t)L.V * 3;  // init poses, or MPC parameters
-  return 3 * (size_t)L.nx + (size_t)L.ny + par + 8;
+  return ev(3 * ev(L.nx) + ev(L.ny) + par + 8);
 }
 
 // per-slot work area (one per resident CTA)
 inline size_t work_doubles(const Lay& L) {
   size_t n = 0;
-  n += 10 * (size_t)L.nx + 4 * (size_t)L.ny;
+  n += 10 * ev(L.nx) + 4 * ev(L.ny);
   n += (size_t)L.V * L.Mv * L.O * 48;
   n += (size_t)L.P * L.Mv * (112 + 27 + 6);
   n += (size_t)L.V * L.Mv * (28 + 7 + 7);
@@ -258,32 +262,34 @@ inline size_t work_doubles(const Lay& L) {
   n += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
   n += (size_t)(L.Nmax + 1) * (L.nX * L.nX + L.nX);
   n += (size_t)(L.Nmax + 1) * L.nX + (size_t)L.Nmax * L.nU;
-  return n + 64;
+  return ev(n + 64);
 }
 
 OBCA_HD void carve_iterate(Scratch& W, const Lay& L, double* p) {
-  W.x = p, p += L.nx;
-  W.zL = p, p += L.nx;
-  W.zU = p, p += L.nx;
-  W.y = p, p += L.ny;
+  const size_t nx = ev(L.nx), ny = ev(L.ny);
+  W.x = p, p += nx;
+  W.zL = p, p += nx;
+  W.zU = p, p += nx;
+  W.y = p, p += ny;
   W.init_pose = p;
 }
 
 OBCA_HD void carve_work(Scratch& W, const Lay& L, double* p) {
-  W.dx = p, p += L.nx;
-  W.dzL = p, p += L.nx;
-  W.dzU = p, p += L.nx;
-  W.gl = p, p += L.nx;
-  W.gphi = p, p += L.nx;
-  W.sig = p, p += L.nx;
-  W.xt = p, p += L.nx;
-  W.dy = p, p += L.ny;
-  W.c = p, p += L.ny;
-  W.ct = p, p += L.ny;
-  W.bx = p, p += L.nx;
-  W.bzL = p, p += L.nx;
-  W.bzU = p, p += L.nx;
-  W.by = p, p += L.ny;
+  const size_t nx = ev(L.nx), ny = ev(L.ny);
+  W.dx = p, p += nx;
+  W.dzL = p, p += nx;
+  W.dzU = p, p += nx;
+  W.gl = p, p += nx;
+  W.gphi = p, p += nx;
+  W.sig = p, p += nx;
+  W.xt = p, p += nx;
+  W.dy = p, p += ny;
+  W.c = p, p += ny;
+  W.ct = p, p += ny;
+  W.bx = p, p += nx;
+  W.bzL = p, p += nx;
+  W.bzU = p, p += nx;
+  W.by = p, p += ny;
   W.XO = p, p += (size_t)L.V * L.Mv * L.O * 48;
   W.XP = p, p += (size_t)L.P * L.Mv * 112;
   W.PH = p, p += (size_t)L.P * L.Mv * 27;

@@ -12,6 +12,7 @@ struct Shared {   // lives in shared memory on the device
   int again;   // interval_nullspace: another pass needed
   int filt_n;
   double filt_theta[FILTER_MAX], filt_phi[FILTER_MAX];
+  unsigned long long bars[4];  // mbarriers of the staged flat passes
 };
 
 struct Counts {
@@ -20,6 +21,98 @@ struct Counts {
 };
 
 OBCA_HD bool finite_d(double v) { return v - v == 0.0; }
+
+// ------------------------------------------------------------------------------------------------
+// Flat passes over the primal-dual vectors.  The vectors of one instance (n ~ 9e4 doubles each) live in HBM; a pass
+// reads NA of them once.  With 8 warps per SM plain loads cannot keep enough bytes in flight to cover the DRAM latency,
+// so on the device the pass is staged: one thread issues 1-D bulk copies (TMA, cp.async.bulk) of the next tiles into the
+// shared-memory arena (free outside the KKT solve) while the CTA works on the current tile; completion is tracked by
+// mbarriers.  `body(q, v)` receives the NA loaded values of element q and writes its results straight to global memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int ST_TILE = 1024;  // elements per tile
+constexpr int ST_STAGES = 3;
+
+struct Stage {
+  double* buf;              // shared-memory arena (nullptr: no staging)
+  size_t cap;               // doubles available in it
+  unsigned long long* bar;  // ST_STAGES mbarriers in shared memory
+};
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned st_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  const unsigned a = st_smem(bar);
+  while (!done)
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+#endif
+
+template <int NA, class Body>
+OBCA_HD void flat_pass(const Ctx& ctx, const Stage& st, const double* const (&src)[NA], int n, Body&& body) {
+#if defined(__CUDA_ARCH__)
+  if (st.buf && st.cap >= (size_t)ST_STAGES * NA * ST_TILE && n >= 4 * ST_TILE && ctx.nt * 4 == ST_TILE) {
+    const int ntile = (n + ST_TILE - 1) / ST_TILE;
+    if (ctx.tid == 0) {
+      for (int k = 0; k < ST_STAGES; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem(st.bar + k)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic writes to the arena vs the bulk copies
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+      const int stage = t % ST_STAGES, start = t * ST_TILE;
+      const int cnt = n - start < ST_TILE ? n - start : ST_TILE;
+      const unsigned bytes = (unsigned)(((cnt + 1) & ~1) * 8);
+      const unsigned bar = st_smem(st.bar + stage);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * NA) : "memory");
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         st_smem(st.buf + (size_t)(stage * NA + a) * ST_TILE)),
+                     "l"(src[a] + start), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    if (ctx.tid == 0)
+      for (int t = 0; t < ST_STAGES - 1 && t < ntile; ++t) issue(t);
+    for (int t = 0; t < ntile; ++t) {
+      if (ctx.tid == 0 && t + ST_STAGES - 1 < ntile) issue(t + ST_STAGES - 1);  // its stage was released by the barrier below
+      st_wait(st.bar + t % ST_STAGES, (unsigned)((t / ST_STAGES) & 1));
+      const double* tb = st.buf + (size_t)(t % ST_STAGES) * NA * ST_TILE;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = ctx.tid + u * ctx.nt, q = t * ST_TILE + e;
+        if (q < n) {
+          double v[NA];
+#pragma unroll
+          for (int a = 0; a < NA; ++a) v[a] = tb[a * ST_TILE + e];
+          body(q, v);
+        }
+      }
+      __syncthreads();
+    }
+    if (ctx.tid == 0)
+      for (int k = 0; k < ST_STAGES; ++k) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(st_smem(st.bar + k)) : "memory");
+    __syncthreads();
+    return;
+  }
+#endif
+  (void)st;
+  for (int q0 = ctx.tid; q0 < n; q0 += VW * ctx.nt) {
+    double v[VW][NA];
+#pragma unroll
+    for (int u = 0; u < VW; ++u) {
+      const int q = q0 + u * ctx.nt;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) v[u][a] = q < n ? src[a][q] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < VW; ++u) {
+      const int q = q0 + u * ctx.nt;
+      if (q < n) body(q, v[u]);
+    }
+  }
+}
+
 
 // model dispatch: MODE 0 = collocation OBCA (obca_core.h / obca_kkt.h), MODE 1 = MPC (obca_mpc.h)
 template <int MODE>
@@ -86,7 +179,7 @@ OBCA_HDN void push_into_bounds(const Ctx& ctx, const Lay& L, const double* xL, c
 
 template <int MODE>
 OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
-                        const double* xU, const Scratch& W, double* RW, Shared* sh, Result* res) {
+                        const double* xU, const Scratch& W, double* RW, size_t rw_cap, Shared* sh, Result* res) {
   assume_scratch(W);
   OBCA_ASSUME_STATIC(L, S);
   OBCA_ASSUME_GLOBAL(xL), OBCA_ASSUME_GLOBAL(xU);
@@ -116,38 +209,32 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
   int n_acceptable = 0;
   int status = OBCA_MAXITER_EXCEEDED, it = 0;
   double dual_inf = 0, cviol = 0, compl0 = 0;
+  const Stage st = {RW, rw_cap, sh->bars};
   for (;;) {
     // ---- error measures at the current iterate (c, gl, f are up to date)
     double e_du = 0, e_c = 0, e_c1 = 0, s_y = 0, s_z = 0, cmax0 = 0, cmaxmu_lo = INFINITY, cmaxmu_hi = 0;
     double s_log = 0, s_gap = 0;  // barrier pieces: phi = f + mu (-sum log gap + kappa_d sum one-sided gap)
-    for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
-      double lo[VW], hi[VW], xv[VW], zl[VW], zu[VW], gq[VW];
-#pragma unroll
-      for (int u = 0; u < VW; ++u) {
-        int q = q0 + u * ctx.nt;
-        bool in = q < L.nx;
-        lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
-        xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0, gq[u] = in ? W.gl[q] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < VW; ++u) {
-        e_du = fmax(e_du, fabs(gq[u] - zl[u] + zu[u]));
-        bool hl = lo[u] > -INFINITY, hu = hi[u] < INFINITY;
+    {
+      const double* const src[6] = {xL, xU, W.x, W.zL, W.zU, W.gl};
+      flat_pass<6>(ctx, st, src, L.nx, [&](int, const double* v) {
+        const double lo = v[0], hi = v[1], xv = v[2], zl = v[3], zu = v[4], gq = v[5];
+        e_du = fmax(e_du, fabs(gq - zl + zu));
+        const bool hl = lo > -INFINITY, hu = hi < INFINITY;
         if (hl) {
-          double gp = xv[u] - lo[u], pr = gp * zl[u];
+          const double gp = xv - lo, pr = gp * zl;
           cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
-          s_z += zl[u];
+          s_z += zl;
           s_log -= log(gp);
           if (!hu) s_gap += gp;
         }
         if (hu) {
-          double gp = hi[u] - xv[u], pr = gp * zu[u];
+          const double gp = hi - xv, pr = gp * zu;
           cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
-          s_z += zu[u];
+          s_z += zu;
           s_log -= log(gp);
           if (!hl) s_gap += gp;
         }
-      }
+      });
     }
 #pragma unroll 4
     for (int q = ctx.tid; q < L.ny; q += ctx.nt) {
@@ -215,34 +302,26 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     double dw = 0.0;
     bool first = true, have = false;
     for (;;) {
-      for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
-        double lo[VW], hi[VW], xv[VW], zl[VW], zu[VW], gq[VW];
-#pragma unroll
-        for (int u = 0; u < VW; ++u) {
-          int q = q0 + u * ctx.nt;
-          bool in = q < L.nx;
-          lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
-          xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0, gq[u] = in ? W.gl[q] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < VW; ++u) {
-          int q = q0 + u * ctx.nt;
-          bool hl = lo[u] > -INFINITY, hu = hi[u] < INFINITY;
-          double sg = dw, gp = gq[u];
+      {
+        const double* const src[6] = {xL, xU, W.x, W.zL, W.zU, W.gl};
+        flat_pass<6>(ctx, st, src, L.nx, [&](int q, const double* v) {
+          const double lo = v[0], hi = v[1], xv = v[2], zl = v[3], zu = v[4];
+          const bool hl = lo > -INFINITY, hu = hi < INFINITY;
+          double sg = dw, gp = v[5];
           if (hl) {
-            double gpL = xv[u] - lo[u];
-            sg += zl[u] / gpL;
+            const double gpL = xv - lo;
+            sg += zl / gpL;
             gp -= mu / gpL;
             if (!hu) gp += o.kappa_d * mu;
           }
           if (hu) {
-            double gpU = hi[u] - xv[u];
-            sg += zu[u] / gpU;
+            const double gpU = hi - xv;
+            sg += zu / gpU;
             gp += mu / gpU;
             if (!hl) gp -= o.kappa_d * mu;
           }
-          if (q < L.nx) W.sig[q] = sg, W.gphi[q] = gp;
-        }
+          W.sig[q] = sg, W.gphi[q] = gp;
+        });
       }
       cta_sync(ctx);
       if (model_kkt<MODE>(ctx, L, S, W, RW, &sh->ok)) {
@@ -263,34 +342,25 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     if (dw > 0) dw_last = dw;
     // ---- dz, fraction to the boundary, directional derivative of the barrier objective
     double a_pr = 1.0, a_du = 1.0, dphi = 0, rel = 0;
-    for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
-      double lo[VW], hi[VW], xv[VW], zl[VW], zu[VW], gq[VW], dd[VW];
-#pragma unroll
-      for (int u = 0; u < VW; ++u) {
-        int q = q0 + u * ctx.nt;
-        bool in = q < L.nx;
-        lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
-        xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0;
-        gq[u] = in ? W.gphi[q] : 0.0, dd[u] = in ? W.dx[q] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < VW; ++u) {
-        double d = dd[u];
-        rel = fmax(rel, fabs(d) / (1.0 + fabs(xv[u])));
-        if (lo[u] > -INFINITY) {
-          double gp = xv[u] - lo[u];
-          double dz = mu / gp - zl[u] - zl[u] / gp * d;
+    {
+      const double* const src[7] = {xL, xU, W.x, W.zL, W.zU, W.gphi, W.dx};
+      flat_pass<7>(ctx, st, src, L.nx, [&](int, const double* v) {
+        const double lo = v[0], hi = v[1], xv = v[2], zl = v[3], zu = v[4], d = v[6];
+        rel = fmax(rel, fabs(d) / (1.0 + fabs(xv)));
+        if (lo > -INFINITY) {
+          const double gp = xv - lo;
+          const double dz = mu / gp - zl - zl / gp * d;
           if (d < 0) a_pr = fmin(a_pr, -tau * gp / d);
-          if (dz < 0) a_du = fmin(a_du, -tau * zl[u] / dz);
+          if (dz < 0) a_du = fmin(a_du, -tau * zl / dz);
         }
-        if (hi[u] < INFINITY) {
-          double gp = hi[u] - xv[u];
-          double dz = mu / gp - zu[u] + zu[u] / gp * d;
+        if (hi < INFINITY) {
+          const double gp = hi - xv;
+          const double dz = mu / gp - zu + zu / gp * d;
           if (d > 0) a_pr = fmin(a_pr, tau * gp / d);
-          if (dz < 0) a_du = fmin(a_du, -tau * zu[u] / dz);
+          if (dz < 0) a_du = fmin(a_du, -tau * zu / dz);
         }
-        dphi += gq[u] * d;
-      }
+        dphi += v[5] * d;
+      });
     }
     // grad_phi'dx = (gphi)'dx - y'J dx ; J dx = -c - (local delta_c terms, negligible) => use the exact product:
     // y'J dx is accumulated from the structure: J dx = -(c) on all rows up to delta_c * dy.
@@ -349,33 +419,26 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       // trial point and its barrier terms in one pass
       double sbar = 0;
       int bad = 0;
-      for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
-        double lo[VW], hi[VW], xv[VW], dd[VW];
-#pragma unroll
-        for (int u = 0; u < VW; ++u) {
-          int q = q0 + u * ctx.nt;
-          bool in = q < L.nx;
-          lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY, xv[u] = in ? W.x[q] : 0.0, dd[u] = in ? W.dx[q] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < VW; ++u) {
-          int q = q0 + u * ctx.nt;
-          const double v = xv[u] + alpha * dd[u];
-          if (q < L.nx) W.xt[q] = v;
-          const bool hl = lo[u] > -INFINITY, hu = hi[u] < INFINITY;
+      {
+        const double* const src[4] = {xL, xU, W.x, W.dx};
+        flat_pass<4>(ctx, st, src, L.nx, [&](int q, const double* v) {
+          const double lo = v[0], hi = v[1];
+          const double xn = v[2] + alpha * v[3];
+          W.xt[q] = xn;
+          const bool hl = lo > -INFINITY, hu = hi < INFINITY;
           if (hl) {
-            const double gp = v - lo[u];
+            const double gp = xn - lo;
             if (gp <= 0) bad = 1;
             else sbar -= log(gp);
             if (!hu) sbar += o.kappa_d * gp;
           }
           if (hu) {
-            const double gp = hi[u] - v;
+            const double gp = hi - xn;
             if (gp <= 0) bad = 1;
             else sbar -= log(gp);
             if (!hl) sbar += o.kappa_d * gp;
           }
-        }
+        });
       }
       cta_sync(ctx);
       model_eval<MODE>(ctx, L, S, W, W.xt, nullptr, W.ct, nullptr, &ft, &gdt_t);
@@ -420,32 +483,23 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       break;
     }
     // ---- accept the trial point (dz is recomputed from dx; x + alpha dx reproduces the trial point bit for bit)
-    for (int q0 = ctx.tid; q0 < L.nx; q0 += VW * ctx.nt) {
-      double lo[VW], hi[VW], xv[VW], zl[VW], zu[VW], dd[VW];
-#pragma unroll
-      for (int u = 0; u < VW; ++u) {
-        int q = q0 + u * ctx.nt;
-        bool in = q < L.nx;
-        lo[u] = in ? xL[q] : -INFINITY, hi[u] = in ? xU[q] : INFINITY;
-        xv[u] = in ? W.x[q] : 0.0, zl[u] = in ? W.zL[q] : 0.0, zu[u] = in ? W.zU[q] : 0.0, dd[u] = in ? W.dx[q] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < VW; ++u) {
-        int q = q0 + u * ctx.nt;
-        if (q >= L.nx) continue;
-        double d = dd[u], xn = xv[u] + alpha * d;
+    {
+      const double* const src[6] = {xL, xU, W.x, W.zL, W.zU, W.dx};
+      flat_pass<6>(ctx, st, src, L.nx, [&](int q, const double* v) {
+        const double lo = v[0], hi = v[1], xv = v[2], zl = v[3], zu = v[4], d = v[5];
+        const double xn = xv + alpha * d;
         W.x[q] = xn;
-        if (lo[u] > -INFINITY) {
-          double gp0 = xv[u] - lo[u], gp = xn - lo[u];
-          double zv = zl[u] + a_du * (mu / gp0 - zl[u] - zl[u] / gp0 * d);
+        if (lo > -INFINITY) {
+          const double gp0 = xv - lo, gp = xn - lo;
+          const double zv = zl + a_du * (mu / gp0 - zl - zl / gp0 * d);
           W.zL[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
         }
-        if (hi[u] < INFINITY) {
-          double gp0 = hi[u] - xv[u], gp = hi[u] - xn;
-          double zv = zu[u] + a_du * (mu / gp0 - zu[u] + zu[u] / gp0 * d);
+        if (hi < INFINITY) {
+          const double gp0 = hi - xv, gp = hi - xn;
+          const double zv = zu + a_du * (mu / gp0 - zu + zu / gp0 * d);
           W.zU[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
         }
-      }
+      });
     }
     for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.y[q] += alpha * W.dy[q];
     cta_sync(ctx);
