@@ -2,7 +2,7 @@
 import os, sys, time, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["OBCA_PROFILE"] = "1"
+os.environ.setdefault("OBCA_PROFILE", "1")
 import numpy as np, torch
 from conflict_rez_b200.control.strategy import write_strategy
 from conflict_rez_b200.control.batch_planner import prepare_joint_batch, random_init_offsets
