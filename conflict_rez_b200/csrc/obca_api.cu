@@ -533,6 +533,53 @@ int obca_set_mpc_params(ObcaHandle* h, const double* cur, const double* ref, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// DFMA throughput of the device (the FP64 roofline denominator asked for in SURVEY.md 8d)
+// ------------------------------------------------------------------------------------------------
+#ifndef OBCA_HOST_EMU
+__global__ void k_fp64_peak(double* out, int n) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < n; ++i) {
+    a0 = fma(a0, b, c), a1 = fma(a1, b, c), a2 = fma(a2, b, c), a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c), a5 = fma(a5, b, c), a6 = fma(a6, b, c), a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+#endif
+
+int obca_measure_dfma_peak(int device, double* tflops) {
+  if (!tflops) return fail("obca_measure_dfma_peak: null argument");
+#ifdef OBCA_HOST_EMU
+  (void)device;
+  *tflops = 0.0;
+  return fail("obca_measure_dfma_peak: not available in the host emulation");
+#else
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, thr = 256, it = 1 << 14;
+  double* out = nullptr;
+  CUDA_OK(cudaMalloc(&out, (size_t)blocks * thr * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+    cudaEventRecord(e0);
+    k_fp64_peak<<<blocks, thr>>>(out, it);
+    cudaEventRecord(e1);
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(out);
+  *tflops = 2.0 * 8 * it * (double)blocks * thr / (best * 1e-3) / 1e12;
+  return 0;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
 // closed-form dual warm starts (obca_ws.h)
 // ------------------------------------------------------------------------------------------------
 #ifndef OBCA_HOST_EMU

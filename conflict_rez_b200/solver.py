@@ -82,6 +82,7 @@ EXPORTS = [
     "obca_set_mpc_params",
     "obca_dual_ws",
     "obca_joint_dual_ws",
+    "obca_measure_dfma_peak",
     "obca_solve",
     "obca_get_solution",
     "obca_get_stats",
@@ -121,6 +122,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.obca_set_mpc_params.argtypes = [vp, vp, vp, vp, vp]
     lib.obca_dual_ws.argtypes = [vp, vp, vp, vp, vp]
     lib.obca_joint_dual_ws.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.obca_measure_dfma_peak.argtypes = [ctypes.c_int, _dp]
     lib.obca_solve.argtypes = [vp, vp]
     lib.obca_get_solution.argtypes = [vp] + [vp] * 7 + [vp]
     lib.obca_get_stats.argtypes = [vp] + [vp] * 6 + [vp]

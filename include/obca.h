@@ -112,6 +112,10 @@ int obca_set_mpc_params(ObcaHandle* h, const double* cur, const double* ref, con
 int obca_dual_ws(ObcaHandle* h, const double* z, double* lam, double* mu, void* stream);
 int obca_joint_dual_ws(ObcaHandle* h, const double* z, double* pair_lam, double* pair_mu, double* pair_s, void* stream);
 
+/* DFMA micro-benchmark: sustained FP64 FMA throughput of `device` in TFLOP/s (the FP64 roofline denominator of bench.py;
+ * SURVEY.md 8d asks for a measured figure next to the data-sheet 37 TFLOP/s) */
+int obca_measure_dfma_peak(int device, double* tflops);
+
 /* run the batched interior-point solve, asynchronously on `stream`; no host sync inside */
 int obca_solve(ObcaHandle* h, void* stream);
 
