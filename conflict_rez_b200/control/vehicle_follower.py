@@ -231,3 +231,94 @@ class MultiDistributedFollower(object):
         for v in self.vehicles:
             self.iter_time[v.agent] = v.iter_time
             self.final_results[v.agent] = v.final_traj
+
+
+class _RemotePrediction(object):
+    """The part of a neighbour's ``VehiclePrediction`` that the controllers read (x, y, psi over the horizon)."""
+
+    def __init__(self, xyp: np.ndarray):
+        self.x, self.y, self.psi = xyp[:, 0].copy(), xyp[:, 1].copy(), xyp[:, 2].copy()
+
+    def copy(self):
+        return _RemotePrediction(np.stack([self.x, self.y, self.psi], axis=1))
+
+
+class DistributedFollowerNode(object):
+    """One process per GPU (``torch.distributed``): the multi-process form of ``MultiDistributedFollower``.
+
+    The reference runs one ROS node per vehicle and exchanges predictions on the ``/pred`` topic
+    (ros2_ws/src/confrez_ros/confrez_ros/vehicle_node.py:80-189, launch/multi_follower.launch.py:37-52); in the
+    single-process simulation the exchange is the Jacobi snapshot of vehicle_follower.py:636-637.  Here rank r owns the
+    agents ``agents[r::world]`` and solves their MPC problems in one batched launch on its own GPU; the only
+    communication is one all-gather per control step of every vehicle's predicted (x, y, psi)[N] -- 720 bytes per
+    vehicle -- over NCCL (gloo on CPU).  Trajectories are identical to the single-process closed loop.
+    """
+
+    def __init__(self, rl_file_name: str, spline_ws_config: Dict[str, bool], colors: Dict[str, Tuple[float, float, float]],
+                 init_offsets: Dict[str, VehicleState], final_headings: Dict[str, float], device="cuda:0", lib=None, group=None) -> None:
+        import torch.distributed as dist
+
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device, self._lib = device, lib
+        self.agents = sorted(spline_ws_config.keys())
+        if len(self.agents) % self.world:
+            raise ValueError("the number of vehicles must be a multiple of the number of ranks")
+        self.local_agents = self.agents[self.rank :: self.world]
+        self.spline_ws_config = spline_ws_config
+        self.vehicles: List[VehicleFollower] = []
+        for agent in self.local_agents:
+            v = VehicleFollower(rl_file_name=rl_file_name, agent=agent, color=colors[agent], init_offset=init_offsets[agent],
+                                final_heading=final_headings[agent], device=device)
+            v._lib = lib
+            self.vehicles.append(v)
+        self.step_time: List[float] = []
+        self.exchange_time: List[float] = []
+        self.final_results: Dict[str, VehiclePrediction] = {}
+        self.solver = None
+
+    def setup_multi_vehicles(self, dt: float = 0.1, N: int = 30, dmin: float = 0.05):
+        for v in self.vehicles:
+            v.plan_single_path(spline_ws=self.spline_ws_config[v.agent])
+            v.others = [a for a in self.agents if a != v.agent]
+        self.solver = ObcaMpcSolver(self.vehicles[0].mpc_problem(dt, N, dmin, batch=len(self.vehicles)), SolveOptions(max_iter=600),
+                                    device=self.device, lib=self._lib)
+        for v in self.vehicles:
+            v.setup_controller(dt=dt, N=N, dmin=dmin, solver=self.solver)
+            v.get_current_ref()
+        self.N = N
+
+    def exchange_predictions(self):
+        """All-gather of the predicted poses: (n_local, N, 3) per rank -> every vehicle's ``others_pred``."""
+        import torch
+
+        dev = self.solver.device
+        mine = torch.as_tensor(np.stack([np.stack([v.pred.x, v.pred.y, v.pred.psi], axis=1) for v in self.vehicles]), dtype=torch.float64).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(parts, mine.contiguous(), group=self.group)
+        full = torch.stack(parts).cpu().numpy()  # [rank][local index][N][3]; agent agents[r + k * world] is local index k of rank r
+        for v in self.vehicles:
+            for o in v.others:
+                g = self.agents.index(o)
+                v.others_pred[o] = _RemotePrediction(full[g % self.world, g // self.world])
+
+    def solve(self, num_iter: int = 500):
+        for _ in range(num_iter):
+            t0 = time.perf_counter()
+            self.exchange_predictions()
+            t1 = time.perf_counter()
+            inputs = [v.step_inputs() for v in self.vehicles]
+            cur = np.stack([i[0] for i in inputs])
+            ref = np.stack([i[1] for i in inputs])
+            others = np.stack([i[2] for i in inputs])
+            st = lambda k: np.stack([i[3][k] for i in inputs])
+            guess = CollocationGuess(st("z")[:, None], st("lam")[:, None], st("mu")[:, None], np.zeros(len(inputs)), st("pl"), st("pm"), st("ps"))
+            t2 = time.perf_counter()
+            res = self.solver.solve_step(cur, ref, others, guess)
+            dt_solve = time.perf_counter() - t2
+            self.exchange_time.append(t1 - t0)
+            self.step_time.append(dt_solve)
+            for b, v in enumerate(self.vehicles):
+                v.apply_result(bool(res.status[b] >= 0), res, b, dt_solve)
+        for v in self.vehicles:
+            self.final_results[v.agent] = v.final_traj
