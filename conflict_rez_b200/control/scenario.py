@@ -128,3 +128,32 @@ def build_guess(prob: CollocationProblem, rl_file_name: str, agents: Sequence[st
     dt0 = dts.mean(axis=1)  # multi_vehicle_planner.py:360
     g = CollocationGuess(z, lam, mu, dt0, pl, pm, ps)
     return g if batched else g.instance(0)
+
+
+def random_obstacles(rl_file_name: str, n_extra: int, seed: int = 0, clearance: float = 0.6):
+    """The six parking-row rectangles plus ``n_extra`` seeded axis-aligned rectangles (obstacle
+    count sweep).  A candidate is rejected when it comes closer than ``clearance`` to any tube set of any agent, so the
+    strategy stays feasible."""
+    from conflict_rez_b200.control.compute_sets import _rect
+
+    rng = np.random.default_rng(seed)
+    base = compute_obstacles()
+    tubes = compute_sets(rl_file_name)
+    boxes = []
+    for sets in tubes.values():
+        for s in sets:
+            for body in ("back", "front"):
+                V = np.asarray(s[body].V)
+                boxes.append((V[:, 0].min(), V[:, 0].max(), V[:, 1].min(), V[:, 1].max()))
+    rg = GeofenceRegion()
+    out, tries = [], 0
+    while len(out) < n_extra and tries < 10000:
+        tries += 1
+        w, h = rng.uniform(0.5, 2.0, size=2)
+        x0, y0 = rng.uniform(rg.x_min, rg.x_max - w), rng.uniform(rg.y_min, rg.y_max - h)
+        if any(x0 - clearance < b[1] and x0 + w + clearance > b[0] and y0 - clearance < b[3] and y0 + h + clearance > b[2] for b in boxes):
+            continue
+        out.append(_rect(x0, x0 + w, y0, y0 + h))
+    if len(out) < n_extra:
+        raise RuntimeError("could not place %d obstacles" % n_extra)
+    return base + out

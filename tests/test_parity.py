@@ -185,3 +185,35 @@ def test_four_vehicle_batch_properties(cuda_lib, strategy_file):
     assert worst["collocation"] <= 1e-2 and worst["tube"] <= 1e-2 and worst["terminal"] <= 1e-2 and worst["init"] <= 1e-2
     assert worst["obstacle_clearance"] >= plan.problem.dmin - 1e-2
     assert worst["vehicle_clearance"] >= plan.problem.dmin - 1e-2
+
+
+SWEEP = [
+    pytest.param(("vehicle_1", "vehicle_2"), 2, 3, "emu", id="emu-V2-O8-nps3"),
+    pytest.param(("vehicle_1", "vehicle_2"), 2, 3, "cuda", id="cuda-V2-O8-nps3", marks=pytest.mark.gpu),
+    pytest.param(("vehicle_1", "vehicle_2", "vehicle_3"), 4, 5, "cuda", id="cuda-V3-O10-nps5", marks=pytest.mark.gpu),
+    pytest.param(("vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"), 6, 4, "cuda", id="cuda-V4-O12-nps4", marks=pytest.mark.gpu),
+]
+
+
+@pytest.mark.parametrize("agents,n_extra,nps,which", SWEEP)
+def test_scaling_sweep_cells(request, strategy_file, agents, n_extra, nps, which):
+    """Cells of the scaling sweep: vehicle count, obstacle count (seeded extra rectangles) and
+    intervals per move vary; every converged plan must satisfy the reference problem statement by plain geometry."""
+    from conflict_rez_b200.control.batch_planner import random_init_offsets, solve_joint_batch
+    from conflict_rez_b200.control.scenario import random_obstacles
+
+    lib, dev = (request.getfixturevalue("emu_lib"), "cpu") if which == "emu" else (request.getfixturevalue("cuda_lib"), "cuda:0")
+    obstacles = random_obstacles(strategy_file, n_extra, seed=7)
+    idx = [int(a[-1]) for a in agents]
+    B = 2 if which == "emu" else 6
+    offs = random_init_offsets(B, 4, seed=11)[:, idx]
+    plan = solve_joint_batch(strategy_file, list(agents), offs, SolveOptions(max_iter=600), device=dev, lib=lib, obstacles=obstacles, n_per_set=nps)
+    res = plan.result
+    assert plan.problem.O == 6 + n_extra and plan.problem.V == len(agents)
+    ok = res.status >= 0
+    assert ok.sum() >= B - 1, res.status
+    worst = check_solution_properties(plan.problem, res.z[ok], res.dt[ok])
+    assert worst["collocation"] <= 1e-2 and worst["tube"] <= 1e-2 and worst["terminal"] <= 1e-2 and worst["init"] <= 1e-2
+    assert worst["obstacle_clearance"] >= plan.problem.dmin - 1e-2
+    if len(agents) > 1:
+        assert worst["vehicle_clearance"] >= plan.problem.dmin - 1e-2
