@@ -1205,51 +1205,50 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     }
     cta_sync(ctx);
     prof_mark(ctx, 13);
-    // Cholesky F = L L' by warp 0 (right-looking, lanes over rows / columns); a non-positive pivot means the reduced
-    // Hessian is not positive definite
-#if defined(__CUDA_ARCH__)
-    if (ctx.tid < 32)
-#endif
-    {
-      for (int j = 0; j < nu; ++j) {
-        double d = R.F[j * nu + j];
-        bool bad = !(d > 1e-14 * fmax(1.0, fabs(R.R[j * nu + j])));
-        if (bad) d = 1.0;
-        const double sd = sqrt(d), inv = 1.0 / sd;
-        OBCA_WARP_SYNC();
-        OBCA_LANES(lane) {
-          if (lane == 0) {
-            R.invd[j] = inv;
-            if (bad) *ok = 0;
-          }
-          for (int r = j + lane; r < nu; r += 32) R.F[r * nu + j] = (r == j) ? sd : R.F[r * nu + j] * inv;
-        }
-        OBCA_WARP_SYNC();
-        OBCA_LANES(lane) {
-          for (int c = j + 1 + lane; c < nu; c += 32) {
-            const double lcj = R.F[c * nu + j];
-            for (int r = c; r < nu; ++r) R.F[r * nu + c] -= R.F[r * nu + j] * lcj;
-          }
-        }
-        OBCA_WARP_SYNC();
-      }
-    }
+    // Cholesky F = L L' fused with the forward substitution of [K | k] = -F^-1 Gm: right-looking elimination of the
+    // augmented matrix [F | Gm] by the whole CTA (two barriers per pivot); a non-positive pivot means the reduced
+    // Hessian is not positive definite.  Then a column-oriented backward substitution (one barrier per row).
+    const int nc = nX + 1;
+    for (int it = ctx.tid; it < nu * nc; it += ctx.nt) R.K[it] = R.Gm[it];
     cta_sync(ctx);
-    prof_mark(ctx, 14);
-    // [K | k] = -F^-1 Gm : one thread per column, in place in shared memory
-    for (int col = ctx.tid; col < nX + 1; col += ctx.nt) {
-      for (int r = 0; r < nu; ++r) {
-        double v = R.Gm[r * (nX + 1) + col];
-        for (int m = 0; m < r; ++m) v -= R.F[r * nu + m] * R.K[m * (nX + 1) + col];
-        R.K[r * (nX + 1) + col] = v * R.invd[r];
+    for (int j = 0; j < nu; ++j) {
+      double d = R.F[j * nu + j];
+      const bool bad = !(d > 1e-14 * fmax(1.0, fabs(R.R[j * nu + j])));
+      if (bad) d = 1.0;
+      const double sd = sqrt(d), inv = 1.0 / sd;
+      const int n1 = nu - j - 1;
+      for (int it = ctx.tid; it < n1 + nc + 1; it += ctx.nt) {  // the pivot entry itself is left untouched (only 1/L_jj is used later)
+        if (it < n1) R.F[(j + 1 + it) * nu + j] *= inv;
+        else if (it < n1 + nc) R.K[j * nc + (it - n1)] *= inv;
+        else {
+          R.invd[j] = inv;
+          if (bad) *ok = 0;
+        }
       }
-      for (int r = nu - 1; r >= 0; --r) {
-        double v = R.K[r * (nX + 1) + col];
-        for (int m = r + 1; m < nu; ++m) v -= R.F[m * nu + r] * R.K[m * (nX + 1) + col];
-        R.K[r * (nX + 1) + col] = v * R.invd[r];
+      cta_sync(ctx);
+      for (int it = ctx.tid; it < n1 * (n1 + nc); it += ctx.nt) {
+        const int r = j + 1 + it / (n1 + nc), c = it % (n1 + nc);
+        const double lrj = R.F[r * nu + j];
+        if (c < n1) {
+          const int cc = j + 1 + c;
+          if (cc <= r) R.F[r * nu + cc] -= lrj * R.F[cc * nu + j];
+        } else
+          R.K[r * nc + (c - n1)] -= lrj * R.K[j * nc + (c - n1)];
       }
-      for (int r = 0; r < nu; ++r) R.K[r * (nX + 1) + col] = -R.K[r * (nX + 1) + col];
+      // the next pivot read is ordered by the barrier at the top of the next iteration's scaling phase
+      cta_sync(ctx);
     }
+    prof_mark(ctx, 14);
+    // backward: rows r = nu-1 .. 0, w_r = K[r,:] stays unscaled until the end; K[m,:] -= L[r][m] invd[r] w_r for m < r
+    for (int r = nu - 1; r > 0; --r) {
+      const double ir = R.invd[r];
+      for (int it = ctx.tid; it < r * nc; it += ctx.nt) {
+        const int m = it / nc, c = it % nc;
+        R.K[m * nc + c] -= R.F[r * nu + m] * ir * R.K[r * nc + c];
+      }
+      cta_sync(ctx);
+    }
+    for (int it = ctx.tid; it < nu * nc; it += ctx.nt) R.K[it] = -R.K[it] * R.invd[it / nc];
     cta_sync(ctx);
     prof_mark(ctx, 15);
     // gains to global memory (forward pass) in the padded layout [nUmax][nX] + [nUmax]
