@@ -68,7 +68,9 @@ constexpr int EXSZ = 1 + NEX * 9;      // emitted rows: count, then (h_xi[7], h_
 // [4] (rank, rows, ndrop, unused), then NDR x (column j, emission slot or -1, staircase length, alpha[35], implied row h[9]), then nu[NEX]
 constexpr int QR_TAU = 35 * NC, QR_PIV = QR_TAU + 35, QR_META = QR_PIV + 35, QR_DROP = QR_META + 4, DRSZ = 3 + 35 + 9;
 constexpr int QR_NU = QR_DROP + NDR * DRSZ;  // multipliers of the received implied rows
-constexpr int QRSZ = QR_NU + NEX;
+constexpr int QR_BU = QR_NU + NEX;      // coefficients of (a_5, w_5) in the terminal / implied rows before their elimination: [2][NC]
+constexpr int QRSZ = QR_BU + 2 * NC;
+constexpr int NQ = 25;                  // state variables of the nodes 1..K of a block: the controls are eliminated analytically
 constexpr int MAXV = OBCA_MAX_V;
 constexpr int MAXP = MAXV * (MAXV - 1) / 2;
 constexpr int NXMAX = 7 * MAXV + 1;

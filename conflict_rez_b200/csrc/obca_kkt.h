@@ -424,7 +424,7 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
 // QR record: [35*35] reflectors below / R on and above the staircase, [35] tau, [35] pivot column of every
 // staircase row, [2] (rank, nr).
 // ------------------------------------------------------------------------------------------------
-// apply Q = H_0 ... H_{rk-1} (transpose = false) or Q' (transpose = true) to v[35]
+// apply Q = H_0 ... H_{rk-1} (transpose = false) or Q' (transpose = true) to v[NQ]
 OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
   const double* tau = QRm + QR_TAU;
   const double* piv = QRm + QR_PIV;
@@ -432,10 +432,10 @@ OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
     int i = transpose ? jj : rk - 1 - jj;          // reflector i acts on rows i..34, stored in column piv[i]
     int col = (int)piv[i];
     double s = v[i];
-    for (int r = i + 1; r < NW; ++r) s += QRm[r * NC + col] * v[r];
+    for (int r = i + 1; r < NQ; ++r) s += QRm[r * NC + col] * v[r];
     s *= tau[i];
     v[i] -= s;
-    for (int r = i + 1; r < NW; ++r) v[r] -= s * QRm[r * NC + col];
+    for (int r = i + 1; r < NQ; ++r) v[r] -= s * QRm[r * NC + col];
   }
 }
 
@@ -497,8 +497,8 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   const int nterm = last ? (4 + L.heading[a]) : 0;
   const int nex = (int)ex[0];
   const int nr = 30 + nterm + nex;
-  double* Mq = sw;                 // [35][NC]
-  double* G0 = Mq + NW * NC;       // [NC][7]
+  double* Mq = sw;                 // [NQ][NC] (later reused for the projection: 42 x NRED + ...)
+  double* G0 = Mq + NQ * NC;       // [NC][7]
   double* gd = G0 + NC * 7;        // [NC]
   double* rr = gd + NC;            // [NC]
   double* tau = rr + NC;           // [35]
@@ -510,9 +510,11 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   double* gnv = hdv + NS;          // [42] node gradients
   double* wred = gnv + NS;         // [64] reduction scratch
   double* misc = wred + 64;        // [64]: al[35], h[9], flags
+  double* bu = misc + 64;          // [2][NC] coefficients of (a_K, w_K) in the rows before the elimination
   double* QRg = W.QR + (size_t)(a * L.Nmax + i) * QRSZ;
   OBCA_LANES(lane) {
-    for (int q = lane; q < NW * NC + NC * 7; q += 32) Mq[q] = 0;  // Mq and G0 are contiguous
+    for (int q = lane; q < NQ * NC + NC * 7; q += 32) Mq[q] = 0;  // Mq and G0 are contiguous
+    for (int q = lane; q < 2 * NC; q += 32) bu[q] = 0;
     for (int q = lane; q < NS; q += 32) {
       zb[q] = x[L.Z(a, q % NZ, n0 + q / NZ)];
       hdv[q] = W.HD[(size_t)(a * L.Mv + n0 + q / NZ) * 7 + q % NZ];
@@ -530,7 +532,7 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
         double coef = S.cA[j][k] * idt;
         pl += S.cA[j][k] * zb[j * NZ + q];
         if (j == 0) G0[r * 7 + q] += coef;
-        else Mq[((j - 1) * 7 + q) * NC + r] += coef;
+        else Mq[((j - 1) * 5 + q) * NC + r] += coef;
       }
       gd[r] = -pl * idt * idt;
       rr[r] = W.c[L.YCOL(a, q, n0 + k)];
@@ -543,22 +545,46 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
       for (int m = 2; m < NZ; ++m) {
         if (dfz[m] == 0.0) continue;
         if (k == 0) G0[r * 7 + m] -= dfz[m];
-        else Mq[((k - 1) * 7 + m) * NC + r] -= dfz[m];
+        else if (m < 5) Mq[((k - 1) * 5 + m) * NC + r] -= dfz[m];
+        // k >= 1, m = 5, 6: the -1 on (a_k, w_k) makes rows (k, 3), (k, 4) the defining rows of the controls (not stored)
       }
     } else if (lane == 30) {
       int r = 30;
       if (last) {
         if (L.heading[a]) {
-          Mq[(28 + 2) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, 0)];
+          Mq[(20 + 2) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, 0)];
           ++r;
         }
-        for (int m = 3; m < NZ; ++m, ++r) Mq[(28 + m) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, m - 2)];
+        for (int m = 3; m < NZ; ++m, ++r) {
+          if (m < 5) Mq[(20 + m) * NC + r] = 1.0;
+          else bu[(m - 5) * NC + r] = 1.0;
+          gd[r] = 0, rr[r] = W.c[L.YTERM(a, m - 2)];
+        }
       }
       for (int e = 0; e < nex; ++e, ++r) {
         const double* h = ex + 1 + e * 9;
-        for (int m = 0; m < NZ; ++m) Mq[(28 + m) * NC + r] = h[m];
+        for (int m = 0; m < 5; ++m) Mq[(20 + m) * NC + r] = h[m];
+        bu[r] = h[5], bu[NC + r] = h[6];
         gd[r] = h[7], rr[r] = h[8];
       }
+    }
+  }
+  OBCA_WARP_SYNC();
+  // Controls of the nodes 1..K: row (k, 3) reads  -a_k + sum_j cA[j][k]/dt v_j + ... = -r, row (k, 4) the same for (w_k, delta_j),
+  // so a_k, w_k are affine in the states and are eliminated exactly; they also appear in the terminal / implied rows (node K),
+  // where they are substituted.  The QR below then works on the 25 states and the 20 (+ terminal + implied) remaining rows.
+  OBCA_LANES(lane) {
+    const int r = 30 + lane;
+    if (r < nr) {
+      const double ba = bu[r], bw = bu[NC + r];
+      for (int j = 1; j < NK; ++j) {
+        const double coef = S.cA[j][5] * idt;
+        Mq[((j - 1) * 5 + 3) * NC + r] += ba * coef;
+        Mq[((j - 1) * 5 + 4) * NC + r] += bw * coef;
+      }
+      G0[r * 7 + 3] += ba * S.cA[0][5] * idt, G0[r * 7 + 4] += bw * S.cA[0][5] * idt;
+      gd[r] += ba * gd[28] + bw * gd[29];
+      rr[r] += ba * rr[28] + bw * rr[29];
     }
   }
   OBCA_WARP_SYNC();
@@ -566,12 +592,13 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   // Householder QR with rank test (LAPACK dgeqr2 reflector convention: v[rk] = 1 implicit)
   int rk = 0, ndrop = 0, nem = 0;
   for (int j = 0; j < nr; ++j) {
+    if (j >= 5 && j < 30 && j % 5 >= 3) continue;  // defining rows of the eliminated controls
     double full = 0, nrm = 0;
 #if defined(__CUDA_ARCH__)
     {
       const int lane = ctx.tid & 31;
       double head = 0, tail = 0;
-      for (int q = lane; q < NW; q += 32) {
+      for (int q = lane; q < NQ; q += 32) {
         double v = Mq[q * NC + j];
         if (q < rk) head += v * v;
         else if (q > rk) tail += v * v;
@@ -584,16 +611,16 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
       full = head, nrm = tail;
     }
 #else
-    for (int q = 0; q < NW; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       double v = Mq[q * NC + j];
       if (q < rk) full += v * v;
       else if (q > rk) nrm += v * v;
     }
 #endif
-    double alpha = rk < NW ? Mq[rk * NC + j] : 0.0;
+    double alpha = rk < NQ ? Mq[rk * NC + j] : 0.0;
     double beta = sqrt(alpha * alpha + nrm);
     full = sqrt(full + alpha * alpha + nrm);
-    if (rk >= NW || !(beta > 1e-8 * full) || !(full > 0)) {
+    if (rk >= NQ || !(beta > 1e-8 * full) || !(full > 0)) {
       // dependent row j = sum_i al[i] * (staircase row i): its remainder is an implied constraint on (xi, dt)
       if (ndrop >= NDR) {
         *ok = 0;
@@ -647,37 +674,38 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     const double t = (beta - alpha) * ibeta;
     const double sc = 1.0 / (alpha - beta);
     OBCA_LANES(lane) {
-      for (int q = rk + 1 + lane; q < NW; q += 32) Mq[q * NC + j] *= sc;
+      for (int q = rk + 1 + lane; q < NQ; q += 32) Mq[q * NC + j] *= sc;
       if (lane == 0) tau[rk] = t, piv[rk] = (double)j, Mq[rk * NC + j] = beta, wred[rk] = ibeta;
     }
     OBCA_WARP_SYNC();
     OBCA_LANES(lane) {
       for (int cc = j + 1 + lane; cc < nr; cc += 32) {
+        if (cc >= 5 && cc < 30 && cc % 5 >= 3) continue;
         const double* uj = Mq + j;
         double* vc = Mq + cc;
         double a0 = vc[rk * NC], a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int q = rk + 1;
-        for (; q + 3 < NW; q += 4) {
+        for (; q + 3 < NQ; q += 4) {
           const double u0 = uj[q * NC], u1 = uj[(q + 1) * NC], u2 = uj[(q + 2) * NC], u3 = uj[(q + 3) * NC];
           const double v0 = vc[q * NC], v1 = vc[(q + 1) * NC], v2 = vc[(q + 2) * NC], v3 = vc[(q + 3) * NC];
           a0 += u0 * v0, a1 += u1 * v1, a2 += u2 * v2, a3 += u3 * v3;
         }
-        for (; q < NW; ++q) a0 += uj[q * NC] * vc[q * NC];
+        for (; q < NQ; ++q) a0 += uj[q * NC] * vc[q * NC];
         const double sacc = ((a0 + a1) + (a2 + a3)) * t;
         vc[rk * NC] -= sacc;
         q = rk + 1;
-        for (; q + 3 < NW; q += 4) {  // column cc != column j: load everything first, then store
+        for (; q + 3 < NQ; q += 4) {  // column cc != column j: load everything first, then store
           const double u0 = uj[q * NC], u1 = uj[(q + 1) * NC], u2 = uj[(q + 2) * NC], u3 = uj[(q + 3) * NC];
           const double v0 = vc[q * NC], v1 = vc[(q + 1) * NC], v2 = vc[(q + 2) * NC], v3 = vc[(q + 3) * NC];
           vc[q * NC] = v0 - sacc * u0, vc[(q + 1) * NC] = v1 - sacc * u1, vc[(q + 2) * NC] = v2 - sacc * u2, vc[(q + 3) * NC] = v3 - sacc * u3;
         }
-        for (; q < NW; ++q) vc[q * NC] -= sacc * uj[q * NC];
+        for (; q < NQ; ++q) vc[q * NC] -= sacc * uj[q * NC];
       }
     }
     OBCA_WARP_SYNC();
     ++rk;
   }
-  int np = NW - rk;
+  int np = NQ - rk;
   if (np > NP) {
     *ok = 0;
     np = NP;
@@ -690,13 +718,13 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
       // The column lives in registers (all indices below are compile-time constants after unrolling): the shared-memory
       // pipe, shared by the 8 warps of the CTA, then only serves the broadcast loads of R and of the reflectors.
       const int col = lane;
-      double v[NW];
+      double v[NQ];
 #pragma unroll
-      for (int q = 0; q < NW; ++q) v[q] = 0.0;
+      for (int q = 0; q < NQ; ++q) v[q] = 0.0;
       if (col < 9) {
         // b = -G0[:,col] (col < 7), -gd (col 7), -r (col 8); forward substitution R' w = b on the staircase
 #pragma unroll
-        for (int ii = 0; ii < NW; ++ii) {
+        for (int ii = 0; ii < NQ; ++ii) {
           if (ii < rk) {
             const int j = (int)piv[ii];
             const double* Rj = Mq + j;
@@ -710,17 +738,17 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
       } else {
         const int jn = col - 9;
 #pragma unroll
-        for (int q = 0; q < NW; ++q) v[q] = (jn < np && q == rk + jn) ? 1.0 : 0.0;
+        for (int q = 0; q < NQ; ++q) v[q] = (jn < np && q == rk + jn) ? 1.0 : 0.0;
       }
       if (col < 9 || col - 9 < np) {
         // v <- H_0 ... H_{rk-1} v ; reflector i = (1, u_{i+1..34}) stored below the staircase of its pivot column
 #pragma unroll
-        for (int i = NW - 1; i >= 0; --i) {
+        for (int i = NQ - 1; i >= 0; --i) {
           if (i < rk) {
             const double* u = Mq + (int)piv[i];
             double a0 = v[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-            for (int r = i + 1; r < NW; ++r) {
+            for (int r = i + 1; r < NQ; ++r) {
               const double ur = u[r * NC];
               if (((r - i - 1) & 3) == 0) a0 += ur * v[r];
               else if (((r - i - 1) & 3) == 1) a1 += ur * v[r];
@@ -730,14 +758,26 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
             const double sacc = ((a0 + a1) + (a2 + a3)) * tau[i];
             v[i] -= sacc;
 #pragma unroll
-            for (int r = i + 1; r < NW; ++r) v[r] -= sacc * u[r * NC];
+            for (int r = i + 1; r < NQ; ++r) v[r] -= sacc * u[r * NC];
           }
         }
       }
       double* vo = col < 7 ? T + col : (col == 7 ? T + IDT : (col == 8 ? s0 : T + 7 + (col - 9)));
       const int stride = col == 8 ? 1 : NRED;
 #pragma unroll
-      for (int q = 0; q < NW; ++q) vo[q * stride] = v[q];
+      for (int q = 0; q < NQ; ++q) vo[((q / 5) * 7 + q % 5) * stride] = v[q];  // state rows of the 35-row stage map
+    }
+  }
+  OBCA_WARP_SYNC();
+  // control rows of the stage map: a_k = sum_j cA[j][k]/dt v_j + cA[0][k]/dt xi_v + gd dt + r  (w_k likewise with delta)
+  OBCA_LANES(lane) {
+    for (int e = lane; e < 10 * (9 + NP); e += 32) {
+      const int col = e % (9 + NP), kc = e / (9 + NP), k = 1 + kc / 2, q = 3 + kc % 2, re = k * 5 + q;
+      double* vo = col < 7 ? T + col : (col == 7 ? T + IDT : (col == 8 ? s0 : T + 7 + (col - 9)));
+      const int stride = col == 8 ? 1 : NRED;
+      double sacc = col == q ? S.cA[0][k] * idt : (col == 7 ? gd[re] : (col == 8 ? rr[re] : 0.0));
+      for (int j = 1; j < NK; ++j) sacc += S.cA[j][k] * idt * vo[((j - 1) * 7 + q) * stride];
+      vo[((k - 1) * 7 + q + 2) * stride] = sacc;
     }
   }
   OBCA_WARP_SYNC();
@@ -745,8 +785,9 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   // QR record and T map to global memory (multiplier recovery, Riccati dynamics, primal expansion)
   double* Tg = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
   OBCA_LANES(lane) {
-    for (int q = lane; q < NW * NC; q += 32) QRg[q] = Mq[q];
-    for (int q = lane; q < NW; q += 32) QRg[QR_TAU + q] = tau[q], QRg[QR_PIV + q] = piv[q];
+    for (int q = lane; q < NQ * NC; q += 32) QRg[q] = Mq[q];
+    for (int q = lane; q < NQ; q += 32) QRg[QR_TAU + q] = tau[q], QRg[QR_PIV + q] = piv[q];
+    for (int q = lane; q < 2 * NC; q += 32) QRg[QR_BU + q] = bu[q];
     for (int q = lane; q < NW * NRED + NW; q += 32) Tg[q] = T[q];  // T and s0 are contiguous
   }
   OBCA_WARP_SYNC();
@@ -1008,7 +1049,7 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
 // free directions of block (a, i): 35 - rank, 0 for a vehicle whose horizon has ended
 OBCA_HD int block_np(const Lay& L, const Scratch& W, int a, int i) {
   if (i >= L.N[a]) return 0;
-  int np = NW - (int)W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_META];
+  int np = NQ - (int)W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_META];
   return np > NP ? NP : np;
 }
 
@@ -1436,6 +1477,16 @@ OBCA_HD double* block_row_multiplier(const Lay& L, const Scratch& W, int a, int 
   return &W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_NU + (r - 30 - nterm)];
 }
 
+// dy of row r of block (a, i) += d; a terminal / implied row also feeds the multipliers of the two defining rows of (a_K, w_K)
+OBCA_HD void add_row_multiplier(const Lay& L, const Scratch& W, int a, int i, int r, double d) {
+  *block_row_multiplier(L, W, a, i, r) += d;
+  if (r >= 30) {
+    const double* bu = W.QR + (size_t)(a * L.Nmax + i) * QRSZ + QR_BU;
+    *block_row_multiplier(L, W, a, i, 28) += bu[r] * d;
+    *block_row_multiplier(L, W, a, i, 29) += bu[NC + r] * d;
+  }
+}
+
 OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W) {
   assume_scratch(W);
   OBCA_ASSUME_STATIC(L, S);
@@ -1463,22 +1514,38 @@ OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, c
     const double* QRm = W.QR + (size_t)(a * L.Nmax + i) * QRSZ;
     const double* piv = QRm + QR_PIV;
     int rk = (int)QRm[QR_META], nr = (int)QRm[QR_META + 1];
-    double v[NW], dyr[NC];
+    double v[NW], vt[NQ], dyr[NC];
     for (int r = 0; r < NW; ++r) v[r] = -W.GN[(size_t)(a * L.Mv + n0 + 1 + r / NZ) * 7 + r % NZ];
     if (i < L.N[a] - 1)
       for (int q = 0; q < NZ; ++q) v[28 + q] -= W.dy[L.YCONT(a, q, i + 1)];
-    apply_q(QRm, rk, v, true);
-    // R dy = v[0:rk] on the staircase; dropped (dependent) rows keep dy = 0 here
+    // reduced right-hand side on the 25 states: the control equations  -y_(k,c) + sum beta y = v_(a_k | w_k)  are substituted
+    for (int j = 1; j < NK; ++j)
+      for (int q = 0; q < 5; ++q) {
+        double sacc = v[(j - 1) * 7 + q];
+        if (q >= 3)
+          for (int k = 1; k < NK; ++k) sacc += S.cA[j][k] * idt * v[(k - 1) * 7 + q + 2];
+        vt[(j - 1) * 5 + q] = sacc;
+      }
+    apply_q(QRm, rk, vt, true);
+    // R dy = vt[0:rk] on the staircase; dropped (dependent) rows keep dy = 0 here
     for (int r = 0; r < nr; ++r) dyr[r] = 0;
     for (int ii = rk - 1; ii >= 0; --ii) {
       int j = (int)piv[ii];
-      double s = v[ii];
+      double s = vt[ii];
       for (int m = ii + 1; m < rk; ++m) {
         int jm = (int)piv[m];
         s -= QRm[ii * NC + jm] * dyr[jm];
       }
       dyr[j] = s / QRm[ii * NC + j];
     }
+    // defining rows of the controls
+    for (int k = 1; k < NK; ++k)
+      for (int c = 5; c < 7; ++c) {
+        double s = -v[(k - 1) * 7 + c];
+        if (k == NK - 1)
+          for (int r = 30; r < nr; ++r) s += QRm[QR_BU + (c - 5) * NC + r] * dyr[r];
+        dyr[k * 5 + c - 2] = s;
+      }
     for (int r = 0; r < nr; ++r) *block_row_multiplier(L, W, a, i, r) = dyr[r];
     if (i == L.N[a] - 1 && !L.heading[a]) W.dy[L.YTERM(a, 0)] = 0.0;
     if (i == 0) {
@@ -1509,8 +1576,8 @@ OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, c
         int j = (int)dr[0], slot = (int)dr[1], rkd = (int)dr[2];
         if (slot < 0) continue;
         double nv = nu[slot];
-        *block_row_multiplier(L, W, a, i + 1, j) += nv;
-        for (int q = 0; q < rkd; ++q) *block_row_multiplier(L, W, a, i + 1, (int)Qn[QR_PIV + q]) -= dr[3 + q] * nv;
+        add_row_multiplier(L, W, a, i + 1, j, nv);
+        for (int q = 0; q < rkd; ++q) add_row_multiplier(L, W, a, i + 1, (int)Qn[QR_PIV + q], -dr[3 + q] * nv);
         for (int q = 0; q < NZ; ++q) W.dy[L.YCONT(a, q, i + 1)] += nv * dr[3 + 35 + q];
       }
     }
