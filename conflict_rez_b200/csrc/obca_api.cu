@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -405,6 +406,27 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   for (int q = 0; q < 8; ++q) S.limits[q] = st->limits[q];
   for (int a = 0; a < L.V; ++a) S.heading[a] = mpc ? 0.0 : st->final_heading[a];
   collocation_matrices(S.cA, S.cB);
+  {
+    // inverse of A1[k][j] = cA[j][k] (j, k = 1..K) by Gauss-Jordan with partial pivoting: the interior collocation block
+    double M[5][10];
+    for (int k = 0; k < 5; ++k)
+      for (int j = 0; j < 5; ++j) M[k][j] = S.cA[j + 1][k + 1], M[k][5 + j] = (k == j) ? 1.0 : 0.0;
+    for (int c = 0; c < 5; ++c) {
+      int pr = c;
+      for (int r = c + 1; r < 5; ++r)
+        if (fabs(M[r][c]) > fabs(M[pr][c])) pr = r;
+      for (int q = 0; q < 10; ++q) std::swap(M[c][q], M[pr][q]);
+      const double ip = 1.0 / M[c][c];
+      for (int q = 0; q < 10; ++q) M[c][q] *= ip;
+      for (int r = 0; r < 5; ++r) {
+        if (r == c) continue;
+        const double f = M[r][c];
+        for (int q = 0; q < 10; ++q) M[r][q] -= f * M[c][q];
+      }
+    }
+    for (int j = 0; j < 5; ++j)
+      for (int k = 0; k < 5; ++k) S.cAi[j][k] = M[j][5 + k];  // (A1^-1)[j][k]: x_j = sum_k cAi[j][k] rhs_k
+  }
   std::vector<double> tube((size_t)L.V * L.Smax * 2 * 4 * 3);
   for (int a = 0; a < L.V && !mpc; ++a)
     for (int q = 0; q < L.Smax; ++q)

@@ -71,6 +71,7 @@ constexpr int QR_NU = QR_DROP + NDR * DRSZ;  // multipliers of the received impl
 constexpr int QR_BU = QR_NU + NEX;      // coefficients of (a_5, w_5) in the terminal / implied rows before their elimination: [2][NC]
 constexpr int QRSZ = QR_BU + 2 * NC;
 constexpr int NQ = 25;                  // state variables of the nodes 1..K of a block: the controls are eliminated analytically
+constexpr int NU2 = 10;                 // of these (x, y, psi) are eliminated through the constant interior collocation block: the QR sees (v, delta)
 constexpr int MAXV = OBCA_MAX_V;
 constexpr int MAXP = MAXV * (MAXV - 1) / 2;
 constexpr int NXMAX = 7 * MAXV + 1;
@@ -195,6 +196,7 @@ struct Stat {
   double region[4], limits[8];
   double heading[MAXV];
   double cA[NK][NK], cB[NK];  // collocation matrices: cA[j][k] = L_j'(tau_k), cB[k] quadrature weights
+  double cAi[5][5];           // inverse of the interior block: sum_j cA[j][k] cAi[j'][k]... i.e. (A1^-1)[j][k], A1[k][j] = cA[j][k], j,k = 1..K
   // tube sets, b already reduced by shrink_tube: [V][Smax][2][4][3] = (ax, ay, b)
   const double* tube;
   OBCA_HD const double* tube_row(const Lay& L, int a, int q, int body, int r) const {

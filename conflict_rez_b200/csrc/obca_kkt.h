@@ -424,7 +424,7 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
 // QR record: [35*35] reflectors below / R on and above the staircase, [35] tau, [35] pivot column of every
 // staircase row, [2] (rank, nr).
 // ------------------------------------------------------------------------------------------------
-// apply Q = H_0 ... H_{rk-1} (transpose = false) or Q' (transpose = true) to v[NQ]
+// apply Q = H_0 ... H_{rk-1} (transpose = false) or Q' (transpose = true) to v[NU2]
 OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
   const double* tau = QRm + QR_TAU;
   const double* piv = QRm + QR_PIV;
@@ -432,10 +432,10 @@ OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
     int i = transpose ? jj : rk - 1 - jj;          // reflector i acts on rows i..34, stored in column piv[i]
     int col = (int)piv[i];
     double s = v[i];
-    for (int r = i + 1; r < NQ; ++r) s += QRm[r * NC + col] * v[r];
+    for (int r = i + 1; r < NU2; ++r) s += QRm[r * NC + col] * v[r];
     s *= tau[i];
     v[i] -= s;
-    for (int r = i + 1; r < NQ; ++r) v[r] -= s * QRm[r * NC + col];
+    for (int r = i + 1; r < NU2; ++r) v[r] -= s * QRm[r * NC + col];
   }
 }
 
@@ -448,6 +448,11 @@ OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
 #define OBCA_WARP_SYNC()
 #endif
 
+#if defined(OBCA_HOST_EMU)
+#define OBCA_DBG(...) do { if (getenv("OBCA_TRACE")) printf(__VA_ARGS__); } while (0)
+#else
+#define OBCA_DBG(...) do { } while (0)
+#endif
 constexpr int NSW = 2720;  // shared-memory doubles per warp of the null-space phase
 
 // apply Q or Q' to the strided vector v[q * stride], q < 35 (reflectors in the shared-memory QR matrix)
@@ -511,6 +516,8 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   double* wred = gnv + NS;         // [64] reduction scratch
   double* misc = wred + 64;        // [64]: al[35], h[9], flags
   double* bu = misc + 64;          // [2][NC] coefficients of (a_K, w_K) in the rows before the elimination
+  double* ndv = bu + 2 * NC;       // [5][5] per interior node: cos, sin, tan/wb, v sec^2/wb, v
+  double* rref = ndv + 25;         // [NC] norm of every remaining row before the elimination
   double* QRg = W.QR + (size_t)(a * L.Nmax + i) * QRSZ;
   OBCA_LANES(lane) {
     for (int q = lane; q < NQ * NC + NC * 7; q += 32) Mq[q] = 0;  // Mq and G0 are contiguous
@@ -522,69 +529,111 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     }
   }
   OBCA_WARP_SYNC();
+  // variable rows of the matrix: (v_j, delta_j) -> (j-1)*2 + (q-3) in 0..9 (the QR part), (x, y, psi)_j -> 10 + q*5 + (j-1)
+#define OBCA_VROW(j, q) ((q) >= 3 ? ((j) - 1) * 2 + (q) - 3 : 10 + (q) * 5 + (j) - 1)
   OBCA_LANES(lane) {
     if (lane < 30) {
       int k = lane / 5, q = lane % 5, r = lane;
       double psi = zb[k * NZ + 2], v = zb[k * NZ + 3], de = zb[k * NZ + 4];
       double cs = cos(psi), sn = sin(psi), tde = tan(de), sec2 = 1.0 + tde * tde;
       double pl = 0;
-      for (int j = 0; j < NK; ++j) {
-        double coef = S.cA[j][k] * idt;
-        pl += S.cA[j][k] * zb[j * NZ + q];
-        if (j == 0) G0[r * 7 + q] += coef;
-        else Mq[((j - 1) * 5 + q) * NC + r] += coef;
-      }
+      for (int j = 0; j < NK; ++j) pl += S.cA[j][k] * zb[j * NZ + q];
+      G0[r * 7 + q] += S.cA[0][k] * idt;
       gd[r] = -pl * idt * idt;
       rr[r] = W.c[L.YCOL(a, q, n0 + k)];
-      double dfz[NZ] = {0, 0, 0, 0, 0, 0, 0};  // df_q/d(z,u) at node k
-      if (q == 0) dfz[2] = -v * sn, dfz[3] = cs;
-      else if (q == 1) dfz[2] = v * cs, dfz[3] = sn;
-      else if (q == 2) dfz[3] = tde / S.wb, dfz[4] = v * sec2 / S.wb;
-      else if (q == 3) dfz[5] = 1.0;
-      else dfz[6] = 1.0;
-      for (int m = 2; m < NZ; ++m) {
-        if (dfz[m] == 0.0) continue;
-        if (k == 0) G0[r * 7 + m] -= dfz[m];
-        else if (m < 5) Mq[((k - 1) * 5 + m) * NC + r] -= dfz[m];
-        // k >= 1, m = 5, 6: the -1 on (a_k, w_k) makes rows (k, 3), (k, 4) the defining rows of the controls (not stored)
+      if (k == 0) {
+        // rows of node 0: collocation coefficients on the stage variables, dynamics derivatives on xi
+        for (int j = 1; j < NK; ++j) Mq[OBCA_VROW(j, q) * NC + r] = S.cA[j][0] * idt;
+        if (q == 0) G0[r * 7 + 2] -= -v * sn, G0[r * 7 + 3] -= cs;
+        else if (q == 1) G0[r * 7 + 2] -= v * cs, G0[r * 7 + 3] -= sn;
+        else if (q == 2) G0[r * 7 + 3] -= tde / S.wb, G0[r * 7 + 4] -= v * sec2 / S.wb;
+        else if (q == 3) G0[r * 7 + 5] -= 1.0;
+        else G0[r * 7 + 6] -= 1.0;
+      } else if (q == 0) {
+        // rows (k >= 1, q) are the defining rows of (x, y, psi, a, w)_k and are never stored; node data for their elimination
+        double* nd = ndv + (k - 1) * 5;
+        nd[0] = cs, nd[1] = sn, nd[2] = tde / S.wb, nd[3] = v * sec2 / S.wb, nd[4] = v;
       }
     } else if (lane == 30) {
       int r = 30;
       if (last) {
         if (L.heading[a]) {
-          Mq[(20 + 2) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, 0)];
+          Mq[OBCA_VROW(5, 2) * NC + r] = 1.0, gd[r] = 0, rr[r] = W.c[L.YTERM(a, 0)];
           ++r;
         }
         for (int m = 3; m < NZ; ++m, ++r) {
-          if (m < 5) Mq[(20 + m) * NC + r] = 1.0;
+          if (m < 5) Mq[OBCA_VROW(5, m) * NC + r] = 1.0;
           else bu[(m - 5) * NC + r] = 1.0;
           gd[r] = 0, rr[r] = W.c[L.YTERM(a, m - 2)];
         }
       }
       for (int e = 0; e < nex; ++e, ++r) {
         const double* h = ex + 1 + e * 9;
-        for (int m = 0; m < 5; ++m) Mq[(20 + m) * NC + r] = h[m];
+        for (int m = 0; m < 5; ++m) Mq[OBCA_VROW(5, m) * NC + r] = h[m];
         bu[r] = h[5], bu[NC + r] = h[6];
         gd[r] = h[7], rr[r] = h[8];
       }
     }
   }
   OBCA_WARP_SYNC();
-  // Controls of the nodes 1..K: row (k, 3) reads  -a_k + sum_j cA[j][k]/dt v_j + ... = -r, row (k, 4) the same for (w_k, delta_j),
-  // so a_k, w_k are affine in the states and are eliminated exactly; they also appear in the terminal / implied rows (node K),
-  // where they are substituted.  The QR below then works on the 25 states and the 20 (+ terminal + implied) remaining rows.
+  // Exact eliminations, one lane per remaining row r (rows of node 0, terminal rows, implied rows):
+  //  (1) controls: row (k, 3) reads -a_k + sum_j cA[j][k]/dt v_j + ... = -r (row (k, 4): w_k, delta_j), so a_k, w_k are affine in
+  //      the states; they appear in the terminal / implied rows of node K, where they are substituted;
+  //  (2) (x, y, psi): rows (k, 0..2), k >= 1, have the constant interior collocation block C = cA'/dt on them (plus the
+  //      psi_k terms of the x and y rows), B = [[C, 0, Dx], [0, C, Dy], [0, 0, C]]; with W = M B^-1 the rows become
+  //      K - W N on (v, delta).  W overwrites M (it is needed again for the multipliers).
+  // The QR below then sees 10 variables and 5 (+ terminal + implied) rows, and a rank deficiency (standing vehicle) can only
+  // show up there: the eliminated blocks are nonsingular whatever the state.
   OBCA_LANES(lane) {
-    const int r = 30 + lane;
-    if (r < nr) {
-      const double ba = bu[r], bw = bu[NC + r];
-      for (int j = 1; j < NK; ++j) {
-        const double coef = S.cA[j][5] * idt;
-        Mq[((j - 1) * 5 + 3) * NC + r] += ba * coef;
-        Mq[((j - 1) * 5 + 4) * NC + r] += bw * coef;
+    const int r = lane < 5 ? lane : 30 + lane - 5;
+    if (r < nr && lane < 5 + NC - 30) {
+      if (r >= 30) {
+        const double ba = bu[r], bw = bu[NC + r];
+        for (int j = 1; j < NK; ++j) {
+          const double coef = S.cA[j][5] * idt;
+          Mq[OBCA_VROW(j, 3) * NC + r] += ba * coef;
+          Mq[OBCA_VROW(j, 4) * NC + r] += bw * coef;
+        }
+        G0[r * 7 + 3] += ba * S.cA[0][5] * idt, G0[r * 7 + 4] += bw * S.cA[0][5] * idt;
+        gd[r] += ba * gd[28] + bw * gd[29];
+        rr[r] += ba * rr[28] + bw * rr[29];
       }
-      G0[r * 7 + 3] += ba * S.cA[0][5] * idt, G0[r * 7 + 4] += bw * S.cA[0][5] * idt;
-      gd[r] += ba * gd[28] + bw * gd[29];
-      rr[r] += ba * rr[28] + bw * rr[29];
+      // scale of the row before the elimination: the rank test below must not accept a row that cancelled to rounding noise
+      {
+        double sq = 0;
+        for (int q = 0; q < NQ; ++q) sq += Mq[q * NC + r] * Mq[q * NC + r];
+        rref[r] = sqrt(sq);
+      }
+      double wx[5], wy[5], wp[5], t[5];
+      for (int k = 0; k < 5; ++k) {
+        double sx = 0, sy = 0;
+        for (int j = 0; j < 5; ++j) sx += Mq[(10 + j) * NC + r] * S.cAi[j][k], sy += Mq[(15 + j) * NC + r] * S.cAi[j][k];
+        wx[k] = sx * dt, wy[k] = sy * dt;
+      }
+      for (int j = 0; j < 5; ++j) {
+        const double* nd = ndv + j * 5;  // Dx = v sin(psi), Dy = -v cos(psi)
+        t[j] = Mq[(20 + j) * NC + r] - wx[j] * nd[4] * nd[1] + wy[j] * nd[4] * nd[0];
+      }
+      for (int k = 0; k < 5; ++k) {
+        double sp = 0;
+        for (int j = 0; j < 5; ++j) sp += t[j] * S.cAi[j][k];
+        wp[k] = sp * dt;
+      }
+      double g0 = 0, g1 = 0, g2 = 0, sgd = 0, srr = 0;
+      for (int k = 0; k < 5; ++k) {
+        const double* nd = ndv + k * 5;
+        Mq[(10 + k) * NC + r] = wx[k], Mq[(15 + k) * NC + r] = wy[k], Mq[(20 + k) * NC + r] = wp[k];
+        // N: row (k,0) has -cos on v_k, row (k,1) -sin on v_k, row (k,2) -tan/wb on v_k and -v sec^2/wb on delta_k
+        Mq[(k * 2 + 0) * NC + r] += wx[k] * nd[0] + wy[k] * nd[1] + wp[k] * nd[2];
+        Mq[(k * 2 + 1) * NC + r] += wp[k] * nd[3];
+        const double c0 = S.cA[0][k + 1] * idt;
+        g0 += wx[k] * c0, g1 += wy[k] * c0, g2 += wp[k] * c0;
+        const int rd = (k + 1) * 5;
+        sgd += wx[k] * gd[rd] + wy[k] * gd[rd + 1] + wp[k] * gd[rd + 2];
+        srr += wx[k] * rr[rd] + wy[k] * rr[rd + 1] + wp[k] * rr[rd + 2];
+      }
+      G0[r * 7 + 0] -= g0, G0[r * 7 + 1] -= g1, G0[r * 7 + 2] -= g2;
+      gd[r] -= sgd, rr[r] -= srr;
     }
   }
   OBCA_WARP_SYNC();
@@ -592,13 +641,13 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   // Householder QR with rank test (LAPACK dgeqr2 reflector convention: v[rk] = 1 implicit)
   int rk = 0, ndrop = 0, nem = 0;
   for (int j = 0; j < nr; ++j) {
-    if (j >= 5 && j < 30 && j % 5 >= 3) continue;  // defining rows of the eliminated controls
+    if (j >= 5 && j < 30) continue;  // defining rows of the eliminated variables
     double full = 0, nrm = 0;
 #if defined(__CUDA_ARCH__)
     {
       const int lane = ctx.tid & 31;
       double head = 0, tail = 0;
-      for (int q = lane; q < NQ; q += 32) {
+      for (int q = lane; q < NU2; q += 32) {
         double v = Mq[q * NC + j];
         if (q < rk) head += v * v;
         else if (q > rk) tail += v * v;
@@ -611,19 +660,19 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
       full = head, nrm = tail;
     }
 #else
-    for (int q = 0; q < NQ; ++q) {
+    for (int q = 0; q < NU2; ++q) {
       double v = Mq[q * NC + j];
       if (q < rk) full += v * v;
       else if (q > rk) nrm += v * v;
     }
 #endif
-    double alpha = rk < NQ ? Mq[rk * NC + j] : 0.0;
+    double alpha = rk < NU2 ? Mq[rk * NC + j] : 0.0;
     double beta = sqrt(alpha * alpha + nrm);
     full = sqrt(full + alpha * alpha + nrm);
-    if (rk >= NQ || !(beta > 1e-8 * full) || !(full > 0)) {
+    if (rk >= NU2 || !(beta > 1e-8 * fmax(full, rref[j])) || !(full > 0)) {
       // dependent row j = sum_i al[i] * (staircase row i): its remainder is an implied constraint on (xi, dt)
       if (ndrop >= NDR) {
-        *ok = 0;
+        { *ok = 0; OBCA_DBG("ns fail line %d a=%d i=%d rk=%d ndrop=%d nem=%d nr=%d\n", 663, a, i, rk, ndrop, nem, nr); }
         continue;
       }
       OBCA_LANES(lane) {
@@ -657,7 +706,7 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
               misc[40] = 1.0;
               for (int m = 0; m < 9; ++m) em[1 + slot * 9 + m] = h[m];
             } else
-              *ok = 0;
+              { *ok = 0; OBCA_DBG("ns fail line %d a=%d i=%d rk=%d ndrop=%d nem=%d nr=%d\n", 697, a, i, rk, ndrop, nem, nr); }
           }
           dr[0] = (double)j, dr[1] = (double)slot, dr[2] = (double)rk;
           for (int m = 0; m < 9; ++m) dr[3 + 35 + m] = h[m];
@@ -674,40 +723,40 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     const double t = (beta - alpha) * ibeta;
     const double sc = 1.0 / (alpha - beta);
     OBCA_LANES(lane) {
-      for (int q = rk + 1 + lane; q < NQ; q += 32) Mq[q * NC + j] *= sc;
+      for (int q = rk + 1 + lane; q < NU2; q += 32) Mq[q * NC + j] *= sc;
       if (lane == 0) tau[rk] = t, piv[rk] = (double)j, Mq[rk * NC + j] = beta, wred[rk] = ibeta;
     }
     OBCA_WARP_SYNC();
     OBCA_LANES(lane) {
       for (int cc = j + 1 + lane; cc < nr; cc += 32) {
-        if (cc >= 5 && cc < 30 && cc % 5 >= 3) continue;
+        if (cc >= 5 && cc < 30) continue;
         const double* uj = Mq + j;
         double* vc = Mq + cc;
         double a0 = vc[rk * NC], a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int q = rk + 1;
-        for (; q + 3 < NQ; q += 4) {
+        for (; q + 3 < NU2; q += 4) {
           const double u0 = uj[q * NC], u1 = uj[(q + 1) * NC], u2 = uj[(q + 2) * NC], u3 = uj[(q + 3) * NC];
           const double v0 = vc[q * NC], v1 = vc[(q + 1) * NC], v2 = vc[(q + 2) * NC], v3 = vc[(q + 3) * NC];
           a0 += u0 * v0, a1 += u1 * v1, a2 += u2 * v2, a3 += u3 * v3;
         }
-        for (; q < NQ; ++q) a0 += uj[q * NC] * vc[q * NC];
+        for (; q < NU2; ++q) a0 += uj[q * NC] * vc[q * NC];
         const double sacc = ((a0 + a1) + (a2 + a3)) * t;
         vc[rk * NC] -= sacc;
         q = rk + 1;
-        for (; q + 3 < NQ; q += 4) {  // column cc != column j: load everything first, then store
+        for (; q + 3 < NU2; q += 4) {  // column cc != column j: load everything first, then store
           const double u0 = uj[q * NC], u1 = uj[(q + 1) * NC], u2 = uj[(q + 2) * NC], u3 = uj[(q + 3) * NC];
           const double v0 = vc[q * NC], v1 = vc[(q + 1) * NC], v2 = vc[(q + 2) * NC], v3 = vc[(q + 3) * NC];
           vc[q * NC] = v0 - sacc * u0, vc[(q + 1) * NC] = v1 - sacc * u1, vc[(q + 2) * NC] = v2 - sacc * u2, vc[(q + 3) * NC] = v3 - sacc * u3;
         }
-        for (; q < NQ; ++q) vc[q * NC] -= sacc * uj[q * NC];
+        for (; q < NU2; ++q) vc[q * NC] -= sacc * uj[q * NC];
       }
     }
     OBCA_WARP_SYNC();
     ++rk;
   }
-  int np = NQ - rk;
+  int np = NU2 - rk;
   if (np > NP) {
-    *ok = 0;
+    { *ok = 0; OBCA_DBG("ns fail line %d a=%d i=%d rk=%d ndrop=%d nem=%d nr=%d\n", 747, a, i, rk, ndrop, nem, nr); }
     np = NP;
   }
   prof_mark(ctx, 17);
@@ -718,13 +767,13 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
       // The column lives in registers (all indices below are compile-time constants after unrolling): the shared-memory
       // pipe, shared by the 8 warps of the CTA, then only serves the broadcast loads of R and of the reflectors.
       const int col = lane;
-      double v[NQ];
+      double v[NU2];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) v[q] = 0.0;
+      for (int q = 0; q < NU2; ++q) v[q] = 0.0;
       if (col < 9) {
         // b = -G0[:,col] (col < 7), -gd (col 7), -r (col 8); forward substitution R' w = b on the staircase
 #pragma unroll
-        for (int ii = 0; ii < NQ; ++ii) {
+        for (int ii = 0; ii < NU2; ++ii) {
           if (ii < rk) {
             const int j = (int)piv[ii];
             const double* Rj = Mq + j;
@@ -738,17 +787,17 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
       } else {
         const int jn = col - 9;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) v[q] = (jn < np && q == rk + jn) ? 1.0 : 0.0;
+        for (int q = 0; q < NU2; ++q) v[q] = (jn < np && q == rk + jn) ? 1.0 : 0.0;
       }
       if (col < 9 || col - 9 < np) {
         // v <- H_0 ... H_{rk-1} v ; reflector i = (1, u_{i+1..34}) stored below the staircase of its pivot column
 #pragma unroll
-        for (int i = NQ - 1; i >= 0; --i) {
+        for (int i = NU2 - 1; i >= 0; --i) {
           if (i < rk) {
             const double* u = Mq + (int)piv[i];
             double a0 = v[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-            for (int r = i + 1; r < NQ; ++r) {
+            for (int r = i + 1; r < NU2; ++r) {
               const double ur = u[r * NC];
               if (((r - i - 1) & 3) == 0) a0 += ur * v[r];
               else if (((r - i - 1) & 3) == 1) a1 += ur * v[r];
@@ -758,14 +807,45 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
             const double sacc = ((a0 + a1) + (a2 + a3)) * tau[i];
             v[i] -= sacc;
 #pragma unroll
-            for (int r = i + 1; r < NQ; ++r) v[r] -= sacc * u[r * NC];
+            for (int r = i + 1; r < NU2; ++r) v[r] -= sacc * u[r * NC];
           }
         }
+      }
+      // (x, y, psi) of the interior nodes from their defining rows: t = rhs - N u, psi = Ci t_psi, x = Ci (t_x - Dx psi), ...
+      double tx[5], ty[5], tp[5], ps[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double* nd = ndv + k * 5;
+        const int rd = (k + 1) * 5;
+        const double c0 = S.cA[0][k + 1] * idt;
+        const double uv = v[2 * k], ud = v[2 * k + 1];
+        double bx = col == 0 ? -c0 : (col == 7 ? -gd[rd] : (col == 8 ? -rr[rd] : 0.0));
+        double by = col == 1 ? -c0 : (col == 7 ? -gd[rd + 1] : (col == 8 ? -rr[rd + 1] : 0.0));
+        double bp = col == 2 ? -c0 : (col == 7 ? -gd[rd + 2] : (col == 8 ? -rr[rd + 2] : 0.0));
+        tx[k] = bx + nd[0] * uv, ty[k] = by + nd[1] * uv, tp[k] = bp + nd[2] * uv + nd[3] * ud;
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        double sacc = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) sacc += S.cAi[j][k] * tp[k];
+        ps[j] = sacc * dt;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double* nd = ndv + k * 5;
+        tx[k] -= nd[4] * nd[1] * ps[k], ty[k] += nd[4] * nd[0] * ps[k];
       }
       double* vo = col < 7 ? T + col : (col == 7 ? T + IDT : (col == 8 ? s0 : T + 7 + (col - 9)));
       const int stride = col == 8 ? 1 : NRED;
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) vo[((q / 5) * 7 + q % 5) * stride] = v[q];  // state rows of the 35-row stage map
+      for (int j = 0; j < 5; ++j) {
+        double sx = 0, sy = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) sx += S.cAi[j][k] * tx[k], sy += S.cAi[j][k] * ty[k];
+        vo[(j * 7 + 0) * stride] = sx * dt, vo[(j * 7 + 1) * stride] = sy * dt, vo[(j * 7 + 2) * stride] = ps[j];
+        vo[(j * 7 + 3) * stride] = v[2 * j], vo[(j * 7 + 4) * stride] = v[2 * j + 1];
+      }
     }
   }
   OBCA_WARP_SYNC();
@@ -1049,7 +1129,7 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
 // free directions of block (a, i): 35 - rank, 0 for a vehicle whose horizon has ended
 OBCA_HD int block_np(const Lay& L, const Scratch& W, int a, int i) {
   if (i >= L.N[a]) return 0;
-  int np = NQ - (int)W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_META];
+  int np = NU2 - (int)W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_META];
   return np > NP ? NP : np;
 }
 
@@ -1256,6 +1336,7 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
       double d = R.F[j * nu + j];
       const bool bad = !(d > 1e-14 * fmax(1.0, fabs(R.R[j * nu + j])));
       if (bad) d = 1.0;
+      if (bad) OBCA_DBG("riccati bad pivot stage %d j=%d nu=%d d=%.3e R=%.3e\n", i, j, nu, R.F[j * nu + j], R.R[j * nu + j]);
       const double sd = sqrt(d), inv = 1.0 / sd;
       const int n1 = nu - j - 1;
       for (int it = ctx.tid; it < n1 + nc + 1; it += ctx.nt) {  // the pivot entry itself is left untouched (only 1/L_jj is used later)
@@ -1477,13 +1558,16 @@ OBCA_HD double* block_row_multiplier(const Lay& L, const Scratch& W, int a, int 
   return &W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_NU + (r - 30 - nterm)];
 }
 
-// dy of row r of block (a, i) += d; a terminal / implied row also feeds the multipliers of the two defining rows of (a_K, w_K)
+// dy of the remaining row r (node-0, terminal or implied row) of block (a, i) += d, together with what it induces on the
+// multipliers of the defining rows of the eliminated variables
 OBCA_HD void add_row_multiplier(const Lay& L, const Scratch& W, int a, int i, int r, double d) {
   *block_row_multiplier(L, W, a, i, r) += d;
+  const double* Q = W.QR + (size_t)(a * L.Nmax + i) * QRSZ;
+  for (int k = 0; k < 5; ++k)  // y_D = z - W' y_R
+    for (int g = 0; g < 3; ++g) *block_row_multiplier(L, W, a, i, (k + 1) * 5 + g) -= Q[(10 + g * 5 + k) * NC + r] * d;
   if (r >= 30) {
-    const double* bu = W.QR + (size_t)(a * L.Nmax + i) * QRSZ + QR_BU;
-    *block_row_multiplier(L, W, a, i, 28) += bu[r] * d;
-    *block_row_multiplier(L, W, a, i, 29) += bu[NC + r] * d;
+    *block_row_multiplier(L, W, a, i, 28) += Q[QR_BU + r] * d;
+    *block_row_multiplier(L, W, a, i, 29) += Q[QR_BU + NC + r] * d;
   }
 }
 
@@ -1514,18 +1598,38 @@ OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, c
     const double* QRm = W.QR + (size_t)(a * L.Nmax + i) * QRSZ;
     const double* piv = QRm + QR_PIV;
     int rk = (int)QRm[QR_META], nr = (int)QRm[QR_META + 1];
-    double v[NW], vt[NQ], dyr[NC];
+    double v[NW], vt[NU2], dyr[NC];
     for (int r = 0; r < NW; ++r) v[r] = -W.GN[(size_t)(a * L.Mv + n0 + 1 + r / NZ) * 7 + r % NZ];
     if (i < L.N[a] - 1)
       for (int q = 0; q < NZ; ++q) v[28 + q] -= W.dy[L.YCONT(a, q, i + 1)];
-    // reduced right-hand side on the 25 states: the control equations  -y_(k,c) + sum beta y = v_(a_k | w_k)  are substituted
+    // (1) control equations  -y_(k,c) + sum beta y = v_(a_k | w_k)  substituted into the (v, delta) equations
     for (int j = 1; j < NK; ++j)
-      for (int q = 0; q < 5; ++q) {
+      for (int q = 3; q < 5; ++q) {
         double sacc = v[(j - 1) * 7 + q];
-        if (q >= 3)
-          for (int k = 1; k < NK; ++k) sacc += S.cA[j][k] * idt * v[(k - 1) * 7 + q + 2];
-        vt[(j - 1) * 5 + q] = sacc;
+        for (int k = 1; k < NK; ++k) sacc += S.cA[j][k] * idt * v[(k - 1) * 7 + q + 2];
+        v[(j - 1) * 7 + q] = sacc;
       }
+    // (2) z = B^-T v_P on the defining rows of (x, y, psi); reduced right-hand side v_U - N' z
+    double zx[5], zy[5], zp[5], nd[5][5];
+    for (int k = 0; k < 5; ++k) {
+      const int n = n0 + 1 + k;
+      const double psi = W.x[L.Z(a, 2, n)], vv = W.x[L.Z(a, 3, n)], tde = tan(W.x[L.Z(a, 4, n)]);
+      nd[k][0] = cos(psi), nd[k][1] = sin(psi), nd[k][2] = tde / S.wb, nd[k][3] = vv * (1.0 + tde * tde) / S.wb, nd[k][4] = vv;
+    }
+    for (int k = 0; k < 5; ++k) {
+      double sx = 0, sy = 0;
+      for (int j = 0; j < 5; ++j) sx += S.cAi[j][k] * v[j * 7 + 0], sy += S.cAi[j][k] * v[j * 7 + 1];
+      zx[k] = sx * dt, zy[k] = sy * dt;
+    }
+    for (int k = 0; k < 5; ++k) {
+      double sp = 0;
+      for (int j = 0; j < 5; ++j) sp += S.cAi[j][k] * (v[j * 7 + 2] - nd[j][4] * nd[j][1] * zx[j] + nd[j][4] * nd[j][0] * zy[j]);
+      zp[k] = sp * dt;
+    }
+    for (int k = 0; k < 5; ++k) {
+      vt[2 * k] = v[k * 7 + 3] + nd[k][0] * zx[k] + nd[k][1] * zy[k] + nd[k][2] * zp[k];
+      vt[2 * k + 1] = v[k * 7 + 4] + nd[k][3] * zp[k];
+    }
     apply_q(QRm, rk, vt, true);
     // R dy = vt[0:rk] on the staircase; dropped (dependent) rows keep dy = 0 here
     for (int r = 0; r < nr; ++r) dyr[r] = 0;
@@ -1537,6 +1641,15 @@ OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, c
         s -= QRm[ii * NC + jm] * dyr[jm];
       }
       dyr[j] = s / QRm[ii * NC + j];
+    }
+    // defining rows of (x, y, psi): y_D = z - W' y_R
+    for (int k = 0; k < 5; ++k) {
+      double sx = zx[k], sy = zy[k], sp = zp[k];
+      for (int r = 0; r < nr; ++r) {
+        if (r >= 5 && r < 30) continue;
+        sx -= QRm[(10 + k) * NC + r] * dyr[r], sy -= QRm[(15 + k) * NC + r] * dyr[r], sp -= QRm[(20 + k) * NC + r] * dyr[r];
+      }
+      dyr[(k + 1) * 5 + 0] = sx, dyr[(k + 1) * 5 + 1] = sy, dyr[(k + 1) * 5 + 2] = sp;
     }
     // defining rows of the controls
     for (int k = 1; k < NK; ++k)
