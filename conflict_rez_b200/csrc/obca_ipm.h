@@ -210,6 +210,9 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
   int status = OBCA_MAXITER_EXCEEDED, it = 0;
   double dual_inf = 0, cviol = 0, compl0 = 0;
   const Stage st = {RW, rw_cap, sh->bars};
+  // barrier terms of the current iterate: carried over from the accepted trial point (bit-identical x), recomputed otherwise
+  double bar_cur = 0.0;
+  bool bar_valid = false;
   for (;;) {
     // ---- error measures at the current iterate (c, gl, f are up to date)
     double e_du = 0, e_c = 0, e_c1 = 0, s_y = 0, s_z = 0, cmax0 = 0, cmaxmu_lo = INFINITY, cmaxmu_hi = 0;
@@ -224,17 +227,22 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
           const double gp = xv - lo, pr = gp * zl;
           cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
           s_z += zl;
-          s_log -= log(gp);
-          if (!hu) s_gap += gp;
+          if (!bar_valid) {
+            s_log -= log(gp);
+            if (!hu) s_gap += gp;
+          }
         }
         if (hu) {
           const double gp = hi - xv, pr = gp * zu;
           cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
           s_z += zu;
-          s_log -= log(gp);
-          if (!hl) s_gap += gp;
+          if (!bar_valid) {
+            s_log -= log(gp);
+            if (!hl) s_gap += gp;
+          }
         }
       });
+      prof_mark(ctx, 21);
     }
 #pragma unroll 4
     for (int q = ctx.tid; q < L.ny; q += ctx.nt) {
@@ -247,8 +255,12 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     double theta = cta_sum(ctx, e_c1);
     s_y = cta_sum(ctx, s_y);
     s_z = cta_sum(ctx, s_z);
-    s_log = cta_sum(ctx, s_log);
-    s_gap = cta_sum(ctx, s_gap);
+    if (!bar_valid) {
+      s_log = cta_sum(ctx, s_log);
+      s_gap = cta_sum(ctx, s_gap);
+      bar_cur = s_log + o.kappa_d * s_gap;
+      bar_valid = true;
+    }
     compl0 = cta_max(ctx, cmax0);
     double pr_lo = cta_min(ctx, cmaxmu_lo), pr_hi = cta_max(ctx, cmaxmu_hi);
     double s_d = fmax(o.s_max, (s_y + s_z) / fmax(1.0, (double)(cnt.m_active + cnt.nb))) / o.s_max;
@@ -297,7 +309,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     cta_sync(ctx);
     const double tau = fmax(o.tau_min, 1.0 - mu);
     // ---- gradient of the barrier Lagrangian, barrier objective and grad_phi'dx bookkeeping
-    const double phi = f + mu * (s_log + o.kappa_d * s_gap);  // the iterate is strictly inside its bounds
+    const double phi = f + mu * bar_cur;  // the iterate is strictly inside its bounds
     // ---- search direction with inertia correction
     double dw = 0.0;
     bool first = true, have = false;
@@ -309,19 +321,20 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
           const bool hl = lo > -INFINITY, hu = hi < INFINITY;
           double sg = dw, gp = v[5];
           if (hl) {
-            const double gpL = xv - lo;
-            sg += zl / gpL;
-            gp -= mu / gpL;
+            const double iL = 1.0 / (xv - lo);
+            sg += zl * iL;
+            gp -= mu * iL;
             if (!hu) gp += o.kappa_d * mu;
           }
           if (hu) {
-            const double gpU = hi - xv;
-            sg += zu / gpU;
-            gp += mu / gpU;
+            const double iU = 1.0 / (hi - xv);
+            sg += zu * iU;
+            gp += mu * iU;
             if (!hl) gp -= o.kappa_d * mu;
           }
           W.sig[q] = sg, W.gphi[q] = gp;
         });
+      prof_mark(ctx, 22);
       }
       cta_sync(ctx);
       if (model_kkt<MODE>(ctx, L, S, W, RW, &sh->ok)) {
@@ -341,26 +354,27 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     }
     if (dw > 0) dw_last = dw;
     // ---- dz, fraction to the boundary, directional derivative of the barrier objective
-    double a_pr = 1.0, a_du = 1.0, dphi = 0, rel = 0;
+    double a_pr = 1.0, a_du = 1.0, dphi = 0, rel = 0, r_pr = 0;
     {
       const double* const src[7] = {xL, xU, W.x, W.zL, W.zU, W.gphi, W.dx};
       flat_pass<7>(ctx, st, src, L.nx, [&](int, const double* v) {
         const double lo = v[0], hi = v[1], xv = v[2], zl = v[3], zu = v[4], d = v[6];
         rel = fmax(rel, fabs(d) / (1.0 + fabs(xv)));
         if (lo > -INFINITY) {
-          const double gp = xv - lo;
-          const double dz = mu / gp - zl - zl / gp * d;
-          if (d < 0) a_pr = fmin(a_pr, -tau * gp / d);
+          const double ig = 1.0 / (xv - lo);
+          const double dz = (mu - zl * d) * ig - zl;
+          r_pr = fmax(r_pr, -d * ig);            // alpha_pr = tau / max(-d / gap)
           if (dz < 0) a_du = fmin(a_du, -tau * zl / dz);
         }
         if (hi < INFINITY) {
-          const double gp = hi - xv;
-          const double dz = mu / gp - zu + zu / gp * d;
-          if (d > 0) a_pr = fmin(a_pr, tau * gp / d);
+          const double ig = 1.0 / (hi - xv);
+          const double dz = (mu + zu * d) * ig - zu;
+          r_pr = fmax(r_pr, d * ig);
           if (dz < 0) a_du = fmin(a_du, -tau * zu / dz);
         }
         dphi += v[5] * d;
       });
+      prof_mark(ctx, 23);
     }
     // grad_phi'dx = (gphi)'dx - y'J dx ; J dx = -c - (local delta_c terms, negligible) => use the exact product:
     // y'J dx is accumulated from the structure: J dx = -(c) on all rows up to delta_c * dy.
@@ -368,7 +382,8 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     for (int q = ctx.tid; q < L.ny; q += ctx.nt) yJdx += W.y[q] * (-W.c[q]);
     for (int q = ctx.tid; q < L.V * L.O * 4 * L.Mv; q += ctx.nt) yJdx += W.y[L.oYOBS + q] * DELTA_C_LOCAL * W.dy[L.oYOBS + q];
     for (int q = ctx.tid; q < L.P * 6 * L.Mv; q += ctx.nt) yJdx += W.y[L.oYPAIR + q] * DELTA_C_LOCAL * W.dy[L.oYPAIR + q];
-    a_pr = cta_min(ctx, a_pr);
+    r_pr = cta_max(ctx, r_pr);
+    if (r_pr > tau) a_pr = tau / r_pr;
     a_du = cta_min(ctx, a_du);
     rel = cta_max(ctx, rel);
     dphi = cta_sum(ctx, dphi) - cta_sum(ctx, yJdx);
@@ -413,6 +428,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       tiny_last = true, force_mu = true;
       for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.xt[q] = W.x[q] + alpha * W.dx[q];
       accepted = true;
+      bar_valid = false;  // no trial evaluation: the barrier terms are recomputed in the next error pass
     } else
       tiny_last = false;
     while (alpha >= a_min && !accepted) {
@@ -421,6 +437,9 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       int bad = 0;
       {
         const double* const src[4] = {xL, xU, W.x, W.dx};
+        // sum of log(gap) as log of products: the gaps of four consecutive elements of a thread (up to 8 factors, each within
+        // [1e-12, 1e2]) are multiplied and one log is taken for the group; all lanes flush at the same elements
+        double prod = 1.0;
         flat_pass<4>(ctx, st, src, L.nx, [&](int q, const double* v) {
           const double lo = v[0], hi = v[1];
           const double xn = v[2] + alpha * v[3];
@@ -429,23 +448,27 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
           if (hl) {
             const double gp = xn - lo;
             if (gp <= 0) bad = 1;
-            else sbar -= log(gp);
+            else prod *= gp;
             if (!hu) sbar += o.kappa_d * gp;
           }
           if (hu) {
             const double gp = hi - xn;
             if (gp <= 0) bad = 1;
-            else sbar -= log(gp);
+            else prod *= gp;
             if (!hl) sbar += o.kappa_d * gp;
           }
+          if (((q / ctx.nt) & 3) == 3) sbar -= log(prod), prod = 1.0;
         });
+        sbar -= log(prod);
       }
+      prof_mark(ctx, 24);
       cta_sync(ctx);
       model_eval<MODE>(ctx, L, S, W, W.xt, nullptr, W.ct, nullptr, &ft, &gdt_t);
       double tht = 0;
 #pragma unroll 4
       for (int q = ctx.tid; q < L.ny; q += ctx.nt) tht += fabs(W.ct[q]);
       tht = cta_sum(ctx, tht);
+      prof_mark(ctx, 25);
       sbar = cta_sum(ctx, sbar);
       const double pht = cta_max(ctx, (double)bad) > 0 ? INFINITY : ft + mu * sbar;
       bool okp = finite_d(pht) && finite_d(tht) && tht <= theta_max;
@@ -459,6 +482,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
         if (switching) {
           if (pht - (phi + o.eta_phi * alpha * dphi) <= slack_phi) {
             accepted = true;
+            bar_cur = sbar;
             break;
           }
         } else if (tht - (1 - o.gamma_theta) * theta <= slack_th || pht - (phi - o.gamma_phi * theta) <= slack_phi) {
@@ -469,6 +493,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
             sh->filt_n++;
           }
           accepted = true;
+          bar_cur = sbar;
           break;
         }
       }
@@ -483,6 +508,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       break;
     }
     // ---- accept the trial point (dz is recomputed from dx; x + alpha dx reproduces the trial point bit for bit)
+    const double iks = 1.0 / o.kappa_sigma;
     {
       const double* const src[6] = {xL, xU, W.x, W.zL, W.zU, W.dx};
       flat_pass<6>(ctx, st, src, L.nx, [&](int q, const double* v) {
@@ -490,16 +516,17 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
         const double xn = xv + alpha * d;
         W.x[q] = xn;
         if (lo > -INFINITY) {
-          const double gp0 = xv - lo, gp = xn - lo;
-          const double zv = zl + a_du * (mu / gp0 - zl - zl / gp0 * d);
-          W.zL[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
+          const double i0 = 1.0 / (xv - lo), mg = mu / (xn - lo);
+          const double zv = zl + a_du * ((mu - zl * d) * i0 - zl);
+          W.zL[q] = fmin(fmax(zv, mg * iks), o.kappa_sigma * mg);
         }
         if (hi < INFINITY) {
-          const double gp0 = hi - xv, gp = hi - xn;
-          const double zv = zu + a_du * (mu / gp0 - zu + zu / gp0 * d);
-          W.zU[q] = fmin(fmax(zv, mu / (o.kappa_sigma * gp)), o.kappa_sigma * mu / gp);
+          const double i0 = 1.0 / (hi - xv), mg = mu / (hi - xn);
+          const double zv = zu + a_du * ((mu + zu * d) * i0 - zu);
+          W.zU[q] = fmin(fmax(zv, mg * iks), o.kappa_sigma * mg);
         }
       });
+      prof_mark(ctx, 26);
     }
     for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.y[q] += alpha * W.dy[q];
     cta_sync(ctx);
