@@ -1279,30 +1279,34 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     prof_mark(ctx, 6);
     riccati_stage_assemble(ctx, L, W, R, i, hdtdt, nu);
     prof_mark(ctx, 12);
-    // PA = P A ; PB = P B ; pc = P c + p   (block structure of A, B)
-    for (int it = ctx.tid; it < nX * (nX + nu + 1); it += ctx.nt) {
-      int r = it / (nX + nu + 1), col = it % (nX + nu + 1);
+    // PA = P A ; PB = P B ; pc = P c + p   (block structure of A, B).  The 7-term items and the two dense columns (dt and the
+    // constant) are separate loops so that the lanes of a warp do the same amount of work; the dense ones go to the last threads.
+    for (int it = ctx.tid; it < nX * (idt + nu); it += ctx.nt) {
+      const int r = it / (idt + nu), col = it % (idt + nu);
       const double* Pr = R.P + r * nX;
       double s = 0;
       if (col < idt) {
-        int a = col / 7, c = col % 7;
+        const int a = col / 7, c = col % 7;
         for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Ab[a * 49 + m * 7 + c];
         R.PA[r * nX + col] = s;
-      } else if (col == idt) {
-        s = Pr[idt];
-        for (int m = 0; m < idt; ++m) s += Pr[m] * R.db[m];
-        R.PA[r * nX + idt] = s;
-      } else if (col < nX + nu) {
-        int u = col - nX, a = 0;
+      } else {
+        int u = col - idt, a = 0;
         while (u >= R.uoff[a + 1]) ++a;
-        int j = u - R.uoff[a];
+        const int j = u - R.uoff[a];
         for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Bb[(a * 7 + m) * NP + j];
         R.PB[r * nu + u] = s;
-      } else {
-        s = R.p[r];
-        for (int m = 0; m < idt; ++m) s += Pr[m] * R.cb[m];
-        R.pc[r] = s;
       }
+    }
+    for (int it = ctx.nt - 1 - ctx.tid; it < 2 * nX; it += ctx.nt) {
+      const int r = it >> 1;
+      const double* Pr = R.P + r * nX;
+      const double* vec = (it & 1) ? R.cb : R.db;
+      double s0 = (it & 1) ? R.p[r] : Pr[idt], s1 = 0;
+      int m = 0;
+      for (; m + 1 < idt; m += 2) s0 += Pr[m] * vec[m], s1 += Pr[m + 1] * vec[m + 1];
+      if (m < idt) s0 += Pr[m] * vec[m];
+      if (it & 1) R.pc[r] = s0 + s1;
+      else R.PA[r * nX + idt] = s0 + s1;
     }
     cta_sync(ctx);
     // F = R + B'PB ; Gm = [S + B'PA | r + B'pc]
@@ -1382,30 +1386,42 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
         else Kg[nUmax * nX + u] = R.K[it];
       }
     }
-    // P <- Q + A'PA + Gm'K ; p <- q + A'pc + Gm'k   (written into Q/q first, then copied: P is still needed)
-    for (int it = ctx.tid; it < nX * (nX + 1); it += ctx.nt) {
-      int r = it / (nX + 1), col = it % (nX + 1);
-      double s = 0;
-      if (col < nX) {
+    // P <- Q + A'PA + Gm'K ; p <- q + A'pc + Gm'k   (written into Q/q first, then copied: P is still needed).
+    // P is symmetric: only col >= r is computed (rows r and nX-1-r share one strip of nX+1 items) and mirrored; item nX of
+    // the strips < nX is the gradient entry.  The dense dt row only occurs in the items (dt, dt) and p[dt].
+    {
+      const int np1 = nX + 1, nstrip = (nX + 1) / 2;
+      for (int it = ctx.tid; it < nstrip * np1 + nX; it += ctx.nt) {
+        int r, col;
+        if (it < nstrip * np1) {
+          const int p = it / np1, e = it % np1;
+          if (e < nX - p) r = p, col = p + e;
+          else {
+            r = nX - 1 - p, col = r + (e - (nX - p));
+            if (r == p) continue;  // middle row of an odd dimension: already covered
+          }
+        } else
+          r = it - nstrip * np1, col = nX;
+        double s = 0;
+        const double* rhs = col < nX ? R.PA + col : R.pc;  // column of PA (stride nX) or pc (stride 1)
+        const int rs = col < nX ? nX : 1;
         if (r < idt) {
-          int a = r / 7, rr = r % 7;
-          for (int m = 0; m < 7; ++m) s += R.Ab[a * 49 + m * 7 + rr] * R.PA[(7 * a + m) * nX + col];
+          const int a = r / 7, rr = r % 7;
+          for (int m = 0; m < 7; ++m) s += R.Ab[a * 49 + m * 7 + rr] * rhs[(7 * a + m) * rs];
         } else {
-          s = R.PA[idt * nX + col];
-          for (int m = 0; m < idt; ++m) s += R.db[m] * R.PA[m * nX + col];
+          s = rhs[idt * rs];
+          for (int m = 0; m < idt; ++m) s += R.db[m] * rhs[m * rs];
         }
-        for (int m = 0; m < nu; ++m) s += R.Gm[m * (nX + 1) + r] * R.K[m * (nX + 1) + col];
-        R.Q[r * nX + col] += s;
-      } else {
-        if (r < idt) {
-          int a = r / 7, rr = r % 7;
-          for (int m = 0; m < 7; ++m) s += R.Ab[a * 49 + m * 7 + rr] * R.pc[7 * a + m];
-        } else {
-          s = R.pc[idt];
-          for (int m = 0; m < idt; ++m) s += R.db[m] * R.pc[m];
-        }
-        for (int m = 0; m < nu; ++m) s += R.Gm[m * (nX + 1) + r] * R.K[m * (nX + 1) + nX];
-        R.q[r] += s;
+        double s1 = 0;
+        int m = 0;
+        for (; m + 1 < nu; m += 2) s += R.Gm[m * np1 + r] * R.K[m * np1 + col], s1 += R.Gm[(m + 1) * np1 + r] * R.K[(m + 1) * np1 + col];
+        if (m < nu) s += R.Gm[m * np1 + r] * R.K[m * np1 + col];
+        s += s1;
+        if (col < nX) {
+          const double v = R.Q[r * nX + col] + s;
+          R.Q[r * nX + col] = v, R.Q[col * nX + r] = v;
+        } else
+          R.q[r] += s;
       }
     }
     cta_sync(ctx);
