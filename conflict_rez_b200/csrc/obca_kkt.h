@@ -1336,12 +1336,19 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     const int nc = nX + 1;
     for (int it = ctx.tid; it < nu * nc; it += ctx.nt) R.K[it] = R.Gm[it];
     cta_sync(ctx);
+    // thread -> (row group rg, column c): c < 64 covers the n1 trailing columns of F and the nc columns of K without any
+    // integer division in the loops; every thread keeps its column
+    const int c64 = ctx.tid & 63, rg = ctx.tid >> 6, nrg = ctx.nt >> 6 > 0 ? ctx.nt >> 6 : 1;
     for (int j = 0; j < nu; ++j) {
       double d = R.F[j * nu + j];
       const bool bad = !(d > 1e-14 * fmax(1.0, fabs(R.R[j * nu + j])));
-      if (bad) d = 1.0;
       if (bad) OBCA_DBG("riccati bad pivot stage %d j=%d nu=%d d=%.3e R=%.3e\n", i, j, nu, R.F[j * nu + j], R.R[j * nu + j]);
-      const double sd = sqrt(d), inv = 1.0 / sd;
+      if (bad) d = 1.0;
+#if defined(__CUDA_ARCH__)
+      const double inv = rsqrt(d);
+#else
+      const double inv = 1.0 / sqrt(d);
+#endif
       const int n1 = nu - j - 1;
       for (int it = ctx.tid; it < n1 + nc + 1; it += ctx.nt) {  // the pivot entry itself is left untouched (only 1/L_jj is used later)
         if (it < n1) R.F[(j + 1 + it) * nu + j] *= inv;
@@ -1352,16 +1359,30 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
         }
       }
       cta_sync(ctx);
-      for (int it = ctx.tid; it < n1 * (n1 + nc); it += ctx.nt) {
-        const int r = j + 1 + it / (n1 + nc), c = it % (n1 + nc);
-        const double lrj = R.F[r * nu + j];
-        if (c < n1) {
-          const int cc = j + 1 + c;
-          if (cc <= r) R.F[r * nu + cc] -= lrj * R.F[cc * nu + j];
-        } else
-          R.K[r * nc + (c - n1)] -= lrj * R.K[j * nc + (c - n1)];
+#if defined(__CUDA_ARCH__)
+      if (n1 + nc <= 64) {
+        if (c64 < n1) {
+          const int cc = j + 1 + c64;
+          const double lcj = R.F[cc * nu + j];
+          for (int r = cc + rg; r < nu; r += nrg) R.F[r * nu + cc] -= R.F[r * nu + j] * lcj;
+        } else if (c64 < n1 + nc) {
+          const int c = c64 - n1;
+          const double kj = R.K[j * nc + c];
+          for (int r = j + 1 + rg; r < nu; r += nrg) R.K[r * nc + c] -= R.F[r * nu + j] * kj;
+        }
+      } else
+#endif
+      {
+        for (int it = ctx.tid; it < n1 * (n1 + nc); it += ctx.nt) {
+          const int r = j + 1 + it / (n1 + nc), c = it % (n1 + nc);
+          const double lrj = R.F[r * nu + j];
+          if (c < n1) {
+            const int cc = j + 1 + c;
+            if (cc <= r) R.F[r * nu + cc] -= lrj * R.F[cc * nu + j];
+          } else
+            R.K[r * nc + (c - n1)] -= lrj * R.K[j * nc + (c - n1)];
+        }
       }
-      // the next pivot read is ordered by the barrier at the top of the next iteration's scaling phase
       cta_sync(ctx);
     }
     prof_mark(ctx, 14);
