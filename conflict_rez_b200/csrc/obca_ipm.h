@@ -244,11 +244,13 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       });
       prof_mark(ctx, 21);
     }
-#pragma unroll 4
-    for (int q = ctx.tid; q < L.ny; q += ctx.nt) {
-      e_c = fmax(e_c, fabs(W.c[q]));
-      e_c1 += fabs(W.c[q]);
-      s_y += fabs(W.y[q]);
+    {
+      const double* const src[2] = {W.c, W.y};
+      flat_pass<2>(ctx, st, src, L.ny, [&](int, const double* v) {
+        e_c = fmax(e_c, fabs(v[0]));
+        e_c1 += fabs(v[0]);
+        s_y += fabs(v[1]);
+      });
     }
     dual_inf = cta_max(ctx, e_du);
     cviol = cta_max(ctx, e_c);
@@ -379,9 +381,14 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     // grad_phi'dx = (gphi)'dx - y'J dx ; J dx = -c - (local delta_c terms, negligible) => use the exact product:
     // y'J dx is accumulated from the structure: J dx = -(c) on all rows up to delta_c * dy.
     double yJdx = 0;
-    for (int q = ctx.tid; q < L.ny; q += ctx.nt) yJdx += W.y[q] * (-W.c[q]);
-    for (int q = ctx.tid; q < L.V * L.O * 4 * L.Mv; q += ctx.nt) yJdx += W.y[L.oYOBS + q] * DELTA_C_LOCAL * W.dy[L.oYOBS + q];
-    for (int q = ctx.tid; q < L.P * 6 * L.Mv; q += ctx.nt) yJdx += W.y[L.oYPAIR + q] * DELTA_C_LOCAL * W.dy[L.oYPAIR + q];
+    {
+      const int o0 = L.oYOBS, o1 = L.oYOBS + L.V * L.O * 4 * L.Mv, p0 = L.oYPAIR, p1 = L.oYPAIR + L.P * 6 * L.Mv;
+      const double* const src[3] = {W.y, W.c, W.dy};
+      flat_pass<3>(ctx, st, src, L.ny, [&](int q, const double* v) {
+        yJdx -= v[0] * v[1];
+        if ((q >= o0 && q < o1) || (q >= p0 && q < p1)) yJdx += v[0] * DELTA_C_LOCAL * v[2];
+      });
+    }
     r_pr = cta_max(ctx, r_pr);
     if (r_pr > tau) a_pr = tau / r_pr;
     a_du = cta_min(ctx, a_du);
@@ -465,8 +472,10 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       cta_sync(ctx);
       model_eval<MODE>(ctx, L, S, W, W.xt, nullptr, W.ct, nullptr, &ft, &gdt_t);
       double tht = 0;
-#pragma unroll 4
-      for (int q = ctx.tid; q < L.ny; q += ctx.nt) tht += fabs(W.ct[q]);
+      {
+        const double* const src[1] = {W.ct};
+        flat_pass<1>(ctx, st, src, L.ny, [&](int, const double* v) { tht += fabs(v[0]); });
+      }
       tht = cta_sum(ctx, tht);
       prof_mark(ctx, 25);
       sbar = cta_sum(ctx, sbar);
@@ -528,7 +537,10 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       });
       prof_mark(ctx, 26);
     }
-    for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.y[q] += alpha * W.dy[q];
+    {
+      const double* const src[2] = {W.y, W.dy};
+      flat_pass<2>(ctx, st, src, L.ny, [&](int q, const double* v) { W.y[q] = v[0] + alpha * v[1]; });
+    }
     cta_sync(ctx);
     model_eval<MODE>(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
     ++it;
