@@ -1014,6 +1014,7 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, dou
   double* sa = tb + NK * 3 * NRED;  // [6][3] pose entries of s0a
   double* sb = sa + NK * 3;         // [6][3]
   double* hc = sb + NK * 3;         // [6][9] rows pose_a, cols pose_b
+  double* hb = hc + NK * 9;         // [18][NRED + 1] Hc Tb and Hc s0b
   for (int it = wid; it < L.P * L.Nmax && wid < nw; it += nw) {
     int p = it / L.Nmax, i = it % L.Nmax;
     if (i * NK >= L.Mp[p]) continue;
@@ -1039,26 +1040,30 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, dou
     OBCA_WARP_SYNC();
     double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
     OBCA_LANES(lane) {
+      // HB[k][r][cb] = sum_m Hc_k[r][m] Tb_k[m][cb] first (and Hc_k s0b), then Mab = sum_{k,r} Ta_k[r][ra] HB[k][r][cb]:
+      // 18 terms per entry instead of 72
+      for (int e = lane; e < NK * 3 * (NRED + 1); e += 32) {
+        const int kr = e / (NRED + 1), cb = e % (NRED + 1), k = kr / 3;
+        double h = 0;
+        if (cb < NRED)
+          for (int m = 0; m < 3; ++m) h += hc[kr * 3 + m] * tb[(k * 3 + m) * NRED + cb];
+        else
+          for (int m = 0; m < 3; ++m) h += hc[kr * 3 + m] * sb[k * 3 + m];
+        hb[kr * (NRED + 1) + cb] = h;
+      }
+    }
+    OBCA_WARP_SYNC();
+    OBCA_LANES(lane) {
       for (int e = lane; e < NRED * NRED + 2 * NRED; e += 32) {
-        double acc = 0;
-        if (e < NRED * NRED) {
-          int ra = e / NRED, cb = e % NRED;
-          for (int k = 0; k < NK; ++k)
-            for (int r = 0; r < 3; ++r) {
-              double t = ta[(k * 3 + r) * NRED + ra];
-              if (t == 0.0) continue;
-              double h = 0;
-              for (int m = 0; m < 3; ++m) h += hc[k * 9 + r * 3 + m] * tb[(k * 3 + m) * NRED + cb];
-              acc += t * h;
-            }
-        } else if (e < NRED * NRED + NRED) {
-          int ra = e - NRED * NRED;  // Ta' Hc s0b
-          for (int k = 0; k < NK; ++k)
-            for (int r = 0; r < 3; ++r) {
-              double h = 0;
-              for (int m = 0; m < 3; ++m) h += hc[k * 9 + r * 3 + m] * sb[k * 3 + m];
-              acc += ta[(k * 3 + r) * NRED + ra] * h;
-            }
+        double acc = 0, acc1 = 0;
+        if (e < NRED * NRED + NRED) {
+          // e < NRED^2: Mab[ra][cb]; then Ta' Hc s0b (column NRED of hb)
+          const int ra = e < NRED * NRED ? e / NRED : e - NRED * NRED, cb = e < NRED * NRED ? e % NRED : NRED;
+          for (int kr = 0; kr + 1 < NK * 3; kr += 2) {
+            acc += ta[kr * NRED + ra] * hb[kr * (NRED + 1) + cb];
+            acc1 += ta[(kr + 1) * NRED + ra] * hb[(kr + 1) * (NRED + 1) + cb];
+          }
+          acc += acc1;
         } else {
           int rb = e - NRED * NRED - NRED;  // Tb' Hc' s0a
           for (int k = 0; k < NK; ++k)
