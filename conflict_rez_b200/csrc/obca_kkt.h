@@ -415,15 +415,17 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
 }
 
 // ------------------------------------------------------------------------------------------------
-// [NULLSP] one thread per (vehicle, interval)
+// [NULLSP] one warp per (vehicle, interval)
 //
-// G_w (nr x 35) = Jacobian of the interval's collocation (+ terminal) rows w.r.t. the stage variables of nodes
-// 1..K.  Householder QR of G_w' with a rank test: where LICQ fails (a vehicle standing still over a whole
-// interval makes the over-collocated rows dependent) the dependent rows are dropped and the null space grows,
-// the analogue of IPOPT's delta_c perturbation for a singular Jacobian.
-// QR record: [35*35] reflectors below / R on and above the staircase, [35] tau, [35] pivot column of every
-// staircase row, [2] (rank, nr).
-// ------------------------------------------------------------------------------------------------
+// G_w (nr x 35) = Jacobian of the interval's collocation (+ terminal + implied) rows w.r.t. the stage variables of
+// nodes 1..K.  The controls (a_k, w_k) and the poses (x, y, psi) of the interior nodes are eliminated exactly through
+// their defining rows (nullspace_block); what remains is a Householder QR of the node-0 / terminal / implied rows on
+// the 10 variables (v_j, delta_j), with a rank test: where LICQ fails (a vehicle standing still over a whole interval
+// makes the over-collocated rows dependent) the dependent rows are dropped and the null space grows, the analogue of
+// IPOPT's delta_c perturbation for a singular Jacobian.
+// QR record: [NQ][NC] rows 0..9 = reflectors below / R on and above the staircase, rows 10..24 = W (the multipliers of
+// the eliminated (x, y, psi) rows onto every remaining row), [35] tau, [35] pivot column of every staircase row,
+// [4] (rank, nr, ndrop, -), dropped-row records, nu, [2][NC] control coefficients of the terminal / implied rows.
 // apply Q = H_0 ... H_{rk-1} (transpose = false) or Q' (transpose = true) to v[NU2]
 OBCA_HD void apply_q(const double* QRm, int rk, double* v, bool transpose) {
   const double* tau = QRm + QR_TAU;
