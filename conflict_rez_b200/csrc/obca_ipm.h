@@ -29,7 +29,10 @@ OBCA_HD bool finite_d(double v) { return v - v == 0.0; }
 // shared-memory arena (free outside the KKT solve) while the CTA works on the current tile; completion is tracked by
 // mbarriers.  `body(q, v)` receives the NA loaded values of element q and writes its results straight to global memory.
 // ------------------------------------------------------------------------------------------------
-constexpr int ST_TILE = 1024;  // elements per tile
+#ifndef OBCA_ST_TILE
+#define OBCA_ST_TILE 1024
+#endif
+constexpr int ST_TILE = OBCA_ST_TILE;  // elements per tile (4 per thread)
 constexpr int ST_STAGES = 3;
 
 struct Stage {
