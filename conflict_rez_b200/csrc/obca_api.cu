@@ -287,7 +287,9 @@ const char* obca_version(void) {
 #ifdef OBCA_HOST_EMU
   return "obca-b200 0.1.0 (HOST EMULATION - developer tool, not the product)";
 #else
-  return "obca-b200 0.1.0 (sm_100a)";
+#define OBCA_STR2(x) #x
+#define OBCA_STR(x) OBCA_STR2(x)
+  return "obca-b200 0.1.0 (sm_100a, " OBCA_STR(CTA_THREADS) " threads x " OBCA_STR(CTAS_PER_SM) " CTA/SM)";
 #endif
 }
 const char* obca_last_error(void) { return g_err.c_str(); }

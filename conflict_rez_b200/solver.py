@@ -209,6 +209,7 @@ class ObcaSolver:
         st = ObcaStatic(wb=float(prob.wb), **{n: _np_ptr(a) for n, a in keep.items()})
         self._check(self.lib.obca_set_static(self.handle, ctypes.byref(st)))
         self._stream = None
+        self._staging = {}
 
     # -- helpers -----------------------------------------------------------------------------------
     def _check(self, rc):
@@ -221,11 +222,41 @@ class ObcaSolver:
             return None
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _to_dev(self, a, shape):
-        t = torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True).reshape(shape))
-        if self.device.type == "cuda":
-            t = t.pin_memory().to(self.device, non_blocking=True)
-        return t.contiguous()
+    def _to_dev(self, a, shape, name=None):
+        """Host array -> device tensor.  With ``name`` the copy goes through a persistent pinned staging buffer and a
+        persistent device tensor (one host memcpy + one asynchronous H2D copy per call, no allocation after the first)."""
+        if self.device.type != "cuda":
+            return torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True).reshape(shape)).contiguous()
+        if name is None:
+            t = torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True).reshape(shape))
+            return t.pin_memory().to(self.device, non_blocking=True).contiguous()
+        shape = tuple(int(v) for v in shape)
+        buf = self._staging.get(name)
+        if buf is None or tuple(buf[0].shape) != shape:
+            buf = (torch.empty(shape, dtype=torch.float64, pin_memory=True), torch.empty(shape, dtype=torch.float64, device=self.device))
+            self._staging[name] = buf
+        np.copyto(buf[0].numpy(), np.asarray(a, dtype=np.float64).reshape(shape))
+        buf[1].copy_(buf[0], non_blocking=True)
+        return buf[1]
+
+    def _to_host(self, tensors):
+        """Device tensors -> independent numpy arrays: asynchronous D2H copies into persistent pinned buffers, one sync."""
+        if self.device.type != "cuda":
+            return [None if t is None else t.numpy().copy() for t in tensors]
+        pins = []
+        for k, t in enumerate(tensors):
+            if t is None:
+                pins.append(None)
+                continue
+            key = ("out", k, tuple(t.shape), t.dtype)
+            pin = self._staging.get(key)
+            if pin is None:
+                pin = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+                self._staging[key] = pin
+            pin.copy_(t, non_blocking=True)
+            pins.append(pin)
+        torch.cuda.synchronize(self.device)
+        return [None if p_ is None else p_.numpy().copy() for p_ in pins]
 
     def close(self):
         if getattr(self, "handle", None):
@@ -244,20 +275,21 @@ class ObcaSolver:
 
     # -- device-resident API (inputs already on the GPU) -------------------------------------------------
     def upload(self, guess: CollocationGuess, init_pose: Optional[np.ndarray] = None):
-        """Host -> device copies of the per-instance data; returns the device tensors (kept alive by the caller)."""
+        """Host -> device copies of the per-instance data through persistent pinned staging buffers; returns the device
+        tensors, which are owned by the solver and overwritten by the next ``upload``."""
         B, V, M, O, P = self.B, self.V, self.Mmax, self.O, self.P
         pose = self.prob.init_pose if init_pose is None else init_pose
         d = {
-            "pose": self._to_dev(pose, (B, V, 3)),
-            "z": self._to_dev(guess.z, (B, V, M, 7)),
-            "lam": self._to_dev(guess.lam, (B, V, M, O, 4)),
-            "mu": self._to_dev(guess.mu, (B, V, M, O, 4)),
-            "dt": self._to_dev(np.broadcast_to(guess.dt, (B,)), (B,)),
+            "pose": self._to_dev(pose, (B, V, 3), "pose"),
+            "z": self._to_dev(guess.z, (B, V, M, 7), "z"),
+            "lam": self._to_dev(guess.lam, (B, V, M, O, 4), "lam"),
+            "mu": self._to_dev(guess.mu, (B, V, M, O, 4), "mu"),
+            "dt": self._to_dev(np.broadcast_to(guess.dt, (B,)), (B,), "dt"),
         }
         if P:
-            d["pl"] = self._to_dev(guess.pair_lam, (B, P, M, 4))
-            d["pm"] = self._to_dev(guess.pair_mu, (B, P, M, 4))
-            d["ps"] = self._to_dev(guess.pair_s, (B, P, M, 2))
+            d["pl"] = self._to_dev(guess.pair_lam, (B, P, M, 4), "pl")
+            d["pm"] = self._to_dev(guess.pair_mu, (B, P, M, 4), "pm")
+            d["ps"] = self._to_dev(guess.pair_s, (B, P, M, 2), "ps")
         return d
 
     def dual_ws(self, z):
@@ -327,24 +359,10 @@ class ObcaSolver:
         self.run()
         st, it, dbl = self.fetch_stats()
         sol = self.fetch_solution()
-        if self.device.type == "cuda":
-            torch.cuda.synchronize(self.device)
-        cpu = lambda t: None if t is None else t.cpu().numpy()
-        return BatchResult(
-            status=cpu(st),
-            iters=cpu(it),
-            obj=cpu(dbl[0]),
-            cviol=cpu(dbl[1]),
-            dual_inf=cpu(dbl[2]),
-            compl_inf=cpu(dbl[3]),
-            z=cpu(sol["z"]),
-            lam=cpu(sol["lam"]) if want_duals else None,
-            mu=cpu(sol["mu"]) if want_duals else None,
-            dt=cpu(sol["dt"]),
-            pair_lam=cpu(sol.get("pl")),
-            pair_mu=cpu(sol.get("pm")),
-            pair_s=cpu(sol.get("ps")),
-        )
+        h = self._to_host([st, it, dbl[0], dbl[1], dbl[2], dbl[3], sol["z"], sol["lam"] if want_duals else None, sol["mu"] if want_duals else None,
+                           sol["dt"], sol.get("pl"), sol.get("pm"), sol.get("ps")])
+        return BatchResult(status=h[0], iters=h[1], obj=h[2], cviol=h[3], dual_inf=h[4], compl_inf=h[5], z=h[6], lam=h[7], mu=h[8], dt=h[9],
+                           pair_lam=h[10], pair_mu=h[11], pair_s=h[12])
 
     # -- introspection for the parity tests --------------------------------------------------------------
     def layout(self):
@@ -431,6 +449,7 @@ class ObcaMpcSolver(ObcaSolver):
         if self.device.type == "cuda" and not torch.cuda.is_available():
             raise RuntimeError("ObcaMpcSolver: CUDA is not available on this machine (no CPU fallback)")
         self.prob = prob
+        self._staging = {}
         self.opts = options or SolveOptions(max_iter=600)  # vehicle_follower.py:362-364
         self.B, self.V, self.O, self.P, self.Mmax = prob.batch, 1, prob.obs_A.shape[0], prob.n_others, prob.N
         dims = ObcaDims(batch=self.B, V=1, O=self.O, K=5, n_per_set=1, mode=1, horizon=prob.N, n_others=prob.n_others)
@@ -448,8 +467,8 @@ class ObcaMpcSolver(ObcaSolver):
 
     def upload_params(self, cur, ref, others):
         B, N, P = self.B, self.Mmax, self.P
-        d = {"cur": self._to_dev(cur, (B, 5)), "ref": self._to_dev(ref, (B, N, 3))}
-        d["others"] = self._to_dev(others, (B, P, N, 3)) if P else None
+        d = {"cur": self._to_dev(cur, (B, 5), "cur"), "ref": self._to_dev(ref, (B, N, 3), "ref")}
+        d["others"] = self._to_dev(others, (B, P, N, 3), "others") if P else None
         return d
 
     def set_params(self, d):
@@ -458,15 +477,15 @@ class ObcaMpcSolver(ObcaSolver):
     def upload(self, guess: CollocationGuess, init_pose=None):
         B, M, O, P = self.B, self.Mmax, self.O, self.P
         d = {
-            "z": self._to_dev(guess.z, (B, 1, M, 7)),
-            "lam": self._to_dev(guess.lam, (B, 1, M, O, 4)),
-            "mu": self._to_dev(guess.mu, (B, 1, M, O, 4)),
-            "dt": self._to_dev(np.zeros(B), (B,)),
+            "z": self._to_dev(guess.z, (B, 1, M, 7), "z"),
+            "lam": self._to_dev(guess.lam, (B, 1, M, O, 4), "lam"),
+            "mu": self._to_dev(guess.mu, (B, 1, M, O, 4), "mu"),
+            "dt": self._to_dev(np.zeros(B), (B,), "dt"),
         }
         if P:
-            d["pl"] = self._to_dev(guess.pair_lam, (B, P, M, 4))
-            d["pm"] = self._to_dev(guess.pair_mu, (B, P, M, 4))
-            d["ps"] = self._to_dev(guess.pair_s, (B, P, M, 2))
+            d["pl"] = self._to_dev(guess.pair_lam, (B, P, M, 4), "pl")
+            d["pm"] = self._to_dev(guess.pair_mu, (B, P, M, 4), "pm")
+            d["ps"] = self._to_dev(guess.pair_s, (B, P, M, 2), "ps")
         return d
 
     def set_inputs(self, d):
