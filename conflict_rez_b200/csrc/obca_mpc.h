@@ -232,92 +232,115 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   const int N = L.Mv;
   double* PG = W.PG;
   prof_mark(ctx, 11);
-  // pair blocks (other vehicle's pose is a parameter): residuals, gl of the pair variables, own-pose gradient -> PG
-  for (int it = ctx.tid; it < L.P * N; it += ctx.nt) {
-    int o = it / N, n = it % N;
-    Pose a, b;
-    load_pose(L, x, 0, n, a);
-    load_other_pose(L, par, o, n, b);
-    PairBlk B;
-    load_pair(L, x, o, n, B);
-    pair_residual(S, a, b, B);
-    for (int r = 0; r < 6; ++r) c[L.YPAIR(o, r, n)] = B.c[r];
-    if (!y) continue;
-    double yd = y[L.YPAIR(o, 0, n)], ye1[2] = {y[L.YPAIR(o, 1, n)], y[L.YPAIR(o, 2, n)]};
-    double ye2[2] = {y[L.YPAIR(o, 3, n)], y[L.YPAIR(o, 4, n)]}, yn = y[L.YPAIR(o, 5, n)];
-    double Rtea[2] = {a.c * ye1[0] + a.s * ye1[1], -a.s * ye1[0] + a.c * ye1[1]};
-    double Rteb[2] = {b.c * ye2[0] + b.s * ye2[1], -b.s * ye2[0] + b.c * ye2[1]};
-    for (int r = 0; r < 4; ++r) {
-      gl[L.PL(o, r, n)] = -yd * B.ba[r] + S.G[r][0] * Rtea[0] + S.G[r][1] * Rtea[1];
-      gl[L.PM(o, r, n)] = -yd * B.bb[r] + S.G[r][0] * Rteb[0] + S.G[r][1] * Rteb[1];
-    }
-    gl[L.PS(o, 0, n)] = ye1[0] - ye2[0] - 2.0 * yn * B.s[0];
-    gl[L.PS(o, 1, n)] = ye1[1] - ye2[1] - 2.0 * yn * B.s[1];
-    gl[L.PSD(o, n)] = -yd;
-    gl[L.PSN(o, n)] = -yn;
-    gl[L.PEL(o, n)] = S.rho + yd;
-    double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
-    double* g = PG + (size_t)(o * L.Mv + n) * 6;
-    g[0] = -yd * B.Rua[0];
-    g[1] = -yd * B.Rua[1];
-    g[2] = -yd * (a.x * dRua[0] + a.y * dRua[1]) + ye1[0] * dRua[0] + ye1[1] * dRua[1];
-  }
-  cta_sync(ctx);
-  prof_mark(ctx, 0);
+  // task families in units of 32 tasks of one family, longest first, from a shared counter (see mpc_kkt_solve):
+  //   pair blocks (other vehicle's pose is a parameter): residuals, gl of the pair variables, own-pose gradient -> PG
+  //   (node, obstacle): residual rows, gradient of the block variables, pose gradient -> OG
+  //   (node, nonlinear input i): column i of the dynamics Jacobian contracted with y -> JG, residual rows; values only without y
   double f_part = 0;
-  // scratch (the collocation-mode node buffers are free in MPC mode): dynamics y'J columns [N][5], obstacle pose gradients [N][O][3]
-  double* JG = W.HN;
+  double* JG = W.HN;  // scratch (the collocation-mode node buffers are free in MPC mode): [N][5], then [N][O][3]
   double* OG = W.HN + (size_t)N * 5;
-  // tasks (node, nonlinear input i = psi, v, delta, a, w): column i of the dynamics Jacobian, contracted with y; residual rows
-  if (y) {
-    for (int it = ctx.tid; it < (N - 1) * 5; it += ctx.nt) {
-      const int n = it / 5, i = it % 5;
-      double z[NZ], d[NZ] = {0, 0, 0, 0, 0, 0, 0};
-      for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
-      d[2 + i] = 1.0;
-      Tay<false> F[5];
-      tay_rk4<false>(z, d, S.dt_mpc, S.wb, F);
-      double acc = 0;
-      for (int r = 0; r < 5; ++r) acc += y[L.YCOL(0, r, n)] * F[r].a;
-      JG[n * 5 + i] = acc;
-      if (i == 0)
-        for (int r = 0; r < 5; ++r) c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r].v;
+  const int nPair = L.P * N, nObs = N * L.O, nDyn = y ? (N - 1) * 5 : N - 1;
+  const int uPair = (nPair + 31) / 32, uObs = (nObs + 31) / 32, uDyn = (nDyn + 31) / 32;
+  int* next_unit = (int*)(ctx.red + 36);  // shared-memory slot of the reduction scratch that the reductions never touch
+  if (ctx.tid == 0) *next_unit = 0;
+  cta_sync(ctx);
+  for (;;) {
+    int unit;
+#if defined(__CUDA_ARCH__)
+    {
+      int u0 = 0;
+      if ((ctx.tid & 31) == 0) u0 = atomicAdd(next_unit, 1);
+      unit = __shfl_sync(0xffffffffu, u0, 0);
     }
-  } else {
-    for (int n = ctx.tid; n < N - 1; n += ctx.nt) {
-      double z[NZ], F[5];
-      for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
-      rk4_value(z, S.dt_mpc, S.wb, F);
-      for (int r = 0; r < 5; ++r) c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r];
+    const int lane0 = ctx.tid & 31, lane1 = lane0 + 1;
+#else
+    unit = (*next_unit)++;
+    const int lane0 = 0, lane1 = 32;
+#endif
+    if (unit >= uPair + uObs + uDyn) break;
+    for (int ln = lane0; ln < lane1; ++ln) {
+      if (unit < uPair) {
+        const int it = unit * 32 + ln;
+        if (it >= nPair) continue;
+        int o = it / N, n = it % N;
+        Pose a, b;
+        load_pose(L, x, 0, n, a);
+        load_other_pose(L, par, o, n, b);
+        PairBlk B;
+        load_pair(L, x, o, n, B);
+        pair_residual(S, a, b, B);
+        for (int r = 0; r < 6; ++r) c[L.YPAIR(o, r, n)] = B.c[r];
+        if (!y) continue;
+        double yd = y[L.YPAIR(o, 0, n)], ye1[2] = {y[L.YPAIR(o, 1, n)], y[L.YPAIR(o, 2, n)]};
+        double ye2[2] = {y[L.YPAIR(o, 3, n)], y[L.YPAIR(o, 4, n)]}, yn = y[L.YPAIR(o, 5, n)];
+        double Rtea[2] = {a.c * ye1[0] + a.s * ye1[1], -a.s * ye1[0] + a.c * ye1[1]};
+        double Rteb[2] = {b.c * ye2[0] + b.s * ye2[1], -b.s * ye2[0] + b.c * ye2[1]};
+        for (int r = 0; r < 4; ++r) {
+          gl[L.PL(o, r, n)] = -yd * B.ba[r] + S.G[r][0] * Rtea[0] + S.G[r][1] * Rtea[1];
+          gl[L.PM(o, r, n)] = -yd * B.bb[r] + S.G[r][0] * Rteb[0] + S.G[r][1] * Rteb[1];
+        }
+        gl[L.PS(o, 0, n)] = ye1[0] - ye2[0] - 2.0 * yn * B.s[0];
+        gl[L.PS(o, 1, n)] = ye1[1] - ye2[1] - 2.0 * yn * B.s[1];
+        gl[L.PSD(o, n)] = -yd;
+        gl[L.PSN(o, n)] = -yn;
+        gl[L.PEL(o, n)] = S.rho + yd;
+        double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
+        double* g = PG + (size_t)(o * L.Mv + n) * 6;
+        g[0] = -yd * B.Rua[0];
+        g[1] = -yd * B.Rua[1];
+        g[2] = -yd * (a.x * dRua[0] + a.y * dRua[1]) + ye1[0] * dRua[0] + ye1[1] * dRua[1];
+      } else if (unit < uPair + uObs) {
+        const int it = (unit - uPair) * 32 + ln;
+        if (it >= nObs) continue;
+        const int n = it / L.O, j = it % L.O;
+        Pose p;
+        load_pose(L, x, 0, n, p);
+        ObsBlk B;
+        for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(0, j, r, n)], B.mu[r] = x[L.MU(0, j, r, n)];
+        B.sd = x[L.SD(0, j, n)];
+        B.el = x[L.EL(0, j, n)];
+        f_part += S.rho * B.el;
+        obs_residual(S, j, p, B);
+        for (int r = 0; r < 4; ++r) c[L.YOBS(0, j, r, n)] = B.c[r];
+        if (!y) continue;
+        double y1 = y[L.YOBS(0, j, 0, n)], y2[2] = {y[L.YOBS(0, j, 1, n)], y[L.YOBS(0, j, 2, n)]}, y3 = y[L.YOBS(0, j, 3, n)];
+        double Ry[2] = {p.c * y2[0] - p.s * y2[1], p.s * y2[0] + p.c * y2[1]};
+        for (int r = 0; r < 4; ++r) {
+          const double* A = S.obsA[j][r];
+          gl[L.LAM(0, j, r, n)] = y1 * B.Atb[r] + A[0] * Ry[0] + A[1] * Ry[1] + 2.0 * y3 * (A[0] * B.u[0] + A[1] * B.u[1]);
+          gl[L.MU(0, j, r, n)] = -y1 * S.g[r] + S.G[r][0] * y2[0] + S.G[r][1] * y2[1];
+        }
+        gl[L.SD(0, j, n)] = -y1;
+        gl[L.EL(0, j, n)] = S.rho + y1;
+        double* og = OG + (size_t)it * 3;
+        og[0] = y1 * B.u[0];
+        og[1] = y1 * B.u[1];
+        og[2] = y2[0] * (-p.s * B.u[0] + p.c * B.u[1]) + y2[1] * (-p.c * B.u[0] - p.s * B.u[1]);
+      } else if (y) {
+        const int it = (unit - uPair - uObs) * 32 + ln;
+        if (it >= nDyn) continue;
+        const int n = it / 5, i = it % 5;
+        double z[NZ], d[NZ] = {0, 0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
+        d[2 + i] = 1.0;
+        Tay<false> F[5];
+        tay_rk4<false>(z, d, S.dt_mpc, S.wb, F);
+        double acc = 0;
+        for (int r = 0; r < 5; ++r) acc += y[L.YCOL(0, r, n)] * F[r].a;
+        JG[n * 5 + i] = acc;
+        if (i == 0)
+          for (int r = 0; r < 5; ++r) c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r].v;
+      } else {
+        const int n = (unit - uPair - uObs) * 32 + ln;
+        if (n >= nDyn) continue;
+        double z[NZ], F[5];
+        for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
+        rk4_value(z, S.dt_mpc, S.wb, F);
+        for (int r = 0; r < 5; ++r) c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r];
+      }
     }
   }
-  // tasks (node, obstacle): residual rows, gradient of the block variables, pose gradient
-  for (int it = ctx.tid; it < N * L.O; it += ctx.nt) {
-    const int n = it / L.O, j = it % L.O;
-    Pose p;
-    load_pose(L, x, 0, n, p);
-    ObsBlk B;
-    for (int r = 0; r < 4; ++r) B.lam[r] = x[L.LAM(0, j, r, n)], B.mu[r] = x[L.MU(0, j, r, n)];
-    B.sd = x[L.SD(0, j, n)];
-    B.el = x[L.EL(0, j, n)];
-    f_part += S.rho * B.el;
-    obs_residual(S, j, p, B);
-    for (int r = 0; r < 4; ++r) c[L.YOBS(0, j, r, n)] = B.c[r];
-    if (!y) continue;
-    double y1 = y[L.YOBS(0, j, 0, n)], y2[2] = {y[L.YOBS(0, j, 1, n)], y[L.YOBS(0, j, 2, n)]}, y3 = y[L.YOBS(0, j, 3, n)];
-    double Ry[2] = {p.c * y2[0] - p.s * y2[1], p.s * y2[0] + p.c * y2[1]};
-    for (int r = 0; r < 4; ++r) {
-      const double* A = S.obsA[j][r];
-      gl[L.LAM(0, j, r, n)] = y1 * B.Atb[r] + A[0] * Ry[0] + A[1] * Ry[1] + 2.0 * y3 * (A[0] * B.u[0] + A[1] * B.u[1]);
-      gl[L.MU(0, j, r, n)] = -y1 * S.g[r] + S.G[r][0] * y2[0] + S.G[r][1] * y2[1];
-    }
-    gl[L.SD(0, j, n)] = -y1;
-    gl[L.EL(0, j, n)] = S.rho + y1;
-    double* og = OG + (size_t)it * 3;
-    og[0] = y1 * B.u[0];
-    og[1] = y1 * B.u[1];
-    og[2] = y2[0] * (-p.s * B.u[0] + p.c * B.u[1]) + y2[1] * (-p.c * B.u[0] - p.s * B.u[1]);
-  }
+  prof_mark(ctx, 0);
   cta_sync(ctx);
   for (int n = ctx.tid; n < N; n += ctx.nt) {
     double z[NZ];
@@ -367,18 +390,9 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   if (ctx.tid == 0) *ok_shared = 1;
   cta_sync(ctx);
   prof_mark(ctx, 11);
-  // pair blocks: same elimination as the joint problem, the other pose being constant (its Schur block is unused)
-  for (int it = ctx.tid; it < L.P * N; it += ctx.nt) {
-    int o = it / N, n = it % N;
-    Pose a, b;
-    load_pose(L, x, 0, n, a);
-    load_other_pose(L, par, o, n, b);
-    pair_block_eliminate(L, S, W, o, n, a, b, ok_shared);
-  }
-  cta_sync(ctx);
-  prof_mark(ctx, 2);
-  // node Hessian / gradient (7 x 7) and dynamics linearisation; stage data in the arena: per node
-  //   Hn[28], gn[7], A[5][7] (dF/d(z,u)), r[5] (dynamics residual)
+  // Three independent task families -- pair blocks (the longest chains), obstacle blocks, (node, direction) Taylor tasks of
+  // the RK4 map -- are dealt out in units of 32 tasks of one family (no divergence inside a warp), longest first, from a
+  // shared counter: the warps stay busy until all families are done instead of waiting at a barrier after each family.
   double* HN = RW;                    // [N][28]
   double* GN = HN + (size_t)N * 28;   // [N][7]
   double* AJ = GN + (size_t)N * 7;    // [N][35]
@@ -387,33 +401,68 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   double* DZ = KK + (size_t)N * 12;   // [N][7] step
   double* QD = DZ + (size_t)N * 7;    // [N][15] y-contracted second directional derivatives of the RK4 map
   double* OB = QD + (size_t)N * 15;   // [N][O][9] obstacle Schur complements on the pose (6 sym + 3 grad)
-  // tasks (node, direction): e_i and e_i + e_j over the nonlinear inputs (psi, v, delta, a, w); x and y enter F linearly
-  for (int it = ctx.tid; it < (N - 1) * 15; it += ctx.nt) {
-    const int n = it / 15, k = it % 15;
-    int i = 0;
-    while ((i + 1) * (i + 2) / 2 <= k) ++i;
-    const int j = k - i * (i + 1) / 2;
-    double z[NZ], d[NZ] = {0, 0, 0, 0, 0, 0, 0};
-    for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
-    d[2 + i] = 1.0, d[2 + j] = 1.0;
-    Tay<true> F[5];
-    tay_rk4<true>(z, d, S.dt_mpc, S.wb, F);
-    double acc = 0;
-    for (int r = 0; r < 5; ++r) acc += y[L.YCOL(0, r, n)] * 2.0 * F[r].b;
-    QD[n * 15 + k] = acc;
-    if (i == j)
-      for (int r = 0; r < 5; ++r) AJ[(size_t)n * 35 + r * 7 + 2 + i] = F[r].a;
+  const int nPair = L.P * N, nObs = N * L.O, nDir = (N - 1) * 15;
+  const int uPair = (nPair + 31) / 32, uObs = (nObs + 31) / 32, uDir = (nDir + 31) / 32;
+  int* next_unit = ok_shared + 1;  // Shared::again, unused in MPC mode
+  if (ctx.tid == 0) *next_unit = 0;
+  cta_sync(ctx);
+  for (;;) {
+    int unit;
+#if defined(__CUDA_ARCH__)
+    {
+      int u0 = 0;
+      if ((ctx.tid & 31) == 0) u0 = atomicAdd(next_unit, 1);
+      unit = __shfl_sync(0xffffffffu, u0, 0);
+    }
+    const int lane0 = ctx.tid & 31, lane1 = lane0 + 1;
+#else
+    unit = (*next_unit)++;
+    const int lane0 = 0, lane1 = 32;
+#endif
+    if (unit >= uPair + uObs + uDir) break;
+    for (int ln = lane0; ln < lane1; ++ln) {
+      if (unit < uPair) {
+        // pair block: same elimination as the joint problem, the other pose being constant (its Schur block is unused)
+        const int it = unit * 32 + ln;
+        if (it >= nPair) continue;
+        const int o = it / N, n = it % N;
+        Pose a, b;
+        load_pose(L, x, 0, n, a);
+        load_other_pose(L, par, o, n, b);
+        pair_block_eliminate(L, S, W, o, n, a, b, ok_shared);
+      } else if (unit < uPair + uObs) {
+        const int it = (unit - uPair) * 32 + ln;
+        if (it >= nObs) continue;
+        const int n = it / L.O, j = it % L.O;
+        Pose p;
+        load_pose(L, x, 0, n, p);
+        double H6[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0};
+        obs_block_eliminate(L, S, W, 0, n, j, p, H6, g3, ok_shared);
+        double* ob = OB + (size_t)it * 9;
+        for (int q = 0; q < 6; ++q) ob[q] = H6[q];
+        for (int q = 0; q < 3; ++q) ob[6 + q] = g3[q];
+      } else {
+        // (node, direction): e_i and e_i + e_j over the nonlinear inputs (psi, v, delta, a, w); x and y enter F linearly
+        const int it = (unit - uPair - uObs) * 32 + ln;
+        if (it >= nDir) continue;
+        const int n = it / 15, k = it % 15;
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= k) ++i;
+        const int j = k - i * (i + 1) / 2;
+        double z[NZ], d[NZ] = {0, 0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
+        d[2 + i] = 1.0, d[2 + j] = 1.0;
+        Tay<true> F[5];
+        tay_rk4<true>(z, d, S.dt_mpc, S.wb, F);
+        double acc = 0;
+        for (int r = 0; r < 5; ++r) acc += y[L.YCOL(0, r, n)] * 2.0 * F[r].b;
+        QD[n * 15 + k] = acc;
+        if (i == j)
+          for (int r = 0; r < 5; ++r) AJ[(size_t)n * 35 + r * 7 + 2 + i] = F[r].a;
+      }
+    }
   }
-  for (int it = ctx.tid; it < N * L.O; it += ctx.nt) {
-    const int n = it / L.O, j = it % L.O;
-    Pose p;
-    load_pose(L, x, 0, n, p);
-    double H6[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0};
-    obs_block_eliminate(L, S, W, 0, n, j, p, H6, g3, ok_shared);
-    double* ob = OB + (size_t)it * 9;
-    for (int q = 0; q < 6; ++q) ob[q] = H6[q];
-    for (int q = 0; q < 3; ++q) ob[6 + q] = g3[q];
-  }
+  prof_mark(ctx, 2);
   cta_sync(ctx);
   for (int n = ctx.tid; n < N; n += ctx.nt) {
     double z[NZ];
@@ -571,9 +620,17 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
       if (n == 0) W.dy[L.YINIT(0, r)] = -s;
       else W.dy[L.YCOL(0, r, n - 1)] = -s;
     }
-    double dp[3] = {w[0], w[1], w[2]};
-    for (int j = 0; j < L.O; ++j) obs_block_backsub(L, W, 0, n, j, dp);
-    for (int o = 0; o < L.P; ++o) {
+  }
+  // local blocks: one task per (node, obstacle) and (other, node)
+  for (int it = ctx.tid; it < N * (L.O + L.P); it += ctx.nt) {
+    if (it < N * L.O) {
+      const int n = it / L.O, j = it % L.O;
+      const double* w = DZ + (size_t)n * 7;
+      double dp[3] = {w[0], w[1], w[2]};
+      obs_block_backsub(L, W, 0, n, j, dp);
+    } else {
+      const int e = it - N * L.O, o = e / N, n = e % N;
+      const double* w = DZ + (size_t)n * 7;
       double dp6[6] = {w[0], w[1], w[2], 0.0, 0.0, 0.0};
       pair_block_backsub(L, W, o, n, dp6);
     }
