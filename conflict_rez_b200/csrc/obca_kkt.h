@@ -36,9 +36,8 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
     double ynm = yn < 0 ? yn : 0.0;  // local convexification: exact at KKT points (yn = -z_sn <= 0)
     // Block elimination in registers: lam, mu (diagonal Hessians) -> 5 x 5 Schur complement on (yd, ye1, ye2)
     // (the yn row only has its own pivot), then the 2 x 2 system of s.  7 right-hand sides (6 pose couplings + residual).
-    double X[16 * 7];
     const double isd = 1.0 / W.sig[L.PSD(p, n)], iel = 1.0 / W.sig[L.PEL(p, n)], isn = 1.0 / W.sig[L.PSN(p, n)];
-    const double dn = DELTA_C_LOCAL + isn;
+    const double dn = DELTA_C_LOCAL + isn, idn = 1.0 / dn;
     const double hs0 = W.sig[L.PS(p, 0, n)] - 2.0 * ynm, hs1 = W.sig[L.PS(p, 1, n)] - 2.0 * ynm;
     double sl[4], smu[4], ea[4], fa[4], eb[4], fb[4];
 #pragma unroll
@@ -68,7 +67,7 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
     }
     if (!chol_packed<5>(S5)) *ok = 0;
     // Z = S6^-1 E' with E = [[0, 1, 0, -1, 0, -2 s0], [0, 0, 1, 0, -1, -2 s1]]
-    double Z0[6] = {0, 1, 0, -1, 0, -2.0 * B.s[0] / dn}, Z1[6] = {0, 0, 1, 0, -1, -2.0 * B.s[1] / dn};
+    double Z0[6] = {0, 1, 0, -1, 0, -2.0 * B.s[0] * idn}, Z1[6] = {0, 0, 1, 0, -1, -2.0 * B.s[1] * idn};
     chol_solve_packed<5>(S5, Z0);
     chol_solve_packed<5>(S5, Z1);
     // Ms = diag(hs) + E Z  (2 x 2, symmetric positive definite)
@@ -77,37 +76,42 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
     double m11 = hs1 + Z1[2] - Z1[4] - 2.0 * B.s[1] * Z1[5];
     double det = m00 * m11 - m01 * m01;
     if (!(m00 > 0) || !(det > 0)) *ok = 0;
+    const double idet = 1.0 / det;
     // coupling columns: (x_a, y_a, psi_a, x_b, y_b, psi_b)
     double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
     double dRub[2] = {-b.s * B.ub[0] - b.c * B.ub[1], b.c * B.ub[0] - b.s * B.ub[1]};
     double dRtea[2] = {-a.s * ye1[0] + a.c * ye1[1], -a.c * ye1[0] - a.s * ye1[1]};  // (dR/dpsi)' ye1
     double dRteb[2] = {-b.s * ye2[0] + b.c * ye2[1], -b.c * ye2[0] - b.s * ye2[1]};
-    double C[16 * 6];
-#pragma unroll
-    for (int q = 0; q < 16 * 6; ++q) C[q] = 0;
+    // Coupling columns C (16 x 6, sparse): column k < 3 (pose a) touches lam (rows 0-3), yd (row 8) and, for psi, ye1 (9, 10);
+    // column k >= 3 (pose b) touches mu (rows 4-7), yd and ye2 (11, 12).  The entries are kept in registers (no local arrays:
+    // the per-thread stack lives in L2 at this shared-memory carve-out) and the Schur complement C'X is accumulated column by
+    // column while the solves X[:, k] are produced and streamed to global memory.
+    double ca[3][4], cb[3][4];  // lam rows of columns 0-2, mu rows of columns 3-5
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      double dax = -S.G[r][0] * a.s - S.G[r][1] * a.c, day = S.G[r][0] * a.c - S.G[r][1] * a.s;
-      double dbx = -S.G[r][0] * b.s - S.G[r][1] * b.c, dby = S.G[r][0] * b.c - S.G[r][1] * b.s;
-      C[r * 6 + 0] = -yd * ea[r];
-      C[r * 6 + 1] = -yd * fa[r];
-      C[r * 6 + 2] = -yd * (dax * a.x + day * a.y) + S.G[r][0] * dRtea[0] + S.G[r][1] * dRtea[1];
-      C[(4 + r) * 6 + 3] = -yd * eb[r];
-      C[(4 + r) * 6 + 4] = -yd * fb[r];
-      C[(4 + r) * 6 + 5] = -yd * (dbx * b.x + dby * b.y) + S.G[r][0] * dRteb[0] + S.G[r][1] * dRteb[1];
+      const double dax = -S.G[r][0] * a.s - S.G[r][1] * a.c, day = S.G[r][0] * a.c - S.G[r][1] * a.s;
+      const double dbx = -S.G[r][0] * b.s - S.G[r][1] * b.c, dby = S.G[r][0] * b.c - S.G[r][1] * b.s;
+      ca[0][r] = -yd * ea[r], ca[1][r] = -yd * fa[r];
+      ca[2][r] = -yd * (dax * a.x + day * a.y) + S.G[r][0] * dRtea[0] + S.G[r][1] * dRtea[1];
+      cb[0][r] = -yd * eb[r], cb[1][r] = -yd * fb[r];
+      cb[2][r] = -yd * (dbx * b.x + dby * b.y) + S.G[r][0] * dRteb[0] + S.G[r][1] * dRteb[1];
     }
-    C[8 * 6 + 0] = -B.Rua[0], C[8 * 6 + 1] = -B.Rua[1], C[8 * 6 + 2] = -(a.x * dRua[0] + a.y * dRua[1]);
-    C[8 * 6 + 3] = -B.Rub[0], C[8 * 6 + 4] = -B.Rub[1], C[8 * 6 + 5] = -(b.x * dRub[0] + b.y * dRub[1]);
-    C[9 * 6 + 2] = dRua[0], C[10 * 6 + 2] = dRua[1];
-    C[11 * 6 + 5] = dRub[0], C[12 * 6 + 5] = dRub[1];
+    const double c8[6] = {-B.Rua[0], -B.Rua[1], -(a.x * dRua[0] + a.y * dRua[1]), -B.Rub[0], -B.Rub[1], -(b.x * dRub[0] + b.y * dRub[1])};
+    double* xp = W.XP + (size_t)(p * L.Mv + n) * 112;
+    double CX[6][7];  // C' X
+#pragma unroll
     for (int k = 0; k < 7; ++k) {
-      double bl[4], bm[4], by[6], bs[2];
-      if (k < 6) {
+      double bl[4] = {0, 0, 0, 0}, bm[4] = {0, 0, 0, 0}, by[6] = {0, 0, 0, 0, 0, 0}, bs[2] = {0, 0};
+      if (k < 3) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) bl[r] = C[r * 6 + k], bm[r] = C[(4 + r) * 6 + k];
+        for (int r = 0; r < 4; ++r) bl[r] = ca[k][r];
+        by[0] = c8[k];
+        if (k == 2) by[1] = dRua[0], by[2] = dRua[1];
+      } else if (k < 6) {
 #pragma unroll
-        for (int r = 0; r < 6; ++r) by[r] = C[(8 + r) * 6 + k];
-        bs[0] = bs[1] = 0;
+        for (int r = 0; r < 4; ++r) bm[r] = cb[k - 3][r];
+        by[0] = c8[k];
+        if (k == 5) by[3] = dRub[0], by[4] = dRub[1];
       } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) bl[r] = -W.gphi[L.PL(p, r, n)], bm[r] = -W.gphi[L.PM(p, r, n)];
@@ -126,44 +130,50 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
         ry[1] += ea[r] * tl, ry[2] += fa[r] * tl, ry[3] += eb[r] * tm, ry[4] += fb[r] * tm;
       }
       // u = S6^-1 ry ; ds = Ms^-1 (bs - E u) ; dy = u + Z ds
-      ry[5] /= dn;
+      ry[5] *= idn;
       chol_solve_packed<5>(S5, ry);
       double q0 = bs[0] - (ry[1] - ry[3] - 2.0 * B.s[0] * ry[5]);
       double q1 = bs[1] - (ry[2] - ry[4] - 2.0 * B.s[1] * ry[5]);
-      double ds0 = (m11 * q0 - m01 * q1) / det, ds1 = (m00 * q1 - m01 * q0) / det;
-      double dy[6];
+      double ds0 = (m11 * q0 - m01 * q1) * idet, ds1 = (m00 * q1 - m01 * q0) * idet;
+      double dy[6], xl[4], xm[4];
 #pragma unroll
       for (int r = 0; r < 6; ++r) dy[r] = ry[r] + Z0[r] * ds0 + Z1[r] * ds1;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        X[r * 7 + k] = (bl[r] - (-B.ba[r] * dy[0] + ea[r] * dy[1] + fa[r] * dy[2])) * sl[r];
-        X[(4 + r) * 7 + k] = (bm[r] - (-B.bb[r] * dy[0] + eb[r] * dy[3] + fb[r] * dy[4])) * smu[r];
+        xl[r] = (bl[r] - (-B.ba[r] * dy[0] + ea[r] * dy[1] + fa[r] * dy[2])) * sl[r];
+        xm[r] = (bm[r] - (-B.bb[r] * dy[0] + eb[r] * dy[3] + fb[r] * dy[4])) * smu[r];
+        xp[r * 7 + k] = xl[r], xp[(4 + r) * 7 + k] = xm[r];
       }
 #pragma unroll
-      for (int r = 0; r < 6; ++r) X[(8 + r) * 7 + k] = dy[r];
-      X[14 * 7 + k] = ds0, X[15 * 7 + k] = ds1;
-    }
-    double* xp = W.XP + (size_t)(p * L.Mv + n) * 112;
-    for (int q = 0; q < 112; ++q) xp[q] = X[q];
-    // Schur complement on (pose_a, pose_b): direct Hessian - C' Xc ; gradient C' Xr
-    double H[36];
-    for (int q = 0; q < 36; ++q) H[q] = 0;
-    H[2 * 6 + 0] = H[0 * 6 + 2] = -yd * dRua[0];
-    H[2 * 6 + 1] = H[1 * 6 + 2] = -yd * dRua[1];
-    H[2 * 6 + 2] = yd * (a.x * B.Rua[0] + a.y * B.Rua[1]) - (ye1[0] * B.Rua[0] + ye1[1] * B.Rua[1]);
-    H[5 * 6 + 3] = H[3 * 6 + 5] = -yd * dRub[0];
-    H[5 * 6 + 4] = H[4 * 6 + 5] = -yd * dRub[1];
-    H[5 * 6 + 5] = yd * (b.x * B.Rub[0] + b.y * B.Rub[1]) - (ye2[0] * B.Rub[0] + ye2[1] * B.Rub[1]);
-    double* ph = W.PH + (size_t)(p * L.Mv + n) * 27;
-    for (int r = 0; r < 6; ++r) {
-      for (int q = 0; q <= r; ++q) {
-        double s = H[r * 6 + q];
-        for (int m = 0; m < 16; ++m) s -= C[m * 6 + r] * X[m * 7 + q];
-        ph[sym(r, q)] = s;
+      for (int r = 0; r < 6; ++r) xp[(8 + r) * 7 + k] = dy[r];
+      xp[14 * 7 + k] = ds0, xp[15 * 7 + k] = ds1;
+      // row r of C' X[:, k]
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        double sa_ = c8[r] * dy[0], sb_ = c8[3 + r] * dy[0];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) sa_ += ca[r][m] * xl[m], sb_ += cb[r][m] * xm[m];
+        CX[r][k] = sa_, CX[3 + r][k] = sb_;
       }
-      double s = 0;
-      for (int m = 0; m < 16; ++m) s += C[m * 6 + r] * X[m * 7 + 6];
-      ph[21 + r] = s;
+      CX[2][k] += dRua[0] * dy[1] + dRua[1] * dy[2];
+      CX[5][k] += dRub[0] * dy[3] + dRub[1] * dy[4];
+    }
+    // Schur complement on (pose_a, pose_b): direct Hessian - C' Xc ; gradient C' Xr
+    double* ph = W.PH + (size_t)(p * L.Mv + n) * 27;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+      for (int q = 0; q <= r; ++q) {
+        double h = 0;
+        if (r == 2 && q == 0) h = -yd * dRua[0];
+        if (r == 2 && q == 1) h = -yd * dRua[1];
+        if (r == 2 && q == 2) h = yd * (a.x * B.Rua[0] + a.y * B.Rua[1]) - (ye1[0] * B.Rua[0] + ye1[1] * B.Rua[1]);
+        if (r == 5 && q == 3) h = -yd * dRub[0];
+        if (r == 5 && q == 4) h = -yd * dRub[1];
+        if (r == 5 && q == 5) h = yd * (b.x * B.Rub[0] + b.y * B.Rub[1]) - (ye2[0] * B.Rub[0] + ye2[1] * B.Rub[1]);
+        ph[sym(r, q)] = h - CX[r][q];
+      }
+      ph[21 + r] = CX[r][6];
     }
   }
 }
