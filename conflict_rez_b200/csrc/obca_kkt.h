@@ -205,7 +205,8 @@ OBCA_HD void obs_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, 
       double y3p = y3 > 0 ? y3 : 0.0;  // local convexification: exact at KKT points (y3 >= 0)
       // Block elimination in registers: lam (H = diag + 2 y3+ A A'), mu (diagonal), then the 4 x 4 Schur complement
       //   S = D + Jl Hl^-1 Jl' + Jm Dm^-1 Jm'  on (y1, y2, y3); 4 right-hand sides (3 pose couplings + residual).
-      double X[12 * 4];
+      double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 48;
+      double CX[3][4];  // C' X
       double dRy[2] = {-p.s * y2[0] - p.c * y2[1], p.c * y2[0] - p.s * y2[1]};   // (dR/dpsi) y2
       double dRtu[2] = {-p.s * B.u[0] + p.c * B.u[1], -p.c * B.u[0] - p.s * B.u[1]};  // (dR'/dpsi) u
       double Hl[10], Jl[4][4], sm[4], Cl[4][3], bl[4], bm[4];
@@ -276,33 +277,33 @@ OBCA_HD void obs_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, 
           ry[i2] = acc;
         }
         chol_solve_packed<4>(Ss, ry);
+        double xl[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           double dl = t[r], jm = -S.g[r] * ry[0] + S.G[r][0] * ry[1] + S.G[r][1] * ry[2];
 #pragma unroll
           for (int i2 = 0; i2 < 4; ++i2) dl -= Wl[i2][r] * ry[i2];
-          X[r * 4 + k] = dl;
-          X[(4 + r) * 4 + k] = ((k == 3 ? bm[r] : 0.0) - jm) * sm[r];
-          X[(8 + r) * 4 + k] = ry[r];
+          xl[r] = dl;
+          // block solves go straight to global memory (back-substitution); no per-thread local array
+          xo[r * 4 + k] = dl;
+          xo[(4 + r) * 4 + k] = ((k == 3 ? bm[r] : 0.0) - jm) * sm[r];
+          xo[(8 + r) * 4 + k] = ry[r];
+        }
+        // column k of C'X: the lam rows carry Cl, the y rows carry Cy (the mu rows do not couple to the pose)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          double sacc = Cy[0][r] * ry[0] + Cy[1][r] * ry[1] + Cy[2][r] * ry[2];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) sacc += Cl[m][r] * xl[m];
+          CX[r][k] = sacc;
         }
       }
-      double C[12 * 3];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) C[r * 3 + q] = Cl[r][q], C[(4 + r) * 3 + q] = 0.0, C[(8 + r) * 3 + q] = Cy[r][q];
-      double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 48;
-      for (int q = 0; q < 48; ++q) xo[q] = X[q];
       H[sym(2, 2)] -= y2[0] * (p.c * B.u[0] + p.s * B.u[1]) + y2[1] * (-p.s * B.u[0] + p.c * B.u[1]);
+#pragma unroll
       for (int r = 0; r < 3; ++r) {
-        for (int q = 0; q <= r; ++q) {
-          double s = 0;
-          for (int m = 0; m < 12; ++m) s += C[m * 3 + r] * X[m * 4 + q];
-          H[sym(r, q)] -= s;
-        }
-        double s = 0;
-        for (int m = 0; m < 12; ++m) s += C[m * 3 + r] * X[m * 4 + 3];
-        g[r] += s;
+#pragma unroll
+        for (int q = 0; q <= r; ++q) H[sym(r, q)] -= CX[r][q];
+        g[r] += CX[r][3];
       }
   }
 }
