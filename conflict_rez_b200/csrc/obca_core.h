@@ -344,7 +344,7 @@ struct Ctx {
   long long* prof;  // optional per-slot phase cycle counters [NPROF + 1] (last = time stamp), or nullptr
 };
 
-constexpr int NPROF = 27;  // 16..21: sub-phases of the null-space block (warp 0 only): setup, QR, T columns, store, projection
+constexpr int NPROF = 31;  // 16..21: sub-phases of the null-space block (warp 0 only): setup, QR, T columns, store, projection
 // phase ids: 0 eval_pairs 1 eval_nodes 2 pair_eliminate 3 node_assemble 4 nullspace 5 cross 6 riccati_bwd 7 riccati_fwd
 //            8 expand+node_residual 9 multipliers 10 local_backsub 11 ipm vector ops / line-search bookkeeping
 OBCA_HD void prof_mark(const Ctx& ctx, int phase) {

@@ -1100,14 +1100,14 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, dou
 // All stage matrices live in the work arena RW (shared memory on the device).
 // ------------------------------------------------------------------------------------------------
 struct RicWork {
-  double *P, *p, *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *K, *Ab, *Bb, *db, *cb, *invd, *MAs, *MABs;
-  int *uoff, *npv;  // [MAXV + 1]
+  double *P, *p, *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *K, *Ab, *Bb, *db, *cb, *invd, *MAs, *MABs, *TBs;
+  int *uoff, *npv, *npt;  // [MAXV + 1], [MAXV + 1], [V][Nmax]
 };
 
 inline size_t riccati_only_doubles(const Lay& L) {
   size_t nX = L.nX, nU = L.nU;
-  return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU +
-         (OBCA_RIC_PREFETCH ? (size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) : 0);
+  return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU + ((size_t)L.V * L.Nmax + 2) / 2 +
+         (OBCA_RIC_PREFETCH ? (size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) + (size_t)L.V * 7 * (NRED + 1) : 0);
 }
 
 // work arena shared by the null-space phase (NSW doubles per warp) and the Riccati phase
@@ -1139,12 +1139,55 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
   R.invd = w, w += nU;
   R.MAs = w;
   R.MABs = w + L.V * (NSYM + NRED);
-  if (OBCA_RIC_PREFETCH) w += L.V * (NSYM + NRED) + L.P * (NRED * NRED + 2 * NRED);
+  R.TBs = R.MABs + L.P * (NRED * NRED + 2 * NRED);
+  if (OBCA_RIC_PREFETCH) w += L.V * (NSYM + NRED) + L.P * (NRED * NRED + 2 * NRED) + L.V * 7 * (NRED + 1);
   R.uoff = (int*)w;
   R.npv = R.uoff + (MAXV + 1);
+  R.npt = R.npv + (MAXV + 1);  // [V][Nmax] free directions of every block
 }
 
-// free directions of block (a, i): 35 - rank, 0 for a vehicle whose horizon has ended
+// Stage inputs of the Riccati recursion (projected Hessians MA, coupling blocks MAB, last rows of the T maps).  The copies
+// for stage i-1 are issued as asynchronous global -> shared copies (cp.async, 8 bytes each, zero fill for blocks beyond a
+// vehicle's horizon) once stage i has consumed its inputs, so the global-memory latency hides behind the factorisation.
+OBCA_HD int ric_input_count(const Lay& L) { return L.V * (NSYM + NRED) + L.P * (NRED * NRED + 2 * NRED) + L.V * 7 * (NRED + 1); }
+OBCA_HD const double* ric_input_addr(const Lay& L, const Scratch& W, int i, int it, bool* active) {
+  const int n1 = L.V * (NSYM + NRED), n2 = n1 + L.P * (NRED * NRED + 2 * NRED);
+  if (it < n1) {
+    const int a = it / (NSYM + NRED);
+    *active = i < L.N[a];
+    return W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED) + it % (NSYM + NRED);
+  }
+  if (it < n2) {
+    const int e = it - n1, p = e / (NRED * NRED + 2 * NRED);
+    *active = i * NK < L.Mp[p];
+    return W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED) + e % (NRED * NRED + 2 * NRED);
+  }
+  const int e = it - n2, a = e / (7 * (NRED + 1)), r = (e / (NRED + 1)) % 7, cc = e % (NRED + 1);
+  *active = i < L.N[a];
+  const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+  return cc < NRED ? T + (28 + r) * NRED + cc : T + NW * NRED + 28 + r;
+}
+OBCA_HD void ric_input_fetch(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R, int i) {
+  const int tot = ric_input_count(L);
+  for (int it = ctx.tid; it < tot; it += ctx.nt) {
+    bool active;
+    const double* src = ric_input_addr(L, W, i, it, &active);
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(R.MAs + it)), "l"(active ? src : W.MA),
+                 "r"(active ? 8 : 0)
+                 : "memory");
+#else
+    R.MAs[it] = active ? *src : 0.0;  // MAs, MABs, TBs are contiguous
+#endif
+  }
+}
+OBCA_HD void ric_input_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// free directions of block (a, i): 10 - rank, 0 for a vehicle whose horizon has ended
 OBCA_HD int block_np(const Lay& L, const Scratch& W, int a, int i) {
   if (i >= L.N[a]) return 0;
   int np = NU2 - (int)W.QR[(size_t)(a * L.Nmax + i) * QRSZ + QR_META];
@@ -1175,35 +1218,34 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
   for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.Q[q] = 0;
   for (int q = ctx.tid; q < nu * nX; q += ctx.nt) R.S[q] = 0;
   for (int q = ctx.tid; q < nu * nu; q += ctx.nt) R.R[q] = 0;
-  // stage data -> shared memory (coalesced, independent loads) when the arena has room for it
+  // stage data: already in shared memory (ric_input_fetch) when the arena has room for it
 #if OBCA_RIC_PREFETCH
-  for (int it = ctx.tid; it < V * (NSYM + NRED); it += ctx.nt) {
-    int a = it / (NSYM + NRED);
-    R.MAs[it] = i < L.N[a] ? W.MA[(size_t)(a * L.Nmax + i) * (NSYM + NRED) + it % (NSYM + NRED)] : 0.0;
-  }
-  for (int it = ctx.tid; it < L.P * (NRED * NRED + 2 * NRED); it += ctx.nt) {
-    int p = it / (NRED * NRED + 2 * NRED);
-    R.MABs[it] = i * NK < L.Mp[p] ? W.MAB[(size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED) + it % (NRED * NRED + 2 * NRED)] : 0.0;
-  }
 #define OBCA_MA(a) (R.MAs + (a) * (NSYM + NRED))
 #define OBCA_MAB(p) (R.MABs + (p) * (NRED * NRED + 2 * NRED))
 #else
 #define OBCA_MA(a) (W.MA + (size_t)((a) * L.Nmax + i) * (NSYM + NRED))
 #define OBCA_MAB(p) (W.MAB + (size_t)((p) * L.Nmax + i) * (NRED * NRED + 2 * NRED))
 #endif
+  prof_mark(ctx, 27);
   // block dynamics from the T maps
   for (int it = ctx.tid; it < V * 7 * (NRED + 1); it += ctx.nt) {
     int a = it / (7 * (NRED + 1)), r = (it / (NRED + 1)) % 7, cc = it % (NRED + 1);
-    bool active = i < L.N[a];
-    const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+#if OBCA_RIC_PREFETCH
+    const double v = R.TBs[it];
+#else
     double v = 0.0;
-    if (active) v = cc < NRED ? T[(28 + r) * NRED + cc] : T[NW * NRED + 28 + r];
+    if (i < L.N[a]) {
+      const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+      v = cc < NRED ? T[(28 + r) * NRED + cc] : T[NW * NRED + 28 + r];
+    }
+#endif
     if (cc < 7) R.Ab[a * 49 + r * 7 + cc] = v;
     else if (cc < IDT) R.Bb[(a * 7 + r) * NP + cc - 7] = v;
     else if (cc == IDT) R.db[a * 7 + r] = v;
     else R.cb[a * 7 + r] = v;
   }
   cta_sync(ctx);
+  prof_mark(ctx, 28);
   // pass A: own-vehicle entries that do not involve dt
   for (int it = ctx.tid; it < V * NRED * NRED; it += ctx.nt) {
     int a = it / (NRED * NRED), r = (it / NRED) % NRED, cc = it % NRED;
@@ -1216,6 +1258,7 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
     else if (kr == 1 && kc == 0) R.S[tr * nX + tc] = v;
     else if (kr == 1 && kc == 1) R.R[tr * nu + tc] = v;
   }
+  prof_mark(ctx, 29);
   // pass B: cross-vehicle entries that do not involve dt (each (pair, ra, cb) owns its targets)
   for (int it = ctx.tid; it < L.P * NRED * NRED; it += ctx.nt) {
     int p = it / (NRED * NRED), ra = (it / NRED) % NRED, cb = it % NRED;
@@ -1229,6 +1272,7 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
     else if (ka == 0 && kb == 1) R.S[tb * nX + ta] = v;
     else R.R[ta * nu + tb] = v, R.R[tb * nu + ta] = v;
   }
+  prof_mark(ctx, 30);
   // pass C: everything that touches dt, and the gradients: one thread per target, fixed summation order
   for (int t = ctx.tid; t < idt + nu + 1; t += ctx.nt) {
     int a = -1, rc = IDT;
@@ -1281,17 +1325,24 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     double* Pn = W.RP + (size_t)L.Nmax * pstride;
     for (int q = ctx.tid; q < (int)pstride; q += ctx.nt) Pn[q] = 0;
   }
+  for (int it = ctx.tid; it < V * L.Nmax; it += ctx.nt) R.npt[it] = block_np(L, W, it / L.Nmax, it % L.Nmax);
+#if OBCA_RIC_PREFETCH
+  ric_input_fetch(ctx, L, W, R, L.Nmax - 1);
+#endif
   cta_sync(ctx);
   for (int i = L.Nmax - 1; i >= 0; --i) {
     if (ctx.tid == 0) {
       int off = 0;
       for (int a = 0; a < V; ++a) {
         R.uoff[a] = off;
-        R.npv[a] = block_np(L, W, a, i);
+        R.npv[a] = R.npt[a * L.Nmax + i];
         off += R.npv[a];
       }
       R.uoff[V] = off;
     }
+#if OBCA_RIC_PREFETCH
+    ric_input_wait();  // this stage's inputs (issued during the previous stage) have landed; the barrier publishes them
+#endif
     cta_sync(ctx);
     const int nu = R.uoff[V];
     prof_mark(ctx, 6);
@@ -1354,6 +1405,9 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     const int nc = nX + 1;
     for (int it = ctx.tid; it < nu * nc; it += ctx.nt) R.K[it] = R.Gm[it];
     cta_sync(ctx);
+#if OBCA_RIC_PREFETCH
+    if (i > 0) ric_input_fetch(ctx, L, W, R, i - 1);  // the assembly of this stage is done with the buffers: next stage's inputs
+#endif
     // thread -> (row group rg, column c): c < 64 covers the n1 trailing columns of F and the nc columns of K without any
     // integer division in the loops; every thread keeps its column
     const int c64 = ctx.tid & 63, rg = ctx.tid >> 6, nrg = ctx.nt >> 6 > 0 ? ctx.nt >> 6 : 1;

@@ -375,11 +375,11 @@ class ObcaSolver:
 
     PHASES = ["eval_pairs", "eval_nodes", "pair_eliminate", "node_assemble", "nullspace", "cross", "riccati_bwd", "riccati_fwd",
               "expand+residual", "multipliers", "local_backsub", "ipm_vector_ops", "ric_assemble", "ric_products", "ric_cholesky", "ric_ksolve",
-              "ns_setup", "ns_qr", "ns_tcols", "ns_store", "ns_project", "ipm_P1_errors", "ipm_P2_sigma", "ipm_P3_ftb", "ipm_P4_trial", "ipm_theta", "ipm_P5_accept"]
+              "ns_setup", "ns_qr", "ns_tcols", "ns_store", "ns_project", "ipm_P1_errors", "ipm_P2_sigma", "ipm_P3_ftb", "ipm_P4_trial", "ipm_theta", "ipm_P5_accept", "ra_zero+prefetch", "ra_Tmaps+sync", "ra_passA", "ra_passB"]
 
     def debug_profile(self):
-        buf = (ctypes.c_int64 * 27)()
-        self._check(self.lib.obca_debug_profile(self.handle, buf, 27))
+        buf = (ctypes.c_int64 * 31)()
+        self._check(self.lib.obca_debug_profile(self.handle, buf, 31))
         return {k: int(buf[i]) for i, k in enumerate(self.PHASES)}
 
     def debug_get_iterate(self, b=0):
