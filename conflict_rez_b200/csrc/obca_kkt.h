@@ -1102,12 +1102,14 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, dou
 struct RicWork {
   double *P, *p, *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *K, *Ab, *Bb, *db, *cb, *invd, *MAs, *MABs, *TBs;
   int *uoff, *npv, *npt;  // [MAXV + 1], [MAXV + 1], [V][Nmax]
+  const double** isrc;     // [n_in] address of every stage input at stage 0
+  int* istr;               // [n_in][2] (doubles per stage, first stage beyond the block's horizon)
 };
 
 inline size_t riccati_only_doubles(const Lay& L) {
   size_t nX = L.nX, nU = L.nU;
   return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU + ((size_t)L.V * L.Nmax + 2) / 2 +
-         (OBCA_RIC_PREFETCH ? (size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) + (size_t)L.V * 7 * (NRED + 1) : 0);
+         (OBCA_RIC_PREFETCH ? 3 * ((size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) + (size_t)L.V * 7 * (NRED + 1)) + 4 : 0);
 }
 
 // work arena shared by the null-space phase (NSW doubles per warp) and the Riccati phase
@@ -1116,6 +1118,7 @@ inline size_t riccati_work_doubles(const Lay& L, int nwarps) {
   return a > b ? a : b;
 }
 
+OBCA_HD int ric_input_count(const Lay& L);
 OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
   OBCA_ASSUME_SHARED(w);
   int nX = L.nX, nU = L.nU;
@@ -1144,34 +1147,51 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
   R.uoff = (int*)w;
   R.npv = R.uoff + (MAXV + 1);
   R.npt = R.npv + (MAXV + 1);  // [V][Nmax] free directions of every block
+  {
+    size_t off = (size_t)((char*)(R.npt + L.V * L.Nmax) - (char*)0);
+    off = (off + 15) & ~(size_t)15;
+    R.isrc = (const double**)((char*)0 + off);
+    R.istr = (int*)(R.isrc + ric_input_count(L));
+  }
 }
 
 // Stage inputs of the Riccati recursion (projected Hessians MA, coupling blocks MAB, last rows of the T maps).  The copies
 // for stage i-1 are issued as asynchronous global -> shared copies (cp.async, 8 bytes each, zero fill for blocks beyond a
 // vehicle's horizon) once stage i has consumed its inputs, so the global-memory latency hides behind the factorisation.
 OBCA_HD int ric_input_count(const Lay& L) { return L.V * (NSYM + NRED) + L.P * (NRED * NRED + 2 * NRED) + L.V * 7 * (NRED + 1); }
-OBCA_HD const double* ric_input_addr(const Lay& L, const Scratch& W, int i, int it, bool* active) {
+OBCA_HD const double* ric_input_addr(const Lay& L, const Scratch& W, int i, int it, int* lim) {
   const int n1 = L.V * (NSYM + NRED), n2 = n1 + L.P * (NRED * NRED + 2 * NRED);
   if (it < n1) {
     const int a = it / (NSYM + NRED);
-    *active = i < L.N[a];
+    *lim = L.N[a];
     return W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED) + it % (NSYM + NRED);
   }
   if (it < n2) {
     const int e = it - n1, p = e / (NRED * NRED + 2 * NRED);
-    *active = i * NK < L.Mp[p];
+    *lim = (L.Mp[p] + NK - 1) / NK;  // active while i * NK < Mp
     return W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED) + e % (NRED * NRED + 2 * NRED);
   }
   const int e = it - n2, a = e / (7 * (NRED + 1)), r = (e / (NRED + 1)) % 7, cc = e % (NRED + 1);
-  *active = i < L.N[a];
+  *lim = L.N[a];
   const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
   return cc < NRED ? T + (28 + r) * NRED + cc : T + NW * NRED + 28 + r;
+}
+// table of the stage inputs (address at stage 0, stride per stage, horizon): the per-stage fetch then needs no divisions
+OBCA_HD void ric_input_table(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R) {
+  const int tot = ric_input_count(L);
+  for (int it = ctx.tid; it < tot; it += ctx.nt) {
+    int lim, lim1;
+    const double* s0 = ric_input_addr(L, W, 0, it, &lim);
+    const double* s1 = ric_input_addr(L, W, 1, it, &lim1);
+    R.isrc[it] = s0;
+    R.istr[2 * it] = (int)(s1 - s0), R.istr[2 * it + 1] = lim;
+  }
 }
 OBCA_HD void ric_input_fetch(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R, int i) {
   const int tot = ric_input_count(L);
   for (int it = ctx.tid; it < tot; it += ctx.nt) {
-    bool active;
-    const double* src = ric_input_addr(L, W, i, it, &active);
+    const bool active = i < R.istr[2 * it + 1];
+    const double* src = R.isrc[it] + (size_t)i * R.istr[2 * it];
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(R.MAs + it)), "l"(active ? src : W.MA),
                  "r"(active ? 8 : 0)
@@ -1327,6 +1347,8 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
   }
   for (int it = ctx.tid; it < V * L.Nmax; it += ctx.nt) R.npt[it] = block_np(L, W, it / L.Nmax, it % L.Nmax);
 #if OBCA_RIC_PREFETCH
+  ric_input_table(ctx, L, W, R);
+  cta_sync(ctx);
   ric_input_fetch(ctx, L, W, R, L.Nmax - 1);
 #endif
   cta_sync(ctx);
