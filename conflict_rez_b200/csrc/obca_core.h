@@ -87,6 +87,7 @@ struct Lay {
   int V, O, P, Mv, Nmax, Smax, npset;
   int N[MAXV], M[MAXV], S[MAXV], heading[MAXV];
   int pa[MAXP], pb[MAXP], Mp[MAXP];
+  int nPairNodes;  // sum of Mp: the (pair, node) blocks that exist
   // primal fields
   int oZ, oLAM, oMU, oSD, oEL, oTS, oPL, oPM, oPS, oPSD, oPSN, oPEL, oDT, nx;
   // multiplier / residual fields
@@ -142,6 +143,8 @@ inline void lay_build(Lay& L, const ObcaDims& d, const double* final_heading) {
       L.Mp[L.P] = L.M[a] < L.M[b] ? L.M[a] : L.M[b];
       ++L.P;
     }
+  L.nPairNodes = 0;
+  for (int p = 0; p < L.P; ++p) L.nPairNodes += L.Mp[p];
   lay_offsets(L);
   L.nX = 7 * L.V + 1;
   L.nU = NP * L.V;
@@ -182,6 +185,7 @@ inline void lay_build_mpc(Lay& L, int horizon, int n_obstacles, int n_others) {
   L.S[0] = 1, L.N[0] = 1, L.M[0] = horizon, L.heading[0] = 0;
   L.P = n_others;
   for (int p = 0; p < n_others; ++p) L.pa[p] = 0, L.pb[p] = 0, L.Mp[p] = horizon;
+  L.nPairNodes = n_others * horizon;
   lay_offsets(L);
   L.nX = 5, L.nU = 2;
 }
@@ -589,9 +593,9 @@ OBCA_HDN void eval_pairs(const Ctx& ctx, const Lay& L, const Stat& S, const doub
   OBCA_ASSUME_STATIC(L, S);
   OBCA_ASSUME_GLOBAL(x), OBCA_ASSUME_GLOBAL(c), OBCA_ASSUME_GLOBAL(PG);
   if (y) OBCA_ASSUME_GLOBAL(y), OBCA_ASSUME_GLOBAL(gl);
-  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
-    int p = it / L.Mv, n = it % L.Mv;
-    if (n >= L.Mp[p]) continue;
+  for (int it = ctx.tid; it < L.nPairNodes; it += ctx.nt) {  // compact index over the existing (pair, node) blocks
+    int p = 0, n = it;
+    while (n >= L.Mp[p]) n -= L.Mp[p], ++p;
     Pose a, b;
     load_pose(L, x, L.pa[p], n, a);
     load_pose(L, x, L.pb[p], n, b);

@@ -181,9 +181,9 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
 OBCA_HDN void pair_eliminate(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, int* ok) {
   assume_scratch(W);
   OBCA_ASSUME_STATIC(L, S);
-  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
-    int p = it / L.Mv, n = it % L.Mv;
-    if (n >= L.Mp[p]) continue;
+  for (int it = ctx.tid; it < L.nPairNodes; it += ctx.nt) {  // compact index over the existing (pair, node) blocks
+    int p = 0, n = it;
+    while (n >= L.Mp[p]) n -= L.Mp[p], ++p;
     Pose a, b;
     load_pose(L, W.x, L.pa[p], n, a);
     load_pose(L, W.x, L.pb[p], n, b);
@@ -1848,9 +1848,9 @@ OBCA_HDN void local_backsub(const Ctx& ctx, const Lay& L, const Stat& S, const S
       }
     }
   }
-  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
-    int p = it / L.Mv, n = it % L.Mv;
-    if (n >= L.Mp[p]) continue;
+  for (int it = ctx.tid; it < L.nPairNodes; it += ctx.nt) {  // compact index over the existing (pair, node) blocks
+    int p = 0, n = it;
+    while (n >= L.Mp[p]) n -= L.Mp[p], ++p;
     int a = L.pa[p], b = L.pb[p];
     double dp[6] = {W.dx[L.Z(a, 0, n)], W.dx[L.Z(a, 1, n)], W.dx[L.Z(a, 2, n)], W.dx[L.Z(b, 0, n)], W.dx[L.Z(b, 1, n)], W.dx[L.Z(b, 2, n)]};
     pair_block_backsub(L, W, p, n, dp);
