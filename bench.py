@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 AGENTS = ["vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"]
 METRIC = "converged multi-vehicle OBCA solves/sec (batched)"
 # SURVEY.md section 8(d) convention for the 4-vehicle joint problem, per IPM iteration and instance
-DRAM_BYTES_PER_ITER_NCU = 22.2e6  # measured, see roofline.traffic_note
+DRAM_BYTES_PER_ITER_NCU = 21.9e6  # measured, see roofline.traffic_note
 BYTES_PER_ITER = 3.456e6
 FLOPS_PER_ITER_CONVENTION = 767e6
 FP64_PEAK_TFLOPS = 37.0  # B200 data sheet (non-tensor FP64); not measured on this pool
@@ -351,8 +351,8 @@ def main():
             "unit": "GB/s",
             "frac": achieved_gbs / peak,
             "traffic": DRAM_BYTES_PER_ITER_NCU * sum_iters / world,
-            "traffic_note": "22.2 MB of DRAM traffic per IPM iteration and instance (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-            "capture of k_solve, profiles/r01c_ncu_full_k_solve_summary_final.txt) x the iterations of one launch; 6.4x the algorithmic bytes: "
+            "traffic_note": "21.9 MB of DRAM traffic per IPM iteration and instance (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+            "capture of k_solve, profiles/r01c_ncu_full_k_solve_summary_final.txt) x the iterations of one launch; 6.3x the algorithmic bytes: "
             "per-CTA work areas (block solves, QR records, T maps) and local-memory arrays stream through L2/HBM every iteration",
             "peak_source": peak_src,
             "note": "algorithmic bytes = 3.456 MB per IPM iteration and instance (one read + one write of the primal-dual iterate, SURVEY.md 8d) "
