@@ -145,7 +145,7 @@ def prepare_joint_batch(
         muj[:, ia, :M] = pick(sol["mu"], d["mu"])[:, 0]
         dt_sum += pick(sol["dt"], d["dt"])
         cpu = lambda t: t.cpu().numpy()
-        singles.append(BatchResult(cpu(st), cpu(it), cpu(dbl[0]), cpu(dbl[1]), cpu(dbl[2]), cpu(dbl[3]), cpu(sol["z"]), None, None, cpu(sol["dt"]), None, None, None))
+        singles.append(BatchResult(cpu(st), cpu(it), cpu(dbl[0]), cpu(dbl[1]), cpu(dbl[2]), cpu(dbl[3]), cpu(dbl[4]), cpu(sol["z"]), None, None, cpu(sol["dt"]), None, None, None))
         sv.close()
     dg = {"pose": joint._to_dev(prob.init_pose, (B, V, 3)), "z": zj, "lam": lamj, "mu": muj, "dt": dt_sum / V}  # dt0: multi_vehicle_planner.py:360
     if joint.P:

@@ -27,17 +27,7 @@ from conflict_rez_b200.vehicle_types import VehicleBody, VehicleConfig
 
 def collocation_coefficients(K: int):
     """Lagrange-basis collocation matrices on tau = [0, Radau(K)] (reference: vehicle.py:54-97)."""
-    tau = warmstart.radau_nodes(K)
-    A, B, D = np.zeros((K + 1, K + 1)), np.zeros(K + 1), np.zeros(K + 1)
-    for j in range(K + 1):
-        p = np.poly1d([1.0])
-        for k in range(K + 1):
-            if k != j:
-                p *= np.poly1d([1.0, -tau[k]]) / (tau[j] - tau[k])
-        D[j] = p(1.0)
-        A[j] = np.polyder(p)(tau)
-        B[j] = np.polyint(p)(1.0)
-    return A, B, D
+    return warmstart.collocation_coefficients(K)
 
 
 class ObcaSol:

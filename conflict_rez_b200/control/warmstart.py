@@ -160,6 +160,23 @@ def radau_nodes(K=5):
     return np.append(0.0, (np.sort(legendre.legroots(c)) + 1.0) / 2.0)
 
 
+def collocation_coefficients(K: int = 5):
+    """Lagrange-basis collocation matrices on tau = [0, Radau(K)], computed the way the reference computes them
+    (numpy poly1d arithmetic, confrez/control/vehicle.py:54-97): A[j,k] = L_j'(tau_k), B[j] = int_0^1 L_j, D[j] = L_j(1).
+    The solver receives A and B through ObcaStatic, so host, oracle and kernels use bit-identical constants."""
+    tau = radau_nodes(K)
+    A, B, D = np.zeros((K + 1, K + 1)), np.zeros(K + 1), np.zeros(K + 1)
+    for j in range(K + 1):
+        p = np.poly1d([1.0])
+        for k in range(K + 1):
+            if k != j:
+                p *= np.poly1d([1.0, -tau[k]]) / (tau[j] - tau[k])
+        D[j] = p(1.0)
+        A[j] = np.polyder(p)(tau)
+        B[j] = np.polyint(p)(1.0)
+    return A, B, D
+
+
 def interp_ws_for_collocation(t, signals, N, K=5):
     """Linear interpolation of every signal (T,...) onto t_interp = (i + tau_k)/N * t[-1] (vehicle.py:321-331)."""
     tau = radau_nodes(K)

@@ -55,8 +55,27 @@ struct ObcaHandle {
   double* d_rw;    // [slots][rw_stride]
   Result* d_res;   // [B]
   int* d_counter;
+  int* d_order;    // [B] processing order of the instances (longest expected first), or identity
+  bool have_order;
   long long* d_prof;  // [slots][NPROF + 1]
   int64_t launches;
+};
+
+// Every entry point that touches the device runs on the handle's device and restores the caller's current device
+// afterwards (a process may hold handles on several GPUs, and torch keeps its own notion of the current device).
+struct DeviceGuard {
+#ifndef OBCA_HOST_EMU
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+#else
+  explicit DeviceGuard(int) {}
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -173,6 +192,7 @@ struct SolveArgs {
   Result* res;
   int B;
   int* counter;
+  const int* order;  // instance processed by the k-th pull of the work counter (nullptr: k itself)
   long long* prof;
   // debug modes: 0 = solve, 1 = eval at stored iterate, 2 = Newton step at stored iterate
   int mode, b_only;
@@ -193,10 +213,11 @@ OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, const Lay& L, con
   for (int q = ctx.tid; q < L.nx; q += ctx.nt) W.gl[q] = 0, W.dx[q] = 0;
   for (int q = ctx.tid; q < L.ny; q += ctx.nt) W.c[q] = 0, W.dy[q] = 0;
   cta_sync(ctx);
+  if (A.mode == 3 && L.mode != 0) return;
   if (L.mode == 0) eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
   else mpc_eval_all(ctx, L, S, W, W.x, W.y, W.c, W.gl, &f, &gdt);
   if (ctx.tid == 0) A.res[b].obj = f;
-  if (A.mode == 2) {
+  if (A.mode == 2 || A.mode == 3) {
     double mu = A.dbg_mu, dw = A.dbg_dw;
     for (int q = ctx.tid; q < L.nx; q += ctx.nt) {
       double lo = A.xL[q], hi = A.xU[q];
@@ -215,8 +236,15 @@ OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, const Lay& L, con
       W.sig[q] = sg, W.gphi[q] = gp;
     }
     cta_sync(ctx);
+    if (A.mode == 3) {  // K [dx; dy]: inputs in W.dzU / W.ry, outputs in W.dzL / W.ct
+      kkt_apply(ctx, L, S, W, W.dzU, W.ry, W.dzL, W.ct);
+      return;
+    }
     int ok = L.mode == 0 ? kkt_solve(ctx, L, S, W, RW, &sh->ok) : mpc_kkt_solve(ctx, L, S, W, RW, &sh->ok);
-    if (ctx.tid == 0) A.res[b].status = ok;
+    double rr = 0;
+    int nref = 0;
+    if (ok && L.mode == 0 && A.o.refine_steps > 0) nref = kkt_refine(ctx, L, S, W, RW, &sh->ok, A.o.refine_steps, A.o.refine_ratio, &rr);
+    if (ctx.tid == 0) A.res[b].status = ok, A.res[b].refines = nref, A.res[b].elastic = rr;
   }
 }
 
@@ -261,12 +289,12 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_solve(SolveArgs A)
     __syncthreads();
     if (threadIdx.x == 0) cur = atomicAdd(A.counter, 1);
     __syncthreads();
-    int b = cur;
-    if (b >= A.B) break;
+    if (cur >= A.B) break;
+    const int b = A.order ? A.order[cur] : cur;
     run_instance(ctx, A, sL, sS, b, blockIdx.x, &sh, RW);
   }
 }
-__global__ void k_stats(const Result* res, int B, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf, double* compl_inf) {
+__global__ void k_stats(const Result* res, int B, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf, double* compl_inf, double* elastic) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   if (status) status[b] = res[b].status;
@@ -275,6 +303,7 @@ __global__ void k_stats(const Result* res, int B, int32_t* status, int32_t* iter
   if (cviol) cviol[b] = res[b].cviol;
   if (dual_inf) dual_inf[b] = res[b].dual_inf;
   if (compl_inf) compl_inf[b] = res[b].compl_inf;
+  if (elastic) elastic[b] = res[b].elastic;
 }
 #endif
 
@@ -296,13 +325,14 @@ const char* obca_last_error(void) { return g_err.c_str(); }
 
 void obca_default_options(ObcaOptions* o) {
   o->tol = 1e-2, o->constr_viol_tol = 1e-2, o->dual_inf_tol = 1.0, o->compl_inf_tol = 1e-4;
-  o->mu_init = 0.1, o->dmin = 0.05, o->shrink_tube = 0.5, o->elastic_weight = 1e3, o->max_iter = 3000, o->reserved = 0;
+  o->mu_init = 0.1, o->dmin = 0.05, o->shrink_tube = 0.5, o->elastic_weight = 1e3, o->max_iter = 3000, o->refine_steps = -1;
 }
 
 static void apply_options(ObcaHandle* h, const ObcaOptions* o) {
   h->opts.tol = o->tol, h->opts.constr_viol_tol = o->constr_viol_tol, h->opts.dual_inf_tol = o->dual_inf_tol;
   h->opts.compl_inf_tol = o->compl_inf_tol, h->opts.mu_init = o->mu_init, h->opts.max_iter = o->max_iter;
   h->dmin = o->dmin, h->shrink = o->shrink_tube, h->rho = o->elastic_weight;
+  h->opts.refine_steps = o->refine_steps >= 0 ? o->refine_steps : (o->tol > 1e-5 ? 0 : 2);
 }
 
 int obca_create(const ObcaDims* dims, const ObcaOptions* opts, int device, ObcaHandle** out) {
@@ -323,8 +353,7 @@ int obca_create(const ObcaDims* dims, const ObcaOptions* opts, int device, ObcaH
 #ifndef OBCA_HOST_EMU
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("obca_create: no CUDA device (this library has no CPU fallback)");
-  if (device < 0 || device >= ndev) return fail("obca_create: bad device index");
-  CUDA_OK(cudaSetDevice(device));
+  if (device < 0 || device >= ndev) return fail("obca_create: bad device index");  // the caller's current device is left alone
 #endif
   ObcaHandle* h = new ObcaHandle();
   memset((void*)h, 0, sizeof(*h));
@@ -348,7 +377,8 @@ int obca_set_options(ObcaHandle* h, const ObcaOptions* opts) {
 
 static void free_device(ObcaHandle* h) {
   dev_free(h->d_L), dev_free(h->d_S), dev_free(h->d_tube), dev_free(h->d_xL), dev_free(h->d_xU);
-  dev_free(h->d_iter), dev_free(h->d_work), dev_free(h->d_rw), dev_free(h->d_res), dev_free(h->d_counter), dev_free(h->d_prof);
+  dev_free(h->d_iter), dev_free(h->d_work), dev_free(h->d_rw), dev_free(h->d_res), dev_free(h->d_counter), dev_free(h->d_order), dev_free(h->d_prof);
+  h->d_order = nullptr, h->have_order = false;
   h->d_prof = nullptr;
   h->d_L = nullptr, h->d_S = nullptr, h->d_tube = nullptr, h->d_xL = h->d_xU = nullptr;
   h->d_iter = h->d_work = h->d_rw = nullptr, h->d_res = nullptr, h->d_counter = nullptr;
@@ -356,6 +386,7 @@ static void free_device(ObcaHandle* h) {
 
 int obca_destroy(ObcaHandle* h) {
   if (!h) return 0;
+  DeviceGuard guard(h->device);
   free_device(h);
   delete h;
   return 0;
@@ -390,6 +421,7 @@ static void collocation_matrices(double cA[NK][NK], double cB[NK]) {
 
 int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   if (!h || !st) return fail("obca_set_static: null argument");
+  DeviceGuard guard(h->device);
   free_device(h);
   const bool mpc = h->dims.mode == OBCA_MODE_MPC;
   if (mpc) lay_build_mpc(h->L, h->dims.horizon, h->dims.O, h->dims.n_others);
@@ -408,6 +440,11 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   for (int q = 0; q < 8; ++q) S.limits[q] = st->limits[q];
   for (int a = 0; a < L.V; ++a) S.heading[a] = mpc ? 0.0 : st->final_heading[a];
   collocation_matrices(S.cA, S.cB);
+  if (st->colloc_A && st->colloc_B && !mpc)  // the caller's constants (the reference builds them with numpy poly1d arithmetic): bit-identical parity
+    for (int j = 0; j < NK; ++j) {
+      for (int k = 0; k < NK; ++k) S.cA[j][k] = st->colloc_A[j * NK + k];
+      S.cB[j] = st->colloc_B[j];
+    }
   {
     // inverse of A1[k][j] = cA[j][k] (j, k = 1..K) by Gauss-Jordan with partial pivoting: the interior collocation block
     double M[5][10];
@@ -482,7 +519,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   if (dev_alloc((void**)&h->d_L, sizeof(Lay)) || dev_alloc((void**)&h->d_S, sizeof(Stat)) || dev_alloc((void**)&h->d_tube, tube.size() * 8) ||
       dev_alloc((void**)&h->d_xL, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_xU, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_iter, (size_t)B * h->it_stride * 8) ||
       dev_alloc((void**)&h->d_work, (size_t)h->slots * h->wk_stride * 8) || dev_alloc((void**)&h->d_rw, (size_t)h->slots * h->rw_stride * 8) ||
-      dev_alloc((void**)&h->d_res, (size_t)B * sizeof(Result)) || dev_alloc((void**)&h->d_counter, sizeof(int)) ||
+      dev_alloc((void**)&h->d_res, (size_t)B * sizeof(Result)) || dev_alloc((void**)&h->d_counter, sizeof(int)) || dev_alloc((void**)&h->d_order, (size_t)B * sizeof(int)) ||
       dev_alloc((void**)&h->d_prof, (size_t)h->slots * (NPROF + 1) * sizeof(long long)))
     return fail("obca_set_static: device allocation failed");
   S.tube = h->d_tube;
@@ -501,6 +538,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
 int obca_set_init_pose(ObcaHandle* h, const double* pose, void* stream) {
   if (!h || !h->have_static) return fail("obca_set_init_pose: call obca_set_static first");
   if (h->L.mode != 0) return fail("obca_set_init_pose: collocation mode only (use obca_set_mpc_params)");
+  DeviceGuard guard(h->device);
   int B = h->dims.batch, per = h->L.V * 3;
 #ifdef OBCA_HOST_EMU
   (void)stream;
@@ -537,6 +575,7 @@ int obca_set_mpc_params(ObcaHandle* h, const double* cur, const double* ref, con
   if (!h || !h->have_static) return fail("obca_set_mpc_params: call obca_set_static first");
   if (h->L.mode != 1) return fail("obca_set_mpc_params: the handle was not created in MPC mode");
   if (!cur || !ref || (h->L.P > 0 && !others)) return fail("obca_set_mpc_params: null argument");
+  DeviceGuard guard(h->device);
   const int B = h->dims.batch, N = h->L.Mv, P = h->L.P, per = 5 + 3 * N * (1 + P);
 #ifdef OBCA_HOST_EMU
   (void)stream;
@@ -578,7 +617,7 @@ int obca_measure_dfma_peak(int device, double* tflops) {
   *tflops = 0.0;
   return fail("obca_measure_dfma_peak: not available in the host emulation");
 #else
-  CUDA_OK(cudaSetDevice(device));
+  DeviceGuard guard(device);
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   const int blocks = prop.multiProcessorCount * 8, thr = 256, it = 1 << 14;
@@ -620,6 +659,7 @@ __global__ void k_joint_dual_ws(const Lay* L, const Stat* S, const double* z, do
 int obca_dual_ws(ObcaHandle* h, const double* z, double* lam, double* mu, void* stream) {
   if (!h || !h->have_static) return fail("obca_dual_ws: call obca_set_static first");
   if (!z || !lam || !mu) return fail("obca_dual_ws: null argument");
+  DeviceGuard guard(h->device);
   const size_t tot = (size_t)h->dims.batch * h->L.V * h->L.Mv * h->L.O;
 #ifdef OBCA_HOST_EMU
   (void)stream;
@@ -639,6 +679,7 @@ int obca_joint_dual_ws(ObcaHandle* h, const double* z, double* pl, double* pm, d
   if (h->L.mode != 0) return fail("obca_joint_dual_ws: collocation mode only");
   if (h->L.P == 0) return 0;
   if (!z || !pl || !pm || !ps) return fail("obca_joint_dual_ws: null argument");
+  DeviceGuard guard(h->device);
   const size_t tot = (size_t)h->dims.batch * h->L.P * h->L.Mv;
 #ifdef OBCA_HOST_EMU
   (void)stream;
@@ -653,6 +694,7 @@ int obca_joint_dual_ws(ObcaHandle* h, const double* z, double* pl, double* pm, d
 
 static int run_pack(ObcaHandle* h, const PackArgs& A, bool unpack, void* stream) {
   int B = h->dims.batch, ne = pack_elems(h->L);
+  DeviceGuard guard(h->device);
 #ifdef OBCA_HOST_EMU
   (void)stream;
   for (int b = 0; b < B; ++b)
@@ -690,6 +732,7 @@ static SolveArgs make_args(ObcaHandle* h, int mode, int b) {
   A.iter = h->d_iter, A.work = h->d_work, A.rw = h->d_rw;
   A.it_stride = h->it_stride, A.wk_stride = h->wk_stride, A.rw_stride = h->rw_stride;
   A.res = h->d_res, A.B = h->dims.batch, A.counter = h->d_counter, A.mode = mode, A.b_only = b;
+  A.order = h->have_order ? h->d_order : nullptr;
   A.prof = getenv("OBCA_PROFILE") ? h->d_prof : nullptr;
   A.dbg_mu = 0, A.dbg_dw = 0;
   A.rw_in_smem = 1;
@@ -697,6 +740,7 @@ static SolveArgs make_args(ObcaHandle* h, int mode, int b) {
 }
 
 static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
+  DeviceGuard guard(h->device);
 #ifdef OBCA_HOST_EMU
   (void)stream;
   Shared sh;
@@ -719,13 +763,32 @@ static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
   return 0;
 }
 
+int obca_set_order(ObcaHandle* h, const int32_t* order_dev, void* stream) {
+  if (!h || !h->have_static) return fail("obca_set_order: call obca_set_static first");
+  DeviceGuard guard(h->device);
+  if (!order_dev) {
+    h->have_order = false;
+    return 0;
+  }
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  memcpy(h->d_order, order_dev, (size_t)h->dims.batch * sizeof(int));
+#else
+  CUDA_OK(cudaMemcpyAsync(h->d_order, order_dev, (size_t)h->dims.batch * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+#endif
+  h->have_order = true;
+  return 0;
+}
+
 int obca_solve(ObcaHandle* h, void* stream) {
   if (!h || !h->have_static) return fail("obca_solve: call obca_set_static first");
   return launch(h, make_args(h, 0, 0), stream);
 }
 
-int obca_get_stats(ObcaHandle* h, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf, double* compl_inf, void* stream) {
+int obca_get_stats(ObcaHandle* h, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf, double* compl_inf, double* elastic,
+                   void* stream) {
   if (!h || !h->have_static) return fail("obca_get_stats: call obca_set_static first");
+  DeviceGuard guard(h->device);
   int B = h->dims.batch;
 #ifdef OBCA_HOST_EMU
   (void)stream;
@@ -737,9 +800,10 @@ int obca_get_stats(ObcaHandle* h, int32_t* status, int32_t* iters, double* obj, 
     if (cviol) cviol[b] = r.cviol;
     if (dual_inf) dual_inf[b] = r.dual_inf;
     if (compl_inf) compl_inf[b] = r.compl_inf;
+    if (elastic) elastic[b] = r.elastic;
   }
 #else
-  k_stats<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_res, B, status, iters, obj, cviol, dual_inf, compl_inf);
+  k_stats<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_res, B, status, iters, obj, cviol, dual_inf, compl_inf, elastic);
   h->launches++;
   CUDA_OK(cudaGetLastError());
 #endif
@@ -750,6 +814,7 @@ int64_t obca_launch_count(const ObcaHandle* h) { return h ? h->launches : 0; }
 
 int obca_debug_profile(ObcaHandle* h, int64_t* out, int n) {
   if (!h || !h->have_static) return fail("obca_debug_profile: call obca_set_static first");
+  DeviceGuard guard(h->device);
   if (dev_sync()) return fail("device sync failed");
   std::vector<long long> buf((size_t)h->slots * (NPROF + 1));
   d2h(buf.data(), h->d_prof, buf.size() * sizeof(long long));
@@ -773,6 +838,7 @@ int obca_layout(const ObcaHandle* h, int64_t* out, int n) {
 
 int obca_debug_get_iterate(ObcaHandle* h, int b, double* x, double* y, double* zL, double* zU) {
   if (!h || !h->have_static || b < 0 || b >= h->dims.batch) return fail("obca_debug_get_iterate: bad argument");
+  DeviceGuard guard(h->device);
   if (dev_sync()) return fail("device sync failed");
   Scratch W;
   carve_iterate(W, h->L, h->d_iter + (size_t)b * h->it_stride);
@@ -785,6 +851,7 @@ int obca_debug_get_iterate(ObcaHandle* h, int b, double* x, double* y, double* z
 
 int obca_debug_set_iterate(ObcaHandle* h, int b, const double* x, const double* y, const double* zL, const double* zU) {
   if (!h || !h->have_static || b < 0 || b >= h->dims.batch) return fail("obca_debug_set_iterate: bad argument");
+  DeviceGuard guard(h->device);
   Scratch W;
   carve_iterate(W, h->L, h->d_iter + (size_t)b * h->it_stride);
   if (x) h2d(W.x, x, h->L.nx * 8);
@@ -796,6 +863,7 @@ int obca_debug_set_iterate(ObcaHandle* h, int b, const double* x, const double* 
 
 int obca_debug_eval(ObcaHandle* h, int b, double* c, double* gl, double* f) {
   if (!h || !h->have_static || b < 0 || b >= h->dims.batch) return fail("obca_debug_eval: bad argument");
+  DeviceGuard guard(h->device);
   if (launch(h, make_args(h, 1, b), nullptr)) return -1;
   if (dev_sync()) return fail("obca_debug_eval: kernel failed");
   Scratch W;
@@ -810,6 +878,7 @@ int obca_debug_eval(ObcaHandle* h, int b, double* c, double* gl, double* f) {
 
 int obca_debug_step(ObcaHandle* h, int b, double mu, double delta_w, double* dx, double* dy, int32_t* ok) {
   if (!h || !h->have_static || b < 0 || b >= h->dims.batch) return fail("obca_debug_step: bad argument");
+  DeviceGuard guard(h->device);
   SolveArgs A = make_args(h, 2, b);
   A.dbg_mu = mu, A.dbg_dw = delta_w;
   if (launch(h, A, nullptr)) return -1;
@@ -821,6 +890,23 @@ int obca_debug_step(ObcaHandle* h, int b, double mu, double delta_w, double* dx,
   Result r;
   d2h(&r, h->d_res + b, sizeof(r));
   if (ok) *ok = r.status;
+  return 0;
+}
+
+int obca_debug_kkt_apply(ObcaHandle* h, int b, double delta_w, const double* dx, const double* dy, double* r1, double* r2) {
+  if (!h || !h->have_static || b < 0 || b >= h->dims.batch || !dx || !dy) return fail("obca_debug_kkt_apply: bad argument");
+  if (h->L.mode != 0) return fail("obca_debug_kkt_apply: collocation mode only");
+  DeviceGuard guard(h->device);
+  Scratch W;
+  carve_work(W, h->L, h->d_work);
+  h2d(W.dzU, dx, h->L.nx * 8);
+  h2d(W.ry, dy, h->L.ny * 8);
+  SolveArgs A = make_args(h, 3, b);
+  A.dbg_mu = 0, A.dbg_dw = delta_w;
+  if (launch(h, A, nullptr)) return -1;
+  if (dev_sync()) return fail("obca_debug_kkt_apply: kernel failed");
+  if (r1) d2h(r1, W.dzL, h->L.nx * 8);
+  if (r2) d2h(r2, W.ct, h->L.ny * 8);
   return 0;
 }
 

@@ -78,6 +78,10 @@ constexpr int NXMAX = 7 * MAXV + 1;
 constexpr int NUMAX = NP * MAXV;
 constexpr int FILTER_MAX = 64;
 constexpr double DELTA_C_LOCAL = 1e-8;
+#ifndef OBCA_PIVOT_TOL
+#define OBCA_PIVOT_TOL 1e-14
+#endif
+constexpr double PIVOT_TOL = OBCA_PIVOT_TOL;  // relative size below which a Riccati pivot counts as non-positive (wrong inertia -> delta_w is raised)
 
 // ------------------------------------------------------------------------------------------------
 // [LAYOUT]
@@ -211,6 +215,8 @@ struct Stat {
 struct Opts {
   double tol, constr_viol_tol, dual_inf_tol, compl_inf_tol, mu_init;
   int max_iter;
+  int refine_steps = 0;         // correction solves per Newton system (obca_refine.h)
+  double refine_ratio = 1e-10;  // IPOPT residual_ratio_max
   // IPOPT constants
   double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
   double bound_push = 1e-2, bound_frac = 1e-2, kappa_sigma = 1e10, kappa_d = 1e-4, s_max = 100.0;
@@ -224,7 +230,7 @@ struct Scratch {
   // x-layout vectors
   double *x, *zL, *zU, *dx, *dzL, *dzU, *gl, *gphi, *sig, *xt;
   // y-layout vectors
-  double *y, *dy, *c, *ct;
+  double *y, *dy, *c, *ct, *ry;  // ry: correction of dy in the refinement loop (obca_refine.h)
   // best "acceptable" iterate so far (IPOPT StoreAcceptablePoint): x, zL, zU, y
   double *bx, *bzL, *bzU, *by;
   // structured solve
@@ -258,13 +264,17 @@ inline size_t iterate_doubles(const Lay& L) {
   return ev(3 * ev(L.nx) + ev(L.ny) + par + 8);
 }
 
+// doubles per node of the HN buffer: the packed 7 x 7 node Hessian; in MPC mode the evaluation also uses it as scratch for
+// the dynamics / obstacle gradient pieces ([N][5] + [N][O][3], obca_mpc.h), which outgrows 28 per node for O >= 8
+OBCA_HD int hn_per_node(const Lay& L) { return (L.mode == 1 && 5 + 3 * L.O > 28) ? 5 + 3 * L.O : 28; }
+
 // per-slot work area (one per resident CTA)
 inline size_t work_doubles(const Lay& L) {
   size_t n = 0;
-  n += 10 * ev(L.nx) + 4 * ev(L.ny);
+  n += 10 * ev(L.nx) + 5 * ev(L.ny);
   n += (size_t)L.V * L.Mv * L.O * 48;
   n += (size_t)L.P * L.Mv * (112 + 27 + 6);
-  n += (size_t)L.V * L.Mv * (28 + 7 + 7);
+  n += (size_t)L.V * L.Mv * (hn_per_node(L) + 7 + 7);
   n += (size_t)L.V * L.Nmax * ((NW * NRED + NW) + QRSZ + (NSYM + NRED) + NS + 2 * EXSZ + 2) + EXSZ;
   n += (size_t)L.P * L.Nmax * (NRED * NRED + 2 * NRED);
   n += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
@@ -298,11 +308,12 @@ OBCA_HD void carve_work(Scratch& W, const Lay& L, double* p) {
   W.bzL = p, p += nx;
   W.bzU = p, p += nx;
   W.by = p, p += ny;
+  W.ry = p, p += ny;
   W.XO = p, p += (size_t)L.V * L.Mv * L.O * 48;
   W.XP = p, p += (size_t)L.P * L.Mv * 112;
   W.PH = p, p += (size_t)L.P * L.Mv * 27;
   W.PG = p, p += (size_t)L.P * L.Mv * 6;
-  W.HN = p, p += (size_t)L.V * L.Mv * 28;
+  W.HN = p, p += (size_t)L.V * L.Mv * hn_per_node(L);
   W.GN = p, p += (size_t)L.V * L.Mv * 7;
   W.HD = p, p += (size_t)L.V * L.Mv * 7;
   W.TT = p, p += (size_t)L.V * L.Nmax * (NW * NRED + NW);
@@ -337,6 +348,8 @@ OBCA_HD void assume_scratch(const Scratch& W) {
 struct Result {
   int status, iters;
   double obj, cviol, dual_inf, compl_inf, mu, dt;
+  double elastic;  // largest elastic variable at the returned point
+  int refines, restarts;  // correction solves of the refinement loop; dual restorations (obca_ipm.h)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -789,4 +802,5 @@ OBCA_HDN void eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Scratc
 #include "obca_kkt.h"
 #include "obca_mpc.h"
 #include "obca_ws.h"
+#include "obca_refine.h"
 #include "obca_ipm.h"

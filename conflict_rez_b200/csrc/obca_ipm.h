@@ -180,9 +180,11 @@ OBCA_HDN void push_into_bounds(const Ctx& ctx, const Lay& L, const double* xL, c
   cta_sync(ctx);
 }
 
+// One interior-point run from the point in W.x (slack initialisation, push into the bounds, z = 1, y = 0, mu = mu_init).
+// `it` and `n_refine` accumulate over the runs of one instance.  Returns the status; *el_out = largest elastic variable.
 template <int MODE>
-OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
-                        const double* xU, const Scratch& W, double* RW, size_t rw_cap, Shared* sh, Result* res) {
+OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
+                         const double* xU, const Scratch& W, double* RW, size_t rw_cap, Shared* sh, Result* res, int& it, int& n_refine, double* el_out) {
   assume_scratch(W);
   OBCA_ASSUME_STATIC(L, S);
   OBCA_ASSUME_GLOBAL(xL), OBCA_ASSUME_GLOBAL(xU);
@@ -210,7 +212,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
   // IPOPT acceptable-point bookkeeping: acceptable_tol 1e-6, acceptable_iter 15
   double best_E = INFINITY, best_f = 0, best_cv = 0, best_du = 0, best_co = 0;
   int n_acceptable = 0;
-  int status = OBCA_MAXITER_EXCEEDED, it = 0;
+  int status = OBCA_MAXITER_EXCEEDED;
   double dual_inf = 0, cviol = 0, compl0 = 0;
   const Stage st = {RW, rw_cap, sh->bars};
   // barrier terms of the current iterate: carried over from the accepted trial point (bit-identical x), recomputed otherwise
@@ -344,6 +346,10 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       cta_sync(ctx);
       if (model_kkt<MODE>(ctx, L, S, W, RW, &sh->ok)) {
         have = true;
+        if (MODE == 0 && o.refine_steps > 0) {
+          double rr;
+          n_refine += kkt_refine(ctx, L, S, W, RW, &sh->ok, o.refine_steps, o.refine_ratio, &rr);
+        }
         break;
       }
       if (first) {
@@ -432,7 +438,9 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     // tiny-step rule: a step below 10 eps relative size is accepted without line search and forces a mu update
     if (rel < 10 * EPS) {
       if (tiny_last && mu <= mu_min) {
-        status = OBCA_SOLVED_TO_ACCEPTABLE_LEVEL;
+        // IPOPT: Search_Direction_Becomes_Too_Small (an error for CasADi) unless this iterate passes the acceptable test
+        const bool acc_here = E0 <= 1e-6 && cviol <= 1e-2 && compl0 <= 1e-2;
+        status = acc_here ? OBCA_SOLVED_TO_ACCEPTABLE_LEVEL : OBCA_SEARCH_DIRECTION_TOO_SMALL;
         break;
       }
       tiny_last = true, force_mu = true;
@@ -487,7 +495,7 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       if (okp) {
         int nf = sh->filt_n;
         for (int k = 0; k < nf; ++k)
-          if (tht >= sh->filt_theta[k] && pht >= sh->filt_phi[k]) okp = false;
+          if (tht - sh->filt_theta[k] > slack_th && pht - sh->filt_phi[k] > slack_phi) okp = false;  // same comparison slack as the acceptance tests
       }
       if (okp) {
         bool switching = theta <= theta_min && dphi < 0 && alpha * pow(-dphi, o.s_phi) > o.delta_ls * pow(theta, o.s_theta);
@@ -557,16 +565,83 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     f = best_f, cviol = best_cv, dual_inf = best_du, compl0 = best_co;
     cta_sync(ctx);
   }
+  // Elastic variables of the distance rows (exact l1 penalty): at a solution of the reference problem they vanish.  A point
+  // that converged with an active elastic variable solves the penalised problem only -- the reference problem is (locally)
+  // infeasible there, IPOPT would report Infeasible_Problem_Detected and Opti would raise.
+  double el_max = 0;
+  for (int q = ctx.tid; q < L.V * L.O * L.Mv; q += ctx.nt) el_max = fmax(el_max, W.x[L.oEL + q]);
+  for (int q = ctx.tid; q < L.P * L.Mv; q += ctx.nt) el_max = fmax(el_max, W.x[L.oPEL + q]);
+  el_max = cta_max(ctx, el_max);
+  *el_out = el_max;
   if (ctx.tid == 0) {
     res->status = status;
     res->iters = it;
     res->obj = f;
-    res->cviol = cviol;
+    res->cviol = fmax(cviol, el_max);
+    res->elastic = el_max;
+    res->refines = n_refine;
     res->dual_inf = dual_inf;
     res->compl_inf = compl0;
     res->mu = mu;
     res->dt = W.x[L.oDT];
   }
+  cta_sync(ctx);
+  return status;
+}
+
+// Dual restoration.  The OBCA dual blocks are non-convex (|A'lam|^2 = 1 is an equality): besides the separating direction
+// (maximal dual distance) the opposite direction is a stationary point too, and with the elastic variable on the distance row
+// the iteration can converge to it -- the elastic variable then carries a "violation" of metres although the shapes are far
+// apart (observed from the reference's random first-step duals, vehicle_follower.py:401-402).  IPOPT meets the hard row
+// there, fails the line search and enters its restoration phase; the equivalent here is exact and local: every block whose
+// elastic variable is active gets the closed-form separating duals of its current poses (obca_ws.h, the same formulas as the
+// dual warm start), and the interior-point iteration restarts from that point.
+template <int MODE>
+OBCA_HDN void dual_restore(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double thr) {
+  assume_scratch(W);
+  OBCA_ASSUME_STATIC(L, S);
+  double* x = W.x;
+  for (int it = ctx.tid; it < L.V * L.O * L.Mv; it += ctx.nt) {
+    const int n = it % L.Mv, aj = it / L.Mv, a = aj / L.O, j = aj % L.O;
+    if (n >= L.M[a] || !(x[L.EL(a, j, n)] > thr)) continue;
+    double lam[4], mu[4];
+    ws_obstacle_duals(S, j, x[L.Z(a, 0, n)], x[L.Z(a, 1, n)], x[L.Z(a, 2, n)], lam, mu);
+    for (int r = 0; r < 4; ++r) x[L.LAM(a, j, r, n)] = lam[r], x[L.MU(a, j, r, n)] = mu[r];
+  }
+  for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
+    const int p = it / L.Mv, n = it % L.Mv;
+    if (n >= L.Mp[p] || !(x[L.PEL(p, n)] > thr)) continue;
+    Pose a, b;
+    load_pose(L, x, L.pa[p], n, a);
+    if (MODE == 1) load_other_pose(L, mpc_par(L, W), p, n, b);
+    else load_pose(L, x, L.pb[p], n, b);
+    double lam[4], mu[4], sv[2];
+    ws_pair_duals(S, a.x, a.y, a.psi, b.x, b.y, b.psi, lam, mu, sv);
+    for (int r = 0; r < 4; ++r) x[L.PL(p, r, n)] = lam[r], x[L.PM(p, r, n)] = mu[r];
+    x[L.PS(p, 0, n)] = sv[0], x[L.PS(p, 1, n)] = sv[1];
+  }
+  cta_sync(ctx);
+}
+
+template <int MODE>
+OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
+                        const double* xU, const Scratch& W, double* RW, size_t rw_cap, Shared* sh, Result* res) {
+  int it = 0, n_refine = 0, restarts = 0, status;
+  double el_max;
+  const double thr = fmax(o.constr_viol_tol, 1e-8);
+  for (;;) {
+    status = ipm_attempt<MODE>(ctx, L, S, o, cnt, xL, xU, W, RW, rw_cap, sh, res, it, n_refine, &el_max);
+    if (!(status >= 0 && el_max > thr)) break;
+    if (restarts >= 2 || it >= o.max_iter) {
+      // a converged point of the penalised problem with an active elastic variable: the reference problem (hard distance rows)
+      // is locally infeasible there; IPOPT reports Infeasible_Problem_Detected and Opti raises
+      status = OBCA_INFEASIBLE_PROBLEM_DETECTED;
+      break;
+    }
+    dual_restore<MODE>(ctx, L, S, W, thr);
+    ++restarts;
+  }
+  if (ctx.tid == 0) res->status = status, res->restarts = restarts;
 }
 
 }  // namespace obca

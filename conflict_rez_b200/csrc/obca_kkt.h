@@ -115,10 +115,11 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
       } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) bl[r] = -W.gphi[L.PL(p, r, n)], bm[r] = -W.gphi[L.PM(p, r, n)];
-        by[0] = -B.c[0] - W.gphi[L.PSD(p, n)] * isd + W.gphi[L.PEL(p, n)] * iel;
+        // the row residuals are read from W.c (not recomputed): the refinement solve passes its own right-hand side
+        by[0] = -W.c[L.YPAIR(p, 0, n)] - W.gphi[L.PSD(p, n)] * isd + W.gphi[L.PEL(p, n)] * iel;
 #pragma unroll
-        for (int r = 1; r < 5; ++r) by[r] = -B.c[r];
-        by[5] = -B.c[5] - W.gphi[L.PSN(p, n)] * isn;
+        for (int r = 1; r < 5; ++r) by[r] = -W.c[L.YPAIR(p, r, n)];
+        by[5] = -W.c[L.YPAIR(p, 5, n)] - W.gphi[L.PSN(p, n)] * isn;
         bs[0] = -W.gphi[L.PS(p, 0, n)], bs[1] = -W.gphi[L.PS(p, 1, n)];
       }
       // ry = J D^-1 b - by   (J rows: yd [-ba, -bb]; e1 [ea; fa | 0]; e2 [0 | eb; fb]; yn 0)
@@ -256,7 +257,8 @@ OBCA_HD void obs_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, 
       Ss[sym(1, 1)] += DELTA_C_LOCAL, Ss[sym(2, 2)] += DELTA_C_LOCAL, Ss[sym(3, 3)] += DELTA_C_LOCAL;
       if (!chol_packed<4>(Ss)) *ok = 0;
       const double Cy[4][3] = {{B.u[0], B.u[1], 0.0}, {0.0, 0.0, dRtu[0]}, {0.0, 0.0, dRtu[1]}, {0.0, 0.0, 0.0}};
-      const double byr[4] = {-B.c[0] - W.gphi[L.SD(a, j, n)] * isd + W.gphi[L.EL(a, j, n)] * iel, -B.c[1], -B.c[2], -B.c[3]};
+      const double byr[4] = {-W.c[L.YOBS(a, j, 0, n)] - W.gphi[L.SD(a, j, n)] * isd + W.gphi[L.EL(a, j, n)] * iel, -W.c[L.YOBS(a, j, 1, n)],
+                             -W.c[L.YOBS(a, j, 2, n)], -W.c[L.YOBS(a, j, 3, n)]};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         double t[4], ry[4];
@@ -722,6 +724,7 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
               { *ok = 0; OBCA_DBG("ns fail line %d a=%d i=%d rk=%d ndrop=%d nem=%d nr=%d\n", 697, a, i, rk, ndrop, nem, nr); }
           }
           dr[0] = (double)j, dr[1] = (double)slot, dr[2] = (double)rk;
+          OBCA_DBG("ns drop a=%d i=%d row=%d rk=%d slot=%d hmax=%.3e scale=%.3e h7=%.3e h8=%.3e beta=%.3e full=%.3e rref=%.3e\n", a, i, j, rk, slot, hmax, scale, h[7], h[8], beta, full, rref[j]);
           for (int m = 0; m < 9; ++m) dr[3 + 35 + m] = h[m];
         }
       }
@@ -1435,7 +1438,7 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     const int c64 = ctx.tid & 63, rg = ctx.tid >> 6, nrg = ctx.nt >> 6 > 0 ? ctx.nt >> 6 : 1;
     for (int j = 0; j < nu; ++j) {
       double d = R.F[j * nu + j];
-      const bool bad = !(d > 1e-14 * fmax(1.0, fabs(R.R[j * nu + j])));
+      const bool bad = !(d > PIVOT_TOL * fmax(1.0, fabs(R.R[j * nu + j])));
       if (bad) OBCA_DBG("riccati bad pivot stage %d j=%d nu=%d d=%.3e R=%.3e\n", i, j, nu, R.F[j * nu + j], R.R[j * nu + j]);
       if (bad) d = 1.0;
 #if defined(__CUDA_ARCH__)
@@ -1569,7 +1572,7 @@ OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, in
     double s = p0[idt];
     for (int m = 0; m < idt; ++m) s += P0[idt * nX + m] * X[m];
     double piv = P0[idt * nX + idt];
-    if (!(piv > 1e-14)) {
+    if (!(piv > PIVOT_TOL * fmax(1.0, fabs(p0[idt])))) {
       *ok = 0;
       piv = 1.0;
     }

@@ -26,6 +26,8 @@ RETURN_STATUS = {
     -2: "Restoration_Failed",
     -3: "Error_In_Step_Computation",
     -4: "Invalid_Number_Detected",
+    -5: "Search_Direction_Becomes_Too_Small",
+    -6: "Infeasible_Problem_Detected",
     -100: "Not_Solved",
 }
 
@@ -55,7 +57,7 @@ class ObcaOptions(ctypes.Structure):
         ("shrink_tube", ctypes.c_double),
         ("elastic_weight", ctypes.c_double),
         ("max_iter", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("refine_steps", ctypes.c_int32),
     ]
 
 
@@ -66,6 +68,8 @@ class ObcaStatic(ctypes.Structure):
     _fields_ = [(n, _dp) for n in ("obs_A", "obs_b", "tube_A", "tube_b", "body_G", "body_g", "region", "limits", "final_heading")] + [
         ("wb", ctypes.c_double),
         ("mpc_dt", ctypes.c_double),
+        ("colloc_A", _dp),
+        ("colloc_B", _dp),
     ]
 
 
@@ -83,6 +87,7 @@ EXPORTS = [
     "obca_dual_ws",
     "obca_joint_dual_ws",
     "obca_measure_dfma_peak",
+    "obca_set_order",
     "obca_solve",
     "obca_get_solution",
     "obca_get_stats",
@@ -92,6 +97,7 @@ EXPORTS = [
     "obca_debug_set_iterate",
     "obca_debug_eval",
     "obca_debug_step",
+    "obca_debug_kkt_apply",
     "obca_debug_profile",
 ]
 
@@ -123,9 +129,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.obca_dual_ws.argtypes = [vp, vp, vp, vp, vp]
     lib.obca_joint_dual_ws.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.obca_measure_dfma_peak.argtypes = [ctypes.c_int, _dp]
+    lib.obca_set_order.argtypes = [vp, vp, vp]
     lib.obca_solve.argtypes = [vp, vp]
     lib.obca_get_solution.argtypes = [vp] + [vp] * 7 + [vp]
-    lib.obca_get_stats.argtypes = [vp] + [vp] * 6 + [vp]
+    lib.obca_get_stats.argtypes = [vp] + [vp] * 7 + [vp]
     lib.obca_launch_count.argtypes = [vp]
     lib.obca_launch_count.restype = ctypes.c_int64
     lib.obca_layout.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
@@ -133,6 +140,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.obca_debug_set_iterate.argtypes = [vp, ctypes.c_int] + [_dp] * 4
     lib.obca_debug_eval.argtypes = [vp, ctypes.c_int, _dp, _dp, _dp]
     lib.obca_debug_step.argtypes = [vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, _dp, _dp, i32p]
+    lib.obca_debug_kkt_apply.argtypes = [vp, ctypes.c_int, ctypes.c_double, _dp, _dp, _dp, _dp]
     lib.obca_debug_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
     return lib
 
@@ -148,6 +156,7 @@ class SolveOptions:
     mu_init: float = 0.1
     max_iter: int = 3000
     elastic_weight: float = 1e3
+    refine_steps: int = -1  # iterative-refinement solves per Newton system; -1: none at tol > 1e-5, 2 at tight tolerances
 
 
 @dataclass
@@ -158,6 +167,7 @@ class BatchResult:
     cviol: np.ndarray
     dual_inf: np.ndarray
     compl_inf: np.ndarray
+    elastic: np.ndarray  # largest elastic variable of the distance rows (0 at a solution of the reference problem)
     z: np.ndarray  # (B,V,Mmax,7)
     lam: np.ndarray
     mu: np.ndarray
@@ -199,13 +209,17 @@ class ObcaSolver:
             dims.n_sets[a] = int(prob.n_sets[a])
         copts = ObcaOptions()
         self.lib.obca_default_options(ctypes.byref(copts))
-        for name in ("tol", "constr_viol_tol", "dual_inf_tol", "compl_inf_tol", "mu_init", "max_iter", "elastic_weight"):
+        for name in ("tol", "constr_viol_tol", "dual_inf_tol", "compl_inf_tol", "mu_init", "max_iter", "elastic_weight", "refine_steps"):
             setattr(copts, name, getattr(self.opts, name))
         copts.dmin, copts.shrink_tube = prob.dmin, prob.shrink_tube
         self.handle = ctypes.c_void_p()
         dev_index = self.device.index or 0 if self.device.type == "cuda" else 0
         self._check(self.lib.obca_create(ctypes.byref(dims), ctypes.byref(copts), dev_index, ctypes.byref(self.handle)))
         keep = {n: np.ascontiguousarray(getattr(prob, n), dtype=np.float64) for n in ("obs_A", "obs_b", "tube_A", "tube_b", "body_G", "body_g", "region", "limits", "final_heading")}
+        from conflict_rez_b200.control.warmstart import collocation_coefficients
+
+        cA, cB, _ = collocation_coefficients(prob.K)  # the reference's own construction (vehicle.py:54-97), bit-identical on both sides
+        keep["colloc_A"], keep["colloc_B"] = np.ascontiguousarray(cA), np.ascontiguousarray(cB)
         st = ObcaStatic(wb=float(prob.wb), **{n: _np_ptr(a) for n, a in keep.items()})
         self._check(self.lib.obca_set_static(self.handle, ctypes.byref(st)))
         self._stream = None
@@ -320,6 +334,16 @@ class ObcaSolver:
             self.lib.obca_set_initial(self.handle, _ptr(d["z"]), _ptr(d["lam"]), _ptr(d["mu"]), _ptr(d["dt"]), _ptr(d.get("pl")), _ptr(d.get("pm")), _ptr(d.get("ps")), s)
         )
 
+    def set_order(self, predicted_cost=None):
+        """Longest-expected-first processing order of the batch (``obca_set_order``): ``predicted_cost`` (B,) array or device
+        tensor, e.g. the iteration counts of the single-vehicle solves behind the warm start; None restores 0..B-1."""
+        if predicted_cost is None:
+            self._check(self.lib.obca_set_order(self.handle, None, self._stream_ptr()))
+            return
+        cost = torch.as_tensor(predicted_cost, device=self.device)
+        self._order = torch.argsort(cost, descending=True, stable=True).to(torch.int32).contiguous()
+        self._check(self.lib.obca_set_order(self.handle, _ptr(self._order), self._stream_ptr()))
+
     def run(self):
         """Launch the batched interior-point solve on the current stream (asynchronous)."""
         self._check(self.lib.obca_solve(self.handle, self._stream_ptr()))
@@ -329,7 +353,7 @@ class ObcaSolver:
         dev = self.device
         st = torch.empty(B, dtype=torch.int32, device=dev)
         it = torch.empty(B, dtype=torch.int32, device=dev)
-        dbl = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(4)]
+        dbl = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(5)]  # obj, cviol, dual_inf, compl_inf, elastic
         self._check(self.lib.obca_get_stats(self.handle, _ptr(st), _ptr(it), *[_ptr(t) for t in dbl], self._stream_ptr()))
         return st, it, dbl
 
@@ -360,8 +384,8 @@ class ObcaSolver:
         st, it, dbl = self.fetch_stats()
         sol = self.fetch_solution()
         h = self._to_host([st, it, dbl[0], dbl[1], dbl[2], dbl[3], sol["z"], sol["lam"] if want_duals else None, sol["mu"] if want_duals else None,
-                           sol["dt"], sol.get("pl"), sol.get("pm"), sol.get("ps")])
-        return BatchResult(status=h[0], iters=h[1], obj=h[2], cviol=h[3], dual_inf=h[4], compl_inf=h[5], z=h[6], lam=h[7], mu=h[8], dt=h[9],
+                           sol["dt"], sol.get("pl"), sol.get("pm"), sol.get("ps"), dbl[4]])
+        return BatchResult(status=h[0], iters=h[1], obj=h[2], cviol=h[3], dual_inf=h[4], compl_inf=h[5], elastic=h[13], z=h[6], lam=h[7], mu=h[8], dt=h[9],
                            pair_lam=h[10], pair_mu=h[11], pair_s=h[12])
 
     # -- introspection for the parity tests --------------------------------------------------------------
@@ -398,6 +422,14 @@ class ObcaSolver:
         c, gl, f = np.zeros(L["ny"]), np.zeros(L["nx"]), ctypes.c_double()
         self._check(self.lib.obca_debug_eval(self.handle, b, _np_ptr(c), _np_ptr(gl), ctypes.cast(ctypes.byref(f), _dp)))
         return c, gl, f.value
+
+    def debug_kkt_apply(self, b, delta_w, dx, dy):
+        """K [dx; dy] at the stored iterate (internal layout), applied matrix-free on the device (obca_refine.h)."""
+        L = self.layout()
+        r1, r2 = np.zeros(L["nx"]), np.zeros(L["ny"])
+        dx, dy = np.ascontiguousarray(dx, dtype=np.float64), np.ascontiguousarray(dy, dtype=np.float64)
+        self._check(self.lib.obca_debug_kkt_apply(self.handle, b, delta_w, _np_ptr(dx), _np_ptr(dy), _np_ptr(r1), _np_ptr(r2)))
+        return r1, r2
 
     def debug_step(self, b, mu, delta_w):
         L = self.layout()
@@ -455,7 +487,7 @@ class ObcaMpcSolver(ObcaSolver):
         dims = ObcaDims(batch=self.B, V=1, O=self.O, K=5, n_per_set=1, mode=1, horizon=prob.N, n_others=prob.n_others)
         copts = ObcaOptions()
         self.lib.obca_default_options(ctypes.byref(copts))
-        for name in ("tol", "constr_viol_tol", "dual_inf_tol", "compl_inf_tol", "mu_init", "max_iter", "elastic_weight"):
+        for name in ("tol", "constr_viol_tol", "dual_inf_tol", "compl_inf_tol", "mu_init", "max_iter", "elastic_weight", "refine_steps"):
             setattr(copts, name, getattr(self.opts, name))
         copts.dmin = prob.dmin
         self.handle = ctypes.c_void_p()

@@ -44,6 +44,8 @@ extern "C" {
 #define OBCA_RESTORATION_FAILED (-2)
 #define OBCA_ERROR_IN_STEP_COMPUTATION (-3)
 #define OBCA_INVALID_NUMBER_DETECTED (-4)
+#define OBCA_SEARCH_DIRECTION_TOO_SMALL (-5)   /* two consecutive tiny steps at the smallest mu without an acceptable point */
+#define OBCA_INFEASIBLE_PROBLEM_DETECTED (-6) /* converged with an active elastic variable: the reference problem (hard distance rows) is infeasible */
 #define OBCA_NOT_SOLVED (-100)
 
 typedef struct ObcaDims {
@@ -64,7 +66,8 @@ typedef struct ObcaOptions {
   double dmin, shrink_tube;
   double elastic_weight;         /* rho of the exact l1 penalty on the elastic variables of the distance rows */
   int32_t max_iter;
-  int32_t reserved;
+  int32_t refine_steps;          /* iterative-refinement solves per Newton system (IPOPT: max_refinement_steps); -1 = automatic:
+                                    0 when tol > 1e-5 (the reference's 1e-2), 2 at tight tolerances */
 } ObcaOptions;
 
 typedef struct ObcaStatic {       /* host pointers; copied by obca_set_static */
@@ -79,6 +82,8 @@ typedef struct ObcaStatic {       /* host pointers; copied by obca_set_static */
   const double* final_heading;   /* (V) NaN = unconstrained */
   double wb;
   double mpc_dt;                 /* MPC sample time (vehicle_follower.py:146, dt = 0.1); unused in collocation mode */
+  const double* colloc_A;        /* (K+1,K+1) A[j][k] = L_j'(tau_k) as Vehicle.collocation_coefficients computes it (vehicle.py:54-97), */
+  const double* colloc_B;        /* (K+1) quadrature weights; NULL = computed inside from the Radau points (same values to ~1e-14) */
 } ObcaStatic;
 
 typedef struct ObcaHandle ObcaHandle;
@@ -116,6 +121,11 @@ int obca_joint_dual_ws(ObcaHandle* h, const double* z, double* pair_lam, double*
  * SURVEY.md 8d asks for a measured figure next to the data-sheet 37 TFLOP/s) */
 int obca_measure_dfma_peak(int device, double* tflops);
 
+/* Processing order of the batch: order_dev (B int32, a permutation, dev pointer, copied) tells which instance the k-th free
+ * CTA picks up.  Instances are independent, so results do not depend on it; putting the instances that are expected to need
+ * the most iterations first shortens the tail of the persistent-CTA queue (longest-processing-time-first).  NULL = 0..B-1. */
+int obca_set_order(ObcaHandle* h, const int32_t* order_dev, void* stream);
+
 /* run the batched interior-point solve, asynchronously on `stream`; no host sync inside */
 int obca_solve(ObcaHandle* h, void* stream);
 
@@ -123,9 +133,10 @@ int obca_solve(ObcaHandle* h, void* stream);
 int obca_get_solution(ObcaHandle* h, double* z, double* lam, double* mu, double* dt, double* pair_lam,
                       double* pair_mu, double* pair_s, void* stream);
 
-/* dev pointers (B): any may be NULL */
+/* dev pointers (B): any may be NULL.  cviol is the violation of the REFERENCE problem: max(|c|, largest elastic variable);
+ * elastic is the largest elastic variable alone (0 at a solution of the reference problem). */
 int obca_get_stats(ObcaHandle* h, int32_t* status, int32_t* iters, double* obj, double* cviol, double* dual_inf,
-                   double* compl_inf, void* stream);
+                   double* compl_inf, double* elastic, void* stream);
 
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */
 int64_t obca_launch_count(const ObcaHandle* h);
@@ -142,6 +153,11 @@ int obca_debug_eval(ObcaHandle* h, int b, double* c, double* gl, double* f);
 /* Newton step at the stored iterate for barrier mu and regularisation delta_w: dx (nx), dy (ny) -> host;
  * returns 1 in *ok when the reduced Hessian was positive definite */
 int obca_debug_step(ObcaHandle* h, int b, double mu, double delta_w, double* dx, double* dy, int32_t* ok);
+
+/* K [dx; dy] at the stored iterate of instance b (collocation mode), K = [[W + Sigma + delta_w I, J'], [J, -delta_c]] applied
+ * matrix-free by obca_refine.h: dx (nx), dy (ny) in -> r1 (nx), r2 (ny) out, all HOST buffers in the internal layout.
+ * Sigma = zL / (x - xL) + zU / (xU - x) from the stored iterate. */
+int obca_debug_kkt_apply(ObcaHandle* h, int b, double delta_w, const double* dx, const double* dy, double* r1, double* r2);
 
 /* per-phase SM cycle counters summed over the resident CTAs (filled when the environment variable OBCA_PROFILE is set
  * at solve time; phase ids in obca_core.h) */

@@ -30,6 +30,8 @@ STATUS = {
     -2: "Restoration_Failed",
     -3: "Error_In_Step_Computation",
     -4: "Invalid_Number_Detected",
+    -5: "Search_Direction_Becomes_Too_Small",
+    -6: "Infeasible_Problem_Detected",
 }
 
 
@@ -278,7 +280,8 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
         tiny = np.max(np.abs(dx) / (1.0 + np.abs(x))) < 10 * np.finfo(float).eps
         if tiny:
             if tiny_last and mu <= mu_min:
-                status = 1
+                # IPOPT: Search_Direction_Becomes_Too_Small unless the iterate passes the acceptable test
+                status = 1 if (E(0.0) <= 1e-6 and cviol <= 1e-2 and compl(0.0) <= 1e-2) else -5
                 break
             tiny_last = True
             force_mu = True
@@ -290,7 +293,7 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
             xt = x + alpha * dx
             ct = nlp.c(xt)
             tht, pht = theta(ct), phi(xt, mu)
-            ok = np.isfinite(pht) and tht <= theta_max and all(not (tht >= ft and pht >= fp) for ft, fp in filt)
+            ok = np.isfinite(pht) and tht <= theta_max and all(not (tht - ft > slack_th and pht - fp > slack_phi) for ft, fp in filt)
             if ok:
                 switching = th <= theta_min and dphi < 0 and alpha * (-dphi) ** o.s_phi > o.delta_ls * th ** o.s_theta
                 if switching:
@@ -317,4 +320,10 @@ def solve(nlp, x0, opts: IpmOptions = None, kkt_factory=KktSolver) -> IpmResult:
     if status != 0 and best is not None:
         _, x, y, zL, zU = best  # IPOPT RestoreAcceptablePoint
         status = 1
+    # an active elastic variable at a converged point: the penalised problem is solved, the reference problem (hard distance
+    # rows) is infeasible there -- IPOPT reports Infeasible_Problem_Detected and Opti raises
+    el = x[nlp._elastic_index()] if hasattr(nlp, "_elastic_index") else np.zeros(0)
+    el_max = float(el.max(initial=0.0))
+    if status >= 0 and el_max > max(o.constr_viol_tol, 1e-8):
+        status = -6
     return IpmResult(x, y, zL, zU, status, it, float(nlp.f(x)), float(np.abs(nlp.c(x)).max()), float(dual_inf), float(compl(0.0)), mu, hist)

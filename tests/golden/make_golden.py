@@ -34,6 +34,9 @@ def save(name, prob, guess, nlp, res):
     if guess.pair_lam is not None:
         out.update(g_pl=guess.pair_lam, g_pm=guess.pair_mu, g_ps=guess.pair_s)
     out.update(s_z=u["z"], s_dt=u["dt"], s_obj=res.obj, s_iters=res.iters, s_status=res.status, s_cviol=res.cviol, s_dual_inf=res.dual_inf)
+    # full primal-dual point in the oracle's own ordering (oracle/nlp.py): input of the KKT certificate of the unmodified
+    # reference NLP (oracle/reference_nlp.py)
+    out.update(s_lam=u["lam"], s_mu=u["mu"], s_pl=u["pair_lam"], s_pm=u["pair_mu"], s_ps=u["pair_s"], s_y=res.y, s_zL=res.zL, s_zU=res.zU)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, res.return_status, res.iters, res.obj, res.cviol)
 
@@ -72,6 +75,31 @@ def main():
     guess = CollocationGuess(z, lam, mu, np.float64(np.mean(dts)), pl, pm, ps)
     nlp = CollocationNLP(prob)
     save("joint_vehicle_1_2", prob, guess, nlp, ipm.solve(nlp, nlp.init_slacks(nlp.pack(guess)), tight))
+    four_vehicle_headline(fn, tight)
+
+
+def four_vehicle_headline(fn, tight):
+    """BASELINE.json configs[1] / the instance shape of configs[3]: 4-vehicle centralised conflict resolution with the
+    initial offsets of multi_vehicle_planner.py:641-642 (vehicle_0: x + 0.1, psi + pi/20), n = 75 601.  The warm start is
+    the one the bench pipeline produces (state_ws -> dual_ws -> single OBCA solves -> pair duals,
+    control/batch_planner.py) -- run here under the developer host emulation of the kernels, since no GPU is available
+    where fixtures are generated; the SOLUTION stored is the oracle's (sparse LU interior point, tol 1e-8) from that start."""
+    from conflict_rez_b200 import solver as S
+    from conflict_rez_b200.control.batch_planner import prepare_joint_batch
+    from conflict_rez_b200.solver import SolveOptions
+
+    emu = S.load_library(os.path.join(ROOT, "tools", "host_emu", "libobca_hostemu.so"))
+    agents = ["vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"]
+    heads = {"vehicle_0": 0.0, "vehicle_1": 3 * np.pi / 2, "vehicle_2": np.pi, "vehicle_3": np.pi / 2}   # multi_vehicle_planner.py:644-649
+    offs = np.zeros((1, 4, 3))
+    offs[0, 0] = [0.1, 0.0, np.pi / 20]
+    plan = prepare_joint_batch(fn, agents, offs, SolveOptions(max_iter=600), device="cpu", lib=emu, final_headings=heads)
+    plan.solver.close()
+    print("warm start: single-vehicle status", [int(r.status[0]) for r in plan.singles], "iters", [int(r.iters[0]) for r in plan.singles])
+    prob, guess = plan.problem.instance(0), plan.guess.instance(0)
+    nlp = CollocationNLP(prob)
+    res = ipm.solve(nlp, nlp.init_slacks(nlp.pack(guess)), tight)
+    save("joint_vehicle_0_1_2_3", prob, guess, nlp, res)
 
 
 if __name__ == "__main__":

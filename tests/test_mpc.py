@@ -164,3 +164,19 @@ def test_distributed_mpc_closed_loop(backend, strategy_file):
     assert quad_distance(ca, cb).min() >= 0.05 - 1e-2
     if dev != "cpu":
         assert mdf.solver.launch_count > 0  # the CUDA kernels ran (the emulation does not count launches)
+
+
+def test_infeasible_neighbour_is_reported_not_adopted(backend, mpc_case):
+    """A neighbour predicted on top of the ego vehicle makes the reference problem infeasible (the distance row cannot reach
+    dmin).  IPOPT reports Infeasible_Problem_Detected, Opti raises and VehicleFollower.step keeps the shifted backup plan
+    (vehicle_follower.py:478-524).  The elastic formulation must not hide this: the status is negative, the elastic magnitude is
+    visible in cviol / elastic, and the planner does not adopt the penetrating plan."""
+    p, par, g = mpc_case
+    sv = _solver(backend, p, max_iter=600)
+    others = par["ref"][None].copy()  # the neighbour sits exactly where the ego reference is
+    res = sv.solve_step(par["cur"][None], par["ref"][None], others[None], _guess(g))
+    assert res.status[0] < 0, res.return_status(0)
+    assert res.return_status(0) in ("Infeasible_Problem_Detected", "Maximum_Iterations_Exceeded", "Restoration_Failed")
+    if res.status[0] == -6:
+        assert res.elastic[0] > 1e-2 and res.cviol[0] >= res.elastic[0]
+    sv.close()
