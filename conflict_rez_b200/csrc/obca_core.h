@@ -247,7 +247,7 @@ struct Scratch {
   double* DF;   // [2][V][Nmax] dirty flags (double-buffered by pass)
   double* MA;   // [V][Nmax][91 + 13]      projected stage Hessian (sym packed 13x13) + gradient
   double* MAB;  // [P][Nmax][169 + 26]     projected cross-vehicle coupling + gradients
-  double* RK;   // [Nmax][nU*nX + nU]      Riccati gains
+  double* RK;   // [Nmax][(nX+1)*nU + nU*nU]   stage records of the Riccati forward pass: Ks' and L
   double* RP;   // [Nmax+1][nX*nX + nX]    cost-to-go
   double* RX;   // [Nmax+1][nX] states, [Nmax][nU] controls
   double* SS;   // [V][Nmax][42] stage solutions
@@ -277,7 +277,7 @@ inline size_t work_doubles(const Lay& L) {
   n += (size_t)L.V * L.Mv * (hn_per_node(L) + 7 + 7);
   n += (size_t)L.V * L.Nmax * ((NW * NRED + NW) + QRSZ + (NSYM + NRED) + NS + 2 * EXSZ + 2) + EXSZ;
   n += (size_t)L.P * L.Nmax * (NRED * NRED + 2 * NRED);
-  n += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
+  n += (size_t)L.Nmax * ((size_t)(L.nX + 1) * L.nU + (size_t)L.nU * L.nU);  // stage records of the Riccati forward pass
   n += (size_t)(L.Nmax + 1) * (L.nX * L.nX + L.nX);
   n += (size_t)(L.Nmax + 1) * L.nX + (size_t)L.Nmax * L.nU;
   return ev(n + 64);
@@ -322,7 +322,7 @@ OBCA_HD void carve_work(Scratch& W, const Lay& L, double* p) {
   W.DF = p, p += (size_t)2 * L.V * L.Nmax;
   W.MA = p, p += (size_t)L.V * L.Nmax * (NSYM + NRED);
   W.MAB = p, p += (size_t)L.P * L.Nmax * (NRED * NRED + 2 * NRED);
-  W.RK = p, p += (size_t)L.Nmax * (L.nU * L.nX + L.nU);
+  W.RK = p, p += (size_t)L.Nmax * ((size_t)(L.nX + 1) * L.nU + (size_t)L.nU * L.nU);
   W.RP = p, p += (size_t)(L.Nmax + 1) * (L.nX * L.nX + L.nX);
   W.RX = p, p += (size_t)(L.Nmax + 1) * L.nX + (size_t)L.Nmax * L.nU;
   W.SS = p;

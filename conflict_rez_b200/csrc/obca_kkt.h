@@ -1102,8 +1102,23 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, dou
 //   xi_a' = Aa xi_a + da dt + Ba u_a + ca   (rows 28..34 of the block's T map),   dt' = dt.
 // All stage matrices live in the work arena RW (shared memory on the device).
 // ------------------------------------------------------------------------------------------------
+// pivot row / column exchange buffers of the stage factorisation (cta_stage_ldl)
+struct LdlBuf {
+  double col[2][32], row[2][64], inv[2], invd[32];
+  int bad;
+};
+#if defined(__CUDA_ARCH__)
+#define OBCA_EMU_LDL 0
+#else
+#define OBCA_EMU_LDL 1  // the host emulation factorises in the same L D L' form (stage_ldl_scalar)
+#endif
+
+// doubles of one stage record of the forward pass: Ks' [nX + 1][nU] and L [nU][nU]
+OBCA_HD size_t ric_record_doubles(const Lay& L) { return (size_t)(L.nX + 1) * L.nU + (size_t)L.nU * L.nU; }
+
 struct RicWork {
   double *P, *p, *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *K, *Ab, *Bb, *db, *cb, *invd, *MAs, *MABs, *TBs;
+  LdlBuf* ldl;  // pivot row / column exchange buffers of the factorisation
   int *uoff, *npv, *npt;  // [MAXV + 1], [MAXV + 1], [V][Nmax]
   const double** isrc;     // [n_in] address of every stage input at stage 0
   int* istr;               // [n_in][2] (doubles per stage, first stage beyond the block's horizon)
@@ -1111,7 +1126,7 @@ struct RicWork {
 
 inline size_t riccati_only_doubles(const Lay& L) {
   size_t nX = L.nX, nU = L.nU;
-  return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU + ((size_t)L.V * L.Nmax + 2) / 2 +
+  return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU + (sizeof(LdlBuf) + 7) / 8 + ((size_t)L.V * L.Nmax + 2) / 2 +
          (OBCA_RIC_PREFETCH ? 3 * ((size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) + (size_t)L.V * 7 * (NRED + 1)) + 4 : 0);
 }
 
@@ -1143,6 +1158,7 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
   R.db = w, w += L.V * 7;
   R.cb = w, w += L.V * 7;
   R.invd = w, w += nU;
+  R.ldl = (LdlBuf*)w, w += (sizeof(LdlBuf) + 7) / 8;
   R.MAs = w;
   R.MABs = w + L.V * (NSYM + NRED);
   R.TBs = R.MABs + L.P * (NRED * NRED + 2 * NRED);
@@ -1336,103 +1352,172 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
   cta_sync(ctx);
 }
 
-OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, double* RW, double hdtdt, int* ok) {
-  assume_scratch(W);
-  const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V;
-  RicWork R;
-  ric_carve(R, L, RW);
-  const size_t pstride = (size_t)nX * nX + nX, kstride = (size_t)nUmax * nX + nUmax;
-  for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.P[q] = 0;
-  for (int q = ctx.tid; q < nX; q += ctx.nt) R.p[q] = 0;
-  {
-    double* Pn = W.RP + (size_t)L.Nmax * pstride;
-    for (int q = ctx.tid; q < (int)pstride; q += ctx.nt) Pn[q] = 0;
+// ------------------------------------------------------------------------------------------------
+// Factorisation of the stage matrix.  F = R + B'PB (nu x nu, nu <= 32) and the right-hand sides Gm = [S + B'PA | r + B'pc]
+// (nu x nc) are eliminated together:  F = L D L' (unit L),  Khat = L^-1 Gm.  The cost-to-go update only needs Khat and D
+// (Gm' F^-1 Gm = Khat' D^-1 Khat), the controls follow in the forward pass from  L' u = -D^-1 Khat [x; 1].
+//
+// Device (256 threads = 4 row groups x 64 columns): every thread owns one column of the augmented matrix [F | Gm] and the
+// rows rg, rg + 4, ... of it, in registers.  The entries are computed in place (the products B'PB, B'PA, B'pc are 7-term
+// dot products), then the right-looking elimination runs with ONE CTA barrier per pivot: the owners of the next pivot row
+// and column publish them through double-buffered shared memory, the owner of the pivot publishes its reciprocal
+// (hardware seed + two Newton steps).  Round 1 eliminated in shared memory with two barriers per pivot plus a barrier per
+// row of the back-substitution: 1.33 M of 8.1 M cycles per iteration; the micro-benchmark of this kernel
+// (tools/microbench/ldl_bench.cu) runs a 20 x 50 stage in 7.9 k cycles.
+// Outputs (shared memory): F <- unit L below the diagonal (row major, ld nu), Gm <- Khat, Ks <- -D^-1 Khat, invd <- 1 / d.
+// A pivot below PIVOT_TOL (relative to R_jj) means the reduced Hessian is not positive definite: *ok = 0.
+// ------------------------------------------------------------------------------------------------
+OBCA_HD bool ldl_fast_shape(const Ctx& ctx, int nu, int nc) {
+#if defined(__CUDA_ARCH__)
+  return ctx.nt == 256 && nu >= 1 && nu <= 32 && nu + nc <= 64;
+#else
+  (void)ctx, (void)nu, (void)nc;
+  return false;
+#endif
+}
+
+#if defined(__CUDA_ARCH__)
+// 1 / d for a positive, normal d: hardware seed (MUFU.RCP64H) + two Newton steps
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  x = fma(x, fma(-d, x, 1.0), x);
+  x = fma(x, fma(-d, x, 1.0), x);
+  return x;
+}
+
+template <int KMAX>
+__device__ __forceinline__ void cta_stage_ldl(const RicWork& R, int nu, int nX, int* ok, LdlBuf* B) {
+  const int t = threadIdx.x, rg = t >> 6, c = t & 63, nc = nX + 1, ncols = nu + nc;
+  double m[KMAX];
+  // entries of [F | Gm] owned by this thread: F = R + B'PB ; Gm = [S + B'PA | r + B'pc]
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int r = rg + 4 * k;
+    double v = 0.0;
+    if (r < nu && c < ncols) {
+      int a = 0;
+      while (r >= R.uoff[a + 1]) ++a;
+      const double* Bj = R.Bb + (a * 7) * NP + (r - R.uoff[a]);
+      const double* rhs;
+      int rs;
+      if (c < nu) rhs = R.PB + (7 * a) * nu + c, rs = nu, v = R.R[r * nu + c];
+      else if (c < nu + nX) rhs = R.PA + (7 * a) * nX + (c - nu), rs = nX, v = R.S[r * nX + (c - nu)];
+      else rhs = R.pc + 7 * a, rs = 1, v = R.r[r];
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; q += 2) s0 += Bj[q * NP] * rhs[q * rs], s1 += Bj[(q + 1) * NP] * rhs[(q + 1) * rs];
+      v += (s0 + Bj[6 * NP] * rhs[6 * rs]) + s1;
+    }
+    m[k] = v;
   }
-  for (int it = ctx.tid; it < V * L.Nmax; it += ctx.nt) R.npt[it] = block_np(L, W, it / L.Nmax, it % L.Nmax);
-#if OBCA_RIC_PREFETCH
-  ric_input_table(ctx, L, W, R);
-  cta_sync(ctx);
-  ric_input_fetch(ctx, L, W, R, L.Nmax - 1);
-#endif
-  cta_sync(ctx);
-  for (int i = L.Nmax - 1; i >= 0; --i) {
-    if (ctx.tid == 0) {
-      int off = 0;
-      for (int a = 0; a < V; ++a) {
-        R.uoff[a] = off;
-        R.npv[a] = R.npt[a * L.Nmax + i];
-        off += R.npv[a];
+  // every column has one diagonal owner, thread (rg = c & 3, c): its pivot tolerance is known before the loop
+  const double mytol = (c < nu && rg == (c & 3)) ? PIVOT_TOL * fmax(1.0, fabs(R.R[c * nu + c])) : 0.0;
+  if (t == 0) B->bad = 0;
+  __syncthreads();
+  if (c == 0) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) B->col[0][rg + 4 * k] = m[k];
+  }
+  if (rg == 0) B->row[0][c] = m[0];
+  if (t == 0) {
+    double d = m[0];
+    if (!(d > mytol)) B->bad = 1, d = 1.0;
+    const double inv = fast_rcp(d);
+    B->inv[0] = inv, B->invd[0] = inv;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4 * KMAX; ++j) {
+    if (j < nu) {  // CTA-uniform
+      const int p = j & 1;
+      const double uc = c > j ? B->row[p][c] * B->inv[p] : 0.0;  // finished columns (c <= j) keep their entries: L (times d)
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (4 * k + 3 > j) {  // static: some row of this slot lies below the pivot
+          const int r = rg + 4 * k;
+          const double l = r > j ? B->col[p][r] : 0.0;
+          m[k] = fma(-l, uc, m[k]);
+        }
       }
-      R.uoff[V] = off;
+      if (j + 1 < nu) {
+        const int jn = j + 1, kn = jn >> 2, gn = jn & 3;
+        if (c == jn) {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (4 * k + 3 > jn) B->col[p ^ 1][rg + 4 * k] = m[k];
+        }
+        if (rg == gn) {
+          B->row[p ^ 1][c] = m[kn < KMAX ? kn : 0];
+          if (c == jn) {
+            double d = m[kn < KMAX ? kn : 0];
+            if (!(d > mytol)) B->bad = 1, d = 1.0;
+            const double inv = fast_rcp(d);
+            B->inv[p ^ 1] = inv, B->invd[jn] = inv;
+          }
+        }
+      }
+      __syncthreads();
     }
-#if OBCA_RIC_PREFETCH
-    ric_input_wait();  // this stage's inputs (issued during the previous stage) have landed; the barrier publishes them
-#endif
-    cta_sync(ctx);
-    const int nu = R.uoff[V];
-    prof_mark(ctx, 6);
-    riccati_stage_assemble(ctx, L, W, R, i, hdtdt, nu);
-    prof_mark(ctx, 12);
-    // PA = P A ; PB = P B ; pc = P c + p   (block structure of A, B).  The 7-term items and the two dense columns (dt and the
-    // constant) are separate loops so that the lanes of a warp do the same amount of work; the dense ones go to the last threads.
-    for (int it = ctx.tid; it < nX * (idt + nu); it += ctx.nt) {
-      const int r = it / (idt + nu), col = it % (idt + nu);
-      const double* Pr = R.P + r * nX;
-      double s = 0;
-      if (col < idt) {
-        const int a = col / 7, c = col % 7;
-        for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Ab[a * 49 + m * 7 + c];
-        R.PA[r * nX + col] = s;
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int r = rg + 4 * k;
+    if (r < nu && c < ncols) {
+      if (c < nu) {
+        if (r > c) R.F[r * nu + c] = m[k] * B->invd[c];
       } else {
-        int u = col - idt, a = 0;
-        while (u >= R.uoff[a + 1]) ++a;
-        const int j = u - R.uoff[a];
-        for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Bb[(a * 7 + m) * NP + j];
-        R.PB[r * nu + u] = s;
+        R.Gm[r * nc + (c - nu)] = m[k];
+        R.K[r * nc + (c - nu)] = -m[k] * B->invd[r];
       }
     }
-    for (int it = ctx.nt - 1 - ctx.tid; it < 2 * nX; it += ctx.nt) {
-      const int r = it >> 1;
-      const double* Pr = R.P + r * nX;
-      const double* vec = (it & 1) ? R.cb : R.db;
-      double s0 = (it & 1) ? R.p[r] : Pr[idt], s1 = 0;
-      int m = 0;
-      for (; m + 1 < idt; m += 2) s0 += Pr[m] * vec[m], s1 += Pr[m + 1] * vec[m + 1];
-      if (m < idt) s0 += Pr[m] * vec[m];
-      if (it & 1) R.pc[r] = s0 + s1;
-      else R.PA[r * nX + idt] = s0 + s1;
+  }
+  if (t < nu) R.invd[t] = B->invd[t];
+  if (t == 0 && B->bad) *ok = 0;
+}
+#endif
+
+// fused products + factorisation of one stage (device fast path); all threads of the CTA call it
+OBCA_HD void stage_ldl_fused(const Ctx& ctx, const RicWork& R, int nu, int nX, int* ok, LdlBuf* B) {
+#if defined(__CUDA_ARCH__)
+  (void)ctx;
+  if (nu <= 8) cta_stage_ldl<2>(R, nu, nX, ok, B);
+  else if (nu <= 16) cta_stage_ldl<4>(R, nu, nX, ok, B);
+  else if (nu <= 24) cta_stage_ldl<6>(R, nu, nX, ok, B);
+  else cta_stage_ldl<8>(R, nu, nX, ok, B);
+#else
+  (void)ctx, (void)R, (void)nu, (void)nX, (void)ok, (void)B;
+#endif
+}
+
+// host emulation / reference form of the same factorisation on the assembled F, Gm (one thread)
+OBCA_HD void stage_ldl_scalar(double* F, int nu, double* Gm, int nc, double* Ks, double* invd, const double* Rm, int* ok) {
+  for (int j = 0; j < nu; ++j) {
+    double d = F[j * nu + j];
+    if (!(d > PIVOT_TOL * fmax(1.0, fabs(Rm[j * nu + j])))) *ok = 0, d = 1.0;
+    const double inv = 1.0 / d;
+    invd[j] = inv;
+    for (int r = j + 1; r < nu; ++r) {
+      const double lr = F[r * nu + j];
+      for (int c = j + 1; c < nu; ++c) F[r * nu + c] -= lr * (F[j * nu + c] * inv);
+      for (int c = 0; c < nc; ++c) Gm[r * nc + c] -= lr * (Gm[j * nc + c] * inv);
     }
-    cta_sync(ctx);
-    // F = R + B'PB ; Gm = [S + B'PA | r + B'pc]
-    for (int it = ctx.tid; it < nu * (nu + nX + 1); it += ctx.nt) {
-      int u = it / (nu + nX + 1), col = it % (nu + nX + 1), a = 0;
-      while (u >= R.uoff[a + 1]) ++a;
-      int j = u - R.uoff[a];
-      const double* Bj = R.Bb + (a * 7) * NP + j;
-      double s = 0;
-      if (col < nu) {
-        for (int m = 0; m < 7; ++m) s += Bj[m * NP] * R.PB[(7 * a + m) * nu + col];
-        R.F[u * nu + col] = R.R[u * nu + col] + s;
-      } else if (col < nu + nX) {
-        int c = col - nu;
-        for (int m = 0; m < 7; ++m) s += Bj[m * NP] * R.PA[(7 * a + m) * nX + c];
-        R.Gm[u * (nX + 1) + c] = R.S[u * nX + c] + s;
-      } else {
-        for (int m = 0; m < 7; ++m) s += Bj[m * NP] * R.pc[7 * a + m];
-        R.Gm[u * (nX + 1) + nX] = R.r[u] + s;
-      }
-    }
-    cta_sync(ctx);
-    prof_mark(ctx, 13);
+    for (int r = j + 1; r < nu; ++r) F[r * nu + j] *= inv;
+  }
+  for (int r = 0; r < nu; ++r)
+    for (int c = 0; c < nc; ++c) Ks[r * nc + c] = -Gm[r * nc + c] * invd[r];
+}
+
+// Stage shapes the register kernel does not cover (more than 32 free directions, V > 4): right-looking Cholesky of the
+// augmented matrix [F | Gm] in shared memory by the whole CTA (two barriers per pivot), then a column-oriented backward
+// substitution (one barrier per row); leaves the gains K = -F^-1 Gm in R.K and Gm untouched.
+OBCA_HDN void riccati_factor_generic(const Ctx& ctx, const RicWork& R, int nu, int nc, int i, int* ok) {
+  (void)i;
     // Cholesky F = L L' fused with the forward substitution of [K | k] = -F^-1 Gm: right-looking elimination of the
     // augmented matrix [F | Gm] by the whole CTA (two barriers per pivot); a non-positive pivot means the reduced
     // Hessian is not positive definite.  Then a column-oriented backward substitution (one barrier per row).
-    const int nc = nX + 1;
     for (int it = ctx.tid; it < nu * nc; it += ctx.nt) R.K[it] = R.Gm[it];
     cta_sync(ctx);
-#if OBCA_RIC_PREFETCH
-    if (i > 0) ric_input_fetch(ctx, L, W, R, i - 1);  // the assembly of this stage is done with the buffers: next stage's inputs
-#endif
     // thread -> (row group rg, column c): c < 64 covers the n1 trailing columns of F and the nc columns of K without any
     // integer division in the loops; every thread keeps its column
     const int c64 = ctx.tid & 63, rg = ctx.tid >> 6, nrg = ctx.nt >> 6 > 0 ? ctx.nt >> 6 : 1;
@@ -1495,13 +1580,126 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     for (int it = ctx.tid; it < nu * nc; it += ctx.nt) R.K[it] = -R.K[it] * R.invd[it / nc];
     cta_sync(ctx);
     prof_mark(ctx, 15);
-    // gains to global memory (forward pass) in the padded layout [nUmax][nX] + [nUmax]
+}
+
+OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, double* RW, double hdtdt, int* ok) {
+  assume_scratch(W);
+  const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V;
+  RicWork R;
+  ric_carve(R, L, RW);
+  const size_t pstride = (size_t)nX * nX + nX, kstride = ric_record_doubles(L);
+  for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.P[q] = 0;
+  for (int q = ctx.tid; q < nX; q += ctx.nt) R.p[q] = 0;
+  {
+    double* Pn = W.RP + (size_t)L.Nmax * pstride;
+    for (int q = ctx.tid; q < (int)pstride; q += ctx.nt) Pn[q] = 0;
+  }
+  for (int it = ctx.tid; it < V * L.Nmax; it += ctx.nt) R.npt[it] = block_np(L, W, it / L.Nmax, it % L.Nmax);
+#if OBCA_RIC_PREFETCH
+  ric_input_table(ctx, L, W, R);
+  cta_sync(ctx);
+  ric_input_fetch(ctx, L, W, R, L.Nmax - 1);
+#endif
+  cta_sync(ctx);
+  for (int i = L.Nmax - 1; i >= 0; --i) {
+    if (ctx.tid == 0) {
+      int off = 0;
+      for (int a = 0; a < V; ++a) {
+        R.uoff[a] = off;
+        R.npv[a] = R.npt[a * L.Nmax + i];
+        off += R.npv[a];
+      }
+      R.uoff[V] = off;
+    }
+#if OBCA_RIC_PREFETCH
+    ric_input_wait();  // this stage's inputs (issued during the previous stage) have landed; the barrier publishes them
+#endif
+    cta_sync(ctx);
+    const int nu = R.uoff[V];
+    prof_mark(ctx, 6);
+    riccati_stage_assemble(ctx, L, W, R, i, hdtdt, nu);
+    prof_mark(ctx, 12);
+    // PA = P A ; PB = P B ; pc = P c + p   (block structure of A, B).  The 7-term items and the two dense columns (dt and the
+    // constant) are separate loops so that the lanes of a warp do the same amount of work; the dense ones go to the last threads.
+    for (int it = ctx.tid; it < nX * (idt + nu); it += ctx.nt) {
+      const int r = it / (idt + nu), col = it % (idt + nu);
+      const double* Pr = R.P + r * nX;
+      double s = 0;
+      if (col < idt) {
+        const int a = col / 7, c = col % 7;
+        for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Ab[a * 49 + m * 7 + c];
+        R.PA[r * nX + col] = s;
+      } else {
+        int u = col - idt, a = 0;
+        while (u >= R.uoff[a + 1]) ++a;
+        const int j = u - R.uoff[a];
+        for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Bb[(a * 7 + m) * NP + j];
+        R.PB[r * nu + u] = s;
+      }
+    }
+    for (int it = ctx.nt - 1 - ctx.tid; it < 2 * nX; it += ctx.nt) {
+      const int r = it >> 1;
+      const double* Pr = R.P + r * nX;
+      const double* vec = (it & 1) ? R.cb : R.db;
+      double s0 = (it & 1) ? R.p[r] : Pr[idt], s1 = 0;
+      int m = 0;
+      for (; m + 1 < idt; m += 2) s0 += Pr[m] * vec[m], s1 += Pr[m + 1] * vec[m + 1];
+      if (m < idt) s0 += Pr[m] * vec[m];
+      if (it & 1) R.pc[r] = s0 + s1;
+      else R.PA[r * nX + idt] = s0 + s1;
+    }
+    cta_sync(ctx);
+    const int nc = nX + 1;
+    const bool fast = ldl_fast_shape(ctx, nu, nc);
+#if OBCA_RIC_PREFETCH
+    if (i > 0) ric_input_fetch(ctx, L, W, R, i - 1);  // the assembly of this stage is done with the buffers: next stage's inputs
+#endif
+    if (fast) {
+      // products and L D L' factorisation in registers, one barrier per pivot; F <- L, Gm <- Khat, K <- -D^-1 Khat
+      stage_ldl_fused(ctx, R, nu, nX, ok, R.ldl);
+      cta_sync(ctx);
+      prof_mark(ctx, 14);
+    } else {
+      // F = R + B'PB ; Gm = [S + B'PA | r + B'pc]
+      for (int it = ctx.tid; it < nu * (nu + nX + 1); it += ctx.nt) {
+        int u = it / (nu + nX + 1), col = it % (nu + nX + 1), a = 0;
+        while (u >= R.uoff[a + 1]) ++a;
+        int j = u - R.uoff[a];
+        const double* Bj = R.Bb + (a * 7) * NP + j;
+        double s = 0;
+        if (col < nu) {
+          for (int m = 0; m < 7; ++m) s += Bj[m * NP] * R.PB[(7 * a + m) * nu + col];
+          R.F[u * nu + col] = R.R[u * nu + col] + s;
+        } else if (col < nu + nX) {
+          int c = col - nu;
+          for (int m = 0; m < 7; ++m) s += Bj[m * NP] * R.PA[(7 * a + m) * nX + c];
+          R.Gm[u * (nX + 1) + c] = R.S[u * nX + c] + s;
+        } else {
+          for (int m = 0; m < 7; ++m) s += Bj[m * NP] * R.pc[7 * a + m];
+          R.Gm[u * (nX + 1) + nX] = R.r[u] + s;
+        }
+      }
+      cta_sync(ctx);
+      prof_mark(ctx, 13);
+#if defined(__CUDA_ARCH__)
+      riccati_factor_generic(ctx, R, nu, nc, i, ok);
+#else
+      stage_ldl_scalar(R.F, nu, R.Gm, nc, R.K, R.invd, R.R, ok);  // the emulation runs the L D L' form (one thread)
+#endif
+    }
+    const bool ldl_form = fast || OBCA_EMU_LDL;
+    // stage record for the forward pass: Ks transposed [nc][nUmax] (lanes read consecutive controls) and the unit L row major
+    // [nUmax][nUmax]; the forward pass computes u = L^-T (Ks [x; 1]).  The generic path stores the gains as Ks and L = I.
     {
       double* Kg = W.RK + (size_t)i * kstride;
-      for (int it = ctx.tid; it < nu * (nX + 1); it += ctx.nt) {
-        int u = it / (nX + 1), col = it % (nX + 1);
-        if (col < nX) Kg[u * nX + col] = R.K[it];
-        else Kg[nUmax * nX + u] = R.K[it];
+      for (int it = ctx.tid; it < nu * nc; it += ctx.nt) {
+        const int u = it / nc, col = it % nc;
+        Kg[col * nUmax + u] = R.K[it];
+      }
+      double* Lg = Kg + (size_t)nc * nUmax;
+      for (int it = ctx.tid; it < nu * nu; it += ctx.nt) {
+        const int r = it / nu, m = it % nu;
+        if (m < r) Lg[r * nUmax + m] = ldl_form ? R.F[it] : 0.0;
       }
     }
     // P <- Q + A'PA + Gm'K ; p <- q + A'pc + Gm'k   (written into Q/q first, then copied: P is still needed).
@@ -1558,10 +1756,18 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
   }
 }
 
-OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, int* ok) {
+// Forward pass.  Per stage: the record (Ks', L) and the dynamics rows of the T maps are staged in shared memory by the whole
+// CTA (coalesced), warp 0 computes the controls  u = L^-T (Ks [x; 1])  -- one lane per control, the back-substitution runs on
+// shuffles --, then the next state follows from the block dynamics.  fb: shared-memory scratch (>= record + V * 7 * (NRED + 1)).
+OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, double* RW, int* ok) {
   assume_scratch(W);
-  const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V;
-  const size_t pstride = (size_t)nX * nX + nX, kstride = (size_t)nUmax * nX + nUmax;
+  const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V, nc = nX + 1;
+  const size_t pstride = (size_t)nX * nX + nX, kstride = ric_record_doubles(L);
+  RicWork R;
+  ric_carve(R, L, RW);  // R.npt (free directions of every block) is still valid; the stage matrices P .. K are dead and serve as scratch
+  double* fb = R.P;
+  double* fT = fb + kstride;                 // [V][7][NRED + 1]
+  double* fU = fT + (size_t)V * 7 * (NRED + 1);  // [nUmax] compact controls of the stage
   double* X = W.RX;
   double* U = W.RX + (size_t)(L.Nmax + 1) * nX;
   if (ctx.tid == 0) {
@@ -1581,36 +1787,84 @@ OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, in
   cta_sync(ctx);
   for (int i = 0; i < L.Nmax; ++i) {
     const double* Kg = W.RK + (size_t)i * kstride;
-    const double* kg = Kg + nUmax * nX;
     const double* Xi = X + (size_t)i * nX;
     double* Ui = U + (size_t)i * nUmax;  // padded per-vehicle layout: NP slots per vehicle
     double* Xn = X + (size_t)(i + 1) * nX;
-    // controls: compacted index u -> (vehicle, slot)
-    for (int t = ctx.tid; t < V * NP; t += ctx.nt) {
-      int a = t / NP, j = t % NP;
-      int off = 0;
-      for (int aa = 0; aa < a; ++aa) off += block_np(L, W, aa, i);
-      double s = 0;
-      if (j < block_np(L, W, a, i)) {
-        int u = off + j;
-        s = kg[u];
-        for (int m = 0; m < nX; ++m) s += Kg[u * nX + m] * Xi[m];
+    int nu = 0;
+    for (int a = 0; a < V; ++a) nu += R.npt[a * L.Nmax + i];
+    // stage record and dynamics rows -> shared memory
+    for (int it = ctx.tid; it < nc * nUmax; it += ctx.nt)
+      if (it % nUmax < nu) fb[it] = Kg[it];
+    for (int it = ctx.tid; it < nu * nUmax; it += ctx.nt)
+      if (it % nUmax < it / nUmax) fb[nc * nUmax + it] = Kg[nc * nUmax + it];
+    for (int it = ctx.tid; it < V * 7 * (NRED + 1); it += ctx.nt) {
+      const int a = it / (7 * (NRED + 1)), r = (it / (NRED + 1)) % 7, cc = it % (NRED + 1);
+      double v = 0.0;
+      if (i < L.N[a]) {
+        const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
+        v = cc < NRED ? T[(28 + r) * NRED + cc] : T[NW * NRED + 28 + r];
       }
-      Ui[t] = s;
+      fT[it] = v;
     }
     cta_sync(ctx);
+    const double* Lf = fb + (size_t)nc * nUmax;
+#if defined(__CUDA_ARCH__)
+    if (nu <= 32) {
+      if ((ctx.tid >> 5) == 0) {
+        const int lane = ctx.tid & 31;
+        double t = 0.0;
+        if (lane < nu) {
+          double t1 = 0.0;
+          t = fb[nX * nUmax + lane];
+          int c = 0;
+          for (; c + 1 < nX; c += 2) t += fb[c * nUmax + lane] * Xi[c], t1 += fb[(c + 1) * nUmax + lane] * Xi[c + 1];
+          if (c < nX) t += fb[c * nUmax + lane] * Xi[c];
+          t += t1;
+        }
+        for (int r = nu - 1; r > 0; --r) {   // L' u = t: u_r is final once the rows above it have been applied
+          const double ur = __shfl_sync(0xffffffffu, t, r);
+          if (lane < r) t -= Lf[r * nUmax + lane] * ur;
+        }
+        if (lane < nu) fU[lane] = t;
+      }
+    } else
+#endif
+    {
+      // generic: t = Ks [x; 1] by all threads, then the back-substitution column by column
+      for (int u = ctx.tid; u < nu; u += ctx.nt) {
+        double t = fb[nX * nUmax + u];
+        for (int c = 0; c < nX; ++c) t += fb[c * nUmax + u] * Xi[c];
+        fU[u] = t;
+      }
+      cta_sync(ctx);
+      for (int r = nu - 1; r > 0; --r) {
+        const double ur = fU[r];
+        for (int m = ctx.tid; m < r; m += ctx.nt) fU[m] -= Lf[r * nUmax + m] * ur;
+        cta_sync(ctx);
+      }
+    }
+    cta_sync(ctx);
+    // compact index u -> (vehicle, slot), zero for the unused slots
+    for (int t = ctx.tid; t < V * NP; t += ctx.nt) {
+      const int a = t / NP, j = t % NP;
+      int off = 0;
+      for (int aa = 0; aa < a; ++aa) off += R.npt[aa * L.Nmax + i];
+      Ui[t] = j < R.npt[a * L.Nmax + i] ? fU[off + j] : 0.0;
+    }
     for (int r = ctx.tid; r < nX; r += ctx.nt) {
       double s;
       if (r == idt) s = Xi[idt];
       else {
-        int a = r / 7, rr = r % 7;
+        const int a = r / 7, rr = r % 7;
         s = 0;
         if (i < L.N[a]) {
-          const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
-          const double* Tr = T + (28 + rr) * NRED;
-          s = T[NW * NRED + 28 + rr] + Tr[IDT] * Xi[idt];
+          const double* Tr = fT + (size_t)(a * 7 + rr) * (NRED + 1);
+          int off = 0;
+          for (int aa = 0; aa < a; ++aa) off += R.npt[aa * L.Nmax + i];
+          const int np = R.npt[a * L.Nmax + i];
+          s = Tr[NRED] + Tr[IDT] * Xi[idt];
           for (int m = 0; m < 7; ++m) s += Tr[m] * Xi[7 * a + m];
-          for (int j = 0; j < NP; ++j) s += Tr[7 + j] * Ui[a * NP + j];
+          for (int j = 0; j < np; ++j) s += Tr[7 + j] * fU[off + j];
         }
       }
       Xn[r] = s;
@@ -1884,7 +2138,7 @@ OBCA_HDN int kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratc
   prof_mark(ctx, 6);
   int ok = *ok_shared;
   if (!ok) return 0;
-  riccati_forward(ctx, L, W, ok_shared);
+  riccati_forward(ctx, L, W, RW, ok_shared);
   cta_sync(ctx);
   prof_mark(ctx, 7);
   ok = *ok_shared;

