@@ -195,6 +195,8 @@ class MultiDistributedFollower(object):
         self.iter_time = {agent: [] for agent in self.agents}
         self.step_time: List[float] = []
         self.step_iters: List[int] = []
+        self.failed_solves = 0  # solves whose status was not a success (the vehicle kept its shifted plan, vehicle_follower.py:501-524)
+        self.failed_steps = 0   # control steps with at least one failed solve
         self.single_results: Dict[str, VehiclePrediction] = {}
         self.final_results: Dict[str, VehiclePrediction] = {}
         self.solver = None
@@ -226,11 +228,155 @@ class MultiDistributedFollower(object):
             dt_solve = time.perf_counter() - t0
             self.step_time.append(dt_solve)
             self.step_iters.append(int(np.max(res.iters)))
+            nfail = int((res.status < 0).sum())
+            self.failed_solves += nfail
+            self.failed_steps += int(nfail > 0)
             for b, v in enumerate(self.vehicles):
                 v.apply_result(bool(res.status[b] >= 0), res, b, dt_solve)
         for v in self.vehicles:
             self.iter_time[v.agent] = v.iter_time
             self.final_results[v.agent] = v.final_traj
+
+
+class DeviceMpcLoop(object):
+    """Device-resident closed loop of ``MultiDistributedFollower``: every quantity a control step touches
+    lives in HBM and every operation of ``VehicleFollower.step`` (vehicle_follower.py:428-563) is a kernel on one stream --
+
+        reference window  get_current_ref (:370-404)      obca_mpc_ref_times + obca_interpolate
+        neighbours        get_others_pred / _adv_onestep  obca_shift_horizon of everybody's last prediction (Jacobi snapshot, :636-637)
+        warm start        shifted previous solution       obca_shift_horizon
+        solve             opti.solve()                    obca_set_mpc_params / obca_set_initial / obca_solve (all vehicles, one launch)
+        fallback          except-branch (:501-524)        torch.where on the per-vehicle status: failed vehicles keep the shifted plan
+        plant             simulator (dynamic_model.py)    obca_plant_step
+
+    so a control step needs no host round trip: ``run(k)`` enqueues k steps and synchronises once; ``run(k, graph=True)`` captures one
+    step in a CUDA graph and replays it.  Built from a ``MultiDistributedFollower`` after ``setup_multi_vehicles()`` so that both
+    loops start from the same plans and the same (random) first-step duals; ``export()`` writes the state back."""
+
+    def __init__(self, mdf: "MultiDistributedFollower"):
+        import torch
+
+        from conflict_rez_b200.solver import TrajectoryOps
+
+        self.torch, self.mdf, self.solver = torch, mdf, mdf.solver
+        sv, vs = mdf.solver, mdf.vehicles
+        self.dev = sv.device
+        self.ops = TrajectoryOps(self.dev, lib=sv.lib)
+        V, N, O = len(vs), vs[0].N, len(vs[0].obstacles)
+        P = V - 1
+        self.V, self.N, self.O, self.P, self.dt = V, N, O, P, vs[0].dt
+        self.wb = vs[0].vehicle_body.wb
+        f64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
+        # reference plans: collocation solutions of plan_single_path (one per vehicle, own interval count and dt)
+        n_ref = [v._interp["N"] for v in vs]
+        Mmax = 6 * max(n_ref)
+        zref = np.zeros((1, V, Mmax, 7))
+        for a, v in enumerate(vs):
+            I = v._interp
+            M = 6 * I["N"]
+            zref[0, a, :M, :5] = I["X"].reshape(M, 5)
+            zref[0, a, :M, 5], zref[0, a, :M, 6] = I["u_a"], I["u_w"]
+        self.n_ref = n_ref
+        self.zref = f64(zref)
+        self.dt_ref = f64([[v._interp["dt"] for v in vs]])
+        self.grid = f64([[[v.reference_traj.t[0], v.reference_traj.t[-1], len(v.reference_traj.t)] for v in vs]])
+        # loop state
+        self.state = f64([[v.state.x.x, v.state.x.y, v.state.e.psi, v.state.v.v, v.state.u.u_steer] for v in vs])
+        self.clock = f64([[v.state.t for v in vs]])
+        self.pred_z = f64([np.stack([getattr(v.pred, k) for k in ("x", "y", "psi", "v", "u_steer", "u_a", "u_steer_dot")], axis=1) for v in vs])
+        self.pred_lam = f64([np.asarray(v.pred.l).reshape(N, O, 4) for v in vs])
+        self.pred_mu = f64([np.asarray(v.pred.m).reshape(N, O, 4) for v in vs])
+        self.pl = f64([[v.opt_lambda_ij[o] for o in v.others] for v in vs]).reshape(V, P, N, 4)
+        self.pm = f64([[v.opt_lambda_ji[o] for o in v.others] for v in vs]).reshape(V, P, N, 4)
+        self.ps = f64([[v.opt_s[o] for o in v.others] for v in vs]).reshape(V, P, N, 2)
+        agents = [v.agent for v in vs]
+        self.other_idx = torch.as_tensor([[agents.index(o) for o in v.others] for v in vs], dtype=torch.long, device=self.dev).reshape(V, P)
+        self.zero_dt = torch.zeros(V, dtype=torch.float64, device=self.dev)
+        self.steps_done = 0
+        self.fail_count = torch.zeros(V, dtype=torch.int64, device=self.dev)
+        self.iters_log, self.status_log, self.traj_log = [], [], []
+
+    def _step(self, log=True):
+        torch, sv, ops = self.torch, self.solver, self.ops
+        V, N = self.V, self.N
+        # parameters: current state, reference window, neighbours' shifted predictions (Jacobi snapshot of the previous solutions)
+        times = ops.mpc_ref_times(self.grid, self.clock, N, self.dt)
+        ref = ops.interpolate(self.zref, self.dt_ref, self.n_ref, times)[0, :, :, :3].contiguous()
+        sh_z = ops.shift_horizon(self.pred_z)
+        others = sh_z[self.other_idx][:, :, :, :3].contiguous() if self.P else None
+        d = {"z": sh_z.unsqueeze(1), "lam": ops.shift_horizon(self.pred_lam).unsqueeze(1), "mu": ops.shift_horizon(self.pred_mu).unsqueeze(1), "dt": self.zero_dt}
+        if self.P:
+            d["pl"] = ops.shift_horizon(self.pl.reshape(V * self.P, N, 4)).reshape(V, self.P, N, 4)
+            d["pm"] = ops.shift_horizon(self.pm.reshape(V * self.P, N, 4)).reshape(V, self.P, N, 4)
+            d["ps"] = ops.shift_horizon(self.ps.reshape(V * self.P, N, 2)).reshape(V, self.P, N, 2)
+        sv.set_params({"cur": self.state, "ref": ref, "others": others})
+        sv.set_inputs({k: v.contiguous() for k, v in d.items()})
+        sv.run()
+        st, it, _ = sv.fetch_stats()
+        sol = sv.fetch_solution()
+        ok = st >= 0
+        pick = lambda new, old: torch.where(ok.view((V,) + (1,) * (old.dim() - 1)), new.reshape(old.shape), old)
+        self.pred_z = pick(sol["z"], d["z"].squeeze(1))
+        self.pred_lam = pick(sol["lam"], d["lam"].squeeze(1))
+        self.pred_mu = pick(sol["mu"], d["mu"].squeeze(1))
+        if self.P:
+            self.pl, self.pm, self.ps = pick(sol["pl"], d["pl"]), pick(sol["pm"], d["pm"]), pick(sol["ps"], d["ps"])
+        self.state = ops.plant_step(self.state, self.pred_z[:, 0, 5:7].contiguous(), self.dt, self.wb)
+        self.clock = self.clock + self.dt
+        self.fail_count += (~ok).to(torch.int64)
+        if log:
+            self.iters_log.append(it)
+            self.status_log.append(st)
+            self.traj_log.append(torch.cat([self.state, self.pred_z[:, 0, 5:7]], dim=1))
+        self.steps_done += 1
+
+    def run(self, num_iter: int, graph: bool = False):
+        """Enqueue ``num_iter`` control steps; one synchronisation at the end.  Returns the wall time per step in seconds."""
+        torch = self.torch
+        if graph and self.dev.type == "cuda":
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):  # warm-up on a side stream (allocator), then capture one step
+                self._step(log=False)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            names = ("state", "clock", "pred_z", "pred_lam", "pred_mu", "pl", "pm", "ps")
+            static = {k: getattr(self, k).clone() for k in names}
+            for k in names:
+                setattr(self, k, static[k])
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step(log=False)
+                for k in names:  # write the new state back into the static tensors the graph reads on its next replay
+                    static[k].copy_(getattr(self, k))
+            for k in names:
+                setattr(self, k, static[k])
+            self.steps_done -= 1  # the capture pass itself does not execute
+            torch.cuda.synchronize(self.dev)
+            t0 = time.perf_counter()
+            for _ in range(num_iter - 1):
+                g.replay()
+            torch.cuda.synchronize(self.dev)
+            self.steps_done += num_iter - 1
+            return (time.perf_counter() - t0) / max(1, num_iter - 1)
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        t0 = time.perf_counter()
+        for _ in range(num_iter):
+            self._step()
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        return (time.perf_counter() - t0) / max(1, num_iter)
+
+    def export(self):
+        """Host copies: states (V,5), clock (V), trajectory log (steps,V,7) = state + applied input, statuses, iterations."""
+        cpu = lambda t: t.detach().cpu().numpy()
+        out = {"state": cpu(self.state), "clock": cpu(self.clock)[0], "failed_solves": int(self.fail_count.sum().item())}
+        if self.traj_log:
+            out["traj"] = np.stack([cpu(t) for t in self.traj_log])
+            out["status"] = np.stack([cpu(t) for t in self.status_log])
+            out["iters"] = np.stack([cpu(t) for t in self.iters_log])
+        return out
 
 
 class _RemotePrediction(object):

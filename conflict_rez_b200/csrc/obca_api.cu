@@ -50,6 +50,8 @@ struct ObcaHandle {
   Stat* d_S;
   double* d_tube;
   double *d_xL, *d_xU;
+  unsigned char* d_bcls;  // [nx + 16] bound class of every variable (obca_ipm.h BoundCls)
+  double blo[8], bhi[8];
   double* d_iter;  // [B][it_stride]
   double* d_work;  // [slots][wk_stride]
   double* d_rw;    // [slots][rw_stride]
@@ -187,6 +189,8 @@ struct SolveArgs {
   Opts o;
   Counts cnt;
   const double *xL, *xU;
+  const unsigned char* bcls;
+  double blo[8], bhi[8];
   double *iter, *work, *rw;
   size_t it_stride, wk_stride, rw_stride;
   Result* res;
@@ -205,8 +209,8 @@ OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, const Lay& L, con
   carve_iterate(W, L, A.iter + (size_t)b * A.it_stride);
   carve_work(W, L, A.work + (size_t)slot * A.wk_stride);
   if (A.mode == 0) {
-    if (L.mode == 0) ipm_solve<0>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, A.rw_stride, sh, A.res + b);
-    else ipm_solve<1>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, W, RW, A.rw_stride, sh, A.res + b);
+    if (L.mode == 0) ipm_solve<0>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, A.bcls, W, RW, A.rw_stride, sh, A.res + b);
+    else ipm_solve<1>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, A.bcls, W, RW, A.rw_stride, sh, A.res + b);
     return;
   }
   double f, gdt;
@@ -277,6 +281,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_solve(SolveArgs A)
     double* dstS = (double*)&sS;
     for (int q = threadIdx.x; q < (int)(sizeof(Stat) / sizeof(double)); q += blockDim.x) dstS[q] = srcS[q];
   }
+  if (threadIdx.x < 8) sh.blo[threadIdx.x] = A.blo[threadIdx.x], sh.bhi[threadIdx.x] = A.bhi[threadIdx.x];
   __syncthreads();
   double* RW = arena;
   Ctx ctx{(int)threadIdx.x, (int)blockDim.x, red, A.prof ? A.prof + (size_t)blockIdx.x * (NPROF + 1) : nullptr};
@@ -376,7 +381,8 @@ int obca_set_options(ObcaHandle* h, const ObcaOptions* opts) {
 }
 
 static void free_device(ObcaHandle* h) {
-  dev_free(h->d_L), dev_free(h->d_S), dev_free(h->d_tube), dev_free(h->d_xL), dev_free(h->d_xU);
+  dev_free(h->d_L), dev_free(h->d_S), dev_free(h->d_tube), dev_free(h->d_xL), dev_free(h->d_xU), dev_free(h->d_bcls);
+  h->d_bcls = nullptr;
   dev_free(h->d_iter), dev_free(h->d_work), dev_free(h->d_rw), dev_free(h->d_res), dev_free(h->d_counter), dev_free(h->d_order), dev_free(h->d_prof);
   h->d_order = nullptr, h->have_order = false;
   h->d_prof = nullptr;
@@ -501,6 +507,22 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
     m_active += 6 * L.Mp[p];
   }
   for (int q = 0; q < L.nx; ++q) nb += (xL[q] > -INFINITY) + (xU[q] < INFINITY);
+  // bound classes: 0 free, 1 lower bound 0, 2..7 the two-sided bounds of x, y, v, delta, a, w
+  std::vector<unsigned char> bcls(L.nx + 16, 0);
+  {
+    const int zc[NZ] = {2, 3, 0, 4, 5, 6, 7};
+    for (int k = 0; k < 8; ++k) h->blo[k] = -INFINITY, h->bhi[k] = INFINITY;
+    h->blo[1] = 0.0;
+    for (int c = 0; c < NZ; ++c)
+      if (zc[c]) h->blo[zc[c]] = lo[c], h->bhi[zc[c]] = hi[c];
+    for (int q = 0; q < L.nx; ++q) {
+      int k = -1;
+      for (int kk = 0; kk < 8 && k < 0; ++kk)
+        if (xL[q] == h->blo[kk] && xU[q] == h->bhi[kk]) k = kk;
+      if (k < 0) return fail("obca_set_static: internal error (a variable's bounds match no bound class)");
+      bcls[q] = (unsigned char)k;
+    }
+  }
   h->cnt.m_active = m_active, h->cnt.nb = nb;
   h->it_stride = iterate_doubles(L), h->wk_stride = work_doubles(L);
   h->rw_stride = mpc ? mpc_work_doubles(L) : riccati_work_doubles(L, NWARPS);
@@ -517,7 +539,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
 #endif
   int B = h->dims.batch;
   if (dev_alloc((void**)&h->d_L, sizeof(Lay)) || dev_alloc((void**)&h->d_S, sizeof(Stat)) || dev_alloc((void**)&h->d_tube, tube.size() * 8) ||
-      dev_alloc((void**)&h->d_xL, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_xU, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_iter, (size_t)B * h->it_stride * 8) ||
+      dev_alloc((void**)&h->d_bcls, bcls.size()) || dev_alloc((void**)&h->d_xL, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_xU, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_iter, (size_t)B * h->it_stride * 8) ||
       dev_alloc((void**)&h->d_work, (size_t)h->slots * h->wk_stride * 8) || dev_alloc((void**)&h->d_rw, (size_t)h->slots * h->rw_stride * 8) ||
       dev_alloc((void**)&h->d_res, (size_t)B * sizeof(Result)) || dev_alloc((void**)&h->d_counter, sizeof(int)) || dev_alloc((void**)&h->d_order, (size_t)B * sizeof(int)) ||
       dev_alloc((void**)&h->d_prof, (size_t)h->slots * (NPROF + 1) * sizeof(long long)))
@@ -526,6 +548,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   h2d(h->d_tube, tube.data(), tube.size() * 8);
   h2d(h->d_L, &L, sizeof(Lay));
   h2d(h->d_S, &S, sizeof(Stat));
+  h2d(h->d_bcls, bcls.data(), bcls.size());
   h2d(h->d_xL, xL.data(), L.nx * 8);
   h2d(h->d_xU, xU.data(), L.nx * 8);
   std::vector<Result> r0(B);
@@ -728,7 +751,8 @@ int obca_get_solution(ObcaHandle* h, double* z, double* lam, double* mu, double*
 
 static SolveArgs make_args(ObcaHandle* h, int mode, int b) {
   SolveArgs A;
-  A.L = h->d_L, A.S = h->d_S, A.o = h->opts, A.cnt = h->cnt, A.xL = h->d_xL, A.xU = h->d_xU;
+  A.L = h->d_L, A.S = h->d_S, A.o = h->opts, A.cnt = h->cnt, A.xL = h->d_xL, A.xU = h->d_xU, A.bcls = h->d_bcls;
+  for (int k = 0; k < 8; ++k) A.blo[k] = h->blo[k], A.bhi[k] = h->bhi[k];
   A.iter = h->d_iter, A.work = h->d_work, A.rw = h->d_rw;
   A.it_stride = h->it_stride, A.wk_stride = h->wk_stride, A.rw_stride = h->rw_stride;
   A.res = h->d_res, A.B = h->dims.batch, A.counter = h->d_counter, A.mode = mode, A.b_only = b;
@@ -744,6 +768,7 @@ static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
 #ifdef OBCA_HOST_EMU
   (void)stream;
   Shared sh;
+  for (int k = 0; k < 8; ++k) sh.blo[k] = A.blo[k], sh.bhi[k] = A.bhi[k];
   double red[40];
   Ctx ctx{0, 1, red, nullptr};
   if (A.mode != 0)
@@ -758,6 +783,118 @@ static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
   if (smem) CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_solve<<<grid, CTA_THREADS, smem, s>>>(A);
   h->launches++;
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trajectory-side kernels (obca_traj.h)
+// ------------------------------------------------------------------------------------------------
+#ifndef OBCA_HOST_EMU
+struct InterpConst {
+  int n_intervals[OBCA_MAX_V];
+  double tau[NK];
+};
+__global__ void k_interpolate(InterpArgs A, InterpConst C, size_t tot) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= tot) return;
+  A.n_intervals = C.n_intervals, A.tau = C.tau;
+  interp_item(A, g);
+}
+__global__ void k_ref_times(const double* grid, const double* clock, int N, double dt_mpc, double* times, size_t tot) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= tot) return;
+  const size_t v = g / N;
+  const int k = (int)(g % N);
+  times[g] = ref_window_start(grid[v * 3], grid[v * 3 + 1], (int)grid[v * 3 + 2], clock[v]) + k * dt_mpc;
+}
+__global__ void k_plant_step(const double* state, const double* input, int B, double dt, double wb, int substeps, double* next) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) plant_step(state + (size_t)b * 5, input + (size_t)b * 2, dt, wb, substeps, next + (size_t)b * 5);
+}
+__global__ void k_shift(const double* in, double* out, int N, int Wd, size_t tot) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < tot) shift_item(in, out, N, Wd, g);
+}
+static int check_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("bad device index");
+  return 0;
+}
+#else
+static int check_device(int) { return 0; }
+#endif
+
+int obca_interpolate(int device, const double* z, const double* dt, const int32_t* n_intervals, const double* tau, int B, int V, int Mmax,
+                     const double* times, int T, int per_vehicle_times, int dt_per_vehicle, double* out, void* stream) {
+  if (!z || !dt || !n_intervals || !tau || !times || !out) return fail("obca_interpolate: null argument");
+  if (B < 1 || V < 1 || V > OBCA_MAX_V || T < 1) return fail("obca_interpolate: bad dimensions");
+  for (int a = 0; a < V; ++a)
+    if (n_intervals[a] < 1 || n_intervals[a] * NK > Mmax) return fail("obca_interpolate: n_intervals does not fit Mmax");
+  if (check_device(device)) return -1;
+  DeviceGuard guard(device);
+  InterpArgs A;
+  A.z = z, A.dt = dt, A.times = times, A.out = out, A.B = B, A.V = V, A.Mmax = Mmax, A.T = T, A.per_vehicle_times = per_vehicle_times, A.dt_per_vehicle = dt_per_vehicle;
+  const size_t tot = (size_t)B * V * T;
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  A.n_intervals = n_intervals, A.tau = tau;
+  for (size_t g = 0; g < tot; ++g) interp_item(A, g);
+#else
+  InterpConst C;
+  for (int a = 0; a < V; ++a) C.n_intervals[a] = n_intervals[a];
+  for (int k = 0; k < NK; ++k) C.tau[k] = tau[k];
+  A.n_intervals = nullptr, A.tau = nullptr;
+  k_interpolate<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A, C, tot);
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+int obca_mpc_ref_times(int device, const double* grid, const double* clock, int B, int V, int N, double dt_mpc, double* times, void* stream) {
+  if (!grid || !clock || !times || B < 1 || V < 1 || N < 1) return fail("obca_mpc_ref_times: bad argument");
+  if (check_device(device)) return -1;
+  DeviceGuard guard(device);
+  const size_t tot = (size_t)B * V * N;
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (size_t g = 0; g < tot; ++g) {
+    const size_t v = g / N;
+    times[g] = ref_window_start(grid[v * 3], grid[v * 3 + 1], (int)grid[v * 3 + 2], clock[v]) + (int)(g % N) * dt_mpc;
+  }
+#else
+  k_ref_times<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(grid, clock, N, dt_mpc, times, tot);
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+int obca_plant_step(int device, const double* state, const double* input, int B, double dt, double wb, int substeps, double* next, void* stream) {
+  if (!state || !input || !next || B < 1 || substeps < 1) return fail("obca_plant_step: bad argument");
+  if (check_device(device)) return -1;
+  DeviceGuard guard(device);
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (int b = 0; b < B; ++b) plant_step(state + (size_t)b * 5, input + (size_t)b * 2, dt, wb, substeps, next + (size_t)b * 5);
+#else
+  k_plant_step<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(state, input, B, dt, wb, substeps, next);
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+int obca_shift_horizon(int device, const double* in, int B, int N, int Wd, double* out, void* stream) {
+  if (!in || !out || B < 1 || N < 1 || Wd < 1 || in == out) return fail("obca_shift_horizon: bad argument");
+  if (check_device(device)) return -1;
+  DeviceGuard guard(device);
+  const size_t tot = (size_t)B * N * Wd;
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (size_t g = 0; g < tot; ++g) shift_item(in, out, N, Wd, g);
+#else
+  k_shift<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(in, out, N, Wd, tot);
   CUDA_OK(cudaGetLastError());
 #endif
   return 0;

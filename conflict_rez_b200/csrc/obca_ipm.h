@@ -12,7 +12,16 @@ struct Shared {   // lives in shared memory on the device
   int again;   // interval_nullspace: another pass needed
   int filt_n;
   double filt_theta[FILTER_MAX], filt_phi[FILTER_MAX];
-  unsigned long long bars[4];  // mbarriers of the staged flat passes
+  unsigned long long bars[8];  // mbarriers of the staged flat passes
+  double blo[8], bhi[8];       // bounds of the 8 bound classes (see BoundCls)
+};
+
+// Simple bounds by class instead of two FP64 vectors: one byte per variable.  Class 0: free, 1: lower bound 0 (duals, slacks,
+// elastic variables), 2..7: the two-sided bounds of x, y, v, delta, a, w.  The flat passes stage the class bytes next to the
+// vectors (1 KB per tile instead of 16 KB for xL and xU): a third less traffic in the passes over the primal vectors.
+struct BoundCls {
+  const unsigned char* cls;  // [nx], padded to a multiple of 16
+  const double *lo, *hi;     // [8] in shared memory
 };
 
 struct Counts {
@@ -33,7 +42,7 @@ OBCA_HD bool finite_d(double v) { return v - v == 0.0; }
 #define OBCA_ST_TILE 1024
 #endif
 constexpr int ST_TILE = OBCA_ST_TILE;  // elements per tile (4 per thread)
-constexpr int ST_STAGES = 3;
+constexpr int ST_STAGES_MAX = 8;
 
 struct Stage {
   double* buf;              // shared-memory arena (nullptr: no staging)
@@ -51,10 +60,15 @@ __device__ __forceinline__ void st_wait(unsigned long long* bar, unsigned parity
 }
 #endif
 
-template <int NA, class Body>
-OBCA_HD void flat_pass(const Ctx& ctx, const Stage& st, const double* const (&src)[NA], int n, Body&& body) {
+// CLS: the class byte of every element is staged too and body(q, v, lo, hi) receives its bounds
+template <int NA, bool CLS, class Body>
+OBCA_HD void flat_pass_impl(const Ctx& ctx, const Stage& st, const BoundCls* bc, const double* const (&src)[NA], int n, Body&& body) {
 #if defined(__CUDA_ARCH__)
-  if (st.buf && st.cap >= (size_t)ST_STAGES * NA * ST_TILE && n >= 4 * ST_TILE && ctx.nt * 4 == ST_TILE) {
+  constexpr int TILE_D = NA * ST_TILE + (CLS ? ST_TILE / 8 : 0);  // doubles per stage buffer
+  // ring depth 3: measured, a deeper ring (up to 8 tiles in flight) is 8 % slower -- the passes are bound by the FP64 instruction
+  // latency of the bodies at 2 warps per scheduler, not by bytes in flight (profiles/r02_flat_pass_experiments.txt)
+  const int ST_STAGES = st.cap / TILE_D >= 3 ? 3 : 0;
+  if (st.buf && ST_STAGES >= 3 && n >= 4 * ST_TILE && ctx.nt * 4 == ST_TILE) {
     const int ntile = (n + ST_TILE - 1) / ST_TILE;
     if (ctx.tid == 0) {
       for (int k = 0; k < ST_STAGES; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem(st.bar + k)) : "memory");
@@ -66,13 +80,18 @@ OBCA_HD void flat_pass(const Ctx& ctx, const Stage& st, const double* const (&sr
       const int stage = t % ST_STAGES, start = t * ST_TILE;
       const int cnt = n - start < ST_TILE ? n - start : ST_TILE;
       const unsigned bytes = (unsigned)(((cnt + 1) & ~1) * 8);
+      const unsigned cbytes = CLS ? (unsigned)((cnt + 15) & ~15) : 0u;
       const unsigned bar = st_smem(st.bar + stage);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * NA) : "memory");
+      double* sb = st.buf + (size_t)stage * TILE_D;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * NA + cbytes) : "memory");
 #pragma unroll
       for (int a = 0; a < NA; ++a)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         st_smem(st.buf + (size_t)(stage * NA + a) * ST_TILE)),
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(sb + (size_t)a * ST_TILE)),
                      "l"(src[a] + start), "r"(bytes), "r"(bar)
+                     : "memory");
+      if (CLS)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(sb + (size_t)NA * ST_TILE)),
+                     "l"(bc->cls + start), "r"(cbytes), "r"(bar)
                      : "memory");
     };
     if (ctx.tid == 0)
@@ -80,7 +99,8 @@ OBCA_HD void flat_pass(const Ctx& ctx, const Stage& st, const double* const (&sr
     for (int t = 0; t < ntile; ++t) {
       if (ctx.tid == 0 && t + ST_STAGES - 1 < ntile) issue(t + ST_STAGES - 1);  // its stage was released by the barrier below
       st_wait(st.bar + t % ST_STAGES, (unsigned)((t / ST_STAGES) & 1));
-      const double* tb = st.buf + (size_t)(t % ST_STAGES) * NA * ST_TILE;
+      const double* tb = st.buf + (size_t)(t % ST_STAGES) * TILE_D;
+      const unsigned char* cb = (const unsigned char*)(tb + (size_t)NA * ST_TILE);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int e = ctx.tid + u * ctx.nt, q = t * ST_TILE + e;
@@ -88,7 +108,11 @@ OBCA_HD void flat_pass(const Ctx& ctx, const Stage& st, const double* const (&sr
           double v[NA];
 #pragma unroll
           for (int a = 0; a < NA; ++a) v[a] = tb[a * ST_TILE + e];
-          body(q, v);
+          if constexpr (CLS) {
+            const int k = cb[e];
+            body(q, v, bc->lo[k], bc->hi[k]);
+          } else
+            body(q, v, 0.0, 0.0);
         }
       }
       __syncthreads();
@@ -102,20 +126,33 @@ OBCA_HD void flat_pass(const Ctx& ctx, const Stage& st, const double* const (&sr
   (void)st;
   for (int q0 = ctx.tid; q0 < n; q0 += VW * ctx.nt) {
     double v[VW][NA];
+    int kc[VW];
 #pragma unroll
     for (int u = 0; u < VW; ++u) {
       const int q = q0 + u * ctx.nt;
 #pragma unroll
       for (int a = 0; a < NA; ++a) v[u][a] = q < n ? src[a][q] : 0.0;
+      kc[u] = (CLS && q < n) ? bc->cls[q] : 0;
     }
 #pragma unroll
     for (int u = 0; u < VW; ++u) {
       const int q = q0 + u * ctx.nt;
-      if (q < n) body(q, v[u]);
+      if (q < n) {
+        if constexpr (CLS) body(q, v[u], bc->lo[kc[u]], bc->hi[kc[u]]);
+        else body(q, v[u], 0.0, 0.0);
+      }
     }
   }
 }
 
+template <int NA, class Body>
+OBCA_HD void flat_pass(const Ctx& ctx, const Stage& st, const double* const (&src)[NA], int n, Body&& body) {
+  flat_pass_impl<NA, false>(ctx, st, nullptr, src, n, [&](int q, const double* v, double, double) { body(q, v); });
+}
+template <int NA, class Body>
+OBCA_HD void flat_pass_b(const Ctx& ctx, const Stage& st, const BoundCls& bc, const double* const (&src)[NA], int n, Body&& body) {
+  flat_pass_impl<NA, true>(ctx, st, &bc, src, n, body);
+}
 
 // model dispatch: MODE 0 = collocation OBCA (obca_core.h / obca_kkt.h), MODE 1 = MPC (obca_mpc.h)
 template <int MODE>
@@ -184,7 +221,9 @@ OBCA_HDN void push_into_bounds(const Ctx& ctx, const Lay& L, const double* xL, c
 // `it` and `n_refine` accumulate over the runs of one instance.  Returns the status; *el_out = largest elastic variable.
 template <int MODE>
 OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
-                         const double* xU, const Scratch& W, double* RW, size_t rw_cap, Shared* sh, Result* res, int& it, int& n_refine, double* el_out) {
+                         const double* xU, const unsigned char* bcls, const Scratch& W, double* RW, size_t rw_cap, Shared* sh, Result* res, int& it,
+                         int& n_refine, double* el_out) {
+  const BoundCls bc = {bcls, sh->blo, sh->bhi};
   assume_scratch(W);
   OBCA_ASSUME_STATIC(L, S);
   OBCA_ASSUME_GLOBAL(xL), OBCA_ASSUME_GLOBAL(xU);
@@ -223,9 +262,9 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
     double e_du = 0, e_c = 0, e_c1 = 0, s_y = 0, s_z = 0, cmax0 = 0, cmaxmu_lo = INFINITY, cmaxmu_hi = 0;
     double s_log = 0, s_gap = 0;  // barrier pieces: phi = f + mu (-sum log gap + kappa_d sum one-sided gap)
     {
-      const double* const src[6] = {xL, xU, W.x, W.zL, W.zU, W.gl};
-      flat_pass<6>(ctx, st, src, L.nx, [&](int, const double* v) {
-        const double lo = v[0], hi = v[1], xv = v[2], zl = v[3], zu = v[4], gq = v[5];
+      const double* const src[4] = {W.x, W.zL, W.zU, W.gl};
+      flat_pass_b<4>(ctx, st, bc, src, L.nx, [&](int, const double* v, double lo, double hi) {
+        const double xv = v[0], zl = v[1], zu = v[2], gq = v[3];
         e_du = fmax(e_du, fabs(gq - zl + zu));
         const bool hl = lo > -INFINITY, hu = hi < INFINITY;
         if (hl) {
@@ -322,19 +361,19 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
     bool first = true, have = false;
     for (;;) {
       {
-        const double* const src[6] = {xL, xU, W.x, W.zL, W.zU, W.gl};
-        flat_pass<6>(ctx, st, src, L.nx, [&](int q, const double* v) {
-          const double lo = v[0], hi = v[1], xv = v[2], zl = v[3], zu = v[4];
+        const double* const src[4] = {W.x, W.zL, W.zU, W.gl};
+        flat_pass_b<4>(ctx, st, bc, src, L.nx, [&](int q, const double* v, double lo, double hi) {
+          const double xv = v[0], zl = v[1], zu = v[2];
           const bool hl = lo > -INFINITY, hu = hi < INFINITY;
-          double sg = dw, gp = v[5];
+          double sg = dw, gp = v[3];
           if (hl) {
-            const double iL = 1.0 / (xv - lo);
+            const double iL = rcp_pos(xv - lo);
             sg += zl * iL;
             gp -= mu * iL;
             if (!hu) gp += o.kappa_d * mu;
           }
           if (hu) {
-            const double iU = 1.0 / (hi - xv);
+            const double iU = rcp_pos(hi - xv);
             sg += zu * iU;
             gp += mu * iU;
             if (!hl) gp -= o.kappa_d * mu;
@@ -367,23 +406,23 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
     // ---- dz, fraction to the boundary, directional derivative of the barrier objective
     double a_pr = 1.0, a_du = 1.0, dphi = 0, rel = 0, r_pr = 0;
     {
-      const double* const src[7] = {xL, xU, W.x, W.zL, W.zU, W.gphi, W.dx};
-      flat_pass<7>(ctx, st, src, L.nx, [&](int, const double* v) {
-        const double lo = v[0], hi = v[1], xv = v[2], zl = v[3], zu = v[4], d = v[6];
+      const double* const src[5] = {W.x, W.zL, W.zU, W.gphi, W.dx};
+      flat_pass_b<5>(ctx, st, bc, src, L.nx, [&](int, const double* v, double lo, double hi) {
+        const double xv = v[0], zl = v[1], zu = v[2], d = v[4];
         rel = fmax(rel, fabs(d) / (1.0 + fabs(xv)));
         if (lo > -INFINITY) {
-          const double ig = 1.0 / (xv - lo);
+          const double ig = rcp_pos(xv - lo);
           const double dz = (mu - zl * d) * ig - zl;
           r_pr = fmax(r_pr, -d * ig);            // alpha_pr = tau / max(-d / gap)
           if (dz < 0) a_du = fmin(a_du, -tau * zl / dz);
         }
         if (hi < INFINITY) {
-          const double ig = 1.0 / (hi - xv);
+          const double ig = rcp_pos(hi - xv);
           const double dz = (mu + zu * d) * ig - zu;
           r_pr = fmax(r_pr, d * ig);
           if (dz < 0) a_du = fmin(a_du, -tau * zu / dz);
         }
-        dphi += v[5] * d;
+        dphi += v[3] * d;
       });
       prof_mark(ctx, 23);
     }
@@ -454,13 +493,12 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
       double sbar = 0;
       int bad = 0;
       {
-        const double* const src[4] = {xL, xU, W.x, W.dx};
+        const double* const src[2] = {W.x, W.dx};
         // sum of log(gap) as log of products: the gaps of four consecutive elements of a thread (up to 8 factors, each within
         // [1e-12, 1e2]) are multiplied and one log is taken for the group; all lanes flush at the same elements
         double prod = 1.0;
-        flat_pass<4>(ctx, st, src, L.nx, [&](int q, const double* v) {
-          const double lo = v[0], hi = v[1];
-          const double xn = v[2] + alpha * v[3];
+        flat_pass_b<2>(ctx, st, bc, src, L.nx, [&](int q, const double* v, double lo, double hi) {
+          const double xn = v[0] + alpha * v[1];
           W.xt[q] = xn;
           const bool hl = lo > -INFINITY, hu = hi < INFINITY;
           if (hl) {
@@ -530,18 +568,18 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
     // ---- accept the trial point (dz is recomputed from dx; x + alpha dx reproduces the trial point bit for bit)
     const double iks = 1.0 / o.kappa_sigma;
     {
-      const double* const src[6] = {xL, xU, W.x, W.zL, W.zU, W.dx};
-      flat_pass<6>(ctx, st, src, L.nx, [&](int q, const double* v) {
-        const double lo = v[0], hi = v[1], xv = v[2], zl = v[3], zu = v[4], d = v[5];
+      const double* const src[4] = {W.x, W.zL, W.zU, W.dx};
+      flat_pass_b<4>(ctx, st, bc, src, L.nx, [&](int q, const double* v, double lo, double hi) {
+        const double xv = v[0], zl = v[1], zu = v[2], d = v[3];
         const double xn = xv + alpha * d;
         W.x[q] = xn;
         if (lo > -INFINITY) {
-          const double i0 = 1.0 / (xv - lo), mg = mu / (xn - lo);
+          const double i0 = rcp_pos(xv - lo), mg = mu * rcp_pos(xn - lo);
           const double zv = zl + a_du * ((mu - zl * d) * i0 - zl);
           W.zL[q] = fmin(fmax(zv, mg * iks), o.kappa_sigma * mg);
         }
         if (hi < INFINITY) {
-          const double i0 = 1.0 / (hi - xv), mg = mu / (hi - xn);
+          const double i0 = rcp_pos(hi - xv), mg = mu * rcp_pos(hi - xn);
           const double zv = zu + a_du * ((mu + zu * d) * i0 - zu);
           W.zU[q] = fmin(fmax(zv, mg * iks), o.kappa_sigma * mg);
         }
@@ -625,12 +663,12 @@ OBCA_HDN void dual_restore(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
 
 template <int MODE>
 OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts& o, const Counts& cnt, const double* xL,
-                        const double* xU, const Scratch& W, double* RW, size_t rw_cap, Shared* sh, Result* res) {
+                        const double* xU, const unsigned char* bcls, const Scratch& W, double* RW, size_t rw_cap, Shared* sh, Result* res) {
   int it = 0, n_refine = 0, restarts = 0, status;
   double el_max;
   const double thr = fmax(o.constr_viol_tol, 1e-8);
   for (;;) {
-    status = ipm_attempt<MODE>(ctx, L, S, o, cnt, xL, xU, W, RW, rw_cap, sh, res, it, n_refine, &el_max);
+    status = ipm_attempt<MODE>(ctx, L, S, o, cnt, xL, xU, bcls, W, RW, rw_cap, sh, res, it, n_refine, &el_max);
     if (!(status >= 0 && el_max > thr)) break;
     if (restarts >= 2 || it >= o.max_iter) {
       // a converged point of the penalised problem with an active elastic variable: the reference problem (hard distance rows)

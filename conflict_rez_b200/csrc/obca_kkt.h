@@ -36,14 +36,14 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
     double ynm = yn < 0 ? yn : 0.0;  // local convexification: exact at KKT points (yn = -z_sn <= 0)
     // Block elimination in registers: lam, mu (diagonal Hessians) -> 5 x 5 Schur complement on (yd, ye1, ye2)
     // (the yn row only has its own pivot), then the 2 x 2 system of s.  7 right-hand sides (6 pose couplings + residual).
-    const double isd = 1.0 / W.sig[L.PSD(p, n)], iel = 1.0 / W.sig[L.PEL(p, n)], isn = 1.0 / W.sig[L.PSN(p, n)];
-    const double dn = DELTA_C_LOCAL + isn, idn = 1.0 / dn;
+    const double isd = rcp_pos(W.sig[L.PSD(p, n)]), iel = rcp_pos(W.sig[L.PEL(p, n)]), isn = rcp_pos(W.sig[L.PSN(p, n)]);
+    const double dn = DELTA_C_LOCAL + isn, idn = rcp_pos(dn);
     const double hs0 = W.sig[L.PS(p, 0, n)] - 2.0 * ynm, hs1 = W.sig[L.PS(p, 1, n)] - 2.0 * ynm;
     double sl[4], smu[4], ea[4], fa[4], eb[4], fb[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      sl[r] = 1.0 / W.sig[L.PL(p, r, n)];
-      smu[r] = 1.0 / W.sig[L.PM(p, r, n)];
+      sl[r] = rcp_pos(W.sig[L.PL(p, r, n)]);
+      smu[r] = rcp_pos(W.sig[L.PM(p, r, n)]);
       ea[r] = a.c * S.G[r][0] - a.s * S.G[r][1];
       fa[r] = a.s * S.G[r][0] + a.c * S.G[r][1];
       eb[r] = b.c * S.G[r][0] - b.s * S.G[r][1];
@@ -217,7 +217,7 @@ OBCA_HD void obs_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, 
 #pragma unroll
         for (int q = 0; q <= r; ++q) Hl[sym(r, q)] = 2.0 * y3p * (A[0] * S.obsA[j][q][0] + A[1] * S.obsA[j][q][1]);
         Hl[sym(r, r)] += W.sig[L.LAM(a, j, r, n)];
-        sm[r] = 1.0 / W.sig[L.MU(a, j, r, n)];  // inverse
+        sm[r] = rcp_pos(W.sig[L.MU(a, j, r, n)]);  // inverse
         Jl[0][r] = B.Atb[r];
         Jl[1][r] = p.c * A[0] + p.s * A[1];
         Jl[2][r] = -p.s * A[0] + p.c * A[1];
@@ -228,7 +228,7 @@ OBCA_HD void obs_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, 
         bl[r] = -W.gphi[L.LAM(a, j, r, n)];
         bm[r] = -W.gphi[L.MU(a, j, r, n)];
       }
-      const double isd = 1.0 / W.sig[L.SD(a, j, n)], iel = 1.0 / W.sig[L.EL(a, j, n)];
+      const double isd = rcp_pos(W.sig[L.SD(a, j, n)]), iel = rcp_pos(W.sig[L.EL(a, j, n)]);
       if (!chol_packed<4>(Hl)) *ok = 0;
       double Wl[4][4];  // Wl[i] = Hl^-1 Jl[i]'
 #pragma unroll
@@ -320,8 +320,8 @@ OBCA_HD void obs_block_backsub(const Lay& L, const Scratch& W, int a, int n, int
     W.dy[L.YOBS(a, j, q, n)] = r[8 + q];
   }
   // sd: sig dsd - dy1 = -gphi ; el: sig del + dy1 = -gphi
-  W.dx[L.SD(a, j, n)] = (r[8] - W.gphi[L.SD(a, j, n)]) / W.sig[L.SD(a, j, n)];
-  W.dx[L.EL(a, j, n)] = -(r[8] + W.gphi[L.EL(a, j, n)]) / W.sig[L.EL(a, j, n)];
+  W.dx[L.SD(a, j, n)] = (r[8] - W.gphi[L.SD(a, j, n)]) * rcp_pos(W.sig[L.SD(a, j, n)]);
+  W.dx[L.EL(a, j, n)] = -(r[8] + W.gphi[L.EL(a, j, n)]) * rcp_pos(W.sig[L.EL(a, j, n)]);
 }
 
 OBCA_HD void pair_block_backsub(const Lay& L, const Scratch& W, int p, int n, const double* dp) {
@@ -336,9 +336,9 @@ OBCA_HD void pair_block_backsub(const Lay& L, const Scratch& W, int p, int n, co
   for (int q = 0; q < 6; ++q) W.dy[L.YPAIR(p, q, n)] = r[8 + q];
   W.dx[L.PS(p, 0, n)] = r[14];
   W.dx[L.PS(p, 1, n)] = r[15];
-  W.dx[L.PSD(p, n)] = (r[8] - W.gphi[L.PSD(p, n)]) / W.sig[L.PSD(p, n)];
-  W.dx[L.PEL(p, n)] = -(r[8] + W.gphi[L.PEL(p, n)]) / W.sig[L.PEL(p, n)];
-  W.dx[L.PSN(p, n)] = (r[13] - W.gphi[L.PSN(p, n)]) / W.sig[L.PSN(p, n)];
+  W.dx[L.PSD(p, n)] = (r[8] - W.gphi[L.PSD(p, n)]) * rcp_pos(W.sig[L.PSD(p, n)]);
+  W.dx[L.PEL(p, n)] = -(r[8] + W.gphi[L.PEL(p, n)]) * rcp_pos(W.sig[L.PEL(p, n)]);
+  W.dx[L.PSN(p, n)] = (r[13] - W.gphi[L.PSN(p, n)]) * rcp_pos(W.sig[L.PSN(p, n)]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1377,15 +1377,6 @@ OBCA_HD bool ldl_fast_shape(const Ctx& ctx, int nu, int nc) {
 }
 
 #if defined(__CUDA_ARCH__)
-// 1 / d for a positive, normal d: hardware seed (MUFU.RCP64H) + two Newton steps
-__device__ __forceinline__ double fast_rcp(double d) {
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  x = fma(x, fma(-d, x, 1.0), x);
-  x = fma(x, fma(-d, x, 1.0), x);
-  return x;
-}
-
 template <int KMAX>
 __device__ __forceinline__ void cta_stage_ldl(const RicWork& R, int nu, int nX, int* ok, LdlBuf* B) {
   const int t = threadIdx.x, rg = t >> 6, c = t & 63, nc = nX + 1, ncols = nu + nc;
@@ -1423,7 +1414,7 @@ __device__ __forceinline__ void cta_stage_ldl(const RicWork& R, int nu, int nX, 
   if (t == 0) {
     double d = m[0];
     if (!(d > mytol)) B->bad = 1, d = 1.0;
-    const double inv = fast_rcp(d);
+    const double inv = rcp_pos(d);
     B->inv[0] = inv, B->invd[0] = inv;
   }
   __syncthreads();
@@ -1452,7 +1443,7 @@ __device__ __forceinline__ void cta_stage_ldl(const RicWork& R, int nu, int nX, 
           if (c == jn) {
             double d = m[kn < KMAX ? kn : 0];
             if (!(d > mytol)) B->bad = 1, d = 1.0;
-            const double inv = fast_rcp(d);
+            const double inv = rcp_pos(d);
             B->inv[p ^ 1] = inv, B->invd[jn] = inv;
           }
         }
@@ -1756,84 +1747,105 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
   }
 }
 
-// Forward pass.  Per stage: the record (Ks', L) and the dynamics rows of the T maps are staged in shared memory by the whole
-// CTA (coalesced), warp 0 computes the controls  u = L^-T (Ks [x; 1])  -- one lane per control, the back-substitution runs on
-// shuffles --, then the next state follows from the block dynamics.  fb: shared-memory scratch (>= record + V * 7 * (NRED + 1)).
+// Forward pass.  The stage record (Ks', L) and the dynamics rows of the T maps of stage i + 1 are fetched into shared memory
+// with asynchronous copies (cp.async, two buffers) while stage i is computed; the state stays in shared memory (ping-pong).
+// Per stage: warp 0 computes the controls  u = L^-T (Ks [x; 1])  -- one lane per control, its column of L in registers, the
+// back-substitution runs on shuffles --, then all threads advance the state through the block dynamics.  Two CTA barriers per
+// stage and no exposed global-memory latency (round 1: gains read from global memory inside the loop, 7 k cycles per stage).
+OBCA_HD size_t ric_fwd_buffer_doubles(const Lay& L) { return ric_record_doubles(L) + (size_t)L.V * 7 * (NRED + 1); }
+
+OBCA_HD void ric_fwd_fetch(const Ctx& ctx, const Lay& L, const Scratch& W, int i, double* buf) {
+  const size_t kstride = ric_record_doubles(L);
+  const double* Kg = W.RK + (size_t)i * kstride;
+  double* fT = buf + kstride;
+#if defined(__CUDA_ARCH__)
+  for (int it = ctx.tid; it < (int)kstride; it += ctx.nt)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(buf + it)), "l"(Kg + it) : "memory");
+#else
+  for (int it = ctx.tid; it < (int)kstride; it += ctx.nt) buf[it] = Kg[it];
+#endif
+  for (int it = ctx.tid; it < L.V * 7 * (NRED + 1); it += ctx.nt) {
+    const int a = it / (7 * (NRED + 1)), r = (it / (NRED + 1)) % 7, cc = it % (NRED + 1);
+    const bool active = i < L.N[a];
+    const double* T = W.TT + (size_t)(a * L.Nmax + (active ? i : 0)) * (NW * NRED + NW);
+    const double* src = cc < NRED ? T + (28 + r) * NRED + cc : T + NW * NRED + 28 + r;
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(fT + it)), "l"(src), "r"(active ? 8 : 0) : "memory");
+#else
+    fT[it] = active ? *src : 0.0;
+#endif
+  }
+}
+
 OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, double* RW, int* ok) {
   assume_scratch(W);
   const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V, nc = nX + 1;
-  const size_t pstride = (size_t)nX * nX + nX, kstride = ric_record_doubles(L);
+  const size_t pstride = (size_t)nX * nX + nX, kstride = ric_record_doubles(L), bstride = ric_fwd_buffer_doubles(L);
   RicWork R;
   ric_carve(R, L, RW);  // R.npt (free directions of every block) is still valid; the stage matrices P .. K are dead and serve as scratch
-  double* fb = R.P;
-  double* fT = fb + kstride;                 // [V][7][NRED + 1]
-  double* fU = fT + (size_t)V * 7 * (NRED + 1);  // [nUmax] compact controls of the stage
+  double* fb0 = R.P;
+  double* Xs = fb0 + 2 * bstride;   // [2][nX] state ping-pong
+  double* fU = Xs + 2 * nX;         // [nUmax] compact controls of the stage
   double* X = W.RX;
   double* U = W.RX + (size_t)(L.Nmax + 1) * nX;
+  ric_fwd_fetch(ctx, L, W, 0, fb0);
   if (ctx.tid == 0) {
     for (int a = 0; a < V; ++a)
-      for (int q = 0; q < NZ; ++q) X[7 * a + q] = -W.c[L.YINIT(a, q)];
+      for (int q = 0; q < NZ; ++q) Xs[7 * a + q] = -W.c[L.YINIT(a, q)];
     const double* P0 = W.RP;
     const double* p0 = P0 + nX * nX;
     double s = p0[idt];
-    for (int m = 0; m < idt; ++m) s += P0[idt * nX + m] * X[m];
+    for (int m = 0; m < idt; ++m) s += P0[idt * nX + m] * Xs[m];
     double piv = P0[idt * nX + idt];
     if (!(piv > PIVOT_TOL * fmax(1.0, fabs(p0[idt])))) {
       *ok = 0;
       piv = 1.0;
     }
-    X[idt] = -s / piv;
+    Xs[idt] = -s / piv;
+    for (int m = 0; m < nX; ++m) X[m] = Xs[m];
   }
-  cta_sync(ctx);
   for (int i = 0; i < L.Nmax; ++i) {
-    const double* Kg = W.RK + (size_t)i * kstride;
-    const double* Xi = X + (size_t)i * nX;
-    double* Ui = U + (size_t)i * nUmax;  // padded per-vehicle layout: NP slots per vehicle
-    double* Xn = X + (size_t)(i + 1) * nX;
+    double* buf = fb0 + (size_t)(i & 1) * bstride;
+    const double* fT = buf + kstride;
+    const double* Xi = Xs + (size_t)(i & 1) * nX;
+    double* Xn = Xs + (size_t)((i + 1) & 1) * nX;
+    ric_input_wait();
+    cta_sync(ctx);  // stage i's record has landed, Xi is complete, fU of the previous stage has been consumed
+    if (i + 1 < L.Nmax) ric_fwd_fetch(ctx, L, W, i + 1, fb0 + (size_t)((i + 1) & 1) * bstride);
     int nu = 0;
     for (int a = 0; a < V; ++a) nu += R.npt[a * L.Nmax + i];
-    // stage record and dynamics rows -> shared memory
-    for (int it = ctx.tid; it < nc * nUmax; it += ctx.nt)
-      if (it % nUmax < nu) fb[it] = Kg[it];
-    for (int it = ctx.tid; it < nu * nUmax; it += ctx.nt)
-      if (it % nUmax < it / nUmax) fb[nc * nUmax + it] = Kg[nc * nUmax + it];
-    for (int it = ctx.tid; it < V * 7 * (NRED + 1); it += ctx.nt) {
-      const int a = it / (7 * (NRED + 1)), r = (it / (NRED + 1)) % 7, cc = it % (NRED + 1);
-      double v = 0.0;
-      if (i < L.N[a]) {
-        const double* T = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
-        v = cc < NRED ? T[(28 + r) * NRED + cc] : T[NW * NRED + 28 + r];
-      }
-      fT[it] = v;
-    }
-    cta_sync(ctx);
-    const double* Lf = fb + (size_t)nc * nUmax;
+    const double* Lf = buf + (size_t)nc * nUmax;
 #if defined(__CUDA_ARCH__)
     if (nu <= 32) {
       if ((ctx.tid >> 5) == 0) {
         const int lane = ctx.tid & 31;
-        double t = 0.0;
+        double Lc[32];  // this lane's column of L (rows below the diagonal)
+#pragma unroll
+        for (int r = 1; r < 32; ++r) Lc[r] = (r < nu && lane < r) ? Lf[r * nUmax + lane] : 0.0;
+        double t = 0.0, t1 = 0.0;
         if (lane < nu) {
-          double t1 = 0.0;
-          t = fb[nX * nUmax + lane];
+          t = buf[nX * nUmax + lane];
           int c = 0;
-          for (; c + 1 < nX; c += 2) t += fb[c * nUmax + lane] * Xi[c], t1 += fb[(c + 1) * nUmax + lane] * Xi[c + 1];
-          if (c < nX) t += fb[c * nUmax + lane] * Xi[c];
+          for (; c + 1 < nX; c += 2) t += buf[c * nUmax + lane] * Xi[c], t1 += buf[(c + 1) * nUmax + lane] * Xi[c + 1];
+          if (c < nX) t += buf[c * nUmax + lane] * Xi[c];
           t += t1;
         }
-        for (int r = nu - 1; r > 0; --r) {   // L' u = t: u_r is final once the rows above it have been applied
-          const double ur = __shfl_sync(0xffffffffu, t, r);
-          if (lane < r) t -= Lf[r * nUmax + lane] * ur;
+#pragma unroll
+        for (int r = 31; r > 0; --r) {   // L' u = t: u_r is final once the rows above it have been applied
+          if (r < nu) {                  // warp-uniform
+            const double ur = __shfl_sync(0xffffffffu, t, r);
+            t = fma(-Lc[r], ur, t);
+          }
         }
         if (lane < nu) fU[lane] = t;
       }
     } else
 #endif
     {
-      // generic: t = Ks [x; 1] by all threads, then the back-substitution column by column
+      // generic: t = Ks [x; 1] by all threads, then the back-substitution row by row
       for (int u = ctx.tid; u < nu; u += ctx.nt) {
-        double t = fb[nX * nUmax + u];
-        for (int c = 0; c < nX; ++c) t += fb[c * nUmax + u] * Xi[c];
+        double t = buf[nX * nUmax + u];
+        for (int c = 0; c < nX; ++c) t += buf[c * nUmax + u] * Xi[c];
         fU[u] = t;
       }
       cta_sync(ctx);
@@ -1845,6 +1857,7 @@ OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, do
     }
     cta_sync(ctx);
     // compact index u -> (vehicle, slot), zero for the unused slots
+    double* Ui = U + (size_t)i * nUmax;  // padded per-vehicle layout: NP slots per vehicle
     for (int t = ctx.tid; t < V * NP; t += ctx.nt) {
       const int a = t / NP, j = t % NP;
       int off = 0;
@@ -1868,9 +1881,10 @@ OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, do
         }
       }
       Xn[r] = s;
+      X[(size_t)(i + 1) * nX + r] = s;
     }
-    cta_sync(ctx);
   }
+  cta_sync(ctx);
 }
 
 // ------------------------------------------------------------------------------------------------

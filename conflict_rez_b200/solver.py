@@ -87,6 +87,10 @@ EXPORTS = [
     "obca_dual_ws",
     "obca_joint_dual_ws",
     "obca_measure_dfma_peak",
+    "obca_interpolate",
+    "obca_mpc_ref_times",
+    "obca_plant_step",
+    "obca_shift_horizon",
     "obca_set_order",
     "obca_solve",
     "obca_get_solution",
@@ -129,6 +133,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.obca_dual_ws.argtypes = [vp, vp, vp, vp, vp]
     lib.obca_joint_dual_ws.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.obca_measure_dfma_peak.argtypes = [ctypes.c_int, _dp]
+    lib.obca_interpolate.argtypes = [ctypes.c_int, vp, vp, i32p, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.obca_mpc_ref_times.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp]
+    lib.obca_plant_step.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, vp, vp]
+    lib.obca_shift_horizon.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.obca_set_order.argtypes = [vp, vp, vp]
     lib.obca_solve.argtypes = [vp, vp]
     lib.obca_get_solution.argtypes = [vp] + [vp] * 7 + [vp]
@@ -186,6 +194,63 @@ def _ptr(t: Optional[torch.Tensor]):
 
 def _np_ptr(a: np.ndarray):
     return a.ctypes.data_as(_dp)
+
+
+class TrajectoryOps:
+    """Trajectory-side kernels around the solve (csrc/obca_traj.h): batched evaluation of collocation solutions
+    (``Vehicle.interpolate_states``, vehicle.py:722-829), the MPC reference window (``get_current_ref``, vehicle_follower.py:370-404),
+    the plant step (``simulator``, dynamic_model.py:61-93) and the one-step horizon shift (``_adv_onestep``).  All arrays are device
+    tensors (float64, contiguous) on ``device``; the kernels run on torch's current stream."""
+
+    def __init__(self, device="cuda:0", lib: Optional[ctypes.CDLL] = None):
+        self.lib = lib if lib is not None else load_library()
+        self.device = torch.device(device)
+        self.is_emulation = b"EMULATION" in self.lib.obca_version()
+        if self.device.type != "cuda" and not self.is_emulation:
+            raise RuntimeError("TrajectoryOps needs a CUDA device (no CPU fallback)")
+        self.index = (self.device.index or 0) if self.device.type == "cuda" else 0
+        from conflict_rez_b200.control.warmstart import radau_nodes
+
+        self._tau = np.ascontiguousarray(radau_nodes(5))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.device.type == "cuda" else None
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError("obca: " + self.lib.obca_last_error().decode())
+
+    def interpolate(self, z: torch.Tensor, dt: torch.Tensor, n_intervals, times: torch.Tensor) -> torch.Tensor:
+        """z (B,V,Mmax,7), dt (B) or (B,V), n_intervals (V) ints, times (T) or (B,V,T) -> (B,V,T,7) = x y psi v delta a w."""
+        B, V, Mmax, _ = z.shape
+        per = times.dim() == 3
+        T = times.shape[-1]
+        out = torch.empty((B, V, T, 7), dtype=torch.float64, device=z.device)
+        ni = (ctypes.c_int32 * V)(*[int(n) for n in n_intervals])
+        self._check(self.lib.obca_interpolate(self.index, _ptr(z.contiguous()), _ptr(dt.contiguous()), ni, _np_ptr(self._tau), B, V, Mmax,
+                                              _ptr(times.contiguous()), T, int(per), int(dt.dim() == 2), _ptr(out), self._stream()))
+        return out
+
+    def mpc_ref_times(self, grid: torch.Tensor, clock: torch.Tensor, N: int, dt_mpc: float) -> torch.Tensor:
+        """grid (B,V,3) = (t_first, t_last, n_ref) of each dense reference time grid, clock (B,V) -> (B,V,N) sample times."""
+        B, V, _ = grid.shape
+        out = torch.empty((B, V, N), dtype=torch.float64, device=grid.device)
+        self._check(self.lib.obca_mpc_ref_times(self.index, _ptr(grid.contiguous()), _ptr(clock.contiguous()), B, V, N, float(dt_mpc), _ptr(out), self._stream()))
+        return out
+
+    def plant_step(self, state: torch.Tensor, u: torch.Tensor, dt: float, wb: float, substeps: int = 100) -> torch.Tensor:
+        """state (B,5), u (B,2) -> state after dt under constant input."""
+        out = torch.empty_like(state)
+        self._check(self.lib.obca_plant_step(self.index, _ptr(state.contiguous()), _ptr(u.contiguous()), state.shape[0], float(dt), float(wb), int(substeps), _ptr(out), self._stream()))
+        return out
+
+    def shift_horizon(self, a: torch.Tensor) -> torch.Tensor:
+        """(B,N,...) -> shifted by one step along N with the last value held (``_adv_onestep``)."""
+        B, N = a.shape[:2]
+        W = int(np.prod(a.shape[2:])) if a.dim() > 2 else 1
+        out = torch.empty_like(a)
+        self._check(self.lib.obca_shift_horizon(self.index, _ptr(a.contiguous()), B, N, W, _ptr(out), self._stream()))
+        return out
 
 
 class ObcaSolver:

@@ -117,6 +117,25 @@ int obca_set_mpc_params(ObcaHandle* h, const double* cur, const double* ref, con
 int obca_dual_ws(ObcaHandle* h, const double* z, double* lam, double* mu, void* stream);
 int obca_joint_dual_ws(ObcaHandle* h, const double* z, double* pair_lam, double* pair_mu, double* pair_s, void* stream);
 
+/* ---- trajectory-side kernels (csrc/obca_traj.h); no handle needed, all pointers dev unless noted ------------------------ */
+/* replaces Vehicle.get_interpolator / interpolate_states (confrez/control/vehicle.py:722-829), one thread per sample:
+ * z (B,V,Mmax,7) collocation solution, dt (B) -- or (B,V) when dt_per_vehicle != 0 (separately planned vehicles) --,
+ * n_intervals (V, HOST), tau (K+1 = 6, HOST) collocation nodes on [0,1];
+ * times (T) shared by all vehicles, or (B,V,T) when per_vehicle_times != 0; out (B,V,T,7) = x y psi v delta a w.
+ * States: degree-K Lagrange polynomial of the interval that contains t, final state held beyond the horizon;
+ * inputs: piecewise constant between the collocation nodes (ca.pw_const semantics). */
+int obca_interpolate(int device, const double* z, const double* dt, const int32_t* n_intervals, const double* tau, int B, int V, int Mmax,
+                     const double* times, int T, int per_vehicle_times, int dt_per_vehicle, double* out, void* stream);
+/* replaces the time lookup of VehicleFollower.get_current_ref (confrez/control/vehicle_follower.py:370-404): for every vehicle
+ * (B,V) the N sample times  t_ref[argmin |t_ref - clock|] + k * dt_mpc  of the dense reference grid linspace(t_first, t_last, n_ref);
+ * grid (B,V,3) = t_first, t_last, n_ref (as double), clock (B,V) -> times (B,V,N) (feed to obca_interpolate, per_vehicle_times = 1) */
+int obca_mpc_ref_times(int device, const double* grid, const double* clock, int B, int V, int N, double dt_mpc, double* times, void* stream);
+/* replaces simulator (confrez/control/dynamic_model.py:61-93): state (B,5), input (B,2) -> next (B,5) after dt under constant input
+ * (fixed-step RK4, `substeps` sub-steps; the reference integrates the same ODE with IDAS) */
+int obca_plant_step(int device, const double* state, const double* input, int B, double dt, double wb, int substeps, double* next, void* stream);
+/* replaces VehicleFollower._adv_onestep (vehicle_follower.py:413-426) for a (B,N,W) array: out[b][n] = in[b][min(n+1, N-1)] */
+int obca_shift_horizon(int device, const double* in, int B, int N, int W, double* out, void* stream);
+
 /* DFMA micro-benchmark: sustained FP64 FMA throughput of `device` in TFLOP/s (the FP64 roofline denominator of bench.py;
  * SURVEY.md 8d asks for a measured figure next to the data-sheet 37 TFLOP/s) */
 int obca_measure_dfma_peak(int device, double* tflops);

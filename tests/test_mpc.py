@@ -180,3 +180,38 @@ def test_infeasible_neighbour_is_reported_not_adopted(backend, mpc_case):
     if res.status[0] == -6:
         assert res.elastic[0] > 1e-2 and res.cviol[0] >= res.elastic[0]
     sv.close()
+
+
+def test_device_resident_loop_reproduces_the_host_loop(backend, strategy_file):
+    """DeviceMpcLoop (reference window, neighbour shift, warm-start shift, solve, fallback, plant step all as kernels on one
+    stream) follows the same closed-loop trajectories as MultiDistributedFollower.solve, which does those steps in numpy."""
+    from conflict_rez_b200.control.vehicle_follower import DeviceMpcLoop, MultiDistributedFollower
+
+    lib, dev = backend
+    agents = ["vehicle_1", "vehicle_2"]
+    heads = {"vehicle_1": 3 * np.pi / 2, "vehicle_2": np.pi}
+
+    def make():
+        np.random.seed(0)  # the first-step duals are 0.1 * rand (vehicle_follower.py:401-402)
+        m = MultiDistributedFollower(strategy_file, {a: True for a in agents}, {a: {} for a in agents}, {a: VehicleState() for a in agents}, heads, device=dev, lib=lib)
+        m.setup_multi_vehicles()
+        return m
+
+    steps = 6
+    host = make()
+    host.solve(num_iter=steps)
+    loop = DeviceMpcLoop(make())
+    loop.run(steps)
+    out = loop.export()
+    assert out["traj"].shape == (steps, 2, 7) and (out["status"] >= 0).all()
+    for b, v in enumerate(host.vehicles):
+        ft = v.final_traj
+        ref = np.stack([ft.x[1:], ft.y[1:], ft.psi[1:], ft.v[1:], ft.u_steer[1:], ft.u_a[1:], ft.u_steer_dot[1:]], axis=1)
+        assert np.abs(out["traj"][:, b] - ref).max() <= 1e-8
+        assert abs(out["clock"][b] - v.state.t) <= 1e-12
+    assert out["failed_solves"] == host.failed_solves
+    if dev != "cpu":  # the same loop replayed from a CUDA graph: no host work between the steps
+        g = DeviceMpcLoop(make())
+        per_step = g.run(steps, graph=True)
+        assert per_step > 0
+        assert np.abs(g.export()["state"] - out["state"]).max() <= 1e-8
