@@ -234,13 +234,13 @@ struct Scratch {
   // best "acceptable" iterate so far (IPOPT StoreAcceptablePoint): x, zL, zU, y
   double *bx, *bzL, *bzU, *by;
   // structured solve
-  double* XO;   // [V][Mv][O][48]   obstacle block solves: 12 x (3 coupling cols + 1 rhs)
-  double* XP;   // [P][Mv][112]     pair block solves: 16 x (6 + 1)
-  double* PH;   // [P][Mv][27]      pair Schur complement on (pose_a, pose_b): 21 sym + 6 grad
-  double* PG;   // [P][2][3][Mv]    pair contributions to the pose gradient (gl)
-  double* HN;   // [V][Mv][28]      node Hessian (sym packed)
-  double* GN;   // [V][Mv][7]       node gradient
-  double* HD;   // [V][Mv][7]       node x dt cross Hessian
+  double* XO;   // [V][O][48][Mv]   obstacle block solves: 12 x (3 coupling cols + 1 rhs), node minor
+  double* XP;   // [P][112][Mv]     pair block solves: 16 x (6 + 1), node minor
+  double* PH;   // [P][27][Mv]      pair Schur complement on (pose_a, pose_b): 21 sym + 6 grad, node minor
+  double* PG;   // [P][6][Mv]       pair contributions to the pose gradient (gl), node minor
+  double* HN;   // [V][28][Mv]      node Hessian (sym packed), node minor
+  double* GN;   // [V][7][Mv]       node gradient, node minor
+  double* HD;   // [V][7][Mv]       node x dt cross Hessian, node minor
   double* TT;   // [V][Nmax][35*13 + 35]   reduced-coordinate map T and particular solution s0
   double* QR;   // [V][Nmax][QRSZ]   Householder factors, tau, pivots, dropped-row records
   double* EM;   // [2][V][Nmax][EXSZ] implied rows emitted to the previous interval (double-buffered by pass)
@@ -653,13 +653,14 @@ OBCA_HDN void eval_pairs(const Ctx& ctx, const Lay& L, const Stat& S, const doub
     // pose gradients: d/dt_a = -yd R_a ua ; d/dpsi_a = -yd t_a' R_a' ua + ye1' R_a' ua   (R' = dR/dpsi here)
     double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
     double dRub[2] = {-b.s * B.ub[0] - b.c * B.ub[1], b.c * B.ub[0] - b.s * B.ub[1]};
-    double* g = PG + (size_t)(p * L.Mv + n) * 6;
+    double* g = PG + (size_t)p * 6 * L.Mv + n;  // [P][6][Mv], node minor
+    const int gs = L.Mv;
     g[0] = -yd * B.Rua[0];
-    g[1] = -yd * B.Rua[1];
-    g[2] = -yd * (a.x * dRua[0] + a.y * dRua[1]) + ye1[0] * dRua[0] + ye1[1] * dRua[1];
-    g[3] = -yd * B.Rub[0];
-    g[4] = -yd * B.Rub[1];
-    g[5] = -yd * (b.x * dRub[0] + b.y * dRub[1]) + ye2[0] * dRub[0] + ye2[1] * dRub[1];
+    g[gs] = -yd * B.Rua[1];
+    g[2 * gs] = -yd * (a.x * dRua[0] + a.y * dRua[1]) + ye1[0] * dRua[0] + ye1[1] * dRua[1];
+    g[3 * gs] = -yd * B.Rub[0];
+    g[4 * gs] = -yd * B.Rub[1];
+    g[5 * gs] = -yd * (b.x * dRub[0] + b.y * dRub[1]) + ye2[0] * dRub[0] + ye2[1] * dRub[1];
   }
 }
 
@@ -783,9 +784,10 @@ OBCA_HDN void eval_nodes(const Ctx& ctx, const Lay& L, const Stat& S, const doub
     if (y) {
       for (int pp = 0; pp < L.P; ++pp) {
         if (n >= L.Mp[pp]) continue;
-        const double* pg = PG + (size_t)(pp * L.Mv + n) * 6;
-        if (L.pa[pp] == a) g[0] += pg[0], g[1] += pg[1], g[2] += pg[2];
-        if (L.pb[pp] == a) g[0] += pg[3], g[1] += pg[4], g[2] += pg[5];
+        const double* pg = PG + (size_t)pp * 6 * L.Mv + n;
+        const int gs = L.Mv;
+        if (L.pa[pp] == a) g[0] += pg[0], g[1] += pg[gs], g[2] += pg[2 * gs];
+        if (L.pb[pp] == a) g[0] += pg[3 * gs], g[1] += pg[4 * gs], g[2] += pg[5 * gs];
       }
       for (int qq = 0; qq < NZ; ++qq) gl[L.Z(a, qq, n)] = g[qq];
     }

@@ -97,7 +97,9 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
       cb[2][r] = -yd * (dbx * b.x + dby * b.y) + S.G[r][0] * dRteb[0] + S.G[r][1] * dRteb[1];
     }
     const double c8[6] = {-B.Rua[0], -B.Rua[1], -(a.x * dRua[0] + a.y * dRua[1]), -B.Rub[0], -B.Rub[1], -(b.x * dRub[0] + b.y * dRub[1])};
-    double* xp = W.XP + (size_t)(p * L.Mv + n) * 112;
+    // block solves, node minor ([P][112][Mv]): the threads of a warp own consecutive nodes, every store / load is one coalesced line
+    double* xp = W.XP + (size_t)p * 112 * L.Mv + n;
+    const int xs = L.Mv;
     double CX[6][7];  // C' X
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -143,11 +145,11 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
       for (int r = 0; r < 4; ++r) {
         xl[r] = (bl[r] - (-B.ba[r] * dy[0] + ea[r] * dy[1] + fa[r] * dy[2])) * sl[r];
         xm[r] = (bm[r] - (-B.bb[r] * dy[0] + eb[r] * dy[3] + fb[r] * dy[4])) * smu[r];
-        xp[r * 7 + k] = xl[r], xp[(4 + r) * 7 + k] = xm[r];
+        xp[(r * 7 + k) * xs] = xl[r], xp[((4 + r) * 7 + k) * xs] = xm[r];
       }
 #pragma unroll
-      for (int r = 0; r < 6; ++r) xp[(8 + r) * 7 + k] = dy[r];
-      xp[14 * 7 + k] = ds0, xp[15 * 7 + k] = ds1;
+      for (int r = 0; r < 6; ++r) xp[((8 + r) * 7 + k) * xs] = dy[r];
+      xp[(14 * 7 + k) * xs] = ds0, xp[(15 * 7 + k) * xs] = ds1;
       // row r of C' X[:, k]
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
@@ -160,7 +162,7 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
       CX[5][k] += dRub[0] * dy[3] + dRub[1] * dy[4];
     }
     // Schur complement on (pose_a, pose_b): direct Hessian - C' Xc ; gradient C' Xr
-    double* ph = W.PH + (size_t)(p * L.Mv + n) * 27;
+    double* ph = W.PH + (size_t)p * 27 * L.Mv + n;  // [P][27][Mv], node minor
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
 #pragma unroll
@@ -172,9 +174,9 @@ OBCA_HD void pair_block_eliminate(const Lay& L, const Stat& S, const Scratch& W,
         if (r == 5 && q == 3) h = -yd * dRub[0];
         if (r == 5 && q == 4) h = -yd * dRub[1];
         if (r == 5 && q == 5) h = yd * (b.x * B.Rub[0] + b.y * B.Rub[1]) - (ye2[0] * B.Rub[0] + ye2[1] * B.Rub[1]);
-        ph[sym(r, q)] = h - CX[r][q];
+        ph[sym(r, q) * xs] = h - CX[r][q];
       }
-      ph[21 + r] = CX[r][6];
+      ph[(21 + r) * xs] = CX[r][6];
     }
   }
 }
@@ -206,7 +208,8 @@ OBCA_HD void obs_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, 
       double y3p = y3 > 0 ? y3 : 0.0;  // local convexification: exact at KKT points (y3 >= 0)
       // Block elimination in registers: lam (H = diag + 2 y3+ A A'), mu (diagonal), then the 4 x 4 Schur complement
       //   S = D + Jl Hl^-1 Jl' + Jm Dm^-1 Jm'  on (y1, y2, y3); 4 right-hand sides (3 pose couplings + residual).
-      double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 48;
+      double* xo = W.XO + (size_t)(a * L.O + j) * 48 * L.Mv + n;  // node minor ([V][O][48][Mv]): coalesced across the threads of a warp
+      const int xs = L.Mv;
       double CX[3][4];  // C' X
       double dRy[2] = {-p.s * y2[0] - p.c * y2[1], p.c * y2[0] - p.s * y2[1]};   // (dR/dpsi) y2
       double dRtu[2] = {-p.s * B.u[0] + p.c * B.u[1], -p.c * B.u[0] - p.s * B.u[1]};  // (dR'/dpsi) u
@@ -287,9 +290,9 @@ OBCA_HD void obs_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, 
           for (int i2 = 0; i2 < 4; ++i2) dl -= Wl[i2][r] * ry[i2];
           xl[r] = dl;
           // block solves go straight to global memory (back-substitution); no per-thread local array
-          xo[r * 4 + k] = dl;
-          xo[(4 + r) * 4 + k] = ((k == 3 ? bm[r] : 0.0) - jm) * sm[r];
-          xo[(8 + r) * 4 + k] = ry[r];
+          xo[(r * 4 + k) * xs] = dl;
+          xo[((4 + r) * 4 + k) * xs] = ((k == 3 ? bm[r] : 0.0) - jm) * sm[r];
+          xo[((8 + r) * 4 + k) * xs] = ry[r];
         }
         // column k of C'X: the lam rows carry Cl, the y rows carry Cy (the mu rows do not couple to the pose)
 #pragma unroll
@@ -311,9 +314,10 @@ OBCA_HD void obs_block_eliminate(const Lay& L, const Stat& S, const Scratch& W, 
 }
 
 OBCA_HD void obs_block_backsub(const Lay& L, const Scratch& W, int a, int n, int j, const double* dp) {
-  const double* xo = W.XO + ((size_t)(a * L.Mv + n) * L.O + j) * 48;
+  const double* xo = W.XO + (size_t)(a * L.O + j) * 48 * L.Mv + n;
+  const int xs = L.Mv;
   double r[12];
-  for (int m = 0; m < 12; ++m) r[m] = xo[m * 4 + 3] - xo[m * 4 + 0] * dp[0] - xo[m * 4 + 1] * dp[1] - xo[m * 4 + 2] * dp[2];
+  for (int m = 0; m < 12; ++m) r[m] = xo[(m * 4 + 3) * xs] - xo[(m * 4 + 0) * xs] * dp[0] - xo[(m * 4 + 1) * xs] * dp[1] - xo[(m * 4 + 2) * xs] * dp[2];
   for (int q = 0; q < 4; ++q) {
     W.dx[L.LAM(a, j, q, n)] = r[q];
     W.dx[L.MU(a, j, q, n)] = r[4 + q];
@@ -325,11 +329,12 @@ OBCA_HD void obs_block_backsub(const Lay& L, const Scratch& W, int a, int n, int
 }
 
 OBCA_HD void pair_block_backsub(const Lay& L, const Scratch& W, int p, int n, const double* dp) {
-  const double* xp = W.XP + (size_t)(p * L.Mv + n) * 112;
+  const double* xp = W.XP + (size_t)p * 112 * L.Mv + n;
+  const int xs = L.Mv;
   double r[16];
   for (int m = 0; m < 16; ++m) {
-    double s = xp[m * 7 + 6];
-    for (int q = 0; q < 6; ++q) s -= xp[m * 7 + q] * dp[q];
+    double s = xp[(m * 7 + 6) * xs];
+    for (int q = 0; q < 6; ++q) s -= xp[(m * 7 + q) * xs] * dp[q];
     r[m] = s;
   }
   for (int q = 0; q < 4; ++q) W.dx[L.PL(p, q, n)] = r[q], W.dx[L.PM(p, q, n)] = r[4 + q];
@@ -408,19 +413,20 @@ OBCA_HDN void node_assemble(const Ctx& ctx, const Lay& L, const Stat& S, const S
     // ---- pair Schur complements (diagonal blocks and gradients)
     for (int pp = 0; pp < L.P; ++pp) {
       if (n >= L.Mp[pp]) continue;
-      const double* ph = W.PH + (size_t)(pp * L.Mv + n) * 27;
+      const double* ph = W.PH + (size_t)pp * 27 * L.Mv + n;
       int off = L.pa[pp] == a ? 0 : (L.pb[pp] == a ? 3 : -1);
       if (off < 0) continue;
       for (int r = 0; r < 3; ++r) {
-        for (int m = 0; m <= r; ++m) H[sym(r, m)] += ph[sym(off + r, off + m)];
-        g[r] += ph[21 + off + r];
+        for (int m = 0; m <= r; ++m) H[sym(r, m)] += ph[sym(off + r, off + m) * L.Mv];
+        g[r] += ph[(21 + off + r) * L.Mv];
       }
     }
-    double* hn = W.HN + (size_t)(a * L.Mv + n) * 28;
-    double* gn = W.GN + (size_t)(a * L.Mv + n) * 7;
-    double* hdn = W.HD + (size_t)(a * L.Mv + n) * 7;
-    for (int m = 0; m < 28; ++m) hn[m] = H[m];
-    for (int m = 0; m < NZ; ++m) gn[m] = g[m], hdn[m] = hd[m];
+    // node minor ([V][28][Mv], [V][7][Mv]): the threads of a warp own consecutive nodes, every store is one coalesced line
+    double* hn = W.HN + (size_t)a * 28 * L.Mv + n;
+    double* gn = W.GN + (size_t)a * 7 * L.Mv + n;
+    double* hdn = W.HD + (size_t)a * 7 * L.Mv + n;
+    for (int m = 0; m < 28; ++m) hn[(size_t)m * L.Mv] = H[m];
+    for (int m = 0; m < NZ; ++m) gn[(size_t)m * L.Mv] = g[m], hdn[(size_t)m * L.Mv] = hd[m];
   }
   double hdt = cta_sum(ctx, hdt_part);
   for (int a = 0; a < L.V; ++a) hdt += 2.0 * L.N[a] * L.N[a];
@@ -539,8 +545,8 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     for (int q = lane; q < 2 * NC; q += 32) bu[q] = 0;
     for (int q = lane; q < NS; q += 32) {
       zb[q] = x[L.Z(a, q % NZ, n0 + q / NZ)];
-      hdv[q] = W.HD[(size_t)(a * L.Mv + n0 + q / NZ) * 7 + q % NZ];
-      gnv[q] = W.GN[(size_t)(a * L.Mv + n0 + q / NZ) * 7 + q % NZ];
+      hdv[q] = W.HD[((size_t)a * 7 + q % NZ) * L.Mv + n0 + q / NZ];
+      gnv[q] = W.GN[((size_t)a * 7 + q % NZ) * L.Mv + n0 + q / NZ];
     }
   }
   OBCA_WARP_SYNC();
@@ -894,7 +900,7 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   double* hn = hs0 + NS;              // [6][28]
   double* hdT = hn + NK * 28;         // [NRED] + hds0
   OBCA_LANES(lane) {
-    for (int q = lane; q < NK * 28; q += 32) hn[q] = W.HN[(size_t)(a * L.Mv + n0) * 28 + q];
+    for (int q = lane; q < NK * 28; q += 32) hn[(q % NK) * 28 + q / NK] = W.HN[((size_t)a * 28 + q / NK) * L.Mv + n0 + q % NK];
   }
   OBCA_WARP_SYNC();
   OBCA_LANES(lane) {
@@ -1050,7 +1056,7 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, dou
       }
       for (int e = lane; e < NK * 9; e += 32) {
         int k = e / 9, r = (e / 3) % 3, m = e % 3;
-        hc[e] = W.PH[(size_t)(p * L.Mv + i * NK + k) * 27 + sym(3 + m, r)];
+        hc[e] = W.PH[((size_t)p * 27 + sym(3 + m, r)) * L.Mv + i * NK + k];
       }
     }
     OBCA_WARP_SYNC();
@@ -1922,30 +1928,31 @@ OBCA_HDN void node_residual(const Ctx& ctx, const Lay& L, const Scratch& W) {
   for (int it = ctx.tid; it < L.V * L.Mv; it += ctx.nt) {
     int a = it / L.Mv, n = it % L.Mv;
     if (n >= L.M[a]) continue;
-    const double* hn = W.HN + (size_t)(a * L.Mv + n) * 28;
-    double* gn = W.GN + (size_t)(a * L.Mv + n) * 7;
-    const double* hd = W.HD + (size_t)(a * L.Mv + n) * 7;
+    const double* hn = W.HN + (size_t)a * 28 * L.Mv + n;
+    double* gn = W.GN + (size_t)a * 7 * L.Mv + n;
+    const double* hd = W.HD + (size_t)a * 7 * L.Mv + n;
+    const size_t ns = L.Mv;
     double dz[NZ], out[NZ];
     for (int q = 0; q < NZ; ++q) dz[q] = W.dx[L.Z(a, q, n)];
     for (int r = 0; r < NZ; ++r) {
-      double s = gn[r] + hd[r] * ddt;
-      for (int m = 0; m < NZ; ++m) s += hn[sym(r, m)] * dz[m];
+      double s = gn[r * ns] + hd[r * ns] * ddt;
+      for (int m = 0; m < NZ; ++m) s += hn[sym(r, m) * ns] * dz[m];
       out[r] = s;
     }
     for (int p = 0; p < L.P; ++p) {
       if (n >= L.Mp[p]) continue;
-      const double* ph = W.PH + (size_t)(p * L.Mv + n) * 27;
+      const double* ph = W.PH + (size_t)p * 27 * L.Mv + n;
       if (L.pa[p] == a) {
         int b = L.pb[p];
         for (int r = 0; r < 3; ++r)
-          for (int m = 0; m < 3; ++m) out[r] += ph[sym(3 + m, r)] * W.dx[L.Z(b, m, n)];
+          for (int m = 0; m < 3; ++m) out[r] += ph[sym(3 + m, r) * L.Mv] * W.dx[L.Z(b, m, n)];
       } else if (L.pb[p] == a) {
         int b = L.pa[p];
         for (int r = 0; r < 3; ++r)
-          for (int m = 0; m < 3; ++m) out[r] += ph[sym(3 + r, m)] * W.dx[L.Z(b, m, n)];
+          for (int m = 0; m < 3; ++m) out[r] += ph[sym(3 + r, m) * L.Mv] * W.dx[L.Z(b, m, n)];
       }
     }
-    for (int q = 0; q < NZ; ++q) gn[q] = out[q];
+    for (int q = 0; q < NZ; ++q) gn[q * ns] = out[q];
   }
 }
 
@@ -2001,7 +2008,7 @@ OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, c
     const double* piv = QRm + QR_PIV;
     int rk = (int)QRm[QR_META], nr = (int)QRm[QR_META + 1];
     double v[NW], vt[NU2], dyr[NC];
-    for (int r = 0; r < NW; ++r) v[r] = -W.GN[(size_t)(a * L.Mv + n0 + 1 + r / NZ) * 7 + r % NZ];
+    for (int r = 0; r < NW; ++r) v[r] = -W.GN[((size_t)a * 7 + r % NZ) * L.Mv + n0 + 1 + r / NZ];
     if (i < L.N[a] - 1)
       for (int q = 0; q < NZ; ++q) v[28 + q] -= W.dy[L.YCONT(a, q, i + 1)];
     // (1) control equations  -y_(k,c) + sum beta y = v_(a_k | w_k)  substituted into the (v, delta) equations
@@ -2075,7 +2082,7 @@ OBCA_HDN void recover_multipliers(const Ctx& ctx, const Lay& L, const Stat& S, c
       gy[4] -= dyr[2] * vv * sec2 / S.wb;
       gy[5] -= dyr[3];
       gy[6] -= dyr[4];
-      for (int q = 0; q < NZ; ++q) W.dy[L.YINIT(a, q)] = -W.GN[(size_t)(a * L.Mv) * 7 + q] - gy[q];
+      for (int q = 0; q < NZ; ++q) W.dy[L.YINIT(a, q)] = -W.GN[((size_t)a * 7 + q) * L.Mv] - gy[q];
     }
   }
   cta_sync(ctx);

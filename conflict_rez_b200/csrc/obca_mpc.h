@@ -285,10 +285,10 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
         gl[L.PSN(o, n)] = -yn;
         gl[L.PEL(o, n)] = S.rho + yd;
         double dRua[2] = {-a.s * B.ua[0] - a.c * B.ua[1], a.c * B.ua[0] - a.s * B.ua[1]};
-        double* g = PG + (size_t)(o * L.Mv + n) * 6;
+        double* g = PG + (size_t)o * 6 * L.Mv + n;
         g[0] = -yd * B.Rua[0];
-        g[1] = -yd * B.Rua[1];
-        g[2] = -yd * (a.x * dRua[0] + a.y * dRua[1]) + ye1[0] * dRua[0] + ye1[1] * dRua[1];
+        g[L.Mv] = -yd * B.Rua[1];
+        g[2 * L.Mv] = -yd * (a.x * dRua[0] + a.y * dRua[1]) + ye1[0] * dRua[0] + ye1[1] * dRua[1];
       } else if (unit < uPair + uObs) {
         const int it = (unit - uPair) * 32 + ln;
         if (it >= nObs) continue;
@@ -366,8 +366,8 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
       g[0] += og[0], g[1] += og[1], g[2] += og[2];
     }
     for (int o = 0; o < L.P; ++o) {
-      const double* pg = PG + (size_t)(o * L.Mv + n) * 6;
-      g[0] += pg[0], g[1] += pg[1], g[2] += pg[2];
+      const double* pg = PG + (size_t)o * 6 * L.Mv + n;
+      g[0] += pg[0], g[1] += pg[L.Mv], g[2] += pg[2 * L.Mv];
     }
     for (int q = 0; q < NZ; ++q) gl[L.Z(0, q, n)] = g[q];
   }
@@ -488,10 +488,10 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
       for (int q = 0; q < 3; ++q) g[q] += ob[6 + q];
     }
     for (int o = 0; o < L.P; ++o) {
-      const double* ph = W.PH + (size_t)(o * L.Mv + n) * 27;
+      const double* ph = W.PH + (size_t)o * 27 * L.Mv + n;
       for (int r = 0; r < 3; ++r) {
-        for (int m = 0; m <= r; ++m) H[sym(r, m)] += ph[sym(r, m)];
-        g[r] += ph[21 + r];
+        for (int m = 0; m <= r; ++m) H[sym(r, m)] += ph[sym(r, m) * L.Mv];
+        g[r] += ph[(21 + r) * L.Mv];
       }
     }
     for (int q = 0; q < 28; ++q) HN[(size_t)n * 28 + q] = H[q];

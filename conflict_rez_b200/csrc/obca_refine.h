@@ -82,8 +82,9 @@ OBCA_HDN void apply_pairs(const Ctx& ctx, const Lay& L, const Stat& S, const Scr
     r2[L.YPAIR(p, 3, n)] = je2[0] - DELTA_C_LOCAL * dyv[3];
     r2[L.YPAIR(p, 4, n)] = je2[1] - DELTA_C_LOCAL * dyv[4];
     r2[L.YPAIR(p, 5, n)] = jn - DELTA_C_LOCAL * dyv[5];
-    double* g = W.PG + (size_t)(p * L.Mv + n) * 6;
-    g[0] = ga[0], g[1] = ga[1], g[2] = ga[2], g[3] = gb[0], g[4] = gb[1], g[5] = gb[2];
+    double* g = W.PG + (size_t)p * 6 * L.Mv + n;
+    const int gs = L.Mv;
+    g[0] = ga[0], g[gs] = ga[1], g[2 * gs] = ga[2], g[3 * gs] = gb[0], g[4 * gs] = gb[1], g[5 * gs] = gb[2];
   }
 }
 
@@ -214,9 +215,10 @@ OBCA_HDN void apply_nodes(const Ctx& ctx, const Lay& L, const Stat& S, const Scr
     }
     for (int pp = 0; pp < L.P; ++pp) {
       if (n >= L.Mp[pp]) continue;
-      const double* pg = W.PG + (size_t)(pp * L.Mv + n) * 6;
-      if (L.pa[pp] == a) g[0] += pg[0], g[1] += pg[1], g[2] += pg[2];
-      if (L.pb[pp] == a) g[0] += pg[3], g[1] += pg[4], g[2] += pg[5];
+      const double* pg = W.PG + (size_t)pp * 6 * L.Mv + n;
+      const int gs = L.Mv;
+      if (L.pa[pp] == a) g[0] += pg[0], g[1] += pg[gs], g[2] += pg[2 * gs];
+      if (L.pb[pp] == a) g[0] += pg[3 * gs], g[1] += pg[4 * gs], g[2] += pg[5 * gs];
     }
     for (int q = 0; q < NZ; ++q) r1[L.Z(a, q, n)] = g[q];
   }
