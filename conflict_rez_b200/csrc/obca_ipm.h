@@ -263,28 +263,36 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
     double s_log = 0, s_gap = 0;  // barrier pieces: phi = f + mu (-sum log gap + kappa_d sum one-sided gap)
     {
       const double* const src[4] = {W.x, W.zL, W.zU, W.gl};
-      flat_pass_b<4>(ctx, st, bc, src, L.nx, [&](int, const double* v, double lo, double hi) {
+      flat_pass_b<4>(ctx, st, bc, src, L.nx, [&](int q, const double* v, double lo, double hi) {
         const double xv = v[0], zl = v[1], zu = v[2], gq = v[3];
         e_du = fmax(e_du, fabs(gq - zl + zu));
         const bool hl = lo > -INFINITY, hu = hi < INFINITY;
+        // Sigma and the barrier gradient for the CURRENT mu and delta_w = 0 ride along (same inputs): the separate pass is only
+        // needed when mu changes below or the inertia correction raises delta_w -- a handful of iterations per solve
+        double sg = 0.0, gph = gq;
         if (hl) {
-          const double gp = xv - lo, pr = gp * zl;
+          const double gp = xv - lo, pr = gp * zl, iL = rcp_pos(gp);
           cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
           s_z += zl;
+          sg += zl * iL, gph -= mu * iL;
+          if (!hu) gph += o.kappa_d * mu;
           if (!bar_valid) {
             s_log -= log(gp);
             if (!hu) s_gap += gp;
           }
         }
         if (hu) {
-          const double gp = hi - xv, pr = gp * zu;
+          const double gp = hi - xv, pr = gp * zu, iU = rcp_pos(gp);
           cmax0 = fmax(cmax0, pr), cmaxmu_lo = fmin(cmaxmu_lo, pr), cmaxmu_hi = fmax(cmaxmu_hi, pr);
           s_z += zu;
+          sg += zu * iU, gph += mu * iU;
+          if (!hl) gph -= o.kappa_d * mu;
           if (!bar_valid) {
             s_log -= log(gp);
             if (!hl) s_gap += gp;
           }
         }
+        W.sig[q] = sg, W.gphi[q] = gph;
       });
       prof_mark(ctx, 21);
     }
@@ -341,6 +349,7 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
       break;
     }
     // ---- barrier parameter update
+    bool sig_ready = true;  // W.sig / W.gphi from the error pass are valid for (mu, delta_w = 0)
     for (;;) {
       double cmu = fmax(fabs(pr_lo - mu), fabs(pr_hi - mu));
       double Emu = fmax(fmax(dual_inf / s_d, cviol), cmu / s_c);
@@ -348,6 +357,7 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
         mu = fmax(mu_min, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
         if (ctx.tid == 0) sh->filt_n = 0;
         force_mu = false;
+        sig_ready = false;
       } else
         break;
     }
@@ -360,7 +370,7 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
     double dw = 0.0;
     bool first = true, have = false;
     for (;;) {
-      {
+      if (!sig_ready) {
         const double* const src[4] = {W.x, W.zL, W.zU, W.gl};
         flat_pass_b<4>(ctx, st, bc, src, L.nx, [&](int q, const double* v, double lo, double hi) {
           const double xv = v[0], zl = v[1], zu = v[2];
@@ -382,6 +392,7 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
         });
       prof_mark(ctx, 22);
       }
+      sig_ready = false;  // any further trial of this iteration changes delta_w
       cta_sync(ctx);
       if (model_kkt<MODE>(ctx, L, S, W, RW, &sh->ok)) {
         have = true;
@@ -409,7 +420,7 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
       const double* const src[5] = {W.x, W.zL, W.zU, W.gphi, W.dx};
       flat_pass_b<5>(ctx, st, bc, src, L.nx, [&](int, const double* v, double lo, double hi) {
         const double xv = v[0], zl = v[1], zu = v[2], d = v[4];
-        rel = fmax(rel, fabs(d) / (1.0 + fabs(xv)));
+        rel = fmax(rel, fabs(d) * rcp_pos(1.0 + fabs(xv)));
         if (lo > -INFINITY) {
           const double ig = rcp_pos(xv - lo);
           const double dz = (mu - zl * d) * ig - zl;
@@ -494,8 +505,8 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
       int bad = 0;
       {
         const double* const src[2] = {W.x, W.dx};
-        // sum of log(gap) as log of products: the gaps of four consecutive elements of a thread (up to 8 factors, each within
-        // [1e-12, 1e2]) are multiplied and one log is taken for the group; all lanes flush at the same elements
+        // sum of log(gap) as log of products: a thread multiplies the gaps of its elements (each within [1e-20, 1e2]) and takes one
+        // log whenever the running product approaches the end of the FP64 range (every ~20 elements) and at the end
         double prod = 1.0;
         flat_pass_b<2>(ctx, st, bc, src, L.nx, [&](int q, const double* v, double lo, double hi) {
           const double xn = v[0] + alpha * v[1];
@@ -513,7 +524,7 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
             else prod *= gp;
             if (!hl) sbar += o.kappa_d * gp;
           }
-          if (((q / ctx.nt) & 3) == 3) sbar -= log(prod), prod = 1.0;
+          if (prod < 1e-250 || prod > 1e250) sbar -= log(prod), prod = 1.0;  // flush before the running product leaves the FP64 range
         });
         sbar -= log(prod);
       }

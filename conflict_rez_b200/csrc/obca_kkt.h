@@ -894,36 +894,50 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   }
   OBCA_WARP_SYNC();
   prof_mark(ctx, 19);
-  // projected stage Hessian M = Tt' H Tt + dt cross terms, gradient m = Tt'(H s0 + gn) + e_dt hd's0
-  double* HT = Mq;                    // [42][NRED]   (the QR matrix is no longer needed in shared memory)
+  // projected stage Hessian M = Tt' H Tt + dt cross terms, gradient m = Tt'(H s0 + gn) + e_dt hd's0.
+  // The node Hessians are expanded to full 7 x 7 blocks first: the inner loops then run over plain strided arrays with
+  // compile-time trip counts (the packed-index arithmetic cost more than the multiplications it fed).
+  double* HT = Mq;                    // [42][NRED]   (the QR matrix and G0 are no longer needed in shared memory)
   double* hs0 = HT + NS * NRED;       // [42]
-  double* hn = hs0 + NS;              // [6][28]
-  double* hdT = hn + NK * 28;         // [NRED] + hds0
+  double* Hf = hs0 + NS;              // [6][7][7]
+  double* hdT = Hf + NK * 49;         // [NRED] + hds0
   OBCA_LANES(lane) {
-    for (int q = lane; q < NK * 28; q += 32) hn[(q % NK) * 28 + q / NK] = W.HN[((size_t)a * 28 + q / NK) * L.Mv + n0 + q % NK];
+    for (int e = lane; e < NK * 49; e += 32) {
+      const int k = e / 49, rc = e % 49, r = rc / 7, c = rc % 7;
+      Hf[e] = W.HN[((size_t)a * 28 + sym(r, c)) * L.Mv + n0 + k];
+    }
   }
   OBCA_WARP_SYNC();
   OBCA_LANES(lane) {
-    for (int e = lane; e < NS * NRED; e += 32) {
-      int row = e / NRED, col = e % NRED, k = row / NZ, q = row % NZ;
-      double sacc = 0;
-      for (int m = 0; m < NZ; ++m) {
-        double tv = (k == 0) ? ((m == col) ? 1.0 : 0.0) : T[((k - 1) * NZ + m) * NRED + col];
-        sacc += hn[k * 28 + sym(q, m)] * tv;
-      }
-      HT[e] = sacc;
+    for (int e = lane; e < NZ * NRED; e += 32) {  // node 0: identity rows of the stage map
+      const int row = e / NRED, col = e % NRED;
+      HT[e] = col < NZ ? Hf[row * 7 + col] : 0.0;
+    }
+    for (int e = lane; e < NW * NRED; e += 32) {
+      const int row = e / NRED, col = e % NRED, k = row / NZ + 1, q = row % NZ;
+      const double* Hr = Hf + k * 49 + q * 7;
+      const double* Tc = T + ((k - 1) * NZ) * NRED + col;
+      const double a0 = Hr[0] * Tc[0] + Hr[2] * Tc[2 * NRED] + Hr[4] * Tc[4 * NRED] + Hr[6] * Tc[6 * NRED];
+      const double a1 = Hr[1] * Tc[NRED] + Hr[3] * Tc[3 * NRED] + Hr[5] * Tc[5 * NRED];
+      HT[(NZ + row) * NRED + col] = a0 + a1;
     }
     for (int row = lane; row < NS; row += 32) {
-      int k = row / NZ, q = row % NZ;
       double acc0 = 0;
-      if (k > 0)
-        for (int m = 0; m < NZ; ++m) acc0 += hn[k * 28 + sym(q, m)] * s0[(k - 1) * NZ + m];
+      if (row >= NZ) {
+        const int k = row / NZ, q = row % NZ;
+        const double* Hr = Hf + k * 49 + q * 7;
+        const double* sv = s0 + (k - 1) * NZ;
+#pragma unroll
+        for (int m = 0; m < NZ; ++m) acc0 += Hr[m] * sv[m];
+      }
       hs0[row] = acc0;
     }
     if (lane < NRED) {
-      double sacc = lane < NZ ? hdv[lane] : 0.0;
-      for (int row = NZ; row < NS; ++row) sacc += hdv[row] * T[(row - NZ) * NRED + lane];
-      hdT[lane] = sacc;
+      double sacc = lane < NZ ? hdv[lane] : 0.0, s1 = 0.0;
+      int row = NZ;
+      for (; row + 1 < NS; row += 2) sacc += hdv[row] * T[(row - NZ) * NRED + lane], s1 += hdv[row + 1] * T[(row + 1 - NZ) * NRED + lane];
+      for (; row < NS; ++row) sacc += hdv[row] * T[(row - NZ) * NRED + lane];
+      hdT[lane] = sacc + s1;
     } else if (lane == NRED) {
       double sacc = 0;
       for (int row = NZ; row < NS; ++row) sacc += hdv[row] * s0[row - NZ];
@@ -935,19 +949,23 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   OBCA_LANES(lane) {
     for (int e = lane; e < NSYM + NRED; e += 32) {
       if (e < NSYM) {
-        int q = 0;
-        while ((q + 1) * (q + 2) / 2 <= e) ++q;
-        int cc = e - q * (q + 1) / 2;
-        double sacc = 0;
-        if (q < NZ) sacc += HT[q * NRED + cc];  // node-0 identity rows
-        for (int row = NZ; row < NS; ++row) sacc += T[(row - NZ) * NRED + q] * HT[row * NRED + cc];
+        int q = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);  // row of the packed lower triangle; the float estimate is off by one at most
+        if ((q + 1) * (q + 2) / 2 <= e) ++q;
+        if (q * (q + 1) / 2 > e) --q;
+        const int cc = e - q * (q + 1) / 2;
+        double sacc = q < NZ ? HT[q * NRED + cc] : 0.0, s1 = 0.0;  // node-0 identity rows
+        const double* Tq = T + q;
+        const double* Hc = HT + NZ * NRED + cc;
+        int row = 0;
+        for (; row + 1 < NW; row += 2) sacc += Tq[row * NRED] * Hc[row * NRED], s1 += Tq[(row + 1) * NRED] * Hc[(row + 1) * NRED];
+        sacc += Tq[row * NRED] * Hc[row * NRED];  // NW = 35 is odd
+        sacc += s1;
         if (q == IDT) sacc += hdT[cc];
         if (cc == IDT) sacc += hdT[q];
         Mo[e] = sacc;
       } else {
-        int q = e - NSYM;
-        double sacc = 0;
-        if (q < NZ) sacc += hs0[q] + gnv[q];
+        const int q = e - NSYM;
+        double sacc = q < NZ ? hs0[q] + gnv[q] : 0.0;
         for (int row = NZ; row < NS; ++row) sacc += T[(row - NZ) * NRED + q] * (hs0[row] + gnv[row]);
         if (q == IDT) sacc += hdT[NRED];
         Mo[e] = sacc;

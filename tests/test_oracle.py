@@ -89,3 +89,20 @@ def test_oracle_reproduces_golden_and_matches_scipy_on_a_tiny_case(strategy_file
     bounds = [(None if not np.isfinite(lo) else lo, None if not np.isfinite(hi) else hi) for lo, hi in zip(tn.xL, tn.xU)]
     s = minimize(tn.f, r.x, jac=tn.grad_f, constraints=cons, bounds=bounds, method="SLSQP", options={"maxiter": 200, "ftol": 1e-12})
     assert s.fun >= r.obj - 1e-5 * abs(r.obj) or np.abs(tn.c(s.x)).max() > 1e-6
+
+
+def test_casadi_ipopt_pins_the_oracle_when_available():
+    """on a machine that has CasADi/IPOPT the literal Opti statement of the reference problem
+    (oracle/casadi_ref.py) must reproduce the oracle's golden solutions.  Skipped (and the parity stays "unpinned at the
+    CasADi/IPOPT boundary") where the wheels are missing -- as in the build image."""
+    from oracle import casadi_ref
+
+    if not casadi_ref.available():
+        pytest.skip("casadi is not installed here: the oracle is the restated port (parity unpinned at the CasADi/IPOPT boundary)")
+    for name in ("single_vehicle_2", "joint_vehicle_1_2"):
+        prob, guess, gold = load_golden(name)
+        ref = casadi_ref.solve(prob, guess, tol=1e-8)
+        assert ref["return_status"] in ("Solve_Succeeded", "Solved_To_Acceptable_Level")
+        assert abs(ref["obj"] - gold["obj"]) <= 1e-6 * abs(gold["obj"])
+        assert np.abs(ref["z"] - gold["z"]).max() <= 1e-4 and abs(ref["dt"] - gold["dt"]) <= 1e-6
+        print(name, "IPOPT iterations", ref["iters"], "oracle", int(gold["iters"]), "linear solver", ref["linear_solver"])
