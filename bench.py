@@ -209,8 +209,33 @@ def mpc_latency(rl_file, device, steps):
            "iters_p50": float(np.percentile(mdf.step_iters[5:], 50)), "iters_max": int(np.max(mdf.step_iters[5:])),
            "note": "closed loop of %d control steps, Jacobi exchange of predictions, one batched k_solve launch per control step (4 NLPs); "
            "failed solves fall back to the shifted plan like the reference (vehicle_follower.py:501-524) and are counted, their time is the measured one" % steps}
-    if hasattr(mdf, "timing"):
-        out.update(mdf.timing())
+    # the same closed loop device resident (DeviceMpcLoop): reference window, shifts, solve, fallback and plant step as kernels on
+    # one stream; "eager" = one host synchronisation per control step (a controller that has to ship the input), "graph" = one
+    # captured step replayed back to back
+    try:
+        import torch
+
+        from conflict_rez_b200.control.vehicle_follower import DeviceMpcLoop
+
+        np.random.seed(0)
+        m2 = MultiDistributedFollower(rl_file, {a: True for a in AGENTS}, {a: {} for a in AGENTS}, {a: VehicleState() for a in AGENTS}, HEADINGS, device=device)
+        m2.setup_multi_vehicles()
+        loop = DeviceMpcLoop(m2)
+        ts = []
+        for _ in range(steps):
+            ts.append(1e3 * loop.run(1))
+        ex = loop.export()
+        te = np.array(ts[5:])
+        out["device_loop"] = {"p50_step_ms": float(np.percentile(te, 50)), "p99_step_ms": float(np.percentile(te, 99)), "mean_step_ms": float(te.mean()),
+                              "steps": int(len(te)), "failed_solves": int(ex["failed_solves"]), "iters_p50": float(np.percentile(ex["iters"].max(1)[5:], 50))}
+        np.random.seed(0)
+        m3 = MultiDistributedFollower(rl_file, {a: True for a in AGENTS}, {a: {} for a in AGENTS}, {a: VehicleState() for a in AGENTS}, HEADINGS, device=device)
+        m3.setup_multi_vehicles()
+        g = DeviceMpcLoop(m3)
+        g.run(5)  # the restoration-heavy first steps stay out of the replayed average
+        out["device_loop"]["graph_mean_step_ms"] = 1e3 * g.run(steps - 5, graph=True)
+    except Exception as e:  # the device loop is an extra: report why it is missing instead of losing the bench line
+        out["device_loop"] = {"error": repr(e)[:200]}
     return out
 
 

@@ -1275,13 +1275,14 @@ OBCA_HD int red_target(int a, int rc, int V, const int* uoff, const int* npv, in
   return 0;
 }
 
+// Stage assembly as ONE gather pass: every entry of Q, S, R (and of the dt row / column and the gradients q, r) is computed by
+// one thread from the prefetched stage inputs -- no zero fill, no scatter passes, one barrier (round 1: zero fill + three scatter
+// passes with three barriers, 11 k cycles per stage).
+//   state index t < 7V -> (vehicle t / 7, reduced coordinate t % 7); control u -> (vehicle, 7 + slot) through ctl[]; dt = 7V
+//   own-vehicle entries come from MA (packed symmetric 16 x 16), cross-vehicle entries from MAB of the pair (rows: first vehicle)
 OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R, int i, double hdtdt, int nu) {
   assume_scratch(W);
   const int nX = L.nX, idt = 7 * L.V, V = L.V;
-  for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.Q[q] = 0;
-  for (int q = ctx.tid; q < nu * nX; q += ctx.nt) R.S[q] = 0;
-  for (int q = ctx.tid; q < nu * nu; q += ctx.nt) R.R[q] = 0;
-  // stage data: already in shared memory (ric_input_fetch) when the arena has room for it
 #if OBCA_RIC_PREFETCH
 #define OBCA_MA(a) (R.MAs + (a) * (NSYM + NRED))
 #define OBCA_MAB(p) (R.MABs + (p) * (NRED * NRED + 2 * NRED))
@@ -1307,70 +1308,70 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
     else if (cc == IDT) R.db[a * 7 + r] = v;
     else R.cb[a * 7 + r] = v;
   }
-  cta_sync(ctx);
   prof_mark(ctx, 28);
-  // pass A: own-vehicle entries that do not involve dt
-  for (int it = ctx.tid; it < V * NRED * NRED; it += ctx.nt) {
-    int a = it / (NRED * NRED), r = (it / NRED) % NRED, cc = it % NRED;
-    if (i >= L.N[a] || r == IDT || cc == IDT) continue;
-    int kr, kc;
-    int tr = red_target(a, r, V, R.uoff, R.npv, &kr), tc = red_target(a, cc, V, R.uoff, R.npv, &kc);
-    if (kr < 0 || kc < 0) continue;
-    double v = OBCA_MA(a)[sym(r, cc)];
-    if (kr == 0 && kc == 0) R.Q[tr * nX + tc] = v;
-    else if (kr == 1 && kc == 0) R.S[tr * nX + tc] = v;
-    else if (kr == 1 && kc == 1) R.R[tr * nu + tc] = v;
-  }
-  prof_mark(ctx, 29);
-  // pass B: cross-vehicle entries that do not involve dt (each (pair, ra, cb) owns its targets)
-  for (int it = ctx.tid; it < L.P * NRED * NRED; it += ctx.nt) {
-    int p = it / (NRED * NRED), ra = (it / NRED) % NRED, cb = it % NRED;
-    if (i * NK >= L.Mp[p] || ra == IDT || cb == IDT) continue;
-    int a = L.pa[p], b = L.pb[p], ka, kb;
-    int ta = red_target(a, ra, V, R.uoff, R.npv, &ka), tb = red_target(b, cb, V, R.uoff, R.npv, &kb);
-    if (ka < 0 || kb < 0) continue;
-    double v = OBCA_MAB(p)[ra * NRED + cb];
-    if (ka == 0 && kb == 0) R.Q[ta * nX + tb] = v, R.Q[tb * nX + ta] = v;
-    else if (ka == 1 && kb == 0) R.S[ta * nX + tb] = v;
-    else if (ka == 0 && kb == 1) R.S[tb * nX + ta] = v;
-    else R.R[ta * nu + tb] = v, R.R[tb * nu + ta] = v;
-  }
-  prof_mark(ctx, 30);
-  // pass C: everything that touches dt, and the gradients: one thread per target, fixed summation order
-  for (int t = ctx.tid; t < idt + nu + 1; t += ctx.nt) {
-    int a = -1, rc = IDT;
-    if (t < idt) a = t / 7, rc = t % 7;
-    else if (t < idt + nu) {
-      for (int aa = 0; aa < V; ++aa)
-        if (t - idt >= R.uoff[aa] && t - idt < R.uoff[aa] + R.npv[aa]) a = aa, rc = 7 + t - idt - R.uoff[aa];
-    }
-    double hd = 0, g = 0;
-    if (a >= 0) {
-      if (i < L.N[a]) {
-        const double* Mo = OBCA_MA(a);
-        hd = Mo[sym(IDT, rc)], g = Mo[NSYM + rc];
-      }
-      for (int p = 0; p < L.P; ++p) {
-        if (i * NK >= L.Mp[p]) continue;
-        const double* Mo = OBCA_MAB(p);
-        if (L.pa[p] == a) hd += Mo[rc * NRED + IDT], g += Mo[NRED * NRED + rc];
-        else if (L.pb[p] == a) hd += Mo[IDT * NRED + rc], g += Mo[NRED * NRED + NRED + rc];
-      }
-      if (t < idt) R.Q[t * nX + idt] = hd, R.Q[idt * nX + t] = hd, R.q[t] = g;
-      else R.S[(t - idt) * nX + idt] = hd, R.r[t - idt] = g;
+  // entry (vehicle a, reduced coordinate ra) x (vehicle b, reduced coordinate rb) of the stage Hessian
+  auto entry = [&](int a, int ra, int b, int rb) -> double {
+    if (a == b) return i < L.N[a] ? OBCA_MA(a)[sym(ra, rb)] : 0.0;
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    const int p = lo * V - lo * (lo + 1) / 2 + (hi - lo - 1);  // index of the pair (lo, hi) in combinations order
+    if (i * NK >= L.Mp[p]) return 0.0;
+    return a < b ? OBCA_MAB(p)[ra * NRED + rb] : OBCA_MAB(p)[rb * NRED + ra];
+  };
+  auto ctl = [&](int u, int* a) -> int {  // control u -> vehicle, returns its reduced coordinate
+    int aa = 0;
+    while (u >= R.uoff[aa + 1]) ++aa;
+    *a = aa;
+    return 7 + u - R.uoff[aa];
+  };
+  const int nQ = idt * idt, nS = nu * idt, nR = nu * nu, nD = idt + nu + 1;
+  for (int it = ctx.tid; it < nQ + nS + nR + nD; it += ctx.nt) {
+    if (it < nQ) {
+      const int tr = it / idt, tc = it % idt;
+      R.Q[tr * nX + tc] = entry(tr / 7, tr % 7, tc / 7, tc % 7);
+    } else if (it < nQ + nS) {
+      const int e = it - nQ, u = e / idt, tc = e % idt;
+      int a;
+      const int ra = ctl(u, &a);
+      R.S[u * nX + tc] = entry(a, ra, tc / 7, tc % 7);
+    } else if (it < nQ + nS + nR) {
+      const int e = it - nQ - nS, u = e / nu, u2 = e % nu;
+      int a, b;
+      const int ra = ctl(u, &a), rb = ctl(u2, &b);
+      R.R[u * nu + u2] = entry(a, ra, b, rb);
     } else {
-      for (int aa = 0; aa < V; ++aa) {
-        if (i >= L.N[aa]) continue;
-        const double* Mo = OBCA_MA(aa);
-        hd += Mo[sym(IDT, IDT)], g += Mo[NSYM + IDT];
+      // everything that touches dt, and the gradients: one thread per target, fixed summation order
+      const int t = it - nQ - nS - nR;
+      int a = -1, rc = IDT;
+      if (t < idt) a = t / 7, rc = t % 7;
+      else if (t < idt + nu) rc = ctl(t - idt, &a);
+      double hd = 0, g = 0;
+      if (a >= 0) {
+        if (i < L.N[a]) {
+          const double* Mo = OBCA_MA(a);
+          hd = Mo[sym(IDT, rc)], g = Mo[NSYM + rc];
+        }
+        for (int p = 0; p < L.P; ++p) {
+          if (i * NK >= L.Mp[p]) continue;
+          const double* Mo = OBCA_MAB(p);
+          if (L.pa[p] == a) hd += Mo[rc * NRED + IDT], g += Mo[NRED * NRED + rc];
+          else if (L.pb[p] == a) hd += Mo[IDT * NRED + rc], g += Mo[NRED * NRED + NRED + rc];
+        }
+        if (t < idt) R.Q[t * nX + idt] = hd, R.Q[idt * nX + t] = hd, R.q[t] = g;
+        else R.S[(t - idt) * nX + idt] = hd, R.r[t - idt] = g;
+      } else {
+        for (int aa = 0; aa < V; ++aa) {
+          if (i >= L.N[aa]) continue;
+          const double* Mo = OBCA_MA(aa);
+          hd += Mo[sym(IDT, IDT)], g += Mo[NSYM + IDT];
+        }
+        for (int p = 0; p < L.P; ++p) {
+          if (i * NK >= L.Mp[p]) continue;
+          const double* Mo = OBCA_MAB(p);
+          hd += 2.0 * Mo[IDT * NRED + IDT], g += Mo[NRED * NRED + IDT] + Mo[NRED * NRED + NRED + IDT];
+        }
+        if (i == 0) hd += hdtdt, g += W.gphi[L.oDT];
+        R.Q[idt * nX + idt] = hd, R.q[idt] = g;
       }
-      for (int p = 0; p < L.P; ++p) {
-        if (i * NK >= L.Mp[p]) continue;
-        const double* Mo = OBCA_MAB(p);
-        hd += 2.0 * Mo[IDT * NRED + IDT], g += Mo[NRED * NRED + IDT] + Mo[NRED * NRED + NRED + IDT];
-      }
-      if (i == 0) hd += hdtdt, g += W.gphi[L.oDT];
-      R.Q[idt * nX + idt] = hd, R.q[idt] = g;
     }
   }
   cta_sync(ctx);
@@ -1717,10 +1718,12 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
         if (m < r) Lg[r * nUmax + m] = ldl_form ? R.F[it] : 0.0;
       }
     }
-    // P <- Q + A'PA + Gm'K ; p <- q + A'pc + Gm'k   (written into Q/q first, then copied: P is still needed).
+    // P <- Q + A'PA + Gm'K ; p <- q + A'pc + Gm'k, written straight into the cost-to-go of the next stage (shared memory) and into
+    // the global copy the multiplier recovery reads: nothing of this stage reads the old P any more (PA, PB, pc hold its products).
     // P is symmetric: only col >= r is computed (rows r and nX-1-r share one strip of nX+1 items) and mirrored; item nX of
     // the strips < nX is the gradient entry.  The dense dt row only occurs in the items (dt, dt) and p[dt].
     {
+      double* P0 = W.RP + (size_t)i * pstride;
       const int np1 = nX + 1, nstrip = (nX + 1) / 2;
       for (int it = ctx.tid; it < nstrip * np1 + nX; it += ctx.nt) {
         int r, col;
@@ -1750,21 +1753,12 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
         s += s1;
         if (col < nX) {
           const double v = R.Q[r * nX + col] + s;
-          R.Q[r * nX + col] = v, R.Q[col * nX + r] = v;
-        } else
-          R.q[r] += s;
-      }
-    }
-    cta_sync(ctx);
-    {
-      double* P0 = W.RP + (size_t)i * pstride;
-      for (int q = ctx.tid; q < nX * nX; q += ctx.nt) {
-        double v = R.Q[q];
-        R.P[q] = v, P0[q] = v;
-      }
-      for (int q = ctx.tid; q < nX; q += ctx.nt) {
-        double v = R.q[q];
-        R.p[q] = v, P0[nX * nX + q] = v;
+          R.P[r * nX + col] = v, R.P[col * nX + r] = v;
+          P0[r * nX + col] = v, P0[col * nX + r] = v;
+        } else {
+          const double v = R.q[r] + s;
+          R.p[r] = v, P0[nX * nX + r] = v;
+        }
       }
     }
     cta_sync(ctx);
