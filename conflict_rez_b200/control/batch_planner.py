@@ -166,3 +166,54 @@ def solve_joint_batch(rl_file_name, agents, init_offsets, options=None, device="
     plan.solver.close()
     plan.solver = None
     return plan
+
+
+def replicate_problem(prob: CollocationProblem, copies: int, shift=(35.0, 0.0)) -> CollocationProblem:
+    """``copies`` parking lots side by side (copy c translated by c * shift) in ONE joint problem of ``copies * V`` vehicles and
+    ``copies * O`` obstacles: the synthetic scenario of the scaling sweep beyond the four agents of the RL environment (SURVEY.md 8d,
+    config 5: 2-8 vehicles).  Every pair of vehicles keeps its collision-avoidance block, also across lots (far apart: inactive)."""
+    s = np.asarray(shift, dtype=float)
+    tile = lambda a: np.concatenate([a] * copies, axis=0)
+    obs_b = np.concatenate([prob.obs_b + c * (prob.obs_A @ s) for c in range(copies)], axis=0)
+    tube_b = np.concatenate([prob.tube_b + c * (prob.tube_A @ s) for c in range(copies)], axis=0)
+    off = np.concatenate([np.array([c * s[0], c * s[1], 0.0])[None].repeat(prob.V, 0) for c in range(copies)], axis=0)
+    init = np.concatenate([prob.init_pose] * copies, axis=-2) + off
+    region = prob.region.copy()
+    region[1] += (copies - 1) * max(s[0], 0.0)
+    region[3] += (copies - 1) * max(s[1], 0.0)
+    return dataclasses.replace(prob, n_sets=tile(prob.n_sets), obs_A=tile(prob.obs_A), obs_b=obs_b, tube_A=tile(prob.tube_A), tube_b=tube_b,
+                               init_pose=init, final_heading=tile(prob.final_heading), region=region)
+
+
+def prepare_replicated_batch(rl_file_name: str, agents: Sequence[str], copies: int, init_offsets: np.ndarray, options: Optional[SolveOptions] = None,
+                             device="cuda:0", lib=None, shift=(35.0, 0.0), **kw) -> JointPlan:
+    """Warm start + joint handle for ``copies`` replicated lots (``copies * len(agents)`` vehicles per instance):
+    ``init_offsets`` (B, copies * V, 3).  Each lot runs the reference chain (``prepare_joint_batch``) in its own frame; the joint
+    guess concatenates the single-vehicle solutions (translated), the duals of all ``copies * O`` obstacles and of all pairs come
+    from the closed-form device warm starts."""
+    V = len(agents)
+    init_offsets = np.asarray(init_offsets, dtype=float)
+    assert init_offsets.shape[1] == copies * V
+    t0 = time.perf_counter()
+    lots = [prepare_joint_batch(rl_file_name, agents, init_offsets[:, c * V:(c + 1) * V], options, device, lib, **kw) for c in range(copies)]
+    for p in lots:
+        p.solver.close()
+    base = lots[0].problem
+    prob = replicate_problem(base, copies, shift)
+    prob.init_pose = np.concatenate([lots[c].problem.init_pose + np.array([c * shift[0], c * shift[1], 0.0]) for c in range(copies)], axis=1)
+    joint = ObcaSolver(prob, options, device=device, lib=lib)
+    zs = []
+    for c, p in enumerate(lots):
+        z = p.dev_guess["z"].clone()
+        z[..., 0] += c * shift[0]
+        z[..., 1] += c * shift[1]
+        zs.append(z)
+    zj = torch.cat(zs, dim=1).contiguous()
+    dg = {"pose": joint._to_dev(prob.init_pose, (joint.B, joint.V, 3)), "z": zj, "dt": torch.stack([p.dev_guess["dt"] for p in lots]).mean(0)}
+    dg["lam"], dg["mu"] = joint.dual_ws(zj)
+    dg["pl"], dg["pm"], dg["ps"] = joint.joint_dual_ws(zj)
+    _sync(joint.device)
+    host = lambda k: dg[k].cpu().numpy()
+    guess = CollocationGuess(host("z"), host("lam"), host("mu"), host("dt"), host("pl"), host("pm"), host("ps"))
+    singles = [r for p in lots for r in p.singles]
+    return JointPlan(prob, guess, singles, dev_guess=dg, timing={"warm_start_s": time.perf_counter() - t0}, solver=joint)

@@ -44,7 +44,7 @@ struct ObcaHandle {
   int device;
   int slots;
   bool have_static;
-  size_t it_stride, wk_stride, rw_stride;
+  size_t it_stride, wk_stride, rw_stride, ric_stride;  // rw: shared-memory arena, ric: global Riccati arena (0 = the Riccati phase lives in the shared arena)
   // device memory
   Lay* d_L;
   Stat* d_S;
@@ -192,7 +192,7 @@ struct SolveArgs {
   const unsigned char* bcls;
   double blo[8], bhi[8];
   double *iter, *work, *rw;
-  size_t it_stride, wk_stride, rw_stride;
+  size_t it_stride, wk_stride, rw_stride, ric_stride;
   Result* res;
   int B;
   int* counter;
@@ -208,6 +208,7 @@ OBCA_HDN void run_instance(const Ctx& ctx, const SolveArgs& A, const Lay& L, con
   Scratch W;
   carve_iterate(W, L, A.iter + (size_t)b * A.it_stride);
   carve_work(W, L, A.work + (size_t)slot * A.wk_stride);
+  W.ricg = A.rw_in_smem ? nullptr : A.rw + (size_t)slot * A.ric_stride;
   if (A.mode == 0) {
     if (L.mode == 0) ipm_solve<0>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, A.bcls, W, RW, A.rw_stride, sh, A.res + b);
     else ipm_solve<1>(ctx, L, S, A.o, A.cnt, A.xL, A.xU, A.bcls, W, RW, A.rw_stride, sh, A.res + b);
@@ -284,7 +285,8 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_solve(SolveArgs A)
   if (threadIdx.x < 8) sh.blo[threadIdx.x] = A.blo[threadIdx.x], sh.bhi[threadIdx.x] = A.bhi[threadIdx.x];
   __syncthreads();
   double* RW = arena;
-  Ctx ctx{(int)threadIdx.x, (int)blockDim.x, red, A.prof ? A.prof + (size_t)blockIdx.x * (NPROF + 1) : nullptr};
+  __shared__ LdlBuf sldl;
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x, red, &sldl, A.prof ? A.prof + (size_t)blockIdx.x * (NPROF + 1) : nullptr};
   if (ctx.prof && threadIdx.x == 0) ctx.prof[NPROF] = clock64();
   if (A.mode != 0) {
     run_instance(ctx, A, sL, sS, A.b_only, 0, &sh, RW);
@@ -526,9 +528,17 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   h->cnt.m_active = m_active, h->cnt.nb = nb;
   h->it_stride = iterate_doubles(L), h->wk_stride = work_doubles(L);
   h->rw_stride = mpc ? mpc_work_doubles(L) : riccati_work_doubles(L, NWARPS);
+  h->ric_stride = 0;
 #ifndef OBCA_HOST_EMU
-  if (h->rw_stride * sizeof(double) > (size_t)(CTAS_PER_SM == 1 ? 200 : 100) * 1024)
-    return fail("obca_set_static: the shared-memory work arena of this problem shape exceeds 200 KB (too many vehicles for this build)");
+  const size_t smem_cap = (size_t)(CTAS_PER_SM == 1 ? 200 : 100) * 1024;
+  if (!mpc && h->rw_stride * sizeof(double) > smem_cap) {
+    // more than 4 vehicles: the stage matrices of the joint Riccati state (7 V + 1) do not fit next to the null-space work areas;
+    // the Riccati phase then runs from a per-slot arena in global memory (L2 resident), everything else keeps the shared arena
+    h->ric_stride = riccati_only_doubles(L);
+    h->rw_stride = (size_t)NWARPS * NSW;
+  }
+  if (h->rw_stride * sizeof(double) > smem_cap)
+    return fail("obca_set_static: the shared-memory work arena of this problem shape exceeds 200 KB");
 #endif
 #ifdef OBCA_HOST_EMU
   h->slots = 1;
@@ -540,7 +550,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   int B = h->dims.batch;
   if (dev_alloc((void**)&h->d_L, sizeof(Lay)) || dev_alloc((void**)&h->d_S, sizeof(Stat)) || dev_alloc((void**)&h->d_tube, tube.size() * 8) ||
       dev_alloc((void**)&h->d_bcls, bcls.size()) || dev_alloc((void**)&h->d_xL, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_xU, (L.nx + 2) * 8) || dev_alloc((void**)&h->d_iter, (size_t)B * h->it_stride * 8) ||
-      dev_alloc((void**)&h->d_work, (size_t)h->slots * h->wk_stride * 8) || dev_alloc((void**)&h->d_rw, (size_t)h->slots * h->rw_stride * 8) ||
+      dev_alloc((void**)&h->d_work, (size_t)h->slots * h->wk_stride * 8) || dev_alloc((void**)&h->d_rw, (size_t)h->slots * (h->ric_stride ? h->ric_stride : h->rw_stride) * 8) ||
       dev_alloc((void**)&h->d_res, (size_t)B * sizeof(Result)) || dev_alloc((void**)&h->d_counter, sizeof(int)) || dev_alloc((void**)&h->d_order, (size_t)B * sizeof(int)) ||
       dev_alloc((void**)&h->d_prof, (size_t)h->slots * (NPROF + 1) * sizeof(long long)))
     return fail("obca_set_static: device allocation failed");
@@ -754,12 +764,12 @@ static SolveArgs make_args(ObcaHandle* h, int mode, int b) {
   A.L = h->d_L, A.S = h->d_S, A.o = h->opts, A.cnt = h->cnt, A.xL = h->d_xL, A.xU = h->d_xU, A.bcls = h->d_bcls;
   for (int k = 0; k < 8; ++k) A.blo[k] = h->blo[k], A.bhi[k] = h->bhi[k];
   A.iter = h->d_iter, A.work = h->d_work, A.rw = h->d_rw;
-  A.it_stride = h->it_stride, A.wk_stride = h->wk_stride, A.rw_stride = h->rw_stride;
+  A.it_stride = h->it_stride, A.wk_stride = h->wk_stride, A.rw_stride = h->rw_stride, A.ric_stride = h->ric_stride;
   A.res = h->d_res, A.B = h->dims.batch, A.counter = h->d_counter, A.mode = mode, A.b_only = b;
   A.order = h->have_order ? h->d_order : nullptr;
   A.prof = getenv("OBCA_PROFILE") ? h->d_prof : nullptr;
   A.dbg_mu = 0, A.dbg_dw = 0;
-  A.rw_in_smem = 1;
+  A.rw_in_smem = h->ric_stride == 0;
   return A;
 }
 
@@ -770,7 +780,7 @@ static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
   Shared sh;
   for (int k = 0; k < 8; ++k) sh.blo[k] = A.blo[k], sh.bhi[k] = A.bhi[k];
   double red[40];
-  Ctx ctx{0, 1, red, nullptr};
+  Ctx ctx{0, 1, red, nullptr, nullptr};
   if (A.mode != 0)
     run_instance(ctx, A, *A.L, *A.S, A.b_only, 0, &sh, A.rw);
   else
@@ -779,7 +789,7 @@ static int launch(ObcaHandle* h, const SolveArgs& A, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (A.mode == 0) CUDA_OK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   int grid = A.mode == 0 ? h->slots : 1;
-  size_t smem = A.rw_in_smem ? h->rw_stride * sizeof(double) : 0;
+  size_t smem = h->rw_stride * sizeof(double);
   if (smem) CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_solve<<<grid, CTA_THREADS, smem, s>>>(A);
   h->launches++;

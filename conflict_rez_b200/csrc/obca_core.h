@@ -252,6 +252,7 @@ struct Scratch {
   double* RX;   // [Nmax+1][nX] states, [Nmax][nU] controls
   double* SS;   // [V][Nmax][42] stage solutions
   double* init_pose;  // [V][3]
+  double* ricg;       // per-slot global-memory Riccati arena when the stage matrices do not fit shared memory (V > 4), else nullptr
 };
 
 // vector lengths are padded to an even number of doubles: every flat vector starts 16-byte aligned, which the bulk
@@ -358,6 +359,7 @@ struct Result {
 struct Ctx {
   int tid, nt;
   double* red;  // shared scratch for reductions (>= 40 doubles)
+  void* ldl;    // LdlBuf in shared memory: pivot row / column exchange of the Riccati stage factorisation (device only)
   long long* prof;  // optional per-slot phase cycle counters [NPROF + 1] (last = time stamp), or nullptr
 };
 

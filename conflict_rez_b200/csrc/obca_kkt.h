@@ -1128,7 +1128,7 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, dou
 // ------------------------------------------------------------------------------------------------
 // pivot row / column exchange buffers of the stage factorisation (cta_stage_ldl)
 struct LdlBuf {
-  double col[2][32], row[2][64], inv[2], invd[32];
+  double col[2][64], row[2][128], inv[2], invd[64];
   int bad;
 };
 #if defined(__CUDA_ARCH__)
@@ -1142,7 +1142,6 @@ OBCA_HD size_t ric_record_doubles(const Lay& L) { return (size_t)(L.nX + 1) * L.
 
 struct RicWork {
   double *P, *p, *Q, *S, *R, *q, *r, *PA, *PB, *pc, *F, *Gm, *K, *Ab, *Bb, *db, *cb, *invd, *MAs, *MABs, *TBs;
-  LdlBuf* ldl;  // pivot row / column exchange buffers of the factorisation
   int *uoff, *npv, *npt;  // [MAXV + 1], [MAXV + 1], [V][Nmax]
   const double** isrc;     // [n_in] address of every stage input at stage 0
   int* istr;               // [n_in][2] (doubles per stage, first stage beyond the block's horizon)
@@ -1150,7 +1149,7 @@ struct RicWork {
 
 inline size_t riccati_only_doubles(const Lay& L) {
   size_t nX = L.nX, nU = L.nU;
-  return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU + (sizeof(LdlBuf) + 7) / 8 + ((size_t)L.V * L.Nmax + 2) / 2 +
+  return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU + ((size_t)L.V * L.Nmax + 2) / 2 +
          (OBCA_RIC_PREFETCH ? 3 * ((size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) + (size_t)L.V * 7 * (NRED + 1)) + 4 : 0);
 }
 
@@ -1161,8 +1160,11 @@ inline size_t riccati_work_doubles(const Lay& L, int nwarps) {
 }
 
 OBCA_HD int ric_input_count(const Lay& L);
+// SM: the arena is shared memory (V <= 4: everything of a stage fits); otherwise it is the per-slot global-memory arena
+// (the state of V > 4 vehicles, 7 V + 1 > 29, no longer fits next to the null-space work areas) -- same code, other address space
+template <bool SM>
 OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
-  OBCA_ASSUME_SHARED(w);
+  if (SM) OBCA_ASSUME_SHARED(w);
   int nX = L.nX, nU = L.nU;
   R.P = w, w += nX * nX;
   R.p = w, w += nX;
@@ -1182,7 +1184,6 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
   R.db = w, w += L.V * 7;
   R.cb = w, w += L.V * 7;
   R.invd = w, w += nU;
-  R.ldl = (LdlBuf*)w, w += (sizeof(LdlBuf) + 7) / 8;
   R.MAs = w;
   R.MABs = w + L.V * (NSYM + NRED);
   R.TBs = R.MABs + L.P * (NRED * NRED + 2 * NRED);
@@ -1230,18 +1231,21 @@ OBCA_HD void ric_input_table(const Ctx& ctx, const Lay& L, const Scratch& W, con
     R.istr[2 * it] = (int)(s1 - s0), R.istr[2 * it + 1] = lim;
   }
 }
+template <bool SM>
 OBCA_HD void ric_input_fetch(const Ctx& ctx, const Lay& L, const Scratch& W, const RicWork& R, int i) {
   const int tot = ric_input_count(L);
   for (int it = ctx.tid; it < tot; it += ctx.nt) {
     const bool active = i < R.istr[2 * it + 1];
     const double* src = R.isrc[it] + (size_t)i * R.istr[2 * it];
 #if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(R.MAs + it)), "l"(active ? src : W.MA),
-                 "r"(active ? 8 : 0)
-                 : "memory");
-#else
-    R.MAs[it] = active ? *src : 0.0;  // MAs, MABs, TBs are contiguous
+    if (SM) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(R.MAs + it)), "l"(active ? src : W.MA),
+                   "r"(active ? 8 : 0)
+                   : "memory");
+      continue;
+    }
 #endif
+    R.MAs[it] = active ? *src : 0.0;  // MAs, MABs, TBs are contiguous
   }
 }
 OBCA_HD void ric_input_wait() {
@@ -1394,7 +1398,7 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
 // ------------------------------------------------------------------------------------------------
 OBCA_HD bool ldl_fast_shape(const Ctx& ctx, int nu, int nc) {
 #if defined(__CUDA_ARCH__)
-  return ctx.nt == 256 && nu >= 1 && nu <= 32 && nu + nc <= 64;
+  return ctx.nt == 256 && ctx.ldl && nu >= 1 && nu <= 64 && nu + nc <= 128;
 #else
   (void)ctx, (void)nu, (void)nc;
   return false;
@@ -1402,14 +1406,18 @@ OBCA_HD bool ldl_fast_shape(const Ctx& ctx, int nu, int nc) {
 }
 
 #if defined(__CUDA_ARCH__)
-template <int KMAX>
+// LOG2CG: log2 of the columns per row group (64 columns x 4 row groups for up to 4 vehicles, 128 x 2 beyond);
+// KMAX: rows per thread (row r = rg + RG k)
+template <int LOG2CG, int KMAX>
 __device__ __forceinline__ void cta_stage_ldl(const RicWork& R, int nu, int nX, int* ok, LdlBuf* B) {
-  const int t = threadIdx.x, rg = t >> 6, c = t & 63, nc = nX + 1, ncols = nu + nc;
+  constexpr int CG = 1 << LOG2CG, RG = 256 >> LOG2CG;
+  OBCA_ASSUME_SHARED(B);  // the exchange buffers are static shared memory of k_solve (LDS / STS instead of generic accesses)
+  const int t = threadIdx.x, rg = t >> LOG2CG, c = t & (CG - 1), nc = nX + 1, ncols = nu + nc;
   double m[KMAX];
   // entries of [F | Gm] owned by this thread: F = R + B'PB ; Gm = [S + B'PA | r + B'pc]
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
-    const int r = rg + 4 * k;
+    const int r = rg + RG * k;
     double v = 0.0;
     if (r < nu && c < ncols) {
       int a = 0;
@@ -1427,13 +1435,13 @@ __device__ __forceinline__ void cta_stage_ldl(const RicWork& R, int nu, int nX, 
     }
     m[k] = v;
   }
-  // every column has one diagonal owner, thread (rg = c & 3, c): its pivot tolerance is known before the loop
-  const double mytol = (c < nu && rg == (c & 3)) ? PIVOT_TOL * fmax(1.0, fabs(R.R[c * nu + c])) : 0.0;
+  // every column has one diagonal owner, thread (rg = c mod RG, c): its pivot tolerance is known before the loop
+  const double mytol = (c < nu && rg == (c & (RG - 1))) ? PIVOT_TOL * fmax(1.0, fabs(R.R[c * nu + c])) : 0.0;
   if (t == 0) B->bad = 0;
   __syncthreads();
   if (c == 0) {
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) B->col[0][rg + 4 * k] = m[k];
+    for (int k = 0; k < KMAX; ++k) B->col[0][rg + RG * k] = m[k];
   }
   if (rg == 0) B->row[0][c] = m[0];
   if (t == 0) {
@@ -1444,24 +1452,24 @@ __device__ __forceinline__ void cta_stage_ldl(const RicWork& R, int nu, int nX, 
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4 * KMAX; ++j) {
+  for (int j = 0; j < RG * KMAX; ++j) {
     if (j < nu) {  // CTA-uniform
       const int p = j & 1;
       const double uc = c > j ? B->row[p][c] * B->inv[p] : 0.0;  // finished columns (c <= j) keep their entries: L (times d)
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
-        if (4 * k + 3 > j) {  // static: some row of this slot lies below the pivot
-          const int r = rg + 4 * k;
+        if (RG * k + (RG - 1) > j) {  // static: some row of this slot lies below the pivot
+          const int r = rg + RG * k;
           const double l = r > j ? B->col[p][r] : 0.0;
           m[k] = fma(-l, uc, m[k]);
         }
       }
       if (j + 1 < nu) {
-        const int jn = j + 1, kn = jn >> 2, gn = jn & 3;
+        const int jn = j + 1, kn = jn / RG, gn = jn & (RG - 1);
         if (c == jn) {
 #pragma unroll
           for (int k = 0; k < KMAX; ++k)
-            if (4 * k + 3 > jn) B->col[p ^ 1][rg + 4 * k] = m[k];
+            if (RG * k + (RG - 1) > jn) B->col[p ^ 1][rg + RG * k] = m[k];
         }
         if (rg == gn) {
           B->row[p ^ 1][c] = m[kn < KMAX ? kn : 0];
@@ -1478,7 +1486,7 @@ __device__ __forceinline__ void cta_stage_ldl(const RicWork& R, int nu, int nX, 
   }
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
-    const int r = rg + 4 * k;
+    const int r = rg + RG * k;
     if (r < nu && c < ncols) {
       if (c < nu) {
         if (r > c) R.F[r * nu + c] = m[k] * B->invd[c];
@@ -1497,10 +1505,16 @@ __device__ __forceinline__ void cta_stage_ldl(const RicWork& R, int nu, int nX, 
 OBCA_HD void stage_ldl_fused(const Ctx& ctx, const RicWork& R, int nu, int nX, int* ok, LdlBuf* B) {
 #if defined(__CUDA_ARCH__)
   (void)ctx;
-  if (nu <= 8) cta_stage_ldl<2>(R, nu, nX, ok, B);
-  else if (nu <= 16) cta_stage_ldl<4>(R, nu, nX, ok, B);
-  else if (nu <= 24) cta_stage_ldl<6>(R, nu, nX, ok, B);
-  else cta_stage_ldl<8>(R, nu, nX, ok, B);
+  if (nu + nX + 1 <= 64) {
+    if (nu <= 8) cta_stage_ldl<6, 2>(R, nu, nX, ok, B);
+    else if (nu <= 16) cta_stage_ldl<6, 4>(R, nu, nX, ok, B);
+    else if (nu <= 24) cta_stage_ldl<6, 6>(R, nu, nX, ok, B);
+    else cta_stage_ldl<6, 8>(R, nu, nX, ok, B);
+  } else {
+    if (nu <= 32) cta_stage_ldl<7, 16>(R, nu, nX, ok, B);
+    else if (nu <= 48) cta_stage_ldl<7, 24>(R, nu, nX, ok, B);
+    else cta_stage_ldl<7, 32>(R, nu, nX, ok, B);
+  }
 #else
   (void)ctx, (void)R, (void)nu, (void)nX, (void)ok, (void)B;
 #endif
@@ -1598,11 +1612,12 @@ OBCA_HDN void riccati_factor_generic(const Ctx& ctx, const RicWork& R, int nu, i
     prof_mark(ctx, 15);
 }
 
+template <bool SM>
 OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, double* RW, double hdtdt, int* ok) {
   assume_scratch(W);
   const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V;
   RicWork R;
-  ric_carve(R, L, RW);
+  ric_carve<SM>(R, L, RW);
   const size_t pstride = (size_t)nX * nX + nX, kstride = ric_record_doubles(L);
   for (int q = ctx.tid; q < nX * nX; q += ctx.nt) R.P[q] = 0;
   for (int q = ctx.tid; q < nX; q += ctx.nt) R.p[q] = 0;
@@ -1614,7 +1629,7 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
 #if OBCA_RIC_PREFETCH
   ric_input_table(ctx, L, W, R);
   cta_sync(ctx);
-  ric_input_fetch(ctx, L, W, R, L.Nmax - 1);
+  ric_input_fetch<SM>(ctx, L, W, R, L.Nmax - 1);
 #endif
   cta_sync(ctx);
   for (int i = L.Nmax - 1; i >= 0; --i) {
@@ -1668,11 +1683,11 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     const int nc = nX + 1;
     const bool fast = ldl_fast_shape(ctx, nu, nc);
 #if OBCA_RIC_PREFETCH
-    if (i > 0) ric_input_fetch(ctx, L, W, R, i - 1);  // the assembly of this stage is done with the buffers: next stage's inputs
+    if (i > 0) ric_input_fetch<SM>(ctx, L, W, R, i - 1);  // the assembly of this stage is done with the buffers: next stage's inputs
 #endif
     if (fast) {
       // products and L D L' factorisation in registers, one barrier per pivot; F <- L, Gm <- Khat, K <- -D^-1 Khat
-      stage_ldl_fused(ctx, R, nu, nX, ok, R.ldl);
+      stage_ldl_fused(ctx, R, nu, nX, ok, (LdlBuf*)ctx.ldl);
       cta_sync(ctx);
       prof_mark(ctx, 14);
     } else {
@@ -1772,41 +1787,48 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
 // stage and no exposed global-memory latency (round 1: gains read from global memory inside the loop, 7 k cycles per stage).
 OBCA_HD size_t ric_fwd_buffer_doubles(const Lay& L) { return ric_record_doubles(L) + (size_t)L.V * 7 * (NRED + 1); }
 
+template <bool SM>
 OBCA_HD void ric_fwd_fetch(const Ctx& ctx, const Lay& L, const Scratch& W, int i, double* buf) {
   const size_t kstride = ric_record_doubles(L);
   const double* Kg = W.RK + (size_t)i * kstride;
   double* fT = buf + kstride;
 #if defined(__CUDA_ARCH__)
-  for (int it = ctx.tid; it < (int)kstride; it += ctx.nt)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(buf + it)), "l"(Kg + it) : "memory");
-#else
-  for (int it = ctx.tid; it < (int)kstride; it += ctx.nt) buf[it] = Kg[it];
+  if (SM) {
+    for (int it = ctx.tid; it < (int)kstride; it += ctx.nt)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(buf + it)), "l"(Kg + it) : "memory");
+  } else
 #endif
+  {
+    for (int it = ctx.tid; it < (int)kstride; it += ctx.nt) buf[it] = Kg[it];
+  }
   for (int it = ctx.tid; it < L.V * 7 * (NRED + 1); it += ctx.nt) {
     const int a = it / (7 * (NRED + 1)), r = (it / (NRED + 1)) % 7, cc = it % (NRED + 1);
     const bool active = i < L.N[a];
     const double* T = W.TT + (size_t)(a * L.Nmax + (active ? i : 0)) * (NW * NRED + NW);
     const double* src = cc < NRED ? T + (28 + r) * NRED + cc : T + NW * NRED + 28 + r;
 #if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(fT + it)), "l"(src), "r"(active ? 8 : 0) : "memory");
-#else
-    fT[it] = active ? *src : 0.0;
+    if (SM) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(fT + it)), "l"(src), "r"(active ? 8 : 0) : "memory");
+      continue;
+    }
 #endif
+    fT[it] = active ? *src : 0.0;
   }
 }
 
+template <bool SM>
 OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, double* RW, int* ok) {
   assume_scratch(W);
   const int nX = L.nX, nUmax = L.nU, idt = 7 * L.V, V = L.V, nc = nX + 1;
   const size_t pstride = (size_t)nX * nX + nX, kstride = ric_record_doubles(L), bstride = ric_fwd_buffer_doubles(L);
   RicWork R;
-  ric_carve(R, L, RW);  // R.npt (free directions of every block) is still valid; the stage matrices P .. K are dead and serve as scratch
+  ric_carve<SM>(R, L, RW);  // R.npt (free directions of every block) is still valid; the stage matrices P .. K are dead and serve as scratch
   double* fb0 = R.P;
   double* Xs = fb0 + 2 * bstride;   // [2][nX] state ping-pong
   double* fU = Xs + 2 * nX;         // [nUmax] compact controls of the stage
   double* X = W.RX;
   double* U = W.RX + (size_t)(L.Nmax + 1) * nX;
-  ric_fwd_fetch(ctx, L, W, 0, fb0);
+  ric_fwd_fetch<SM>(ctx, L, W, 0, fb0);
   if (ctx.tid == 0) {
     for (int a = 0; a < V; ++a)
       for (int q = 0; q < NZ; ++q) Xs[7 * a + q] = -W.c[L.YINIT(a, q)];
@@ -1829,7 +1851,7 @@ OBCA_HDN void riccati_forward(const Ctx& ctx, const Lay& L, const Scratch& W, do
     double* Xn = Xs + (size_t)((i + 1) & 1) * nX;
     ric_input_wait();
     cta_sync(ctx);  // stage i's record has landed, Xi is complete, fU of the previous stage has been consumed
-    if (i + 1 < L.Nmax) ric_fwd_fetch(ctx, L, W, i + 1, fb0 + (size_t)((i + 1) & 1) * bstride);
+    if (i + 1 < L.Nmax) ric_fwd_fetch<SM>(ctx, L, W, i + 1, fb0 + (size_t)((i + 1) & 1) * bstride);
     int nu = 0;
     for (int a = 0; a < V; ++a) nu += R.npt[a * L.Nmax + i];
     const double* Lf = buf + (size_t)nc * nUmax;
@@ -2166,12 +2188,15 @@ OBCA_HDN int kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratc
   interval_cross(ctx, L, W, RW);
   cta_sync(ctx);
   prof_mark(ctx, 5);
-  riccati_backward(ctx, L, W, RW, hdtdt, ok_shared);
+  // the Riccati arena: shared memory, or the per-slot global arena when the stage matrices of V > 4 vehicles do not fit
+  if (W.ricg) riccati_backward<false>(ctx, L, W, W.ricg, hdtdt, ok_shared);
+  else riccati_backward<true>(ctx, L, W, RW, hdtdt, ok_shared);
   cta_sync(ctx);
   prof_mark(ctx, 6);
   int ok = *ok_shared;
   if (!ok) return 0;
-  riccati_forward(ctx, L, W, RW, ok_shared);
+  if (W.ricg) riccati_forward<false>(ctx, L, W, W.ricg, ok_shared);
+  else riccati_forward<true>(ctx, L, W, RW, ok_shared);
   cta_sync(ctx);
   prof_mark(ctx, 7);
   ok = *ok_shared;

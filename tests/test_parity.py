@@ -222,3 +222,46 @@ def test_scaling_sweep_cells(request, strategy_file, agents, n_extra, nps, which
     assert worst["obstacle_clearance"] >= plan.problem.dmin - 1e-2
     if len(agents) > 1:
         assert worst["vehicle_clearance"] >= plan.problem.dmin - 1e-2
+
+
+REPL = [
+    pytest.param(("vehicle_1", "vehicle_2"), 3, 2, 1, "emu", id="emu-V6"),
+    pytest.param(("vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"), 2, 3, 4, "cuda", id="cuda-V8-O12", marks=pytest.mark.gpu),
+    pytest.param(("vehicle_1", "vehicle_2", "vehicle_3"), 2, 5, 4, "cuda", id="cuda-V6-O12-nps5", marks=pytest.mark.gpu),
+]
+
+
+@pytest.mark.parametrize("agents,copies,nps,B,which", REPL)
+def test_more_than_four_vehicles(request, strategy_file, agents, copies, nps, B, which):
+    """V > 4 (BASELINE.json configs[4]: up to 8 vehicles): replicated parking lots in one joint NLP -- copies * V vehicles, copies * 6
+    obstacles, all V' (V' - 1) / 2 pair blocks.  On the device the Riccati phase of these shapes runs from the global-memory arena
+    (7 V' + 1 > 29 states no longer fit shared memory).  Every plan must satisfy the reference problem statement by plain
+    geometry, and -- the lots do not interact -- reproduce the joint solution of a single lot."""
+    from conflict_rez_b200.control.batch_planner import prepare_joint_batch, prepare_replicated_batch, random_init_offsets
+
+    lib, dev = (request.getfixturevalue("emu_lib"), "cpu") if which == "emu" else (request.getfixturevalue("cuda_lib"), "cuda:0")
+    V = len(agents)
+    idx = [int(a[-1]) for a in agents]
+    offs1 = random_init_offsets(B, 4, seed=5)[:, idx]
+    offs = np.concatenate([offs1] * copies, axis=1)  # the same perturbation in every lot: the lots must then agree
+    opts = SolveOptions(max_iter=600)
+    plan = prepare_replicated_batch(strategy_file, list(agents), copies, offs, opts, device=dev, lib=lib, n_per_set=nps)
+    assert plan.problem.V == copies * V and plan.problem.O == 6 * copies and len(plan.problem.pairs) == copies * V * (copies * V - 1) // 2
+    res = plan.solver.solve(plan.guess)
+    plan.solver.close()
+    assert (res.status >= 0).all(), res.status
+    worst = check_solution_properties(plan.problem, res.z, res.dt)
+    assert worst["collocation"] <= 1e-2 and worst["tube"] <= 1e-2 and worst["terminal"] <= 1e-2 and worst["init"] <= 1e-2
+    assert worst["obstacle_clearance"] >= plan.problem.dmin - 1e-2 and worst["vehicle_clearance"] >= plan.problem.dmin - 1e-2
+    # the lots are copies of each other: same trajectories up to the translation (loose: the solves stop at tol = 1e-2)
+    dmax, dmean = 0.0, []
+    for c in range(1, copies):
+        for a in range(V):
+            M = int(plan.problem.nodes[a])
+            zc = res.z[:, c * V + a, :M, :3].copy()
+            zc[..., 0] -= 35.0 * c
+            d = np.abs(zc - res.z[:, a, :M, :3])
+            dmax, dmean = max(dmax, d.max()), dmean + [d.mean()]
+    print("lot-to-lot difference: max %.3e mean %.3e" % (dmax, np.mean(dmean)))
+    assert np.mean(dmean) <= 2e-2 and dmax <= 1.0
+    print("V=%d iterations" % (copies * V), res.iters)
