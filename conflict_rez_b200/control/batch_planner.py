@@ -27,6 +27,13 @@ def random_init_offsets(batch: int, n_vehicles: int, seed: int = 0) -> np.ndarra
     return off * np.array([0.15, 0.15, np.pi / 20])
 
 
+def shard_instances(global_batch: int, rank: int, world: int) -> np.ndarray:
+    """Indices of the instances rank ``rank`` owns: a fixed GLOBAL batch dealt out round robin (instance b -> rank b % world).
+    The instances are i.i.d. draws, so every rank gets the same expected load and no data-path collective is needed
+    (SURVEY.md 8e); with the contiguous block partition of round 1 one unlucky rank set the step time."""
+    return np.arange(rank, global_batch, world)
+
+
 def joint_guess_from_singles(prob: CollocationProblem, singles: Sequence[BatchResult]) -> CollocationGuess:
     """Joint warm start: per-agent single solutions, dt0 = mean of the agents' dt (multi_vehicle_planner.py:360),
     pair duals from the closed-form ``joint_dual_ws``."""

@@ -646,15 +646,24 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
 // elastic variable is active gets the closed-form separating duals of its current poses (obca_ws.h, the same formulas as the
 // dual warm start), and the interior-point iteration restarts from that point.
 template <int MODE>
-OBCA_HDN void dual_restore(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double thr) {
+OBCA_HDN int dual_restore(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double thr) {
   assume_scratch(W);
   OBCA_ASSUME_STATIC(L, S);
   double* x = W.x;
+  int improved = 0;  // blocks whose distance row gains more than thr from the separating duals: only those justify a restart
   for (int it = ctx.tid; it < L.V * L.O * L.Mv; it += ctx.nt) {
     const int n = it % L.Mv, aj = it / L.Mv, a = aj / L.O, j = aj % L.O;
     if (n >= L.M[a] || !(x[L.EL(a, j, n)] > thr)) continue;
     double lam[4], mu[4];
-    ws_obstacle_duals(S, j, x[L.Z(a, 0, n)], x[L.Z(a, 1, n)], x[L.Z(a, 2, n)], lam, mu);
+    const double px = x[L.Z(a, 0, n)], py = x[L.Z(a, 1, n)];
+    ws_obstacle_duals(S, j, px, py, x[L.Z(a, 2, n)], lam, mu);
+    double d_new = 0, d_old = 0;
+    for (int r = 0; r < 4; ++r) {
+      const double atb = S.obsA[j][r][0] * px + S.obsA[j][r][1] * py - S.obsb[j][r];
+      d_new += atb * lam[r] - S.g[r] * mu[r];
+      d_old += atb * x[L.LAM(a, j, r, n)] - S.g[r] * x[L.MU(a, j, r, n)];
+    }
+    if (d_new > d_old + thr) ++improved;
     for (int r = 0; r < 4; ++r) x[L.LAM(a, j, r, n)] = lam[r], x[L.MU(a, j, r, n)] = mu[r];
   }
   for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
@@ -664,12 +673,18 @@ OBCA_HDN void dual_restore(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
     load_pose(L, x, L.pa[p], n, a);
     if (MODE == 1) load_other_pose(L, mpc_par(L, W), p, n, b);
     else load_pose(L, x, L.pb[p], n, b);
-    double lam[4], mu[4], sv[2];
-    ws_pair_duals(S, a.x, a.y, a.psi, b.x, b.y, b.psi, lam, mu, sv);
-    for (int r = 0; r < 4; ++r) x[L.PL(p, r, n)] = lam[r], x[L.PM(p, r, n)] = mu[r];
-    x[L.PS(p, 0, n)] = sv[0], x[L.PS(p, 1, n)] = sv[1];
+    PairBlk B;
+    load_pair(L, x, p, n, B);
+    pair_residual(S, a, b, B);
+    const double d_old = B.c[0] + B.sd - B.el;  // -b_a'lam - b_b'mu - dmin with the current duals
+    ws_pair_duals(S, a.x, a.y, a.psi, b.x, b.y, b.psi, B.lam, B.mu, B.s);
+    pair_residual(S, a, b, B);
+    if (B.c[0] + B.sd - B.el > d_old + thr) ++improved;
+    for (int r = 0; r < 4; ++r) x[L.PL(p, r, n)] = B.lam[r], x[L.PM(p, r, n)] = B.mu[r];
+    x[L.PS(p, 0, n)] = B.s[0], x[L.PS(p, 1, n)] = B.s[1];
   }
   cta_sync(ctx);
+  return (int)cta_sum(ctx, (double)improved);
 }
 
 template <int MODE>
@@ -687,7 +702,11 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
       status = OBCA_INFEASIBLE_PROBLEM_DETECTED;
       break;
     }
-    dual_restore<MODE>(ctx, L, S, W, thr);
+    if (dual_restore<MODE>(ctx, L, S, W, thr) == 0) {
+      // the duals already are the separating ones: the shapes themselves are closer than dmin -- nothing to restore
+      status = OBCA_INFEASIBLE_PROBLEM_DETECTED;
+      break;
+    }
     ++restarts;
   }
   if (ctx.tid == 0) res->status = status, res->restarts = restarts;

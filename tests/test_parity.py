@@ -141,6 +141,10 @@ def test_batch_equals_individual_solves_and_is_deterministic(backend, strategy_f
     sv = _solver(backend, prob)
     r1, r2 = sv.solve(guess), sv.solve(guess)
     assert np.array_equal(r1.z, r2.z) and np.array_equal(r1.iters, r2.iters)
+    sv.set_order(np.array([1.0, 3.0, 2.0]))  # longest-expected-first queue (obca_set_order): another processing order, same results
+    r3 = sv.solve(guess)
+    assert np.array_equal(r1.z, r3.z) and np.array_equal(r1.iters, r3.iters) and np.array_equal(r1.obj, r3.obj)
+    sv.set_order(None)
     assert (r1.status == 0).all()
     assert np.abs(r1.z[:, 0, 0, :3] - prob.init_pose[:, 0]).max() <= 1e-6
     for b in range(3):
