@@ -41,12 +41,13 @@ NCU = {"dram_bytes_per_iter": 21.9e6, "fp64_pipe_pct": 6.7, "issue_active_pct": 
 
 def load_ncu():
     """The committed ncu summary of the current kernel, if this round produced one (profiles/r02_ncu_k_solve.json)."""
-    path = os.path.join(ROOT, "profiles", "r02_ncu_k_solve.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            d = json.load(f)
-        d["source"] = "profiles/r02_ncu_k_solve.json"
-        return d
+    for name in ("r02g_ncu_k_solve.json", "r02_ncu_k_solve.json"):  # newest first
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as f:
+                d = json.load(f)
+            d["source"] = "profiles/" + name
+            return d
     return dict(NCU)
 
 
@@ -289,6 +290,67 @@ def latency_single_instance(fn, device, opts):
     return out
 
 
+# (vehicles, obstacles, intervals per move): BASELINE.json configs[4] -- V 2-8 x O 5-20 x N 20-100 at batch 1024.  The parking lot
+# has 6 obstacles (fewer is not this scenario), extra ones are seeded rectangles between the tubes; N = n_per_set x 9 moves
+SWEEP_CELLS = [(2, 6, 5), (4, 6, 5), (8, 12, 5), (4, 10, 5), (4, 20, 5), (4, 6, 2), (4, 6, 11), (8, 12, 2)]
+
+
+def sweep_leg(fn, device, tol, batch, cells=None):
+    """Scaling sweep: one batched joint solve per cell, device-timed (1 warm-up + 1 timed launch, warm start untimed)."""
+    import torch
+
+    from conflict_rez_b200.control.batch_planner import prepare_joint_batch, prepare_replicated_batch, random_init_offsets
+    from conflict_rez_b200.control.scenario import random_obstacles
+    from conflict_rez_b200.solver import RETURN_STATUS, SolveOptions
+
+    out = []
+    opts = SolveOptions(tol=tol, constr_viol_tol=tol, max_iter=600)
+    for V, O, nps in cells or SWEEP_CELLS:
+        t0 = time.perf_counter()
+        copies = 2 if V > 4 else 1
+        v1 = V // copies
+        agents = AGENTS if v1 == 4 else ["vehicle_1", "vehicle_2"] if v1 == 2 else AGENTS[1:1 + v1]
+        idx = [int(a[-1]) for a in agents]
+        heads = {a: HEADINGS[a] for a in agents}
+        kw = dict(n_per_set=nps, final_headings=heads)
+        n_extra = O // copies - 6
+        if n_extra > 0:
+            kw["obstacles"] = random_obstacles(fn, n_extra, seed=7)
+        offs = random_init_offsets(batch, 4 * copies, seed=3).reshape(batch, copies, 4, 3)[:, :, idx].reshape(batch, copies * v1, 3)
+        try:
+            if copies == 1:
+                plan = prepare_joint_batch(fn, agents, offs, opts, device=device, **kw)
+            else:
+                plan = prepare_replicated_batch(fn, agents, copies, offs, opts, device=device, **kw)
+            sv = plan.solver
+            sv.set_order(np.sum([r.iters for r in plan.singles[:v1]], axis=0))
+            torch.cuda.synchronize(device)
+            t_ws = time.perf_counter() - t0
+            sv.set_inputs(plan.dev_guess), sv.run(), sv.fetch_stats()
+            torch.cuda.synchronize(device)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sv.set_inputs(plan.dev_guess)
+            a0.record()
+            sv.run()
+            a1.record()
+            st, it, _ = sv.fetch_stats()
+            torch.cuda.synchronize(device)
+            st, it = st.cpu().numpy(), it.cpu().numpy()
+            ms = a0.elapsed_time(a1)
+            L = sv.layout()
+            out.append({"vehicles": plan.problem.V, "obstacles": plan.problem.O, "intervals": int(plan.problem.nodes.max()) // 6, "batch": batch,
+                        "nx": L["nx"], "ny": L["ny"], "solves_per_s": float((st >= 0).sum()) / (ms / 1e3), "k_solve_ms": ms,
+                        "converged_fraction": float((st >= 0).mean()), "iters_median": float(np.median(it)), "iters_max": int(it.max()),
+                        "ms_per_iteration_and_instance": ms * min(batch, 148) / float(it.sum()),
+                        "status_hist": {RETURN_STATUS[int(k)]: int(v) for k, v in zip(*np.unique(st, return_counts=True))},
+                        "warm_start_s": t_ws})
+            sv.close()
+        except Exception as e:  # a cell that does not fit (memory, shape limits) is reported, not hidden
+            out.append({"vehicles": V, "obstacles": O, "n_per_set": nps, "batch": batch, "error": "%s: %s" % (type(e).__name__, str(e)[:300])})
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -303,6 +365,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the tight-tolerance leg, the single-instance latencies and the MPC leg")
     ap.add_argument("--mpc-steps", type=int, default=250)
     ap.add_argument("--tight-batch", type=int, default=592)
+    ap.add_argument("--sweep", action="store_true", help="add the scaling sweep (BASELINE.json configs[4]) at --sweep-batch instances per cell")
+    ap.add_argument("--sweep-batch", type=int, default=1024)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -561,6 +625,8 @@ def main():
         tsv.close()
         line["latency"] = latency_single_instance(fn, device, opts)
         line["mpc"] = mpc_latency(fn, device, args.mpc_steps)
+    if world == 1 and args.sweep:
+        line["sweep"] = sweep_leg(fn, device, args.tol, args.sweep_batch)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(fn, offs_all, args.tol, plan=plan)
     sv.close()

@@ -351,6 +351,7 @@ struct Result {
   double obj, cviol, dual_inf, compl_inf, mu, dt;
   double elastic;  // largest elastic variable at the returned point
   int refines, restarts;  // correction solves of the refinement loop; dual restorations (obca_ipm.h)
+  double rho_carry;       // MPC mode: raised penalty weight kept for the next control step of this vehicle (0: none)
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -66,7 +66,9 @@ OBCA_HD void flat_pass_impl(const Ctx& ctx, const Stage& st, const BoundCls* bc,
 #if defined(__CUDA_ARCH__)
   constexpr int TILE_D = NA * ST_TILE + (CLS ? ST_TILE / 8 : 0);  // doubles per stage buffer
   // ring depth 3: measured, a deeper ring (up to 8 tiles in flight) is 8 % slower -- the passes are bound by the FP64 instruction
-  // latency of the bodies at 2 warps per scheduler, not by bytes in flight (profiles/r02_flat_pass_experiments.txt)
+  // latency of the bodies at 2 warps per scheduler, not by bytes in flight.  Also measured and
+  // dropped: a warp-uniform fast path for tiles of plain non-negative variables (constant bounds, the four elements of a thread as one
+  // straight-line block): 5.98 vs 5.90 M cycles per iteration, no gain (profiles/r02h_phase_cycles_flat_fast_path_rejected.txt)
   const int ST_STAGES = st.cap / TILE_D >= 3 ? 3 : 0;
   if (st.buf && ST_STAGES >= 3 && n >= 4 * ST_TILE && ctx.nt * 4 == ST_TILE) {
     const int ntile = (n + ST_TILE - 1) / ST_TILE;
@@ -664,6 +666,9 @@ OBCA_HDN int dual_restore(const Ctx& ctx, const Lay& L, const Stat& S, const Scr
       d_old += atb * x[L.LAM(a, j, r, n)] - S.g[r] * x[L.MU(a, j, r, n)];
     }
     if (d_new > d_old + thr) ++improved;
+#ifdef OBCA_HOST_EMU
+    if (getenv("OBCA_TRACE_RESTORE")) printf("restore obs j=%d n=%d el=%.4f d_old=%.4f d_new=%.4f pose %.3f %.3f %.3f\n", j, n, x[L.EL(a, j, n)], d_old, d_new, px, py, x[L.Z(a, 2, n)]);
+#endif
     for (int r = 0; r < 4; ++r) x[L.LAM(a, j, r, n)] = lam[r], x[L.MU(a, j, r, n)] = mu[r];
   }
   for (int it = ctx.tid; it < L.P * L.Mv; it += ctx.nt) {
@@ -693,23 +698,52 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
   int it = 0, n_refine = 0, restarts = 0, status;
   double el_max;
   const double thr = fmax(o.constr_viol_tol, 1e-8);
+  // S is this CTA's private copy of the static data (shared memory on the device): the penalty weight of the elastic variables
+  // may be raised for the instance at hand and is put back before the next one
+  double* rho = const_cast<double*>(&S.rho);
+  const double rho0 = S.rho;
+  // MPC mode: the solves of one handle are consecutive control steps of the same vehicle; a weight that had to be raised stays
+  // raised for the next step (the geometry that made the penalty inexact is still there) and is dropped after a failed solve
+  const double carry = MODE == 1 ? res->rho_carry : 0.0;
+  cta_sync(ctx);
+  if (carry > rho0) {
+    if (ctx.tid == 0) *rho = carry;
+    cta_sync(ctx);
+  }
   for (;;) {
     status = ipm_attempt<MODE>(ctx, L, S, o, cnt, xL, xU, bcls, W, RW, rw_cap, sh, res, it, n_refine, &el_max);
+#ifdef OBCA_HOST_EMU
+    if (getenv("OBCA_TRACE_RESTORE")) printf("attempt: status %d it %d el_max %.4f restarts %d rho %.1e\n", status, it, el_max, restarts, S.rho);
+#endif
     if (!(status >= 0 && el_max > thr)) break;
-    if (restarts >= 2 || it >= o.max_iter) {
+    if (restarts >= 5 || it >= o.max_iter) {
       // a converged point of the penalised problem with an active elastic variable: the reference problem (hard distance rows)
       // is locally infeasible there; IPOPT reports Infeasible_Problem_Detected and Opti raises
       status = OBCA_INFEASIBLE_PROBLEM_DETECTED;
       break;
     }
     if (dual_restore<MODE>(ctx, L, S, W, thr) == 0) {
-      // the duals already are the separating ones: the shapes themselves are closer than dmin -- nothing to restore
-      status = OBCA_INFEASIBLE_PROBLEM_DETECTED;
-      break;
+      // The duals already are the separating ones: the minimiser of the PENALISED problem really is closer than dmin -- the
+      // l1 penalty was not exact for this instance (the MPC tracking cost, 100 per m^2 and node, can outweigh rho = 1e3).
+      // Exact-penalty update: raise the weight and solve again from this point; give up when a 1e4 times larger weight still
+      // leaves a violation (then the hard-constrained problem has no solution nearby).
+      if (S.rho >= 1e4 * rho0) {
+        status = OBCA_INFEASIBLE_PROBLEM_DETECTED;
+        break;
+      }
+      cta_sync(ctx);
+      if (ctx.tid == 0) *rho = S.rho * 10.0;
+      cta_sync(ctx);
     }
     ++restarts;
   }
-  if (ctx.tid == 0) res->status = status, res->restarts = restarts;
+  cta_sync(ctx);
+  if (ctx.tid == 0) {
+    res->status = status, res->restarts = restarts;
+    res->rho_carry = (MODE == 1 && status >= 0 && S.rho > rho0) ? S.rho : 0.0;
+    *rho = rho0;
+  }
+  cta_sync(ctx);
 }
 
 }  // namespace obca

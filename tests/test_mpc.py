@@ -215,3 +215,34 @@ def test_device_resident_loop_reproduces_the_host_loop(backend, strategy_file):
         per_step = g.run(steps, graph=True)
         assert per_step > 0
         assert np.abs(g.export()["state"] - out["state"]).max() <= 1e-8
+
+
+def test_inexact_penalty_is_escalated_and_carried_over(backend, strategy_file):
+    """4-vehicle scene (the bench's MPC leg).  vehicle_1's plan passes an obstacle corner so closely that the minimiser of the
+    penalised problem (rho = 1e3 against a tracking cost of 100 per m^2 and node) cuts the corner by 7 cm with the *separating*
+    duals -- the l1 penalty is not exact there.  The solver must raise the weight and return a feasible plan (round 2: it returned
+    Infeasible_Problem_Detected for the first 31 control steps), and the raised weight must carry over to the next control step of
+    that vehicle (second step without a second attempt: far fewer iterations than the first)."""
+    from conflict_rez_b200.control.vehicle_follower import MultiDistributedFollower
+
+    lib, dev = backend
+    agents = ["vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"]
+    heads = {"vehicle_0": 0.0, "vehicle_1": 3 * np.pi / 2, "vehicle_2": np.pi, "vehicle_3": np.pi / 2}
+    np.random.seed(0)
+    mdf = MultiDistributedFollower(strategy_file, {a: True for a in agents}, {a: {} for a in agents}, {a: VehicleState() for a in agents}, heads, device=dev, lib=lib)
+    mdf.setup_multi_vehicles()
+    log = []
+    orig = mdf.solver.solve_step
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        log.append((r.status.copy(), r.iters.copy(), r.elastic.copy()))
+        return r
+
+    mdf.solver.solve_step = spy
+    mdf.solve(num_iter=3)
+    for st, it, el in log:
+        assert (st == 0).all(), st
+        assert el.max() <= 1e-2
+    assert log[1][1][1] < log[0][1][1] // 2, (log[0][1], log[1][1])
+    assert mdf.failed_solves == 0
