@@ -78,6 +78,22 @@ def build_problem(
     )
 
 
+def kinematic_paths(prob: CollocationProblem, rl_file_name: str, agents: Sequence[str], N_ws: int = 30, dt_ws: float = 0.1):
+    """Per agent the kinematic guess on the uniform grid of ``Vehicle.state_ws`` (N_ws samples per move): list of (B,T_a,7) arrays
+    (x, y, psi, v, delta, a, w), blended towards each instance's perturbed initial pose like ``pose_guess``."""
+    vb = VehicleBody()
+    paths = interp_along_sets(rl_file_name, vb, N_ws)
+    init = prob.init_pose if prob.batch is not None else prob.init_pose[None]
+    out = []
+    for ia, a in enumerate(agents):
+        path0 = paths[a]
+        blend = np.clip(1.0 - np.arange(len(path0)) / float(N_ws), 0.0, 1.0)[:, None]
+        path = path0[None] + blend[None] * (init[:, ia] - path0[0])[:, None, :]
+        kin = warmstart.kinematic_guess(path, dt_ws, prob.wb, prob.limits)
+        out.append(np.stack([kin[k] for k in ("x", "y", "psi", "v", "delta", "a", "w")], axis=-1))
+    return out
+
+
 def pose_guess(prob: CollocationProblem, rl_file_name: str, agents: Sequence[str], N_ws: int = 30, dt_ws: float = 0.1):
     """Spline pose guess -> kinematic state guess -> Radau resampling, vectorised over the batch: z (B,V,Mmax,7), dts (B,V).
 

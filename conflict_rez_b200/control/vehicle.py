@@ -6,10 +6,10 @@ and ``solve_single_final_problem`` calls the CUDA solver (:class:`~conflict_rez_
 The returned ``sol`` offers what the reference consumes from ``OptiSol``: ``stats()["return_status"]``,
 ``stats()["t_wall_total"]`` and an exception on non-success.
 
-Deviations (documented, warm-start stages only -- SURVEY.md section 8f-1):
-* ``state_ws`` reconstructs a kinematic state guess from the Bezier pose guess instead of solving the Euler NLP
-  (vehicle.py:116-216);
-* ``dual_ws`` uses the closed-form rectangle-distance duals instead of an IPOPT solve (vehicle.py:250-294).
+Warm-start stages:
+* ``state_ws`` solves the reference's Euler-discretised tube-following NLP (vehicle.py:116-216) on the device, started from the spline
+  guess whatever ``spline_ws`` says (the all-zero start needs IPOPT's restoration phase);
+* ``dual_ws`` uses the closed-form rectangle-distance duals instead of an IPOPT solve (vehicle.py:250-294) -- the same optimum.
 """
 import time
 from typing import Dict, Optional, Tuple
@@ -71,37 +71,47 @@ class Vehicle(object):
     # ------------------------------------------------------------------ warm start
     def state_ws(self, N: int = 30, dt: float = 0.1, init_offset: VehicleState = VehicleState(), final_heading: float = None,
                  bounded_input: bool = False, shrink_tube: float = 0.8, spline_ws: bool = False, verbose: int = 0) -> VehiclePrediction:
-        """Tube-following state warm start (vehicle.py:99-231).  The reference solves an Euler-discretised NLP without
-        obstacles; here the *collocation* problem without obstacles is solved on the device from the kinematic
-        reconstruction of the Bezier pose guess, and its solution is sampled on the reference's uniform grid."""
+        """Tube-following state warm start (vehicle.py:99-231): the reference's Euler-discretised NLP -- nodes 0 .. N (num_sets - 1),
+        cost sum a^2 + w^2, tube sets at k = N i, a_0 = w_0 = 0, optional final heading, input bounds only with ``bounded_input`` --
+        solved on the device (``ObcaStateWsSolver``, OBCA_MODE_STATE_WS).  Initial guess: the Bezier pose guess through the sets
+        (what ``spline_ws=True`` passes to ``opti.set_initial``) completed by the speeds of its kinematic reconstruction; the
+        all-zero start of ``spline_ws=False`` (outside the region, IPOPT reaches the tube through its restoration phase) is not
+        reproduced -- both settings start from the spline.  Output as the reference returns it: uniform grid t, inputs padded by
+        their last value (vehicle.py:219-229)."""
+        from conflict_rez_b200.solver import ObcaStateWsSolver, StateWsProblem
+
         path = interp_along_sets(self.rl_file_name, self.vehicle_body, N)[self.agent].copy()
         off = np.array([init_offset.x.x, init_offset.x.y, init_offset.e.psi])
         path += np.clip(1.0 - np.arange(len(path)) / float(N), 0.0, 1.0)[:, None] * off[None, :]
-        vc = self.vehicle_config
+        vc, rg = self.vehicle_config, self.region
         limits = np.array([vc.v_min, vc.v_max, vc.delta_min, vc.delta_max, vc.a_min, vc.a_max, vc.w_delta_min, vc.w_delta_max], dtype=float)
         kin = warmstart.kinematic_guess(path, dt, self.vehicle_body.wb, limits)
         names = ("x", "y", "psi", "v", "delta", "a", "w")
-        K, nps = 5, 5
-        Ncol = nps * (self.num_sets - 1)
-        zc = np.stack([warmstart.resample_for_collocation(kin["t"], kin[k], Ncol, K) for k in names], axis=1)
-        tube = JointProblem([], self.vehicle_body, self.vehicle_config, self.region)
-        tube.add_vehicle(dict(agent=self.agent, tube=self.rl_tube, pose0=path[0] * 1.0, heading=final_heading, z=zc,
-                              lam=np.zeros((len(zc), 0, 4)), mu=np.zeros((len(zc), 0, 4)), dt0=kin["t"][-1] / Ncol),
-                         dict(K=K, n_per_set=nps, dmin=0.05, shrink_tube=shrink_tube), None)
-        try:
-            sol = tube.solve(self.solve_options, self.device, getattr(self, "_lib", None))
-            r = sol.result
-            tn = ((np.arange(Ncol)[:, None] + warmstart.radau_nodes(K)[None, :]).ravel()) * float(r.dt[0])
-            tu = np.linspace(0.0, tn[-1], len(kin["t"]))
-            kin = {k: np.interp(tu, tn, r.z[0, 0, : len(tn), c]) for c, k in enumerate(names)}
-            kin["t"] = tu
-        except RuntimeError as e:  # keep the kinematic guess when the tube-following solve does not converge
-            if not hasattr(e, "sol"):
-                raise
+        S = self.num_sets
+        tube_A, tube_b = np.zeros((S, 2, 4, 2)), np.zeros((S, 2, 4))
+        for q, sets in enumerate(self.rl_tube):
+            for ib, body in enumerate(("back", "front")):
+                tube_A[q, ib], tube_b[q, ib] = sets[body].A, np.ravel(sets[body].b)
+        prob = StateWsProblem(tube_A=tube_A, tube_b=tube_b, N=N, dt=dt, final_heading=final_heading, bounded_input=bounded_input, shrink_tube=shrink_tube,
+                              wb=self.vehicle_body.wb, region=np.array([rg.x_min, rg.x_max, rg.y_min, rg.y_max]), limits=limits)
+        M = prob.nodes
+        assert len(path) == M, (len(path), M)
+        z0 = np.stack([kin[k] for k in names], axis=1)
+        cur = np.array([path[0, 0], path[0, 1], path[0, 2], 0.0, 0.0])
+        sv = ObcaStateWsSolver(prob, SolveOptions(tol=1e-2, constr_viol_tol=1e-2, max_iter=500), device=self.device, lib=getattr(self, "_lib", None))  # vehicle.py:207-213
+        res = sv.solve_ws(cur[None], z0[None])
+        sv.close()
+        self.state_ws_result = res
+        if verbose:
+            print(res.return_status(0))
+        if res.status[0] >= 0:
+            kin = {k: res.z[0, 0, :, c].copy() for c, k in enumerate(names)}
         result = VehiclePrediction()
-        result.t = kin["t"]
+        result.t = np.linspace(0, (M - 1) * dt, M, endpoint=True)
         result.x, result.y, result.psi, result.v = kin["x"], kin["y"], kin["psi"], kin["v"]
-        result.u_a, result.u_steer, result.u_steer_dot = kin["a"], kin["delta"], kin["w"]
+        result.u_steer = kin["delta"]
+        result.u_a = np.append(kin["a"][:-1], kin["a"][-2])
+        result.u_steer_dot = np.append(kin["w"][:-1], kin["w"][-2])
         return result
 
     def _obstacle_arrays(self):

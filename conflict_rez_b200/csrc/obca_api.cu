@@ -350,6 +350,10 @@ int obca_create(const ObcaDims* dims, const ObcaOptions* opts, int device, ObcaH
   if (dims->mode == OBCA_MODE_MPC) {
     if (dims->horizon < 2 || dims->horizon > 4096) return fail("obca_create: MPC horizon out of range");
     if (dims->n_others < 0 || dims->n_others > MAXP) return fail("obca_create: n_others out of range");
+  } else if (dims->mode == OBCA_MODE_STATE_WS) {
+    if (dims->n_per_set < 1 || dims->n_sets[0] < 2 || dims->n_sets[0] > OBCA_MAX_SETS) return fail("obca_create: state_ws needs n_per_set >= 1 and 2 <= n_sets[0] <= 64");
+    if (dims->n_per_set * (dims->n_sets[0] - 1) + 1 > 4096) return fail("obca_create: state_ws horizon out of range");
+    if (dims->O != 0) return fail("obca_create: the state warm start has no obstacles (O must be 0)");
   } else if (dims->mode == OBCA_MODE_COLLOCATION) {
     if (dims->V < 1 || dims->V > OBCA_MAX_V) return fail("obca_create: V out of range");
     if (dims->n_per_set < 1) return fail("obca_create: bad n_per_set");
@@ -431,8 +435,10 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   if (!h || !st) return fail("obca_set_static: null argument");
   DeviceGuard guard(h->device);
   free_device(h);
-  const bool mpc = h->dims.mode == OBCA_MODE_MPC;
-  if (mpc) lay_build_mpc(h->L, h->dims.horizon, h->dims.O, h->dims.n_others);
+  const bool sws = h->dims.mode == OBCA_MODE_STATE_WS;
+  const bool mpc = h->dims.mode == OBCA_MODE_MPC || sws;  // the state warm start shares the MPC layout and kernels (obca_mpc.h)
+  if (sws) lay_build_state_ws(h->L, h->dims.n_sets[0], h->dims.n_per_set, h->dims.bounded_input != 0, st->final_heading && st->final_heading[0] == st->final_heading[0]);
+  else if (mpc) lay_build_mpc(h->L, h->dims.horizon, h->dims.O, h->dims.n_others);
   else lay_build(h->L, h->dims, st->final_heading);
   Lay& L = h->L;
   Stat& S = h->S;
@@ -446,7 +452,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   S.wb = st->wb, S.dmin = h->dmin, S.rho = h->rho, S.dt_mpc = st->mpc_dt;
   for (int q = 0; q < 4; ++q) S.region[q] = st->region[q];
   for (int q = 0; q < 8; ++q) S.limits[q] = st->limits[q];
-  for (int a = 0; a < L.V; ++a) S.heading[a] = mpc ? 0.0 : st->final_heading[a];
+  for (int a = 0; a < L.V; ++a) S.heading[a] = (mpc && !sws) ? 0.0 : (L.heading[a] ? st->final_heading[a] : 0.0);
   collocation_matrices(S.cA, S.cB);
   if (st->colloc_A && st->colloc_B && !mpc)  // the caller's constants (the reference builds them with numpy poly1d arithmetic): bit-identical parity
     for (int j = 0; j < NK; ++j) {
@@ -475,7 +481,7 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
       for (int k = 0; k < 5; ++k) S.cAi[j][k] = M[j][5 + k];  // (A1^-1)[j][k]: x_j = sum_k cAi[j][k] rhs_k
   }
   std::vector<double> tube((size_t)L.V * L.Smax * 2 * 4 * 3);
-  for (int a = 0; a < L.V && !mpc; ++a)
+  for (int a = 0; a < L.V && (!mpc || sws); ++a)
     for (int q = 0; q < L.Smax; ++q)
       for (int body = 0; body < 2; ++body)
         for (int r = 0; r < 4; ++r) {
@@ -498,7 +504,14 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
     }
     for (int q = 0; q < L.S[a] - 1; ++q)
       for (int r = 0; r < 8; ++r) xL[L.TS(a, q, r)] = 0;
-    if (mpc) m_active += 5 + 5 * (L.M[a] - 1) + 4 * L.O * L.M[a];
+    if (sws) {
+      // vehicle.py:140-167: bounds at k < N M only, input bounds only with bounded_input
+      for (int c = 0; c < NZ; ++c) xL[L.Z(a, c, L.M[a] - 1)] = -INFINITY, xU[L.Z(a, c, L.M[a] - 1)] = INFINITY;
+      if (L.euler != 2)
+        for (int n = 0; n < L.M[a]; ++n)
+          for (int c = 5; c < NZ; ++c) xL[L.Z(a, c, n)] = -INFINITY, xU[L.Z(a, c, n)] = INFINITY;
+      m_active += 7 + 5 * (L.M[a] - 1) + 8 * (L.S[a] - 1) + L.heading[a];
+    } else if (mpc) m_active += 5 + 5 * (L.M[a] - 1) + 4 * L.O * L.M[a];
     else m_active += 7 + 5 * L.M[a] + 7 * (L.N[a] - 1) + 4 + L.heading[a] + 4 * L.O * L.M[a] + 8 * (L.S[a] - 1);
   }
   for (int p = 0; p < L.P; ++p) {
@@ -531,6 +544,12 @@ int obca_set_static(ObcaHandle* h, const ObcaStatic* st) {
   h->ric_stride = 0;
 #ifndef OBCA_HOST_EMU
   const size_t smem_cap = (size_t)(CTAS_PER_SM == 1 ? 200 : 100) * 1024;
+  if (mpc && h->rw_stride * sizeof(double) > smem_cap) {
+    // long horizons (the 271-node state warm start): the stage buffers of the MPC-mode solve live in a per-slot global arena;
+    // the shared arena only stages the flat passes
+    h->ric_stride = h->rw_stride;
+    h->rw_stride = 1024;
+  }
   if (!mpc && h->rw_stride * sizeof(double) > smem_cap) {
     // more than 4 vehicles: the stage matrices of the joint Riccati state (7 V + 1) do not fit next to the null-space work areas;
     // the Riccati phase then runs from a per-slot arena in global memory (L2 resident), everything else keeps the shared arena
@@ -827,6 +846,10 @@ __global__ void k_shift(const double* in, double* out, int N, int Wd, size_t tot
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g < tot) shift_item(in, out, N, Wd, g);
 }
+__global__ void k_ws_interp(const double* in, const double* t, InterpConst C6, int T, int C, int N, double* out, size_t tot) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < tot) ws_interp_item(in, t, C6.tau, T, C, N, out, g);
+}
 static int check_device(int device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device (this library has no CPU fallback)");
@@ -858,6 +881,25 @@ int obca_interpolate(int device, const double* z, const double* dt, const int32_
   for (int k = 0; k < NK; ++k) C.tau[k] = tau[k];
   A.n_intervals = nullptr, A.tau = nullptr;
   k_interpolate<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A, C, tot);
+  CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+int obca_interp_ws(int device, const double* in, const double* t, const double* tau, int B, int T, int C, int N, double* out, void* stream) {
+  if (!in || !t || !tau || !out) return fail("obca_interp_ws: null argument");
+  if (B < 1 || T < 2 || C < 1 || N < 1) return fail("obca_interp_ws: bad dimensions");
+  if (check_device(device)) return -1;
+  DeviceGuard guard(device);
+  const size_t tot = (size_t)B * N * NK * C;
+#ifdef OBCA_HOST_EMU
+  (void)stream;
+  for (size_t g = 0; g < tot; ++g) ws_interp_item(in, t, tau, T, C, N, out, g);
+#else
+  InterpConst C6;
+  for (int a = 0; a < OBCA_MAX_V; ++a) C6.n_intervals[a] = 0;
+  for (int k = 0; k < NK; ++k) C6.tau[k] = tau[k];
+  k_ws_interp<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(in, t, C6, T, C, N, out, tot);
   CUDA_OK(cudaGetLastError());
 #endif
   return 0;

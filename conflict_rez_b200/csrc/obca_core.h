@@ -88,6 +88,9 @@ constexpr double PIVOT_TOL = OBCA_PIVOT_TOL;  // relative size below which a Ric
 // ------------------------------------------------------------------------------------------------
 struct Lay {
   int mode;  // 0 = collocation OBCA (single / joint), 1 = MPC (obca_mpc.h)
+  int euler; // mode 1 only: 1 = the Euler-discretised tube-following NLP of Vehicle.state_ws (vehicle.py:99-231) instead of the MPC NLP:
+             // forward-Euler dynamics, cost a^2 + w^2, tube sets every npset nodes, a_0 = w_0 = 0, optional final heading; 2 = same
+             // with bounded inputs
   int V, O, P, Mv, Nmax, Smax, npset;
   int N[MAXV], M[MAXV], S[MAXV], heading[MAXV];
   int pa[MAXP], pb[MAXP], Mp[MAXP];
@@ -124,6 +127,7 @@ inline void lay_offsets(Lay& L);
 
 inline void lay_build(Lay& L, const ObcaDims& d, const double* final_heading) {
   L.mode = 0;
+  L.euler = 0;
   L.V = d.V;
   L.O = d.O;
   L.npset = d.n_per_set;
@@ -184,6 +188,7 @@ inline void lay_offsets(Lay& L) {
 // MPC problem: one vehicle, N nodes, P other vehicles (parameters); YCOL rows are the dynamics rows
 inline void lay_build_mpc(Lay& L, int horizon, int n_obstacles, int n_others) {
   L.mode = 1;
+  L.euler = 0;
   L.V = 1, L.O = n_obstacles, L.npset = 1;
   L.Mv = horizon, L.Nmax = 1, L.Smax = 1;
   L.S[0] = 1, L.N[0] = 1, L.M[0] = horizon, L.heading[0] = 0;
@@ -194,6 +199,19 @@ inline void lay_build_mpc(Lay& L, int horizon, int n_obstacles, int n_others) {
   L.nX = 5, L.nU = 2;
 }
 
+
+// state warm start (Vehicle.state_ws, vehicle.py:99-231): n_sets strategy sets, nodes_per_set Euler steps per move; nodes
+// k = 0 .. nodes_per_set (n_sets - 1), a tube set at every k = nodes_per_set i, i >= 1.  Same flat layout as the MPC problem.
+inline void lay_build_state_ws(Lay& L, int n_sets, int nodes_per_set, bool bounded_input, bool has_heading) {
+  lay_build_mpc(L, nodes_per_set * (n_sets - 1) + 1, 0, 0);
+  L.euler = bounded_input ? 2 : 1;
+  L.npset = nodes_per_set;
+  L.Smax = n_sets, L.S[0] = n_sets;
+  L.heading[0] = has_heading ? 1 : 0;
+  lay_offsets(L);
+}
+// Euler mode: index q >= 1 of the tube set enforced at node n, or -1 (vehicle.py:178-192: k = N i, i = 1 .. M)
+OBCA_HD int euler_set_at(const Lay& L, int n) { return (n > 0 && n % L.npset == 0) ? n / L.npset : -1; }
 
 // batch-invariant problem data
 struct Stat {

@@ -738,9 +738,26 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
     ++restarts;
   }
   cta_sync(ctx);
+  // Which weight the next control step starts with: the l1 penalty is exact when it exceeds the multipliers of the hard distance rows
+  // (|y_d| <= rho by the elastic variable's bound multiplier z = rho + y_d >= 0).  Keep the smallest rho0 10^k with a factor 1.25 of
+  // margin over the largest |y_d| of this solution -- back to rho0 as soon as the geometry that needed more is gone (a raised weight
+  // costs iterations: the elastic bound multipliers start at 1, far from rho).
+  double next = 0.0;
+  if (MODE == 1 && status >= 0 && S.rho > rho0) {
+    double ymax = 0.0;
+    for (int q = ctx.tid; q < L.V * L.O * L.Mv; q += ctx.nt) {
+      const int n = q % L.Mv, aj = q / L.Mv;
+      ymax = fmax(ymax, fabs(W.y[L.YOBS(aj / L.O, aj % L.O, 0, n)]));
+    }
+    for (int q = ctx.tid; q < L.P * L.Mv; q += ctx.nt) ymax = fmax(ymax, fabs(W.y[L.YPAIR(q / L.Mv, 0, q % L.Mv)]));
+    ymax = cta_max(ctx, ymax);
+    next = rho0;
+    while (next < 1.25 * ymax && next < S.rho) next *= 10.0;
+    if (next <= rho0) next = 0.0;
+  }
   if (ctx.tid == 0) {
     res->status = status, res->restarts = restarts;
-    res->rho_carry = (MODE == 1 && status >= 0 && S.rho > rho0) ? S.rho : 0.0;
+    res->rho_carry = next;
     *rho = rho0;
   }
   cta_sync(ctx);

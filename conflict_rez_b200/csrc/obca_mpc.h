@@ -202,6 +202,21 @@ OBCA_HD void rk4_value(const double* zu, double dt, double wb, double* out) {
   for (int q = 0; q < 5; ++q) out[q] = z[q];
 }
 
+// forward Euler z + dt f(z, u) (Vehicle.state_ws, vehicle.py:169-173) along z(t) = zu + t d, and its plain value
+template <bool S2>
+OBCA_HD void tay_euler(const double* zu, const double* d, double dt, double wb, Tay<S2>* z) {
+  Tay<S2> u[2] = {{zu[5], d[5], 0.0}, {zu[6], d[6], 0.0}}, z0[5], f[5];
+  for (int q = 0; q < 5; ++q) z0[q].v = zu[q], z0[q].a = d[q], z0[q].b = 0.0;
+  tay_f<S2>(z0, u, wb, f);
+  for (int q = 0; q < 5; ++q) z[q] = tay_axpy<S2>(z0[q], dt, f[q]);
+}
+OBCA_HD void euler_value(const double* zu, double dt, double wb, double* out) {
+  out[0] = zu[0] + dt * zu[3] * cos(zu[2]);
+  out[1] = zu[1] + dt * zu[3] * sin(zu[2]);
+  out[2] = zu[2] + dt * zu[3] * tan(zu[4]) / wb;
+  out[3] = zu[3] + dt * zu[5];
+  out[4] = zu[4] + dt * zu[6];
+}
 // per-instance MPC parameters behind the iterate: cur[5], ref[N][3], others[P][N][3]
 struct MpcPar {
   const double *cur, *ref, *others;
@@ -230,6 +245,7 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   assume_scratch(W);
   const MpcPar par = mpc_par(L, W);
   const int N = L.Mv;
+  const bool EU = L.euler != 0;  // state warm start: Euler dynamics, cost a^2 + w^2, tube sets, a_0 = w_0 = 0, final heading
   double* PG = W.PG;
   prof_mark(ctx, 11);
   // task families in units of 32 tasks of one family, longest first, from a shared counter (see mpc_kkt_solve):
@@ -324,7 +340,8 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
         for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
         d[2 + i] = 1.0;
         Tay<false> F[5];
-        tay_rk4<false>(z, d, S.dt_mpc, S.wb, F);
+        if (EU) tay_euler<false>(z, d, S.dt_mpc, S.wb, F);
+        else tay_rk4<false>(z, d, S.dt_mpc, S.wb, F);
         double acc = 0;
         for (int r = 0; r < 5; ++r) acc += y[L.YCOL(0, r, n)] * F[r].a;
         JG[n * 5 + i] = acc;
@@ -335,7 +352,8 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
         if (n >= nDyn) continue;
         double z[NZ], F[5];
         for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
-        rk4_value(z, S.dt_mpc, S.wb, F);
+        if (EU) euler_value(z, S.dt_mpc, S.wb, F);
+        else rk4_value(z, S.dt_mpc, S.wb, F);
         for (int r = 0; r < 5; ++r) c[L.YCOL(0, r, n)] = x[L.Z(0, r, n + 1)] - F[r];
       }
     }
@@ -347,12 +365,36 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
     for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
     const double* rf = par.ref + 3 * n;
     double ex = z[0] - rf[0], ey = z[1] - rf[1], ep = z[2] - rf[2];
-    f_part += 100.0 * (ex * ex + ey * ey + ep * ep) + z[5] * z[5] + z[3] * z[3] * z[6] * z[6] + z[4] * z[4];
+    if (EU) f_part += z[5] * z[5] + z[6] * z[6];
+    else f_part += 100.0 * (ex * ex + ey * ey + ep * ep) + z[5] * z[5] + z[3] * z[3] * z[6] * z[6] + z[4] * z[4];
     for (int o = 0; o < L.P; ++o) f_part += S.rho * x[L.PEL(o, n)];
-    if (n == 0)
+    if (n == 0) {
       for (int q = 0; q < 5; ++q) c[L.YINIT(0, q)] = z[q] - par.cur[q];
+      if (EU) c[L.YINIT(0, 5)] = z[5], c[L.YINIT(0, 6)] = z[6];
+    }
+    if (EU && n == N - 1 && L.heading[0]) c[L.YTERM(0, 0)] = z[2] - S.heading[0];
+    const int qs = EU ? euler_set_at(L, n) : -1;
+    double tg[3] = {0, 0, 0};
+    if (qs >= 1) {
+      const double cs = cos(z[2]), sn = sin(z[2]), fx = z[0] + S.wb * cs, fy = z[1] + S.wb * sn;
+      for (int r = 0; r < 4; ++r) {
+        const double* tb = S.tube_row(L, 0, qs, 0, r);
+        const double* tf = S.tube_row(L, 0, qs, 1, r);
+        c[L.YTUBE(0, qs - 1, r)] = tb[2] - tb[0] * z[0] - tb[1] * z[1] - x[L.TS(0, qs - 1, r)];
+        c[L.YTUBE(0, qs - 1, 4 + r)] = tf[2] - tf[0] * fx - tf[1] * fy - x[L.TS(0, qs - 1, 4 + r)];
+        if (y) {
+          const double yb = y[L.YTUBE(0, qs - 1, r)], yf = y[L.YTUBE(0, qs - 1, 4 + r)];
+          gl[L.TS(0, qs - 1, r)] = -yb;
+          gl[L.TS(0, qs - 1, 4 + r)] = -yf;
+          tg[0] -= tb[0] * yb + tf[0] * yf;
+          tg[1] -= tb[1] * yb + tf[1] * yf;
+          tg[2] -= yf * S.wb * (-tf[0] * sn + tf[1] * cs);
+        }
+      }
+    }
     if (!y) continue;
     double g[NZ] = {200.0 * ex, 200.0 * ey, 200.0 * ep, 2.0 * z[3] * z[6] * z[6], 2.0 * z[4], 2.0 * z[5], 2.0 * z[3] * z[3] * z[6]};
+    if (EU) g[0] = tg[0], g[1] = tg[1], g[2] = tg[2], g[3] = 0.0, g[4] = 0.0, g[6] = 2.0 * z[6];
     if (n < N - 1) {
       g[0] -= y[L.YCOL(0, 0, n)], g[1] -= y[L.YCOL(0, 1, n)];  // F_x = x + ..., F_y = y + ...: identity columns
       for (int i = 0; i < 5; ++i) g[2 + i] -= JG[n * 5 + i];
@@ -360,7 +402,8 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
     if (n >= 1)
       for (int r = 0; r < 5; ++r) g[r] += y[L.YCOL(0, r, n - 1)];
     if (n == 0)
-      for (int q = 0; q < 5; ++q) g[q] += y[L.YINIT(0, q)];
+      for (int q = 0; q < (EU ? NZ : 5); ++q) g[q] += y[L.YINIT(0, q)];
+    if (EU && n == N - 1 && L.heading[0]) g[2] += y[L.YTERM(0, 0)];
     for (int j = 0; j < L.O; ++j) {
       const double* og = OG + (size_t)(n * L.O + j) * 3;
       g[0] += og[0], g[1] += og[1], g[2] += og[2];
@@ -380,12 +423,16 @@ OBCA_HDN void mpc_eval_all(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
 // ------------------------------------------------------------------------------------------------
 // [LOCAL] + [RICCATI] + [BACKSUB]
 // ------------------------------------------------------------------------------------------------
-OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double* RW, int* ok_shared) {
+// SM: the work arena RW is shared memory (MPC horizons); false: per-slot global memory (the 271-node state warm start)
+template <bool SM>
+OBCA_HDN int mpc_kkt_solve_impl(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double* RW, int* ok_shared) {
   OBCA_ASSUME_STATIC(L, S);
   assume_scratch(W);
-  OBCA_ASSUME_SHARED(RW);
+  if (SM) OBCA_ASSUME_SHARED(RW);
+  else OBCA_ASSUME_GLOBAL(RW);
   const MpcPar par = mpc_par(L, W);
   const int N = L.Mv;
+  const bool EU = L.euler != 0;
   const double *x = W.x, *y = W.y;
   if (ctx.tid == 0) *ok_shared = 1;
   cta_sync(ctx);
@@ -453,7 +500,8 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
         for (int q = 0; q < NZ; ++q) z[q] = x[L.Z(0, q, n)];
         d[2 + i] = 1.0, d[2 + j] = 1.0;
         Tay<true> F[5];
-        tay_rk4<true>(z, d, S.dt_mpc, S.wb, F);
+        if (EU) tay_euler<true>(z, d, S.dt_mpc, S.wb, F);
+        else tay_rk4<true>(z, d, S.dt_mpc, S.wb, F);
         double acc = 0;
         for (int r = 0; r < 5; ++r) acc += y[L.YCOL(0, r, n)] * 2.0 * F[r].b;
         QD[n * 15 + k] = acc;
@@ -470,9 +518,28 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
     double H[28], g[NZ];
     for (int q = 0; q < 28; ++q) H[q] = 0;
     for (int q = 0; q < NZ; ++q) H[sym(q, q)] = W.sig[L.Z(0, q, n)], g[q] = W.gphi[L.Z(0, q, n)];
-    H[sym(0, 0)] += 200.0, H[sym(1, 1)] += 200.0, H[sym(2, 2)] += 200.0;
-    H[sym(3, 3)] += 2.0 * z[6] * z[6], H[sym(6, 6)] += 2.0 * z[3] * z[3], H[sym(6, 3)] += 4.0 * z[3] * z[6];
-    H[sym(4, 4)] += 2.0, H[sym(5, 5)] += 2.0;
+    if (EU) {
+      H[sym(5, 5)] += 2.0, H[sym(6, 6)] += 2.0;
+      const int qs = euler_set_at(L, n);
+      if (qs >= 1) {  // tube set: slack and multiplier eliminated analytically (same algebra as node_assemble, obca_kkt.h)
+        const double cs = cos(z[2]), sn = sin(z[2]);
+        for (int r = 0; r < 8; ++r) {
+          const double* t = S.tube_row(L, 0, qs, r / 4, r % 4);
+          const double gr[3] = {t[0], t[1], r < 4 ? 0.0 : S.wb * (-t[0] * sn + t[1] * cs)};
+          const double sg = W.sig[L.TS(0, qs - 1, r)];
+          const double w = sg * W.c[L.YTUBE(0, qs - 1, r)] + W.gphi[L.TS(0, qs - 1, r)];
+          for (int m = 0; m < 3; ++m) {
+            g[m] -= gr[m] * w;
+            for (int mm = 0; mm <= m; ++mm) H[sym(m, mm)] += sg * gr[m] * gr[mm];
+          }
+          if (r >= 4) H[sym(2, 2)] += y[L.YTUBE(0, qs - 1, r)] * S.wb * (t[0] * cs + t[1] * sn);
+        }
+      }
+    } else {
+      H[sym(0, 0)] += 200.0, H[sym(1, 1)] += 200.0, H[sym(2, 2)] += 200.0;
+      H[sym(3, 3)] += 2.0 * z[6] * z[6], H[sym(6, 6)] += 2.0 * z[3] * z[3], H[sym(6, 3)] += 4.0 * z[3] * z[6];
+      H[sym(4, 4)] += 2.0, H[sym(5, 5)] += 2.0;
+    }
     if (n < N - 1) {
       const double* qd = QD + n * 15;
       for (int i = 0; i < 5; ++i)
@@ -499,11 +566,18 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   }
   cta_sync(ctx);
   prof_mark(ctx, 3);
-  // Riccati recursion (state 5, control 2), serial over the stages: thread 0
-  // warp 0, lanes over the matrix entries; per stage: PA = P A, Q += A'PA, gains, cost-to-go
-  double* SC = OB + (size_t)N * L.O * 9;  // [112] stage scratch: PA[35], Pr[5], Q[49], qv[7], K[12]
+  // Riccati recursion (state 5, control 2), serial over the stages:
+  // warp 0, lanes over the matrix entries; per stage: PA = P A, Q += A'PA, gains, cost-to-go.
+  // State warm start (EU): the inputs of stage 0 are fixed by a_0 = w_0 = 0 (no gain, du_0 = -c), and a final-heading row
+  // e'dz_{N-1} = -c_h is handled exactly by a second right-hand side through the same factorisation (TWO): solution 2 answers a unit
+  // gradient on psi_{N-1}; the row's multiplier step is dy_h = -(c_h + e'dz1) / (e'dz2) and every quantity is X1 + dy_h X2.
+  double* SC = OB + (size_t)N * L.O * 9;  // [128] stage scratch: PA[35], Pr[5], Q[49], qv[7], K[12], Pr2[5], qv2[7]
+  double* K2 = SC + 128;                  // [N][2]   constant gain terms of solution 2
+  double* P2 = K2 + (size_t)N * 2;        // [N+1][5] cost-to-go gradient of solution 2
+  double* DZ2 = P2 + (size_t)(N + 1) * 5; // [N][7]   step of solution 2
+  const bool TWO = EU && L.heading[0];
   if (ctx.tid < 32) {
-    double *PA = SC, *Pr = SC + 35, *Q = SC + 40, *qv = SC + 89;
+    double *PA = SC, *Pr = SC + 35, *Q = SC + 40, *qv = SC + 89, *Pr2 = SC + 108, *qv2 = SC + 113;
     for (int n = N - 1; n >= 0; --n) {
       const double* H = HN + (size_t)n * 28;
       const double* g = GN + (size_t)n * 7;
@@ -512,36 +586,43 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
       double* K = KK + (size_t)n * 12;
       if (n < N - 1) {
         OBCA_LANES(lane) {
-          for (int e = lane; e < 40; e += 32) {
+          for (int e = lane; e < (TWO ? 45 : 40); e += 32) {
             if (e < 35) {
               const int r = e / 7, q = e % 7;
               double sacc = 0;
               for (int m = 0; m < 5; ++m) sacc += Pn[r * 5 + m] * A[m * 7 + q];
               PA[e] = sacc;
-            } else {
+            } else if (e < 40) {
               const int r = e - 35;
               double cr = 0;
               for (int m = 0; m < 5; ++m) cr += Pn[r * 5 + m] * W.c[L.YCOL(0, m, n)];
               Pr[r] = Pn[25 + r] - cr;  // P (-r) + pv
-            }
+            } else
+              Pr2[e - 40] = P2[(size_t)(n + 1) * 5 + (e - 40)];
           }
         }
         OBCA_WARP_SYNC();
       }
       OBCA_LANES(lane) {
-        for (int e = lane; e < 56; e += 32) {
+        for (int e = lane; e < (TWO ? 63 : 56); e += 32) {
           if (e < 49) {
             const int r = e / 7, q = e % 7;
             double sacc = H[sym(r, q)];
             if (n < N - 1)
               for (int m = 0; m < 5; ++m) sacc += A[m * 7 + r] * PA[m * 7 + q];
             Q[e] = sacc;
-          } else {
+          } else if (e < 56) {
             const int r = e - 49;
             double sacc = g[r];
             if (n < N - 1)
               for (int m = 0; m < 5; ++m) sacc += A[m * 7 + r] * Pr[m];
             qv[r] = sacc;
+          } else {
+            const int r = e - 56;
+            double sacc = (n == N - 1 && r == 2) ? 1.0 : 0.0;
+            if (n < N - 1)
+              for (int m = 0; m < 5; ++m) sacc += A[m * 7 + r] * Pr2[m];
+            qv2[r] = sacc;
           }
         }
       }
@@ -550,27 +631,39 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
       double f00 = Q[5 * 7 + 5], f01 = Q[5 * 7 + 6], f11 = Q[6 * 7 + 6], det = f00 * f11 - f01 * f01;
       if (!(f00 > 0) || !(det > 1e-14 * f00 * f11)) {
         *ok_shared = 0;
+#ifdef OBCA_HOST_EMU
+        if (getenv("OBCA_TRACE")) printf("       stage %d: F not positive definite (%.3e %.3e %.3e)\n", n, f00, f01, f11);
+#endif
         f00 = f11 = 1.0, f01 = 0.0, det = 1.0;
       }
       const double i00 = f11 / det, i01 = -f01 / det, i11 = f00 / det;
+      const bool fixed_u = EU && n == 0;
       OBCA_LANES(lane) {
         if (lane < 12) {
           const int q = lane % 6, row = lane / 6;  // q = 5: the constant term
           const double b5 = q < 5 ? Q[5 * 7 + q] : qv[5], b6 = q < 5 ? Q[6 * 7 + q] : qv[6];
-          const double kv = row == 0 ? -(i00 * b5 + i01 * b6) : -(i01 * b5 + i11 * b6);
+          double kv = row == 0 ? -(i00 * b5 + i01 * b6) : -(i01 * b5 + i11 * b6);
+          if (fixed_u) kv = q < 5 ? 0.0 : -W.c[L.YINIT(0, 5 + row)];
           K[q < 5 ? row * 5 + q : 10 + row] = kv;
+        } else if (TWO && lane < 14) {
+          const int row = lane - 12;
+          const double kv = row == 0 ? -(i00 * qv2[5] + i01 * qv2[6]) : -(i01 * qv2[5] + i11 * qv2[6]);
+          K2[(size_t)n * 2 + row] = fixed_u ? 0.0 : kv;
         }
       }
       OBCA_WARP_SYNC();
       OBCA_LANES(lane) {
-        if (lane < 30) {
+        for (int e = lane; e < (TWO ? 35 : 30); e += 32) {
           double* Po = PP + (size_t)n * 30;
-          if (lane < 25) {
-            const int r = lane / 5, q = lane % 5;
-            Po[lane] = Q[r * 7 + q] + Q[r * 7 + 5] * K[q] + Q[r * 7 + 6] * K[5 + q];
+          if (e < 25) {
+            const int r = e / 5, q = e % 5;
+            Po[e] = Q[r * 7 + q] + Q[r * 7 + 5] * K[q] + Q[r * 7 + 6] * K[5 + q];
+          } else if (e < 30) {
+            const int r = e - 25;
+            Po[e] = qv[r] + Q[r * 7 + 5] * K[10] + Q[r * 7 + 6] * K[11];
           } else {
-            const int r = lane - 25;
-            Po[lane] = qv[r] + Q[r * 7 + 5] * K[10] + Q[r * 7 + 6] * K[11];
+            const int r = e - 30;
+            P2[(size_t)n * 5 + r] = qv2[r] + Q[r * 7 + 5] * K2[(size_t)n * 2] + Q[r * 7 + 6] * K2[(size_t)n * 2 + 1];
           }
         }
       }
@@ -579,16 +672,23 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
     // forward pass
     OBCA_LANES(lane) {
       if (lane < 5) DZ[lane] = -W.c[L.YINIT(0, lane)];
+      else if (TWO && lane < 10) DZ2[lane - 5] = 0.0;
     }
     OBCA_WARP_SYNC();
     for (int n = 0; n < N; ++n) {
       const double* K = KK + (size_t)n * 12;
       double* w = DZ + (size_t)n * 7;
+      double* w2 = DZ2 + (size_t)n * 7;
       OBCA_LANES(lane) {
         if (lane < 2) {
           double du = K[10 + lane];
           for (int q = 0; q < 5; ++q) du += K[lane * 5 + q] * w[q];
           w[5 + lane] = du;
+        } else if (TWO && lane < 4) {
+          const int row = lane - 2;
+          double du = K2[(size_t)n * 2 + row];
+          for (int q = 0; q < 5; ++q) du += K[row * 5 + q] * w2[q];
+          w2[5 + row] = du;
         }
       }
       OBCA_WARP_SYNC();
@@ -599,10 +699,46 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
             double sacc = -W.c[L.YCOL(0, lane, n)];
             for (int q = 0; q < 7; ++q) sacc += A[lane * 7 + q] * w[q];
             w[7 + lane] = sacc;  // dz of stage n+1
+          } else if (TWO && lane < 10) {
+            const int r = lane - 5;
+            double sacc = 0.0;
+            for (int q = 0; q < 7; ++q) sacc += A[r * 7 + q] * w2[q];
+            w2[7 + r] = sacc;
           }
         }
         OBCA_WARP_SYNC();
       }
+    }
+    if (EU) {
+      // combine the two solutions and recover the multipliers of the a_0 = w_0 = 0 rows from the stationarity of u_0
+      // (Q, qv, qv2 still hold stage 0): dy_u = -(Q_u. [dz_0; du_0] + q_u)
+      double dyh = 0.0;
+      if (TWO) {
+        const double e1 = DZ[(size_t)(N - 1) * 7 + 2], e2 = DZ2[(size_t)(N - 1) * 7 + 2];
+#ifdef OBCA_HOST_EMU
+        if (getenv("OBCA_TRACE")) printf("       heading row: e1 %.3e e2 %.3e c %.3e\n", e1, e2, W.c[L.YTERM(0, 0)]);
+#endif
+        // e'dz2 = -(e' Hred^-1 e) <= 0; it vanishes where the linearised dynamics cannot turn the vehicle (v = 0 and delta = 0 along the
+        // whole guess): the pivot is then bounded away from zero, the role of IPOPT's delta_c perturbation of a singular KKT matrix
+        if (!(e2 <= 0.0)) *ok_shared = 0;
+        else dyh = -(W.c[L.YTERM(0, 0)] + e1) / fmin(e2, -1e-8);
+        OBCA_LANES(lane) {
+          for (int e = lane; e < N * 7; e += 32) DZ[e] += dyh * DZ2[e];
+        }
+        OBCA_LANES(lane) {
+          for (int e = lane; e < N * 5; e += 32) PP[(size_t)(e / 5) * 30 + 25 + e % 5] += dyh * P2[e];
+        }
+        OBCA_WARP_SYNC();
+      }
+      OBCA_LANES(lane) {
+        if (lane < 2) {
+          double sacc = qv[5 + lane] + (TWO ? dyh * qv2[5 + lane] : 0.0);
+          for (int q = 0; q < 7; ++q) sacc += Q[(5 + lane) * 7 + q] * DZ[q];
+          W.dy[L.YINIT(0, 5 + lane)] = -sacc;
+        } else if (lane == 2 && TWO)
+          W.dy[L.YTERM(0, 0)] = dyh;
+      }
+      OBCA_WARP_SYNC();
     }
   }
   cta_sync(ctx);
@@ -619,6 +755,19 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
       for (int m = 0; m < 5; ++m) s += P[r * 5 + m] * w[m];
       if (n == 0) W.dy[L.YINIT(0, r)] = -s;
       else W.dy[L.YCOL(0, r, n - 1)] = -s;
+    }
+    if (EU) {
+      const int qs = euler_set_at(L, n);
+      if (qs >= 1) {
+        const double psi = x[L.Z(0, 2, n)], cs = cos(psi), sn = sin(psi);
+        for (int r = 0; r < 8; ++r) {
+          const double* t = S.tube_row(L, 0, qs, r / 4, r % 4);
+          const double gr[3] = {t[0], t[1], r < 4 ? 0.0 : S.wb * (-t[0] * sn + t[1] * cs)};
+          const double dts = W.c[L.YTUBE(0, qs - 1, r)] - (gr[0] * w[0] + gr[1] * w[1] + gr[2] * w[2]);
+          W.dx[L.TS(0, qs - 1, r)] = dts;
+          W.dy[L.YTUBE(0, qs - 1, r)] = W.sig[L.TS(0, qs - 1, r)] * dts + W.gphi[L.TS(0, qs - 1, r)];
+        }
+      }
     }
   }
   // local blocks: one task per (node, obstacle) and (other, node)
@@ -640,6 +789,11 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   return 1;
 }
 
-inline size_t mpc_work_doubles(const Lay& L) { return (size_t)(L.Mv + 1) * (28 + 7 + 35 + 30 + 12 + 7 + 15 + 9 * L.O) + 128; }
+OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Scratch& W, double* RW, int* ok_shared) {
+  if (W.ricg) return mpc_kkt_solve_impl<false>(ctx, L, S, W, W.ricg, ok_shared);
+  return mpc_kkt_solve_impl<true>(ctx, L, S, W, RW, ok_shared);
+}
+
+inline size_t mpc_work_doubles(const Lay& L) { return (size_t)(L.Mv + 1) * (28 + 7 + 35 + 30 + 12 + 7 + 15 + 9 * L.O) + 128 + (L.euler ? (size_t)(L.Mv + 1) * 14 : 0); }
 
 }  // namespace obca

@@ -108,6 +108,25 @@ OBCA_HD void plant_step(const double* s, const double* u, double dt, double wb, 
   for (int q = 0; q < 5; ++q) out[q] = z[q];
 }
 
+// [WSINTERP] Vehicle.interp_ws_for_collocation (confrez/control/vehicle.py:298-358): every warm-start signal, sampled on the grid
+// t (T), is interpolated linearly (scipy interp1d) onto the collocation times t_interp[i (K+1) + k] = (i + tau_k) / N * t[T-1].
+// in (B,T,C) -> out (B,N (K+1),C); one thread per output entry.
+OBCA_HD void ws_interp_item(const double* in, const double* t, const double* tau, int T, int C, int N, double* out, size_t g) {
+  const int c = (int)(g % C), m = (int)((g / C) % (N * NK));
+  const size_t b = g / ((size_t)C * N * NK);
+  const double tq = ((m / NK) + tau[m % NK]) / N * t[T - 1];
+  int lo = 0, hi = T - 1;  // largest lo with t[lo] <= tq, kept below T - 1 (tq never exceeds t[T-1]: tau <= 1, i <= N - 1)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (t[mid] <= tq) lo = mid;
+    else hi = mid;
+  }
+  const double* s = in + (b * T) * (size_t)C + c;
+  const double y0 = s[(size_t)lo * C], y1 = s[(size_t)(lo + 1) * C];
+  // scipy.interpolate.interp1d(kind="linear"): slope * (x_new - x_lo) + y_lo
+  out[g] = (y1 - y0) / (t[lo + 1] - t[lo]) * (tq - t[lo]) + y0;
+}
+
 // [SHIFT] out[b][n][:] = in[b][min(n + 1, N - 1)][:] for (B, N, W) arrays
 OBCA_HD void shift_item(const double* in, double* out, int N, int Wd, size_t g) {
   const int w = (int)(g % Wd), n = (int)((g / Wd) % N);

@@ -43,6 +43,7 @@ class ObcaDims(ctypes.Structure):
         ("mode", ctypes.c_int32),
         ("horizon", ctypes.c_int32),
         ("n_others", ctypes.c_int32),
+        ("bounded_input", ctypes.c_int32),
     ]
 
 
@@ -88,6 +89,7 @@ EXPORTS = [
     "obca_joint_dual_ws",
     "obca_measure_dfma_peak",
     "obca_interpolate",
+    "obca_interp_ws",
     "obca_mpc_ref_times",
     "obca_plant_step",
     "obca_shift_horizon",
@@ -134,6 +136,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.obca_joint_dual_ws.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.obca_measure_dfma_peak.argtypes = [ctypes.c_int, _dp]
     lib.obca_interpolate.argtypes = [ctypes.c_int, vp, vp, i32p, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.obca_interp_ws.argtypes = [ctypes.c_int, vp, vp, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.obca_mpc_ref_times.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp]
     lib.obca_plant_step.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, vp, vp]
     lib.obca_shift_horizon.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
@@ -229,6 +232,14 @@ class TrajectoryOps:
         ni = (ctypes.c_int32 * V)(*[int(n) for n in n_intervals])
         self._check(self.lib.obca_interpolate(self.index, _ptr(z.contiguous()), _ptr(dt.contiguous()), ni, _np_ptr(self._tau), B, V, Mmax,
                                               _ptr(times.contiguous()), T, int(per), int(dt.dim() == 2), _ptr(out), self._stream()))
+        return out
+
+    def interp_ws(self, sig: torch.Tensor, t: torch.Tensor, N: int) -> torch.Tensor:
+        """``Vehicle.interp_ws_for_collocation`` (vehicle.py:298-358) for a batch: sig (B,T,C) sampled on t (T) -> (B,N*6,C), linear
+        interpolation onto the collocation times (i + tau_k) / N * t[-1]."""
+        B, T, C = sig.shape
+        out = torch.empty((B, N * 6, C), dtype=torch.float64, device=sig.device)
+        self._check(self.lib.obca_interp_ws(self.index, _ptr(sig.contiguous()), _ptr(t.contiguous()), _np_ptr(self._tau), B, T, C, N, _ptr(out), self._stream()))
         return out
 
     def mpc_ref_times(self, grid: torch.Tensor, clock: torch.Tensor, N: int, dt_mpc: float) -> torch.Tensor:
@@ -597,3 +608,84 @@ class ObcaMpcSolver(ObcaSolver):
 
     def solve(self, guess, init_pose=None, want_duals=True):  # parameters must have been set with set_params
         return ObcaSolver.solve(self, guess, want_duals=want_duals)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# State warm start: the Euler-discretised tube-following NLP of Vehicle.state_ws (confrez/control/vehicle.py:99-231)
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class StateWsProblem:
+    """Static data of ``Vehicle.state_ws``: ``n_sets`` strategy sets, ``N`` Euler steps of ``dt`` per move, tube sets (raw b; the
+    solver subtracts ``shrink_tube``), optional final heading, ``bounded_input`` (vehicle.py:99-108)."""
+
+    tube_A: np.ndarray  # (S,2,4,2) [set][back,front][row][x,y]
+    tube_b: np.ndarray  # (S,2,4)
+    N: int = 30
+    dt: float = 0.1
+    final_heading: Optional[float] = None
+    bounded_input: bool = False
+    shrink_tube: float = 0.8
+    wb: float = 2.5
+    region: np.ndarray = None
+    limits: np.ndarray = None
+    batch: int = 1
+
+    def __post_init__(self):
+        if self.region is None:
+            self.region = np.array([2.5, 32.5, 7.5, 27.5])
+        if self.limits is None:
+            self.limits = np.array([-2.5, 2.5, -0.85, 0.85, -1.5, 1.5, -1.0, 1.0])
+
+    @property
+    def n_sets(self):
+        return int(np.asarray(self.tube_A).shape[0])
+
+    @property
+    def nodes(self):
+        return self.N * (self.n_sets - 1) + 1
+
+
+class ObcaStateWsSolver(ObcaMpcSolver):
+    """``batch`` state warm starts of one vehicle shape (same tube, different initial poses) in one launch.  The NLP runs through
+    the MPC-mode kernels (stage-wise Riccati over the N (S - 1) + 1 nodes); ``solve_ws`` takes the initial states (B,5) and the
+    node-major guess z (B,nodes,7) = (x, y, psi, v, delta, a, w)."""
+
+    def __init__(self, prob: StateWsProblem, options: Optional[SolveOptions] = None, device="cuda:0", lib: Optional[ctypes.CDLL] = None):
+        self.lib = lib if lib is not None else load_library()
+        self.device = torch.device(device)
+        self.is_emulation = b"EMULATION" in self.lib.obca_version()
+        if self.device.type != "cuda" and not self.is_emulation:
+            raise RuntimeError("ObcaStateWsSolver needs a CUDA device (no CPU fallback)")
+        if self.device.type == "cuda" and not torch.cuda.is_available():
+            raise RuntimeError("ObcaStateWsSolver: CUDA is not available on this machine (no CPU fallback)")
+        self.prob = prob
+        self._staging = {}
+        self.opts = options or SolveOptions(max_iter=500)  # vehicle.py:207-213
+        self.B, self.V, self.O, self.P, self.Mmax = prob.batch, 1, 0, 0, prob.nodes
+        dims = ObcaDims(batch=self.B, V=1, O=0, K=5, n_per_set=prob.N, mode=2, horizon=prob.nodes, n_others=0, bounded_input=int(bool(prob.bounded_input)))
+        dims.n_sets[0] = prob.n_sets
+        copts = ObcaOptions()
+        self.lib.obca_default_options(ctypes.byref(copts))
+        for name in ("tol", "constr_viol_tol", "dual_inf_tol", "compl_inf_tol", "mu_init", "max_iter", "elastic_weight", "refine_steps"):
+            setattr(copts, name, getattr(self.opts, name))
+        copts.shrink_tube = float(prob.shrink_tube)
+        self.handle = ctypes.c_void_p()
+        dev_index = self.device.index or 0 if self.device.type == "cuda" else 0
+        self._check(self.lib.obca_create(ctypes.byref(dims), ctypes.byref(copts), dev_index, ctypes.byref(self.handle)))
+        S = prob.n_sets
+        keep = {
+            "obs_A": np.zeros((1, 4, 2)), "obs_b": np.zeros((1, 4)), "body_G": np.array([[1.0, 0], [0, 1], [-1, 0], [0, -1]]), "body_g": np.array([3.3, 0.9, 0.6, 0.9]),
+            "tube_A": np.ascontiguousarray(prob.tube_A, dtype=np.float64).reshape(1, S, 2, 4, 2), "tube_b": np.ascontiguousarray(prob.tube_b, dtype=np.float64).reshape(1, S, 2, 4),
+            "region": np.ascontiguousarray(prob.region, dtype=np.float64), "limits": np.ascontiguousarray(prob.limits, dtype=np.float64),
+            "final_heading": np.array([np.nan if prob.final_heading is None else float(prob.final_heading)]),
+        }
+        self._keep = keep
+        st = ObcaStatic(wb=float(prob.wb), mpc_dt=float(prob.dt), **{n: _np_ptr(a) for n, a in keep.items()})
+        self._check(self.lib.obca_set_static(self.handle, ctypes.byref(st)))
+
+    def solve_ws(self, init_state, z_guess) -> BatchResult:
+        B, M = self.B, self.Mmax
+        init_state = np.ascontiguousarray(init_state, dtype=np.float64).reshape(B, 5)
+        z = np.ascontiguousarray(z_guess, dtype=np.float64).reshape(B, 1, M, 7)
+        guess = CollocationGuess(z, np.zeros((B, 1, M, 0, 4)), np.zeros((B, 1, M, 0, 4)), np.zeros(B))
+        return self.solve_step(init_state, np.zeros((B, M, 3)), None, guess)

@@ -36,6 +36,9 @@ extern "C" {
 #define OBCA_MAX_SETS 64  /* strategy sets per vehicle */
 #define OBCA_MODE_COLLOCATION 0
 #define OBCA_MODE_MPC 1   /* VehicleFollower.setup_controller NLP (confrez/control/vehicle_follower.py:146-368) */
+#define OBCA_MODE_STATE_WS 2 /* Vehicle.state_ws: Euler-discretised tube-following NLP (confrez/control/vehicle.py:99-231); one vehicle,
+                                n_sets[0] strategy sets, n_per_set = Euler steps per move (the reference's N), nodes 0 .. N (S - 1);
+                                the sample time is ObcaStatic.mpc_dt, the initial state goes in through obca_set_mpc_params (cur) */
 
 /* per-instance return status, mirroring IPOPT's ApplicationReturnStatus strings */
 #define OBCA_SOLVE_SUCCEEDED 0
@@ -58,6 +61,7 @@ typedef struct ObcaDims {
   int32_t mode;                  /* OBCA_MODE_COLLOCATION (default 0) or OBCA_MODE_MPC */
   int32_t horizon;               /* MPC: nodes N (vehicle_follower.py:146, N = 30) */
   int32_t n_others;              /* MPC: other vehicles whose predictions are parameters */
+  int32_t bounded_input;         /* STATE_WS: a / w limits enforced (state_ws(bounded_input=True), vehicle.py:155-167) */
 } ObcaDims;
 
 typedef struct ObcaOptions {
@@ -126,6 +130,10 @@ int obca_joint_dual_ws(ObcaHandle* h, const double* z, double* pair_lam, double*
  * inputs: piecewise constant between the collocation nodes (ca.pw_const semantics). */
 int obca_interpolate(int device, const double* z, const double* dt, const int32_t* n_intervals, const double* tau, int B, int V, int Mmax,
                      const double* times, int T, int per_vehicle_times, int dt_per_vehicle, double* out, void* stream);
+/* replaces Vehicle.interp_ws_for_collocation (confrez/control/vehicle.py:298-358): C warm-start signals sampled on the time grid
+ * t (T, dev) are interpolated linearly (scipy interp1d) onto the collocation times (i + tau_k) / N * t[T-1], i < N, k <= K:
+ * in (B,T,C) -> out (B,N*(K+1),C); tau (K+1 = 6, HOST). */
+int obca_interp_ws(int device, const double* in, const double* t, const double* tau, int B, int T, int C, int N, double* out, void* stream);
 /* replaces the time lookup of VehicleFollower.get_current_ref (confrez/control/vehicle_follower.py:370-404): for every vehicle
  * (B,V) the N sample times  t_ref[argmin |t_ref - clock|] + k * dt_mpc  of the dense reference grid linspace(t_first, t_last, n_ref);
  * grid (B,V,3) = t_first, t_last, n_ref (as double), clock (B,V) -> times (B,V,N) (feed to obca_interpolate, per_vehicle_times = 1) */

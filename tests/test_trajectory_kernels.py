@@ -113,3 +113,22 @@ def test_horizon_shift_is_adv_onestep(ops):
         assert np.array_equal(out[b].reshape(30, -1), VehicleFollower._adv_onestep(a[b].reshape(30, -1)))
     v = rng.standard_normal((2, 30))
     assert np.array_equal(ops.shift_horizon(_dev(ops, v)).cpu().numpy()[1], VehicleFollower._adv_onestep(v[1]))
+
+
+def test_warm_start_interpolation_is_scipy_interp1d(ops):
+    """obca_interp_ws == Vehicle.interp_ws_for_collocation (vehicle.py:298-358): scipy's linear interp1d of every signal onto
+    t_interp = (i + tau_k) / N * t[-1]; uniform and non-uniform sample grids, end points included."""
+    from scipy.interpolate import interp1d
+
+    from conflict_rez_b200.control.warmstart import interp_ws_for_collocation, radau_nodes
+
+    rng = np.random.default_rng(5)
+    dev = ops.device
+    for T, N, t in ((271, 45, np.linspace(0, 27.0, 271)), (40, 7, np.sort(np.concatenate([[0.0], rng.uniform(0.01, 3.9, 38), [4.0]])))):
+        sig = rng.normal(size=(3, T, 9))
+        out = ops.interp_ws(torch.tensor(sig, device=dev), torch.tensor(t, device=dev), N).cpu().numpy()
+        ti = (np.arange(N)[:, None] + radau_nodes(5)[None]).ravel() / N * t[-1]
+        assert out.shape == (3, N * 6, 9)
+        assert np.abs(out - interp1d(t, sig, axis=1)(ti)).max() <= 1e-13
+        t_host, host = interp_ws_for_collocation(t, {"s": sig[1]}, N, 5)  # the single-instance host helper behind Vehicle.interp_ws_for_collocation
+        assert np.abs(t_host - ti).max() <= 1e-14 and np.abs(out[1] - host["s"]).max() <= 1e-13

@@ -76,3 +76,23 @@ def test_device_warm_start_pipeline(backend, strategy_file):
     np.testing.assert_allclose(g.pair_lam[:, 0, :m], l_, atol=1e-12)
     np.testing.assert_allclose(g.pair_s[:, 0, :m], s_, atol=1e-12)
     assert set(plan.timing) >= {"host_pose_guess_s", "device_warm_start_s"}
+
+
+def test_batched_pipeline_with_the_reference_state_ws(emu_lib, strategy_file):
+    """prepare_joint_batch(state_ws="euler"): Vehicle.state_ws (Euler NLP) -> interp_ws_for_collocation -> dual_ws -> single OBCA solve per
+    agent, all batched on the device -- the reference chain (multi_vehicle_planner.py:68-109).  It must reach the same joint plans
+    as the default pipeline (tube following in collocation form)."""
+    from conflict_rez_b200.control.batch_planner import prepare_joint_batch, random_init_offsets
+    from conflict_rez_b200.solver import SolveOptions
+
+    agents = ["vehicle_1", "vehicle_2"]
+    offs = random_init_offsets(2, 4, seed=0)[:, [1, 2]]
+    out = {}
+    for mode in ("collocation", "euler"):
+        plan = prepare_joint_batch(strategy_file, agents, offs, SolveOptions(max_iter=600), device="cpu", lib=emu_lib, state_ws=mode)
+        assert plan.timing["state_ws_failures"] == 0 and all((r.status >= 0).all() for r in plan.singles)
+        out[mode] = plan.solver.solve(plan.guess)
+        plan.solver.close()
+        assert (out[mode].status == 0).all()
+    assert np.abs(out["euler"].obj - out["collocation"].obj).max() <= 1e-4 * np.abs(out["collocation"].obj).max()
+    assert np.abs(out["euler"].z[..., :3] - out["collocation"].z[..., :3]).max() <= 5e-2  # both stop at tol = 1e-2
