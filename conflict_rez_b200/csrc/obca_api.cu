@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_solve(SolveArgs A)
   __shared__ Shared sh;
   __shared__ double red[40];
   __shared__ int cur;
-  extern __shared__ double arena[];
+  extern __shared__ __align__(16) double arena[];
   __shared__ Lay sL;
   __shared__ Stat sS;
   {

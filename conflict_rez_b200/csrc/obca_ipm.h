@@ -68,7 +68,8 @@ OBCA_HD void flat_pass_impl(const Ctx& ctx, const Stage& st, const BoundCls* bc,
   // ring depth 3: measured, a deeper ring (up to 8 tiles in flight) is 8 % slower -- the passes are bound by the FP64 instruction
   // latency of the bodies at 2 warps per scheduler, not by bytes in flight.  Also measured and
   // dropped: a warp-uniform fast path for tiles of plain non-negative variables (constant bounds, the four elements of a thread as one
-  // straight-line block): 5.98 vs 5.90 M cycles per iteration, no gain (profiles/r02h_phase_cycles_flat_fast_path_rejected.txt)
+  // straight-line block): 5.98 vs 5.90 M cycles per iteration, no gain (profiles/r02h_phase_cycles_flat_fast_path_rejected.txt); per-stage
+  // "empty" mbarriers instead of the CTA barrier after every tile (warps drifting by a tile): +60 k cycles (profiles/r02n_*)
   const int ST_STAGES = st.cap / TILE_D >= 3 ? 3 : 0;
   if (st.buf && ST_STAGES >= 3 && n >= 4 * ST_TILE && ctx.nt * 4 == ST_TILE) {
     const int ntile = (n + ST_TILE - 1) / ST_TILE;

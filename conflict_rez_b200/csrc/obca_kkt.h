@@ -913,13 +913,35 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
       const int row = e / NRED, col = e % NRED;
       HT[e] = col < NZ ? Hf[row * 7 + col] : 0.0;
     }
-    for (int e = lane; e < NW * NRED; e += 32) {
-      const int row = e / NRED, col = e % NRED, k = row / NZ + 1, q = row % NZ;
-      const double* Hr = Hf + k * 49 + q * 7;
-      const double* Tc = T + ((k - 1) * NZ) * NRED + col;
-      const double a0 = Hr[0] * Tc[0] + Hr[2] * Tc[2 * NRED] + Hr[4] * Tc[4 * NRED] + Hr[6] * Tc[6 * NRED];
-      const double a1 = Hr[1] * Tc[NRED] + Hr[3] * Tc[3 * NRED] + Hr[5] * Tc[5 * NRED];
-      HT[(NZ + row) * NRED + col] = a0 + a1;
+    // HT rows of the nodes k = 1..K: (7 x 7 node Hessian) x (7 x NRED block of T).  The phase is bound by shared-memory loads (8 warps
+    // on one LDS pipe), so the products are register tiled: a lane owns (k, four columns) -- 14 vector loads of T and the 49 Hessian
+    // entries (broadcast loads) feed 196 FMAs, 0.3 loads per FMA instead of 2.
+    static_assert(NRED == 16 && NZ == 7, "lane mapping written for NRED = 16");
+    if (lane < (NK - 1) * 4) {
+      const int k = lane / 4 + 1, c0 = (lane % 4) * 4;
+      double tc[NZ][4];
+#pragma unroll
+      for (int m = 0; m < NZ; ++m) {
+        const double* tp = T + ((k - 1) * NZ + m) * NRED + c0;
+#if defined(__CUDA_ARCH__)
+        const double2 v0 = *reinterpret_cast<const double2*>(tp), v1 = *reinterpret_cast<const double2*>(tp + 2);
+        tc[m][0] = v0.x, tc[m][1] = v0.y, tc[m][2] = v1.x, tc[m][3] = v1.y;
+#else
+        for (int j = 0; j < 4; ++j) tc[m][j] = tp[j];
+#endif
+      }
+#pragma unroll
+      for (int q = 0; q < NZ; ++q) {
+        const double* Hr = Hf + k * 49 + q * 7;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int m = 0; m < NZ; ++m) {
+          const double h = Hr[m];
+          a0 = fma(h, tc[m][0], a0), a1 = fma(h, tc[m][1], a1), a2 = fma(h, tc[m][2], a2), a3 = fma(h, tc[m][3], a3);
+        }
+        double* o = HT + (NZ + (k - 1) * NZ + q) * NRED + c0;
+        o[0] = a0, o[1] = a1, o[2] = a2, o[3] = a3;
+      }
     }
     for (int row = lane; row < NS; row += 32) {
       double acc0 = 0;
@@ -947,29 +969,45 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
   OBCA_WARP_SYNC();
   double* Mo = W.MA + (size_t)(a * L.Nmax + i) * (NSYM + NRED);
   OBCA_LANES(lane) {
-    for (int e = lane; e < NSYM + NRED; e += 32) {
-      if (e < NSYM) {
-        int q = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);  // row of the packed lower triangle; the float estimate is off by one at most
-        if ((q + 1) * (q + 2) / 2 <= e) ++q;
-        if (q * (q + 1) / 2 > e) --q;
-        const int cc = e - q * (q + 1) / 2;
-        double sacc = q < NZ ? HT[q * NRED + cc] : 0.0, s1 = 0.0;  // node-0 identity rows
-        const double* Tq = T + q;
-        const double* Hc = HT + NZ * NRED + cc;
-        int row = 0;
-        for (; row + 1 < NW; row += 2) sacc += Tq[row * NRED] * Hc[row * NRED], s1 += Tq[(row + 1) * NRED] * Hc[(row + 1) * NRED];
-        sacc += Tq[row * NRED] * Hc[row * NRED];  // NW = 35 is odd
-        sacc += s1;
-        if (q == IDT) sacc += hdT[cc];
-        if (cc == IDT) sacc += hdT[q];
-        Mo[e] = sacc;
-      } else {
-        const int q = e - NSYM;
-        double sacc = q < NZ ? hs0[q] + gnv[q] : 0.0;
-        for (int row = NZ; row < NS; ++row) sacc += T[(row - NZ) * NRED + q] * (hs0[row] + gnv[row]);
-        if (q == IDT) sacc += hdT[NRED];
-        Mo[e] = sacc;
+    // M = Tt' HT (lower triangle, packed): a lane owns rows q0, q0 + 1 and columns c0 .. c0 + 3 of the 16 x 16 product -- per row of T one
+    // vector load of T and two of HT for 8 FMAs (the tiles above the diagonal are skipped)
+    {
+      const int q0 = (lane / 4) * 2, c0 = (lane % 4) * 4;
+      if (q0 + 1 >= c0) {
+        double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (int row = 0; row < NW; ++row) {
+          const double* tp = T + row * NRED + q0;
+          const double* hp = HT + (NZ + row) * NRED + c0;
+#if defined(__CUDA_ARCH__)
+          const double2 t = *reinterpret_cast<const double2*>(tp), h01 = *reinterpret_cast<const double2*>(hp), h23 = *reinterpret_cast<const double2*>(hp + 2);
+          const double tq[2] = {t.x, t.y}, hv[4] = {h01.x, h01.y, h23.x, h23.y};
+#else
+          const double tq[2] = {tp[0], tp[1]}, hv[4] = {hp[0], hp[1], hp[2], hp[3]};
+#endif
+#pragma unroll
+          for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2) acc[a2][b2] = fma(tq[a2], hv[b2], acc[a2][b2]);
+        }
+#pragma unroll
+        for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+          for (int b2 = 0; b2 < 4; ++b2) {
+            const int q = q0 + a2, cc = c0 + b2;
+            if (cc > q) continue;
+            double sacc = acc[a2][b2] + (q < NZ ? HT[q * NRED + cc] : 0.0);  // node-0 identity rows
+            if (q == IDT) sacc += hdT[cc];
+            if (cc == IDT) sacc += hdT[q];
+            Mo[q * (q + 1) / 2 + cc] = sacc;
+          }
       }
+    }
+    if (lane < NRED) {
+      const int q = lane;
+      double sacc = q < NZ ? hs0[q] + gnv[q] : 0.0;
+      for (int row = NZ; row < NS; ++row) sacc += T[(row - NZ) * NRED + q] * (hs0[row] + gnv[row]);
+      if (q == IDT) sacc += hdT[NRED];
+      Mo[NSYM + q] = sacc;
     }
   }
   OBCA_WARP_SYNC();
@@ -1049,74 +1087,140 @@ OBCA_HDN void interval_cross(const Ctx& ctx, const Lay& L, const Scratch& W, dou
 #endif
   OBCA_ASSUME_SHARED(arena);
   double* sw = arena + (size_t)(wid < nw ? wid : 0) * NSW;
-  double* ta = sw;                  // [6][3][NRED] pose rows of Ta
-  double* tb = ta + NK * 3 * NRED;  // [6][3][NRED]
-  double* sa = tb + NK * 3 * NRED;  // [6][3] pose entries of s0a
-  double* sb = sa + NK * 3;         // [6][3]
-  double* hc = sb + NK * 3;         // [6][9] rows pose_a, cols pose_b
-  double* hb = hc + NK * 9;         // [18][NRED + 1] Hc Tb and Hc s0b
-  for (int it = wid; it < L.P * L.Nmax && wid < nw; it += nw) {
-    int p = it / L.Nmax, i = it % L.Nmax;
-    if (i * NK >= L.Mp[p]) continue;
-    int a = L.pa[p], b = L.pb[p];
+  // inputs of one (pair, interval) task, double buffered: the next task's operands are fetched from the per-slot work area
+  // (global memory, written by the null-space phase) with asynchronous copies while the current task is computed -- under full
+  // load (148 CTAs streaming their work areas) the L2/HBM round trip otherwise sits on the critical path of every task
+  constexpr int CIN = 2 * NK * 3 * NRED + 2 * NK * 3 + NK * 9;  // ta, tb, sa, sb, hc
+  static_assert(2 * CIN + NK * 3 * (NRED + 1) <= NSW, "cross-coupling buffers exceed the warp's shared-memory area");
+  double* hb = sw + 2 * CIN;  // [18][NRED + 1] Hc Tb and Hc s0b
+  auto fetch = [&](int it, double* in) {
+    double* ta = in;                  // [6][3][NRED] pose rows of Ta
+    double* tb = ta + NK * 3 * NRED;  // [6][3][NRED]
+    double* sa = tb + NK * 3 * NRED;  // [6][3] pose entries of s0a
+    double* sb = sa + NK * 3;         // [6][3]
+    double* hc = sb + NK * 3;         // [6][9] rows pose_a, cols pose_b
+    const int p = it / L.Nmax, i = it % L.Nmax;
+    const int a = L.pa[p], b = L.pb[p];
     const double* Ta = W.TT + (size_t)(a * L.Nmax + i) * (NW * NRED + NW);
     const double* Tb = W.TT + (size_t)(b * L.Nmax + i) * (NW * NRED + NW);
     OBCA_LANES(lane) {
       for (int e = lane; e < NK * 3 * NRED; e += 32) {
-        int k = e / (3 * NRED), r = (e / NRED) % 3, col = e % NRED;
-        ta[e] = tt_entry(Ta, k, r, col);
-        tb[e] = tt_entry(Tb, k, r, col);
+        const int k = e / (3 * NRED), r = (e / NRED) % 3, col = e % NRED;
+        if (k == 0) ta[e] = tb[e] = r == col ? 1.0 : 0.0;  // node 0 is the state itself
+        else {
+          const int o = ((k - 1) * NZ + r) * NRED + col;
+#if defined(__CUDA_ARCH__)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(ta + e)), "l"(Ta + o) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(tb + e)), "l"(Tb + o) : "memory");
+#else
+          ta[e] = Ta[o], tb[e] = Tb[o];
+#endif
+        }
       }
       for (int e = lane; e < NK * 3; e += 32) {
-        int k = e / 3, r = e % 3;
-        sa[e] = k == 0 ? 0.0 : Ta[NW * NRED + (k - 1) * NZ + r];
-        sb[e] = k == 0 ? 0.0 : Tb[NW * NRED + (k - 1) * NZ + r];
+        const int k = e / 3, r = e % 3;
+        if (k == 0) sa[e] = sb[e] = 0.0;
+        else {
+          const int o = NW * NRED + (k - 1) * NZ + r;
+#if defined(__CUDA_ARCH__)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sa + e)), "l"(Ta + o) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sb + e)), "l"(Tb + o) : "memory");
+#else
+          sa[e] = Ta[o], sb[e] = Tb[o];
+#endif
+        }
       }
       for (int e = lane; e < NK * 9; e += 32) {
-        int k = e / 9, r = (e / 3) % 3, m = e % 3;
-        hc[e] = W.PH[((size_t)p * 27 + sym(3 + m, r)) * L.Mv + i * NK + k];
+        const int k = e / 9, r = (e / 3) % 3, m = e % 3;
+        const double* src = W.PH + ((size_t)p * 27 + sym(3 + m, r)) * L.Mv + i * NK + k;
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(hc + e)), "l"(src) : "memory");
+#else
+        hc[e] = *src;
+#endif
       }
     }
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+  };
+  // the tasks of this warp: it = wid, wid + nw, ... over (pair, interval), skipping intervals beyond the pair's horizon
+  auto next_task = [&](int it) {
+    while (it < L.P * L.Nmax && (it % L.Nmax) * NK >= L.Mp[it / L.Nmax]) it += nw;
+    return it;
+  };
+  int it = wid < nw ? next_task(wid) : L.P * L.Nmax, buf = 0;
+  if (it < L.P * L.Nmax) fetch(it, sw);
+  for (; it < L.P * L.Nmax;) {
+    const int p = it / L.Nmax, i = it % L.Nmax;
+    const int itn = next_task(it + nw);
+    if (itn < L.P * L.Nmax) fetch(itn, sw + (buf ^ 1) * CIN);
+#if defined(__CUDA_ARCH__)
+    if (itn < L.P * L.Nmax) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
     OBCA_WARP_SYNC();
+    const double* ta = sw + buf * CIN;
+    const double* tb = ta + NK * 3 * NRED;
+    const double* sa = tb + NK * 3 * NRED;
+    const double* sb = sa + NK * 3;
+    const double* hc = sb + NK * 3;
     double* Mo = W.MAB + (size_t)(p * L.Nmax + i) * (NRED * NRED + 2 * NRED);
+    static_assert(NRED == 16, "the lane mapping below is written for NRED = 16");
+    // Register-tiled products (the phase is bound by shared-memory loads, 8 warps on one LDS pipe): a lane owns column cb = lane % 16
+    // and, with hf = lane / 16, one half of the k's (first product) or eight rows ra (second product).
+    //   HB[k][r][cb] = sum_m Hc_k[r][m] Tb_k[m][cb]          -- the three Tb entries of (k, cb) are loaded once for the three rows r
+    //   Mab[ra][cb]  = sum_{k,r} Ta_k[r][ra] HB[k][r][cb]    -- one HB entry and eight contiguous Ta entries per (k, r): 5 loads for 8 FMAs
     OBCA_LANES(lane) {
-      // HB[k][r][cb] = sum_m Hc_k[r][m] Tb_k[m][cb] first (and Hc_k s0b), then Mab = sum_{k,r} Ta_k[r][ra] HB[k][r][cb]:
-      // 18 terms per entry instead of 72
-      for (int e = lane; e < NK * 3 * (NRED + 1); e += 32) {
-        const int kr = e / (NRED + 1), cb = e % (NRED + 1), k = kr / 3;
-        double h = 0;
-        if (cb < NRED)
-          for (int m = 0; m < 3; ++m) h += hc[kr * 3 + m] * tb[(k * 3 + m) * NRED + cb];
-        else
-          for (int m = 0; m < 3; ++m) h += hc[kr * 3 + m] * sb[k * 3 + m];
-        hb[kr * (NRED + 1) + cb] = h;
-      }
-    }
-    OBCA_WARP_SYNC();
-    OBCA_LANES(lane) {
-      for (int e = lane; e < NRED * NRED + 2 * NRED; e += 32) {
-        double acc = 0, acc1 = 0;
-        if (e < NRED * NRED + NRED) {
-          // e < NRED^2: Mab[ra][cb]; then Ta' Hc s0b (column NRED of hb)
-          const int ra = e < NRED * NRED ? e / NRED : e - NRED * NRED, cb = e < NRED * NRED ? e % NRED : NRED;
-          for (int kr = 0; kr + 1 < NK * 3; kr += 2) {
-            acc += ta[kr * NRED + ra] * hb[kr * (NRED + 1) + cb];
-            acc1 += ta[(kr + 1) * NRED + ra] * hb[(kr + 1) * (NRED + 1) + cb];
-          }
-          acc += acc1;
-        } else {
-          int rb = e - NRED * NRED - NRED;  // Tb' Hc' s0a
-          for (int k = 0; k < NK; ++k)
-            for (int m = 0; m < 3; ++m) {
-              double h = 0;
-              for (int r = 0; r < 3; ++r) h += hc[k * 9 + r * 3 + m] * sa[k * 3 + r];
-              acc += tb[(k * 3 + m) * NRED + rb] * h;
-            }
+      const int cb = lane & 15, hf = lane >> 4;
+      for (int k = hf; k < NK; k += 2) {
+        const double t0 = tb[(k * 3 + 0) * NRED + cb], t1 = tb[(k * 3 + 1) * NRED + cb], t2 = tb[(k * 3 + 2) * NRED + cb];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const double* h = hc + (k * 3 + r) * 3;
+          hb[(k * 3 + r) * (NRED + 1) + cb] = (h[0] * t0 + h[1] * t1) + h[2] * t2;
         }
-        Mo[e] = acc;
+      }
+      if (lane < NK * 3) {  // column NRED: Hc_k s0b
+        const int kr = lane, k = kr / 3;
+        hb[kr * (NRED + 1) + NRED] = (hc[kr * 3] * sb[k * 3] + hc[kr * 3 + 1] * sb[k * 3 + 1]) + hc[kr * 3 + 2] * sb[k * 3 + 2];
       }
     }
     OBCA_WARP_SYNC();
+    OBCA_LANES(lane) {
+      const int cb = lane & 15, hf = lane >> 4;
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+      for (int kr = 0; kr < NK * 3; ++kr) {
+        const double h = hb[kr * (NRED + 1) + cb];
+        const double* t = ta + kr * NRED + hf * 8;  // 16-byte aligned: vectorised loads
+#if defined(__CUDA_ARCH__)
+        const double2 a01 = *reinterpret_cast<const double2*>(t), a23 = *reinterpret_cast<const double2*>(t + 2);
+        const double2 a45 = *reinterpret_cast<const double2*>(t + 4), a67 = *reinterpret_cast<const double2*>(t + 6);
+        acc[0] = fma(a01.x, h, acc[0]), acc[1] = fma(a01.y, h, acc[1]), acc[2] = fma(a23.x, h, acc[2]), acc[3] = fma(a23.y, h, acc[3]);
+        acc[4] = fma(a45.x, h, acc[4]), acc[5] = fma(a45.y, h, acc[5]), acc[6] = fma(a67.x, h, acc[6]), acc[7] = fma(a67.y, h, acc[7]);
+#else
+        for (int j = 0; j < 8; ++j) acc[j] = fma(t[j], h, acc[j]);
+#endif
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) Mo[(hf * 8 + j) * NRED + cb] = acc[j];
+      // the two gradient pieces: Ta' Hc s0b (lanes 0..15) and Tb' Hc' s0a (lanes 16..31)
+      double g = 0;
+      if (hf == 0) {
+        for (int kr = 0; kr < NK * 3; ++kr) g = fma(ta[kr * NRED + cb], hb[kr * (NRED + 1) + NRED], g);
+      } else {
+        for (int k = 0; k < NK; ++k)
+          for (int m = 0; m < 3; ++m) {
+            double h = 0;
+            for (int r = 0; r < 3; ++r) h += hc[k * 9 + r * 3 + m] * sa[k * 3 + r];
+            g += tb[(k * 3 + m) * NRED + cb] * h;
+          }
+      }
+      Mo[NRED * NRED + lane] = g;
+    }
+    OBCA_WARP_SYNC();
+    it = itn, buf ^= 1;
   }
 }
 
@@ -1145,12 +1249,14 @@ struct RicWork {
   int *uoff, *npv, *npt;  // [MAXV + 1], [MAXV + 1], [V][Nmax]
   const double** isrc;     // [n_in] address of every stage input at stage 0
   int* istr;               // [n_in][2] (doubles per stage, first stage beyond the block's horizon)
+  int* rmap;               // [7 V + nUmax] row / column of the stage matrix [states; controls] -> vehicle * 32 + reduced coordinate (-1: unused)
 };
 
 inline size_t riccati_only_doubles(const Lay& L) {
   size_t nX = L.nX, nU = L.nU;
   return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU + ((size_t)L.V * L.Nmax + 2) / 2 +
-         (OBCA_RIC_PREFETCH ? 3 * ((size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) + (size_t)L.V * 7 * (NRED + 1)) + 4 : 0);
+         (OBCA_RIC_PREFETCH ? 3 * ((size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) + (size_t)L.V * 7 * (NRED + 1)) + 4 : 0) +
+         (nX + nU) / 2 + 2;
 }
 
 // work arena shared by the null-space phase (NSW doubles per warp) and the Riccati phase
@@ -1196,6 +1302,7 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
     off = (off + 15) & ~(size_t)15;
     R.isrc = (const double**)((char*)0 + off);
     R.istr = (int*)(R.isrc + ric_input_count(L));
+    R.rmap = R.istr + (OBCA_RIC_PREFETCH ? 2 * ric_input_count(L) : 0);
   }
 }
 
@@ -1321,33 +1428,28 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
     if (i * NK >= L.Mp[p]) return 0.0;
     return a < b ? OBCA_MAB(p)[ra * NRED + rb] : OBCA_MAB(p)[rb * NRED + ra];
   };
-  auto ctl = [&](int u, int* a) -> int {  // control u -> vehicle, returns its reduced coordinate
-    int aa = 0;
-    while (u >= R.uoff[aa + 1]) ++aa;
-    *a = aa;
-    return 7 + u - R.uoff[aa];
-  };
-  const int nQ = idt * idt, nS = nu * idt, nR = nu * nu, nD = idt + nu + 1;
-  for (int it = ctx.tid; it < nQ + nS + nR + nD; it += ctx.nt) {
-    if (it < nQ) {
-      const int tr = it / idt, tc = it % idt;
-      R.Q[tr * nX + tc] = entry(tr / 7, tr % 7, tc / 7, tc % 7);
-    } else if (it < nQ + nS) {
-      const int e = it - nQ, u = e / idt, tc = e % idt;
-      int a;
-      const int ra = ctl(u, &a);
-      R.S[u * nX + tc] = entry(a, ra, tc / 7, tc % 7);
-    } else if (it < nQ + nS + nR) {
-      const int e = it - nQ - nS, u = e / nu, u2 = e % nu;
-      int a, b;
-      const int ra = ctl(u, &a), rb = ctl(u2, &b);
-      R.R[u * nu + u2] = entry(a, ra, b, rb);
-    } else {
-      // everything that touches dt, and the gradients: one thread per target, fixed summation order
-      const int t = it - nQ - nS - nR;
+  // [Q S'; S R]: `tpr` threads per row, each walks a contiguous run of columns (row / column coordinates from R.rmap)
+  const int nrow = idt + nu, nD = nrow + 1;
+  const int sh = ctx.nt >= 4 * nrow ? 2 : (ctx.nt >= 2 * nrow ? 1 : 0), tpr = 1 << sh;
+  for (int t = ctx.tid; t < nrow * tpr; t += ctx.nt) {
+    const int row = t >> sh, part = t & (tpr - 1);
+    const int cr = R.rmap[row], a = cr >> 5, ra = cr & 31;
+    const int ncol = row < idt ? idt : nrow;  // state rows: Q only (S' is not stored)
+    const int c0 = (part * ncol) >> sh, c1 = ((part + 1) * ncol) >> sh;
+    double* ds = row < idt ? R.Q + row * nX : R.S + (row - idt) * nX;
+    double* dc = R.R + (row - idt) * nu - idt;
+    for (int c = c0; c < c1; ++c) {
+      const int cc = R.rmap[c];
+      const double v = entry(a, ra, cc >> 5, cc & 31);
+      if (c < idt) ds[c] = v;
+      else dc[c] = v;
+    }
+  }
+  // everything that touches dt, and the gradients: one thread per target (the last threads of the CTA), fixed summation order
+  for (int t = ctx.nt - 1 - ctx.tid; t < nD; t += ctx.nt) {
+    {
       int a = -1, rc = IDT;
-      if (t < idt) a = t / 7, rc = t % 7;
-      else if (t < idt + nu) rc = ctl(t - idt, &a);
+      if (t < nrow) a = R.rmap[t] >> 5, rc = R.rmap[t] & 31;
       double hd = 0, g = 0;
       if (a >= 0) {
         if (i < L.N[a]) {
@@ -1642,6 +1744,21 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
       }
       R.uoff[V] = off;
     }
+    // (vehicle, reduced coordinate) of every row / column of this stage's matrix, once per stage: the gather below then needs no
+    // integer divisions by run-time values and no searches
+    for (int t = ctx.nt - 1 - ctx.tid; t < idt + nUmax; t += ctx.nt) {
+      int code = -1;
+      if (t < idt) code = (t / 7) * 32 + t % 7;
+      else {
+        int u = t - idt, off = 0;
+        for (int a = 0; a < V && code < 0; ++a) {
+          const int np = R.npt[a * L.Nmax + i];
+          if (u < off + np) code = a * 32 + 7 + (u - off);
+          off += np;
+        }
+      }
+      R.rmap[t] = code;
+    }
 #if OBCA_RIC_PREFETCH
     ric_input_wait();  // this stage's inputs (issued during the previous stage) have landed; the barrier publishes them
 #endif
@@ -1652,20 +1769,32 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     prof_mark(ctx, 12);
     // PA = P A ; PB = P B ; pc = P c + p   (block structure of A, B).  The 7-term items and the two dense columns (dt and the
     // constant) are separate loops so that the lanes of a warp do the same amount of work; the dense ones go to the last threads.
-    for (int it = ctx.tid; it < nX * (idt + nu); it += ctx.nt) {
-      const int r = it / (idt + nu), col = it % (idt + nu);
-      const double* Pr = R.P + r * nX;
-      double s = 0;
-      if (col < idt) {
-        const int a = col / 7, c = col % 7;
-        for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Ab[a * 49 + m * 7 + c];
-        R.PA[r * nX + col] = s;
-      } else {
-        int u = col - idt, a = 0;
-        while (u >= R.uoff[a + 1]) ++a;
-        const int j = u - R.uoff[a];
-        for (int m = 0; m < 7; ++m) s += Pr[7 * a + m] * R.Bb[(a * 7 + m) * NP + j];
-        R.PB[r * nu + u] = s;
+    {
+      // a thread owns one column (64 or 128 columns per pass) and every nrg-th row: the 7 coefficients of the column stay in registers
+      // and no index needs a division by a run-time value; a single thread (host emulation) walks all columns
+      const int ncols = idt + nu;
+      const bool grid2d = ctx.nt >= 128 && (ctx.nt & (ctx.nt - 1)) == 0;
+      const int lcg = ncols <= 64 ? 6 : 7;
+      const int cstep = grid2d ? (1 << lcg) : 1, rg = grid2d ? ctx.tid >> lcg : 0, nrg = grid2d ? ctx.nt >> lcg : 1;
+      for (int col = grid2d ? (ctx.tid & (cstep - 1)) : 0; col < ncols; col += grid2d ? ncols : 1) {
+        const double* src;
+        double* dst;
+        int a, sstr, ld;
+        if (col < idt) a = col / 7, src = R.Ab + a * 49 + col % 7, sstr = 7, dst = R.PA + col, ld = nX;
+        else {
+          const int code = R.rmap[col];
+          a = code >> 5, src = R.Bb + (a * 7) * NP + ((code & 31) - 7), sstr = NP, dst = R.PB + (col - idt), ld = nu;
+        }
+        double cf[7];
+#pragma unroll
+        for (int m = 0; m < 7; ++m) cf[m] = src[m * sstr];
+        for (int r = rg; r < nX; r += nrg) {
+          const double* Pr = R.P + r * nX + 7 * a;
+          double s = 0;
+#pragma unroll
+          for (int m = 0; m < 7; ++m) s += Pr[m] * cf[m];
+          dst[r * ld] = s;
+        }
       }
     }
     for (int it = ctx.nt - 1 - ctx.tid; it < 2 * nX; it += ctx.nt) {
@@ -1740,17 +1869,7 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     {
       double* P0 = W.RP + (size_t)i * pstride;
       const int np1 = nX + 1, nstrip = (nX + 1) / 2;
-      for (int it = ctx.tid; it < nstrip * np1 + nX; it += ctx.nt) {
-        int r, col;
-        if (it < nstrip * np1) {
-          const int p = it / np1, e = it % np1;
-          if (e < nX - p) r = p, col = p + e;
-          else {
-            r = nX - 1 - p, col = r + (e - (nX - p));
-            if (r == p) continue;  // middle row of an odd dimension: already covered
-          }
-        } else
-          r = it - nstrip * np1, col = nX;
+      auto item = [&](int r, int col) {
         double s = 0;
         const double* rhs = col < nX ? R.PA + col : R.pc;  // column of PA (stride nX) or pc (stride 1)
         const int rs = col < nX ? nX : 1;
@@ -1774,7 +1893,23 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
           const double v = R.q[r] + s;
           R.p[r] = v, P0[nX * nX + r] = v;
         }
-      }
+      };
+      // strip p holds rows p and nX-1-p: np1 items.  Threads form a (strip group) x (item) grid, 32 or 64 items wide, so that no index
+      // needs a division by a run-time value; the nX gradient entries of the strips' complement go to the last threads
+      const bool grid2d = ctx.nt >= 64 && (ctx.nt & (ctx.nt - 1)) == 0;
+      const int lce = np1 <= 32 ? 5 : 6;
+      const int e0 = grid2d ? (ctx.tid & ((1 << lce) - 1)) : 0, pg = grid2d ? ctx.tid >> lce : 0, npg = grid2d ? ctx.nt >> lce : 1;
+      for (int p = pg; p < nstrip; p += npg)
+        for (int e = e0; e < np1; e += grid2d ? np1 : 1) {
+          int r, col;
+          if (e < nX - p) r = p, col = p + e;
+          else {
+            r = nX - 1 - p, col = r + (e - (nX - p));
+            if (r == p) continue;  // middle row of an odd dimension: already covered
+          }
+          item(r, col);
+        }
+      for (int r = ctx.nt - 1 - ctx.tid; r < nX; r += ctx.nt) item(r, nX);
     }
     cta_sync(ctx);
   }

@@ -325,8 +325,15 @@ class ObcaSolver:
         if buf is None or tuple(buf[0].shape) != shape:
             buf = (torch.empty(shape, dtype=torch.float64, pin_memory=True), torch.empty(shape, dtype=torch.float64, device=self.device))
             self._staging[name] = buf
-        np.copyto(buf[0].numpy(), np.asarray(a, dtype=np.float64).reshape(shape))
-        buf[1].copy_(buf[0], non_blocking=True)
+        arr = np.ascontiguousarray(a, dtype=np.float64).reshape(shape)
+        if not arr.flags.writeable:  # torch.from_numpy warns about read-only arrays (it is only read here)
+            arr = arr.copy()
+        src = torch.from_numpy(arr)
+        if src.is_pinned():  # the caller's array already is page-locked (e.g. allocated through torch.empty(pin_memory=True)): DMA straight from it
+            buf[1].copy_(src, non_blocking=True)
+        else:
+            buf[0].copy_(src)  # torch's CPU copy runs on all intra-op threads: several times the rate of a single-threaded memcpy
+            buf[1].copy_(buf[0], non_blocking=True)
         return buf[1]
 
     def _to_host(self, tensors):
@@ -346,7 +353,7 @@ class ObcaSolver:
             pin.copy_(t, non_blocking=True)
             pins.append(pin)
         torch.cuda.synchronize(self.device)
-        return [None if p_ is None else p_.numpy().copy() for p_ in pins]
+        return [None if p_ is None else p_.clone().numpy() for p_ in pins]  # independent copies (multi-threaded), the pinned buffers are reused
 
     def close(self):
         if getattr(self, "handle", None):
