@@ -448,6 +448,7 @@ OBCA_HDN int mpc_kkt_solve_impl(const Ctx& ctx, const Lay& L, const Stat& S, con
   double* DZ = KK + (size_t)N * 12;   // [N][7] step
   double* QD = DZ + (size_t)N * 7;    // [N][15] y-contracted second directional derivatives of the RK4 map
   double* OB = QD + (size_t)N * 15;   // [N][O][9] obstacle Schur complements on the pose (6 sym + 3 grad)
+  double* CR_ = OB + (size_t)N * L.O * 9 + 128;  // [N][5] + [5] staged residuals (= CR below, behind the stage scratch)
   const int nPair = L.P * N, nObs = N * L.O, nDir = (N - 1) * 15;
   const int uPair = (nPair + 31) / 32, uObs = (nObs + 31) / 32, uDir = (nDir + 31) / 32;
   int* next_unit = ok_shared + 1;  // Shared::again, unused in MPC mode
@@ -563,6 +564,10 @@ OBCA_HDN int mpc_kkt_solve_impl(const Ctx& ctx, const Lay& L, const Stat& S, con
     }
     for (int q = 0; q < 28; ++q) HN[(size_t)n * 28 + q] = H[q];
     for (int q = 0; q < NZ; ++q) GN[(size_t)n * 7 + q] = g[q];
+    if (n < N - 1)
+      for (int r = 0; r < 5; ++r) CR_[n * 5 + r] = W.c[L.YCOL(0, r, n)];
+    if (n == 0)
+      for (int r = 0; r < 5; ++r) CR_[N * 5 + r] = W.c[L.YINIT(0, r)];
   }
   cta_sync(ctx);
   prof_mark(ctx, 3);
@@ -572,7 +577,9 @@ OBCA_HDN int mpc_kkt_solve_impl(const Ctx& ctx, const Lay& L, const Stat& S, con
   // e'dz_{N-1} = -c_h is handled exactly by a second right-hand side through the same factorisation (TWO): solution 2 answers a unit
   // gradient on psi_{N-1}; the row's multiplier step is dy_h = -(c_h + e'dz1) / (e'dz2) and every quantity is X1 + dy_h X2.
   double* SC = OB + (size_t)N * L.O * 9;  // [128] stage scratch: PA[35], Pr[5], Q[49], qv[7], K[12], Pr2[5], qv2[7]
-  double* K2 = SC + 128;                  // [N][2]   constant gain terms of solution 2
+  double* CR = SC + 128;                  // [N][5] + [5] dynamics / initial-state residuals staged next to the stage data: the serial
+                                          // recursion would otherwise wait for a global-memory round trip in every stage
+  double* K2 = CR + (size_t)(N + 1) * 5;  // [N][2]   constant gain terms of solution 2
   double* P2 = K2 + (size_t)N * 2;        // [N+1][5] cost-to-go gradient of solution 2
   double* DZ2 = P2 + (size_t)(N + 1) * 5; // [N][7]   step of solution 2
   const bool TWO = EU && L.heading[0];
@@ -595,7 +602,7 @@ OBCA_HDN int mpc_kkt_solve_impl(const Ctx& ctx, const Lay& L, const Stat& S, con
             } else if (e < 40) {
               const int r = e - 35;
               double cr = 0;
-              for (int m = 0; m < 5; ++m) cr += Pn[r * 5 + m] * W.c[L.YCOL(0, m, n)];
+              for (int m = 0; m < 5; ++m) cr += Pn[r * 5 + m] * CR[n * 5 + m];
               Pr[r] = Pn[25 + r] - cr;  // P (-r) + pv
             } else
               Pr2[e - 40] = P2[(size_t)(n + 1) * 5 + (e - 40)];
@@ -671,7 +678,7 @@ OBCA_HDN int mpc_kkt_solve_impl(const Ctx& ctx, const Lay& L, const Stat& S, con
     }
     // forward pass
     OBCA_LANES(lane) {
-      if (lane < 5) DZ[lane] = -W.c[L.YINIT(0, lane)];
+      if (lane < 5) DZ[lane] = -CR[N * 5 + lane];
       else if (TWO && lane < 10) DZ2[lane - 5] = 0.0;
     }
     OBCA_WARP_SYNC();
@@ -696,7 +703,7 @@ OBCA_HDN int mpc_kkt_solve_impl(const Ctx& ctx, const Lay& L, const Stat& S, con
         const double* A = AJ + (size_t)n * 35;
         OBCA_LANES(lane) {
           if (lane < 5) {
-            double sacc = -W.c[L.YCOL(0, lane, n)];
+            double sacc = -CR[n * 5 + lane];
             for (int q = 0; q < 7; ++q) sacc += A[lane * 7 + q] * w[q];
             w[7 + lane] = sacc;  // dz of stage n+1
           } else if (TWO && lane < 10) {
@@ -794,6 +801,6 @@ OBCA_HDN int mpc_kkt_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Sc
   return mpc_kkt_solve_impl<true>(ctx, L, S, W, RW, ok_shared);
 }
 
-inline size_t mpc_work_doubles(const Lay& L) { return (size_t)(L.Mv + 1) * (28 + 7 + 35 + 30 + 12 + 7 + 15 + 9 * L.O) + 128 + (L.euler ? (size_t)(L.Mv + 1) * 14 : 0); }
+inline size_t mpc_work_doubles(const Lay& L) { return (size_t)(L.Mv + 1) * (28 + 7 + 35 + 30 + 12 + 7 + 15 + 5 + 9 * L.O) + 128 + (L.euler ? (size_t)(L.Mv + 1) * 14 : 0); }
 
 }  // namespace obca
