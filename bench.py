@@ -420,6 +420,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the OBCA solver has no CPU fallback")
+    # torchrun sets OMP_NUM_THREADS=1: give every rank its share of the host cores back (the e2e leg stages its buffers with torch's
+    # multi-threaded CPU copy)
+    torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(1, world)))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
