@@ -1250,13 +1250,14 @@ struct RicWork {
   const double** isrc;     // [n_in] address of every stage input at stage 0
   int* istr;               // [n_in][2] (doubles per stage, first stage beyond the block's horizon)
   int* rmap;               // [7 V + nUmax] row / column of the stage matrix [states; controls] -> vehicle * 32 + reduced coordinate (-1: unused)
+  int* btab;               // [V][V] block (a, b) of the stage Hessian: 4 * (offset from MAs) + kind (0 zero, 1 packed diagonal block, 2 MAB, 3 MAB transposed)
 };
 
 inline size_t riccati_only_doubles(const Lay& L) {
   size_t nX = L.nX, nU = L.nU;
   return 4 * nX * nX + 4 * nX * nU + 2 * nU * nU + 2 * nU * (nX + 1) + 8 * (nX + nU) + (size_t)L.V * (49 + 7 * NP + 14) + 2 * (MAXV + 1) + 32 + nU + ((size_t)L.V * L.Nmax + 2) / 2 +
          (OBCA_RIC_PREFETCH ? 3 * ((size_t)L.V * (NSYM + NRED) + (size_t)L.P * (NRED * NRED + 2 * NRED) + (size_t)L.V * 7 * (NRED + 1)) + 4 : 0) +
-         (nX + nU) / 2 + 2;
+         (nX + nU) / 2 + 2 + (size_t)(L.V * L.V + 1) / 2;
 }
 
 // work arena shared by the null-space phase (NSW doubles per warp) and the Riccati phase
@@ -1303,6 +1304,7 @@ OBCA_HD void ric_carve(RicWork& R, const Lay& L, double* w) {
     R.isrc = (const double**)((char*)0 + off);
     R.istr = (int*)(R.isrc + ric_input_count(L));
     R.rmap = R.istr + (OBCA_RIC_PREFETCH ? 2 * ric_input_count(L) : 0);
+    R.btab = R.rmap + (7 * L.V + L.nU);
   }
 }
 
@@ -1422,11 +1424,19 @@ OBCA_HD void riccati_stage_assemble(const Ctx& ctx, const Lay& L, const Scratch&
   prof_mark(ctx, 28);
   // entry (vehicle a, reduced coordinate ra) x (vehicle b, reduced coordinate rb) of the stage Hessian
   auto entry = [&](int a, int ra, int b, int rb) -> double {
+#if OBCA_RIC_PREFETCH
+    // block table of this stage (filled with the row map): no horizon tests, no pair-index arithmetic per entry
+    const int code = R.btab[a * V + b], kind = code & 3;
+    const double* base = R.MAs + (code >> 2);
+    if (kind == 0) return 0.0;
+    return kind == 1 ? base[sym(ra, rb)] : (kind == 2 ? base[ra * NRED + rb] : base[rb * NRED + ra]);
+#else
     if (a == b) return i < L.N[a] ? OBCA_MA(a)[sym(ra, rb)] : 0.0;
     const int lo = a < b ? a : b, hi = a < b ? b : a;
     const int p = lo * V - lo * (lo + 1) / 2 + (hi - lo - 1);  // index of the pair (lo, hi) in combinations order
     if (i * NK >= L.Mp[p]) return 0.0;
     return a < b ? OBCA_MAB(p)[ra * NRED + rb] : OBCA_MAB(p)[rb * NRED + ra];
+#endif
   };
   // [Q S'; S R]: `tpr` threads per row, each walks a contiguous run of columns (row / column coordinates from R.rmap)
   const int nrow = idt + nu, nD = nrow + 1;
@@ -1760,6 +1770,20 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
       R.rmap[t] = code;
     }
 #if OBCA_RIC_PREFETCH
+    for (int t = ctx.tid; t < V * V; t += ctx.nt) {
+      const int a = t / V, b = t % V;
+      int code = 0;
+      if (a == b) {
+        if (i < L.N[a]) code = 4 * (a * (NSYM + NRED)) + 1;
+      } else {
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        const int p = lo * V - lo * (lo + 1) / 2 + (hi - lo - 1);  // index of the pair (lo, hi) in combinations order
+        if (i * NK < L.Mp[p]) code = 4 * (V * (NSYM + NRED) + p * (NRED * NRED + 2 * NRED)) + (a < b ? 2 : 3);
+      }
+      R.btab[t] = code;
+    }
+#endif
+#if OBCA_RIC_PREFETCH
     ric_input_wait();  // this stage's inputs (issued during the previous stage) have landed; the barrier publishes them
 #endif
     cta_sync(ctx);
@@ -1852,14 +1876,24 @@ OBCA_HDN void riccati_backward(const Ctx& ctx, const Lay& L, const Scratch& W, d
     // [nUmax][nUmax]; the forward pass computes u = L^-T (Ks [x; 1]).  The generic path stores the gains as Ks and L = I.
     {
       double* Kg = W.RK + (size_t)i * kstride;
-      for (int it = ctx.tid; it < nu * nc; it += ctx.nt) {
-        const int u = it / nc, col = it % nc;
-        Kg[col * nUmax + u] = R.K[it];
-      }
       double* Lg = Kg + (size_t)nc * nUmax;
-      for (int it = ctx.tid; it < nu * nu; it += ctx.nt) {
-        const int r = it / nu, m = it % nu;
-        if (m < r) Lg[r * nUmax + m] = ldl_form ? R.F[it] : 0.0;
+      if (ctx.nt >= 64 && (ctx.nt & (ctx.nt - 1)) == 0) {
+        // lanes over consecutive controls (coalesced global stores), thread groups over the columns / rows: no run-time divisions
+        const int lu = nu <= 32 ? 5 : 6, u = ctx.tid & ((1 << lu) - 1), g0 = ctx.tid >> lu, ng = ctx.nt >> lu;
+        if (u < nu) {
+          for (int col = g0; col < nc; col += ng) Kg[col * nUmax + u] = R.K[u * nc + col];
+          for (int r = g0; r < nu; r += ng)
+            if (u < r) Lg[r * nUmax + u] = ldl_form ? R.F[r * nu + u] : 0.0;
+        }
+      } else {
+        for (int it = ctx.tid; it < nu * nc; it += ctx.nt) {
+          const int u = it / nc, col = it % nc;
+          Kg[col * nUmax + u] = R.K[it];
+        }
+        for (int it = ctx.tid; it < nu * nu; it += ctx.nt) {
+          const int r = it / nu, m = it % nu;
+          if (m < r) Lg[r * nUmax + m] = ldl_form ? R.F[it] : 0.0;
+        }
       }
     }
     // P <- Q + A'PA + Gm'K ; p <- q + A'pc + Gm'k, written straight into the cost-to-go of the next stage (shared memory) and into
