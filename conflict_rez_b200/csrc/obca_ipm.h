@@ -254,6 +254,7 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
   // IPOPT acceptable-point bookkeeping: acceptable_tol 1e-6, acceptable_iter 15
   double best_E = INFINITY, best_f = 0, best_cv = 0, best_du = 0, best_co = 0;
   int n_acceptable = 0;
+  int n_rescue = 0;  // line-search failures answered by a barrier reset (see below)
   int status = OBCA_MAXITER_EXCEEDED;
   double dual_inf = 0, cviol = 0, compl0 = 0;
   const Stage st = {RW, rw_cap, sh->bars};
@@ -576,6 +577,19 @@ OBCA_HDN int ipm_attempt(const Ctx& ctx, const Lay& L, const Stat& S, const Opts
     if (getenv("OBCA_TRACE")) printf("       a_pr=%.3e a_du=%.3e alpha=%.3e a_min=%.3e dphi=%.3e dw=%.1e acc=%d\n", a_pr, a_du, alpha, a_min, dphi, dw, (int)accepted);
 #endif
     if (!accepted) {
+      // IPOPT enters its feasibility-restoration phase here.  This solver has none; what it can do cheaply is leave the corner the
+      // iterate is stuck in: raise the barrier parameter again (x10, at most mu_init), forget the filter and iterate on -- a larger mu
+      // re-centres the slacks that blocked the step.  Three attempts, then Restoration_Failed as before.
+      if (n_rescue < 3 && it < o.max_iter) {
+        ++n_rescue;
+        mu = fmin(o.mu_init, 10.0 * mu);
+        cta_sync(ctx);
+        if (ctx.tid == 0) sh->filt_n = 0;
+        cta_sync(ctx);
+        tiny_last = false, force_mu = false;
+        ++it;
+        continue;
+      }
       status = OBCA_RESTORATION_FAILED;  // becomes Solved_To_Acceptable_Level below when an acceptable point was stored
       break;
     }
