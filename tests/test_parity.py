@@ -189,7 +189,7 @@ def test_four_vehicle_batch_properties(cuda_lib, strategy_file):
     plan = solve_joint_batch(strategy_file, agents, random_init_offsets(8, 4, seed=0), SolveOptions(max_iter=600), lib=cuda_lib)
     res = plan.result
     ok = res.status >= 0
-    assert ok.sum() >= 6, res.status
+    assert ok.all(), res.status  # round 1 tolerated 2 failures of 8 here
     worst = check_solution_properties(plan.problem, res.z[ok], res.dt[ok])
     assert worst["collocation"] <= 1e-2 and worst["tube"] <= 1e-2 and worst["terminal"] <= 1e-2 and worst["init"] <= 1e-2
     assert worst["obstacle_clearance"] >= plan.problem.dmin - 1e-2
@@ -201,6 +201,8 @@ SWEEP = [
     pytest.param(("vehicle_1", "vehicle_2"), 2, 3, "cuda", id="cuda-V2-O8-nps3", marks=pytest.mark.gpu),
     pytest.param(("vehicle_1", "vehicle_2", "vehicle_3"), 4, 5, "cuda", id="cuda-V3-O10-nps5", marks=pytest.mark.gpu),
     pytest.param(("vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"), 6, 4, "cuda", id="cuda-V4-O12-nps4", marks=pytest.mark.gpu),
+    # 20 obstacles, 128 instances: before the barrier-reset rescue of failed line searches ~2 % of this cell ended in Restoration_Failed
+    pytest.param(("vehicle_0", "vehicle_1", "vehicle_2", "vehicle_3"), 14, 5, "cuda128", id="cuda-V4-O20-nps5-B128", marks=pytest.mark.gpu),
 ]
 
 
@@ -214,13 +216,13 @@ def test_scaling_sweep_cells(request, strategy_file, agents, n_extra, nps, which
     lib, dev = (request.getfixturevalue("emu_lib"), "cpu") if which == "emu" else (request.getfixturevalue("cuda_lib"), "cuda:0")
     obstacles = random_obstacles(strategy_file, n_extra, seed=7)
     idx = [int(a[-1]) for a in agents]
-    B = 2 if which == "emu" else 6
+    B = 2 if which == "emu" else (128 if which == "cuda128" else 6)
     offs = random_init_offsets(B, 4, seed=11)[:, idx]
     plan = solve_joint_batch(strategy_file, list(agents), offs, SolveOptions(max_iter=600), device=dev, lib=lib, obstacles=obstacles, n_per_set=nps)
     res = plan.result
     assert plan.problem.O == 6 + n_extra and plan.problem.V == len(agents)
     ok = res.status >= 0
-    assert ok.sum() >= B - 1, res.status
+    assert ok.all(), res.status
     worst = check_solution_properties(plan.problem, res.z[ok], res.dt[ok])
     assert worst["collocation"] <= 1e-2 and worst["tube"] <= 1e-2 and worst["terminal"] <= 1e-2 and worst["init"] <= 1e-2
     assert worst["obstacle_clearance"] >= plan.problem.dmin - 1e-2
