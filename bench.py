@@ -448,6 +448,14 @@ def main():
     mine = shard_instances(global_batch, rank, world)  # interleaved shard: random instances, equal expected load per rank
     offs = offs_all[mine]
     B = len(mine)
+    # the warm-start pipeline runs twice: the first call also pays the one-time costs of a process (CUDA context, growth of the device
+    # memory pool the handles allocate from, pinned staging buffers); the second one is what a planner that runs continuously sees
+    t_ws0 = time.perf_counter()
+    plan = prepare_joint_batch(fn, AGENTS, offs, opts, device=device, final_headings=HEADINGS)
+    torch.cuda.synchronize(device)
+    t_ws0 = time.perf_counter() - t_ws0
+    plan.solver.close()
+    del plan
     t_ws = time.perf_counter()
     plan = prepare_joint_batch(fn, AGENTS, offs, opts, device=device, final_headings=HEADINGS)  # warm start, device resident
     torch.cuda.synchronize(device)
@@ -591,9 +599,10 @@ def main():
     }
     ws_total = t_ws
     line["warm_start"] = {
-        "wall_s_rank0": t_ws, **plan.timing, "single_vehicle_fail_rank0": int(sum((r.status < 0).sum() for r in plan.singles)),
+        "wall_s_rank0": t_ws, "first_call_wall_s_rank0": t_ws0, **plan.timing, "single_vehicle_fail_rank0": int(sum((r.status < 0).sum() for r in plan.singles)),
         "plan_to_plan_solves_per_s": converged / (ws_total + t_dev / args.steps) if world == 1 else None,
-        "note": "untimed setup of the step (SURVEY.md 8f rank 1): vectorised pose guess on the host, tube-following solves (state_ws), obstacle and pair "
+        "note": "untimed setup of the step (SURVEY.md 8f rank 1), second call of the pipeline in this process (first_call_wall_s_rank0 = the first, with "
+        "the process's one-time costs): kinematic guess on the host, state_ws (Euler NLP) + interp_ws_for_collocation, obstacle and pair "
         "duals by obca_dual_ws / obca_joint_dual_ws on the device, 4 batched single-vehicle solves; the joint warm start stays in HBM. "
         "plan_to_plan = converged plans / (warm-start pipeline + one joint solve), the reference's solve_single_problems -> solve_final_problem_obca chain",
     }

@@ -150,9 +150,14 @@ def prepare_joint_batch(
     tm = {}
     t0 = time.perf_counter()
     prob = build_problem(rl_file_name, list(agents), init_offsets=init_offsets, final_headings=final_headings, **problem_kwargs)
-    z0, dts = pose_guess(prob, rl_file_name, list(agents))
+    kin_all = None
+    if state_ws == "euler":  # the Euler warm start takes the kinematic guess on its own uniform grid: no collocation resampling needed on the host
+        kin_all = kinematic_paths(prob, rl_file_name, list(agents))
+        z0 = dts = None
+    else:
+        z0, dts = pose_guess(prob, rl_file_name, list(agents))
     tm["host_pose_guess_s"] = time.perf_counter() - t0
-    B, V, O = z0.shape[0], prob.V, prob.O
+    B, V, O = init_offsets.shape[0], prob.V, prob.O
     Mmax = int(prob.nodes.max())
     joint = ObcaSolver(prob, options, device=device, lib=lib)
     dev = joint.device
@@ -163,17 +168,16 @@ def prepare_joint_batch(
     dt_sum = torch.zeros(B, dtype=torch.float64, device=dev)
     singles = []
     ws_fail = 0
-    kin_all = None
     for ia, agent in enumerate(agents):
         p1 = build_problem(rl_file_name, [agent], init_offsets=init_offsets[:, ia : ia + 1], final_headings=final_headings, **problem_kwargs)
         M = int(p1.nodes[0])
         sv = ObcaSolver(p1, options, device=device, lib=lib)
-        d = {"pose": sv._to_dev(p1.init_pose, (B, 1, 3)), "z": sv._to_dev(z0[:, ia : ia + 1, :M], (B, 1, M, 7)), "dt": sv._to_dev(dts[:, ia], (B,))}
+        d = {"pose": sv._to_dev(p1.init_pose, (B, 1, 3))}
+        if z0 is not None:
+            d["z"], d["dt"] = sv._to_dev(z0[:, ia : ia + 1, :M], (B, 1, M, 7)), sv._to_dev(dts[:, ia], (B,))
         # stage 1 (the role of Vehicle.state_ws, vehicle.py:99-231): the same tube-following problem without obstacles gives a
         # dynamically feasible trajectory inside the tube sets; the OBCA solve then starts from it
         if state_ws == "euler":
-            if kin_all is None:
-                kin_all = kinematic_paths(prob, rl_file_name, list(agents))
             z1, dt1, st1 = euler_state_ws(p1, kin_all[ia], 30, 0.1, device, lib)
         else:
             z1, dt1, st1 = tube_following_ws(p1, d, options, device, lib)

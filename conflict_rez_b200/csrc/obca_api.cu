@@ -8,7 +8,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "obca_core.h"
@@ -104,11 +106,47 @@ static int dev_sync() { return 0; }
     cudaError_t e_ = (call);                                                      \
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
+// Handles come and go (the warm-start pipeline creates one per agent and stage, each with gigabytes of iterates for a 4096 batch), and
+// cudaMalloc / cudaFree of such buffers cost ~0.3 s per handle.  The buffers therefore come from the device's stream-ordered memory pool
+// with the release threshold lifted: a freed buffer stays in the pool and the next handle reuses it without a driver round trip.
+static std::mutex g_pool_mu;
+static std::unordered_set<void*> g_pool_ptrs;  // pointers that came from cudaMallocAsync (the others from the cudaMalloc fallback)
 static int dev_alloc(void** p, size_t bytes) {
-  if (cudaMalloc(p, bytes ? bytes : 1) != cudaSuccess) return -1;
-  return cudaMemset(*p, 0, bytes ? bytes : 1) == cudaSuccess ? 0 : -1;
+  static bool pool_ready[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+      pool_ready[dev] = true;
+    }
+  }
+  const size_t n = bytes ? bytes : 1;
+  if (cudaMallocAsync(p, n, 0) == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool_ptrs.insert(*p);
+  } else {
+    cudaGetLastError();
+    if (cudaMalloc(p, n) != cudaSuccess) return -1;
+  }
+  if (cudaMemsetAsync(*p, 0, n, 0) != cudaSuccess) return -1;
+  return cudaStreamSynchronize(0) == cudaSuccess ? 0 : -1;  // usable from every stream afterwards
 }
-static void dev_free(void* p) { cudaFree(p); }
+static void dev_free(void* p) {
+  if (!p) return;
+  bool pooled;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    pooled = g_pool_ptrs.erase(p) > 0;
+  }
+  if (pooled) cudaFreeAsync(p, 0);  // free_device synchronises the device before the first free of a handle
+  else cudaFree(p);
+}
 static int h2d(void* d, const void* h, size_t n) { return cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1; }
 static int d2h(void* h, const void* d, size_t n) { return cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1; }
 static int dev_sync() { return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1; }
@@ -387,6 +425,9 @@ int obca_set_options(ObcaHandle* h, const ObcaOptions* opts) {
 }
 
 static void free_device(ObcaHandle* h) {
+#ifndef OBCA_HOST_EMU
+  if (h->d_iter || h->d_L) cudaDeviceSynchronize();  // kernels of this handle may still run on another stream: the frees below are stream ordered on stream 0
+#endif
   dev_free(h->d_L), dev_free(h->d_S), dev_free(h->d_tube), dev_free(h->d_xL), dev_free(h->d_xU), dev_free(h->d_bcls);
   h->d_bcls = nullptr;
   dev_free(h->d_iter), dev_free(h->d_work), dev_free(h->d_rw), dev_free(h->d_res), dev_free(h->d_counter), dev_free(h->d_order), dev_free(h->d_prof);
