@@ -99,3 +99,10 @@ class MultiVehiclePlanner(object):
         for agent in self.agents:
             self.vehicles[agent].get_solution(sol=sol)
             self.final_results[agent] = self.vehicles[agent].interpolate_states(final_t)
+
+    def solve_final_problem_circles(self, K: int = 5, N_per_set: int = 5, shrink_tube: float = 0.5, dmin: float = 0.05, d_buffer: float = 0.2):
+        """The circle-approximation variant of the joint problem (multi_vehicle_planner.py:111-206, rect2circles.py:13-37) is not
+        provided: the reference method cannot run as shipped (``self.agents - {agent}`` on a list raises ``TypeError`` at :150; it also
+        omits ``final_heading`` and only constrains the nodes ``k < K``), nothing in the reference calls it, and the OBCA formulation
+        (``solve_final_problem_obca``) is the one every experiment uses.  Stated explicitly instead of failing with ``AttributeError``."""
+        raise NotImplementedError("solve_final_problem_circles: the reference variant is unusable as shipped (SURVEY.md App. B-1); use solve_final_problem_obca")
