@@ -41,7 +41,7 @@ NCU = {"dram_bytes_per_iter": 21.9e6, "fp64_pipe_pct": 6.7, "issue_active_pct": 
 
 def load_ncu():
     """The committed ncu summary of the current kernel, if this round produced one (profiles/r02_ncu_k_solve.json)."""
-    for name in ("r02q_ncu_k_solve.json", "r02g_ncu_k_solve.json", "r02_ncu_k_solve.json"):  # newest first
+    for name in ("r03m_ncu_k_solve_full_load.json", "r02q_ncu_k_solve.json", "r02g_ncu_k_solve.json", "r02_ncu_k_solve.json"):  # newest first (r03m: one instance on every SM)
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
             with open(path) as f:
