@@ -76,8 +76,10 @@ OBCA_HD void flat_pass_impl(const Ctx& ctx, const Stage& st, const BoundCls* bc,
     if (ctx.tid == 0) {
       for (int k = 0; k < ST_STAGES; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem(st.bar + k)) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic writes to the arena vs the bulk copies
     }
+    // earlier generic-proxy accesses of the arena (every thread's own, by the phases before this pass) vs the bulk copies issued
+    // below: each thread fences its accesses, the barrier hands them to the issuing thread
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     auto issue = [&](int t) {
       const int stage = t % ST_STAGES, start = t * ST_TILE;

@@ -688,6 +688,7 @@ OBCA_HDN void nullspace_block(const Ctx& ctx, const Lay& L, const Stat& S, const
     }
 #endif
     double alpha = rk < NU2 ? Mq[rk * NC + j] : 0.0;
+    OBCA_WARP_SYNC();  // every lane holds the pivot entry before lane 0 overwrites it with beta (racecheck: intra-warp read / write hazard)
     double beta = sqrt(alpha * alpha + nrm);
     full = sqrt(full + alpha * alpha + nrm);
     if (rk >= NU2 || !(beta > 1e-8 * fmax(full, rref[j])) || !(full > 0)) {
