@@ -775,8 +775,9 @@ OBCA_HDN void ipm_solve(const Ctx& ctx, const Lay& L, const Stat& S, const Opts&
   if (ctx.tid == 0) {
     res->status = status, res->restarts = restarts;
     res->rho_carry = next;
-    *rho = rho0;
   }
+  cta_sync(ctx);  // every warp has evaluated the test on S.rho above before the weight is reset (racecheck: read / write hazard)
+  if (ctx.tid == 0) *rho = rho0;
   cta_sync(ctx);
 }
 
