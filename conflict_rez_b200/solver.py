@@ -352,7 +352,7 @@ class ObcaSolver:
                 self._staging[key] = pin
             pin.copy_(t, non_blocking=True)
             pins.append(pin)
-        torch.cuda.synchronize(self.device)
+        torch.cuda.current_stream(self.device).synchronize()  # every copy above is on this stream; other streams (PipelinedSolver) keep running
         return [None if p_ is None else p_.clone().numpy() for p_ in pins]  # independent copies (multi-threaded), the pinned buffers are reused
 
     def close(self):
@@ -519,6 +519,89 @@ class ObcaSolver:
         dx, dy, ok = np.zeros(L["nx"]), np.zeros(L["ny"]), ctypes.c_int32()
         self._check(self.lib.obca_debug_step(self.handle, b, mu, delta_w, _np_ptr(dx), _np_ptr(dy), ctypes.byref(ok)))
         return dx, dy, int(ok.value)
+
+
+class PipelinedSolver:
+    """Consecutive batches of the SAME problem shape, double buffered: ``depth`` library handles on ``depth`` CUDA streams.
+
+    One batch is one persistent ``k_solve`` launch (one CTA per SM pulling instances from a queue); its last wave leaves SMs idle
+    (3.46 instances per SM at 512 instances: a fifth of the launch).  With the next batch already launched on another stream, its CTAs
+    start on every SM the moment the previous batch's CTA retires, and its host<->device copies overlap the previous solve.  Nothing is
+    shared between the handles (own iterates, work areas, queue counter); results are bit-identical to ``ObcaSolver.solve``.
+
+    ``solve_many`` is the host-facing call (host arrays in, host arrays out, one worker thread per handle calling the ordinary
+    ``ObcaSolver.solve`` on its stream); ``run_resident`` the device-resident one (inputs already in HBM)."""
+
+    def __init__(self, prob: CollocationProblem, options: Optional[SolveOptions] = None, device="cuda:0", lib: Optional[ctypes.CDLL] = None, depth: int = 2,
+                 first: Optional["ObcaSolver"] = None):
+        self.solvers = [first if first is not None else ObcaSolver(prob, options, device=device, lib=lib)]
+        self.solvers += [ObcaSolver(prob, options, device=device, lib=lib) for _ in range(depth - 1)]
+        self.device = self.solvers[0].device
+        if self.device.type != "cuda":
+            raise RuntimeError("PipelinedSolver needs a CUDA device")
+        self.streams = [torch.cuda.Stream(self.device) for _ in self.solvers]
+
+    @property
+    def launch_count(self):
+        return sum(s.launch_count for s in self.solvers)
+
+    def set_order(self, predicted_cost=None):
+        for s in self.solvers:
+            s.set_order(predicted_cost)
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def run_resident(self, dev_inputs, steps: int):
+        """``steps`` batches with device-resident inputs (the dict of ``ObcaSolver.upload``), alternating over the handles.  Asynchronous:
+        returns the per-step (status, iters, [obj, cviol, dual_inf, compl_inf, elastic]) device tensors; the caller's current stream
+        waits for all of them."""
+        main = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(main)
+        out = []
+        for k in range(steps):
+            sv, st = self.solvers[k % len(self.solvers)], self.streams[k % len(self.solvers)]
+            with torch.cuda.stream(st):
+                sv.set_inputs(dev_inputs)
+                sv.run()
+                out.append(sv.fetch_stats())
+        for st in self.streams:
+            main.wait_stream(st)
+        return out
+
+    def solve_many(self, guesses, want_duals: bool = True):
+        """Host arrays in, host arrays out, for a list of batches: list of BatchResult in the order of ``guesses``."""
+        import threading
+
+        todo = list(enumerate(guesses))
+        out = [None] * len(todo)
+        lock = threading.Lock()
+        err = []
+
+        def worker(sv, st):
+            try:
+                torch.cuda.set_device(self.device)  # the current device is per thread
+                with torch.cuda.stream(st):
+                    while True:
+                        with lock:
+                            if not todo:
+                                return
+                            k, g = todo.pop(0)
+                        out[k] = sv.solve(g, want_duals=want_duals)
+            except BaseException as e:  # surfaced in the calling thread
+                err.append(e)
+
+        threads = [threading.Thread(target=worker, args=(sv, st)) for sv, st in zip(self.solvers, self.streams)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if err:
+            raise err[0]
+        return out
+
+    def close(self):
+        for s in self.solvers:
+            s.close()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
