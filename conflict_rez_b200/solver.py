@@ -534,11 +534,13 @@ class PipelinedSolver:
 
     def __init__(self, prob: CollocationProblem, options: Optional[SolveOptions] = None, device="cuda:0", lib: Optional[ctypes.CDLL] = None, depth: int = 2,
                  first: Optional["ObcaSolver"] = None):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("PipelinedSolver needs a CUDA device (streams); there is no CPU fallback")
+        if depth < 1:
+            raise ValueError("PipelinedSolver: depth must be >= 1")
         self.solvers = [first if first is not None else ObcaSolver(prob, options, device=device, lib=lib)]
         self.solvers += [ObcaSolver(prob, options, device=device, lib=lib) for _ in range(depth - 1)]
         self.device = self.solvers[0].device
-        if self.device.type != "cuda":
-            raise RuntimeError("PipelinedSolver needs a CUDA device")
         self.streams = [torch.cuda.Stream(self.device) for _ in self.solvers]
 
     @property

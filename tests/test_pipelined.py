@@ -36,3 +36,9 @@ def test_pipelined_batches_equal_plain_solves(cuda_lib):
         assert float(dbl[0][0]) == float(ref.obj[0])
     assert pipe.launch_count >= 9
     pipe.close()
+
+
+def test_pipelined_solver_refuses_cpu_device():
+    prob, _, _ = load_golden("single_vehicle_1")
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        PipelinedSolver(prob, SolveOptions(), device="cpu")
