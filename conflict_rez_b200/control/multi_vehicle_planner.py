@@ -104,5 +104,6 @@ class MultiVehiclePlanner(object):
         """The circle-approximation variant of the joint problem (multi_vehicle_planner.py:111-206, rect2circles.py:13-37) is not
         provided: the reference method cannot run as shipped (``self.agents - {agent}`` on a list raises ``TypeError`` at :150; it also
         omits ``final_heading`` and only constrains the nodes ``k < K``), nothing in the reference calls it, and the OBCA formulation
-        (``solve_final_problem_obca``) is the one every experiment uses.  Stated explicitly instead of failing with ``AttributeError``."""
+        (``solve_final_problem_obca``) is the one every experiment uses.  Stated explicitly instead of failing with ``AttributeError``.
+        The variant's geometry -- the circle cover ``v2c`` / ``v2c_ca`` and the values of its pair rows -- is in ``control/rect2circles.py``."""
         raise NotImplementedError("solve_final_problem_circles: the reference variant is unusable as shipped (SURVEY.md App. B-1); use solve_final_problem_obca")
