@@ -621,7 +621,9 @@ def main():
             "ncu_source": ncu["source"],
             "peak_source": peak_src,
             "note": "algorithmic bytes = 3.456 MB per IPM iteration and instance (one read + one write of the primal-dual iterate, SURVEY.md 8d) "
-            "x iterations of all instances / k_solve time; the kernel is FP64-latency bound, not bandwidth bound (DESIGN.md)",
+            "x iterations of all instances / k_solve time; the kernel is FP64-latency bound, not bandwidth bound (DESIGN.md)"
+            + ("" if args.no_pipeline else "; pipelined steps: the launches of consecutive steps overlap, so the k_solve time per launch is the timed region / steps "
+               "(with --no-pipeline it is the average of CUDA events around each launch: 4592 ms vs 4594 ms per step at batch 4096)"),
             "fp64_convention": {
                 "achieved_tflops": sum_iters * FLOPS_PER_ITER_CONVENTION / t_kernel / 1e12 / world,
                 "peak_tflops": fp64_peak.value,
